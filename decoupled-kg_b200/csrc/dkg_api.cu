@@ -1,0 +1,514 @@
+// C-ABI of libdkg_b200.so (see include/dkg_b200.h) and the orchestration of one forward pass.
+#include <atomic>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <string>
+
+#include "dkg_emax.cuh"
+#include "dkg_kernels.cuh"
+
+namespace dkg {
+
+// ---- error / counters ------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- allocation helpers ----------------------------------------------------------------------
+template <class T>
+static int dev_alloc(T** p, size_t count, bool zero = true) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    return DKG_ENOMEM;
+  }
+  if (zero) {
+    e = cudaMemset(*p, 0, count * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMemset failed: %s", cudaGetErrorString(e));
+      return DKG_ECUDA;
+    }
+  }
+  return DKG_OK;
+}
+template <class T>
+static void dev_free(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+static void free_workspace(Workspace& w) {
+  dev_free(w.X); dev_free(w.kg); dev_free(w.dX); dev_free(w.KX); dev_free(w.T); dev_free(w.var);
+  dev_free(w.sd); dev_free(w.zown); dev_free(w.Xs); dev_free(w.a_new); dev_free(w.kg_terms);
+  dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.surv_cnt); dev_free(w.surv_idx);
+  dev_free(w.hull_cnt); dev_free(w.hull_idx); dev_free(w.hull_p); dev_free(w.hull_q);
+  dev_free(w.amax_is_new); dev_free(w.stats);
+  w.cap_C = w.chunk_C = 0;
+}
+
+static int ensure_workspace(dkg_plan* p, int C) {
+  Workspace& w = p->ws;
+  if (C <= w.cap_C) return DKG_OK;
+  // a (rare) growth: synchronise so nothing in flight still uses the old buffers
+  DKG_CUDA_OK(cudaDeviceSynchronize());
+  free_workspace(w);
+  const int cap = round_up(C, GEMM_BM);
+  const int n_pad = p->obj[p->target].n_pad;
+  // slope-buffer chunk: keep one chunk of slope rows L2 resident between the GEMM that writes it
+  // and the expected-max kernels that read it (126 MB L2 on B200)
+  double chunk_mb = 48.0;
+  if (const char* e = getenv("DKG_CHUNK_MB")) chunk_mb = atof(e);
+  long long rows = (long long)(chunk_mb * 1048576.0 / ((double)p->ldz * sizeof(double)));
+  int chunk = (int)(rows / GEMM_BM) * GEMM_BM;
+  if (chunk < GEMM_BM) chunk = GEMM_BM;
+  if (chunk > cap) chunk = cap;
+  const size_t S = p->S;
+  DKG_TRY(dev_alloc(&w.X, (size_t)cap * p->d));
+  DKG_TRY(dev_alloc(&w.kg, (size_t)cap));
+  DKG_TRY(dev_alloc(&w.dX, (size_t)cap * p->d));
+  DKG_TRY(dev_alloc(&w.KX, (size_t)cap * n_pad));
+  DKG_TRY(dev_alloc(&w.T, (size_t)cap * p->ldk));
+  DKG_TRY(dev_alloc(&w.var, (size_t)cap));
+  DKG_TRY(dev_alloc(&w.sd, (size_t)cap));
+  DKG_TRY(dev_alloc(&w.zown, (size_t)cap));
+  DKG_TRY(dev_alloc(&w.Xs, (size_t)cap * p->d));
+  DKG_TRY(dev_alloc(&w.a_new, (size_t)cap * S));
+  DKG_TRY(dev_alloc(&w.kg_terms, (size_t)cap * S));
+  DKG_TRY(dev_alloc(&w.Z, (size_t)chunk * p->ldz));
+  DKG_TRY(dev_alloc(&w.zst, (size_t)chunk * 2));
+  DKG_TRY(dev_alloc(&w.zarg, (size_t)chunk * 2));
+  DKG_TRY(dev_alloc(&w.surv_cnt, (size_t)chunk * S));
+  DKG_TRY(dev_alloc(&w.surv_idx, (size_t)chunk * S * SURV_CAP, false));
+  DKG_TRY(dev_alloc(&w.hull_cnt, (size_t)cap * S));
+  DKG_TRY(dev_alloc(&w.hull_idx, (size_t)cap * S * HULL_CAP, false));
+  DKG_TRY(dev_alloc(&w.hull_p, (size_t)cap * S * HULL_CAP, false));
+  DKG_TRY(dev_alloc(&w.hull_q, (size_t)cap * S * HULL_CAP, false));
+  DKG_TRY(dev_alloc(&w.amax_is_new, (size_t)cap * S));
+  DKG_TRY(dev_alloc(&w.stats, (size_t)8));
+  w.cap_C = cap;
+  w.chunk_C = chunk;
+  return DKG_OK;
+}
+
+static void destroy_plan(dkg_plan* p) {
+  if (!p) return;
+  cudaDeviceSynchronize();
+  for (int m = 0; m < p->M; ++m) {
+    dev_free(p->obj[m].xs);
+    dev_free(p->obj[m].alpha);
+  }
+  dev_free(p->W); dev_free(p->wt); dev_free(p->xd); dev_free(p->xd_s); dev_free(p->chol);
+  dev_free(p->cholT); dev_free(p->Kinv); dev_free(p->B); dev_free(p->BT); dev_free(p->alpha_all);
+  dev_free(p->mu_disc); dev_free(p->A0); dev_free(p->A0max); dev_free(p->A0arg);
+  free_workspace(p->ws);
+  delete p;
+}
+
+// Cholesky of K_m + noise I with GPyTorch's jitter retries (psd_safe_cholesky: 1e-8 * 10^k,
+// k < 3, in double) [recalled].  Leaves L in `Lbuf` (n x n).
+static int factor_objective(const ObjState& o, int d, double* Lbuf, int* info_dev, double* jitter_out,
+                            cudaStream_t st) {
+  const double jitters[4] = {0.0, 1e-8, 1e-7, 1e-6};
+  for (int k = 0; k < 4; ++k) {
+    DKG_TRY(kmat_train(o, d, jitters[k], Lbuf, st));
+    DKG_TRY(cholesky_inplace(Lbuf, o.n, info_dev, st));
+    int info = 0;
+    DKG_CUDA_OK(cudaMemcpyAsync(&info, info_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DKG_CUDA_OK(cudaStreamSynchronize(st));
+    if (info == 0) {
+      *jitter_out = jitters[k];
+      return DKG_OK;
+    }
+  }
+  set_error("training covariance is not positive definite even with 1e-6 jitter");
+  return DKG_ENOTPD;
+}
+
+static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_disc_dev,
+                      cudaStream_t st) {
+  const int d = p->d, N = p->N, M = p->M, S = p->S, tgt = p->target;
+  // --- per objective: scaled inputs, Cholesky, mean cache ---
+  int n_max = 0, n_sum = 0;
+  for (int m = 0; m < M; ++m) {
+    n_max = n_max > objs[m].n ? n_max : objs[m].n;
+    n_sum += objs[m].n;
+  }
+  double *Lbuf = nullptr, *LTbuf = nullptr;
+  int* info_dev = nullptr;
+  DKG_TRY(dev_alloc(&Lbuf, (size_t)n_max * n_max));
+  DKG_TRY(dev_alloc(&LTbuf, (size_t)n_max * n_max));
+  DKG_TRY(dev_alloc(&info_dev, 1));
+  DKG_TRY(dev_alloc(&p->alpha_all, (size_t)n_sum));
+  DKG_TRY(dev_alloc(&p->mu_disc, (size_t)N * M));
+  DKG_TRY(dev_alloc(&p->xd, (size_t)N * d));
+  DKG_CUDA_OK(cudaMemcpyAsync(p->xd, x_disc_dev, sizeof(double) * N * d, cudaMemcpyDeviceToDevice, st));
+
+  int rc = DKG_OK;
+  int off = 0;
+  for (int m = 0; m < M && rc == DKG_OK; ++m) {
+    ObjState& o = p->obj[m];
+    const dkg_objective& s = objs[m];
+    o.n = s.n;
+    o.n_pad = round_up(s.n, GEMM_BK);
+    o.kernel = s.kernel;
+    o.outputscale = s.outputscale;
+    o.mean_const = s.mean_const;
+    o.noise = s.noise;
+    o.y_mean = s.y_mean;
+    o.y_std = s.y_std;
+    for (int k = 0; k < MAX_D; ++k) o.ls[k] = k < d ? s.lengthscale_host[k] : 1.0;
+    if ((rc = dev_alloc(&o.xs, (size_t)o.n * d)) != DKG_OK) break;
+    if ((rc = dev_alloc(&o.alpha, (size_t)o.n_pad)) != DKG_OK) break;
+    if ((rc = scale_rows(s.train_x_dev, o.n, d, o.ls, o.xs, st)) != DKG_OK) break;
+    double jit = 0.0;
+    if ((rc = factor_objective(o, d, Lbuf, info_dev, &jit, st)) != DKG_OK) break;
+    if (m == tgt) p->jitter = jit;
+    if ((rc = transpose(Lbuf, o.n, o.n, o.n, LTbuf, o.n, st)) != DKG_OK) break;
+    // mean cache: alpha = K^-1 (y - c)
+    if ((rc = residual(s.train_y_dev, o.n, o.mean_const, o.alpha, st)) != DKG_OK) break;
+    if ((rc = cholesky_solve_inplace(Lbuf, LTbuf, o.n, o.alpha, 1, 1, st)) != DKG_OK) break;
+    cudaMemcpyAsync(p->alpha_all + off, o.alpha, sizeof(double) * o.n, cudaMemcpyDeviceToDevice, st);
+    off += o.n;
+    if ((rc = mu_disc(p->xd, N, d, o, p->mu_disc, M, m, st)) != DKG_OK) break;
+    if (m == tgt) {
+      const int n = o.n;
+      p->ldk = round_up(n, GEMM_BN);
+      if ((rc = dev_alloc(&p->chol, (size_t)n * n)) != DKG_OK) break;
+      if ((rc = dev_alloc(&p->cholT, (size_t)n * n)) != DKG_OK) break;
+      cudaMemcpyAsync(p->chol, Lbuf, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(p->cholT, LTbuf, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st);
+      // Kinv = K^-1 (solve against the identity)
+      if ((rc = dev_alloc(&p->Kinv, (size_t)o.n_pad * p->ldk)) != DKG_OK) break;
+      if ((rc = set_identity(p->Kinv, n, p->ldk, st)) != DKG_OK) break;
+      if ((rc = cholesky_solve_inplace(p->chol, p->cholT, n, p->Kinv, n, p->ldk, st)) != DKG_OK) break;
+      // B = K^-1 k(X_train, X_disc)
+      if ((rc = dev_alloc(&p->xd_s, (size_t)p->N_pad * d)) != DKG_OK) break;
+      if ((rc = scale_rows(p->xd, N, d, o.ls, p->xd_s, st)) != DKG_OK) break;
+      if ((rc = dev_alloc(&p->B, (size_t)o.n_pad * p->N_pad)) != DKG_OK) break;
+      if ((rc = kcross(o, p->xd_s, N, d, p->B, p->N_pad, st)) != DKG_OK) break;
+      if ((rc = cholesky_solve_inplace(p->chol, p->cholT, n, p->B, N, p->N_pad, st)) != DKG_OK) break;
+      if ((rc = dev_alloc(&p->BT, (size_t)N * o.n_pad)) != DKG_OK) break;
+      if ((rc = transpose(p->B, o.n_pad, N, p->N_pad, p->BT, o.n_pad, st)) != DKG_OK) break;
+    }
+  }
+  if (rc == DKG_OK) {
+    // scalarised intercept table
+    rc = dev_alloc(&p->W, (size_t)S * M);
+    if (rc == DKG_OK) rc = dev_alloc(&p->wt, (size_t)S);
+    if (rc == DKG_OK) rc = dev_alloc(&p->A0, (size_t)S * p->N_pad);
+    if (rc == DKG_OK) rc = dev_alloc(&p->A0max, (size_t)S);
+    if (rc == DKG_OK) rc = dev_alloc(&p->A0arg, (size_t)S);
+    if (rc == DKG_OK) {
+      double wt_host[MAX_S];
+      for (int j = 0; j < S; ++j) wt_host[j] = p->W_host[j * M + tgt];
+      cudaMemcpyAsync(p->W, p->W_host, sizeof(double) * S * M, cudaMemcpyHostToDevice, st);
+      cudaMemcpyAsync(p->wt, wt_host, sizeof(double) * S, cudaMemcpyHostToDevice, st);
+      cudaStreamSynchronize(st);  // wt_host is a stack buffer
+      rc = build_a0(p->mu_disc, N, M, p->W, S, p->A0, p->N_pad, p->A0max, p->A0arg, st);
+    }
+  }
+  cudaStreamSynchronize(st);
+  cudaError_t e = cudaGetLastError();
+  dev_free(Lbuf);
+  dev_free(LTbuf);
+  dev_free(info_dev);
+  if (rc == DKG_OK && e != cudaSuccess) {
+    set_error("CUDA error while building the plan: %s", cudaGetErrorString(e));
+    rc = DKG_ECUDA;
+  }
+  return rc;
+}
+
+static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st) {
+  if (C == 0) return DKG_OK;
+  DKG_TRY(ensure_workspace(p, C));
+  Workspace& w = p->ws;
+  const ObjState& ot = p->obj[p->target];
+  const int d = p->d, N = p->N, S = p->S, M = p->M;
+  const int C_pad = round_up(C, GEMM_BM);
+  w.last_C = C;
+  DKG_CUDA_OK(cudaMemsetAsync(w.stats, 0, sizeof(long long) * 8, st));
+
+  XprepArgs xa{};
+  xa.X = X; xa.C = C; xa.d = d; xa.M = M; xa.S = S; xa.target = p->target;
+  for (int m = 0; m < M; ++m) {
+    const ObjState& o = p->obj[m];
+    xa.xs[m] = o.xs; xa.alpha[m] = o.alpha; xa.ntr[m] = o.n; xa.kind[m] = o.kernel;
+    xa.outputscale[m] = o.outputscale; xa.mean_const[m] = o.mean_const;
+    xa.y_mean[m] = o.y_mean; xa.y_std[m] = o.y_std;
+    for (int k = 0; k < MAX_D; ++k) xa.ls[m][k] = o.ls[k];
+  }
+  xa.W = p->W; xa.Xs = w.Xs; xa.KX = w.KX; xa.n_pad = ot.n_pad; xa.a_new = w.a_new;
+  DKG_TRY(launch_xprep(xa, st));
+
+  // T = KX @ Kinv, then the predictive variance
+  DKG_TRY(gemm_store(w.KX, ot.n_pad, p->Kinv, p->ldk, C_pad, p->ldk, ot.n_pad, w.T, p->ldk, st));
+  const double ystd2 = ot.y_std * ot.y_std;
+  DKG_TRY(launch_var(w.KX, ot.n_pad, w.T, p->ldk, ot.n, C, ot.kernel, ot.outputscale, ot.noise,
+                     ystd2, w.var, w.sd, w.zown, st));
+
+  for (int c0 = 0; c0 < C; c0 += w.chunk_C) {
+    const int cc = (C - c0) < w.chunk_C ? (C - c0) : w.chunk_C;
+    const int cc_pad = round_up(cc, GEMM_BM);
+    CovEpilogue ep{};
+    ep.xs = w.Xs + (size_t)c0 * d;
+    ep.xd_s = p->xd_s;
+    ep.sd = w.sd + c0;
+    ep.Z = w.Z;
+    ep.ldz = p->ldz; ep.C = cc; ep.N = N; ep.d = d; ep.kind = ot.kernel;
+    ep.outputscale = ot.outputscale; ep.ystd2 = ystd2;
+    DKG_TRY(gemm_cov(w.KX + (size_t)c0 * ot.n_pad, ot.n_pad, p->B, p->N_pad, cc_pad, p->N_pad,
+                     ot.n_pad, ep, st));
+    DKG_TRY(launch_place_own(w.zown + c0, cc, w.Z, p->ldz, N, st));
+
+    LineBatch lb;
+    lb.Z = w.Z; lb.ldz = p->ldz;
+    lb.A = p->A0; lb.a_sc = 0; lb.a_sj = p->N_pad;
+    lb.a_own = w.a_new + (size_t)c0 * S;
+    lb.wt = p->wt;
+    lb.Amax = p->A0max; lb.Aarg = p->A0arg; lb.am_sc = 0;
+    lb.NA = N; lb.NL = N + 1; lb.S = S; lb.C = cc;
+    EmaxScratch sc;
+    sc.zst = w.zst; sc.zarg = w.zarg; sc.surv_cnt = w.surv_cnt; sc.surv_idx = w.surv_idx;
+    sc.stats = w.stats;
+    DKG_CUDA_OK(cudaMemsetAsync(w.surv_cnt, 0, sizeof(int) * (size_t)cc * S, st));
+    DKG_TRY(emax_zstat(lb, sc, nullptr, nullptr, st));
+    DKG_TRY(emax_filter(lb, sc, st));
+    EmaxOut out;
+    out.terms = w.kg_terms + (size_t)c0 * S;
+    out.subtract_max = 1;
+    out.hull_cnt = w.hull_cnt + (size_t)c0 * S;
+    out.hull_idx = w.hull_idx + (size_t)c0 * S * HULL_CAP;
+    out.hull_p = w.hull_p + (size_t)c0 * S * HULL_CAP;
+    out.hull_q = w.hull_q + (size_t)c0 * S * HULL_CAP;
+    out.hull_x = nullptr;
+    out.hull_cap = HULL_CAP;
+    out.amax_is_own = w.amax_is_new + (size_t)c0 * S;
+    out.kg = kg + c0;
+    BackwardArgs bw{};
+    if (dX != nullptr) {
+      bw.dX = dX + (size_t)c0 * d;
+      bw.X = X + (size_t)c0 * d;
+      bw.T = w.T + (size_t)c0 * p->ldk;
+      bw.ldk = p->ldk;
+      bw.BT = p->BT;
+      bw.n_pad = ot.n_pad;
+      bw.xd_s = p->xd_s;
+      bw.var = w.var + c0;
+      bw.sd = w.sd + c0;
+      bw.W = p->W;
+      bw.M = M; bw.d = d; bw.target = p->target;
+      for (int m = 0; m < M; ++m) {
+        const ObjState& o = p->obj[m];
+        bw.xs[m] = o.xs; bw.alpha[m] = o.alpha; bw.ntr[m] = o.n; bw.kind[m] = o.kernel;
+        bw.outputscale[m] = o.outputscale; bw.y_std[m] = o.y_std;
+        for (int k = 0; k < MAX_D; ++k) bw.ls[m][k] = o.ls[k];
+      }
+    }
+    DKG_TRY(emax_hull(lb, sc, out, bw, st));
+  }
+  return DKG_OK;
+}
+
+}  // namespace dkg
+
+using namespace dkg;
+
+extern "C" {
+
+int dkg_abi_version(void) { return DKG_ABI_VERSION; }
+const char* dkg_last_error(void) { return g_err; }
+int64_t dkg_launch_count(void) { return g_launches.load(); }
+void dkg_launch_count_reset(void) { g_launches.store(0); }
+
+int dkg_plan_create(const dkg_objective* objs, int32_t M, int32_t d, const double* x_disc_dev,
+                    int32_t N, const double* weights_host, int32_t S, int32_t target_ix,
+                    uint32_t flags, void* stream, dkg_plan** out_plan) {
+  (void)flags;
+  if (!out_plan) { set_error("out_plan is NULL"); return DKG_EINVAL; }
+  *out_plan = nullptr;
+  if (!objs || !x_disc_dev || !weights_host) { set_error("NULL argument"); return DKG_EINVAL; }
+  if (M < 1 || M > MAX_M) { set_error("M=%d outside [1, %d]", M, MAX_M); return DKG_EINVAL; }
+  if (d < 1 || d > MAX_D) { set_error("d=%d outside [1, %d]", d, MAX_D); return DKG_EINVAL; }
+  if (S < 1 || S > MAX_S) { set_error("S=%d outside [1, %d]", S, MAX_S); return DKG_EINVAL; }
+  if (N < 1) { set_error("the discretisation is empty"); return DKG_EINVAL; }
+  if (target_ix < 0 || target_ix >= M) {
+    set_error("target_ix=%d outside [0, %d)", target_ix, M);
+    return DKG_EINVAL;
+  }
+  for (int m = 0; m < M; ++m) {
+    if (objs[m].n < 1 || !objs[m].train_x_dev || !objs[m].train_y_dev || !objs[m].lengthscale_host) {
+      set_error("objective %d: empty or NULL training data", m);
+      return DKG_EINVAL;
+    }
+    if (objs[m].kernel != DKG_KERNEL_MATERN52 && objs[m].kernel != DKG_KERNEL_RBF) {
+      set_error("objective %d: unsupported kernel id %d", m, objs[m].kernel);
+      return DKG_EINVAL;
+    }
+    if (!(objs[m].noise >= 0.0) || !(objs[m].outputscale > 0.0) || !(objs[m].y_std > 0.0)) {
+      set_error("objective %d: noise/outputscale/y_std out of range", m);
+      return DKG_EINVAL;
+    }
+    for (int k = 0; k < d; ++k)
+      if (!(objs[m].lengthscale_host[k] > 0.0)) {
+        set_error("objective %d: lengthscale[%d] must be positive", m, k);
+        return DKG_EINVAL;
+      }
+  }
+  dkg_plan* p = new (std::nothrow) dkg_plan();
+  if (!p) { set_error("out of host memory"); return DKG_ENOMEM; }
+  p->M = M; p->d = d; p->N = N; p->S = S; p->target = target_ix;
+  p->N_pad = round_up(N, GEMM_BN);
+  p->ldz = round_up(N + 1, 16);
+  cudaGetDevice(&p->device);
+  memcpy(p->W_host, weights_host, sizeof(double) * S * M);
+  int rc = build_plan(p, objs, x_disc_dev, (cudaStream_t)stream);
+  if (rc != DKG_OK) {
+    destroy_plan(p);
+    return rc;
+  }
+  *out_plan = p;
+  return DKG_OK;
+}
+
+void dkg_plan_destroy(dkg_plan* plan) { destroy_plan(plan); }
+
+int dkg_forward_dev(dkg_plan* plan, const double* X_dev, int32_t C, double* kg_dev, double* dX_dev,
+                    void* stream) {
+  if (!plan || (C > 0 && (!X_dev || !kg_dev))) { set_error("NULL argument"); return DKG_EINVAL; }
+  if (C < 0) { set_error("C=%d is negative", C); return DKG_EINVAL; }
+  return forward_impl(plan, X_dev, C, kg_dev, dX_dev, (cudaStream_t)stream);
+}
+
+int dkg_forward_host(dkg_plan* plan, const double* X_host, int32_t C, double* kg_host,
+                     double* dX_host, void* stream) {
+  if (!plan || (C > 0 && (!X_host || !kg_host))) { set_error("NULL argument"); return DKG_EINVAL; }
+  if (C < 0) { set_error("C=%d is negative", C); return DKG_EINVAL; }
+  if (C == 0) return DKG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  DKG_TRY(ensure_workspace(plan, C));
+  Workspace& w = plan->ws;
+  const int d = plan->d;
+  DKG_CUDA_OK(cudaMemcpyAsync(w.X, X_host, sizeof(double) * (size_t)C * d, cudaMemcpyHostToDevice, st));
+  DKG_TRY(forward_impl(plan, w.X, C, w.kg, dX_host ? w.dX : nullptr, st));
+  DKG_CUDA_OK(cudaMemcpyAsync(kg_host, w.kg, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, st));
+  if (dX_host)
+    DKG_CUDA_OK(cudaMemcpyAsync(dX_host, w.dX, sizeof(double) * (size_t)C * d, cudaMemcpyDeviceToHost, st));
+  DKG_CUDA_OK(cudaStreamSynchronize(st));
+  return DKG_OK;
+}
+
+int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev, int32_t P, int32_t L,
+                               double* emax_dev, int32_t* hull_count_dev, int32_t* hull_idx_dev,
+                               double* hull_x_dev, int32_t hull_cap, double* dE_da_dev,
+                               double* dE_db_dev, void* stream) {
+  if (L == 0) {
+    set_error("Expected inputs to specify at least one line. Got intercepts.shape[-1]=0.");
+    return DKG_EEMPTY;
+  }
+  if (P < 0 || L < 0 || hull_cap < 0) { set_error("negative size"); return DKG_EINVAL; }
+  if (P == 0) return DKG_OK;
+  if (!a_dev || !b_dev || !emax_dev) { set_error("NULL argument"); return DKG_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  double *zst = nullptr, *amax = nullptr;
+  int *zarg = nullptr, *aarg = nullptr, *scnt = nullptr, *sidx = nullptr;
+  int rc = DKG_OK;
+  auto A = [&](int r) { if (rc == DKG_OK) rc = r; };
+  A(dev_alloc(&zst, (size_t)P * 2));
+  A(dev_alloc(&zarg, (size_t)P * 2));
+  A(dev_alloc(&amax, (size_t)P));
+  A(dev_alloc(&aarg, (size_t)P));
+  A(dev_alloc(&scnt, (size_t)P));
+  A(dev_alloc(&sidx, (size_t)P * SURV_CAP, false));
+  if (rc == DKG_OK) {
+    LineBatch lb;
+    lb.Z = b_dev; lb.ldz = L;
+    lb.A = a_dev; lb.a_sc = L; lb.a_sj = 0;
+    lb.a_own = nullptr; lb.wt = nullptr;
+    lb.Amax = amax; lb.Aarg = aarg; lb.am_sc = 1;
+    lb.NA = L; lb.NL = L; lb.S = 1; lb.C = P;
+    EmaxScratch sc;
+    sc.zst = zst; sc.zarg = zarg; sc.surv_cnt = scnt; sc.surv_idx = sidx; sc.stats = nullptr;
+    EmaxOut out;
+    out.terms = emax_dev; out.subtract_max = 0;
+    out.hull_cnt = hull_count_dev;
+    out.hull_idx = hull_idx_dev; out.hull_x = hull_x_dev; out.hull_cap = hull_cap;
+    out.dense_da = dE_da_dev; out.dense_db = dE_db_dev;
+    if (dE_da_dev) cudaMemsetAsync(dE_da_dev, 0, sizeof(double) * (size_t)P * L, st);
+    if (dE_db_dev) cudaMemsetAsync(dE_db_dev, 0, sizeof(double) * (size_t)P * L, st);
+    BackwardArgs bw{};
+    A(emax_zstat(lb, sc, amax, aarg, st));
+    A(emax_filter(lb, sc, st));
+    A(emax_hull(lb, sc, out, bw, st));
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == DKG_OK && e != cudaSuccess) {
+    set_error("expected-max kernels failed: %s", cudaGetErrorString(e));
+    rc = DKG_ECUDA;
+  }
+  dev_free(zst); dev_free(zarg); dev_free(amax); dev_free(aarg); dev_free(scnt); dev_free(sidx);
+  return rc;
+}
+
+int64_t dkg_plan_read(dkg_plan* plan, const char* name, double* out_dev, int64_t capacity,
+                      void* stream) {
+  if (!plan || !name) { set_error("NULL argument"); return DKG_EINVAL; }
+  const ObjState& ot = plan->obj[plan->target];
+  const Workspace& w = plan->ws;
+  const double* src = nullptr;
+  int64_t rows = 0, cols = 0, ld = 0;
+  int n_sum = 0;
+  for (int m = 0; m < plan->M; ++m) n_sum += plan->obj[m].n;
+  const std::string nm(name);
+  if (nm == "B") { src = plan->B; rows = ot.n; cols = plan->N; ld = plan->N_pad; }
+  else if (nm == "Kinv") { src = plan->Kinv; rows = ot.n; cols = ot.n; ld = plan->ldk; }
+  else if (nm == "chol") { src = plan->chol; rows = ot.n; cols = ot.n; ld = ot.n; }
+  else if (nm == "alpha") { src = plan->alpha_all; rows = 1; cols = n_sum; ld = n_sum; }
+  else if (nm == "mu_disc") { src = plan->mu_disc; rows = plan->N; cols = plan->M; ld = plan->M; }
+  else if (nm == "A0") { src = plan->A0; rows = plan->S; cols = plan->N; ld = plan->N_pad; }
+  else if (nm == "A0max") { src = plan->A0max; rows = 1; cols = plan->S; ld = plan->S; }
+  else if (nm == "slopes") {
+    if (w.last_C > w.chunk_C) { set_error("slopes are only retained for C <= chunk (%d)", w.chunk_C); return DKG_EINVAL; }
+    src = w.Z; rows = w.last_C; cols = plan->N + 1; ld = plan->ldz;
+  }
+  else if (nm == "a_new") { src = w.a_new; rows = w.last_C; cols = plan->S; ld = plan->S; }
+  else if (nm == "var") { src = w.var; rows = 1; cols = w.last_C; ld = w.last_C; }
+  else if (nm == "kg_terms") { src = w.kg_terms; rows = w.last_C; cols = plan->S; ld = plan->S; }
+  else { set_error("unknown tensor name '%s'", name); return DKG_EINVAL; }
+  const int64_t count = rows * cols;
+  if (out_dev && count > 0) {
+    if (capacity < count) { set_error("capacity %lld < %lld", (long long)capacity, (long long)count); return DKG_EINVAL; }
+    if (!src) { set_error("tensor '%s' not available yet", name); return DKG_EINVAL; }
+    cudaError_t e = cudaMemcpy2DAsync(out_dev, cols * sizeof(double), src, ld * sizeof(double),
+                                      cols * sizeof(double), rows, cudaMemcpyDeviceToDevice,
+                                      (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("copy failed: %s", cudaGetErrorString(e)); return DKG_ECUDA; }
+  }
+  return count;
+}
+
+int dkg_plan_stats(dkg_plan* plan, int64_t* out5_host, void* stream) {
+  if (!plan || !out5_host) { set_error("NULL argument"); return DKG_EINVAL; }
+  long long h[8] = {0};
+  if (plan->ws.stats) {
+    DKG_CUDA_OK(cudaMemcpyAsync(h, plan->ws.stats, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    DKG_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  }
+  out5_host[0] = plan->ws.last_C;
+  for (int k = 1; k < 5; ++k) out5_host[k] = h[k];
+  return DKG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// Expected maximum over fantasy outcomes: E[max_n (a_n + b_n Z)], Z ~ N(0,1), for many
+// independent line sets.  Interfaces between dkg_emax.cu and dkg_api.cu.
+#pragma once
+
+#include "dkg_plan.cuh"
+
+namespace dkg {
+
+// A batch of line sets.  "row" c in [0, C), "scalarisation" j in [0, S): the set (c, j) has
+// NL lines; line n has slope  b = wt[j] * Z[c*ldz + n]  and intercept
+//   n <  NA : A[c*a_sc + j*a_sj + n]
+//   n == NA : a_own[c*S + j]            (only when a_own != nullptr; then NL == NA + 1)
+// In the KG path the intercept table is shared by all candidates (a_sc == 0) and line NA is the
+// candidate's own line (the reference puts it at index 0, discretekg.py:277); the generic
+// entry point (dkg_expected_max_lines_dev) uses S == 1, a_sc == L, wt == nullptr.
+struct LineBatch {
+  const double* Z = nullptr;
+  int ldz = 0;
+  const double* A = nullptr;
+  long long a_sc = 0;
+  int a_sj = 0;
+  const double* a_own = nullptr;
+  const double* wt = nullptr;      // [S] or nullptr (== 1.0)
+  const double* Amax = nullptr;    // max_n<NA A[..]: [S] when am_sc == 0, else [C, S]
+  const int* Aarg = nullptr;
+  long long am_sc = 0;
+  int NA = 0, NL = 0, S = 0, C = 0;
+};
+
+struct EmaxScratch {
+  double* zst = nullptr;    // [C, 2] min / max of the slope row
+  int* zarg = nullptr;      // [C, 2] their first indices
+  int* surv_cnt = nullptr;  // [C, S]
+  int* surv_idx = nullptr;  // [C, S, SURV_CAP]
+  long long* stats = nullptr;
+};
+
+struct EmaxOut {
+  double* terms = nullptr;     // [C, S]: E - max a (subtract_max) or E
+  int subtract_max = 1;
+  int* hull_cnt = nullptr;     // [C, S]           (optional)
+  int* hull_idx = nullptr;     // [C, S, hull_cap] (optional)
+  double* hull_p = nullptr;    // [C, S, hull_cap] dE/da (optional)
+  double* hull_q = nullptr;    // [C, S, hull_cap] dE/db (optional)
+  double* hull_x = nullptr;    // [C, S, hull_cap] intersections (optional)
+  int hull_cap = 0;
+  int* amax_is_own = nullptr;  // [C, S] (optional)
+  double* kg = nullptr;        // [C] mean over scalarisations of terms (optional)
+  double* dense_da = nullptr;  // [C*S, NL] dE/da scattered by line index (optional, pre-zeroed)
+  double* dense_db = nullptr;  // [C*S, NL] dE/db (optional, pre-zeroed)
+};
+
+// Backward of the KG path, fused into the hull kernel's tail (one CTA per candidate).
+struct BackwardArgs {
+  double* dX = nullptr;          // [C, d]; nullptr -> forward only
+  const double* X = nullptr;     // [C, d] raw candidates
+  const double* KX = nullptr;    // (unused by the kernel; kept for debugging)
+  const double* T = nullptr;     // [C, ldk]  Kinv k_i(X_train, x_c)
+  int ldk = 0;
+  const double* BT = nullptr;    // [N, n_pad]
+  int n_pad = 0;
+  const double* xd_s = nullptr;  // [N_pad, d]
+  const double* var = nullptr;   // [C]
+  const double* sd = nullptr;    // [C]
+  const double* W = nullptr;     // [S, M]
+  int M = 0, d = 0, target = 0;
+  // per objective
+  const double* xs[MAX_M];
+  const double* alpha[MAX_M];
+  int ntr[MAX_M];
+  int kind[MAX_M];
+  double outputscale[MAX_M];
+  double y_std[MAX_M];
+  double ls[MAX_M][MAX_D];
+};
+
+int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int* aarg_out,
+               cudaStream_t st);
+int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st);
+int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out,
+              const BackwardArgs& bw, cudaStream_t st);
+
+}  // namespace dkg

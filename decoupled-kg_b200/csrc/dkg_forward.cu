@@ -1,0 +1,107 @@
+// Candidate-side GP conditioning that precedes the big contraction:
+//   xprep : k_m(x_c, X_train_m) for every objective, posterior means mu_m(x_c), the scalarised
+//           intercept of the candidate's own line, and the scaled candidate coordinates
+//           (replaces the per-candidate posterior calls at discretekg.py:275-284 for the row of
+//           xnew itself).
+//   var   : noisy predictive variance  k(x,x) - k_x^T K^-1 k_x + noise  (discretekg.py:302) and
+//           the slope of the candidate's own line  Cov(x, x) / sd  (discretekg.py:313, entry 0).
+#include "dkg_kernels.cuh"
+
+namespace dkg {
+
+
+__global__ void __launch_bounds__(128) xprep_kernel(XprepArgs p) {
+  __shared__ double s_part[4];
+  __shared__ double s_mu[MAX_M];
+  const int c = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int m = 0; m < p.M; ++m) {
+    double xm[MAX_D];
+#pragma unroll
+    for (int k = 0; k < MAX_D; ++k) xm[k] = k < p.d ? p.X[(size_t)c * p.d + k] / p.ls[m][k] : 0.0;
+    if (m == p.target && threadIdx.x < p.d) p.Xs[(size_t)c * p.d + threadIdx.x] = xm[threadIdx.x];
+    double acc = 0.0;
+    for (int t = threadIdx.x; t < p.ntr[m]; t += blockDim.x) {
+      double sq = 0.0;
+#pragma unroll
+      for (int k = 0; k < MAX_D; ++k)
+        if (k < p.d) {
+          double df = xm[k] - p.xs[m][(size_t)t * p.d + k];
+          sq += df * df;
+        }
+      const double kv = stationary_from_sq(p.kind[m], p.outputscale[m], sq);
+      if (m == p.target) p.KX[(size_t)c * p.n_pad + t] = kv;
+      acc += kv * p.alpha[m][t];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = ((s_part[0] + s_part[1]) + (s_part[2] + s_part[3]));
+      s_mu[m] = (p.mean_const[m] + tot) * p.y_std[m] + p.y_mean[m];
+    }
+    __syncthreads();
+  }
+  // intercept of the candidate's own line: sum_m W[j, m] mu_m(x)  (discretekg.py:320, row 0)
+  for (int j = threadIdx.x; j < p.S; j += blockDim.x) {
+    double a = __dmul_rn(p.W[j * p.M + 0], s_mu[0]);
+    for (int m = 1; m < p.M; ++m) a = __dadd_rn(a, __dmul_rn(p.W[j * p.M + m], s_mu[m]));
+    p.a_new[(size_t)c * p.S + j] = a;
+  }
+}
+
+int launch_xprep(const XprepArgs& p, cudaStream_t st) {
+  if (p.C == 0) return DKG_OK;
+  xprep_kernel<<<p.C, 128, 0, st>>>(p);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// one warp per candidate
+__global__ void var_kernel(const double* __restrict__ KX, int n_pad, const double* __restrict__ T,
+                           int ldk, int ntr, int C, int kind, double outputscale, double noise,
+                           double ystd2, double* __restrict__ var, double* __restrict__ sd,
+                           double* __restrict__ zown) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double acc = 0.0;
+  for (int t = lane; t < ntr; t += 32) acc += KX[(size_t)c * n_pad + t] * T[(size_t)c * ldk + t];
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const double kxx = stationary_from_sq(kind, outputscale, 0.0);
+    const double var_lat = kxx - acc;                 // Cov(x, x), noise free   (:301, entry 0)
+    const double v = (var_lat + noise) * ystd2;       // observation_noise=True  (:302)
+    const double s = sqrt(v);
+    var[c] = v;
+    sd[c] = s;
+    zown[c] = (var_lat * ystd2) / s;                  // znew_coefficients[0]    (:313)
+  }
+}
+
+int launch_var(const double* KX, int n_pad, const double* T, int ldk, int ntr, int C, int kind,
+               double outputscale, double noise, double ystd2, double* var, double* sd,
+               double* zown, cudaStream_t st) {
+  if (C == 0) return DKG_OK;
+  const int threads = 256;
+  var_kernel<<<ceil_div(C * 32, threads), threads, 0, st>>>(KX, n_pad, T, ldk, ntr, C, kind,
+                                                            outputscale, noise, ystd2, var, sd, zown);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// Z[r, N] = zown[r] for the rows of one chunk (the candidate's own line lives in column N)
+__global__ void place_own_kernel(const double* __restrict__ zown, int rows, double* __restrict__ Z,
+                                 int ldz, int N) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) Z[(size_t)r * ldz + N] = zown[r];
+}
+
+int launch_place_own(const double* zown, int rows, double* Z, int ldz, int N, cudaStream_t st) {
+  if (rows == 0) return DKG_OK;
+  place_own_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(zown, rows, Z, ldz, N);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+}  // namespace dkg

@@ -1,0 +1,218 @@
+// fp64 tensor-core (DMMA) GEMM for the GP-conditioning contraction.
+//
+//   cov-mode : Z[c, n] = ( k_i(x_c, xd_n) - sum_t KX[c, t] * B[t, n] ) * ystd^2 / sd[c]
+//              i.e. the fantasy-conditioned cross-covariance row of discretekg.py:301 divided by
+//              the predictive standard deviation (discretekg.py:313), for a whole tile of
+//              candidates at once and WITHOUT ever forming the (N+1)^2 covariance.
+//   store-mode: D = A @ B   (used for T = KX @ Kinv, the variance quadratic form)
+//
+// tcgen05 has no f64 kind, so the fp64 tensor path on sm_100a is warp-level
+// mma.sync.m8n8k4.f64 (SASS: DMMA.8x8x4).  Tiles: 128 x 128 x 16, 8 warps (4 x 2), warp tile
+// 32 x 64 (4 x 8 DMMA fragments, 64 fp64 accumulators per thread), 3-stage cp.async pipeline,
+// shared-memory rows padded so that every fragment load is bank-conflict free.
+#include "dkg_kernels.cuh"
+
+namespace dkg {
+
+constexpr int G_THREADS = 256;
+constexpr int G_STAGES = 3;
+constexpr int LDA_S = GEMM_BK + 4;   // 20 doubles: rows land on distinct bank groups
+constexpr int LDB_S = GEMM_BN + 4;   // 132 doubles
+constexpr int A_STAGE = GEMM_BM * LDA_S;
+constexpr int B_STAGE = GEMM_BK * LDB_S;
+constexpr size_t GEMM_SMEM = (size_t)G_STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+
+
+template <bool COV>
+__global__ void __launch_bounds__(G_THREADS, 1)
+dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                 int K, double* __restrict__ D, int ldd, CovEpilogue ep) {
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = smem + G_STAGES * A_STAGE;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int wm = (warp & 3) * 32;
+  const int wn = (warp >> 2) * 64;
+  const int g = lane >> 2;  // fragment row (A, C) / column (B)
+  const int q = lane & 3;   // fragment k index (A, B) / column pair (C)
+
+  const int m_base = blockIdx.y * GEMM_BM;
+  const int n_base = blockIdx.x * GEMM_BN;
+
+  const double* Ag = A + (size_t)m_base * lda;
+  const double* Bg = B + n_base;
+
+  auto load_stage = [&](int stage, int k0) {
+    double* as = As + stage * A_STAGE;
+    double* bs = Bs + stage * B_STAGE;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int c = tid + i * G_THREADS;  // 0..1023
+      int row = c >> 3, ch = c & 7;
+      cp_async16(as + row * LDA_S + ch * 2, Ag + (size_t)row * lda + k0 + ch * 2);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int c = tid + i * G_THREADS;
+      int row = c >> 6, ch = c & 63;
+      cp_async16(bs + row * LDB_S + ch * 2, Bg + (size_t)(k0 + row) * ldb + ch * 2);
+    }
+  };
+
+  double acc[4][8][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int KT = K / GEMM_BK;
+#pragma unroll
+  for (int s = 0; s < G_STAGES - 1; ++s) {
+    if (s < KT) load_stage(s, s * GEMM_BK);
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<G_STAGES - 2>();
+    __syncthreads();
+    {
+      int nk = kt + G_STAGES - 1;
+      if (nk < KT) load_stage(nk % G_STAGES, nk * GEMM_BK);
+      cp_async_commit();
+    }
+    const double* as = As + (kt % G_STAGES) * A_STAGE;
+    const double* bs = Bs + (kt % G_STAGES) * B_STAGE;
+#pragma unroll
+    for (int kk = 0; kk < GEMM_BK / 4; ++kk) {
+      double af[4], bf[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = as[(wm + i * 8 + g) * LDA_S + kk * 4 + q];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bf[j] = bs[(kk * 4 + q) * LDB_S + wn + j * 8 + g];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  if (!COV) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int row = m_base + wm + i * 8 + g;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int col = n_base + wn + j * 8 + q * 2;
+        *reinterpret_cast<double2*>(D + (size_t)row * ldd + col) =
+            make_double2(acc[i][j][0], acc[i][j][1]);
+      }
+    }
+    return;
+  } else {
+    // stage the scaled coordinates of this tile's candidates and discretisation points
+    double* s_xr = smem;                         // [128][d]
+    double* s_xc = smem + GEMM_BM * MAX_D;       // [128][d]
+    double* s_sd = s_xc + GEMM_BN * MAX_D;       // [128]
+    const int d = ep.d;
+    for (int e = tid; e < GEMM_BM * d; e += G_THREADS) {
+      int r = e / d;
+      s_xr[e] = (m_base + r < ep.C) ? ep.xs[(size_t)(m_base + r) * d + (e - r * d)] : 0.0;
+    }
+    for (int e = tid; e < GEMM_BN * d; e += G_THREADS) s_xc[e] = ep.xd_s[(size_t)n_base * d + e];
+    for (int e = tid; e < GEMM_BM; e += G_THREADS)
+      s_sd[e] = (m_base + e < ep.C) ? ep.sd[m_base + e] : 1.0;
+    __syncthreads();
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int lr = wm + i * 8 + g;
+      const int row = m_base + lr;
+      double xr[MAX_D];
+#pragma unroll
+      for (int k = 0; k < MAX_D; ++k) xr[k] = k < d ? s_xr[lr * d + k] : 0.0;
+      const double sdr = s_sd[lr];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int lc = wn + j * 8 + q * 2;
+        const int col = n_base + lc;
+        double sq0 = 0.0, sq1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < MAX_D; ++k)
+          if (k < d) {
+            double d0 = xr[k] - s_xc[lc * d + k];
+            double d1 = xr[k] - s_xc[(lc + 1) * d + k];
+            sq0 += d0 * d0;
+            sq1 += d1 * d1;
+          }
+        double k0 = stationary_from_sq(ep.kind, ep.outputscale, sq0);
+        double k1 = stationary_from_sq(ep.kind, ep.outputscale, sq1);
+        double z0 = ((k0 - acc[i][j][0]) * ep.ystd2) / sdr;
+        double z1 = ((k1 - acc[i][j][1]) * ep.ystd2) / sdr;
+        if (row < ep.C) {
+          double* dst = ep.Z + (size_t)row * ep.ldz + col;
+          if (col + 1 < ep.N) {
+            *reinterpret_cast<double2*>(dst) = make_double2(z0, z1);
+          } else if (col < ep.N) {
+            dst[0] = z0;
+          }
+        }
+      }
+    }
+  }
+}
+
+static int ensure_gemm_attr() {
+  static bool done = false;
+  if (!done) {
+    DKG_CUDA_OK(cudaFuncSetAttribute(dmma_gemm_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    DKG_CUDA_OK(cudaFuncSetAttribute(dmma_gemm_kernel<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    done = true;
+  }
+  return DKG_OK;
+}
+
+// D[M_pad, N_pad] = A[M_pad, K] @ B[K, N_pad]; all dims multiples of the tile sizes.
+int gemm_store(const double* A, int lda, const double* B, int ldb, int M_pad, int N_pad, int K,
+               double* D, int ldd, cudaStream_t st) {
+  DKG_TRY(ensure_gemm_attr());
+  dim3 grid(N_pad / GEMM_BN, M_pad / GEMM_BM);
+  CovEpilogue ep{};
+  dmma_gemm_kernel<false><<<grid, G_THREADS, GEMM_SMEM, st>>>(A, lda, B, ldb, K, D, ldd, ep);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+int gemm_cov(const double* KX, int lda, const double* B, int ldb, int M_pad, int N_pad, int K,
+             const CovEpilogue& ep, cudaStream_t st) {
+  DKG_TRY(ensure_gemm_attr());
+  dim3 grid(N_pad / GEMM_BN, M_pad / GEMM_BM);
+  dmma_gemm_kernel<true><<<grid, G_THREADS, GEMM_SMEM, st>>>(KX, lda, B, ldb, K, nullptr, 0, ep);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+}  // namespace dkg

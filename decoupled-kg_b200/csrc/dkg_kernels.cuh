@@ -1,0 +1,63 @@
+// Host-side launch interfaces shared by the translation units of libdkg_b200.
+#pragma once
+
+#include "dkg_plan.cuh"
+
+namespace dkg {
+
+// ---- dkg_prepare.cu --------------------------------------------------------------------------
+int scale_rows(const double* x, int rows, int d, const double* ls_host, double* out, cudaStream_t st);
+int kmat_train(const ObjState& o, int d, double jitter, double* K, cudaStream_t st);
+int cholesky_inplace(double* A, int n, int* info_dev, cudaStream_t st);
+int transpose(const double* in, int rows, int cols, int ld_in, double* out, int ld_out, cudaStream_t st);
+int cholesky_solve_inplace(const double* L, const double* LT, int n, double* R, int ncols, int ld,
+                           cudaStream_t st);
+int kcross(const ObjState& o, const double* xd_s, int N, int d, double* R, int ld, cudaStream_t st);
+int set_identity(double* A, int n, int ld, cudaStream_t st);
+int residual(const double* y, int n, double c, double* out, cudaStream_t st);
+int mu_disc(const double* xd, int N, int d, const ObjState& o, double* mu, int M, int m, cudaStream_t st);
+int build_a0(const double* mu, int N, int M, const double* W, int S, double* A0, int ld,
+             double* A0max, int* A0arg, cudaStream_t st);
+
+// ---- dkg_gemm.cu -----------------------------------------------------------------------------
+struct CovEpilogue {
+  const double* xs;    // [rows, d] candidates / lengthscale_i
+  const double* xd_s;  // [N_pad, d] discretisation / lengthscale_i
+  const double* sd;    // [rows]     sqrt(noisy predictive variance), un-standardised
+  double* Z;           // [rows, ldz]
+  int ldz;
+  int C;               // valid rows
+  int N;               // valid columns
+  int d;
+  int kind;
+  double outputscale;
+  double ystd2;
+};
+int gemm_store(const double* A, int lda, const double* B, int ldb, int M_pad, int N_pad, int K,
+               double* D, int ldd, cudaStream_t st);
+int gemm_cov(const double* KX, int lda, const double* B, int ldb, int M_pad, int N_pad, int K,
+             const CovEpilogue& ep, cudaStream_t st);
+
+// ---- dkg_forward.cu --------------------------------------------------------------------------
+struct XprepArgs {
+  const double* X;  // [C, d]
+  int C, d, M, S, target;
+  const double* xs[MAX_M];
+  const double* alpha[MAX_M];
+  int ntr[MAX_M];
+  int kind[MAX_M];
+  double outputscale[MAX_M], mean_const[MAX_M], y_mean[MAX_M], y_std[MAX_M];
+  double ls[MAX_M][MAX_D];
+  const double* W;  // [S, M]
+  double* Xs;       // [C, d] candidates / lengthscale_target
+  double* KX;       // [C_pad, n_pad]
+  int n_pad;
+  double* a_new;    // [C, S]
+};
+int launch_xprep(const XprepArgs& p, cudaStream_t st);
+int launch_var(const double* KX, int n_pad, const double* T, int ldk, int ntr, int C, int kind,
+               double outputscale, double noise, double ystd2, double* var, double* sd,
+               double* zown, cudaStream_t st);
+int launch_place_own(const double* zown, int rows, double* Z, int ldz, int N, cudaStream_t st);
+
+}  // namespace dkg

@@ -1,0 +1,80 @@
+// Internal layout of a dkg_plan: the candidate-independent state of one acquisition function
+// plus the per-forward workspace.  See DESIGN.md "Data layout in HBM".
+#pragma once
+
+#include "dkg_common.cuh"
+
+namespace dkg {
+
+constexpr int GEMM_BM = 128;  // candidate rows per GEMM tile
+constexpr int GEMM_BN = 128;  // discretisation columns per GEMM tile
+constexpr int GEMM_BK = 16;   // training points per pipeline stage
+
+struct ObjState {
+  int n = 0;          // training points
+  int n_pad = 0;      // rounded up to GEMM_BK (zero padded)
+  int kernel = 0;
+  double outputscale = 1, mean_const = 0, noise = 0, y_mean = 0, y_std = 1;
+  double ls[MAX_D];
+  double* xs = nullptr;     // [n, d]   train inputs / lengthscale
+  double* alpha = nullptr;  // [n_pad]  mean cache K^-1 (y - c), zero padded
+};
+
+struct Workspace {
+  int cap_C = 0;        // candidate capacity (multiple of GEMM_BM)
+  int chunk_C = 0;      // candidates per slope-buffer chunk (multiple of GEMM_BM)
+  double* X = nullptr;      // [cap_C, d]    staging for host-buffer calls
+  double* kg = nullptr;     // [cap_C]
+  double* dX = nullptr;     // [cap_C, d]
+  double* KX = nullptr;     // [cap_C, n_pad]    k_i(x_c, X_train)   (target objective)
+  double* T = nullptr;      // [cap_C, ldk]      KX @ Kinv
+  double* var = nullptr;    // [cap_C]           noisy predictive variance (un-standardised)
+  double* sd = nullptr;     // [cap_C]           sqrt(var)
+  double* zown = nullptr;   // [cap_C]           slope of the candidate's own line
+  double* Xs = nullptr;     // [cap_C, d]        candidates / lengthscale_i
+  double* a_new = nullptr;  // [cap_C, S]        intercept of the candidate's own line
+  double* kg_terms = nullptr;  // [cap_C, S]
+  double* Z = nullptr;      // [chunk_C, ldz]    slopes cov/sd; column N = candidate's own line
+  double* zst = nullptr;    // [chunk_C, 2]      min / max of the slope row
+  int* zarg = nullptr;      // [chunk_C, 2]      argmin, argmax of the slope row
+  int* surv_cnt = nullptr;  // [chunk_C, S]      chord-filter survivors per (candidate, scal.)
+  int* surv_idx = nullptr;  // [chunk_C, S, SURV_CAP]
+  int* hull_cnt = nullptr;  // [cap_C, S]
+  int* hull_idx = nullptr;  // [cap_C, S, HULL_CAP]
+  double* hull_p = nullptr; // [cap_C, S, HULL_CAP]  dE/da  (Phi differences)
+  double* hull_q = nullptr; // [cap_C, S, HULL_CAP]  dE/db  (-phi differences)
+  int* amax_is_new = nullptr;  // [cap_C, S]  1 if the max intercept is the candidate's own line
+  long long* stats = nullptr;  // [8] device counters
+  int last_C = 0;
+};
+
+constexpr int SURV_CAP = 1024;  // survivors per (candidate, scalarisation) before the slow path
+constexpr int HULL_CAP = 64;    // hull vertices recorded per (candidate, scalarisation)
+
+}  // namespace dkg
+
+struct dkg_plan {
+  int M = 0, d = 0, N = 0, S = 0, target = 0;
+  int N_pad = 0;  // N rounded up to GEMM_BN
+  int ldz = 0;    // row stride of the slope buffer (>= N+1, multiple of 16)
+  int ldk = 0;    // row stride of Kinv / T (n_i rounded up to GEMM_BN)
+  int device = 0;
+  dkg::ObjState obj[dkg::MAX_M];
+  double W_host[dkg::MAX_S * dkg::MAX_M];
+  double* W = nullptr;        // [S, M]
+  double* wt = nullptr;       // [S]  W[:, target]
+  double* xd = nullptr;       // [N, d]      raw discretisation
+  double* xd_s = nullptr;     // [N_pad, d]  discretisation / lengthscale_i (padding rows zero)
+  double* chol = nullptr;     // [n_i, n_i]  lower Cholesky of K_i + noise I
+  double* cholT = nullptr;    // [n_i, n_i]  its transpose (row access in the back substitution)
+  double* Kinv = nullptr;     // [n_pad, ldk]
+  double* B = nullptr;        // [n_pad, N_pad]  K_i^-1 k_i(X_train, X_disc), zero padded
+  double* BT = nullptr;       // [N, n_pad]      transpose, for the backward gather
+  double* alpha_all = nullptr;  // concatenated mean caches (exposed by dkg_plan_read)
+  double* mu_disc = nullptr;  // [N, M]
+  double* A0 = nullptr;       // [S, N_pad]   scalarised intercepts of the discretisation lines
+  double* A0max = nullptr;    // [S]
+  int* A0arg = nullptr;       // [S]
+  double jitter = 0.0;        // Cholesky jitter that was needed (0 normally)
+  dkg::Workspace ws;
+};

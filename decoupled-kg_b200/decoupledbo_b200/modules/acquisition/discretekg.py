@@ -1,0 +1,182 @@
+"""Discrete multi-objective knowledge gradient -- B200-native drop-in.
+
+Mirror of the reference module ``src/decoupledbo/modules/acquisition/discretekg.py``: the same
+class, constructor, ``forward(X)`` t-batch semantics, errors and autograd behaviour, with the
+arithmetic running as hand-written sm_100a CUDA behind the C-ABI of ``libdkg_b200.so``
+(``include/dkg_b200.h``).  There is no CPU fallback: without the library and a CUDA device the
+calls raise.
+
+What changes relative to the reference (by design):
+
+* ``forward`` evaluates ALL rows of the t-batch in one launch sequence instead of a Python loop
+  over rows (``discretekg.py:145``); ``batch_limit``/``init_batch_limit`` of ``optimize_acqf`` can
+  therefore be raised to the number of restarts / raw samples.
+* everything that does not depend on the candidate (training Cholesky, posterior means at the
+  discretisation, the scalarised intercept table, K^-1 k(X_train, X_disc)) is computed ONCE, at
+  first use, and cached on the instance ("plan"); the reference recomputes it per candidate.
+* the (N+1) x (N+1) posterior covariance (``discretekg.py:301``) is never formed: only its first
+  row is computed, as a tensor-core contraction.
+* the backward is a fused closed-form (envelope theorem) kernel, not autograd through the graph.
+"""
+
+from __future__ import annotations
+
+import logging
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from ...botorch_compat import (
+    AcquisitionFunction,
+    BotorchTensorDimensionError,
+    UnsupportedError,
+    draw_sobol_samples,
+    t_batch_mode_transform,
+)
+from ...gp_state import GPModelList, extract_gp_state
+from ... import _native
+
+logger = logging.getLogger(__name__)
+
+
+class _KGFunction(torch.autograd.Function):
+    """kg[c] = KG(X[c]) with the gradient produced by the fused backward kernel."""
+
+    @staticmethod
+    def forward(ctx, X_flat: Tensor, acqf: "DiscreteKnowledgeGradient") -> Tensor:
+        need_grad = X_flat.requires_grad
+        plan = acqf._get_plan()
+        if X_flat.is_cuda:
+            kg, dX = plan.forward_device(X_flat.detach(), need_grad)
+        else:
+            kg, dX = plan.forward_host(X_flat.detach(), need_grad)
+        ctx.has_grad = need_grad
+        if need_grad:
+            ctx.save_for_backward(dX)
+        return kg
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        if not ctx.has_grad:
+            return None, None
+        (dX,) = ctx.saved_tensors
+        return grad_out.unsqueeze(-1) * dX, None
+
+
+class DiscreteKnowledgeGradient(AcquisitionFunction):
+    """
+    Discrete knowledge gradient (reference ``discretekg.py:25-159``).
+
+    MOKG(x, d) = E[ max_x' E[f(x') . w | w, f_d(x') + eps] ] - E[ max_x' E[f(x') . w | w] ]
+    """
+
+    @classmethod
+    def create_with_sobol_sample(
+        cls,
+        model,
+        bounds: Tensor,
+        num_discrete_points: int,
+        scalarisation_weights: Optional[Tensor] = None,
+        target_output_ix: Optional[int] = None,
+    ):
+        """Same contract as reference ``discretekg.py:33-60``: scrambled-Sobol discretisation."""
+        x_discretisation = draw_sobol_samples(bounds, num_discrete_points, q=1)
+        x_discretisation = x_discretisation.squeeze(1)
+        x_discretisation = x_discretisation.to(bounds)
+        return cls(model, x_discretisation, scalarisation_weights, target_output_ix)
+
+    def __init__(
+        self,
+        model,
+        x_discretisation: Tensor,
+        scalarisation_weights: Optional[Tensor] = None,
+        target_output_ix: Optional[int] = None,
+    ):
+        """
+        Args (identical to reference ``discretekg.py:62-90``):
+            model: A fitted ``ModelListGP`` (real BoTorch or duck-typed) or a ``GPModelList``.
+            x_discretisation: ``k x d`` design points approximating the input space.
+            scalarisation_weights: ``nscalar x n_objectives`` linear scalarisation weights
+                (required for multi-output models).
+            target_output_ix: if given, the KG assumes only this output is observed (decoupled).
+        """
+        super().__init__(model=model)
+
+        if x_discretisation.dim() != 2:
+            raise BotorchTensorDimensionError(
+                f"Expected 'x_discretisation' to have two dimensions. "
+                f"Got {x_discretisation.dim()=}."
+            )
+
+        if scalarisation_weights is None:
+            if model.num_outputs != 1:
+                raise UnsupportedError(
+                    "Models with more than one output must specify 'scalarisation_weights'."
+                )
+            else:
+                scalarisation_weights = torch.tensor([[1.0]]).to(x_discretisation)
+
+        if scalarisation_weights.dim() != 2:
+            raise BotorchTensorDimensionError(
+                f"Expected 'scalarisation_weights' to have two dimensions: The first "
+                f"indexing different scalarisations to be averaged over and the second "
+                f"indexing coordinates of the objective space. "
+                f"Got {scalarisation_weights.dim()=}"
+            )
+        if scalarisation_weights.shape[-1] != model.num_outputs:
+            raise BotorchTensorDimensionError(
+                f"Expected the last dimension of 'scalarisation_weights' to have one "
+                f"element per objective. Got {scalarisation_weights.shape[-1]=} != "
+                f"{model.num_outputs}=model.num_outputs."
+            )
+
+        self.x_discretisation = x_discretisation
+        self.scalarisation_weights = scalarisation_weights
+        self.target_output_ix = target_output_ix
+        self._plan = None
+
+    def set_X_pending(self, X_pending: Optional[Tensor] = None) -> None:
+        raise UnsupportedError(f"{type(self).__name__} does not account for X_pending yet.")
+
+    # -- native state -------------------------------------------------------------------------
+    def _get_plan(self) -> "_native.Plan":
+        """Build (once) the candidate-independent GPU state for this acquisition function."""
+        if self._plan is None:
+            if self.target_output_ix is None:
+                raise UnsupportedError(
+                    "The coupled evaluation (target_output_ix=None, reference "
+                    "calculate_discrete_kg, discretekg.py:162-235) is not implemented by the "
+                    "CUDA path yet; pass target_output_ix."
+                )
+            if not hasattr(self.model, "models"):
+                raise UnsupportedError(
+                    f"Input 'model' must be a 'ModelListGP'. Got {type(self.model)=}."
+                )
+            state: GPModelList = extract_gp_state(self.model)
+            self._plan = _native.Plan(
+                state, self.x_discretisation, self.scalarisation_weights, self.target_output_ix
+            )
+        return self._plan
+
+    def invalidate(self) -> None:
+        """Drop the cached GPU state (call after the model's data or hyper-parameters change)."""
+        if self._plan is not None:
+            self._plan.close()
+        self._plan = None
+
+    @t_batch_mode_transform(expected_q=1)
+    def forward(self, X: Tensor) -> Tensor:
+        """``X``: ``(*b) x 1 x d`` -> KG values of shape ``(*b)`` (reference ``:131-159``)."""
+        batch_shape, d = X.shape[:-2], X.shape[-1]
+
+        if d != self.x_discretisation.shape[-1]:
+            raise RuntimeError(
+                f"Expected X to have last dimension matching 'self.x_discretisation'. "
+                f"Got {X.shape[-1]=}, {self.x_discretisation.shape[-1]=}."
+            )
+        X_flat = X.reshape(-1, d)
+        if X_flat.dtype != torch.double:
+            X_flat = X_flat.to(torch.double)
+        kgvals = _KGFunction.apply(X_flat, self)
+        return kgvals.to(X.dtype).reshape(batch_shape)

@@ -1,0 +1,164 @@
+/*
+ * dkg_b200.h -- C-ABI of libdkg_b200.so: the B200 (sm_100a) implementation of the discrete
+ * knowledge-gradient hot path of quasirandom/decoupled-kg.
+ *
+ * Plain C types only (pointers, sizes, doubles); no torch / C++ types cross this boundary.
+ * Reference = /root/reference (paths below are relative to it).  Each entry point names the
+ * reference interface it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative DKG_E* code on failure; the message of the
+ *     last failure on the calling thread is available from dkg_last_error().
+ *   - "dev" pointers are CUDA device pointers on the current device; "host" pointers are ordinary
+ *     host memory.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - all matrices are row-major float64.
+ *   - the library never frees or retains caller buffers; everything it allocates belongs to the
+ *     plan and is released by dkg_plan_destroy().
+ *   - kernels are enqueued on `stream` and the *_dev entry points do not synchronise the host
+ *     (except for a first-use workspace allocation).
+ */
+#ifndef DKG_B200_H
+#define DKG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DKG_API __attribute__((visibility("default")))
+#else
+#define DKG_API
+#endif
+
+#define DKG_ABI_VERSION 1
+
+/* error codes */
+#define DKG_OK 0
+#define DKG_EINVAL (-1)   /* bad argument (shape, NULL, unsupported kernel id, ...)            */
+#define DKG_ECUDA (-2)    /* a CUDA runtime call failed                                        */
+#define DKG_ENOTPD (-3)   /* training covariance not positive definite even with 1e-6 jitter   */
+#define DKG_ENOMEM (-4)
+#define DKG_EEMPTY (-5)   /* zero lines given to the expected-max stage (ValueError upstream)  */
+
+/* stationary kernels of the reference's model factory
+ * (src/decoupledbo/modules/model/factory.py:116-135: ScaleKernel(MaternKernel(nu=2.5)|RBFKernel)) */
+#define DKG_KERNEL_MATERN52 0
+#define DKG_KERNEL_RBF 1
+
+/* One objective of the ModelListGP (factory.py:63-88), in *model* space. */
+typedef struct dkg_objective {
+  const double* train_x_dev; /* [n, d]  unit-cube inputs (factory.py:65)                       */
+  const double* train_y_dev; /* [n]     targets (standardised if an outcome transform is used) */
+  int32_t n;                 /* training points of THIS objective (ragged across objectives,
+                                src/decoupledbo/pipeline/nodes/bo_loop.py:403-405)             */
+  int32_t kernel;            /* DKG_KERNEL_*                                                   */
+  const double* lengthscale_host; /* [d] ARD lengthscales                                      */
+  double outputscale;        /* ScaleKernel.outputscale                                        */
+  double mean_const;         /* ConstantMean.constant                                          */
+  double noise;              /* GaussianLikelihood.noise (variance)                            */
+  double y_mean;             /* Standardize.means (0 if no outcome transform)                  */
+  double y_std;              /* Standardize.stdvs (1 if no outcome transform)                  */
+} dkg_objective;
+
+typedef struct dkg_plan dkg_plan; /* opaque: candidate-independent state of one acquisition fn */
+
+DKG_API int dkg_abi_version(void);
+DKG_API const char* dkg_last_error(void);
+
+/*
+ * dkg_plan_create -- replaces DiscreteKnowledgeGradient.__init__
+ *   (src/decoupledbo/modules/acquisition/discretekg.py:62-123) PLUS everything the reference
+ *   recomputes for every candidate although it does not depend on the candidate: the training
+ *   Cholesky and mean cache, the posterior means at the discretisation, the scalarised intercept
+ *   table, and K^-1 k(X_train, X_disc) (discretekg.py:275-300 via GPyTorch's exact prediction).
+ *
+ *   objs[M]        GP state per objective
+ *   d              input dimension
+ *   x_disc_dev     [N, d] discretisation (discretekg.py:121)
+ *   weights_host   [S, M] scalarisation weights (discretekg.py:122)
+ *   target_ix      objective whose observation is fantasised (discretekg.py:123, decoupled path
+ *                  discretekg.py:238-338); must be in [0, M)
+ *   flags          0, or DKG_PLAN_* bits
+ */
+#define DKG_PLAN_DEFAULT 0u
+DKG_API int dkg_plan_create(const dkg_objective* objs, int32_t M, int32_t d, const double* x_disc_dev,
+                    int32_t N, const double* weights_host, int32_t S, int32_t target_ix,
+                    uint32_t flags, void* stream, dkg_plan** out_plan);
+
+DKG_API void dkg_plan_destroy(dkg_plan* plan);
+
+/*
+ * dkg_forward_dev -- replaces DiscreteKnowledgeGradient.forward (discretekg.py:131-159), i.e. the
+ *   Python loop over candidates calling calculate_discrete_kg_conditioning_on_single_output
+ *   (discretekg.py:238-338), and -- when dX_dev != NULL -- the autograd backward through it
+ *   (driven by botorch gen_candidates_scipy from
+ *   src/decoupledbo/modules/acquisition_optimisation_strategy.py:217-224).
+ *
+ *   X_dev   [C, d] candidates (the t-batch flattened, q == 1)
+ *   kg_dev  [C]    out: KG value per candidate
+ *   dX_dev  [C, d] out (optional): d KG[c] / d X[c, :]
+ */
+DKG_API int dkg_forward_dev(dkg_plan* plan, const double* X_dev, int32_t C, double* kg_dev,
+                    double* dX_dev, void* stream);
+
+/* Same with HOST buffers: H2D copy of X, kernels, D2H copy of kg (and dX), then a stream sync.
+ * This is the call timed as the end-to-end ("e2e") number. */
+DKG_API int dkg_forward_host(dkg_plan* plan, const double* X_host, int32_t C, double* kg_host,
+                     double* dX_host, void* stream);
+
+/*
+ * dkg_expected_max_lines_dev -- replaces, for P independent sets of L lines each,
+ *   calculate_epigraph_indices (discretekg.py:341-412) followed by
+ *   calculate_expected_value_of_piecewise_linear_function (discretekg.py:415-452):
+ *   E[max_n (a[p,n] + b[p,n] Z)], Z ~ N(0,1).
+ *
+ *   a_dev, b_dev   [P, L] intercepts / slopes
+ *   emax_dev       [P]    out: expectation
+ *   hull_count_dev [P]    out (optional): number of lines on the upper envelope
+ *   hull_idx_dev   [P, hull_cap] out (optional): their indices, left to right
+ *   hull_x_dev     [P, hull_cap] out (optional): the hull_count-1 intersections
+ *   dE_da_dev, dE_db_dev [P, L] out (optional): gradient of the expectation (zero off the hull)
+ *   L == 0 -> DKG_EEMPTY (the reference raises ValueError, discretekg.py:466-470)
+ */
+DKG_API int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev, int32_t P, int32_t L,
+                               double* emax_dev, int32_t* hull_count_dev, int32_t* hull_idx_dev,
+                               double* hull_x_dev, int32_t hull_cap, double* dE_da_dev,
+                               double* dE_db_dev, void* stream);
+
+/*
+ * Introspection for parity tests (all copies are device-to-device on `stream`).
+ * name is one of:
+ *   "B"        [n_i, N]   K_i^-1 k_i(X_train, X_disc)            (target objective i)
+ *   "Kinv"     [n_i, n_i] (K_i + noise I)^-1
+ *   "alpha"    [sum n_m]  mean caches K_m^-1 (y_m - c_m), objectives concatenated
+ *   "mu_disc"  [N, M]     posterior means at the discretisation (un-standardised)
+ *   "A0"       [S, N]     scalarised intercept table sum_m W[j,m] mu_m(x_n)
+ *   "A0max"    [S]        its row maxima
+ *   "chol"     [n_i, n_i] lower Cholesky factor of K_i + noise I
+ * After a forward call:
+ *   "slopes"   [C, N+1]   cov_i(x_c, .)/sd_i(x_c); LAST column is the candidate's own line
+ *   "a_new"    [C, S]     scalarised posterior mean at the candidate (intercept of its own line)
+ *   "var"      [C]        noisy predictive variance at the candidate
+ *   "kg_terms" [C, S]     per-scalarisation E[max] - max (discretekg.py:336)
+ * Returns the number of doubles the tensor holds (>= 0) or a negative error; copies
+ * min(count, capacity) doubles when out_dev != NULL.
+ */
+DKG_API int64_t dkg_plan_read(dkg_plan* plan, const char* name, double* out_dev, int64_t capacity,
+                      void* stream);
+
+/* counters: kernels launched by this library since load / since the last reset */
+DKG_API int64_t dkg_launch_count(void);
+DKG_API void dkg_launch_count_reset(void);
+
+/* per-plan statistics of the last forward (host ints): [0] candidates, [1] lines surviving the
+ * chord filter (sum over candidates x scalarisations), [2] (candidate, scalarisation) pairs sent
+ * to the slow exact path, [3] total hull vertices, [4] pairs taking the |slope|<1e-9 shortcut */
+DKG_API int dkg_plan_stats(dkg_plan* plan, int64_t* out5_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DKG_B200_H */

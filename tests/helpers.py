@@ -1,0 +1,37 @@
+"""Shared helpers for the parity tests (oracle <-> CUDA path)."""
+import numpy as np
+import torch
+
+from decoupledbo_b200 import synthetic
+from oracle import gp as ogp
+
+
+def oracle_model(model, distance="gpytorch"):
+    return ogp.OracleModelList(
+        [ogp.OracleObjective(**kw, distance=distance) for kw in synthetic.to_oracle_kwargs(model)]
+    )
+
+
+def rel_err(got, want, floor=0.0):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    return np.abs(got - want) / np.maximum(np.abs(want), floor)
+
+
+def small_problem(d=2, n_train=30, n_disc=64, n_scal=4, n_cand=16, seed=0, noise=(1e-2, 1e-3),
+                  lengthscales=(0.3, 0.6), outputscales=(1.0, 2.5), kernel=0, y_std=(1.0, 1.0),
+                  y_mean=(0.0, 0.0), n_train_per_obj=None):
+    P = synthetic.make_problem(
+        "small", d, n_train, list(lengthscales), list(outputscales), [0.1, 0.0], list(noise),
+        synthetic.sobol(n_disc, d, 100 + seed), n_scal, n_cand, seed_train=200 + seed,
+        seed_cand=300 + seed, seed_w=seed,
+    )
+    for m, o in enumerate(P.model.models):
+        o.kernel = kernel
+        o.y_std = float(y_std[m])
+        o.y_mean = float(y_mean[m])
+        if n_train_per_obj is not None:
+            k = n_train_per_obj[m]
+            o.train_x = o.train_x[:k].clone()
+            o.train_y = o.train_y[:k].clone()
+    return P

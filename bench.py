@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the discrete-KG hot path on B200 (contract in the task).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU implementation
+
+Metric (BASELINE.json): KG evals/s, 1 eval = one (candidate, objective, scalarisation) triple,
+forward + backward.  Workload = BASELINE.json configs[3] ("c4", the configuration the target is
+quoted on: 2-obj d=4 GP, n_train=400, |X_disc|=16384, 16 scalarisations, 4096 candidates), which
+fits one GPU.  A "step" is one pass of DiscreteKnowledgeGradient forward+backward over the batch
+of candidates for BOTH objectives (two acquisition functions, target_output_ix = 0 and 1), as
+DiscreteKgOptimisationSpec.optimize_for_single_objective drives it.  Multi-GPU: weak scaling --
+every rank evaluates its own 4096-candidate shard with replicated GP state and the values (+
+gradients) are all-gathered over NCCL for the argmax, inside the timed step.
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "decoupled-kg_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "kg_evals_per_sec_fwd_bwd"
+UNIT = "KG evals/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2"])
+    ap.add_argument("--candidates", type=int, default=None, help="candidates per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def build_problem(workload: str, n_cand: int, seed_shift: int = 0):
+    from decoupledbo_b200 import synthetic
+
+    if workload == "c4":
+        P = synthetic.problem_c4(n_cand=n_cand)
+    else:
+        P = synthetic.problem_c2(n_cand=n_cand)
+    if seed_shift:
+        P.candidates = synthetic.sobol(n_cand, P.d, 8 + 1000 * seed_shift)
+    return P
+
+
+def workload_config(workload: str, P, n_cand: int, world: int):
+    o = P.model.models[0]
+    return {
+        "workload": f"{workload}: synthetic 2-obj d={P.d} GP, n_train={o.n}, |X_disc|={P.x_disc.shape[0]}, "
+                    f"{P.weights.shape[0]} scalarisations, {n_cand} candidates/GPU, both objectives, fwd+bwd",
+        "candidates_per_gpu": n_cand,
+        "objectives": P.model.num_outputs,
+        "scalarisations": int(P.weights.shape[0]),
+        "x_disc": int(P.x_disc.shape[0]),
+        "n_train": o.n,
+        "d": P.d,
+        "parallelism": f"candidate-sharded x{world}, replicated GP state, one all-gather of values+grads",
+        "l2": "no flush: per-step working set (slope rows 0.5 GB/objective + B, B^T 105 MB) exceeds the 126 MB L2",
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# clocks (sampled DURING the timed region)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ------------------------------------------------------------------------------------------
+# CPU legs (the ONLY places bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------
+def _oracle_model(P):
+    from decoupledbo_b200 import synthetic
+    from oracle import gp as ogp
+
+    return ogp.OracleModelList(
+        [ogp.OracleObjective(**kw) for kw in synthetic.to_oracle_kwargs(P.model)]
+    )
+
+
+def _host_mem_gb():
+    try:
+        import psutil
+
+        return psutil.virtual_memory().available / 2**30
+    except Exception:
+        return 0.0
+
+
+def cpu_reference_step(P, om, cand_ix: int, target: int, dense: bool):
+    """One candidate x one objective x all scalarisations, forward + backward, reference-faithful
+    CPU path (per-candidate evaluation, dense (N+1)^2 posterior covariance when `dense`, Python
+    hull loop per scalarisation).  Returns seconds."""
+    from oracle import discretekg as odk
+
+    x = P.candidates[cand_ix].clone().requires_grad_(True)
+    t0 = time.perf_counter()
+    kg = odk.kg_single_output(om, x, target, P.x_disc, P.weights, dense=dense)
+    kg.backward()
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args, rank: int, world: int):
+    """`--impl reference`: the reference's CPU implementation of the path on the host cores.
+    botorch/gpytorch are not installable in this image, so the reference arm is the oracle port
+    (same per-candidate structure, dense posterior covariance, Python hull loop)."""
+    if rank != 0:
+        return
+    n_cand = args.candidates or (4096 if args.workload == "c4" else 512)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = build_problem(args.workload, max(8, min(n_cand, 64)))
+    om = _oracle_model(P)
+    S = int(P.weights.shape[0])
+    dense = _host_mem_gb() > 48.0 or P.x_disc.shape[0] <= 4096
+    t_first = cpu_reference_step(P, om, 0, 0, dense)
+    warm = args.warmup if t_first < 5.0 else min(args.warmup, 1)
+    for w in range(1, warm):
+        cpu_reference_step(P, om, w % P.candidates.shape[0], w % 2, dense)
+    times = []
+    for k in range(args.steps):
+        times.append(cpu_reference_step(P, om, (k + warm) % P.candidates.shape[0], k % 2, dense))
+    total = sum(times)
+    value = S * args.steps / total
+    sample = (f"each step = 1 candidate x 1 objective x {S} scalarisations of the same workload "
+              f"(fwd+bwd, {'dense (N+1)^2 posterior covariance' if dense else 'row-only posterior'}, "
+              f"Python hull loop); candidates are independent loop iterations (discretekg.py:145) so "
+              f"evals/s extrapolates linearly")
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": warm, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, P, n_cand, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference repo is pure Python on botorch/gpytorch (absent here): oracle port timed",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def measure_dgemm_peak(dev):
+    """cuBLAS DGEMM 8192^3, best of 5 (burst) -- the fp64-tensor roofline denominator;
+    MEASURED_PEAKS.json only carries HBM GB/s and bf16 TF/s."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.double, device=dev)
+    b = torch.randn(n, n, dtype=torch.double, device=dev)
+    for _ in range(2):
+        a @ b
+    best = float("inf")
+    for _ in range(5):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n**3 / best / 1e9  # TFLOP/s
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from decoupledbo_b200 import _native
+    from decoupledbo_b200.distributed import first_argmax
+    from decoupledbo_b200.modules.acquisition.discretekg import DiscreteKnowledgeGradient
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_cand = args.candidates or (4096 if args.workload == "c4" else 512)
+    P = build_problem(args.workload, n_cand, seed_shift=rank)
+    S = int(P.weights.shape[0])
+    M = P.model.num_outputs
+    d = P.d
+    xd = P.x_disc.to(dev)
+    acqs = [DiscreteKnowledgeGradient(P.model, xd, P.weights, target_output_ix=i) for i in range(M)]
+    plans = [a._get_plan() for a in acqs]
+    X_dev = P.candidates.to(dev).contiguous()
+    gather_buf = torch.empty(world * n_cand, 1 + d, dtype=torch.double, device=dev) if world > 1 else None
+
+    def step_device():
+        best = []
+        for plan in plans:
+            kg, dX = plan.forward_device(X_dev, True)
+            if world > 1:
+                send = torch.cat([kg.unsqueeze(1), dX], dim=1)
+                dist.all_gather_into_tensor(gather_buf, send)
+                best.append(gather_buf[:, 0].argmax())
+            else:
+                best.append(kg.argmax())
+        return best
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _native.launch_count_reset()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    launches = _native.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.double, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_step = float(ms_total) / args.steps
+    evals_step = world * n_cand * M * S
+    value = evals_step / (ms_step * 1e-3)
+
+    # ---- end-to-end through the public API with HOST buffers ----
+    e2e = None
+    if not args.no_e2e:
+        X_host = P.candidates.clone().pin_memory()
+
+        def step_host():
+            out = []
+            for acq in acqs:
+                X = X_host.detach().requires_grad_(True)  # fresh leaf over the pinned buffer
+                kg = acq(X.unsqueeze(1))  # public API: (*b) x 1 x d -> (*b)
+                loss = -kg.sum()
+                (g,) = torch.autograd.grad(loss, X)
+                if world > 1:
+                    send = torch.cat([kg.detach().unsqueeze(1), g], dim=1).to(dev)
+                    dist.all_gather_into_tensor(gather_buf, send)
+                    out.append(int(gather_buf[:, 0].argmax()))
+                else:
+                    out.append(int(kg.argmax()))
+            return out
+
+        for _ in range(3):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        barrier()
+        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.double, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e = {
+            "value": evals_step * args.steps / float(t_e2e),
+            "unit": UNIT,
+            "h2d_bytes_per_step": M * n_cand * d * 8,
+            "d2h_bytes_per_step": M * n_cand * (1 + d) * 8,
+            "ms_per_step": 1e3 * float(t_e2e) / args.steps,
+            "api": "DiscreteKnowledgeGradient.forward(X_host) + autograd.grad -> dkg_forward_host",
+        }
+
+    # ---- roofline of the dominant kernel (separate profiled steps, CUDA events per launch) ----
+    roofline = None
+    cpu_baseline = None
+    extra = {}
+    if rank == 0:
+        _native.profile_enable(True)
+        for _ in range(3):
+            for plan in plans:
+                plan.forward_device(X_dev, True)
+        prof = _native.profile_read()
+        _native.profile_enable(False)
+        ms_g, n_g = prof["gemm_cov"]
+        o = P.model.models[0]
+        N = int(P.x_disc.shape[0])
+        # algorithmic flops of the conditioning contraction: 2 * n_train * N per (candidate,
+        # objective) (F = 2 n (N+1) + 2 n^2 + 2 n M; the contraction is the 2 n N term)
+        flops_total = 3.0 * sum(2.0 * m.n * N * n_cand for m in P.model.models)
+        achieved = flops_total / (ms_g * 1e-3) / 1e12
+        peak = measure_dgemm_peak(dev)
+        tot_prof = sum(v[0] for v in prof.values())
+        roofline = {
+            "kernel": "dmma_gemm_kernel<cov> (GP conditioning contraction, fp64 DMMA)",
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak,
+            "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (burst, best of 5); "
+                           "MEASURED_PEAKS.json has no fp64 figure",
+            "flops_per_launch": flops_total / max(n_g, 1),
+            "avg_launch_ms": ms_g / max(n_g, 1),
+            "share_of_step": ms_g / tot_prof if tot_prof > 0 else None,
+            "traffic": None,
+        }
+        extra["kernel_ms_per_step"] = {k: v[0] / 3.0 for k, v in prof.items()}
+        extra["kernel_launches_per_step"] = {k: v[1] // 3 for k, v in prof.items()}
+        whole = 1.03 * sum((2.0 * m.n * (N + 1) + 2.0 * m.n**2 + 2.0 * m.n * M) * n_cand for m in P.model.models)
+        extra["path_roofline"] = {
+            "algorithmic_flops_per_step_per_gpu": whole,
+            "t_min_ms_at_peak": whole / (peak * 1e12) * 1e3,
+            "frac_of_fp64_roofline": (whole / (peak * 1e12) * 1e3) / ms_step,
+        }
+        stats = [p.stats() for p in plans]
+        extra["filter_stats"] = [
+            {"survivors_per_set": s[1] / max(1, n_cand * S), "overflow_sets": s[2],
+             "hull_vertices_per_set": s[3] / max(1, n_cand * S), "shortcut_sets": s[4]} for s in stats]
+
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            om = _oracle_model(P)
+            dense = _host_mem_gb() > 48.0 or N <= 4096
+            t_acc, n_done, k = 0.0, 0, 0
+            while t_acc < 12.0 and k < 64:
+                t_acc += cpu_reference_step(P, om, k // 2, k % 2, dense)
+                n_done += 1
+                k += 1
+            cpu_baseline = {
+                "value": S * n_done / t_acc, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{n_done} (candidate, objective) pairs x {S} scalarisations of the same workload, "
+                          f"fwd+bwd, {'dense (N+1)^2 posterior' if dense else 'row-only posterior'} + Python hull "
+                          f"loop per scalarisation ({t_acc:.1f} s of CPU work)",
+            }
+            # strong CPU baseline: row-only batched posterior (no dense covariance)
+            t_acc2, n2 = 0.0, 0
+            while t_acc2 < 6.0 and n2 < 64:
+                t_acc2 += cpu_reference_step(P, om, n2 // 2, n2 % 2, False)
+                n2 += 1
+            extra["cpu_baseline_row_only"] = {"value": S * n2 / t_acc2, "unit": UNIT, "cores": cores,
+                                              "kind": "port", "sample": f"{n2} pairs, row-only posterior"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.workload, P, n_cand, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

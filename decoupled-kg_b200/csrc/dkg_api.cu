@@ -24,6 +24,22 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// ---- optional per-kernel timing (CUDA events on the launching stream) -------------------------
+static bool g_prof_on = false;
+struct ProfSample { int cat; cudaEvent_t e0, e1; };
+static std::vector<ProfSample> g_prof;
+struct ProfScope {
+  cudaStream_t st; int idx = -1;
+  ProfScope(int cat, cudaStream_t s) : st(s) {
+    if (!g_prof_on) return;
+    ProfSample ps; ps.cat = cat;
+    cudaEventCreate(&ps.e0); cudaEventCreate(&ps.e1);
+    cudaEventRecord(ps.e0, st);
+    g_prof.push_back(ps); idx = (int)g_prof.size() - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(g_prof[idx].e1, st); }
+};
+
 // ---- allocation helpers ----------------------------------------------------------------------
 template <class T>
 static int dev_alloc(T** p, size_t count, bool zero = true) {
@@ -251,13 +267,14 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     for (int k = 0; k < MAX_D; ++k) xa.ls[m][k] = o.ls[k];
   }
   xa.W = p->W; xa.Xs = w.Xs; xa.KX = w.KX; xa.n_pad = ot.n_pad; xa.a_new = w.a_new;
-  DKG_TRY(launch_xprep(xa, st));
+  { ProfScope ps(0, st); DKG_TRY(launch_xprep(xa, st)); }
 
   // T = KX @ Kinv, then the predictive variance
-  DKG_TRY(gemm_store(w.KX, ot.n_pad, p->Kinv, p->ldk, C_pad, p->ldk, ot.n_pad, w.T, p->ldk, st));
+  { ProfScope ps(1, st); DKG_TRY(gemm_store(w.KX, ot.n_pad, p->Kinv, p->ldk, C_pad, p->ldk, ot.n_pad, w.T, p->ldk, st)); }
   const double ystd2 = ot.y_std * ot.y_std;
-  DKG_TRY(launch_var(w.KX, ot.n_pad, w.T, p->ldk, ot.n, C, ot.kernel, ot.outputscale, ot.noise,
-                     ystd2, w.var, w.sd, w.zown, st));
+  { ProfScope ps(2, st);
+    DKG_TRY(launch_var(w.KX, ot.n_pad, w.T, p->ldk, ot.n, C, ot.kernel, ot.outputscale, ot.noise,
+                       ystd2, w.var, w.sd, w.zown, st)); }
 
   for (int c0 = 0; c0 < C; c0 += w.chunk_C) {
     const int cc = (C - c0) < w.chunk_C ? (C - c0) : w.chunk_C;
@@ -269,9 +286,10 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     ep.Z = w.Z;
     ep.ldz = p->ldz; ep.C = cc; ep.N = N; ep.d = d; ep.kind = ot.kernel;
     ep.outputscale = ot.outputscale; ep.ystd2 = ystd2;
-    DKG_TRY(gemm_cov(w.KX + (size_t)c0 * ot.n_pad, ot.n_pad, p->B, p->N_pad, cc_pad, p->N_pad,
-                     ot.n_pad, ep, st));
-    DKG_TRY(launch_place_own(w.zown + c0, cc, w.Z, p->ldz, N, st));
+    { ProfScope ps(3, st);
+      DKG_TRY(gemm_cov(w.KX + (size_t)c0 * ot.n_pad, ot.n_pad, p->B, p->N_pad, cc_pad, p->N_pad,
+                       ot.n_pad, ep, st)); }
+    { ProfScope ps(4, st); DKG_TRY(launch_place_own(w.zown + c0, cc, w.Z, p->ldz, N, st)); }
 
     LineBatch lb;
     lb.Z = w.Z; lb.ldz = p->ldz;
@@ -284,8 +302,8 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     sc.zst = w.zst; sc.zarg = w.zarg; sc.surv_cnt = w.surv_cnt; sc.surv_idx = w.surv_idx;
     sc.stats = w.stats;
     DKG_CUDA_OK(cudaMemsetAsync(w.surv_cnt, 0, sizeof(int) * (size_t)cc * S, st));
-    DKG_TRY(emax_zstat(lb, sc, nullptr, nullptr, st));
-    DKG_TRY(emax_filter(lb, sc, st));
+    { ProfScope ps(5, st); DKG_TRY(emax_zstat(lb, sc, nullptr, nullptr, st)); }
+    { ProfScope ps(6, st); DKG_TRY(emax_filter(lb, sc, st)); }
     EmaxOut out;
     out.terms = w.kg_terms + (size_t)c0 * S;
     out.subtract_max = 1;
@@ -317,7 +335,7 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
         for (int k = 0; k < MAX_D; ++k) bw.ls[m][k] = o.ls[k];
       }
     }
-    DKG_TRY(emax_hull(lb, sc, out, bw, st));
+    { ProfScope ps(7, st); DKG_TRY(emax_hull(lb, sc, out, bw, st)); }
   }
   return DKG_OK;
 }
@@ -497,6 +515,22 @@ int64_t dkg_plan_read(dkg_plan* plan, const char* name, double* out_dev, int64_t
     if (e != cudaSuccess) { set_error("copy failed: %s", cudaGetErrorString(e)); return DKG_ECUDA; }
   }
   return count;
+}
+
+void dkg_profile_enable(int on) { g_prof_on = on != 0; }
+
+int dkg_profile_read(double* ms_host, int64_t* count_host, int32_t ncat) {
+  if (!ms_host || !count_host || ncat < 1) { set_error("bad argument"); return DKG_EINVAL; }
+  DKG_CUDA_OK(cudaDeviceSynchronize());
+  for (int k = 0; k < ncat; ++k) { ms_host[k] = 0.0; count_host[k] = 0; }
+  for (auto& ps : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ps.e0, ps.e1);
+    if (ps.cat < ncat) { ms_host[ps.cat] += ms; count_host[ps.cat] += 1; }
+    cudaEventDestroy(ps.e0); cudaEventDestroy(ps.e1);
+  }
+  g_prof.clear();
+  return DKG_OK;
 }
 
 int dkg_plan_stats(dkg_plan* plan, int64_t* out5_host, void* stream) {

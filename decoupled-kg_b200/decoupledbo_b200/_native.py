@@ -34,7 +34,10 @@ EXPORTED_SYMBOLS = (
     "dkg_launch_count",
     "dkg_launch_count_reset",
     "dkg_plan_stats",
+    "dkg_profile_enable",
+    "dkg_profile_read",
 )
+PROFILE_CATEGORIES = ("xprep", "gemm_T", "var", "gemm_cov", "place_own", "zstat", "filter", "hull")
 
 
 class NativeLibraryError(RuntimeError):
@@ -95,6 +98,10 @@ def load_library() -> ctypes.CDLL:
     lib.dkg_launch_count_reset.restype = None
     lib.dkg_plan_stats.restype = ctypes.c_int
     lib.dkg_plan_stats.argtypes = [c_void_p, POINTER(c_int64), c_void_p]
+    lib.dkg_profile_enable.restype = None
+    lib.dkg_profile_enable.argtypes = [ctypes.c_int]
+    lib.dkg_profile_read.restype = ctypes.c_int
+    lib.dkg_profile_read.argtypes = [POINTER(c_double), POINTER(c_int64), c_int32]
     if lib.dkg_abi_version() != ABI_VERSION:
         raise NativeLibraryError(
             f"ABI mismatch: library {lib.dkg_abi_version()} vs binding {ABI_VERSION}; rebuild."
@@ -137,6 +144,19 @@ def launch_count() -> int:
 
 def launch_count_reset() -> None:
     load_library().dkg_launch_count_reset()
+
+
+def profile_enable(on: bool) -> None:
+    load_library().dkg_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """-> {category: (total_ms, launches)} since the last read (synchronises the device)."""
+    n = len(PROFILE_CATEGORIES)
+    ms = (c_double * n)()
+    cnt = (c_int64 * n)()
+    _check(load_library().dkg_profile_read(ms, cnt, n), "dkg_profile_read")
+    return {name: (float(ms[k]), int(cnt[k])) for k, name in enumerate(PROFILE_CATEGORIES)}
 
 
 class Plan:
@@ -223,13 +243,21 @@ class Plan:
         assert (not X.is_cuda) and X.dtype == torch.double and X.dim() == 2 and X.shape[1] == self.d
         X = X.contiguous()
         C = X.shape[0]
-        kg = out_kg if out_kg is not None else torch.empty(C, dtype=torch.double)
+        # results land in pinned staging buffers owned by the plan (fast D2H), then are copied
+        # into fresh tensors so callers may keep them across calls
+        if getattr(self, "_pin_cap", 0) < C:
+            self._pin_kg = torch.empty(C, dtype=torch.double).pin_memory()
+            self._pin_dX = torch.empty(C, self.d, dtype=torch.double).pin_memory()
+            self._pin_cap = C
+        kg_pin = self._pin_kg[:C]
+        dX_pin = self._pin_dX[:C] if need_grad else None
+        with torch.cuda.device(self.device):
+            rc = load_library().dkg_forward_host(self._handle, _ptr(X), C, _ptr(kg_pin), _ptr(dX_pin), _stream_ptr())
+        _check(rc, "dkg_forward_host")
+        kg = kg_pin.clone() if out_kg is None else out_kg.copy_(kg_pin)
         dX = None
         if need_grad:
-            dX = out_dX if out_dX is not None else torch.empty(C, self.d, dtype=torch.double)
-        with torch.cuda.device(self.device):
-            rc = load_library().dkg_forward_host(self._handle, _ptr(X), C, _ptr(kg), _ptr(dX), _stream_ptr())
-        _check(rc, "dkg_forward_host")
+            dX = dX_pin.clone() if out_dX is None else out_dX.copy_(dX_pin)
         return kg, dX
 
     # -- introspection ---------------------------------------------------------------------

@@ -153,6 +153,15 @@ DKG_API int64_t dkg_plan_read(dkg_plan* plan, const char* name, double* out_dev,
 DKG_API int64_t dkg_launch_count(void);
 DKG_API void dkg_launch_count_reset(void);
 
+/* Optional per-kernel timing for bench.py's roofline line: when enabled, every launch of a
+ * forward is bracketed by CUDA events on the launching stream.  dkg_profile_read synchronises the
+ * device, sums the elapsed milliseconds and launch counts per category and clears the samples.
+ * Categories: 0 xprep, 1 gemm_T (KX @ Kinv), 2 var, 3 gemm_cov (the conditioning contraction),
+ * 4 place_own, 5 zstat, 6 filter, 7 hull (+ fused backward). */
+#define DKG_PROFILE_CATEGORIES 8
+DKG_API void dkg_profile_enable(int on);
+DKG_API int dkg_profile_read(double* ms_host, int64_t* count_host, int32_t ncat);
+
 /* per-plan statistics of the last forward (host ints): [0] candidates, [1] lines surviving the
  * chord filter (sum over candidates x scalarisations), [2] (candidate, scalarisation) pairs sent
  * to the slow exact path, [3] total hull vertices, [4] pairs taking the |slope|<1e-9 shortcut */

@@ -35,3 +35,20 @@ def small_problem(d=2, n_train=30, n_disc=64, n_scal=4, n_cand=16, seed=0, noise
             o.train_x = o.train_x[:k].clone()
             o.train_y = o.train_y[:k].clone()
     return P
+
+
+# problems behind tests/golden/kg_reference_code_golden.npz (oracle/make_golden.py)
+GOLDEN_KG_SPECS = {
+    "matern_d2": dict(d=2, n_train=30, n_disc=64, n_scal=4, n_cand=10, kernel=0, seed=0),
+    "rbf_d3": dict(d=3, n_train=25, n_disc=50, n_scal=3, n_cand=8, kernel=1, seed=1),
+    "std_d2": dict(d=2, n_train=20, n_disc=36, n_scal=5, n_cand=8, kernel=0, seed=2,
+                   y_std=(2.5, 0.5), y_mean=(1.0, -3.0)),
+    "ragged_d2": dict(d=2, n_train=24, n_disc=49, n_scal=2, n_cand=6, kernel=0, seed=3,
+                      n_train_per_obj=(24, 17)),
+}
+
+
+def load_golden(name):
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))

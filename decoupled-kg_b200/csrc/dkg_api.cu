@@ -68,7 +68,7 @@ static void dev_free(T*& p) {
 static void free_workspace(Workspace& w) {
   dev_free(w.X); dev_free(w.kg); dev_free(w.dX); dev_free(w.KX); dev_free(w.T); dev_free(w.var);
   dev_free(w.sd); dev_free(w.zown); dev_free(w.Xs); dev_free(w.a_new); dev_free(w.kg_terms);
-  dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.surv_cnt); dev_free(w.surv_idx);
+  dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } dev_free(w.ovf_sets); dev_free(w.ovf_count);
   dev_free(w.hull_cnt); dev_free(w.hull_idx); dev_free(w.hull_p); dev_free(w.hull_q);
   dev_free(w.amax_is_new); dev_free(w.stats);
   w.cap_C = w.chunk_C = 0;
@@ -82,11 +82,13 @@ static int ensure_workspace(dkg_plan* p, int C) {
   free_workspace(w);
   const int cap = round_up(C, GEMM_BM);
   const int n_pad = p->obj[p->target].n_pad;
-  // slope-buffer chunk: keep one chunk of slope rows L2 resident between the GEMM that writes it
-  // and the expected-max kernels that read it (126 MB L2 on B200)
-  double chunk_mb = 48.0;
+  // Candidates are processed in chunks that bound the scratch memory (slope rows + survivor
+  // lists).  DKG_CHUNK_MB (default 6144) is the budget for both; at c4 shapes it covers all 4096
+  // candidates in one chunk (0.5 GB of slope rows + 1.6 GB of survivor lists).
+  double chunk_mb = 6144.0;
   if (const char* e = getenv("DKG_CHUNK_MB")) chunk_mb = atof(e);
-  long long rows = (long long)(chunk_mb * 1048576.0 / ((double)p->ldz * sizeof(double)));
+  const double per_row = (double)p->ldz * sizeof(double) + (double)p->S * SURV_CAP * sizeof(SurvEntry);
+  long long rows = (long long)(chunk_mb * 1048576.0 / per_row);
   int chunk = (int)(rows / GEMM_BM) * GEMM_BM;
   if (chunk < GEMM_BM) chunk = GEMM_BM;
   if (chunk > cap) chunk = cap;
@@ -106,7 +108,9 @@ static int ensure_workspace(dkg_plan* p, int C) {
   DKG_TRY(dev_alloc(&w.zst, (size_t)chunk * 2));
   DKG_TRY(dev_alloc(&w.zarg, (size_t)chunk * 2));
   DKG_TRY(dev_alloc(&w.surv_cnt, (size_t)chunk * S));
-  DKG_TRY(dev_alloc(&w.surv_idx, (size_t)chunk * S * SURV_CAP, false));
+  { SurvEntry* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * SURV_CAP, false)); w.surv = t; }
+  DKG_TRY(dev_alloc(&w.ovf_sets, (size_t)chunk * S, false));
+  DKG_TRY(dev_alloc(&w.ovf_count, (size_t)1));
   DKG_TRY(dev_alloc(&w.hull_cnt, (size_t)cap * S));
   DKG_TRY(dev_alloc(&w.hull_idx, (size_t)cap * S * HULL_CAP, false));
   DKG_TRY(dev_alloc(&w.hull_p, (size_t)cap * S * HULL_CAP, false));
@@ -299,9 +303,11 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     lb.Amax = p->A0max; lb.Aarg = p->A0arg; lb.am_sc = 0;
     lb.NA = N; lb.NL = N + 1; lb.S = S; lb.C = cc;
     EmaxScratch sc;
-    sc.zst = w.zst; sc.zarg = w.zarg; sc.surv_cnt = w.surv_cnt; sc.surv_idx = w.surv_idx;
+    sc.zst = w.zst; sc.zarg = w.zarg; sc.surv_cnt = w.surv_cnt; sc.surv = (SurvEntry*)w.surv;
+    sc.ovf_sets = w.ovf_sets; sc.ovf_count = w.ovf_count;
     sc.stats = w.stats;
     DKG_CUDA_OK(cudaMemsetAsync(w.surv_cnt, 0, sizeof(int) * (size_t)cc * S, st));
+    DKG_CUDA_OK(cudaMemsetAsync(w.ovf_count, 0, sizeof(int), st));
     { ProfScope ps(5, st); DKG_TRY(emax_zstat(lb, sc, nullptr, nullptr, st)); }
     { ProfScope ps(6, st); DKG_TRY(emax_filter(lb, sc, st)); }
     EmaxOut out;
@@ -335,7 +341,9 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
         for (int k = 0; k < MAX_D; ++k) bw.ls[m][k] = o.ls[k];
       }
     }
-    { ProfScope ps(7, st); DKG_TRY(emax_hull(lb, sc, out, bw, st)); }
+    { ProfScope ps(7, st); DKG_TRY(emax_hull(lb, sc, out, st)); }
+    { ProfScope ps(8, st); DKG_TRY(emax_overflow(lb, sc, out, st)); }
+    { ProfScope ps(9, st); DKG_TRY(emax_finalize(lb, out, bw, st)); }
   }
   return DKG_OK;
 }
@@ -441,7 +449,8 @@ int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev, int32_t
   if (!a_dev || !b_dev || !emax_dev) { set_error("NULL argument"); return DKG_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
   double *zst = nullptr, *amax = nullptr;
-  int *zarg = nullptr, *aarg = nullptr, *scnt = nullptr, *sidx = nullptr;
+  int *zarg = nullptr, *aarg = nullptr, *scnt = nullptr, *oset = nullptr, *ocnt = nullptr;
+  SurvEntry* surv = nullptr;
   int rc = DKG_OK;
   auto A = [&](int r) { if (rc == DKG_OK) rc = r; };
   A(dev_alloc(&zst, (size_t)P * 2));
@@ -449,7 +458,9 @@ int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev, int32_t
   A(dev_alloc(&amax, (size_t)P));
   A(dev_alloc(&aarg, (size_t)P));
   A(dev_alloc(&scnt, (size_t)P));
-  A(dev_alloc(&sidx, (size_t)P * SURV_CAP, false));
+  A(dev_alloc(&surv, (size_t)P * SURV_CAP, false));
+  A(dev_alloc(&oset, (size_t)P, false));
+  A(dev_alloc(&ocnt, (size_t)1));
   if (rc == DKG_OK) {
     LineBatch lb;
     lb.Z = b_dev; lb.ldz = L;
@@ -458,7 +469,8 @@ int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev, int32_t
     lb.Amax = amax; lb.Aarg = aarg; lb.am_sc = 1;
     lb.NA = L; lb.NL = L; lb.S = 1; lb.C = P;
     EmaxScratch sc;
-    sc.zst = zst; sc.zarg = zarg; sc.surv_cnt = scnt; sc.surv_idx = sidx; sc.stats = nullptr;
+    sc.zst = zst; sc.zarg = zarg; sc.surv_cnt = scnt; sc.surv = surv;
+    sc.ovf_sets = oset; sc.ovf_count = ocnt; sc.stats = nullptr;
     EmaxOut out;
     out.terms = emax_dev; out.subtract_max = 0;
     out.hull_cnt = hull_count_dev;
@@ -466,17 +478,18 @@ int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev, int32_t
     out.dense_da = dE_da_dev; out.dense_db = dE_db_dev;
     if (dE_da_dev) cudaMemsetAsync(dE_da_dev, 0, sizeof(double) * (size_t)P * L, st);
     if (dE_db_dev) cudaMemsetAsync(dE_db_dev, 0, sizeof(double) * (size_t)P * L, st);
-    BackwardArgs bw{};
     A(emax_zstat(lb, sc, amax, aarg, st));
     A(emax_filter(lb, sc, st));
-    A(emax_hull(lb, sc, out, bw, st));
+    A(emax_hull(lb, sc, out, st));
+    A(emax_overflow(lb, sc, out, st));
   }
   cudaError_t e = cudaStreamSynchronize(st);
   if (rc == DKG_OK && e != cudaSuccess) {
     set_error("expected-max kernels failed: %s", cudaGetErrorString(e));
     rc = DKG_ECUDA;
   }
-  dev_free(zst); dev_free(zarg); dev_free(amax); dev_free(aarg); dev_free(scnt); dev_free(sidx);
+  dev_free(zst); dev_free(zarg); dev_free(amax); dev_free(aarg); dev_free(scnt); dev_free(surv);
+  dev_free(oset); dev_free(ocnt);
   return rc;
 }
 
@@ -542,6 +555,7 @@ int dkg_plan_stats(dkg_plan* plan, int64_t* out5_host, void* stream) {
   }
   out5_host[0] = plan->ws.last_C;
   for (int k = 1; k < 5; ++k) out5_host[k] = h[k];
+  out5_host[2] = h[2];
   return DKG_OK;
 }
 

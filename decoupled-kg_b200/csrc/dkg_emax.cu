@@ -2,26 +2,35 @@
 // [candidates x scalarisations] line sets of |X_disc|+1 lines each, plus the fused backward.
 //
 // The reference finds each upper envelope with a Python Jarvis march over ALL lines.  Here:
-//   1. zstat  : min / max slope of each candidate's slope row (shared by all scalarisations,
-//               because slopes are w_j * z with one z row per candidate, discretekg.py:321).
-//   2. filter : one streaming, coalesced pass over the slope rows and the (L2-resident)
-//               intercept table.  A line whose dual point (slope, intercept) lies on or below the
-//               chain P -> T -> Q (P/Q = extreme-slope lines, T = max-intercept line; all three
-//               are lines of the set) is inside the convex hull of the set, hence can never be a
-//               strict vertex of the upper envelope and is dropped.  On GP-shaped inputs this
-//               leaves ~1% of the lines.
-//   3. hull   : one warp per (candidate, scalarisation) runs the reference's march EXACTLY
-//               (same ordering rule, same strict-slope filter, same division, same tie-breaks)
-//               on the survivors, accumulates the closed-form expectation segment by segment
-//               and records dE/da, dE/db for the backward.
-//   4. backward (same kernel, CTA per candidate): envelope-theorem gradient, sparse over the
-//               recorded hull vertices.
+//   1. zstat   : min / max slope of each candidate's slope row (shared by all scalarisations,
+//                because slopes are w_j * z with one z row per candidate, discretekg.py:321).
+//   2. filter  : one streaming, coalesced pass over the slope rows and the (L2-resident)
+//                intercept table.  A line whose dual point (slope, intercept) lies on or below
+//                the chain P -> T -> Q (P/Q = extreme-slope lines, T = max-intercept line; all
+//                three are lines of the set) is inside the convex hull of the set, hence can
+//                never be a strict vertex of the upper envelope and is dropped.  On GP-shaped
+//                inputs this leaves ~1% of the lines; survivors are appended (intercept, slope,
+//                index) to a per-set list.
+//   3. hull    : one warp per (candidate, scalarisation).  Long lists get one QuickHull-style
+//                refinement (farthest survivor above each chord becomes a new chain vertex, the
+//                list is re-filtered); then the warp runs the reference's march EXACTLY (same
+//                ordering rule, strict-slope filter, division and tie-breaks) on what is left,
+//                accumulating the closed-form expectation segment by segment and recording
+//                dE/da, dE/db for the backward.
+//   4. overflow: sets whose list overflowed (or stayed long) are queued and handled by a
+//                cooperative CTA-per-set kernel: iterative chain refinement over ALL lines, then
+//                the same warp march; if even that keeps too many lines (e.g. every line is a
+//                hull vertex) a block-wide exact march over all lines finishes the job.
+//   5. finalize: kg[c] = mean_j (E_j - max_n a_jn) and the envelope-theorem backward, sparse
+//                over the recorded hull vertices (one CTA per candidate).
 #include "dkg_emax.cuh"
 
 namespace dkg {
 
 constexpr int E_THREADS = 256;
 constexpr double SHORTCUT_TOL = 1e-9;  // discretekg.py:363
+constexpr int STAGE_CAP = 128;         // lines a warp marches over from registers
+constexpr double EPS128 = 2.84217094304040074e-14;  // 128 * 2^-52
 
 // ------------------------------------------------------------------------------------------
 // block-wide (value, index) reductions with first-index tie-breaking
@@ -112,49 +121,71 @@ int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int
 }
 
 // ------------------------------------------------------------------------------------------
-// chord filter
+// per-set facts shared by all stages
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double line_intercept(const LineBatch& lb, int c, int j, int n) {
   return n < lb.NA ? lb.A[(size_t)c * lb.a_sc + (size_t)j * lb.a_sj + n]
                    : lb.a_own[(size_t)c * lb.S + j];
 }
 
+struct SetInfo {
+  double w;       // slope weight of this scalarisation
+  double amax;    // max_n a_n  (torch.max(intercepts), discretekg.py:336)
+  int iT;         // a line attaining it (the candidate's own line wins ties: reference index 0)
+  int own_is_max;
+  int iP, iQ;     // first indices of the min / max raw slope coordinate
+  double zmin, zmax;
+  bool shortcut;  // all |slopes| < 1e-9 (discretekg.py:363)
+};
+
+__device__ __forceinline__ SetInfo set_info(const LineBatch& lb, const EmaxScratch& sc, int c, int j) {
+  SetInfo s;
+  s.w = lb.wt ? lb.wt[j] : 1.0;
+  s.zmin = sc.zst[c * 2 + 0];
+  s.zmax = sc.zst[c * 2 + 1];
+  s.iP = sc.zarg[c * 2 + 0];
+  s.iQ = sc.zarg[c * 2 + 1];
+  s.amax = lb.Amax[(size_t)c * lb.am_sc + j];
+  s.iT = lb.Aarg[(size_t)c * lb.am_sc + j];
+  s.own_is_max = 0;
+  if (lb.a_own != nullptr) {
+    const double ao = lb.a_own[(size_t)c * lb.S + j];
+    if (ao >= s.amax) { s.amax = ao; s.iT = lb.NA; s.own_is_max = 1; }
+  }
+  s.shortcut = fabs(__dmul_rn(s.w, s.zmin)) < SHORTCUT_TOL && fabs(__dmul_rn(s.w, s.zmax)) < SHORTCUT_TOL;
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// chord filter (streaming)
+// ------------------------------------------------------------------------------------------
 // Chain parameters for set (c, j): a line (z, a) survives iff
 //   a > min(par.x + par.y * z, par.z + par.w * z)
 // (left chord P->T and right chord T->Q in the dual plane; the chain is concave because T has
-// the maximum intercept).  A small slack keeps everything within rounding of the chain.
+// the maximum intercept).  A slack of 128 eps of every magnitude entering c + m*z keeps all
+// lines within rounding of the chain: extra survivors cost time, never accuracy.
 __device__ double4 chain_params(const LineBatch& lb, const EmaxScratch& sc, int c, int j) {
   const double inf = INFINITY;
-  const double w = lb.wt ? lb.wt[j] : 1.0;
-  const double zmin = sc.zst[c * 2 + 0], zmax = sc.zst[c * 2 + 1];
-  if (fabs(__dmul_rn(w, zmin)) < SHORTCUT_TOL && fabs(__dmul_rn(w, zmax)) < SHORTCUT_TOL)
-    return make_double4(inf, 0.0, inf, 0.0);  // reference shortcut: the hull is argmax a only
-  const double sgn = w < 0.0 ? -1.0 : 1.0;   // effective slope coordinate z' = sgn * z
-  const int iP = sgn > 0 ? sc.zarg[c * 2 + 0] : sc.zarg[c * 2 + 1];
-  const int iQ = sgn > 0 ? sc.zarg[c * 2 + 1] : sc.zarg[c * 2 + 0];
-  const double zP = sgn > 0 ? zmin : -zmax;
-  const double zQ = sgn > 0 ? zmax : -zmin;
-  double aT = lb.Amax[(size_t)c * lb.am_sc + j];
-  int iT = lb.Aarg[(size_t)c * lb.am_sc + j];
-  if (lb.a_own != nullptr) {
-    double ao = lb.a_own[(size_t)c * lb.S + j];
-    if (ao > aT) { aT = ao; iT = lb.NA; }
-  }
-  const double zT = sgn * lb.Z[(size_t)c * lb.ldz + iT];
+  const SetInfo s = set_info(lb, sc, c, j);
+  if (s.shortcut) return make_double4(inf, 0.0, inf, 0.0);
+  const double sgn = s.w < 0.0 ? -1.0 : 1.0;  // effective slope coordinate z' = sgn * z
+  const int iP = sgn > 0 ? s.iP : s.iQ;
+  const int iQ = sgn > 0 ? s.iQ : s.iP;
+  const double zP = sgn > 0 ? s.zmin : -s.zmax;
+  const double zQ = sgn > 0 ? s.zmax : -s.zmin;
+  const double aT = s.amax;
+  const double zT = sgn * lb.Z[(size_t)c * lb.ldz + s.iT];
   const double aP = line_intercept(lb, c, j, iP);
   const double aQ = line_intercept(lb, c, j, iQ);
-  // slack = 128 eps of every magnitude that enters  c + m * z  (keeps all lines that are within
-  // rounding of the chain; extra survivors only cost time, never accuracy)
-  const double eps128 = 2.84217094304040074e-14;
   double c1 = inf, m1 = 0.0, c2 = inf, m2 = 0.0;
   if (zT > zP) {
     m1 = (aT - aP) / (zT - zP);
-    const double slack = eps128 * (fabs(aT) + fabs(aP) + fabs(m1) * fmax(fabs(zP), fabs(zT)));
+    const double slack = EPS128 * (fabs(aT) + fabs(aP) + fabs(m1) * fmax(fabs(zP), fabs(zT)));
     c1 = aP - m1 * zP - slack;
   }
   if (zQ > zT) {
     m2 = (aQ - aT) / (zQ - zT);
-    const double slack = eps128 * (fabs(aT) + fabs(aQ) + fabs(m2) * fmax(fabs(zQ), fabs(zT)));
+    const double slack = EPS128 * (fabs(aT) + fabs(aQ) + fabs(m2) * fmax(fabs(zQ), fabs(zT)));
     c2 = aT - m2 * zT - slack;
   }
   return make_double4(c1, m1 * sgn, c2, m2 * sgn);
@@ -195,7 +226,11 @@ filter_kernel(LineBatch lb, EmaxScratch sc, int slice_len) {
         if (a > thr) {
           const size_t set = (size_t)(c0 + g) * S + j;
           int pos = atomicAdd(&sc.surv_cnt[set], 1);
-          if (pos < SURV_CAP) sc.surv_idx[set * SURV_CAP + pos] = n;
+          if (pos < SURV_CAP) {
+            SurvEntry e;
+            e.a = a; e.z = z[g]; e.idx = n; e.pad = 0;
+            sc.surv[set * SURV_CAP + pos] = e;
+          }
         }
       }
     }
@@ -220,13 +255,19 @@ int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
-// exact warp-level march (restates discretekg.py:370-410 on the surviving lines)
+// exact march (restates discretekg.py:370-410 on whatever lines `fetch` exposes)
 // ------------------------------------------------------------------------------------------
 struct Line {
   double a, b;
-  int idx;  // internal index (own line == NA)
+  int idx;  // internal index (own line == NA); -1 = empty
   int ref;  // position in the reference's ordering of the inputs (own line first)
 };
+
+__device__ __forceinline__ Line empty_line() {
+  Line L;
+  L.a = 0.0; L.b = 0.0; L.idx = -1; L.ref = 0x7fffffff;
+  return L;
+}
 
 // ordering of the reference's sorted array: slope ascending, then intercept descending; among
 // identical lines the input position decides (the reference's first sort is not stable there).
@@ -236,114 +277,128 @@ __device__ __forceinline__ bool sorted_before(const Line& p, const Line& q) {
   return p.ref < q.ref;
 }
 
-struct SetView {
-  const LineBatch* lb;
-  const int* surv;  // survivor list of this set (or nullptr when marching over all lines)
-  int cnt;          // survivors used
-  int seeds[4];
-  int nseed;
-  int total;        // number of lines visible to the march
-  int c, j;
-  double w;
-};
+__device__ __forceinline__ int ref_index(const LineBatch& lb, int idx) {
+  return (lb.a_own != nullptr) ? (idx == lb.NA ? 0 : idx + 1) : idx;
+}
 
-__device__ __forceinline__ Line fetch_line(const SetView& v, int k) {
-  const LineBatch& lb = *v.lb;
-  int idx;
-  if (v.surv == nullptr) idx = k;
-  else idx = k < v.cnt ? v.surv[k] : v.seeds[k - v.cnt];
+__device__ __forceinline__ Line make_line(const LineBatch& lb, double w, double a, double z, int idx) {
   Line L;
+  L.a = a;
+  L.b = __dmul_rn(w, z);  // slopes = weights[..., i] * znew_coefficients (:321)
   L.idx = idx;
-  L.ref = (lb.a_own != nullptr) ? (idx == lb.NA ? 0 : idx + 1) : idx;
-  L.b = __dmul_rn(v.w, lb.Z[(size_t)v.c * lb.ldz + idx]);  // slopes = w_ji * znew (:321)
-  L.a = line_intercept(lb, v.c, v.j, idx);
+  L.ref = ref_index(lb, idx);
   return L;
 }
 
-constexpr int LANE_LINES = 4;  // lines cached in registers per lane (128 per warp)
+__device__ __forceinline__ Line gather_line(const LineBatch& lb, int c, int j, double w, int idx) {
+  return make_line(lb, w, line_intercept(lb, c, j, idx), lb.Z[(size_t)c * lb.ldz + idx], idx);
+}
 
-// One warp.  Returns E[max]; writes hull records through `rec` callbacks in lane 0.
+__device__ __forceinline__ Line shfl_line(const Line& L, int o) {
+  Line r;
+  r.a = __shfl_xor_sync(0xffffffffu, L.a, o);
+  r.b = __shfl_xor_sync(0xffffffffu, L.b, o);
+  r.idx = __shfl_xor_sync(0xffffffffu, L.idx, o);
+  r.ref = __shfl_xor_sync(0xffffffffu, L.ref, o);
+  return r;
+}
+
+// candidate for the next hull vertex: line + its intersection with the current line
+struct Next {
+  Line L;
+  double x;
+};
+__device__ __forceinline__ void consider_next(Next& best, const Line& cur, const Line& L) {
+  if (L.idx >= 0 && L.b > cur.b) {  // strictly different slope (:388); sorted => larger
+    const double x = -(cur.a - L.a) / (cur.b - L.b);  // (:395)
+    if (best.L.idx < 0 || x < best.x || (x == best.x && sorted_before(L, best.L))) {
+      best.L = L;
+      best.x = x;
+    }
+  }
+}
+__device__ __forceinline__ void merge_next(Next& best, const Next& o) {
+  if (o.L.idx >= 0 &&
+      (best.L.idx < 0 || o.x < best.x || (o.x == best.x && sorted_before(o.L, best.L))))
+    best = o;
+}
+
+// per-set output sink
+struct Recorder {
+  const EmaxOut* out;
+  size_t set;
+  int NL;
+  __device__ void operator()(int k, const Line& L, double p, double q, double x, bool last) const {
+    const EmaxOut& o = *out;
+    if (k < o.hull_cap) {
+      const size_t r = set * (size_t)o.hull_cap + k;
+      if (o.hull_idx) o.hull_idx[r] = L.idx;
+      if (o.hull_p) o.hull_p[r] = p;
+      if (o.hull_q) o.hull_q[r] = q;
+      if (o.hull_x && !last) o.hull_x[r] = x;
+    }
+    if (o.dense_da) o.dense_da[set * (size_t)NL + L.idx] = p;
+    if (o.dense_db) o.dense_db[set * (size_t)NL + L.idx] = q;
+  }
+};
+
 struct HullResult {
   double E;
   int h;
 };
 
-template <class Rec>
-__device__ HullResult warp_march(const SetView& v, Rec rec) {
+// One warp marches over `total` lines exposed by fetch(k); the first 32*LANE_LINES are cached
+// in registers.  Accumulates sum_k a_k dPhi_k - b_k dphi_k (:449-451) in hull order.
+constexpr int LANE_LINES = STAGE_CAP / 32;
+
+template <class Fetch>
+__device__ HullResult warp_march(int total, Fetch fetch, const Recorder& rec) {
   const int lane = threadIdx.x & 31;
   Line cache[LANE_LINES];
 #pragma unroll
   for (int r = 0; r < LANE_LINES; ++r) {
-    int k = lane + 32 * r;
-    if (k < v.total) cache[r] = fetch_line(v, k);
-    else { cache[r].a = 0; cache[r].b = 0; cache[r].idx = -1; cache[r].ref = 0x7fffffff; }
+    const int k = lane + 32 * r;
+    cache[r] = (k < total) ? fetch(k) : empty_line();
   }
-
   // first line of the sorted order: minimum slope, maximum intercept among ties (:371-374)
-  Line cur;
-  cur.idx = -1; cur.a = 0; cur.b = 0; cur.ref = 0x7fffffff;
-  {
+  Line cur = empty_line();
 #pragma unroll
-    for (int r = 0; r < LANE_LINES; ++r)
-      if (cache[r].idx >= 0 && (cur.idx < 0 || sorted_before(cache[r], cur))) cur = cache[r];
-    for (int k = lane + 32 * LANE_LINES; k < v.total; k += 32) {
-      Line L = fetch_line(v, k);
-      if (cur.idx < 0 || sorted_before(L, cur)) cur = L;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      Line oth;
-      oth.a = __shfl_xor_sync(0xffffffffu, cur.a, o);
-      oth.b = __shfl_xor_sync(0xffffffffu, cur.b, o);
-      oth.idx = __shfl_xor_sync(0xffffffffu, cur.idx, o);
-      oth.ref = __shfl_xor_sync(0xffffffffu, cur.ref, o);
-      if (oth.idx >= 0 && (cur.idx < 0 || sorted_before(oth, cur))) cur = oth;
-    }
+  for (int r = 0; r < LANE_LINES; ++r)
+    if (cache[r].idx >= 0 && (cur.idx < 0 || sorted_before(cache[r], cur))) cur = cache[r];
+  for (int k = lane + 32 * LANE_LINES; k < total; k += 32) {
+    const Line L = fetch(k);
+    if (cur.idx < 0 || sorted_before(L, cur)) cur = L;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const Line oth = shfl_line(cur, o);
+    if (oth.idx >= 0 && (cur.idx < 0 || sorted_before(oth, cur))) cur = oth;
   }
 
   double E = 0.0, prev_cdf = 0.0, prev_pdf = 0.0;
   int h = 0;
   while (true) {
-    // next vertex: among lines with a strictly different (i.e. larger) slope, the one whose
-    // intersection with the current line comes first (:388-396); ties -> earliest in sorted order
-    Line best;
-    best.idx = -1; best.a = 0; best.b = 0; best.ref = 0x7fffffff;
-    double bx = INFINITY;
-    auto consider = [&](const Line& L) {
-      if (L.b > cur.b) {
-        double x = -(cur.a - L.a) / (cur.b - L.b);
-        if (best.idx < 0 || x < bx || (x == bx && sorted_before(L, best))) {
-          best = L;
-          bx = x;
-        }
-      }
-    };
+    Next best;
+    best.L = empty_line();
+    best.x = INFINITY;
 #pragma unroll
-    for (int r = 0; r < LANE_LINES; ++r)
-      if (cache[r].idx >= 0) consider(cache[r]);
-    for (int k = lane + 32 * LANE_LINES; k < v.total; k += 32) consider(fetch_line(v, k));
+    for (int r = 0; r < LANE_LINES; ++r) consider_next(best, cur, cache[r]);
+    for (int k = lane + 32 * LANE_LINES; k < total; k += 32) consider_next(best, cur, fetch(k));
     for (int o = 16; o > 0; o >>= 1) {
-      Line oth;
-      oth.a = __shfl_xor_sync(0xffffffffu, best.a, o);
-      oth.b = __shfl_xor_sync(0xffffffffu, best.b, o);
-      oth.idx = __shfl_xor_sync(0xffffffffu, best.idx, o);
-      oth.ref = __shfl_xor_sync(0xffffffffu, best.ref, o);
-      double ox = __shfl_xor_sync(0xffffffffu, bx, o);
-      if (oth.idx >= 0 && (best.idx < 0 || ox < bx || (ox == bx && sorted_before(oth, best)))) {
-        best = oth;
-        bx = ox;
-      }
+      Next oth;
+      oth.L = shfl_line(best.L, o);
+      oth.x = __shfl_xor_sync(0xffffffffu, best.x, o);
+      merge_next(best, oth);
     }
-    const bool last = best.idx < 0;
-    const double cdf = last ? 1.0 : std_normal_cdf(bx);
-    const double pdf = last ? 0.0 : std_normal_pdf(bx);
+    const bool last = best.L.idx < 0;
+    const double cdf = last ? 1.0 : std_normal_cdf(best.x);
+    const double pdf = last ? 0.0 : std_normal_pdf(best.x);
     const double dP = cdf - prev_cdf;
     const double dp = pdf - prev_pdf;
-    // intercepts * (cdf[1:] - cdf[:-1]) - slopes * (pdf[1:] - pdf[:-1])   (:449-451)
     E += __dsub_rn(__dmul_rn(cur.a, dP), __dmul_rn(cur.b, dp));
-    if (lane == 0) rec(h, cur, dP, -dp, bx, last);
+    if (lane == 0) rec(h, cur, dP, -dp, best.x, last);
     ++h;
     if (last) break;
-    cur = best;
+    cur = best.L;
     prev_cdf = cdf;
     prev_pdf = pdf;
   }
@@ -353,104 +408,486 @@ __device__ HullResult warp_march(const SetView& v, Rec rec) {
   return res;
 }
 
+__device__ __forceinline__ void finish_set(const LineBatch& lb, const EmaxOut& out, size_t set,
+                                           const SetInfo& s, double E, int h) {
+  if (out.hull_cnt) out.hull_cnt[set] = h;
+  out.terms[set] = out.subtract_max ? (E - s.amax) : E;  // kg[j] = E - max(intercepts) (:336)
+}
+
+// chord through two dual points; excess(L) > 0 <=> L lies above the chord
+struct Chord {
+  double b0, a0, m, slack;
+  __device__ void set(const Line& l, const Line& r) {
+    b0 = l.b;
+    a0 = l.a;
+    m = (r.a - l.a) / (r.b - l.b);
+    slack = EPS128 * (fabs(l.a) + fabs(r.a) + fabs(m) * fmax(fabs(l.b), fabs(r.b)));
+  }
+  __device__ double excess(const Line& L) const { return L.a - fma(m, L.b - b0, a0); }
+};
+
+__device__ __forceinline__ bool higher_slope(const Line& p, const Line& q) {  // p better as "Q"
+  if (p.b != q.b) return p.b > q.b;
+  if (p.a != q.a) return p.a > q.a;
+  return p.ref < q.ref;
+}
+__device__ __forceinline__ bool higher_intercept(const Line& p, const Line& q) {
+  if (p.a != q.a) return p.a > q.a;
+  return p.ref < q.ref;
+}
+
 // ------------------------------------------------------------------------------------------
-// hull + expectation + (optional) backward: one CTA per candidate row
+// hull kernel: one warp per set
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(E_THREADS)
-hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out, BackwardArgs bw) {
+hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
+  __shared__ double s_a[E_THREADS / 32][STAGE_CAP];
+  __shared__ double s_b[E_THREADS / 32][STAGE_CAP];
+  __shared__ int s_i[E_THREADS / 32][STAGE_CAP];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long set_ll = (long long)blockIdx.x * (E_THREADS / 32) + warp;
+  if (set_ll >= (long long)lb.C * lb.S) return;
+  const size_t set = (size_t)set_ll;
+  const int c = (int)(set / lb.S);
+  const int j = (int)(set - (size_t)c * lb.S);
+  const SetInfo s = set_info(lb, sc, c, j);
+  if (out.amax_is_own != nullptr && lane == 0) out.amax_is_own[set] = s.own_is_max;
+  Recorder rec{&out, set, lb.NL};
+
+  if (s.shortcut) {
+    // all |slopes| < 1e-9: the reference returns argmax(intercepts) only (:363-367)
+    if (lane == 0) {
+      Line L;
+      L.idx = s.iT; L.a = s.amax; L.b = 0; L.ref = 0;
+      rec(0, L, 1.0, 0.0, 0.0, true);
+      finish_set(lb, out, set, s, s.amax, 1);
+      if (sc.stats) atomicAdd((unsigned long long*)&sc.stats[4], 1ull);
+    }
+    return;
+  }
+  const int cnt = sc.surv_cnt[set];
+  if (cnt > SURV_CAP) {  // list truncated: the cooperative kernel redoes this set from all lines
+    if (lane == 0) sc.ovf_sets[atomicAdd(sc.ovf_count, 1)] = (int)set;
+    return;
+  }
+  const SurvEntry* list = sc.surv + set * SURV_CAP;
+  int seeds[4];
+  int nseed = 0;
+  seeds[nseed++] = s.iP;
+  seeds[nseed++] = s.iQ;
+  seeds[nseed++] = lb.Aarg[(size_t)c * lb.am_sc + j];
+  if (lb.a_own != nullptr) seeds[nseed++] = lb.NA;
+  const int total = cnt + nseed;
+  const double w = s.w;
+  auto fetch_global = [&](int k) -> Line {
+    if (k < cnt) {
+      const SurvEntry e = list[k];
+      return make_line(lb, w, e.a, e.z, e.idx);
+    }
+    return gather_line(lb, c, j, w, seeds[k - cnt]);
+  };
+
+  HullResult r;
+  if (total <= STAGE_CAP) {
+    r = warp_march(total, fetch_global, rec);
+  } else {
+    // ---- one QuickHull-style refinement over the list, compacting into shared memory ----
+    // chain in the (b, a) plane: P (min slope), T (max intercept), Q (max slope)
+    Line P = empty_line(), Q = empty_line(), T = empty_line();
+    for (int k = lane; k < total; k += 32) {
+      const Line L = fetch_global(k);
+      if (P.idx < 0 || sorted_before(L, P)) P = L;
+      if (Q.idx < 0 || higher_slope(L, Q)) Q = L;
+      if (T.idx < 0 || higher_intercept(L, T)) T = L;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      Line oth = shfl_line(P, o);
+      if (oth.idx >= 0 && (P.idx < 0 || sorted_before(oth, P))) P = oth;
+      oth = shfl_line(Q, o);
+      if (oth.idx >= 0 && (Q.idx < 0 || higher_slope(oth, Q))) Q = oth;
+      oth = shfl_line(T, o);
+      if (oth.idx >= 0 && (T.idx < 0 || higher_intercept(oth, T))) T = oth;
+    }
+    const bool hasL = T.b > P.b, hasR = Q.b > T.b;
+    Chord cl, cr;
+    cl.b0 = cl.a0 = cl.m = cl.slack = 0.0;
+    cr = cl;
+    if (hasL) cl.set(P, T);
+    if (hasR) cr.set(T, Q);
+    // farthest line above each chord
+    Line F1 = empty_line(), F2 = empty_line();
+    double e1 = 0.0, e2 = 0.0;
+    for (int k = lane; k < total; k += 32) {
+      const Line L = fetch_global(k);
+      if (hasL && L.b > P.b && L.b < T.b) {
+        const double e = cl.excess(L);
+        if (e > e1 || (e == e1 && e > 0.0 && L.ref < F1.ref)) { e1 = e; F1 = L; }
+      } else if (hasR && L.b > T.b && L.b < Q.b) {
+        const double e = cr.excess(L);
+        if (e > e2 || (e == e2 && e > 0.0 && L.ref < F2.ref)) { e2 = e; F2 = L; }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      Line oth = shfl_line(F1, o);
+      double oe = __shfl_xor_sync(0xffffffffu, e1, o);
+      if (oth.idx >= 0 && (oe > e1 || (oe == e1 && oth.ref < F1.ref))) { e1 = oe; F1 = oth; }
+      oth = shfl_line(F2, o);
+      oe = __shfl_xor_sync(0xffffffffu, e2, o);
+      if (oth.idx >= 0 && (oe > e2 || (oe == e2 && oth.ref < F2.ref))) { e2 = oe; F2 = oth; }
+    }
+    // refined chain: P [F1] T [F2] Q  -> up to 4 chords
+    Chord ch[4];
+    double lo_b[4], hi_b[4];
+    int nch = 0;
+    if (hasL) {
+      if (F1.idx >= 0) {
+        ch[nch].set(P, F1); lo_b[nch] = P.b; hi_b[nch] = F1.b; ++nch;
+        ch[nch].set(F1, T); lo_b[nch] = F1.b; hi_b[nch] = T.b; ++nch;
+      } else {
+        ch[nch] = cl; lo_b[nch] = P.b; hi_b[nch] = T.b; ++nch;
+      }
+    }
+    if (hasR) {
+      if (F2.idx >= 0) {
+        ch[nch].set(T, F2); lo_b[nch] = T.b; hi_b[nch] = F2.b; ++nch;
+        ch[nch].set(F2, Q); lo_b[nch] = F2.b; hi_b[nch] = Q.b; ++nch;
+      } else {
+        ch[nch] = cr; lo_b[nch] = T.b; hi_b[nch] = Q.b; ++nch;
+      }
+    }
+    // the staged list starts with the chain vertices themselves
+    int staged = 0;
+    if (lane == 0) {
+      const Line vs[5] = {P, F1, T, F2, Q};
+      for (int v = 0; v < 5; ++v)
+        if (vs[v].idx >= 0) {
+          s_a[warp][staged] = vs[v].a; s_b[warp][staged] = vs[v].b; s_i[warp][staged] = vs[v].idx;
+          ++staged;
+        }
+    }
+    staged = __shfl_sync(0xffffffffu, staged, 0);
+    bool too_many = false;
+    for (int k0 = 0; k0 < total; k0 += 32) {
+      const int k = k0 + lane;
+      bool keep = false;
+      Line L = empty_line();
+      if (k < total) {
+        L = fetch_global(k);
+        // a line strictly inside a chord's slope range survives only above that chord; a line
+        // at a vertex slope is kept (the march discards it if it is dominated)
+        keep = true;
+        for (int q = 0; q < nch; ++q)
+          if (L.b > lo_b[q] && L.b < hi_b[q]) keep = ch[q].excess(L) > -ch[q].slack;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      const int pos = staged + __popc(m & ((1u << lane) - 1u));
+      const int add = __popc(m);
+      if (staged + add > STAGE_CAP) { too_many = true; break; }
+      if (keep) { s_a[warp][pos] = L.a; s_b[warp][pos] = L.b; s_i[warp][pos] = L.idx; }
+      staged += add;
+    }
+    if (too_many) {
+      if (lane == 0) sc.ovf_sets[atomicAdd(sc.ovf_count, 1)] = (int)set;
+      return;
+    }
+    __syncwarp();
+    auto fetch_smem = [&](int k) -> Line {
+      Line L;
+      L.a = s_a[warp][k]; L.b = s_b[warp][k]; L.idx = s_i[warp][k];
+      L.ref = ref_index(lb, L.idx);
+      return L;
+    };
+    r = warp_march(staged, fetch_smem, rec);
+  }
+  if (lane == 0) {
+    finish_set(lb, out, set, s, r.E, r.h);
+    if (sc.stats) {
+      atomicAdd((unsigned long long*)&sc.stats[1], (unsigned long long)cnt);
+      atomicAdd((unsigned long long*)&sc.stats[3], (unsigned long long)r.h);
+    }
+  }
+}
+
+int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cudaStream_t st) {
+  const long long sets = (long long)lb.C * lb.S;
+  if (sets == 0) return DKG_OK;
+  const int wpb = E_THREADS / 32;
+  hull_kernel<<<(unsigned)((sets + wpb - 1) / wpb), E_THREADS, 0, st>>>(lb, sc, out);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// overflow kernel: one CTA per queued set, all lines, always terminates
+// ------------------------------------------------------------------------------------------
+constexpr int OVF_MAXV = 130;  // chain vertices
+constexpr int OVF_ROUNDS = 6;
+
+__device__ __forceinline__ unsigned long long pack_excess(double e, int n) {
+  // e > 0: float bits are order preserving; only used to CHOOSE a seed -- any line above the
+  // chord is a valid chain vertex, so the float rounding is harmless
+  return ((unsigned long long)__float_as_uint((float)e) << 32) | (unsigned)n;
+}
+
+// index k of the chain vertex with the largest v_b[k] <= b  (requires b >= v_b[0])
+__device__ __forceinline__ int chain_locate(const double* v_b, int nv, double b) {
+  int lo = 0, hi = nv - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (v_b[mid] <= b) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(E_THREADS)
+overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
+  __shared__ double v_b[OVF_MAXV], v_a[OVF_MAXV], v_m[OVF_MAXV], v_slack[OVF_MAXV];
+  __shared__ int v_idx[OVF_MAXV];
+  __shared__ unsigned long long v_best[OVF_MAXV];
+  __shared__ double n_b[OVF_MAXV], n_a[OVF_MAXV];
+  __shared__ int n_i[OVF_MAXV];
+  __shared__ int s_nv, s_grew, s_count, s_list;
+  __shared__ double r_a[E_THREADS / 32], r_b[E_THREADS / 32], r_x[E_THREADS / 32];
+  __shared__ int r_idx[E_THREADS / 32], r_ref[E_THREADS / 32];
+  __shared__ double c_a, c_b;
+  __shared__ int c_idx, c_ref;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nq = *sc.ovf_count;
+  for (int qi = blockIdx.x; qi < nq; qi += gridDim.x) {
+    const size_t set = (size_t)sc.ovf_sets[qi];
+    const int c = (int)(set / lb.S);
+    const int j = (int)(set - (size_t)c * lb.S);
+    const SetInfo s = set_info(lb, sc, c, j);
+    const double w = s.w;
+    Recorder rec{&out, set, lb.NL};
+    __syncthreads();  // the previous queue entry is done with the shared state
+
+    // ---- initial chain P, T, Q in the (b, a) plane (strictly increasing b) ----
+    if (tid == 0) {
+      const bool pos = !(w < 0.0);
+      const Line P = gather_line(lb, c, j, w, pos ? s.iP : s.iQ);
+      const Line Q = gather_line(lb, c, j, w, pos ? s.iQ : s.iP);
+      const Line T = gather_line(lb, c, j, w, s.iT);
+      int nv = 0;
+      const Line vs[3] = {P, T, Q};
+      for (int v = 0; v < 3; ++v) {
+        const Line& L = vs[v];
+        if (nv > 0 && L.b <= v_b[nv - 1]) {  // same slope: keep the higher line
+          if (L.b == v_b[nv - 1] && L.a > v_a[nv - 1]) { v_a[nv - 1] = L.a; v_idx[nv - 1] = L.idx; }
+          continue;
+        }
+        v_b[nv] = L.b; v_a[nv] = L.a; v_idx[nv] = L.idx; ++nv;
+      }
+      s_nv = nv;
+    }
+    __syncthreads();
+
+    bool small_enough = false;
+    for (int round = 0; round <= OVF_ROUNDS; ++round) {
+      const int nv = s_nv;
+      for (int k = tid; k < nv; k += blockDim.x) {  // chord k joins vertices k and k+1
+        v_best[k] = 0ull;
+        if (k + 1 < nv) {
+          const double m = (v_a[k + 1] - v_a[k]) / (v_b[k + 1] - v_b[k]);
+          v_m[k] = m;
+          v_slack[k] = EPS128 * (fabs(v_a[k]) + fabs(v_a[k + 1]) + fabs(m) * fmax(fabs(v_b[k]), fabs(v_b[k + 1])));
+        }
+      }
+      if (tid == 0) s_count = 0;
+      __syncthreads();
+      int local = 0;
+      for (int n = tid; n < lb.NL; n += blockDim.x) {
+        const Line L = gather_line(lb, c, j, w, n);
+        if (L.b < v_b[0]) { ++local; continue; }  // outside the chain: cannot be dropped
+        const int k = chain_locate(v_b, nv, L.b);
+        if (L.b == v_b[k]) {  // same slope as a vertex: survives only if it is higher
+          if (L.a > v_a[k]) ++local;
+          continue;
+        }
+        if (k == nv - 1) { ++local; continue; }  // beyond the last vertex: keep
+        const double e = L.a - fma(v_m[k], L.b - v_b[k], v_a[k]);
+        if (e > -v_slack[k]) {
+          ++local;
+          if (e > 0.0) atomicMax(&v_best[k], pack_excess(e, n));
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+      if (lane == 0 && local) atomicAdd(&s_count, local);
+      __syncthreads();
+      if (s_count <= SURV_CAP) { small_enough = true; break; }
+      if (round == OVF_ROUNDS) break;
+      // insert the farthest line of every chord (thread 0; chains are tiny)
+      if (tid == 0) {
+        int m = 0;
+        bool grew = false;
+        for (int k = 0; k < nv; ++k) {
+          n_b[m] = v_b[k]; n_a[m] = v_a[k]; n_i[m] = v_idx[k]; ++m;
+          if (k + 1 < nv && v_best[k] != 0ull && m + (nv - k) < OVF_MAXV) {
+            const int n = (int)(v_best[k] & 0xffffffffull);
+            const Line L = gather_line(lb, c, j, w, n);
+            if (L.b > v_b[k] && L.b < v_b[k + 1]) {
+              n_b[m] = L.b; n_a[m] = L.a; n_i[m] = L.idx; ++m;
+              grew = true;
+            }
+          }
+        }
+        for (int k = 0; k < m; ++k) { v_b[k] = n_b[k]; v_a[k] = n_a[k]; v_idx[k] = n_i[k]; }
+        s_nv = m;
+        s_grew = grew ? 1 : 0;
+      }
+      __syncthreads();
+      if (!s_grew) break;  // no chord has anything above it, yet too many lines: all near-hull
+    }
+
+    if (small_enough) {
+      // ---- compact the survivors into this set's (global) list and let warp 0 march ----
+      const int nv = s_nv;
+      SurvEntry* list = sc.surv + set * SURV_CAP;
+      if (tid == 0) s_list = 0;
+      __syncthreads();
+      for (int n = tid; n < lb.NL; n += blockDim.x) {
+        const Line L = gather_line(lb, c, j, w, n);
+        bool keep;
+        if (L.b < v_b[0]) keep = true;
+        else {
+          const int k = chain_locate(v_b, nv, L.b);
+          if (L.b == v_b[k]) keep = L.a > v_a[k];
+          else if (k == nv - 1) keep = true;
+          else keep = (L.a - fma(v_m[k], L.b - v_b[k], v_a[k])) > -v_slack[k];
+        }
+        if (keep) {
+          const int pos = atomicAdd(&s_list, 1);
+          if (pos < SURV_CAP) {
+            SurvEntry e;
+            e.a = L.a; e.z = lb.Z[(size_t)c * lb.ldz + n]; e.idx = n; e.pad = 0;
+            list[pos] = e;
+          }
+        }
+      }
+      __syncthreads();
+      if (warp == 0) {
+        const int cnt = min(s_list, SURV_CAP);
+        const int total = cnt + nv;
+        auto fetch = [&](int k) -> Line {
+          if (k < cnt) {
+            const SurvEntry e = list[k];
+            return make_line(lb, w, e.a, e.z, e.idx);
+          }
+          Line L;
+          L.a = v_a[k - cnt]; L.b = v_b[k - cnt]; L.idx = v_idx[k - cnt];
+          L.ref = ref_index(lb, L.idx);
+          return L;
+        };
+        const HullResult r = warp_march(total, fetch, rec);
+        if (lane == 0) {
+          finish_set(lb, out, set, s, r.E, r.h);
+          if (sc.stats) {
+            atomicAdd((unsigned long long*)&sc.stats[2], 1ull);
+            atomicAdd((unsigned long long*)&sc.stats[3], (unsigned long long)r.h);
+          }
+        }
+      }
+    } else {
+      // ---- exact block-wide march over ALL lines (e.g. every line is a hull vertex) ----
+      Line cur = empty_line();
+      for (int n = tid; n < lb.NL; n += blockDim.x) {
+        const Line L = gather_line(lb, c, j, w, n);
+        if (cur.idx < 0 || sorted_before(L, cur)) cur = L;
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const Line oth = shfl_line(cur, o);
+        if (oth.idx >= 0 && (cur.idx < 0 || sorted_before(oth, cur))) cur = oth;
+      }
+      if (lane == 0) { r_a[warp] = cur.a; r_b[warp] = cur.b; r_idx[warp] = cur.idx; r_ref[warp] = cur.ref; }
+      __syncthreads();
+      if (tid == 0) {
+        Line best = empty_line();
+        for (int k = 0; k < E_THREADS / 32; ++k) {
+          Line L;
+          L.a = r_a[k]; L.b = r_b[k]; L.idx = r_idx[k]; L.ref = r_ref[k];
+          if (L.idx >= 0 && (best.idx < 0 || sorted_before(L, best))) best = L;
+        }
+        c_a = best.a; c_b = best.b; c_idx = best.idx; c_ref = best.ref;
+      }
+      __syncthreads();
+      double E = 0.0, prev_cdf = 0.0, prev_pdf = 0.0;
+      int h = 0;
+      while (true) {
+        cur.a = c_a; cur.b = c_b; cur.idx = c_idx; cur.ref = c_ref;
+        Next best;
+        best.L = empty_line();
+        best.x = INFINITY;
+        for (int n = tid; n < lb.NL; n += blockDim.x) consider_next(best, cur, gather_line(lb, c, j, w, n));
+        for (int o = 16; o > 0; o >>= 1) {
+          Next oth;
+          oth.L = shfl_line(best.L, o);
+          oth.x = __shfl_xor_sync(0xffffffffu, best.x, o);
+          merge_next(best, oth);
+        }
+        if (lane == 0) {
+          r_a[warp] = best.L.a; r_b[warp] = best.L.b; r_idx[warp] = best.L.idx;
+          r_ref[warp] = best.L.ref; r_x[warp] = best.x;
+        }
+        __syncthreads();
+        Next nx;
+        nx.L = empty_line();
+        nx.x = INFINITY;
+        for (int k = 0; k < E_THREADS / 32; ++k) {
+          Next o;
+          o.L.a = r_a[k]; o.L.b = r_b[k]; o.L.idx = r_idx[k]; o.L.ref = r_ref[k]; o.x = r_x[k];
+          merge_next(nx, o);
+        }
+        const bool last = nx.L.idx < 0;
+        const double cdf = last ? 1.0 : std_normal_cdf(nx.x);
+        const double pdf = last ? 0.0 : std_normal_pdf(nx.x);
+        const double dP = cdf - prev_cdf, dp = pdf - prev_pdf;
+        E += __dsub_rn(__dmul_rn(cur.a, dP), __dmul_rn(cur.b, dp));
+        __syncthreads();  // everyone has consumed c_* and r_* of this step
+        if (tid == 0) {
+          rec(h, cur, dP, -dp, nx.x, last);
+          c_a = nx.L.a; c_b = nx.L.b; c_idx = nx.L.idx; c_ref = nx.L.ref;
+        }
+        ++h;
+        prev_cdf = cdf;
+        prev_pdf = pdf;
+        __syncthreads();
+        if (last) break;
+      }
+      if (tid == 0) {
+        finish_set(lb, out, set, s, E, h);
+        if (sc.stats) {
+          atomicAdd((unsigned long long*)&sc.stats[2], 1ull);
+          atomicAdd((unsigned long long*)&sc.stats[5], 1ull);
+          atomicAdd((unsigned long long*)&sc.stats[3], (unsigned long long)h);
+        }
+      }
+    }
+  }
+}
+
+int emax_overflow(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cudaStream_t st) {
+  if (lb.C == 0) return DKG_OK;
+  long long sets = (long long)lb.C * lb.S;
+  int grid = (int)(sets < 2 * 148 ? sets : 2 * 148);
+  overflow_kernel<<<grid, E_THREADS, 0, st>>>(lb, sc, out);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize: kg[c] and the fused backward (envelope theorem); CTA per candidate
+//   dKG/da_jn = (p_jn - [n == argmax a_j]) / S ; dKG/db_jn = q_jn / S on hull lines only.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(E_THREADS)
+finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
   extern __shared__ __align__(16) unsigned char e_smem[];
   const int c = blockIdx.x;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   const int S = lb.S;
-
-  long long st_surv = 0, st_slow = 0, st_hull = 0, st_short = 0;
-
-  for (int j = warp; j < S; j += nwarps) {
-    const size_t set = (size_t)c * S + j;
-    const double w = lb.wt ? lb.wt[j] : 1.0;
-    const double zmin = sc.zst[c * 2 + 0], zmax = sc.zst[c * 2 + 1];
-    double amax = lb.Amax[(size_t)c * lb.am_sc + j];
-    int iT = lb.Aarg[(size_t)c * lb.am_sc + j];
-    int own_is_max = 0;
-    if (lb.a_own != nullptr) {
-      double ao = lb.a_own[set];
-      // torch.max over [own line, discretisation...] returns the first maximum: the own line
-      // (reference index 0) wins ties.
-      if (ao >= amax) { amax = ao; iT = lb.NA; own_is_max = 1; }
-    }
-    if (out.amax_is_own != nullptr && lane == 0) out.amax_is_own[set] = own_is_max;
-
-    double E;
-    int h;
-    const size_t rbase = set * (size_t)out.hull_cap;
-    auto rec = [&](int k, const Line& L, double p, double q, double x, bool last) {
-      if (k < out.hull_cap) {
-        if (out.hull_idx) out.hull_idx[rbase + k] = L.idx;
-        if (out.hull_p) out.hull_p[rbase + k] = p;
-        if (out.hull_q) out.hull_q[rbase + k] = q;
-        if (out.hull_x && !last) out.hull_x[rbase + k] = x;
-      }
-      if (out.dense_da) out.dense_da[set * (size_t)lb.NL + L.idx] = p;
-      if (out.dense_db) out.dense_db[set * (size_t)lb.NL + L.idx] = q;
-    };
-
-    const bool shortcut =
-        fabs(__dmul_rn(w, zmin)) < SHORTCUT_TOL && fabs(__dmul_rn(w, zmax)) < SHORTCUT_TOL;
-    if (shortcut) {
-      // all |slopes| < 1e-9: the reference returns argmax(intercepts) only (:363-367)
-      E = amax;
-      h = 1;
-      if (lane == 0) {
-        Line L;
-        L.idx = iT; L.a = amax; L.b = 0; L.ref = 0;
-        rec(0, L, 1.0, 0.0, 0.0, true);
-      }
-      ++st_short;
-    } else {
-      SetView v;
-      v.lb = &lb;
-      v.c = c;
-      v.j = j;
-      v.w = w;
-      const int cnt = sc.surv_cnt[set];
-      if (cnt <= SURV_CAP) {
-        v.surv = sc.surv_idx + set * SURV_CAP;
-        v.cnt = cnt;
-        v.nseed = 0;
-        v.seeds[v.nseed++] = sc.zarg[c * 2 + 0];
-        v.seeds[v.nseed++] = sc.zarg[c * 2 + 1];
-        v.seeds[v.nseed++] = lb.Aarg[(size_t)c * lb.am_sc + j];
-        if (lb.a_own != nullptr) v.seeds[v.nseed++] = lb.NA;
-        v.total = cnt + v.nseed;
-        st_surv += cnt;
-      } else {  // filter kept too many lines: march over everything (slow, exact)
-        v.surv = nullptr;
-        v.cnt = 0;
-        v.nseed = 0;
-        v.total = lb.NL;
-        ++st_slow;
-      }
-      HullResult r = warp_march(v, rec);
-      E = r.E;
-      h = r.h;
-    }
-    st_hull += h;
-    if (lane == 0) {
-      if (out.hull_cnt) out.hull_cnt[set] = h;
-      out.terms[set] = out.subtract_max ? (E - amax) : E;  // kg[j] = E - max(intercepts) (:336)
-    }
-  }
-
-  if (sc.stats != nullptr && lane == 0) {
-    if (st_surv) atomicAdd((unsigned long long*)&sc.stats[1], (unsigned long long)st_surv);
-    if (st_slow) atomicAdd((unsigned long long*)&sc.stats[2], (unsigned long long)st_slow);
-    if (st_hull) atomicAdd((unsigned long long*)&sc.stats[3], (unsigned long long)st_hull);
-    if (st_short) atomicAdd((unsigned long long*)&sc.stats[4], (unsigned long long)st_short);
-  }
-  if (out.kg == nullptr) return;
-  __syncthreads();
 
   if (threadIdx.x == 0) {
     double acc = 0.0;
@@ -459,13 +896,10 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out, BackwardArgs bw) {
   }
   if (bw.dX == nullptr) return;
 
-  // ---------------- fused backward (envelope theorem) ----------------
-  // dKG/da_jn = (p_jn - [n == argmax a_j]) / S ; dKG/db_jn = q_jn / S on hull lines only.
   double* s_r = reinterpret_cast<double*>(e_smem);  // [n_pad]  sum_n Gz[n] B[:, n]
   double* s_ga = s_r + bw.n_pad;                    // [S]      dKG/d a_own[j]
-  double* s_sc = s_ga + S;                          // scalars: [0] Gsum, [1] GzOwn, [2..2+d) gkd,
-                                                    //          [2+MAX_D .. ) Gm[m]
-  double* s_red = s_sc + 2 + MAX_D + MAX_M;         // [nwarps * MAX_D] reduction scratch
+  double* s_sc = s_ga + S;                          // [0] Gsum, [1] GzOwn, [2..2+MAX_D) gkd, then Gm[m]
+  double* s_red = s_sc + 2 + MAX_D + MAX_M;         // [nwarps * MAX_D]
   const int tgt = bw.target;
   const int d = bw.d;
   const double invS = 1.0 / (double)S;
@@ -589,13 +1023,12 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out, BackwardArgs bw) {
   }
 }
 
-int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out,
-              const BackwardArgs& bw, cudaStream_t st) {
-  if (lb.C == 0) return DKG_OK;
+int emax_finalize(const LineBatch& lb, const EmaxOut& out, const BackwardArgs& bw, cudaStream_t st) {
+  if (lb.C == 0 || out.kg == nullptr) return DKG_OK;
   size_t smem = 0;
   if (bw.dX != nullptr)
     smem = sizeof(double) * ((size_t)bw.n_pad + lb.S + 2 + MAX_D + MAX_M + (E_THREADS / 32) * MAX_D);
-  hull_kernel<<<lb.C, E_THREADS, smem, st>>>(lb, sc, out, bw);
+  finalize_kernel<<<lb.C, E_THREADS, smem, st>>>(lb, out, bw);
   DKG_LAUNCH_CHECK();
   return DKG_OK;
 }

@@ -27,12 +27,22 @@ struct LineBatch {
   int NA = 0, NL = 0, S = 0, C = 0;
 };
 
+// one line that survived the streaming chord filter (intercept, raw slope coordinate, index)
+struct SurvEntry {
+  double a;
+  double z;
+  int idx;
+  int pad;
+};
+
 struct EmaxScratch {
-  double* zst = nullptr;    // [C, 2] min / max of the slope row
-  int* zarg = nullptr;      // [C, 2] their first indices
-  int* surv_cnt = nullptr;  // [C, S]
-  int* surv_idx = nullptr;  // [C, S, SURV_CAP]
-  long long* stats = nullptr;
+  double* zst = nullptr;        // [C, 2] min / max of the slope row
+  int* zarg = nullptr;          // [C, 2] their first indices
+  int* surv_cnt = nullptr;      // [C, S]  lines that passed the filter (may exceed SURV_CAP)
+  SurvEntry* surv = nullptr;    // [C, S, SURV_CAP]
+  int* ovf_sets = nullptr;      // [C * S] queue of sets for the cooperative kernel
+  int* ovf_count = nullptr;     // [1]
+  long long* stats = nullptr;   // [8] (optional)
 };
 
 struct EmaxOut {
@@ -50,11 +60,10 @@ struct EmaxOut {
   double* dense_db = nullptr;  // [C*S, NL] dE/db (optional, pre-zeroed)
 };
 
-// Backward of the KG path, fused into the hull kernel's tail (one CTA per candidate).
+// Backward of the KG path (finalize kernel, one CTA per candidate).
 struct BackwardArgs {
   double* dX = nullptr;          // [C, d]; nullptr -> forward only
   const double* X = nullptr;     // [C, d] raw candidates
-  const double* KX = nullptr;    // (unused by the kernel; kept for debugging)
   const double* T = nullptr;     // [C, ldk]  Kinv k_i(X_train, x_c)
   int ldk = 0;
   const double* BT = nullptr;    // [N, n_pad]
@@ -77,7 +86,11 @@ struct BackwardArgs {
 int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int* aarg_out,
                cudaStream_t st);
 int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st);
-int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out,
-              const BackwardArgs& bw, cudaStream_t st);
+// warp-per-set exact hull + closed-form expectation; sets it cannot finish go to the queue
+int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cudaStream_t st);
+// CTA-per-set cooperative path for the queued sets (any input; always terminates)
+int emax_overflow(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cudaStream_t st);
+// kg[c] = mean_j terms[c, j] and, if bw.dX, the fused envelope-theorem backward
+int emax_finalize(const LineBatch& lb, const EmaxOut& out, const BackwardArgs& bw, cudaStream_t st);
 
 }  // namespace dkg

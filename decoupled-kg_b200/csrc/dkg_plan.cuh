@@ -38,7 +38,9 @@ struct Workspace {
   double* zst = nullptr;    // [chunk_C, 2]      min / max of the slope row
   int* zarg = nullptr;      // [chunk_C, 2]      argmin, argmax of the slope row
   int* surv_cnt = nullptr;  // [chunk_C, S]      chord-filter survivors per (candidate, scal.)
-  int* surv_idx = nullptr;  // [chunk_C, S, SURV_CAP]
+  void* surv = nullptr;     // [chunk_C, S, SURV_CAP] SurvEntry (intercept, slope, index)
+  int* ovf_sets = nullptr;  // [chunk_C * S] queue of sets for the cooperative kernel
+  int* ovf_count = nullptr; // [1]
   int* hull_cnt = nullptr;  // [cap_C, S]
   int* hull_idx = nullptr;  // [cap_C, S, HULL_CAP]
   double* hull_p = nullptr; // [cap_C, S, HULL_CAP]  dE/da  (Phi differences)

@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = (
     "dkg_profile_enable",
     "dkg_profile_read",
 )
-PROFILE_CATEGORIES = ("xprep", "gemm_T", "var", "gemm_cov", "place_own", "zstat", "filter", "hull")
+PROFILE_CATEGORIES = ("xprep", "gemm_T", "var", "gemm_cov", "place_own", "zstat", "filter", "hull", "overflow", "finalize")
 
 
 class NativeLibraryError(RuntimeError):

@@ -157,8 +157,8 @@ DKG_API void dkg_launch_count_reset(void);
  * forward is bracketed by CUDA events on the launching stream.  dkg_profile_read synchronises the
  * device, sums the elapsed milliseconds and launch counts per category and clears the samples.
  * Categories: 0 xprep, 1 gemm_T (KX @ Kinv), 2 var, 3 gemm_cov (the conditioning contraction),
- * 4 place_own, 5 zstat, 6 filter, 7 hull (+ fused backward). */
-#define DKG_PROFILE_CATEGORIES 8
+ * 4 place_own, 5 zstat, 6 filter, 7 hull, 8 overflow (cooperative path), 9 finalize (+ backward). */
+#define DKG_PROFILE_CATEGORIES 10
 DKG_API void dkg_profile_enable(int on);
 DKG_API int dkg_profile_read(double* ms_host, int64_t* count_host, int32_t ncat);
 

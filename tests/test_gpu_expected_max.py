@@ -55,8 +55,9 @@ def test_reference_kats():
     assert run([1.5], [0])["e"] == pytest.approx(1.5)
     assert run([0], [1])["e"] == pytest.approx(0, abs=1e-300)
     assert run([0, 0], [0, 1])["e"] == pytest.approx(1 / math.sqrt(2 * math.pi))
-    want = math.erf(1 / math.sqrt(2)) - (1 - math.exp(-1 / 2)) * math.sqrt(2 / math.pi)
-    assert run([0, 1, 1, 0], [0, 1, -1, 0])["e"] == pytest.approx(want)
+    # (the reference's "hump" KAT :312-328 is not an upper envelope -- it is pinned on the oracle's
+    #  expectation function in test_oracle_kats.py; its convex counterpart is E[1 + |Z|])
+    assert run([0, 1, 1, 0], [0, 1, -1, 0])["e"] == pytest.approx(1 + math.sqrt(2 / math.pi))
     # tiny slopes (1e-12 < 1e-9 tolerance) take the shortcut (:363)
     assert run([1.5, 0], [0, 1e-12])["idx"] == [0]
 
@@ -75,8 +76,10 @@ def test_golden_line_sets():
             for i, j in zip(r["idx"], want_idx):
                 assert a[i] == a[j] and b[i] == b[j], (k, r["idx"], want_idx)
         else:
-            np.testing.assert_allclose(r["da"], G[f"ga{k}"], rtol=0, atol=2e-16)
-            np.testing.assert_allclose(r["db"], G[f"gb{k}"], rtol=0, atol=2e-16)
+            # dE/da = Phi differences, dE/db = -phi differences: CUDA's erf/exp and the host libm
+            # differ by an ulp, so a difference of two of them may be off by a few 1e-16
+            np.testing.assert_allclose(r["da"], G[f"ga{k}"], rtol=0, atol=1e-15)
+            np.testing.assert_allclose(r["db"], G[f"gb{k}"], rtol=0, atol=1e-15)
 
 
 @pytest.mark.parametrize("L", [1, 2, 31, 33, 1000, 5000])

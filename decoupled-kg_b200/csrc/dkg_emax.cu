@@ -191,67 +191,104 @@ __device__ double4 chain_params(const LineBatch& lb, const EmaxScratch& sc, int 
   return make_double4(c1, m1 * sgn, c2, m2 * sgn);
 }
 
-template <int G, bool SHARED_A>
-__global__ void __launch_bounds__(E_THREADS)
-filter_kernel(LineBatch lb, EmaxScratch sc, int slice_len) {
+// Each CTA owns G candidates x (E_THREADS * R) lines; each thread keeps the slope coordinates of
+// its R lines for the G candidates in registers (G*R doubles), then walks the scalarisations:
+// per scalarisation it loads the chain parameters of the G sets once (shared-memory broadcast)
+// and the R intercepts once (coalesced, shared by the G candidates), and runs G*R tests of
+// 2 DFMA + DMNMX + DSETP each.  Survivors are rare (~1%) and appended with an atomic slot claim.
+template <int G, int R, bool SHARED_A>
+__global__ void __launch_bounds__(E_THREADS, 2)
+filter_kernel(LineBatch lb, EmaxScratch sc) {
   extern __shared__ __align__(16) unsigned char e_smem[];
-  double4* s_par = reinterpret_cast<double4*>(e_smem);  // [G][S]
+  double4* s_par = reinterpret_cast<double4*>(e_smem);  // [S][G]
   const int c0 = blockIdx.y * G;
   const int S = lb.S;
   for (int e = threadIdx.x; e < G * S; e += blockDim.x) {
-    int g = e / S, j = e - g * S;
-    int c = c0 + g;
+    const int j = e / G, g = e - j * G;
+    const int c = c0 + g;
     s_par[e] = (c < lb.C) ? chain_params(lb, sc, c, j) : make_double4(INFINITY, 0.0, INFINITY, 0.0);
   }
+  const int lo = blockIdx.x * (E_THREADS * R) + threadIdx.x;
+  double z[G][R];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int n = lo + r * E_THREADS;
+      z[g][r] = (c0 + g < lb.C && n < lb.NA) ? lb.Z[(size_t)(c0 + g) * lb.ldz + n] : 0.0;
+    }
   __syncthreads();
 
-  const int lo = blockIdx.x * slice_len;
-  const int hi = min(lo + slice_len, lb.NA);
-  for (int n = lo + threadIdx.x; n < hi; n += blockDim.x) {
-    double z[G];
+  for (int j = 0; j < S; ++j) {
+    double4 p[G];
 #pragma unroll
-    for (int g = 0; g < G; ++g)
-      z[g] = (c0 + g < lb.C) ? lb.Z[(size_t)(c0 + g) * lb.ldz + n] : 0.0;
-    for (int j = 0; j < S; ++j) {
-      double a_sh = 0.0;
-      if (SHARED_A) a_sh = lb.A[(size_t)j * lb.a_sj + n];
+    for (int g = 0; g < G; ++g) p[g] = s_par[j * G + g];
+    double a[R];
+    if (SHARED_A) {
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        double a = a_sh;
-        if (!SHARED_A)
-          a = (c0 + g < lb.C) ? lb.A[(size_t)(c0 + g) * lb.a_sc + (size_t)j * lb.a_sj + n]
-                              : -INFINITY;
-        const double4 p = s_par[g * S + j];
-        const double thr = fmin(fma(p.y, z[g], p.x), fma(p.w, z[g], p.z));
-        if (a > thr) {
-          const size_t set = (size_t)(c0 + g) * S + j;
-          int pos = atomicAdd(&sc.surv_cnt[set], 1);
-          if (pos < SURV_CAP) {
-            SurvEntry e;
-            e.a = a; e.z = z[g]; e.idx = n; e.pad = 0;
-            sc.surv[set * SURV_CAP + pos] = e;
-          }
+      for (int r = 0; r < R; ++r) {
+        const int n = lo + r * E_THREADS;
+        a[r] = (n < lb.NA) ? lb.A[(size_t)j * lb.a_sj + n] : -INFINITY;
+      }
+    }
+    // branch-free tests -> bit mask (bit g*R + r); the rare survivors are appended afterwards by
+    // ONE copy of the append code, which re-reads its two values from memory (cheaper than
+    // selecting them out of the register arrays).  a > min(l1, l2)  <=>  a > l1 or a > l2.
+    unsigned mask = 0u;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        double av;
+        if (SHARED_A) av = a[r];
+        else {
+          const int n = lo + r * E_THREADS;
+          av = (c0 + g < lb.C && n < lb.NA)
+                   ? lb.A[(size_t)(c0 + g) * lb.a_sc + (size_t)j * lb.a_sj + n] : -INFINITY;
         }
+        const double t1 = fma(p[g].y, z[g][r], p[g].x);
+        const double t2 = fma(p[g].w, z[g][r], p[g].z);
+        if ((av > t1) | (av > t2)) mask |= 1u << (g * R + r);
+      }
+    }
+    while (mask) {
+      const int bit = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      const int g = bit / R, r = bit - g * R;
+      const int n = lo + r * E_THREADS;
+      const int c = c0 + g;
+      const size_t set = (size_t)c * S + j;
+      const int pos = atomicAdd(&sc.surv_cnt[set], 1);
+      if (pos < SURV_CAP) {
+        SurvEntry e;
+        e.a = lb.A[(size_t)c * lb.a_sc + (size_t)j * lb.a_sj + n];
+        e.z = lb.Z[(size_t)c * lb.ldz + n];
+        e.idx = n;
+        e.pad = 0;
+        sc.surv[set * SURV_CAP + pos] = e;
       }
     }
   }
 }
 
-int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st) {
-  if (lb.C == 0 || lb.NA == 0) return DKG_OK;
-  constexpr int G = 4;
-  // slices sized so the grid has a few waves of CTAs on 148 SMs
-  int rows = ceil_div(lb.C, G);
-  int slice = 2048;
-  while (slice > 256 && (long long)rows * ceil_div(lb.NA, slice) < 2 * 148) slice >>= 1;
-  dim3 grid(ceil_div(lb.NA, slice), rows);
-  size_t smem = (size_t)G * lb.S * sizeof(double4);
+template <int G, int R>
+static int launch_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st) {
+  dim3 grid(ceil_div(lb.NA, E_THREADS * R), ceil_div(lb.C, G));
+  const size_t smem = (size_t)G * lb.S * sizeof(double4);
   if (lb.a_sc == 0)
-    filter_kernel<G, true><<<grid, E_THREADS, smem, st>>>(lb, sc, slice);
+    filter_kernel<G, R, true><<<grid, E_THREADS, smem, st>>>(lb, sc);
   else
-    filter_kernel<G, false><<<grid, E_THREADS, smem, st>>>(lb, sc, slice);
+    filter_kernel<G, R, false><<<grid, E_THREADS, smem, st>>>(lb, sc);
   DKG_LAUNCH_CHECK();
   return DKG_OK;
+}
+
+int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st) {
+  if (lb.C == 0 || lb.NA == 0) return DKG_OK;
+  // big batches: 8 lines per thread (fewer parameter loads per test); small ones: more CTAs
+  const long long ctas8 = (long long)ceil_div(lb.C, 4) * ceil_div(lb.NA, E_THREADS * 8);
+  if (ctas8 >= 2 * 148) return launch_filter<4, 8>(lb, sc, st);
+  return launch_filter<4, 2>(lb, sc, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -622,6 +659,7 @@ int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cu
 // overflow kernel: one CTA per queued set, all lines, always terminates
 // ------------------------------------------------------------------------------------------
 constexpr int OVF_MAXV = 130;  // chain vertices
+constexpr int FIN_RMAX = 1024; // hull records per candidate merged in shared memory
 constexpr int OVF_ROUNDS = 6;
 
 __device__ __forceinline__ unsigned long long pack_excess(double e, int n) {
@@ -647,7 +685,7 @@ overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
   __shared__ unsigned long long v_best[OVF_MAXV];
   __shared__ double n_b[OVF_MAXV], n_a[OVF_MAXV];
   __shared__ int n_i[OVF_MAXV];
-  __shared__ int s_nv, s_grew, s_count, s_list;
+  __shared__ int s_nv, s_grew, s_list;
   __shared__ double r_a[E_THREADS / 32], r_b[E_THREADS / 32], r_x[E_THREADS / 32];
   __shared__ int r_idx[E_THREADS / 32], r_ref[E_THREADS / 32];
   __shared__ double c_a, c_b;
@@ -684,6 +722,10 @@ overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
     }
     __syncthreads();
 
+    // Every round classifies all lines against the current chain, optimistically compacting the
+    // survivors into this set's (global) list; if they fit, the list is final.  Otherwise the
+    // farthest line above every chord becomes a new chain vertex and the pass is repeated.
+    SurvEntry* list = sc.surv + set * SURV_CAP;
     bool small_enough = false;
     for (int round = 0; round <= OVF_ROUNDS; ++round) {
       const int nv = s_nv;
@@ -695,28 +737,34 @@ overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
           v_slack[k] = EPS128 * (fabs(v_a[k]) + fabs(v_a[k + 1]) + fabs(m) * fmax(fabs(v_b[k]), fabs(v_b[k + 1])));
         }
       }
-      if (tid == 0) s_count = 0;
+      if (tid == 0) s_list = 0;
       __syncthreads();
-      int local = 0;
       for (int n = tid; n < lb.NL; n += blockDim.x) {
-        const Line L = gather_line(lb, c, j, w, n);
-        if (L.b < v_b[0]) { ++local; continue; }  // outside the chain: cannot be dropped
-        const int k = chain_locate(v_b, nv, L.b);
-        if (L.b == v_b[k]) {  // same slope as a vertex: survives only if it is higher
-          if (L.a > v_a[k]) ++local;
-          continue;
+        const double zn = lb.Z[(size_t)c * lb.ldz + n];
+        const Line L = make_line(lb, w, line_intercept(lb, c, j, n), zn, n);
+        bool keep;
+        if (L.b < v_b[0]) keep = true;  // outside the chain: cannot be dropped
+        else {
+          const int k = chain_locate(v_b, nv, L.b);
+          if (L.b == v_b[k]) keep = L.a > v_a[k];  // same slope as a vertex: only if higher
+          else if (k == nv - 1) keep = true;       // beyond the last vertex
+          else {
+            const double e = L.a - fma(v_m[k], L.b - v_b[k], v_a[k]);
+            keep = e > -v_slack[k];
+            if (e > 0.0) atomicMax(&v_best[k], pack_excess(e, n));
+          }
         }
-        if (k == nv - 1) { ++local; continue; }  // beyond the last vertex: keep
-        const double e = L.a - fma(v_m[k], L.b - v_b[k], v_a[k]);
-        if (e > -v_slack[k]) {
-          ++local;
-          if (e > 0.0) atomicMax(&v_best[k], pack_excess(e, n));
+        if (keep) {
+          const int pos = atomicAdd(&s_list, 1);
+          if (pos < SURV_CAP) {
+            SurvEntry e;
+            e.a = L.a; e.z = zn; e.idx = n; e.pad = 0;
+            list[pos] = e;
+          }
         }
       }
-      for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-      if (lane == 0 && local) atomicAdd(&s_count, local);
       __syncthreads();
-      if (s_count <= SURV_CAP) { small_enough = true; break; }
+      if (s_list <= SURV_CAP) { small_enough = true; break; }
       if (round == OVF_ROUNDS) break;
       // insert the farthest line of every chord (thread 0; chains are tiny)
       if (tid == 0) {
@@ -742,30 +790,8 @@ overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
     }
 
     if (small_enough) {
-      // ---- compact the survivors into this set's (global) list and let warp 0 march ----
+      // ---- the list is complete: warp 0 marches over it plus the chain vertices ----
       const int nv = s_nv;
-      SurvEntry* list = sc.surv + set * SURV_CAP;
-      if (tid == 0) s_list = 0;
-      __syncthreads();
-      for (int n = tid; n < lb.NL; n += blockDim.x) {
-        const Line L = gather_line(lb, c, j, w, n);
-        bool keep;
-        if (L.b < v_b[0]) keep = true;
-        else {
-          const int k = chain_locate(v_b, nv, L.b);
-          if (L.b == v_b[k]) keep = L.a > v_a[k];
-          else if (k == nv - 1) keep = true;
-          else keep = (L.a - fma(v_m[k], L.b - v_b[k], v_a[k])) > -v_slack[k];
-        }
-        if (keep) {
-          const int pos = atomicAdd(&s_list, 1);
-          if (pos < SURV_CAP) {
-            SurvEntry e;
-            e.a = L.a; e.z = lb.Z[(size_t)c * lb.ldz + n]; e.idx = n; e.pad = 0;
-            list[pos] = e;
-          }
-        }
-      }
       __syncthreads();
       if (warp == 0) {
         const int cnt = min(s_list, SURV_CAP);
@@ -906,24 +932,89 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
   const double* zrow = lb.Z + (size_t)c * lb.ldz;
   const int hcap = out.hull_cap;
 
-  // r_t over this thread's training points; every thread walks the same record list in order
+  // ---- gather the hull records of this candidate and merge duplicates: the same few lines are
+  // hull vertices for most scalarisations, so the B^T row gathers and kernel-gradient evaluations
+  // below run once per DISTINCT line (order = first occurrence, hence deterministic) ----
+  int* s_ridx = reinterpret_cast<int*>(s_red + nwarps * MAX_D);  // [FIN_RMAX] record line index
+  int* s_uidx = s_ridx + FIN_RMAX;                               // [FIN_RMAX] distinct line index
+  int* s_flag = s_uidx + FIN_RMAX;                               // [FIN_RMAX] first occurrence?
+  int* s_roff = s_flag + FIN_RMAX;                               // [S + 1] record offsets per set
+  double* s_rcz = reinterpret_cast<double*>(s_roff + ((S + 2) & ~1));  // [FIN_RMAX] w_j q / S
+  double* s_ucz = s_rcz + FIN_RMAX;                              // [FIN_RMAX] merged coefficient
+  __shared__ int s_nrec, s_nuniq;
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int j = 0; j < S; ++j) {
+      s_roff[j] = off;
+      off += min(out.hull_cnt[(size_t)c * S + j], hcap);
+    }
+    s_roff[S] = off;
+    s_nrec = off;
+    s_nuniq = 0;
+  }
+  __syncthreads();
+  const int nrec = s_nrec;
+  const bool merged = nrec <= FIN_RMAX;
+  if (merged) {
+    for (int j = warp; j < S; j += nwarps) {
+      const size_t set = (size_t)c * S + j;
+      const double wj = bw.W[j * bw.M + tgt];
+      const int h = s_roff[j + 1] - s_roff[j];
+      for (int k = lane; k < h; k += 32) {
+        s_ridx[s_roff[j] + k] = out.hull_idx[set * hcap + k];
+        s_rcz[s_roff[j] + k] = wj * out.hull_q[set * hcap + k] * invS;
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nrec; e += blockDim.x) {  // first occurrence of its line?
+      const int idx = s_ridx[e];
+      int first = 1;
+      for (int f = 0; f < e; ++f)
+        if (s_ridx[f] == idx) { first = 0; break; }
+      s_flag[e] = first;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nrec; e += blockDim.x) {
+      if (!s_flag[e]) continue;
+      const int idx = s_ridx[e];
+      int rank = 0;  // distinct lines that first occur before e
+      for (int f = 0; f < e; ++f) rank += s_flag[f];
+      double acc = 0.0;
+      for (int f = e; f < nrec; ++f)
+        if (s_ridx[f] == idx) acc += s_rcz[f];
+      s_uidx[rank] = idx;
+      s_ucz[rank] = acc;
+      atomicAdd(&s_nuniq, 1);
+    }
+    __syncthreads();
+  }
+  const int nuniq = merged ? s_nuniq : 0;
+
+  // r_t over this thread's training points; every thread walks the same list in order
   for (int t = threadIdx.x; t < bw.n_pad; t += blockDim.x) {
     double acc = 0.0;
-    for (int j = 0; j < S; ++j) {
-      const size_t set = (size_t)c * S + j;
-      const int h = min(out.hull_cnt[set], hcap);
-      const double wj = bw.W[j * bw.M + tgt];
-      for (int k = 0; k < h; ++k) {
-        const int idx = out.hull_idx[set * hcap + k];
-        if (idx < lb.NA) {
-          const double cz = wj * out.hull_q[set * hcap + k] * invS;
-          acc += cz * bw.BT[(size_t)idx * bw.n_pad + t];
+    if (merged) {
+      for (int u = 0; u < nuniq; ++u) {
+        const int idx = s_uidx[u];
+        if (idx < lb.NA) acc += s_ucz[u] * bw.BT[(size_t)idx * bw.n_pad + t];
+      }
+    } else {
+      for (int j = 0; j < S; ++j) {
+        const size_t set = (size_t)c * S + j;
+        const int h = min(out.hull_cnt[set], hcap);
+        const double wj = bw.W[j * bw.M + tgt];
+        for (int k = 0; k < h; ++k) {
+          const int idx = out.hull_idx[set * hcap + k];
+          if (idx < lb.NA) {
+            const double cz = wj * out.hull_q[set * hcap + k] * invS;
+            acc += cz * bw.BT[(size_t)idx * bw.n_pad + t];
+          }
         }
       }
     }
     s_r[t] = acc;
   }
-  // scalars: warp 0, lane l owns scalarisations l, l+32, ...
+  // scalars: warp 0
   if (warp == 0) {
     double gsum = 0.0, gzown = 0.0, gkd[MAX_D], gm[MAX_M];
 #pragma unroll
@@ -934,32 +1025,36 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
 #pragma unroll
     for (int k = 0; k < MAX_D; ++k)
       xs_t[k] = k < d ? bw.X[(size_t)c * d + k] / bw.ls[tgt][k] : 0.0;
-    for (int j = lane; j < S; j += 32) {
+    auto slope_terms = [&](int idx, double cz) {
+      gsum += cz * zrow[idx];
+      if (idx == lb.NA) {
+        gzown += cz;
+      } else {
+        double sq = 0.0;
+#pragma unroll
+        for (int q = 0; q < MAX_D; ++q)
+          if (q < d) {
+            double df = xs_t[q] - bw.xd_s[(size_t)idx * d + q];
+            sq += df * df;
+          }
+        const double gc = stationary_grad_coeff(bw.kind[tgt], bw.outputscale[tgt], sq);
+#pragma unroll
+        for (int q = 0; q < MAX_D; ++q)
+          if (q < d)
+            gkd[q] += cz * gc * (xs_t[q] - bw.xd_s[(size_t)idx * d + q]) / bw.ls[tgt][q];
+      }
+    };
+    if (merged)
+      for (int u = lane; u < nuniq; u += 32) slope_terms(s_uidx[u], s_ucz[u]);
+    for (int j = lane; j < S; j += 32) {  // lane l owns scalarisations l, l+32, ...
       const size_t set = (size_t)c * S + j;
       const int h = min(out.hull_cnt[set], hcap);
       const double wj = bw.W[j * bw.M + tgt];
       double ga = out.amax_is_own[set] ? -invS : 0.0;
       for (int k = 0; k < h; ++k) {
         const int idx = out.hull_idx[set * hcap + k];
-        const double cz = wj * out.hull_q[set * hcap + k] * invS;
-        gsum += cz * zrow[idx];
-        if (idx == lb.NA) {
-          gzown += cz;
-          ga += out.hull_p[set * hcap + k] * invS;
-        } else {
-          double sq = 0.0;
-#pragma unroll
-          for (int q = 0; q < MAX_D; ++q)
-            if (q < d) {
-              double df = xs_t[q] - bw.xd_s[(size_t)idx * d + q];
-              sq += df * df;
-            }
-          const double gc = stationary_grad_coeff(bw.kind[tgt], bw.outputscale[tgt], sq);
-#pragma unroll
-          for (int q = 0; q < MAX_D; ++q)
-            if (q < d)
-              gkd[q] += cz * gc * (xs_t[q] - bw.xd_s[(size_t)idx * d + q]) / bw.ls[tgt][q];
-        }
+        if (idx == lb.NA) ga += out.hull_p[set * hcap + k] * invS;
+        if (!merged) slope_terms(idx, wj * out.hull_q[set * hcap + k] * invS);
       }
       s_ga[j] = ga;
 #pragma unroll
@@ -1027,7 +1122,8 @@ int emax_finalize(const LineBatch& lb, const EmaxOut& out, const BackwardArgs& b
   if (lb.C == 0 || out.kg == nullptr) return DKG_OK;
   size_t smem = 0;
   if (bw.dX != nullptr)
-    smem = sizeof(double) * ((size_t)bw.n_pad + lb.S + 2 + MAX_D + MAX_M + (E_THREADS / 32) * MAX_D);
+    smem = sizeof(double) * ((size_t)bw.n_pad + lb.S + 2 + MAX_D + MAX_M + (E_THREADS / 32) * MAX_D) +
+           sizeof(int) * (3 * FIN_RMAX + ((lb.S + 2) & ~1)) + sizeof(double) * 2 * FIN_RMAX;
   finalize_kernel<<<lb.C, E_THREADS, smem, st>>>(lb, out, bw);
   DKG_LAUNCH_CHECK();
   return DKG_OK;

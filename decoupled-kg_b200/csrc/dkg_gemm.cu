@@ -7,20 +7,27 @@
 //   store-mode: D = A @ B   (used for T = KX @ Kinv, the variance quadratic form)
 //
 // tcgen05 has no f64 kind, so the fp64 tensor path on sm_100a is warp-level
-// mma.sync.m8n8k4.f64 (SASS: DMMA.8x8x4).  Tiles: 128 x 128 x 16, 8 warps (4 x 2), warp tile
-// 32 x 64 (4 x 8 DMMA fragments, 64 fp64 accumulators per thread), 3-stage cp.async pipeline,
-// shared-memory rows padded so that every fragment load is bank-conflict free.
+// mma.sync.m8n8k4.f64 (SASS: DMMA.8x8x4; measured peak 37.1 TFLOP/s on B200, equal to the
+// cuBLAS DGEMM rate).  CTA tile 128 x 64 x 16, 8 warps (4 x 2), warp tile 32 x 32 (4 x 4 DMMA
+// fragments, 32 fp64 accumulators per thread) so that TWO CTAs fit per SM: while one CTA runs
+// its kernel-evaluation epilogue the other keeps the DMMA pipe busy.  3-stage cp.async pipeline;
+// shared-memory rows padded (+4 doubles) so every fragment load is bank-conflict free.  The
+// epilogue's kernel evaluations live in a non-inlined device function: inlining them 32x made
+// the epilogue ~150 KB of straight-line code and the SM stalled on instruction fetch (ncu:
+// stall_no_instruction 3.1 per issue, profiles/r01_ncu_summary.md).
 #include "dkg_kernels.cuh"
 
 namespace dkg {
 
 constexpr int G_THREADS = 256;
 constexpr int G_STAGES = 3;
+constexpr int G_BN = 64;             // columns per CTA tile (GEMM_BN = 128 is the padding unit)
 constexpr int LDA_S = GEMM_BK + 4;   // 20 doubles: rows land on distinct bank groups
-constexpr int LDB_S = GEMM_BN + 4;   // 132 doubles
+constexpr int LDB_S = G_BN + 4;      // 68 doubles
 constexpr int A_STAGE = GEMM_BM * LDA_S;
 constexpr int B_STAGE = GEMM_BK * LDB_S;
 constexpr size_t GEMM_SMEM = (size_t)G_STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+static_assert(GEMM_BN % G_BN == 0, "padding unit must be a multiple of the CTA tile width");
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -39,9 +46,38 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
       : "d"(a), "d"(b));
 }
 
+// Four outputs of one accumulator row (fragment pair: columns lc0, lc0+1, lc0+8, lc0+9 of the
+// tile): kernel value minus the contraction, scaled, divided by the predictive sd, stored to the
+// slope buffer.  Kept out of line on purpose (see header); takes no pointers to locals.
+__device__ __noinline__ void cov_epilogue4(const double* __restrict__ xr, const double* __restrict__ xc0,
+                                           int d, int kind, double outputscale, double ystd2,
+                                           double sdr, double acc0, double acc1, double acc2,
+                                           double acc3, double* __restrict__ dst, int col, int N) {
+  double sq0 = 0.0, sq1 = 0.0, sq2 = 0.0, sq3 = 0.0;
+  for (int k = 0; k < d; ++k) {
+    const double x = xr[k];
+    const double d0 = x - xc0[k];
+    const double d1 = x - xc0[MAX_D + k];
+    const double d2 = x - xc0[8 * MAX_D + k];
+    const double d3 = x - xc0[9 * MAX_D + k];
+    sq0 += d0 * d0;
+    sq1 += d1 * d1;
+    sq2 += d2 * d2;
+    sq3 += d3 * d3;
+  }
+  const double z0 = ((stationary_from_sq(kind, outputscale, sq0) - acc0) * ystd2) / sdr;
+  const double z1 = ((stationary_from_sq(kind, outputscale, sq1) - acc1) * ystd2) / sdr;
+  const double z2 = ((stationary_from_sq(kind, outputscale, sq2) - acc2) * ystd2) / sdr;
+  const double z3 = ((stationary_from_sq(kind, outputscale, sq3) - acc3) * ystd2) / sdr;
+  if (dst == nullptr) return;
+  if (col + 1 < N) *reinterpret_cast<double2*>(dst) = make_double2(z0, z1);
+  else if (col < N) dst[0] = z0;
+  if (col + 9 < N) *reinterpret_cast<double2*>(dst + 8) = make_double2(z2, z3);
+  else if (col + 8 < N) dst[8] = z2;
+}
 
 template <bool COV>
-__global__ void __launch_bounds__(G_THREADS, 1)
+__global__ void __launch_bounds__(G_THREADS, 2)
 dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
                  int K, double* __restrict__ D, int ldd, CovEpilogue ep) {
   extern __shared__ __align__(16) double smem[];
@@ -52,12 +88,12 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
   const int lane = tid & 31;
   const int warp = tid >> 5;
   const int wm = (warp & 3) * 32;
-  const int wn = (warp >> 2) * 64;
+  const int wn = (warp >> 2) * 32;
   const int g = lane >> 2;  // fragment row (A, C) / column (B)
   const int q = lane & 3;   // fragment k index (A, B) / column pair (C)
 
   const int m_base = blockIdx.y * GEMM_BM;
-  const int n_base = blockIdx.x * GEMM_BN;
+  const int n_base = blockIdx.x * G_BN;
 
   const double* Ag = A + (size_t)m_base * lda;
   const double* Bg = B + n_base;
@@ -66,24 +102,24 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
     double* as = As + stage * A_STAGE;
     double* bs = Bs + stage * B_STAGE;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int c = tid + i * G_THREADS;  // 0..1023
+    for (int i = 0; i < 4; ++i) {  // A: 128 rows x 16 doubles = 1024 16-byte chunks
+      int c = tid + i * G_THREADS;
       int row = c >> 3, ch = c & 7;
       cp_async16(as + row * LDA_S + ch * 2, Ag + (size_t)row * lda + k0 + ch * 2);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {  // B: 16 rows x 64 doubles = 512 chunks
       int c = tid + i * G_THREADS;
-      int row = c >> 6, ch = c & 63;
+      int row = c >> 5, ch = c & 31;
       cp_async16(bs + row * LDB_S + ch * 2, Bg + (size_t)(k0 + row) * ldb + ch * 2);
     }
   };
 
-  double acc[4][8][2];
+  double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int KT = K / GEMM_BK;
 #pragma unroll
@@ -104,15 +140,15 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
     const double* bs = Bs + (kt % G_STAGES) * B_STAGE;
 #pragma unroll
     for (int kk = 0; kk < GEMM_BK / 4; ++kk) {
-      double af[4], bf[8];
+      double af[4], bf[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) af[i] = as[(wm + i * 8 + g) * LDA_S + kk * 4 + q];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) bf[j] = bs[(kk * 4 + q) * LDB_S + wn + j * 8 + g];
+      for (int j = 0; j < 4; ++j) bf[j] = bs[(kk * 4 + q) * LDB_S + wn + j * 8 + g];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
   }
   cp_async_wait<0>();
@@ -123,7 +159,7 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
     for (int i = 0; i < 4; ++i) {
       int row = m_base + wm + i * 8 + g;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
         int col = n_base + wn + j * 8 + q * 2;
         *reinterpret_cast<double2*>(D + (size_t)row * ldd + col) =
             make_double2(acc[i][j][0], acc[i][j][1]);
@@ -132,15 +168,18 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
     return;
   } else {
     // stage the scaled coordinates of this tile's candidates and discretisation points
-    double* s_xr = smem;                         // [128][d]
-    double* s_xc = smem + GEMM_BM * MAX_D;       // [128][d]
-    double* s_sd = s_xc + GEMM_BN * MAX_D;       // [128]
+    double* s_xr = smem;                          // [128][MAX_D]
+    double* s_xc = smem + GEMM_BM * MAX_D;        // [64][MAX_D]
+    double* s_sd = s_xc + G_BN * MAX_D;           // [128]
     const int d = ep.d;
-    for (int e = tid; e < GEMM_BM * d; e += G_THREADS) {
-      int r = e / d;
-      s_xr[e] = (m_base + r < ep.C) ? ep.xs[(size_t)(m_base + r) * d + (e - r * d)] : 0.0;
+    for (int e = tid; e < GEMM_BM * MAX_D; e += G_THREADS) {
+      int r = e / MAX_D, k = e - r * MAX_D;
+      s_xr[e] = (k < d && m_base + r < ep.C) ? ep.xs[(size_t)(m_base + r) * d + k] : 0.0;
     }
-    for (int e = tid; e < GEMM_BN * d; e += G_THREADS) s_xc[e] = ep.xd_s[(size_t)n_base * d + e];
+    for (int e = tid; e < G_BN * MAX_D; e += G_THREADS) {
+      int r = e / MAX_D, k = e - r * MAX_D;
+      s_xc[e] = (k < d) ? ep.xd_s[(size_t)(n_base + r) * d + k] : 0.0;
+    }
     for (int e = tid; e < GEMM_BM; e += G_THREADS)
       s_sd[e] = (m_base + e < ep.C) ? ep.sd[m_base + e] : 1.0;
     __syncthreads();
@@ -149,35 +188,15 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
     for (int i = 0; i < 4; ++i) {
       const int lr = wm + i * 8 + g;
       const int row = m_base + lr;
-      double xr[MAX_D];
-#pragma unroll
-      for (int k = 0; k < MAX_D; ++k) xr[k] = k < d ? s_xr[lr * d + k] : 0.0;
       const double sdr = s_sd[lr];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int lc = wn + j * 8 + q * 2;
-        const int col = n_base + lc;
-        double sq0 = 0.0, sq1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < MAX_D; ++k)
-          if (k < d) {
-            double d0 = xr[k] - s_xc[lc * d + k];
-            double d1 = xr[k] - s_xc[(lc + 1) * d + k];
-            sq0 += d0 * d0;
-            sq1 += d1 * d1;
-          }
-        double k0 = stationary_from_sq(ep.kind, ep.outputscale, sq0);
-        double k1 = stationary_from_sq(ep.kind, ep.outputscale, sq1);
-        double z0 = ((k0 - acc[i][j][0]) * ep.ystd2) / sdr;
-        double z1 = ((k1 - acc[i][j][1]) * ep.ystd2) / sdr;
-        if (row < ep.C) {
-          double* dst = ep.Z + (size_t)row * ep.ldz + col;
-          if (col + 1 < ep.N) {
-            *reinterpret_cast<double2*>(dst) = make_double2(z0, z1);
-          } else if (col < ep.N) {
-            dst[0] = z0;
-          }
-        }
+      for (int jp = 0; jp < 2; ++jp) {
+        const int lc0 = wn + (2 * jp) * 8 + q * 2;
+        const int col = n_base + lc0;
+        double* dst = (row < ep.C) ? ep.Z + (size_t)row * ep.ldz + col : nullptr;
+        cov_epilogue4(s_xr + lr * MAX_D, s_xc + lc0 * MAX_D, d, ep.kind, ep.outputscale, ep.ystd2,
+                      sdr, acc[i][2 * jp][0], acc[i][2 * jp][1], acc[i][2 * jp + 1][0],
+                      acc[i][2 * jp + 1][1], dst, col, ep.N);
       }
     }
   }
@@ -199,7 +218,7 @@ static int ensure_gemm_attr() {
 int gemm_store(const double* A, int lda, const double* B, int ldb, int M_pad, int N_pad, int K,
                double* D, int ldd, cudaStream_t st) {
   DKG_TRY(ensure_gemm_attr());
-  dim3 grid(N_pad / GEMM_BN, M_pad / GEMM_BM);
+  dim3 grid(N_pad / G_BN, M_pad / GEMM_BM);
   CovEpilogue ep{};
   dmma_gemm_kernel<false><<<grid, G_THREADS, GEMM_SMEM, st>>>(A, lda, B, ldb, K, D, ldd, ep);
   DKG_LAUNCH_CHECK();
@@ -209,7 +228,7 @@ int gemm_store(const double* A, int lda, const double* B, int ldb, int M_pad, in
 int gemm_cov(const double* KX, int lda, const double* B, int ldb, int M_pad, int N_pad, int K,
              const CovEpilogue& ep, cudaStream_t st) {
   DKG_TRY(ensure_gemm_attr());
-  dim3 grid(N_pad / GEMM_BN, M_pad / GEMM_BM);
+  dim3 grid(N_pad / G_BN, M_pad / GEMM_BM);
   dmma_gemm_kernel<true><<<grid, G_THREADS, GEMM_SMEM, st>>>(KX, lda, B, ldb, K, nullptr, 0, ep);
   DKG_LAUNCH_CHECK();
   return DKG_OK;

@@ -65,12 +65,30 @@ def test_c4_properties_and_spot_parity(c4):
         assert int(np.argmax(got)) == int(np.argmax(want))
 
 
-def test_c2_full_parity_and_objective_choice():
+def _cond(P):
+    """max over objectives of cond(K + noise I): rounding in the two Cholesky solves is amplified
+    by it, so oracle (LAPACK) and CUDA path can legitimately differ by ~cond * eps * |intercepts|
+    (SURVEY.md 7 'hard parts'; cond = 4.6e7 for objective 1 of the c2 problem)."""
+    from oracle import gp as ogp
+
+    out = 1.0
+    for o in oracle_model(P.model).models:
+        K = ogp.kernel_matrix(o, o.train_x, o.train_x) + o.noise * torch.eye(o.n, dtype=torch.double)
+        out = max(out, float(torch.linalg.cond(K)))
+    return out
+
+
+@pytest.mark.parametrize("noise", [None, (1e-2, 0.5)], ids=["survey-c2", "well-conditioned"])
+def test_c2_full_parity_and_objective_choice(noise):
     from decoupledbo_b200 import synthetic
     from decoupledbo_b200.modules.acquisition_optimisation_strategy import choose_best_objective
 
     P = synthetic.problem_c2(n_cand=64)
+    if noise is not None:
+        for o, nz in zip(P.model.models, noise):
+            o.noise = nz
     om = oracle_model(P.model)
+    cond = _cond(P)
     best, best_o = [], []
     for target in (0, 1):
         acq = _acqf(P, target)
@@ -78,7 +96,12 @@ def test_c2_full_parity_and_objective_choice():
             kg = acq(P.candidates.unsqueeze(1))
         want = odk.forward(om, P.candidates.unsqueeze(1), P.x_disc, P.weights, target, dense=False)
         scale = float(acq._get_plan().read("A0").abs().max())
-        np.testing.assert_allclose(kg.numpy(), want.numpy(), rtol=1e-9, atol=1e-12 * scale)
+        # fp64: rel 1e-9 + conditioning floor 16 * cond * eps * |intercepts| (1e-12 * scale when
+        # the problem is well conditioned)
+        atol = max(1e-12, 16 * cond * 2.2e-16) * scale
+        np.testing.assert_allclose(kg.numpy(), want.numpy(), rtol=1e-9, atol=atol)
+        if noise is not None:
+            assert atol <= 1e-9 * scale
         assert int(kg.argmax()) == int(want.argmax())  # bit-exact argmax candidate
         i = int(kg.argmax())
         best.append((target, P.candidates[i : i + 1], kg[i]))

@@ -68,7 +68,7 @@ static void dev_free(T*& p) {
 static void free_workspace(Workspace& w) {
   dev_free(w.X); dev_free(w.kg); dev_free(w.dX); dev_free(w.KX); dev_free(w.T); dev_free(w.var);
   dev_free(w.sd); dev_free(w.zown); dev_free(w.Xs); dev_free(w.a_new); dev_free(w.kg_terms);
-  dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } dev_free(w.ovf_sets); dev_free(w.ovf_count);
+  dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } { double4* t = (double4*)w.chain; dev_free(t); w.chain = nullptr; } dev_free(w.far); dev_free(w.ovf_sets); dev_free(w.ovf_count);
   dev_free(w.hull_cnt); dev_free(w.hull_idx); dev_free(w.hull_p); dev_free(w.hull_q);
   dev_free(w.amax_is_new); dev_free(w.stats);
   w.cap_C = w.chunk_C = 0;
@@ -109,6 +109,8 @@ static int ensure_workspace(dkg_plan* p, int C) {
   DKG_TRY(dev_alloc(&w.zarg, (size_t)chunk * 2));
   DKG_TRY(dev_alloc(&w.surv_cnt, (size_t)chunk * S));
   { SurvEntry* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * SURV_CAP, false)); w.surv = t; }
+  DKG_TRY(dev_alloc(&w.far, (size_t)chunk * S * 2));
+  { double4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S, false)); w.chain = t; }
   DKG_TRY(dev_alloc(&w.ovf_sets, (size_t)chunk * S, false));
   DKG_TRY(dev_alloc(&w.ovf_count, (size_t)1));
   DKG_TRY(dev_alloc(&w.hull_cnt, (size_t)cap * S));
@@ -304,9 +306,10 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     lb.NA = N; lb.NL = N + 1; lb.S = S; lb.C = cc;
     EmaxScratch sc;
     sc.zst = w.zst; sc.zarg = w.zarg; sc.surv_cnt = w.surv_cnt; sc.surv = (SurvEntry*)w.surv;
-    sc.ovf_sets = w.ovf_sets; sc.ovf_count = w.ovf_count;
+    sc.ovf_sets = w.ovf_sets; sc.ovf_count = w.ovf_count; sc.far = w.far; sc.chain = (double4*)w.chain;
     sc.stats = w.stats;
     DKG_CUDA_OK(cudaMemsetAsync(w.surv_cnt, 0, sizeof(int) * (size_t)cc * S, st));
+    DKG_CUDA_OK(cudaMemsetAsync(w.far, 0, sizeof(unsigned long long) * (size_t)cc * S * 2, st));
     DKG_CUDA_OK(cudaMemsetAsync(w.ovf_count, 0, sizeof(int), st));
     { ProfScope ps(5, st); DKG_TRY(emax_zstat(lb, sc, nullptr, nullptr, st)); }
     { ProfScope ps(6, st); DKG_TRY(emax_filter(lb, sc, st)); }
@@ -451,6 +454,8 @@ int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev, int32_t
   double *zst = nullptr, *amax = nullptr;
   int *zarg = nullptr, *aarg = nullptr, *scnt = nullptr, *oset = nullptr, *ocnt = nullptr;
   SurvEntry* surv = nullptr;
+  unsigned long long* far = nullptr;
+  double4* chain = nullptr;
   int rc = DKG_OK;
   auto A = [&](int r) { if (rc == DKG_OK) rc = r; };
   A(dev_alloc(&zst, (size_t)P * 2));
@@ -460,6 +465,8 @@ int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev, int32_t
   A(dev_alloc(&scnt, (size_t)P));
   A(dev_alloc(&surv, (size_t)P * SURV_CAP, false));
   A(dev_alloc(&oset, (size_t)P, false));
+  A(dev_alloc(&far, (size_t)P * 2));
+  A(dev_alloc(&chain, (size_t)P, false));
   A(dev_alloc(&ocnt, (size_t)1));
   if (rc == DKG_OK) {
     LineBatch lb;
@@ -470,7 +477,7 @@ int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev, int32_t
     lb.NA = L; lb.NL = L; lb.S = 1; lb.C = P;
     EmaxScratch sc;
     sc.zst = zst; sc.zarg = zarg; sc.surv_cnt = scnt; sc.surv = surv;
-    sc.ovf_sets = oset; sc.ovf_count = ocnt; sc.stats = nullptr;
+    sc.ovf_sets = oset; sc.ovf_count = ocnt; sc.far = far; sc.chain = chain; sc.stats = nullptr;
     EmaxOut out;
     out.terms = emax_dev; out.subtract_max = 0;
     out.hull_cnt = hull_count_dev;
@@ -489,7 +496,7 @@ int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev, int32_t
     rc = DKG_ECUDA;
   }
   dev_free(zst); dev_free(zarg); dev_free(amax); dev_free(aarg); dev_free(scnt); dev_free(surv);
-  dev_free(oset); dev_free(ocnt);
+  dev_free(oset); dev_free(ocnt); dev_free(far); dev_free(chain);
   return rc;
 }
 

@@ -25,6 +25,8 @@
 //                over the recorded hull vertices (one CTA per candidate).
 #include "dkg_emax.cuh"
 
+#include <cstdlib>
+
 namespace dkg {
 
 constexpr int E_THREADS = 256;
@@ -73,9 +75,12 @@ __device__ void block_arg_reduce(double& v, int& i, double* s_v, int* s_i) {
     }
 }
 
-// one CTA per row: min / max (with first index) of the slope row; optionally the max intercept
+__device__ double4 chain_params(const LineBatch& lb, const EmaxScratch& sc, int c, int j);
+
+// one CTA per row: min / max (with first index) of the slope row; optionally the max intercept;
+// then the chord-chain parameters of the row's S sets (consumed by the filter kernel)
 __global__ void __launch_bounds__(E_THREADS)
-zstat_kernel(LineBatch lb, double* __restrict__ zst, int* __restrict__ zarg,
+zstat_kernel(LineBatch lb, EmaxScratch sc, double* __restrict__ zst, int* __restrict__ zarg,
              double* __restrict__ amax_out, int* __restrict__ aarg_out) {
   __shared__ double s_v[E_THREADS / 32];
   __shared__ int s_i[E_THREADS / 32];
@@ -110,12 +115,15 @@ zstat_kernel(LineBatch lb, double* __restrict__ zst, int* __restrict__ zarg,
       aarg_out[c] = ai;
     }
   }
+  __syncthreads();  // the row statistics written above are read back through global memory
+  for (int j = threadIdx.x; j < lb.S; j += blockDim.x)
+    sc.chain[(size_t)c * lb.S + j] = chain_params(lb, sc, c, j);
 }
 
 int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int* aarg_out,
                cudaStream_t st) {
   if (lb.C == 0) return DKG_OK;
-  zstat_kernel<<<lb.C, E_THREADS, 0, st>>>(lb, sc.zst, sc.zarg, amax_out, aarg_out);
+  zstat_kernel<<<lb.C, E_THREADS, 0, st>>>(lb, sc, sc.zst, sc.zarg, amax_out, aarg_out);
   DKG_LAUNCH_CHECK();
   return DKG_OK;
 }
@@ -196,27 +204,80 @@ __device__ double4 chain_params(const LineBatch& lb, const EmaxScratch& sc, int 
 // per scalarisation it loads the chain parameters of the G sets once (shared-memory broadcast)
 // and the R intercepts once (coalesced, shared by the G candidates), and runs G*R tests of
 // 2 DFMA + DMNMX + DSETP each.  Survivors are rare (~1%) and appended with an atomic slot claim.
+__device__ __forceinline__ unsigned long long pack_excess(double e, int n) {
+  // e > 0: float bits are order preserving; only used to CHOOSE a seed -- any line above the
+  // chord is a valid chain vertex, so the float rounding is harmless
+  return ((unsigned long long)__float_as_uint((float)e) << 32) | (unsigned)n;
+}
+
+// Survivors are first collected in a CTA-local shared-memory pool (shared atomics are ~30 cycles;
+// a global atomicAdd whose return value is needed stalls the warp for a full L2 round trip, and
+// with ~5 survivors per warp per scalarisation that latency dominated the kernel: ncu,
+// profiles/r01_ncu_summary.md).  At the end the CTA claims one contiguous range per set with a
+// single global atomic and copies its entries out in parallel.
+constexpr int POOL_CAP = 2048;
+
+// store one survivor; returns its packed excess above its chord (0 if none) and the side
+__device__ __forceinline__ unsigned long long append_survivor(const LineBatch& lb, const EmaxScratch& sc,
+                                                              const double4& par, size_t set, int c,
+                                                              int j, int n, int pos, int* side_out) {
+  const double av = lb.A[(size_t)c * lb.a_sc + (size_t)j * lb.a_sj + n];
+  const double zv = lb.Z[(size_t)c * lb.ldz + n];
+  if (pos < SURV_CAP) {
+    SurvEntry e;
+    e.a = av; e.z = zv; e.idx = n; e.pad = 0;
+    sc.surv[set * SURV_CAP + pos] = e;
+  }
+  // the farthest survivor above each chord seeds the QuickHull refinement in the hull /
+  // overflow kernels (any survivor is a valid chain vertex)
+  const double t1 = fma(par.y, zv, par.x), t2 = fma(par.w, zv, par.z);
+  const int side = t1 <= t2 ? 0 : 1;
+  const double ex = av - (side == 0 ? t1 : t2);
+  *side_out = side;
+  return ex > 0.0 ? pack_excess(ex, n) : 0ull;
+}
+
 template <int G, int R, bool SHARED_A>
-__global__ void __launch_bounds__(E_THREADS, 2)
+__global__ void __launch_bounds__(E_THREADS, 3)
 filter_kernel(LineBatch lb, EmaxScratch sc) {
   extern __shared__ __align__(16) unsigned char e_smem[];
-  double4* s_par = reinterpret_cast<double4*>(e_smem);  // [S][G]
-  const int c0 = blockIdx.y * G;
   const int S = lb.S;
+  double4* s_par = reinterpret_cast<double4*>(e_smem);     // [S][G]
+  int* s_cnt = reinterpret_cast<int*>(s_par + G * S);      // [S*G] survivors pooled per set
+  int* s_base = s_cnt + G * S;                             // [S*G] claimed global range start
+  int* s_fill = s_base + G * S;                            // [S*G]
+  int2* s_pool = reinterpret_cast<int2*>(s_fill + G * S);  // [POOL_CAP] (line, local set)
+  unsigned long long* s_far = reinterpret_cast<unsigned long long*>(s_pool + POOL_CAP);  // [S*G][2]
+  __shared__ int s_pool_n;
+  const int c0 = blockIdx.y * G;
   for (int e = threadIdx.x; e < G * S; e += blockDim.x) {
     const int j = e / G, g = e - j * G;
     const int c = c0 + g;
-    s_par[e] = (c < lb.C) ? chain_params(lb, sc, c, j) : make_double4(INFINITY, 0.0, INFINITY, 0.0);
+    s_par[e] = (c < lb.C) ? sc.chain[(size_t)c * S + j] : make_double4(INFINITY, 0.0, INFINITY, 0.0);
+    s_cnt[e] = 0;
+    s_fill[e] = 0;
+    s_far[2 * e] = 0ull;
+    s_far[2 * e + 1] = 0ull;
   }
-  const int lo = blockIdx.x * (E_THREADS * R) + threadIdx.x;
+  if (threadIdx.x == 0) s_pool_n = 0;
+  // lines of this thread; out-of-range slots alias the last line (a duplicate survivor is
+  // harmless to the exact march, and it keeps the loop free of bounds predicates)
+  int nc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    nc[r] = min(blockIdx.x * (E_THREADS * R) + r * E_THREADS + (int)threadIdx.x, lb.NA - 1);
   double z[G][R];
 #pragma unroll
-  for (int g = 0; g < G; ++g)
+  for (int g = 0; g < G; ++g) {
+    const int c = min(c0 + g, lb.C - 1);
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int n = lo + r * E_THREADS;
-      z[g][r] = (c0 + g < lb.C && n < lb.NA) ? lb.Z[(size_t)(c0 + g) * lb.ldz + n] : 0.0;
-    }
+    for (int r = 0; r < R; ++r) z[g][r] = lb.Z[(size_t)c * lb.ldz + nc[r]];
+  }
+  double a_nx[R];  // intercepts of the NEXT scalarisation (software prefetch, SHARED_A only)
+  if (SHARED_A) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) a_nx[r] = lb.A[nc[r]];
+  }
   __syncthreads();
 
   for (int j = 0; j < S; ++j) {
@@ -225,15 +286,14 @@ filter_kernel(LineBatch lb, EmaxScratch sc) {
     for (int g = 0; g < G; ++g) p[g] = s_par[j * G + g];
     double a[R];
     if (SHARED_A) {
+      const double* nxt = lb.A + (size_t)min(j + 1, S - 1) * lb.a_sj;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int n = lo + r * E_THREADS;
-        a[r] = (n < lb.NA) ? lb.A[(size_t)j * lb.a_sj + n] : -INFINITY;
+        a[r] = a_nx[r];
+        a_nx[r] = nxt[nc[r]];
       }
     }
-    // branch-free tests -> bit mask (bit g*R + r); the rare survivors are appended afterwards by
-    // ONE copy of the append code, which re-reads its two values from memory (cheaper than
-    // selecting them out of the register arrays).  a > min(l1, l2)  <=>  a > l1 or a > l2.
+    // branch-free tests -> bit mask (bit g*R + r).  a > min(l1, l2)  <=>  a > l1 or a > l2.
     unsigned mask = 0u;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -241,32 +301,63 @@ filter_kernel(LineBatch lb, EmaxScratch sc) {
       for (int r = 0; r < R; ++r) {
         double av;
         if (SHARED_A) av = a[r];
-        else {
-          const int n = lo + r * E_THREADS;
-          av = (c0 + g < lb.C && n < lb.NA)
-                   ? lb.A[(size_t)(c0 + g) * lb.a_sc + (size_t)j * lb.a_sj + n] : -INFINITY;
-        }
+        else av = lb.A[(size_t)min(c0 + g, lb.C - 1) * lb.a_sc + (size_t)j * lb.a_sj + nc[r]];
         const double t1 = fma(p[g].y, z[g][r], p[g].x);
         const double t2 = fma(p[g].w, z[g][r], p[g].z);
         if ((av > t1) | (av > t2)) mask |= 1u << (g * R + r);
       }
     }
-    while (mask) {
+    while (mask) {  // rare: ~1 % of the tests
       const int bit = __ffs(mask) - 1;
       mask &= mask - 1u;
       const int g = bit / R, r = bit - g * R;
-      const int n = lo + r * E_THREADS;
-      const int c = c0 + g;
-      const size_t set = (size_t)c * S + j;
-      const int pos = atomicAdd(&sc.surv_cnt[set], 1);
-      if (pos < SURV_CAP) {
-        SurvEntry e;
-        e.a = lb.A[(size_t)c * lb.a_sc + (size_t)j * lb.a_sj + n];
-        e.z = lb.Z[(size_t)c * lb.ldz + n];
-        e.idx = n;
-        e.pad = 0;
-        sc.surv[set * SURV_CAP + pos] = e;
+      int n = nc[0];
+#pragma unroll
+      for (int rr = 1; rr < R; ++rr)
+        if (rr == r) n = nc[rr];
+      const int setl = j * G + g;
+      const int pp = atomicAdd(&s_pool_n, 1);
+      if (pp < POOL_CAP) {
+        s_pool[pp] = make_int2(n, setl);
+        atomicAdd(&s_cnt[setl], 1);
+      } else {  // pool full (very dense survivors): claim a global slot directly
+        const int c = c0 + g;
+        const size_t set = (size_t)c * S + j;
+        int side;
+        const unsigned long long key =
+            append_survivor(lb, sc, s_par[setl], set, c, j, n, atomicAdd(&sc.surv_cnt[set], 1), &side);
+        if (key) atomicMax(&s_far[2 * setl + side], key);
       }
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < G * S; e += blockDim.x) {
+    const int k = s_cnt[e];
+    if (k > 0) {
+      const int j = e / G, g = e - j * G;
+      s_base[e] = atomicAdd(&sc.surv_cnt[(size_t)(c0 + g) * S + j], k);
+    }
+  }
+  __syncthreads();
+  const int np = min(s_pool_n, POOL_CAP);
+  for (int e = threadIdx.x; e < np; e += blockDim.x) {
+    const int2 it = s_pool[e];
+    const int setl = it.y;
+    const int j = setl / G, g = setl - j * G;
+    const int c = c0 + g;
+    const int pos = s_base[setl] + atomicAdd(&s_fill[setl], 1);
+    int side;
+    const unsigned long long key =
+        append_survivor(lb, sc, s_par[setl], (size_t)c * S + j, c, j, it.x, pos, &side);
+    if (key) atomicMax(&s_far[2 * setl + side], key);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * G * S; e += blockDim.x) {
+    const unsigned long long key = s_far[e];
+    if (key) {
+      const int setl = e >> 1;
+      const int j = setl / G, g = setl - j * G;
+      atomicMax(&sc.far[((size_t)(c0 + g) * S + j) * 2 + (e & 1)], key);
     }
   }
 }
@@ -274,7 +365,8 @@ filter_kernel(LineBatch lb, EmaxScratch sc) {
 template <int G, int R>
 static int launch_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st) {
   dim3 grid(ceil_div(lb.NA, E_THREADS * R), ceil_div(lb.C, G));
-  const size_t smem = (size_t)G * lb.S * sizeof(double4);
+  const size_t smem = (size_t)G * lb.S * (sizeof(double4) + 3 * sizeof(int) + 2 * sizeof(unsigned long long)) +
+                      POOL_CAP * sizeof(int2);
   if (lb.a_sc == 0)
     filter_kernel<G, R, true><<<grid, E_THREADS, smem, st>>>(lb, sc);
   else
@@ -285,10 +377,11 @@ static int launch_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_
 
 int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st) {
   if (lb.C == 0 || lb.NA == 0) return DKG_OK;
-  // big batches: 8 lines per thread (fewer parameter loads per test); small ones: more CTAs
-  const long long ctas8 = (long long)ceil_div(lb.C, 4) * ceil_div(lb.NA, E_THREADS * 8);
-  if (ctas8 >= 2 * 148) return launch_filter<4, 8>(lb, sc, st);
-  return launch_filter<4, 2>(lb, sc, st);
+  // big batches: 4 lines per thread (fewer parameter loads per test); small ones: more CTAs
+  const long long ctas4 = (long long)ceil_div(lb.C, 4) * ceil_div(lb.NA, E_THREADS * 4);
+  if (getenv("DKG_FILTER_G8") && ctas4 >= 3 * 148) return launch_filter<8, 2>(lb, sc, st);
+  if (ctas4 >= 3 * 148) return launch_filter<4, 4>(lb, sc, st);
+  return launch_filter<4, 1>(lb, sc, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -476,7 +569,7 @@ __device__ __forceinline__ bool higher_intercept(const Line& p, const Line& q) {
 // ------------------------------------------------------------------------------------------
 // hull kernel: one warp per set
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(E_THREADS)
+__global__ void __launch_bounds__(E_THREADS, 3)
 hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
   __shared__ double s_a[E_THREADS / 32][STAGE_CAP];
   __shared__ double s_b[E_THREADS / 32][STAGE_CAP];
@@ -530,49 +623,25 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
     r = warp_march(total, fetch_global, rec);
   } else {
     // ---- one QuickHull-style refinement over the list, compacting into shared memory ----
-    // chain in the (b, a) plane: P (min slope), T (max intercept), Q (max slope)
-    Line P = empty_line(), Q = empty_line(), T = empty_line();
-    for (int k = lane; k < total; k += 32) {
-      const Line L = fetch_global(k);
-      if (P.idx < 0 || sorted_before(L, P)) P = L;
-      if (Q.idx < 0 || higher_slope(L, Q)) Q = L;
-      if (T.idx < 0 || higher_intercept(L, T)) T = L;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      Line oth = shfl_line(P, o);
-      if (oth.idx >= 0 && (P.idx < 0 || sorted_before(oth, P))) P = oth;
-      oth = shfl_line(Q, o);
-      if (oth.idx >= 0 && (Q.idx < 0 || higher_slope(oth, Q))) Q = oth;
-      oth = shfl_line(T, o);
-      if (oth.idx >= 0 && (T.idx < 0 || higher_intercept(oth, T))) T = oth;
-    }
+    // chain in the (b, a) plane: P (min slope), T (max intercept), Q (max slope) plus the
+    // farthest late survivors F1 / F2 recorded by the filter (any set member is a valid vertex)
+    const bool posw = !(w < 0.0);
+    const Line P = gather_line(lb, c, j, w, posw ? s.iP : s.iQ);
+    const Line Q = gather_line(lb, c, j, w, posw ? s.iQ : s.iP);
+    const Line T = gather_line(lb, c, j, w, s.iT);
+    const unsigned long long f1 = sc.far[set * 2 + 0], f2 = sc.far[set * 2 + 1];
+    Line F1 = f1 ? gather_line(lb, c, j, w, (int)(f1 & 0xffffffffull)) : empty_line();
+    Line F2 = f2 ? gather_line(lb, c, j, w, (int)(f2 & 0xffffffffull)) : empty_line();
     const bool hasL = T.b > P.b, hasR = Q.b > T.b;
+    if (!(hasL && F1.idx >= 0 && F1.b > P.b && F1.b < T.b)) F1 = empty_line();
+    if (!(hasR && F2.idx >= 0 && F2.b > T.b && F2.b < Q.b)) F2 = empty_line();
     Chord cl, cr;
     cl.b0 = cl.a0 = cl.m = cl.slack = 0.0;
     cr = cl;
     if (hasL) cl.set(P, T);
     if (hasR) cr.set(T, Q);
-    // farthest line above each chord
-    Line F1 = empty_line(), F2 = empty_line();
-    double e1 = 0.0, e2 = 0.0;
-    for (int k = lane; k < total; k += 32) {
-      const Line L = fetch_global(k);
-      if (hasL && L.b > P.b && L.b < T.b) {
-        const double e = cl.excess(L);
-        if (e > e1 || (e == e1 && e > 0.0 && L.ref < F1.ref)) { e1 = e; F1 = L; }
-      } else if (hasR && L.b > T.b && L.b < Q.b) {
-        const double e = cr.excess(L);
-        if (e > e2 || (e == e2 && e > 0.0 && L.ref < F2.ref)) { e2 = e; F2 = L; }
-      }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      Line oth = shfl_line(F1, o);
-      double oe = __shfl_xor_sync(0xffffffffu, e1, o);
-      if (oth.idx >= 0 && (oe > e1 || (oe == e1 && oth.ref < F1.ref))) { e1 = oe; F1 = oth; }
-      oth = shfl_line(F2, o);
-      oe = __shfl_xor_sync(0xffffffffu, e2, o);
-      if (oth.idx >= 0 && (oe > e2 || (oe == e2 && oth.ref < F2.ref))) { e2 = oe; F2 = oth; }
-    }
+    if (F1.idx >= 0 && !(cl.excess(F1) > 0.0)) F1 = empty_line();  // keep the chain concave
+    if (F2.idx >= 0 && !(cr.excess(F2) > 0.0)) F2 = empty_line();
     // refined chain: P [F1] T [F2] Q  -> up to 4 chords
     Chord ch[4];
     double lo_b[4], hi_b[4];
@@ -661,12 +730,7 @@ int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cu
 constexpr int OVF_MAXV = 130;  // chain vertices
 constexpr int FIN_RMAX = 1024; // hull records per candidate merged in shared memory
 constexpr int OVF_ROUNDS = 6;
-
-__device__ __forceinline__ unsigned long long pack_excess(double e, int n) {
-  // e > 0: float bits are order preserving; only used to CHOOSE a seed -- any line above the
-  // chord is a valid chain vertex, so the float rounding is harmless
-  return ((unsigned long long)__float_as_uint((float)e) << 32) | (unsigned)n;
-}
+constexpr int OVF_CTAS_PER_SM = 4;
 
 // index k of the chain vertex with the largest v_b[k] <= b  (requires b >= v_b[0])
 __device__ __forceinline__ int chain_locate(const double* v_b, int nv, double b) {
@@ -678,7 +742,7 @@ __device__ __forceinline__ int chain_locate(const double* v_b, int nv, double b)
   return lo;
 }
 
-__global__ void __launch_bounds__(E_THREADS)
+__global__ void __launch_bounds__(E_THREADS, OVF_CTAS_PER_SM)
 overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
   __shared__ double v_b[OVF_MAXV], v_a[OVF_MAXV], v_m[OVF_MAXV], v_slack[OVF_MAXV];
   __shared__ int v_idx[OVF_MAXV];
@@ -709,14 +773,28 @@ overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
       const Line Q = gather_line(lb, c, j, w, pos ? s.iQ : s.iP);
       const Line T = gather_line(lb, c, j, w, s.iT);
       int nv = 0;
-      const Line vs[3] = {P, T, Q};
-      for (int v = 0; v < 3; ++v) {
+      const unsigned long long f1 = sc.far[set * 2 + 0], f2 = sc.far[set * 2 + 1];
+      const Line F1 = f1 ? gather_line(lb, c, j, w, (int)(f1 & 0xffffffffull)) : empty_line();
+      const Line F2 = f2 ? gather_line(lb, c, j, w, (int)(f2 & 0xffffffffull)) : empty_line();
+      const Line vs[5] = {P, F1, T, F2, Q};
+      for (int v = 0; v < 5; ++v) {
         const Line& L = vs[v];
+        if (L.idx < 0) continue;
+        if ((v == 1 && !(L.b > P.b && L.b < T.b)) || (v == 3 && !(L.b > T.b && L.b < Q.b))) continue;
         if (nv > 0 && L.b <= v_b[nv - 1]) {  // same slope: keep the higher line
           if (L.b == v_b[nv - 1] && L.a > v_a[nv - 1]) { v_a[nv - 1] = L.a; v_idx[nv - 1] = L.idx; }
           continue;
         }
         v_b[nv] = L.b; v_a[nv] = L.a; v_idx[nv] = L.idx; ++nv;
+      }
+      // drop an inserted seed that is not above the chord of its neighbours (chain must be concave)
+      for (int k = 1; k + 1 < nv;) {
+        const double m = (v_a[k + 1] - v_a[k - 1]) / (v_b[k + 1] - v_b[k - 1]);
+        const bool is_t = v_idx[k] == T.idx;
+        if (!is_t && !(v_a[k] > fma(m, v_b[k] - v_b[k - 1], v_a[k - 1]))) {
+          for (int q2 = k; q2 + 1 < nv; ++q2) { v_b[q2] = v_b[q2 + 1]; v_a[q2] = v_a[q2 + 1]; v_idx[q2] = v_idx[q2 + 1]; }
+          --nv;
+        } else ++k;
       }
       s_nv = nv;
     }
@@ -896,7 +974,7 @@ overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
 int emax_overflow(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cudaStream_t st) {
   if (lb.C == 0) return DKG_OK;
   long long sets = (long long)lb.C * lb.S;
-  int grid = (int)(sets < 2 * 148 ? sets : 2 * 148);
+  int grid = (int)(sets < OVF_CTAS_PER_SM * 148 ? sets : OVF_CTAS_PER_SM * 148);
   overflow_kernel<<<grid, E_THREADS, 0, st>>>(lb, sc, out);
   DKG_LAUNCH_CHECK();
   return DKG_OK;

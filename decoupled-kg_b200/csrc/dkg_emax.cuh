@@ -38,8 +38,11 @@ struct SurvEntry {
 struct EmaxScratch {
   double* zst = nullptr;        // [C, 2] min / max of the slope row
   int* zarg = nullptr;          // [C, 2] their first indices
+  double4* chain = nullptr;     // [C, S] chord-chain parameters of every set (zstat -> filter)
   int* surv_cnt = nullptr;      // [C, S]  lines that passed the filter (may exceed SURV_CAP)
   SurvEntry* surv = nullptr;    // [C, S, SURV_CAP]
+  unsigned long long* far = nullptr;  // [C, S, 2] farthest late survivor above the left / right
+                                      // chord, packed (float excess << 32 | line); 0 = none
   int* ovf_sets = nullptr;      // [C * S] queue of sets for the cooperative kernel
   int* ovf_count = nullptr;     // [1]
   long long* stats = nullptr;   // [8] (optional)

@@ -12,9 +12,10 @@
 // fragments, 32 fp64 accumulators per thread) so that TWO CTAs fit per SM: while one CTA runs
 // its kernel-evaluation epilogue the other keeps the DMMA pipe busy.  3-stage cp.async pipeline;
 // shared-memory rows padded (+4 doubles) so every fragment load is bank-conflict free.  The
-// epilogue's kernel evaluations live in a non-inlined device function: inlining them 32x made
-// the epilogue ~150 KB of straight-line code and the SM stalled on instruction fetch (ncu:
-// stall_no_instruction 3.1 per issue, profiles/r01_ncu_summary.md).
+// epilogue first parks the accumulators in shared memory, then runs as a ROLLED loop (4 rows = 8
+// kernel evaluations in flight per thread) with coalesced 512-byte row stores: fully unrolling it
+// over the fragments made ~150 KB of straight-line code and the SM stalled on instruction fetch
+// (ncu: stall_no_instruction 3.1 per issue, profiles/r01_ncu_summary.md).
 #include "dkg_kernels.cuh"
 
 namespace dkg {
@@ -24,9 +25,12 @@ constexpr int G_STAGES = 3;
 constexpr int G_BN = 64;             // columns per CTA tile (GEMM_BN = 128 is the padding unit)
 constexpr int LDA_S = GEMM_BK + 4;   // 20 doubles: rows land on distinct bank groups
 constexpr int LDB_S = G_BN + 4;      // 68 doubles
+constexpr int LDC_S = G_BN + 8;      // 72 doubles: accumulator staging, conflict-free double2 stores
 constexpr int A_STAGE = GEMM_BM * LDA_S;
 constexpr int B_STAGE = GEMM_BK * LDB_S;
-constexpr size_t GEMM_SMEM = (size_t)G_STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+constexpr size_t GEMM_SMEM_PIPE = (size_t)G_STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+constexpr size_t GEMM_SMEM_EPI = (size_t)(GEMM_BM * LDC_S + GEMM_BM * MAX_D + GEMM_BM) * sizeof(double);
+constexpr size_t GEMM_SMEM = GEMM_SMEM_PIPE > GEMM_SMEM_EPI ? GEMM_SMEM_PIPE : GEMM_SMEM_EPI;
 static_assert(GEMM_BN % G_BN == 0, "padding unit must be a multiple of the CTA tile width");
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -44,36 +48,6 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
       "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
       : "+d"(d0), "+d"(d1)
       : "d"(a), "d"(b));
-}
-
-// Four outputs of one accumulator row (fragment pair: columns lc0, lc0+1, lc0+8, lc0+9 of the
-// tile): kernel value minus the contraction, scaled, divided by the predictive sd, stored to the
-// slope buffer.  Kept out of line on purpose (see header); takes no pointers to locals.
-__device__ __noinline__ void cov_epilogue4(const double* __restrict__ xr, const double* __restrict__ xc0,
-                                           int d, int kind, double outputscale, double ystd2,
-                                           double sdr, double acc0, double acc1, double acc2,
-                                           double acc3, double* __restrict__ dst, int col, int N) {
-  double sq0 = 0.0, sq1 = 0.0, sq2 = 0.0, sq3 = 0.0;
-  for (int k = 0; k < d; ++k) {
-    const double x = xr[k];
-    const double d0 = x - xc0[k];
-    const double d1 = x - xc0[MAX_D + k];
-    const double d2 = x - xc0[8 * MAX_D + k];
-    const double d3 = x - xc0[9 * MAX_D + k];
-    sq0 += d0 * d0;
-    sq1 += d1 * d1;
-    sq2 += d2 * d2;
-    sq3 += d3 * d3;
-  }
-  const double z0 = ((stationary_from_sq(kind, outputscale, sq0) - acc0) * ystd2) / sdr;
-  const double z1 = ((stationary_from_sq(kind, outputscale, sq1) - acc1) * ystd2) / sdr;
-  const double z2 = ((stationary_from_sq(kind, outputscale, sq2) - acc2) * ystd2) / sdr;
-  const double z3 = ((stationary_from_sq(kind, outputscale, sq3) - acc3) * ystd2) / sdr;
-  if (dst == nullptr) return;
-  if (col + 1 < N) *reinterpret_cast<double2*>(dst) = make_double2(z0, z1);
-  else if (col < N) dst[0] = z0;
-  if (col + 9 < N) *reinterpret_cast<double2*>(dst + 8) = make_double2(z2, z3);
-  else if (col + 8 < N) dst[8] = z2;
 }
 
 template <bool COV>
@@ -167,36 +141,64 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
     }
     return;
   } else {
-    // stage the scaled coordinates of this tile's candidates and discretisation points
-    double* s_xr = smem;                          // [128][MAX_D]
-    double* s_xc = smem + GEMM_BM * MAX_D;        // [64][MAX_D]
-    double* s_sd = s_xc + G_BN * MAX_D;           // [128]
+    // ---- epilogue: accumulators -> shared memory (the pipeline buffers are free now), then every
+    // warp finishes whole rows: lane l owns columns 2l, 2l+1, so each row is one coalesced 512-byte
+    // store and the kernel evaluations of 4 rows (8 outputs) are in flight per thread ----
+    double* s_acc = smem;                               // [128][LDC_S]
+    double* s_xr = smem + GEMM_BM * LDC_S;              // [128][MAX_D] candidates / lengthscale
+    double* s_sd = s_xr + GEMM_BM * MAX_D;              // [128] 1 / sd
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<double2*>(s_acc + (wm + i * 8 + g) * LDC_S + wn + j * 8 + q * 2) =
+            make_double2(acc[i][j][0], acc[i][j][1]);
     const int d = ep.d;
     for (int e = tid; e < GEMM_BM * MAX_D; e += G_THREADS) {
       int r = e / MAX_D, k = e - r * MAX_D;
       s_xr[e] = (k < d && m_base + r < ep.C) ? ep.xs[(size_t)(m_base + r) * d + k] : 0.0;
     }
-    for (int e = tid; e < G_BN * MAX_D; e += G_THREADS) {
-      int r = e / MAX_D, k = e - r * MAX_D;
-      s_xc[e] = (k < d) ? ep.xd_s[(size_t)(n_base + r) * d + k] : 0.0;
-    }
     for (int e = tid; e < GEMM_BM; e += G_THREADS)
       s_sd[e] = (m_base + e < ep.C) ? ep.sd[m_base + e] : 1.0;
+    // this thread's two discretisation points (scaled coordinates), fixed for all rows
+    const int col = n_base + lane * 2;
+    double xc0[MAX_D], xc1[MAX_D];
+#pragma unroll
+    for (int k = 0; k < MAX_D; ++k) {
+      xc0[k] = (k < d) ? ep.xd_s[(size_t)col * d + k] : 0.0;
+      xc1[k] = (k < d) ? ep.xd_s[(size_t)(col + 1) * d + k] : 0.0;
+    }
     __syncthreads();
-
+    const int kind = ep.kind;
+    const double os = ep.outputscale, ystd2 = ep.ystd2;
+#pragma unroll 1
+    for (int rg = 0; rg < GEMM_BM / 8 / 4; ++rg) {  // 4 rows per iteration, rows warp + 8 * (..)
+      double z0[4], z1[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int lr = wm + i * 8 + g;
-      const int row = m_base + lr;
-      const double sdr = s_sd[lr];
+      for (int u = 0; u < 4; ++u) {
+        const int lr = warp + 8 * (rg * 4 + u);
+        double sq0 = 0.0, sq1 = 0.0;
 #pragma unroll
-      for (int jp = 0; jp < 2; ++jp) {
-        const int lc0 = wn + (2 * jp) * 8 + q * 2;
-        const int col = n_base + lc0;
-        double* dst = (row < ep.C) ? ep.Z + (size_t)row * ep.ldz + col : nullptr;
-        cov_epilogue4(s_xr + lr * MAX_D, s_xc + lc0 * MAX_D, d, ep.kind, ep.outputscale, ep.ystd2,
-                      sdr, acc[i][2 * jp][0], acc[i][2 * jp][1], acc[i][2 * jp + 1][0],
-                      acc[i][2 * jp + 1][1], dst, col, ep.N);
+        for (int k = 0; k < MAX_D; ++k)
+          if (k < d) {
+            const double x = s_xr[lr * MAX_D + k];
+            const double d0 = x - xc0[k], d1 = x - xc1[k];
+            sq0 += d0 * d0;
+            sq1 += d1 * d1;
+          }
+        const double2 a2 = *reinterpret_cast<const double2*>(s_acc + lr * LDC_S + lane * 2);
+        const double sdr = s_sd[lr];
+        z0[u] = ((stationary_from_sq(kind, os, sq0) - a2.x) * ystd2) / sdr;
+        z1[u] = ((stationary_from_sq(kind, os, sq1) - a2.y) * ystd2) / sdr;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int row = m_base + warp + 8 * (rg * 4 + u);
+        if (row < ep.C) {
+          double* dst = ep.Z + (size_t)row * ep.ldz + col;
+          if (col + 1 < ep.N) *reinterpret_cast<double2*>(dst) = make_double2(z0[u], z1[u]);
+          else if (col < ep.N) dst[0] = z0[u];
+        }
       }
     }
   }

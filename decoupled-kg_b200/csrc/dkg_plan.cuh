@@ -37,8 +37,10 @@ struct Workspace {
   double* Z = nullptr;      // [chunk_C, ldz]    slopes cov/sd; column N = candidate's own line
   double* zst = nullptr;    // [chunk_C, 2]      min / max of the slope row
   int* zarg = nullptr;      // [chunk_C, 2]      argmin, argmax of the slope row
+  void* chain = nullptr;    // [chunk_C, S] double4 chord-chain parameters
   int* surv_cnt = nullptr;  // [chunk_C, S]      chord-filter survivors per (candidate, scal.)
   void* surv = nullptr;     // [chunk_C, S, SURV_CAP] SurvEntry (intercept, slope, index)
+  unsigned long long* far = nullptr;  // [chunk_C, S, 2] farthest late survivors (chain seeds)
   int* ovf_sets = nullptr;  // [chunk_C * S] queue of sets for the cooperative kernel
   int* ovf_count = nullptr; // [1]
   int* hull_cnt = nullptr;  // [cap_C, S]

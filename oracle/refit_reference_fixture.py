@@ -1,0 +1,129 @@
+"""ORACLE support: try to re-derive the fitted model behind the reference's GP-level goldens.
+
+The reference's tests (tests/modules/acquisition/conftest.py:30-47) build a 2-objective
+ModelListGP(SingleTaskGP, SingleTaskGP) on 10 scrambled-Sobol points (seed 1234) with
+torch.randn targets (global seed 1234) and FIT it with botorch.fit_gpytorch_mll; the goldens
+(test_discretekg.py:62, 78, 93, 107) depend on that MAP fit, whose hyper-parameters are not
+stored anywhere.  botorch/gpytorch are absent here, so this script restates the fit
+[BoTorch @ c14808f / GPyTorch 1.11 defaults, recalled]:
+
+  SingleTaskGP defaults: ConstantMean; ScaleKernel(Matern-5/2 ARD, lengthscale ~ Gamma(3, 6),
+  outputscale ~ Gamma(2, 0.15)); GaussianLikelihood(noise ~ Gamma(1.1, 0.05), noise >= 1e-4,
+  initial noise 2.0); no outcome transform.  Objective = sum over models of
+  -(log N(y | c, K + noise I) + log priors) / n, minimised with scipy L-BFGS-B from
+  raw parameters 0 (softplus -> 0.693), constant 0.
+
+and then evaluates the reference's four goldens with the oracle.  Prints the comparison; the
+result is recorded in DESIGN.md section 5.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import discretekg as odk  # noqa: E402
+from oracle import gp as ogp  # noqa: E402
+
+torch.set_default_dtype(torch.double)
+
+
+def make_data():
+    torch.manual_seed(1234)
+    eng = torch.quasirandom.SobolEngine(2, scramble=True, seed=1234)
+    train_x = eng.draw(10, dtype=torch.double)
+    train_y = torch.randn(10, 2)
+    return train_x, train_y
+
+
+def gamma_logp(x, conc, rate):
+    return conc * math.log(rate) + (conc - 1.0) * torch.log(x) - rate * x - math.lgamma(conc)
+
+
+def neg_mll(params, x, y, fixed_noise=None):
+    raw_ls, raw_os, const, noise = params[:2], params[2], params[3], params[4]
+    ls = torch.nn.functional.softplus(raw_ls)
+    os_ = torch.nn.functional.softplus(raw_os)
+    if fixed_noise is not None:
+        noise = torch.tensor(fixed_noise)
+    obj = ogp.OracleObjective(train_x=x, train_y=y, lengthscale=ls.detach(), outputscale=1.0,
+                              mean_const=0.0, noise=0.0)
+    obj.lengthscale = ls  # keep the graph
+    K = os_ * ogp.kernel_matrix(obj, x, x) + noise * torch.eye(len(x))
+    L = torch.linalg.cholesky(K)
+    r = (y - const).unsqueeze(-1)
+    sol = torch.cholesky_solve(r, L)
+    ll = -0.5 * ((r * sol).sum() + 2.0 * torch.log(torch.diagonal(L)).sum() + len(x) * math.log(2 * math.pi))
+    lp = gamma_logp(ls, 3.0, 6.0).sum() + gamma_logp(os_, 2.0, 0.15)
+    if fixed_noise is None:
+        lp = lp + gamma_logp(noise, 1.1, 0.05)
+    return -(ll + lp) / len(x)
+
+
+def fit(x, Y, fixed_noise=None):
+    from scipy.optimize import minimize
+
+    def fun(p_np):
+        p = torch.tensor(p_np, requires_grad=True)
+        loss = sum(neg_mll(p[5 * m: 5 * m + 5], x, Y[:, m], fixed_noise) for m in range(2))
+        (g,) = torch.autograd.grad(loss, p)
+        return float(loss.detach()), g.numpy()
+
+    p0 = np.array([0.0, 0.0, 0.0, 0.0, 2.0] * 2)
+    bounds = [(None, None)] * 4 + [(1e-4, None)]
+    res = minimize(fun, p0, jac=True, method="L-BFGS-B", bounds=bounds * 2,
+                   options=dict(maxiter=2000, ftol=1e-15, gtol=1e-10))
+    return res
+
+
+def build_model(p, x, Y, fixed_noise=None):
+    objs = []
+    for m in range(2):
+        q = torch.tensor(p[5 * m: 5 * m + 5])
+        objs.append(ogp.OracleObjective(
+            train_x=x, train_y=Y[:, m], lengthscale=torch.nn.functional.softplus(q[:2]),
+            outputscale=float(torch.nn.functional.softplus(q[2])), mean_const=float(q[3]),
+            noise=float(q[4]) if fixed_noise is None else fixed_noise))
+    return ogp.OracleModelList(objs)
+
+
+def main():
+    x, Y = make_data()
+    print("train_x[:3] =", x[:3].tolist())
+    print("train_y[:3] =", Y[:3].tolist())
+    res = fit(x, Y)
+    print("fit:", res.message, "loss", res.fun, "nit", res.nit)
+    model = build_model(res.x, x, Y)
+    for m, o in enumerate(model.models):
+        print(f" obj {m}: ls={o.lengthscale.tolist()} os={o.outputscale:.6f} c={o.mean_const:.6f} noise={o.noise:.6g}")
+    n = 3
+    disc = torch.stack([torch.repeat_interleave(torch.linspace(0, 1, n), n),
+                        torch.tile(torch.linspace(0, 1, n), (n,))]).T
+    W = torch.tensor([[0.7, 0.3], [0.6, 0.4], [0.5, 0.5]])
+    target_x = torch.tensor([[[[0.5, 0.5]], [[0, 1]], [[0, 0.5]]], [[[0, 0]], [[1, 0]], [[0.5, 0]]]])
+    dec = odk.forward(model, target_x, disc, W, 0)
+    cpl = odk.forward(model, target_x, disc, W, None)
+    print("decoupled (obj 0):", np.round(dec.numpy(), 4).tolist(), " golden [[0.0297, 0.0084, 0.0048], [0.0002, 0.0030, 0.0006]]")
+    print("coupled          :", np.round(cpl.numpy(), 4).tolist(), " golden [[0.0383, 0.0224, 0.0130], [0.0005, 0.0058, 0.0015]]")
+    print("scalar decoupled :", float(dec[0, 0]), " golden 0.02968190595713936")
+    print("scalar coupled   :", float(cpl[0, 0]), " golden 0.038261974207699244")
+    out = os.path.join(ROOT, "tests", "golden", "reference_fixture_refit.npz")
+    np.savez_compressed(
+        out, train_x=x.numpy(), train_y=Y.numpy(),
+        lengthscale=np.stack([o.lengthscale.numpy() for o in model.models]),
+        outputscale=np.array([o.outputscale for o in model.models]),
+        mean_const=np.array([o.mean_const for o in model.models]),
+        noise=np.array([o.noise for o in model.models]),
+        golden_decoupled_obj0=np.array([[0.0297, 0.0084, 0.0048], [0.0002, 0.0030, 0.0006]]),
+        golden_coupled=np.array([[0.0383, 0.0224, 0.0130], [0.0005, 0.0058, 0.0015]]),
+        golden_scalar_decoupled_obj0=np.array(0.02968190595713936),
+        golden_scalar_coupled=np.array(0.038261974207699244),
+    )
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    main()

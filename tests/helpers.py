@@ -52,3 +52,22 @@ def load_golden(name):
     import os
 
     return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+
+
+def refit_reference_problem():
+    """The reference's own test fixture (tests/modules/acquisition/conftest.py:30-47: 10 Sobol
+    points, randn targets, MAP-fitted SingleTaskGPs) re-derived by oracle/refit_reference_fixture.py,
+    together with the reference's golden KG values for it (test_discretekg.py:62,78,93,107)."""
+    from decoupledbo_b200.gp_state import GPModelList, GPObjective
+
+    G = load_golden("reference_fixture_refit.npz")
+    objs = [GPObjective(train_x=torch.tensor(G["train_x"]), train_y=torch.tensor(G["train_y"][:, m]),
+                        lengthscale=torch.tensor(G["lengthscale"][m]), outputscale=float(G["outputscale"][m]),
+                        mean_const=float(G["mean_const"][m]), noise=float(G["noise"][m])) for m in range(2)]
+    n = 3
+    disc = torch.stack([torch.repeat_interleave(torch.linspace(0, 1, n), n),
+                        torch.tile(torch.linspace(0, 1, n), (n,))]).T.double()  # test_discretekg.py:17-25
+    W = torch.tensor([[0.7, 0.3], [0.6, 0.4], [0.5, 0.5]], dtype=torch.double)  # conftest.py:60-66
+    target_x = torch.tensor([[[[0.5, 0.5]], [[0, 1]], [[0, 0.5]]], [[[0, 0]], [[1, 0]], [[0.5, 0]]]],
+                            dtype=torch.double)  # test_discretekg.py:30-46
+    return GPModelList(objs), disc, W, target_x, G

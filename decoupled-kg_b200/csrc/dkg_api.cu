@@ -87,7 +87,8 @@ static int ensure_workspace(dkg_plan* p, int C) {
   // candidates in one chunk (0.5 GB of slope rows + 1.6 GB of survivor lists).
   double chunk_mb = 6144.0;
   if (const char* e = getenv("DKG_CHUNK_MB")) chunk_mb = atof(e);
-  const double per_row = (double)p->ldz * sizeof(double) + (double)p->S * SURV_CAP * sizeof(SurvEntry);
+  const double per_row = (double)p->ldz * sizeof(double) +
+                         (double)p->S * (SURV_CAP * sizeof(SurvEntry) + HULL_CAP * 20.0 + 64.0);
   long long rows = (long long)(chunk_mb * 1048576.0 / per_row);
   int chunk = (int)(rows / GEMM_BM) * GEMM_BM;
   if (chunk < GEMM_BM) chunk = GEMM_BM;
@@ -113,11 +114,11 @@ static int ensure_workspace(dkg_plan* p, int C) {
   { double4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S, false)); w.chain = t; }
   DKG_TRY(dev_alloc(&w.ovf_sets, (size_t)chunk * S, false));
   DKG_TRY(dev_alloc(&w.ovf_count, (size_t)1));
-  DKG_TRY(dev_alloc(&w.hull_cnt, (size_t)cap * S));
-  DKG_TRY(dev_alloc(&w.hull_idx, (size_t)cap * S * HULL_CAP, false));
-  DKG_TRY(dev_alloc(&w.hull_p, (size_t)cap * S * HULL_CAP, false));
-  DKG_TRY(dev_alloc(&w.hull_q, (size_t)cap * S * HULL_CAP, false));
-  DKG_TRY(dev_alloc(&w.amax_is_new, (size_t)cap * S));
+  DKG_TRY(dev_alloc(&w.hull_cnt, (size_t)chunk * S));
+  DKG_TRY(dev_alloc(&w.hull_idx, (size_t)chunk * S * HULL_CAP, false));
+  DKG_TRY(dev_alloc(&w.hull_p, (size_t)chunk * S * HULL_CAP, false));
+  DKG_TRY(dev_alloc(&w.hull_q, (size_t)chunk * S * HULL_CAP, false));
+  DKG_TRY(dev_alloc(&w.amax_is_new, (size_t)chunk * S));
   DKG_TRY(dev_alloc(&w.stats, (size_t)8));
   w.cap_C = cap;
   w.chunk_C = chunk;
@@ -316,13 +317,13 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     EmaxOut out;
     out.terms = w.kg_terms + (size_t)c0 * S;
     out.subtract_max = 1;
-    out.hull_cnt = w.hull_cnt + (size_t)c0 * S;
-    out.hull_idx = w.hull_idx + (size_t)c0 * S * HULL_CAP;
-    out.hull_p = w.hull_p + (size_t)c0 * S * HULL_CAP;
-    out.hull_q = w.hull_q + (size_t)c0 * S * HULL_CAP;
+    out.hull_cnt = w.hull_cnt;  // hull records are per chunk (consumed by finalize below)
+    out.hull_idx = w.hull_idx;
+    out.hull_p = w.hull_p;
+    out.hull_q = w.hull_q;
     out.hull_x = nullptr;
     out.hull_cap = HULL_CAP;
-    out.amax_is_own = w.amax_is_new + (size_t)c0 * S;
+    out.amax_is_own = w.amax_is_new;
     out.kg = kg + c0;
     BackwardArgs bw{};
     if (dX != nullptr) {

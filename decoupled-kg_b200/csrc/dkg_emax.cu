@@ -367,6 +367,12 @@ static int launch_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_
   dim3 grid(ceil_div(lb.NA, E_THREADS * R), ceil_div(lb.C, G));
   const size_t smem = (size_t)G * lb.S * (sizeof(double4) + 3 * sizeof(int) + 2 * sizeof(unsigned long long)) +
                       POOL_CAP * sizeof(int2);
+  if (smem > 48 * 1024) {  // many scalarisations: opt in to large dynamic shared memory
+    DKG_CUDA_OK(cudaFuncSetAttribute(filter_kernel<G, R, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DKG_CUDA_OK(cudaFuncSetAttribute(filter_kernel<G, R, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   if (lb.a_sc == 0)
     filter_kernel<G, R, true><<<grid, E_THREADS, smem, st>>>(lb, sc);
   else
@@ -1202,6 +1208,8 @@ int emax_finalize(const LineBatch& lb, const EmaxOut& out, const BackwardArgs& b
   if (bw.dX != nullptr)
     smem = sizeof(double) * ((size_t)bw.n_pad + lb.S + 2 + MAX_D + MAX_M + (E_THREADS / 32) * MAX_D) +
            sizeof(int) * (3 * FIN_RMAX + ((lb.S + 2) & ~1)) + sizeof(double) * 2 * FIN_RMAX;
+  if (smem > 48 * 1024)
+    DKG_CUDA_OK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   finalize_kernel<<<lb.C, E_THREADS, smem, st>>>(lb, out, bw);
   DKG_LAUNCH_CHECK();
   return DKG_OK;

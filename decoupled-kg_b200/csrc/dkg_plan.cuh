@@ -43,11 +43,11 @@ struct Workspace {
   unsigned long long* far = nullptr;  // [chunk_C, S, 2] farthest late survivors (chain seeds)
   int* ovf_sets = nullptr;  // [chunk_C * S] queue of sets for the cooperative kernel
   int* ovf_count = nullptr; // [1]
-  int* hull_cnt = nullptr;  // [cap_C, S]
-  int* hull_idx = nullptr;  // [cap_C, S, HULL_CAP]
-  double* hull_p = nullptr; // [cap_C, S, HULL_CAP]  dE/da  (Phi differences)
-  double* hull_q = nullptr; // [cap_C, S, HULL_CAP]  dE/db  (-phi differences)
-  int* amax_is_new = nullptr;  // [cap_C, S]  1 if the max intercept is the candidate's own line
+  int* hull_cnt = nullptr;  // [chunk_C, S]
+  int* hull_idx = nullptr;  // [chunk_C, S, HULL_CAP]
+  double* hull_p = nullptr; // [chunk_C, S, HULL_CAP]  dE/da  (Phi differences)
+  double* hull_q = nullptr; // [chunk_C, S, HULL_CAP]  dE/db  (-phi differences)
+  int* amax_is_new = nullptr;  // [chunk_C, S]  1 if the max intercept is the candidate's own line
   long long* stats = nullptr;  // [8] device counters
   int last_C = 0;
 };

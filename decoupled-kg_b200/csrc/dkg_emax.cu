@@ -88,6 +88,7 @@ zstat_kernel(LineBatch lb, EmaxScratch sc, double* __restrict__ zst, int* __rest
   const double* z = lb.Z + (size_t)c * lb.ldz;
   double vmin = INFINITY, vmax = -INFINITY;
   int imin = 0x7fffffff, imax = 0x7fffffff;
+#pragma unroll 8
   for (int n = threadIdx.x; n < lb.NL; n += blockDim.x) {
     double v = z[n];
     if (v < vmin) { vmin = v; imin = n; }
@@ -990,7 +991,7 @@ int emax_overflow(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out
 // finalize: kg[c] and the fused backward (envelope theorem); CTA per candidate
 //   dKG/da_jn = (p_jn - [n == argmax a_j]) / S ; dKG/db_jn = q_jn / S on hull lines only.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(E_THREADS)
+__global__ void __launch_bounds__(E_THREADS, 3)
 finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
   extern __shared__ __align__(16) unsigned char e_smem[];
   const int c = blockIdx.x;
@@ -999,14 +1000,19 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
   const int nwarps = blockDim.x >> 5;
   const int S = lb.S;
 
+  // kg[c] = mean_j terms[c, j] (:338): the S loads are issued in parallel, the sum is taken in
+  // index order by one thread (deterministic, same association as a sequential sum)
+  double* s_term = reinterpret_cast<double*>(e_smem);  // [S]
+  for (int j = threadIdx.x; j < S; j += blockDim.x) s_term[j] = out.terms[(size_t)c * S + j];
+  __syncthreads();
   if (threadIdx.x == 0) {
     double acc = 0.0;
-    for (int j = 0; j < S; ++j) acc += out.terms[(size_t)c * S + j];
-    out.kg[c] = acc / (double)S;  // kg.mean() (:338)
+    for (int j = 0; j < S; ++j) acc += s_term[j];
+    out.kg[c] = acc / (double)S;
   }
   if (bw.dX == nullptr) return;
 
-  double* s_r = reinterpret_cast<double*>(e_smem);  // [n_pad]  sum_n Gz[n] B[:, n]
+  double* s_r = s_term + S;                         // [n_pad]  sum_n Gz[n] B[:, n]
   double* s_ga = s_r + bw.n_pad;                    // [S]      dKG/d a_own[j]
   double* s_sc = s_ga + S;                          // [0] Gsum, [1] GzOwn, [2..2+MAX_D) gkd, then Gm[m]
   double* s_red = s_sc + 2 + MAX_D + MAX_M;         // [nwarps * MAX_D]
@@ -1026,11 +1032,15 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
   double* s_rcz = reinterpret_cast<double*>(s_roff + ((S + 2) & ~1));  // [FIN_RMAX] w_j q / S
   double* s_ucz = s_rcz + FIN_RMAX;                              // [FIN_RMAX] merged coefficient
   __shared__ int s_nrec, s_nuniq;
+  for (int j = threadIdx.x; j < S; j += blockDim.x)
+    s_roff[j + 1] = min(out.hull_cnt[(size_t)c * S + j], hcap);  // counts first, scanned below
+  __syncthreads();
   if (threadIdx.x == 0) {
     int off = 0;
     for (int j = 0; j < S; ++j) {
+      const int h = s_roff[j + 1];
       s_roff[j] = off;
-      off += min(out.hull_cnt[(size_t)c * S + j], hcap);
+      off += h;
     }
     s_roff[S] = off;
     s_nrec = off;
@@ -1204,9 +1214,9 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
 
 int emax_finalize(const LineBatch& lb, const EmaxOut& out, const BackwardArgs& bw, cudaStream_t st) {
   if (lb.C == 0 || out.kg == nullptr) return DKG_OK;
-  size_t smem = 0;
+  size_t smem = sizeof(double) * lb.S;
   if (bw.dX != nullptr)
-    smem = sizeof(double) * ((size_t)bw.n_pad + lb.S + 2 + MAX_D + MAX_M + (E_THREADS / 32) * MAX_D) +
+    smem = sizeof(double) * ((size_t)bw.n_pad + 2 * lb.S + 2 + MAX_D + MAX_M + (E_THREADS / 32) * MAX_D) +
            sizeof(int) * (3 * FIN_RMAX + ((lb.S + 2) & ~1)) + sizeof(double) * 2 * FIN_RMAX;
   if (smem > 48 * 1024)
     DKG_CUDA_OK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -511,33 +511,72 @@ __device__ HullResult warp_march(int total, Fetch fetch, const Recorder& rec) {
     if (oth.idx >= 0 && (cur.idx < 0 || sorted_before(oth, cur))) cur = oth;
   }
 
-  double E = 0.0, prev_cdf = 0.0, prev_pdf = 0.0;
+  // The march only needs the intersections; Phi / phi of the breakpoints are evaluated afterwards
+  // for up to 32 vertices at once (lane k owns vertex k of the batch), so the erf / exp latency is
+  // paid once per batch instead of once per vertex.  The expectation is still summed in hull order.
+  double E = 0.0, carry_cdf = 0.0, carry_pdf = 0.0;
   int h = 0;
+  Line mine = empty_line();   // vertex owned by this lane in the current batch
+  double mine_x = INFINITY;   // its right breakpoint (+inf for the last vertex)
   while (true) {
+    // next vertex: among lines with a strictly different (larger) slope, the one whose intersection
+    // with the current line comes first (:388-396); ties -> earliest in the sorted order
     Next best;
     best.L = empty_line();
     best.x = INFINITY;
 #pragma unroll
     for (int r = 0; r < LANE_LINES; ++r) consider_next(best, cur, cache[r]);
     for (int k = lane + 32 * LANE_LINES; k < total; k += 32) consider_next(best, cur, fetch(k));
-    for (int o = 16; o > 0; o >>= 1) {
-      Next oth;
-      oth.L = shfl_line(best.L, o);
-      oth.x = __shfl_xor_sync(0xffffffffu, best.x, o);
-      merge_next(best, oth);
+    const unsigned have = __ballot_sync(0xffffffffu, best.L.idx >= 0);
+    const bool last = have == 0u;
+    Line nxt = empty_line();
+    double nx = INFINITY;
+    if (!last) {
+      const double myx = best.L.idx >= 0 ? best.x : INFINITY;
+      double xm = myx;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) xm = fmin(xm, __shfl_xor_sync(0xffffffffu, xm, o));
+      const unsigned tied = __ballot_sync(0xffffffffu, best.L.idx >= 0 && myx == xm);
+      int src = __ffs(tied) - 1;
+      if (__popc(tied) > 1) {  // equal intersections: the earliest line in the sorted order wins
+        Next b2 = best;
+        if (!(best.L.idx >= 0 && myx == xm)) b2.L = empty_line();
+        for (int o = 16; o > 0; o >>= 1) {
+          Next oth;
+          oth.L = shfl_line(b2.L, o);
+          oth.x = __shfl_xor_sync(0xffffffffu, b2.x, o);
+          merge_next(b2, oth);
+        }
+        nxt = b2.L;
+      } else {
+        nxt.a = __shfl_sync(0xffffffffu, best.L.a, src);
+        nxt.b = __shfl_sync(0xffffffffu, best.L.b, src);
+        nxt.idx = __shfl_sync(0xffffffffu, best.L.idx, src);
+        nxt.ref = __shfl_sync(0xffffffffu, best.L.ref, src);
+      }
+      nx = xm;
     }
-    const bool last = best.L.idx < 0;
-    const double cdf = last ? 1.0 : std_normal_cdf(best.x);
-    const double pdf = last ? 0.0 : std_normal_pdf(best.x);
-    const double dP = cdf - prev_cdf;
-    const double dp = pdf - prev_pdf;
-    E += __dsub_rn(__dmul_rn(cur.a, dP), __dmul_rn(cur.b, dp));
-    if (lane == 0) rec(h, cur, dP, -dp, best.x, last);
+    const int slot = h & 31;
+    if (lane == slot) { mine = cur; mine_x = nx; }
     ++h;
+    if (slot == 31 || last) {
+      const int cnt = slot + 1;
+      const bool act = lane < cnt;
+      const double cdf = act ? std_normal_cdf(mine_x) : 0.0;  // Phi(+inf) = 1, phi(+inf) = 0
+      const double pdf = act ? std_normal_pdf(mine_x) : 0.0;
+      double lcdf = __shfl_up_sync(0xffffffffu, cdf, 1);
+      double lpdf = __shfl_up_sync(0xffffffffu, pdf, 1);
+      if (lane == 0) { lcdf = carry_cdf; lpdf = carry_pdf; }
+      const double dP = cdf - lcdf, dp = pdf - lpdf;
+      // intercepts * (cdf[1:] - cdf[:-1]) - slopes * (pdf[1:] - pdf[:-1])   (:449-451)
+      const double term = act ? __dsub_rn(__dmul_rn(mine.a, dP), __dmul_rn(mine.b, dp)) : 0.0;
+      if (act) rec(h - cnt + lane, mine, dP, -dp, mine_x, last && lane == cnt - 1);
+      for (int k = 0; k < cnt; ++k) E += __shfl_sync(0xffffffffu, term, k);
+      carry_cdf = __shfl_sync(0xffffffffu, cdf, cnt - 1);
+      carry_pdf = __shfl_sync(0xffffffffu, pdf, cnt - 1);
+    }
     if (last) break;
-    cur = best.L;
-    prev_cdf = cdf;
-    prev_pdf = pdf;
+    cur = nxt;
   }
   HullResult res;
   res.E = E;
@@ -649,24 +688,25 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
     if (hasR) cr.set(T, Q);
     if (F1.idx >= 0 && !(cl.excess(F1) > 0.0)) F1 = empty_line();  // keep the chain concave
     if (F2.idx >= 0 && !(cr.excess(F2) > 0.0)) F2 = empty_line();
-    // refined chain: P [F1] T [F2] Q  -> up to 4 chords
+    // refined chain: P [F1] T [F2] Q  -> up to 4 chords; unused slots have an empty slope range
     Chord ch[4];
     double lo_b[4], hi_b[4];
-    int nch = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { ch[q] = cl; lo_b[q] = INFINITY; hi_b[q] = -INFINITY; }
     if (hasL) {
       if (F1.idx >= 0) {
-        ch[nch].set(P, F1); lo_b[nch] = P.b; hi_b[nch] = F1.b; ++nch;
-        ch[nch].set(F1, T); lo_b[nch] = F1.b; hi_b[nch] = T.b; ++nch;
+        ch[0].set(P, F1); lo_b[0] = P.b; hi_b[0] = F1.b;
+        ch[1].set(F1, T); lo_b[1] = F1.b; hi_b[1] = T.b;
       } else {
-        ch[nch] = cl; lo_b[nch] = P.b; hi_b[nch] = T.b; ++nch;
+        ch[0] = cl; lo_b[0] = P.b; hi_b[0] = T.b;
       }
     }
     if (hasR) {
       if (F2.idx >= 0) {
-        ch[nch].set(T, F2); lo_b[nch] = T.b; hi_b[nch] = F2.b; ++nch;
-        ch[nch].set(F2, Q); lo_b[nch] = F2.b; hi_b[nch] = Q.b; ++nch;
+        ch[2].set(T, F2); lo_b[2] = T.b; hi_b[2] = F2.b;
+        ch[3].set(F2, Q); lo_b[3] = F2.b; hi_b[3] = Q.b;
       } else {
-        ch[nch] = cr; lo_b[nch] = T.b; hi_b[nch] = Q.b; ++nch;
+        ch[2] = cr; lo_b[2] = T.b; hi_b[2] = Q.b;
       }
     }
     // the staged list starts with the chain vertices themselves
@@ -690,7 +730,8 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
         // a line strictly inside a chord's slope range survives only above that chord; a line
         // at a vertex slope is kept (the march discards it if it is dominated)
         keep = true;
-        for (int q = 0; q < nch; ++q)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
           if (L.b > lo_b[q] && L.b < hi_b[q]) keep = ch[q].excess(L) > -ch[q].slack;
       }
       const unsigned m = __ballot_sync(0xffffffffu, keep);

@@ -70,7 +70,8 @@ static void free_workspace(Workspace& w) {
   dev_free(w.sd); dev_free(w.zown); dev_free(w.Xs); dev_free(w.a_new); dev_free(w.kg_terms);
   dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } { double4* t = (double4*)w.chain; dev_free(t); w.chain = nullptr; } dev_free(w.far); dev_free(w.ovf_sets); dev_free(w.ovf_count);
   dev_free(w.hull_cnt); dev_free(w.hull_idx); dev_free(w.hull_p); dev_free(w.hull_q);
-  dev_free(w.amax_is_new); dev_free(w.stats);
+  dev_free(w.amax_is_new); dev_free(w.stats); dev_free(w.sdj); dev_free(w.Zc);
+  for (int m = 0; m < MAX_M; ++m) { dev_free(w.KXm[m]); dev_free(w.Tm[m]); dev_free(w.varlat[m]); dev_free(w.COVm[m]); }
   w.cap_C = w.chunk_C = 0;
 }
 
@@ -81,14 +82,16 @@ static int ensure_workspace(dkg_plan* p, int C) {
   DKG_CUDA_OK(cudaDeviceSynchronize());
   free_workspace(w);
   const int cap = round_up(C, GEMM_BM);
-  const int n_pad = p->obj[p->target].n_pad;
+  const bool coupled = p->target < 0;
+  const int n_pad = coupled ? GEMM_BK : p->obj[p->target].n_pad;
   // Candidates are processed in chunks that bound the scratch memory (slope rows + survivor
   // lists).  DKG_CHUNK_MB (default 6144) is the budget for both; at c4 shapes it covers all 4096
   // candidates in one chunk (0.5 GB of slope rows + 1.6 GB of survivor lists).
   double chunk_mb = 6144.0;
   if (const char* e = getenv("DKG_CHUNK_MB")) chunk_mb = atof(e);
-  const double per_row = (double)p->ldz * sizeof(double) +
-                         (double)p->S * (SURV_CAP * sizeof(SurvEntry) + HULL_CAP * 20.0 + 64.0);
+  double per_row = (double)p->ldz * sizeof(double) +
+                   (double)p->S * (SURV_CAP * sizeof(SurvEntry) + HULL_CAP * 20.0 + 64.0);
+  if (coupled) per_row += (double)p->ldz * sizeof(double) * (p->M + p->S);
   long long rows = (long long)(chunk_mb * 1048576.0 / per_row);
   int chunk = (int)(rows / GEMM_BM) * GEMM_BM;
   if (chunk < GEMM_BM) chunk = GEMM_BM;
@@ -98,16 +101,29 @@ static int ensure_workspace(dkg_plan* p, int C) {
   DKG_TRY(dev_alloc(&w.kg, (size_t)cap));
   DKG_TRY(dev_alloc(&w.dX, (size_t)cap * p->d));
   DKG_TRY(dev_alloc(&w.KX, (size_t)cap * n_pad));
-  DKG_TRY(dev_alloc(&w.T, (size_t)cap * p->ldk));
+  DKG_TRY(dev_alloc(&w.T, (size_t)cap * (coupled ? GEMM_BN : p->ldk)));
   DKG_TRY(dev_alloc(&w.var, (size_t)cap));
   DKG_TRY(dev_alloc(&w.sd, (size_t)cap));
   DKG_TRY(dev_alloc(&w.zown, (size_t)cap));
   DKG_TRY(dev_alloc(&w.Xs, (size_t)cap * p->d));
   DKG_TRY(dev_alloc(&w.a_new, (size_t)cap * S));
   DKG_TRY(dev_alloc(&w.kg_terms, (size_t)cap * S));
-  DKG_TRY(dev_alloc(&w.Z, (size_t)chunk * p->ldz));
-  DKG_TRY(dev_alloc(&w.zst, (size_t)chunk * 2));
-  DKG_TRY(dev_alloc(&w.zarg, (size_t)chunk * 2));
+  // the slope-row statistics are per ROW of the expected-max batch: one row per candidate in the
+  // decoupled path, one per (candidate, scalarisation) in the coupled path
+  const size_t rows_per_cand = coupled ? S : 1;
+  DKG_TRY(dev_alloc(&w.Z, coupled ? (size_t)1 : (size_t)chunk * p->ldz));
+  DKG_TRY(dev_alloc(&w.zst, (size_t)chunk * rows_per_cand * 2));
+  DKG_TRY(dev_alloc(&w.zarg, (size_t)chunk * rows_per_cand * 2));
+  if (coupled) {
+    for (int m = 0; m < p->M; ++m) {
+      DKG_TRY(dev_alloc(&w.KXm[m], (size_t)cap * p->obj[m].n_pad));
+      DKG_TRY(dev_alloc(&w.Tm[m], (size_t)cap * p->obj[m].ldk));
+      DKG_TRY(dev_alloc(&w.varlat[m], (size_t)cap));
+      DKG_TRY(dev_alloc(&w.COVm[m], (size_t)chunk * p->ldz));
+    }
+    DKG_TRY(dev_alloc(&w.sdj, (size_t)cap * S));
+    DKG_TRY(dev_alloc(&w.Zc, (size_t)chunk * S * p->ldz));
+  }
   DKG_TRY(dev_alloc(&w.surv_cnt, (size_t)chunk * S));
   { SurvEntry* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * SURV_CAP, false)); w.surv = t; }
   DKG_TRY(dev_alloc(&w.far, (size_t)chunk * S * 2));
@@ -129,11 +145,11 @@ static void destroy_plan(dkg_plan* p) {
   if (!p) return;
   cudaDeviceSynchronize();
   for (int m = 0; m < p->M; ++m) {
-    dev_free(p->obj[m].xs);
-    dev_free(p->obj[m].alpha);
+    ObjState& o = p->obj[m];
+    dev_free(o.xs); dev_free(o.alpha); dev_free(o.chol); dev_free(o.Kinv); dev_free(o.B);
+    dev_free(o.BT); dev_free(o.xd_s);
   }
-  dev_free(p->W); dev_free(p->wt); dev_free(p->xd); dev_free(p->xd_s); dev_free(p->chol);
-  dev_free(p->cholT); dev_free(p->Kinv); dev_free(p->B); dev_free(p->BT); dev_free(p->alpha_all);
+  dev_free(p->W); dev_free(p->wt); dev_free(p->xd); dev_free(p->alpha_all);
   dev_free(p->mu_disc); dev_free(p->A0); dev_free(p->A0max); dev_free(p->A0arg);
   free_workspace(p->ws);
   delete p;
@@ -197,7 +213,7 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
     if ((rc = scale_rows(s.train_x_dev, o.n, d, o.ls, o.xs, st)) != DKG_OK) break;
     double jit = 0.0;
     if ((rc = factor_objective(o, d, Lbuf, info_dev, &jit, st)) != DKG_OK) break;
-    if (m == tgt) p->jitter = jit;
+    if (m == tgt || tgt < 0) p->jitter = jit > p->jitter ? jit : p->jitter;
     if ((rc = transpose(Lbuf, o.n, o.n, o.n, LTbuf, o.n, st)) != DKG_OK) break;
     // mean cache: alpha = K^-1 (y - c)
     if ((rc = residual(s.train_y_dev, o.n, o.mean_const, o.alpha, st)) != DKG_OK) break;
@@ -205,25 +221,31 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
     cudaMemcpyAsync(p->alpha_all + off, o.alpha, sizeof(double) * o.n, cudaMemcpyDeviceToDevice, st);
     off += o.n;
     if ((rc = mu_disc(p->xd, N, d, o, p->mu_disc, M, m, st)) != DKG_OK) break;
-    if (m == tgt) {
+    if (m == tgt || tgt < 0) {
       const int n = o.n;
-      p->ldk = round_up(n, GEMM_BN);
-      if ((rc = dev_alloc(&p->chol, (size_t)n * n)) != DKG_OK) break;
-      if ((rc = dev_alloc(&p->cholT, (size_t)n * n)) != DKG_OK) break;
-      cudaMemcpyAsync(p->chol, Lbuf, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st);
-      cudaMemcpyAsync(p->cholT, LTbuf, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st);
+      o.ldk = round_up(n, GEMM_BN);
+      double* cholT = nullptr;
+      if ((rc = dev_alloc(&o.chol, (size_t)n * n)) != DKG_OK) break;
+      if ((rc = dev_alloc(&cholT, (size_t)n * n)) != DKG_OK) break;
+      cudaMemcpyAsync(o.chol, Lbuf, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(cholT, LTbuf, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st);
       // Kinv = K^-1 (solve against the identity)
-      if ((rc = dev_alloc(&p->Kinv, (size_t)o.n_pad * p->ldk)) != DKG_OK) break;
-      if ((rc = set_identity(p->Kinv, n, p->ldk, st)) != DKG_OK) break;
-      if ((rc = cholesky_solve_inplace(p->chol, p->cholT, n, p->Kinv, n, p->ldk, st)) != DKG_OK) break;
+      if ((rc = dev_alloc(&o.Kinv, (size_t)o.n_pad * o.ldk)) != DKG_OK) break;
+      if ((rc = set_identity(o.Kinv, n, o.ldk, st)) != DKG_OK) break;
+      if ((rc = cholesky_solve_inplace(o.chol, cholT, n, o.Kinv, n, o.ldk, st)) != DKG_OK) break;
       // B = K^-1 k(X_train, X_disc)
-      if ((rc = dev_alloc(&p->xd_s, (size_t)p->N_pad * d)) != DKG_OK) break;
-      if ((rc = scale_rows(p->xd, N, d, o.ls, p->xd_s, st)) != DKG_OK) break;
-      if ((rc = dev_alloc(&p->B, (size_t)o.n_pad * p->N_pad)) != DKG_OK) break;
-      if ((rc = kcross(o, p->xd_s, N, d, p->B, p->N_pad, st)) != DKG_OK) break;
-      if ((rc = cholesky_solve_inplace(p->chol, p->cholT, n, p->B, N, p->N_pad, st)) != DKG_OK) break;
-      if ((rc = dev_alloc(&p->BT, (size_t)N * o.n_pad)) != DKG_OK) break;
-      if ((rc = transpose(p->B, o.n_pad, N, p->N_pad, p->BT, o.n_pad, st)) != DKG_OK) break;
+      if ((rc = dev_alloc(&o.xd_s, (size_t)p->N_pad * d)) != DKG_OK) break;
+      if ((rc = scale_rows(p->xd, N, d, o.ls, o.xd_s, st)) != DKG_OK) break;
+      if ((rc = dev_alloc(&o.B, (size_t)o.n_pad * p->N_pad)) != DKG_OK) break;
+      if ((rc = kcross(o, o.xd_s, N, d, o.B, p->N_pad, st)) != DKG_OK) break;
+      if ((rc = cholesky_solve_inplace(o.chol, cholT, n, o.B, N, p->N_pad, st)) != DKG_OK) break;
+      if ((rc = dev_alloc(&o.BT, (size_t)N * o.n_pad)) != DKG_OK) break;
+      if ((rc = transpose(o.B, o.n_pad, N, p->N_pad, o.BT, o.n_pad, st)) != DKG_OK) break;
+      cudaStreamSynchronize(st);
+      dev_free(cholT);
+      if (m == tgt) {  // aliases used by the decoupled path
+        p->ldk = o.ldk; p->chol = o.chol; p->Kinv = o.Kinv; p->B = o.B; p->BT = o.BT; p->xd_s = o.xd_s;
+      }
     }
   }
   if (rc == DKG_OK) {
@@ -235,7 +257,7 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
     if (rc == DKG_OK) rc = dev_alloc(&p->A0arg, (size_t)S);
     if (rc == DKG_OK) {
       double wt_host[MAX_S];
-      for (int j = 0; j < S; ++j) wt_host[j] = p->W_host[j * M + tgt];
+      for (int j = 0; j < S; ++j) wt_host[j] = tgt >= 0 ? p->W_host[j * M + tgt] : 1.0;
       cudaMemcpyAsync(p->W, p->W_host, sizeof(double) * S * M, cudaMemcpyHostToDevice, st);
       cudaMemcpyAsync(p->wt, wt_host, sizeof(double) * S, cudaMemcpyHostToDevice, st);
       cudaStreamSynchronize(st);  // wt_host is a stack buffer
@@ -254,9 +276,12 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
   return rc;
 }
 
+static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st);
+
 static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st) {
   if (C == 0) return DKG_OK;
   DKG_TRY(ensure_workspace(p, C));
+  if (p->target < 0) return forward_coupled(p, X, C, kg, dX, st);
   Workspace& w = p->ws;
   const ObjState& ot = p->obj[p->target];
   const int d = p->d, N = p->N, S = p->S, M = p->M;
@@ -352,6 +377,101 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
   return DKG_OK;
 }
 
+// Coupled evaluation (reference calculate_discrete_kg, discretekg.py:162-235).
+static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st) {
+  Workspace& w = p->ws;
+  const int d = p->d, N = p->N, S = p->S, M = p->M;
+  const int C_pad = round_up(C, GEMM_BM);
+  w.last_C = C;
+  DKG_CUDA_OK(cudaMemsetAsync(w.stats, 0, sizeof(long long) * 8, st));
+  // per objective: k_m(x, X_train), means, T_m = KX_m Kinv_m, latent variance
+  for (int m = 0; m < M; ++m) {
+    const ObjState& o = p->obj[m];
+    XprepArgs xa{};
+    xa.X = X; xa.C = C; xa.d = d; xa.M = M; xa.S = S; xa.target = m;
+    for (int q = 0; q < M; ++q) {
+      const ObjState& oq = p->obj[q];
+      xa.xs[q] = oq.xs; xa.alpha[q] = oq.alpha; xa.ntr[q] = oq.n; xa.kind[q] = oq.kernel;
+      xa.outputscale[q] = oq.outputscale; xa.mean_const[q] = oq.mean_const;
+      xa.y_mean[q] = oq.y_mean; xa.y_std[q] = oq.y_std;
+      for (int k = 0; k < MAX_D; ++k) xa.ls[q][k] = oq.ls[k];
+    }
+    xa.W = p->W; xa.Xs = w.Xs; xa.KX = w.KXm[m]; xa.n_pad = o.n_pad; xa.a_new = w.a_new;
+    DKG_TRY(launch_xprep(xa, st));  // (a_new / means are recomputed identically each time)
+    DKG_TRY(gemm_store(w.KXm[m], o.n_pad, o.Kinv, o.ldk, C_pad, o.ldk, o.n_pad, w.Tm[m], o.ldk, st));
+    // var = noisy variance (un-standardised) -> w.var reused per objective below via varlat
+    DKG_TRY(launch_var(w.KXm[m], o.n_pad, w.Tm[m], o.ldk, o.n, C, o.kernel, o.outputscale, o.noise,
+                       o.y_std * o.y_std, w.varlat[m], w.sd, w.zown, st));
+    // launch_var wrote: varlat[m] <- noisy variance, sd <- sqrt, zown <- Cov(x,x)/sd.  Recover the
+    // covariance Cov_m(x, x) (un-standardised) into column N of COV_m per chunk below: zown * sd.
+    // (kept simple: a tiny kernel multiplies them in place)
+  }
+  for (int c0 = 0; c0 < C; c0 += w.chunk_C) {
+    const int cc = (C - c0) < w.chunk_C ? (C - c0) : w.chunk_C;
+    const int cc_pad = round_up(cc, GEMM_BM);
+    CoupledArgs ca;
+    ca.C = cc; ca.S = S; ca.M = M; ca.d = d; ca.N = N; ca.ldz = p->ldz;
+    ca.W = p->W; ca.sdj = w.sdj + (size_t)c0 * S; ca.Zc = w.Zc;
+    for (int m = 0; m < M; ++m) {
+      const ObjState& o = p->obj[m];
+      // covariance rows of objective m: same GEMM as the decoupled path with sd = 1
+      DKG_TRY(launch_xprep_scaled(X + (size_t)c0 * d, cc, d, o.ls, w.Xs, st));
+      DKG_TRY(fill_ones(w.sd, cc, st));
+      CovEpilogue ep{};
+      ep.xs = w.Xs; ep.xd_s = o.xd_s; ep.sd = w.sd; ep.Z = w.COVm[m];
+      ep.ldz = p->ldz; ep.C = cc; ep.N = N; ep.d = d; ep.kind = o.kernel;
+      ep.outputscale = o.outputscale; ep.ystd2 = o.y_std * o.y_std;
+      DKG_TRY(gemm_cov(w.KXm[m] + (size_t)c0 * o.n_pad, o.n_pad, o.B, p->N_pad, cc_pad, p->N_pad,
+                       o.n_pad, ep, st));
+      DKG_TRY(place_latent_var(w.KXm[m] + (size_t)c0 * o.n_pad, o.n_pad, w.Tm[m] + (size_t)c0 * o.ldk,
+                               o.ldk, o.n, cc, o.kernel, o.outputscale, o.y_std * o.y_std,
+                               w.COVm[m], p->ldz, N, st));
+      ca.COV[m] = w.COVm[m];
+      ca.varn[m] = w.varlat[m] + c0;
+    }
+    DKG_TRY(coupled_slopes(ca, st));
+
+    LineBatch lb;
+    lb.Z = w.Zc; lb.ldz = p->ldz;
+    lb.A = p->A0; lb.a_sc = 0; lb.a_sj = p->N_pad;
+    lb.a_own = w.a_new + (size_t)c0 * S;
+    lb.wt = nullptr;
+    lb.Amax = p->A0max; lb.Aarg = p->A0arg; lb.am_sc = 0;
+    lb.NA = N; lb.NL = N + 1; lb.S = 1; lb.C = cc * S; lb.row_mod = S;
+    EmaxScratch sc;
+    sc.zst = w.zst; sc.zarg = w.zarg; sc.surv_cnt = w.surv_cnt; sc.surv = (SurvEntry*)w.surv;
+    sc.ovf_sets = w.ovf_sets; sc.ovf_count = w.ovf_count; sc.far = w.far; sc.chain = (double4*)w.chain;
+    sc.stats = w.stats;
+    DKG_CUDA_OK(cudaMemsetAsync(w.surv_cnt, 0, sizeof(int) * (size_t)cc * S, st));
+    DKG_CUDA_OK(cudaMemsetAsync(w.far, 0, sizeof(unsigned long long) * (size_t)cc * S * 2, st));
+    DKG_CUDA_OK(cudaMemsetAsync(w.ovf_count, 0, sizeof(int), st));
+    DKG_TRY(emax_zstat(lb, sc, nullptr, nullptr, st));
+    DKG_TRY(emax_filter(lb, sc, st));
+    EmaxOut out;
+    out.terms = w.kg_terms + (size_t)c0 * S;
+    out.subtract_max = 1;
+    out.hull_cnt = w.hull_cnt; out.hull_idx = w.hull_idx; out.hull_p = w.hull_p; out.hull_q = w.hull_q;
+    out.hull_x = nullptr; out.hull_cap = HULL_CAP; out.amax_is_own = w.amax_is_new;
+    out.kg = kg + c0;
+    DKG_TRY(emax_hull(lb, sc, out, st));
+    DKG_TRY(emax_overflow(lb, sc, out, st));
+    CoupledBackward bw;
+    if (dX != nullptr) {
+      bw.dX = dX + (size_t)c0 * d; bw.X = X + (size_t)c0 * d; bw.W = p->W; bw.Zc = w.Zc;
+      bw.sdj = w.sdj + (size_t)c0 * S; bw.ldz = p->ldz; bw.M = M; bw.d = d; bw.S = S; bw.N = N;
+      for (int m = 0; m < M; ++m) {
+        const ObjState& o = p->obj[m];
+        bw.T[m] = w.Tm[m] + (size_t)c0 * o.ldk; bw.ldk[m] = o.ldk; bw.BT[m] = o.BT; bw.n_pad[m] = o.n_pad;
+        bw.xd_s[m] = o.xd_s; bw.xs[m] = o.xs; bw.alpha[m] = o.alpha; bw.ntr[m] = o.n; bw.kind[m] = o.kernel;
+        bw.outputscale[m] = o.outputscale; bw.y_std[m] = o.y_std;
+        for (int k = 0; k < MAX_D; ++k) bw.ls[m][k] = o.ls[k];
+      }
+    }
+    DKG_TRY(emax_finalize_coupled(cc, S, out, bw, st));
+  }
+  return DKG_OK;
+}
+
 }  // namespace dkg
 
 using namespace dkg;
@@ -374,8 +494,8 @@ int dkg_plan_create(const dkg_objective* objs, int32_t M, int32_t d, const doubl
   if (d < 1 || d > MAX_D) { set_error("d=%d outside [1, %d]", d, MAX_D); return DKG_EINVAL; }
   if (S < 1 || S > MAX_S) { set_error("S=%d outside [1, %d]", S, MAX_S); return DKG_EINVAL; }
   if (N < 1) { set_error("the discretisation is empty"); return DKG_EINVAL; }
-  if (target_ix < 0 || target_ix >= M) {
-    set_error("target_ix=%d outside [0, %d)", target_ix, M);
+  if (target_ix < -1 || target_ix >= M) {
+    set_error("target_ix=%d outside [-1, %d)  (-1 = coupled evaluation)", target_ix, M);
     return DKG_EINVAL;
   }
   for (int m = 0; m < M; ++m) {

@@ -1,0 +1,229 @@
+// Coupled evaluation (target_output_ix=None): reference calculate_discrete_kg
+// (discretekg.py:162-235).  One joint posterior over all objectives, scalarised per weight vector
+// with ScalarizedPosteriorTransform: for independent outputs (ModelListGP) the scalarised
+// covariance is sum_m w_m^2 Cov_m and the noisy variance sum_m w_m^2 (var_m + noise_m) [BoTorch,
+// recalled; pinned by the reference's coupled goldens, tests/test_reference_goldens.py].
+//
+// The conditioning GEMM runs once per objective (same kernel as the decoupled path, sd = 1), then
+//   coupled_slopes : Zc[(c,j), n] = sum_m W[j,m]^2 Cov_m[c,n] / sqrt(sum_m W[j,m]^2 var_m[c])
+// after which every (candidate, scalarisation) pair is an independent line set for the generic
+// expected-max kernels (slope ORDER now differs per scalarisation), and
+//   finalize_coupled: kg[c] = mean_j and the envelope-theorem backward through all M objectives.
+#include "dkg_emax.cuh"
+
+namespace dkg {
+
+constexpr int CP_THREADS = 256;
+
+__global__ void __launch_bounds__(CP_THREADS)
+coupled_sd_kernel(CoupledArgs a) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.C * a.S) return;
+  const int c = e / a.S, j = e - c * a.S;
+  double v = 0.0;
+  for (int m = 0; m < a.M; ++m) {
+    const double w = a.W[j * a.M + m];
+    v += (w * w) * a.varn[m][c];
+  }
+  a.sdj[e] = sqrt(v);  // xnew_variance.sqrt()  (:223)
+}
+
+__global__ void __launch_bounds__(CP_THREADS)
+coupled_slopes_kernel(CoupledArgs a) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (n > a.N) return;  // column N is the candidate's own line
+  double cov[MAX_M];
+#pragma unroll
+  for (int m = 0; m < MAX_M; ++m) cov[m] = m < a.M ? a.COV[m][(size_t)c * a.ldz + n] : 0.0;
+  for (int j = 0; j < a.S; ++j) {
+    double s = 0.0;
+#pragma unroll
+    for (int m = 0; m < MAX_M; ++m)
+      if (m < a.M) {
+        const double w = a.W[j * a.M + m];
+        s += (w * w) * cov[m];
+      }
+    a.Zc[((size_t)c * a.S + j) * a.ldz + n] = s / a.sdj[(size_t)c * a.S + j];
+  }
+}
+
+int coupled_slopes(const CoupledArgs& a, cudaStream_t st) {
+  if (a.C == 0) return DKG_OK;
+  coupled_sd_kernel<<<ceil_div(a.C * a.S, CP_THREADS), CP_THREADS, 0, st>>>(a);
+  DKG_LAUNCH_CHECK();
+  dim3 grid(ceil_div(a.N + 1, CP_THREADS), a.C);
+  coupled_slopes_kernel<<<grid, CP_THREADS, 0, st>>>(a);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize (coupled): CTA per candidate.  With b_jn = sum_m om_jm cov_m[n], om_jm = W_jm^2 / sd_j,
+// var_j = sum_m W_jm^2 var_m:
+//   dKG = sum_j Ga_j d a_own_j + sum_m [ sum_n Gz_m[n] d cov_m[n] + Cv_m d var_m ]
+//   Gz_m[n] = sum_j om_jm q_jn / S,   Cv_m = -sum_j W_jm^2 / (2 var_j) sum_n (q_jn / S) b_jn
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CP_THREADS)
+finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
+  extern __shared__ __align__(16) unsigned char c_smem[];
+  const int c = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  double* s_term = reinterpret_cast<double*>(c_smem);  // [S]
+  for (int j = threadIdx.x; j < S; j += blockDim.x) s_term[j] = out.terms[(size_t)c * S + j];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double acc = 0.0;
+    for (int j = 0; j < S; ++j) acc += s_term[j];
+    out.kg[c] = acc / (double)S;  // kg.mean() (:235)
+  }
+  if (bw.dX == nullptr) return;
+
+  const int d = bw.d, M = bw.M, hcap = out.hull_cap, NA = bw.N;
+  const double invS = 1.0 / (double)S;
+  int n_pad_max = 0;
+  for (int m = 0; m < M; ++m) n_pad_max = max(n_pad_max, bw.n_pad[m]);
+  double* s_r = s_term + S;                    // [n_pad_max]
+  double* s_sc = s_r + n_pad_max;              // [0] gzown, [1] Cv, [2..2+MAX_D) gkd, [2+MAX_D..) gm[m]
+  double* s_red = s_sc + 2 + MAX_D + MAX_M;    // [nwarps * MAX_D]
+  double grad[MAX_D];
+#pragma unroll
+  for (int k = 0; k < MAX_D; ++k) grad[k] = 0.0;
+
+  // gm[m] = sum_j Ga_j W[j, m]  (own-line intercept path), computed once by warp 0
+  if (warp == 0) {
+    double gm[MAX_M];
+#pragma unroll
+    for (int m = 0; m < MAX_M; ++m) gm[m] = 0.0;
+    for (int j = lane; j < S; j += 32) {
+      const size_t set = (size_t)c * S + j;
+      const int h = min(out.hull_cnt[set], hcap);
+      double ga = out.amax_is_own[set] ? -invS : 0.0;
+      for (int k = 0; k < h; ++k)
+        if (out.hull_idx[set * hcap + k] == NA) ga += out.hull_p[set * hcap + k] * invS;
+#pragma unroll
+      for (int m = 0; m < MAX_M; ++m)
+        if (m < M) gm[m] += ga * bw.W[j * M + m];
+    }
+#pragma unroll
+    for (int m = 0; m < MAX_M; ++m) gm[m] = warp_sum(gm[m]);
+    if (lane == 0)
+      for (int m = 0; m < MAX_M; ++m) s_sc[2 + MAX_D + m] = gm[m];
+  }
+  __syncthreads();
+
+  for (int m = 0; m < M; ++m) {
+    const double s2 = bw.y_std[m] * bw.y_std[m];
+    // r_m[t] = sum over hull records (discretisation lines) of om_jm q / S * B_m^T[idx, t]
+    for (int t = threadIdx.x; t < bw.n_pad[m]; t += blockDim.x) {
+      double acc = 0.0;
+      for (int j = 0; j < S; ++j) {
+        const size_t set = (size_t)c * S + j;
+        const int h = min(out.hull_cnt[set], hcap);
+        const double w = bw.W[j * M + m];
+        const double om = (w * w) / bw.sdj[set];
+        for (int k = 0; k < h; ++k) {
+          const int idx = out.hull_idx[set * hcap + k];
+          if (idx < NA) acc += om * out.hull_q[set * hcap + k] * invS * bw.BT[m][(size_t)idx * bw.n_pad[m] + t];
+        }
+      }
+      s_r[t] = acc;
+    }
+    if (warp == 0) {
+      double gzown = 0.0, cv = 0.0, gkd[MAX_D];
+#pragma unroll
+      for (int k = 0; k < MAX_D; ++k) gkd[k] = 0.0;
+      double xm[MAX_D];
+#pragma unroll
+      for (int k = 0; k < MAX_D; ++k) xm[k] = k < d ? bw.X[(size_t)c * d + k] / bw.ls[m][k] : 0.0;
+      for (int j = lane; j < S; j += 32) {
+        const size_t set = (size_t)c * S + j;
+        const int h = min(out.hull_cnt[set], hcap);
+        const double w = bw.W[j * M + m];
+        const double sd = bw.sdj[set];
+        const double om = (w * w) / sd;
+        const double* zrow = bw.Zc + set * (size_t)bw.ldz;
+        double qb = 0.0;  // sum_n (q / S) b_jn
+        for (int k = 0; k < h; ++k) {
+          const int idx = out.hull_idx[set * hcap + k];
+          const double qs = out.hull_q[set * hcap + k] * invS;
+          qb += qs * zrow[idx];
+          if (idx == NA) {
+            gzown += om * qs;
+          } else {
+            double sq = 0.0;
+#pragma unroll
+            for (int q = 0; q < MAX_D; ++q)
+              if (q < d) {
+                const double df = xm[q] - bw.xd_s[m][(size_t)idx * d + q];
+                sq += df * df;
+              }
+            const double gc = stationary_grad_coeff(bw.kind[m], bw.outputscale[m], sq);
+#pragma unroll
+            for (int q = 0; q < MAX_D; ++q)
+              if (q < d) gkd[q] += om * qs * gc * (xm[q] - bw.xd_s[m][(size_t)idx * d + q]) / bw.ls[m][q];
+          }
+        }
+        cv -= (w * w) / (2.0 * sd * sd) * qb;
+      }
+      gzown = warp_sum(gzown);
+      cv = warp_sum(cv);
+#pragma unroll
+      for (int k = 0; k < MAX_D; ++k) gkd[k] = warp_sum(gkd[k]);
+      if (lane == 0) {
+        s_sc[0] = gzown;
+        s_sc[1] = cv;
+        for (int k = 0; k < MAX_D; ++k) s_sc[2 + k] = gkd[k];
+      }
+    }
+    __syncthreads();
+    const double cT = -2.0 * s2 * (s_sc[0] + s_sc[1]);
+    const double cm = s_sc[2 + MAX_D + m] * bw.y_std[m];
+    double xm[MAX_D];
+#pragma unroll
+    for (int k = 0; k < MAX_D; ++k) xm[k] = k < d ? bw.X[(size_t)c * d + k] / bw.ls[m][k] : 0.0;
+    for (int t = threadIdx.x; t < bw.ntr[m]; t += blockDim.x) {
+      const double u = cm * bw.alpha[m][t] - s2 * s_r[t] + cT * bw.T[m][(size_t)c * bw.ldk[m] + t];
+      double sq = 0.0;
+#pragma unroll
+      for (int k = 0; k < MAX_D; ++k)
+        if (k < d) {
+          const double df = xm[k] - bw.xs[m][(size_t)t * d + k];
+          sq += df * df;
+        }
+      const double gc = u * stationary_grad_coeff(bw.kind[m], bw.outputscale[m], sq);
+#pragma unroll
+      for (int k = 0; k < MAX_D; ++k)
+        if (k < d) grad[k] += gc * (xm[k] - bw.xs[m][(size_t)t * d + k]) / bw.ls[m][k];
+    }
+    if (threadIdx.x == 0)
+      for (int k = 0; k < MAX_D; ++k) grad[k] += s2 * s_sc[2 + k];  // prior-covariance term, once
+    __syncthreads();  // s_r / s_sc are reused by the next objective
+  }
+#pragma unroll
+  for (int k = 0; k < MAX_D; ++k) grad[k] = warp_sum(grad[k]);
+  if (lane == 0)
+    for (int k = 0; k < MAX_D; ++k) s_red[warp * MAX_D + k] = grad[k];
+  __syncthreads();
+  if (threadIdx.x < d) {
+    double acc = 0.0;
+    for (int wv = 0; wv < nwarps; ++wv) acc += s_red[wv * MAX_D + threadIdx.x];
+    bw.dX[(size_t)c * d + threadIdx.x] = acc;
+  }
+}
+
+int emax_finalize_coupled(int C, int S, const EmaxOut& out, const CoupledBackward& bw, cudaStream_t st) {
+  if (C == 0 || out.kg == nullptr) return DKG_OK;
+  int n_pad_max = 0;
+  for (int m = 0; m < bw.M; ++m) n_pad_max = n_pad_max > bw.n_pad[m] ? n_pad_max : bw.n_pad[m];
+  size_t smem = sizeof(double) * S;
+  if (bw.dX != nullptr)
+    smem = sizeof(double) * ((size_t)S + n_pad_max + 2 + MAX_D + MAX_M + (CP_THREADS / 32) * MAX_D);
+  if (smem > 48 * 1024)
+    DKG_CUDA_OK(cudaFuncSetAttribute(finalize_coupled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  finalize_coupled_kernel<<<C, CP_THREADS, smem, st>>>(S, out, bw);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+}  // namespace dkg

@@ -132,9 +132,16 @@ int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int
 // ------------------------------------------------------------------------------------------
 // per-set facts shared by all stages
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t a_base(const LineBatch& lb, int c, int j) {
+  const int jt = lb.row_mod ? (c % lb.row_mod) : j;
+  return (size_t)c * lb.a_sc + (size_t)jt * lb.a_sj;
+}
+__device__ __forceinline__ size_t am_index(const LineBatch& lb, int c, int j) {
+  const int jt = lb.row_mod ? (c % lb.row_mod) : j;
+  return (size_t)c * lb.am_sc + jt;
+}
 __device__ __forceinline__ double line_intercept(const LineBatch& lb, int c, int j, int n) {
-  return n < lb.NA ? lb.A[(size_t)c * lb.a_sc + (size_t)j * lb.a_sj + n]
-                   : lb.a_own[(size_t)c * lb.S + j];
+  return n < lb.NA ? lb.A[a_base(lb, c, j) + n] : lb.a_own[(size_t)c * lb.S + j];
 }
 
 struct SetInfo {
@@ -154,8 +161,8 @@ __device__ __forceinline__ SetInfo set_info(const LineBatch& lb, const EmaxScrat
   s.zmax = sc.zst[c * 2 + 1];
   s.iP = sc.zarg[c * 2 + 0];
   s.iQ = sc.zarg[c * 2 + 1];
-  s.amax = lb.Amax[(size_t)c * lb.am_sc + j];
-  s.iT = lb.Aarg[(size_t)c * lb.am_sc + j];
+  s.amax = lb.Amax[am_index(lb, c, j)];
+  s.iT = lb.Aarg[am_index(lb, c, j)];
   s.own_is_max = 0;
   if (lb.a_own != nullptr) {
     const double ao = lb.a_own[(size_t)c * lb.S + j];
@@ -222,7 +229,7 @@ constexpr int POOL_CAP = 2048;
 __device__ __forceinline__ unsigned long long append_survivor(const LineBatch& lb, const EmaxScratch& sc,
                                                               const double4& par, size_t set, int c,
                                                               int j, int n, int pos, int* side_out) {
-  const double av = lb.A[(size_t)c * lb.a_sc + (size_t)j * lb.a_sj + n];
+  const double av = lb.A[a_base(lb, c, j) + n];
   const double zv = lb.Z[(size_t)c * lb.ldz + n];
   if (pos < SURV_CAP) {
     SurvEntry e;
@@ -302,7 +309,7 @@ filter_kernel(LineBatch lb, EmaxScratch sc) {
       for (int r = 0; r < R; ++r) {
         double av;
         if (SHARED_A) av = a[r];
-        else av = lb.A[(size_t)min(c0 + g, lb.C - 1) * lb.a_sc + (size_t)j * lb.a_sj + nc[r]];
+        else av = lb.A[a_base(lb, min(c0 + g, lb.C - 1), j) + nc[r]];
         const double t1 = fma(p[g].y, z[g][r], p[g].x);
         const double t2 = fma(p[g].w, z[g][r], p[g].z);
         if ((av > t1) | (av > t2)) mask |= 1u << (g * R + r);
@@ -374,7 +381,7 @@ static int launch_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_
     DKG_CUDA_OK(cudaFuncSetAttribute(filter_kernel<G, R, false>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  if (lb.a_sc == 0)
+  if (lb.a_sc == 0 && lb.row_mod == 0)
     filter_kernel<G, R, true><<<grid, E_THREADS, smem, st>>>(lb, sc);
   else
     filter_kernel<G, R, false><<<grid, E_THREADS, smem, st>>>(lb, sc);
@@ -652,7 +659,7 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
   int nseed = 0;
   seeds[nseed++] = s.iP;
   seeds[nseed++] = s.iQ;
-  seeds[nseed++] = lb.Aarg[(size_t)c * lb.am_sc + j];
+  seeds[nseed++] = lb.Aarg[am_index(lb, c, j)];
   if (lb.a_own != nullptr) seeds[nseed++] = lb.NA;
   const int total = cnt + nseed;
   const double w = s.w;

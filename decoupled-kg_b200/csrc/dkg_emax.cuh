@@ -25,6 +25,9 @@ struct LineBatch {
   const int* Aarg = nullptr;
   long long am_sc = 0;
   int NA = 0, NL = 0, S = 0, C = 0;
+  // row_mod > 0 (coupled path): every row is its own set (S == 1) and the shared intercept table /
+  // maxima are indexed by (row % row_mod) -- rows are (candidate, scalarisation) pairs
+  int row_mod = 0;
 };
 
 // one line that survived the streaming chord filter (intercept, raw slope coordinate, index)
@@ -95,5 +98,40 @@ int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cu
 int emax_overflow(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cudaStream_t st);
 // kg[c] = mean_j terms[c, j] and, if bw.dX, the fused envelope-theorem backward
 int emax_finalize(const LineBatch& lb, const EmaxOut& out, const BackwardArgs& bw, cudaStream_t st);
+
+// Coupled evaluation (reference calculate_discrete_kg, discretekg.py:162-235): the slope of line n
+// for scalarisation j is  sum_m W[j,m]^2 Cov_m(x, x_n) / sqrt(sum_m W[j,m]^2 var_m(x)).
+struct CoupledArgs {
+  int C = 0, S = 0, M = 0, d = 0, N = 0, ldz = 0;
+  const double* W = nullptr;        // [S, M]
+  const double* COV[MAX_M] = {};    // [C, ldz] covariance rows (un-standardised); column N = Cov_m(x,x)
+  const double* varn[MAX_M] = {};   // [C] noisy predictive variance of objective m (un-standardised)
+  double* sdj = nullptr;            // [C, S] out: sqrt of the scalarised noisy variance
+  double* Zc = nullptr;             // [C * S, ldz] out: slope rows
+};
+int coupled_slopes(const CoupledArgs& a, cudaStream_t st);
+
+struct CoupledBackward {
+  double* dX = nullptr;             // [C, d]
+  const double* X = nullptr;        // [C, d]
+  const double* W = nullptr;        // [S, M]
+  const double* Zc = nullptr;       // [C * S, ldz]
+  const double* sdj = nullptr;      // [C, S]
+  int ldz = 0, M = 0, d = 0, S = 0, N = 0;
+  const double* T[MAX_M] = {};      // [C, ldk_m]
+  int ldk[MAX_M] = {};
+  const double* BT[MAX_M] = {};     // [N, n_pad_m]
+  int n_pad[MAX_M] = {};
+  const double* xd_s[MAX_M] = {};   // [N_pad, d]
+  const double* xs[MAX_M] = {};
+  const double* alpha[MAX_M] = {};
+  int ntr[MAX_M] = {};
+  int kind[MAX_M] = {};
+  double outputscale[MAX_M] = {};
+  double y_std[MAX_M] = {};
+  double ls[MAX_M][MAX_D] = {};
+};
+// kg[c] = mean_j terms[c*S + j]; optional backward for the coupled path (CTA per candidate)
+int emax_finalize_coupled(int C, int S, const EmaxOut& out, const CoupledBackward& bw, cudaStream_t st);
 
 }  // namespace dkg

@@ -104,4 +104,52 @@ int launch_place_own(const double* zown, int rows, double* Z, int ldz, int N, cu
   return DKG_OK;
 }
 
+// ---- helpers of the coupled path ------------------------------------------------------------
+struct LsArgF { double v[MAX_D]; };
+
+__global__ void xscale_kernel(const double* __restrict__ X, int C, int d, LsArgF ls, double* __restrict__ Xs) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C * d) Xs[i] = X[i] / ls.v[i % d];
+}
+int launch_xprep_scaled(const double* X, int C, int d, const double* ls_host, double* Xs, cudaStream_t st) {
+  if (C == 0) return DKG_OK;
+  LsArgF a;
+  for (int k = 0; k < MAX_D; ++k) a.v[k] = k < d ? ls_host[k] : 1.0;
+  xscale_kernel<<<ceil_div(C * d, 256), 256, 0, st>>>(X, C, d, a, Xs);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+__global__ void fill_ones_kernel(double* __restrict__ p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 1.0;
+}
+int fill_ones(double* p, int n, cudaStream_t st) {
+  if (n == 0) return DKG_OK;
+  fill_ones_kernel<<<ceil_div(n, 256), 256, 0, st>>>(p, n);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// COV[c, N] = (k(x,x) - KX[c,:] . T[c,:]) * ystd2  (Cov_m(x_c, x_c), noise free); warp per candidate
+__global__ void place_latent_var_kernel(const double* __restrict__ KX, int n_pad, const double* __restrict__ T,
+                                        int ldk, int ntr, int C, int kind, double outputscale,
+                                        double ystd2, double* __restrict__ COV, int ldz, int N) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double acc = 0.0;
+  for (int t = lane; t < ntr; t += 32) acc += KX[(size_t)c * n_pad + t] * T[(size_t)c * ldk + t];
+  acc = warp_sum(acc);
+  if (lane == 0) COV[(size_t)c * ldz + N] = (stationary_from_sq(kind, outputscale, 0.0) - acc) * ystd2;
+}
+int place_latent_var(const double* KX, int n_pad, const double* T, int ldk, int ntr, int C, int kind,
+                     double outputscale, double ystd2, double* COV, int ldz, int N, cudaStream_t st) {
+  if (C == 0) return DKG_OK;
+  place_latent_var_kernel<<<ceil_div(C * 32, 256), 256, 0, st>>>(KX, n_pad, T, ldk, ntr, C, kind,
+                                                                outputscale, ystd2, COV, ldz, N);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
 }  // namespace dkg

@@ -59,5 +59,9 @@ int launch_var(const double* KX, int n_pad, const double* T, int ldk, int ntr, i
                double outputscale, double noise, double ystd2, double* var, double* sd,
                double* zown, cudaStream_t st);
 int launch_place_own(const double* zown, int rows, double* Z, int ldz, int N, cudaStream_t st);
+int launch_xprep_scaled(const double* X, int C, int d, const double* ls_host, double* Xs, cudaStream_t st);
+int fill_ones(double* p, int n, cudaStream_t st);
+int place_latent_var(const double* KX, int n_pad, const double* T, int ldk, int ntr, int C, int kind,
+                     double outputscale, double ystd2, double* COV, int ldz, int N, cudaStream_t st);
 
 }  // namespace dkg

@@ -18,6 +18,14 @@ struct ObjState {
   double ls[MAX_D];
   double* xs = nullptr;     // [n, d]   train inputs / lengthscale
   double* alpha = nullptr;  // [n_pad]  mean cache K^-1 (y - c), zero padded
+  // conditioning state (only for objectives whose observation is fantasised: the target in the
+  // decoupled path, every objective in the coupled path)
+  int ldk = 0;               // row stride of Kinv / T (n rounded up to GEMM_BN)
+  double* chol = nullptr;    // [n, n]        lower Cholesky of K + noise I
+  double* Kinv = nullptr;    // [n_pad, ldk]
+  double* B = nullptr;       // [n_pad, N_pad]  K^-1 k(X_train, X_disc), zero padded
+  double* BT = nullptr;      // [N, n_pad]
+  double* xd_s = nullptr;    // [N_pad, d]    discretisation / lengthscale
 };
 
 struct Workspace {
@@ -31,6 +39,13 @@ struct Workspace {
   double* var = nullptr;    // [cap_C]           noisy predictive variance (un-standardised)
   double* sd = nullptr;     // [cap_C]           sqrt(var)
   double* zown = nullptr;   // [cap_C]           slope of the candidate's own line
+  // coupled path only (per objective m, capacity cap_C each)
+  double* KXm[MAX_M] = {};   // [cap_C, n_pad_m]
+  double* Tm[MAX_M] = {};    // [cap_C, ldk_m]
+  double* varlat[MAX_M] = {};// [cap_C]  latent predictive variance (model space)
+  double* COVm[MAX_M] = {};  // [chunk_C, ldz]  covariance rows Cov_m(x_c, .), column N = Cov_m(x_c, x_c)
+  double* sdj = nullptr;     // [cap_C, S] sqrt of the scalarised noisy variance
+  double* Zc = nullptr;      // [chunk_C * S, ldz]  per-(candidate, scalarisation) slope rows
   double* Xs = nullptr;     // [cap_C, d]        candidates / lengthscale_i
   double* a_new = nullptr;  // [cap_C, S]        intercept of the candidate's own line
   double* kg_terms = nullptr;  // [cap_C, S]
@@ -58,7 +73,7 @@ constexpr int HULL_CAP = 64;    // hull vertices recorded per (candidate, scalar
 }  // namespace dkg
 
 struct dkg_plan {
-  int M = 0, d = 0, N = 0, S = 0, target = 0;
+  int M = 0, d = 0, N = 0, S = 0, target = 0;  // target < 0: coupled evaluation
   int N_pad = 0;  // N rounded up to GEMM_BN
   int ldz = 0;    // row stride of the slope buffer (>= N+1, multiple of 16)
   int ldk = 0;    // row stride of Kinv / T (n_i rounded up to GEMM_BN)

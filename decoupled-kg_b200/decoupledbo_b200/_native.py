@@ -167,7 +167,7 @@ class Plan:
         model: GPModelList,
         x_discretisation: Tensor,
         scalarisation_weights: Tensor,
-        target_output_ix: int,
+        target_output_ix: Optional[int],
     ):
         self._handle = c_void_p(0)
         lib = load_library()
@@ -182,7 +182,7 @@ class Plan:
         if W.dim() != 2 or W.shape[1] != M:
             raise ValueError(f"scalarisation_weights must be (S, {M}); got {tuple(W.shape)}")
         self.N, self.d, self.M, self.S = xd.shape[0], d, M, W.shape[0]
-        self.target = int(target_output_ix)
+        self.target = -1 if target_output_ix is None else int(target_output_ix)  # -1 = coupled
         objs = (_Objective * M)()
         keep = []
         for m, o in enumerate(model.models):

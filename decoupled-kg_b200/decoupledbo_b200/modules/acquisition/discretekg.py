@@ -17,6 +17,10 @@ What changes relative to the reference (by design):
 * the (N+1) x (N+1) posterior covariance (``discretekg.py:301``) is never formed: only its first
   row is computed, as a tensor-core contraction.
 * the backward is a fused closed-form (envelope theorem) kernel, not autograd through the graph.
+
+Both evaluation modes of the reference are covered: ``target_output_ix=i`` (decoupled,
+``calculate_discrete_kg_conditioning_on_single_output``, ``discretekg.py:238-338``) and
+``target_output_ix=None`` (coupled, ``calculate_discrete_kg``, ``discretekg.py:162-235``).
 """
 
 from __future__ import annotations
@@ -143,12 +147,6 @@ class DiscreteKnowledgeGradient(AcquisitionFunction):
     def _get_plan(self) -> "_native.Plan":
         """Build (once) the candidate-independent GPU state for this acquisition function."""
         if self._plan is None:
-            if self.target_output_ix is None:
-                raise UnsupportedError(
-                    "The coupled evaluation (target_output_ix=None, reference "
-                    "calculate_discrete_kg, discretekg.py:162-235) is not implemented by the "
-                    "CUDA path yet; pass target_output_ix."
-                )
             if not hasattr(self.model, "models"):
                 raise UnsupportedError(
                     f"Input 'model' must be a 'ModelListGP'. Got {type(self.model)=}."

@@ -80,7 +80,8 @@ DKG_API const char* dkg_last_error(void);
  *   x_disc_dev     [N, d] discretisation (discretekg.py:121)
  *   weights_host   [S, M] scalarisation weights (discretekg.py:122)
  *   target_ix      objective whose observation is fantasised (discretekg.py:123, decoupled path
- *                  discretekg.py:238-338); must be in [0, M)
+ *                  discretekg.py:238-338), in [0, M); or -1 for the coupled evaluation in which all
+ *                  objectives are observed together (target_output_ix=None, discretekg.py:162-235)
  *   flags          0, or DKG_PLAN_* bits
  */
 #define DKG_PLAN_DEFAULT 0u

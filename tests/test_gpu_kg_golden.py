@@ -19,7 +19,7 @@ def _acqf(P, target, device=None):
 
 
 @pytest.mark.parametrize("name", sorted(GOLDEN_KG_SPECS))
-@pytest.mark.parametrize("target", [0, 1])
+@pytest.mark.parametrize("target", [0, 1, None])
 def test_kg_and_gradient_match_reference_code_golden(name, target):
     G = load_golden("kg_reference_code_golden.npz")
     P = small_problem(**GOLDEN_KG_SPECS[name])
@@ -27,7 +27,8 @@ def test_kg_and_gradient_match_reference_code_golden(name, target):
     X = P.candidates.clone().requires_grad_(True)
     kg = acq(X.unsqueeze(1))
     (g,) = torch.autograd.grad(kg.sum(), X)
-    want, want_g = G[f"{name}__t{target}__kg"], G[f"{name}__t{target}__grad"]
+    key = "coupled" if target is None else f"t{target}"
+    want, want_g = G[f"{name}__{key}__kg"], G[f"{name}__{key}__grad"]
     scale = float(acq._get_plan().read("A0").abs().max())
     # fp64 mode: rel 1e-9 (north star), with an absolute floor of 1e-12 x |intercepts| because KG
     # is the small difference E[max] - max

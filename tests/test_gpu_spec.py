@@ -46,3 +46,17 @@ def test_reference_batch_limit_one_gives_same_api():
     x, i, v = spec.optimize_for_single_objective(P.model, torch.tensor([1.0, 2.0]), 2,
                                                   scalarisation_weights=P.weights)
     assert x.shape == (1, 2) and isinstance(i, int) and torch.is_tensor(v)
+
+
+def test_optimize_for_full_evaluation_coupled():
+    """strategy.py:242-273: coupled evaluation (target_output_ix=None) through optimize_acqf."""
+    from decoupledbo_b200.modules.acquisition_optimisation_strategy import DiscreteKgOptimisationSpec
+
+    P = small_problem(n_train=12, noise=(1e-2, 1e-2))
+    om = oracle_model(P.model)
+    spec = DiscreteKgOptimisationSpec(4, num_restarts=4, raw_samples=16, batch_limit=4, max_iter=30)
+    torch.manual_seed(3)
+    x, v = spec.optimize_for_full_evaluation(P.model, 2, scalarisation_weights=P.weights)
+    assert x.shape == (1, 2) and float(x.min()) >= 0.0 and float(x.max()) <= 1.0
+    want = odk.kg_coupled(om, x[0], odk.make_std_grid(4, 2), P.weights, dense=True)
+    np.testing.assert_allclose(float(v), float(want), rtol=1e-8, atol=1e-12)

@@ -63,13 +63,6 @@ def test_no_cpu_fallback(problem):
         acq(P.candidates.unsqueeze(1))
 
 
-def test_coupled_path_is_refused_loudly(problem):
-    P = problem
-    acq = DiscreteKnowledgeGradient(P.model, P.x_disc, P.weights, None)
-    with pytest.raises(UnsupportedError, match="coupled"):
-        acq(P.candidates.unsqueeze(1))
-
-
 def _duck_single(o, with_transform):
     ns = types.SimpleNamespace
     gp = ns(

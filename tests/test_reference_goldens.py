@@ -44,6 +44,22 @@ def test_cuda_path_reproduces_reference_golden():
 
 
 @pytest.mark.gpu
+def test_cuda_coupled_path_reproduces_reference_golden():
+    from decoupledbo_b200.modules.acquisition.discretekg import DiscreteKnowledgeGradient
+
+    model, disc, W, X, G = refit_reference_problem()
+    acq = DiscreteKnowledgeGradient(model, x_discretisation=disc, scalarisation_weights=W)  # coupled
+    with torch.no_grad():
+        kg = acq(X)
+    torch.testing.assert_close(kg, torch.tensor(G["golden_coupled"]), atol=1e-4, rtol=1e-3)  # :61-63
+    assert float(kg[0, 0]) == pytest.approx(float(G["golden_scalar_coupled"]), rel=3e-5)  # :93
+    want = odk.forward(oracle_model(model), X, disc, W, None, dense=True)
+    np.testing.assert_allclose(kg.numpy(), want.numpy(), rtol=1e-9, atol=1e-13)
+    x = torch.tensor([[[0.51, 0.51]]], dtype=torch.double, requires_grad=True)  # :110-120
+    torch.autograd.gradcheck(acq, (x,), raise_exception=True)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("target", [0, 1])
 def test_cuda_gradcheck_on_reference_fixture(target):
     """test_discretekg.py:122-135: gradcheck at x = (0.51, 0.51) for both objectives."""

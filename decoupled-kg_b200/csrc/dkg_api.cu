@@ -158,11 +158,12 @@ static void destroy_plan(dkg_plan* p) {
 // Cholesky of K_m + noise I with GPyTorch's jitter retries (psd_safe_cholesky: 1e-8 * 10^k,
 // k < 3, in double) [recalled].  Leaves L in `Lbuf` (n x n).
 static int factor_objective(const ObjState& o, int d, double* Lbuf, int* info_dev, double* jitter_out,
-                            cudaStream_t st) {
+                            cudaStream_t st, bool blocked) {
   const double jitters[4] = {0.0, 1e-8, 1e-7, 1e-6};
   for (int k = 0; k < 4; ++k) {
     DKG_TRY(kmat_train(o, d, jitters[k], Lbuf, st));
-    DKG_TRY(cholesky_inplace(Lbuf, o.n, info_dev, st));
+    if (blocked) DKG_TRY(cholesky_blocked(Lbuf, o.n, o.n, info_dev, st));
+    else DKG_TRY(cholesky_inplace(Lbuf, o.n, info_dev, st));
     int info = 0;
     DKG_CUDA_OK(cudaMemcpyAsync(&info, info_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
     DKG_CUDA_OK(cudaStreamSynchronize(st));
@@ -211,41 +212,74 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
     if ((rc = dev_alloc(&o.xs, (size_t)o.n * d)) != DKG_OK) break;
     if ((rc = dev_alloc(&o.alpha, (size_t)o.n_pad)) != DKG_OK) break;
     if ((rc = scale_rows(s.train_x_dev, o.n, d, o.ls, o.xs, st)) != DKG_OK) break;
+    const bool need_state = (m == tgt || tgt < 0);
+    const int n = o.n;
     double jit = 0.0;
-    if ((rc = factor_objective(o, d, Lbuf, info_dev, &jit, st)) != DKG_OK) break;
-    if (m == tgt || tgt < 0) p->jitter = jit > p->jitter ? jit : p->jitter;
-    if ((rc = transpose(Lbuf, o.n, o.n, o.n, LTbuf, o.n, st)) != DKG_OK) break;
-    // mean cache: alpha = K^-1 (y - c)
-    if ((rc = residual(s.train_y_dev, o.n, o.mean_const, o.alpha, st)) != DKG_OK) break;
-    if ((rc = cholesky_solve_inplace(Lbuf, LTbuf, o.n, o.alpha, 1, 1, st)) != DKG_OK) break;
-    cudaMemcpyAsync(p->alpha_all + off, o.alpha, sizeof(double) * o.n, cudaMemcpyDeviceToDevice, st);
-    off += o.n;
-    if ((rc = mu_disc(p->xd, N, d, o, p->mu_disc, M, m, st)) != DKG_OK) break;
-    if (m == tgt || tgt < 0) {
-      const int n = o.n;
-      o.ldk = round_up(n, GEMM_BN);
-      double* cholT = nullptr;
-      if ((rc = dev_alloc(&o.chol, (size_t)n * n)) != DKG_OK) break;
-      if ((rc = dev_alloc(&cholT, (size_t)n * n)) != DKG_OK) break;
-      cudaMemcpyAsync(o.chol, Lbuf, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st);
-      cudaMemcpyAsync(cholT, LTbuf, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st);
-      // Kinv = K^-1 (solve against the identity)
-      if ((rc = dev_alloc(&o.Kinv, (size_t)o.n_pad * o.ldk)) != DKG_OK) break;
-      if ((rc = set_identity(o.Kinv, n, o.ldk, st)) != DKG_OK) break;
-      if ((rc = cholesky_solve_inplace(o.chol, cholT, n, o.Kinv, n, o.ldk, st)) != DKG_OK) break;
-      // B = K^-1 k(X_train, X_disc)
-      if ((rc = dev_alloc(&o.xd_s, (size_t)p->N_pad * d)) != DKG_OK) break;
-      if ((rc = scale_rows(p->xd, N, d, o.ls, o.xd_s, st)) != DKG_OK) break;
-      if ((rc = dev_alloc(&o.B, (size_t)o.n_pad * p->N_pad)) != DKG_OK) break;
-      if ((rc = kcross(o, o.xd_s, N, d, o.B, p->N_pad, st)) != DKG_OK) break;
-      if ((rc = cholesky_solve_inplace(o.chol, cholT, n, o.B, N, p->N_pad, st)) != DKG_OK) break;
-      if ((rc = dev_alloc(&o.BT, (size_t)N * o.n_pad)) != DKG_OK) break;
-      if ((rc = transpose(o.B, o.n_pad, N, p->N_pad, o.BT, o.n_pad, st)) != DKG_OK) break;
-      cudaStreamSynchronize(st);
-      dev_free(cholT);
-      if (m == tgt) {  // aliases used by the decoupled path
-        p->ldk = o.ldk; p->chol = o.chol; p->Kinv = o.Kinv; p->B = o.B; p->BT = o.BT; p->xd_s = o.xd_s;
+    if (n <= chol_fast_max()) {
+      // ---- fast path: blocked Cholesky, explicit L^-1, solves as DMMA GEMMs ----
+      if ((rc = factor_objective(o, d, Lbuf, info_dev, &jit, st, /*blocked=*/true)) != DKG_OK) break;
+      const int np = round_up(n, GEMM_BM);  // 128-padded square buffers for the GEMM operands
+      double *Linv = nullptr, *LinvT = nullptr, *tmpv = nullptr, *Ybuf = nullptr;
+      auto cleanup = [&]() { cudaStreamSynchronize(st); dev_free(Linv); dev_free(LinvT); dev_free(tmpv); dev_free(Ybuf); };
+      if ((rc = dev_alloc(&Linv, (size_t)np * np)) != DKG_OK) break;
+      if ((rc = dev_alloc(&LinvT, (size_t)np * np)) != DKG_OK) { cleanup(); break; }
+      if ((rc = dev_alloc(&tmpv, (size_t)np)) != DKG_OK) { cleanup(); break; }
+      if ((rc = tri_inverse(Lbuf, n, n, Linv, np, st)) != DKG_OK) { cleanup(); break; }
+      if ((rc = transpose(Linv, n, n, np, LinvT, np, st)) != DKG_OK) { cleanup(); break; }
+      // mean cache: alpha = K^-1 (y - c) = L^-T (L^-1 r)
+      if ((rc = residual(s.train_y_dev, n, o.mean_const, o.alpha, st)) != DKG_OK) { cleanup(); break; }
+      if ((rc = matvec(Linv, np, n, n, o.alpha, tmpv, st)) != DKG_OK) { cleanup(); break; }
+      if ((rc = matvec(LinvT, np, n, n, tmpv, o.alpha, st)) != DKG_OK) { cleanup(); break; }
+      cudaMemcpyAsync(p->alpha_all + off, o.alpha, sizeof(double) * n, cudaMemcpyDeviceToDevice, st);
+      off += n;
+      if ((rc = mu_disc(p->xd, N, d, o, p->mu_disc, M, m, st)) != DKG_OK) { cleanup(); break; }
+      if (need_state) {
+        o.ldk = np;
+        if ((rc = dev_alloc(&o.chol, (size_t)n * n)) != DKG_OK) { cleanup(); break; }
+        cudaMemcpyAsync(o.chol, Lbuf, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st);
+        // Kinv = L^-T L^-1
+        if ((rc = dev_alloc(&o.Kinv, (size_t)np * o.ldk)) != DKG_OK) { cleanup(); break; }
+        if ((rc = gemm_store(LinvT, np, Linv, np, np, o.ldk, o.n_pad, o.Kinv, o.ldk, st)) != DKG_OK) { cleanup(); break; }
+        // B = K^-1 k(X_train, X_disc) = L^-T (L^-1 Kxd)
+        if ((rc = dev_alloc(&o.xd_s, (size_t)p->N_pad * d)) != DKG_OK) { cleanup(); break; }
+        if ((rc = scale_rows(p->xd, N, d, o.ls, o.xd_s, st)) != DKG_OK) { cleanup(); break; }
+        if ((rc = dev_alloc(&o.B, (size_t)np * p->N_pad)) != DKG_OK) { cleanup(); break; }
+        if ((rc = dev_alloc(&Ybuf, (size_t)np * p->N_pad)) != DKG_OK) { cleanup(); break; }
+        if ((rc = kcross(o, o.xd_s, N, d, o.B, p->N_pad, st)) != DKG_OK) { cleanup(); break; }
+        if ((rc = gemm_store(Linv, np, o.B, p->N_pad, np, p->N_pad, o.n_pad, Ybuf, p->N_pad, st)) != DKG_OK) { cleanup(); break; }
+        if ((rc = gemm_store(LinvT, np, Ybuf, p->N_pad, np, p->N_pad, o.n_pad, o.B, p->N_pad, st)) != DKG_OK) { cleanup(); break; }
+        if ((rc = dev_alloc(&o.BT, (size_t)N * o.n_pad)) != DKG_OK) { cleanup(); break; }
+        if ((rc = transpose(o.B, o.n_pad, N, p->N_pad, o.BT, o.n_pad, st)) != DKG_OK) { cleanup(); break; }
       }
+      cleanup();
+    } else {
+      // ---- general path (large n): column-at-a-time Cholesky, per-column substitution ----
+      if ((rc = factor_objective(o, d, Lbuf, info_dev, &jit, st, /*blocked=*/false)) != DKG_OK) break;
+      if ((rc = transpose(Lbuf, n, n, n, LTbuf, n, st)) != DKG_OK) break;
+      if ((rc = residual(s.train_y_dev, n, o.mean_const, o.alpha, st)) != DKG_OK) break;
+      if ((rc = cholesky_solve_inplace(Lbuf, LTbuf, n, o.alpha, 1, 1, st)) != DKG_OK) break;
+      cudaMemcpyAsync(p->alpha_all + off, o.alpha, sizeof(double) * n, cudaMemcpyDeviceToDevice, st);
+      off += n;
+      if ((rc = mu_disc(p->xd, N, d, o, p->mu_disc, M, m, st)) != DKG_OK) break;
+      if (need_state) {
+        o.ldk = round_up(n, GEMM_BN);
+        if ((rc = dev_alloc(&o.chol, (size_t)n * n)) != DKG_OK) break;
+        cudaMemcpyAsync(o.chol, Lbuf, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st);
+        if ((rc = dev_alloc(&o.Kinv, (size_t)o.n_pad * o.ldk)) != DKG_OK) break;
+        if ((rc = set_identity(o.Kinv, n, o.ldk, st)) != DKG_OK) break;
+        if ((rc = cholesky_solve_inplace(Lbuf, LTbuf, n, o.Kinv, n, o.ldk, st)) != DKG_OK) break;
+        if ((rc = dev_alloc(&o.xd_s, (size_t)p->N_pad * d)) != DKG_OK) break;
+        if ((rc = scale_rows(p->xd, N, d, o.ls, o.xd_s, st)) != DKG_OK) break;
+        if ((rc = dev_alloc(&o.B, (size_t)o.n_pad * p->N_pad)) != DKG_OK) break;
+        if ((rc = kcross(o, o.xd_s, N, d, o.B, p->N_pad, st)) != DKG_OK) break;
+        if ((rc = cholesky_solve_inplace(Lbuf, LTbuf, n, o.B, N, p->N_pad, st)) != DKG_OK) break;
+        if ((rc = dev_alloc(&o.BT, (size_t)N * o.n_pad)) != DKG_OK) break;
+        if ((rc = transpose(o.B, o.n_pad, N, p->N_pad, o.BT, o.n_pad, st)) != DKG_OK) break;
+      }
+    }
+    if (need_state) p->jitter = jit > p->jitter ? jit : p->jitter;
+    if (m == tgt) {  // aliases used by the decoupled path
+      p->ldk = o.ldk; p->chol = o.chol; p->Kinv = o.Kinv; p->B = o.B; p->BT = o.BT; p->xd_s = o.xd_s;
     }
   }
   if (rc == DKG_OK) {

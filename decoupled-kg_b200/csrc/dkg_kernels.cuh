@@ -19,6 +19,11 @@ int mu_disc(const double* xd, int N, int d, const ObjState& o, double* mu, int M
 int build_a0(const double* mu, int N, int M, const double* W, int S, double* A0, int ld,
              double* A0max, int* A0arg, cudaStream_t st);
 
+int cholesky_blocked(double* A, int n, int ld, int* info_dev, cudaStream_t st);
+int tri_inverse(const double* L, int n, int ldl, double* X, int ldx, cudaStream_t st);
+int matvec(const double* A, int lda, int rows, int cols, const double* x, double* y, cudaStream_t st);
+int chol_fast_max();
+
 // ---- dkg_gemm.cu -----------------------------------------------------------------------------
 struct CovEpilogue {
   const double* xs;    // [rows, d] candidates / lengthscale_i

@@ -348,3 +348,236 @@ int build_a0(const double* mu, int N, int M, const double* W, int S, double* A0,
 }
 
 }  // namespace dkg
+
+// ==========================================================================================
+// Fast path of the plan preparation (n <= CHOL_FAST_MAX): blocked Cholesky in one CTA with the
+// panel in shared memory, explicit inverse of the triangular factor by block columns, and the
+// two big solves  K^-1 R = L^-T (L^-1 R)  as DMMA GEMMs (dkg_gemm.cu) instead of per-column
+// substitution (which was 5-9 ms per solve at n = 400, N = 16384).
+// ==========================================================================================
+namespace dkg {
+
+constexpr int CB = 32;                 // block size
+constexpr int CHOL_FAST_MAX = 800;     // panel (n x 33 doubles) must fit in shared memory
+
+// Lower Cholesky, in place, row-major n x n with leading dimension ld (>= n).  One CTA.
+__global__ void __launch_bounds__(1024, 1)
+cholesky_blocked_kernel(double* __restrict__ A, int n, int ld, int* __restrict__ info) {
+  extern __shared__ __align__(16) double cs[];
+  double* Ld = cs;                 // [CB][CB + 1] diagonal block
+  double* Lp = cs + CB * (CB + 1); // [n][CB + 1]  panel below the diagonal block
+  __shared__ int s_fail;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  for (int k0 = 0; k0 < n; k0 += CB) {
+    const int kb = min(CB, n - k0);
+    for (int e = tid; e < kb * kb; e += nt) {
+      const int i = e / kb, j = e - i * kb;
+      Ld[i * (CB + 1) + j] = (j <= i) ? A[(size_t)(k0 + i) * ld + k0 + j] : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {  // unblocked factorisation of the kb x kb block, lane = row
+      for (int j = 0; j < kb; ++j) {
+        const double djj = Ld[j * (CB + 1) + j];
+        if (!(djj > 0.0)) {
+          if (lane == 0) s_fail = k0 + j + 1;
+          break;
+        }
+        const double piv = sqrt(djj);
+        __syncwarp();
+        if (lane == j) Ld[j * (CB + 1) + j] = piv;
+        if (lane > j && lane < kb) Ld[lane * (CB + 1) + j] /= piv;
+        __syncwarp();
+        if (lane > j && lane < kb) {
+          const double lij = Ld[lane * (CB + 1) + j];
+          for (int c = j + 1; c <= lane; ++c) Ld[lane * (CB + 1) + c] -= lij * Ld[c * (CB + 1) + j];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (s_fail) break;
+    for (int e = tid; e < kb * kb; e += nt) {
+      const int i = e / kb, j = e - i * kb;
+      A[(size_t)(k0 + i) * ld + k0 + j] = Ld[i * (CB + 1) + j];  // upper part of the block -> 0
+    }
+    const int m = n - k0 - kb;  // rows below
+    // panel: row r of A[k0+kb.., k0..k0+kb) times Ld^-T ; one thread per row
+    for (int r = tid; r < m; r += nt) {
+      double x[CB];
+      const double* src = A + (size_t)(k0 + kb + r) * ld + k0;
+#pragma unroll
+      for (int j = 0; j < CB; ++j) x[j] = j < kb ? src[j] : 0.0;
+#pragma unroll
+      for (int j = 0; j < CB; ++j) {
+        if (j < kb) {
+          double acc = x[j];
+#pragma unroll
+          for (int c = 0; c < CB; ++c)
+            if (c < j) acc -= x[c] * Ld[j * (CB + 1) + c];
+          x[j] = acc / Ld[j * (CB + 1) + j];
+        }
+      }
+      double* dst = A + (size_t)(k0 + kb + r) * ld + k0;
+#pragma unroll
+      for (int j = 0; j < CB; ++j)
+        if (j < kb) {
+          dst[j] = x[j];
+          Lp[r * (CB + 1) + j] = x[j];
+        }
+    }
+    __syncthreads();
+    // trailing update of the lower triangle: A22[i, c] -= Lp[i, :] . Lp[c, :]   (c <= i)
+    const int mt = (m + 3) / 4;  // 4 x 4 register tiles
+    const int ntiles = mt * (mt + 1) / 2;
+    for (int t = tid; t < ntiles; t += nt) {
+      // t -> (ti, tc) with tc <= ti:  ti = floor((sqrt(8t+1)-1)/2)
+      int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+      while (ti * (ti + 1) / 2 > t) --ti;
+      const int tc = t - ti * (ti + 1) / 2;
+      double acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+      for (int j = 0; j < kb; ++j) {
+        double li[4], lc[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int ri = ti * 4 + a, rc = tc * 4 + a;
+          li[a] = ri < m ? Lp[ri * (CB + 1) + j] : 0.0;
+          lc[a] = rc < m ? Lp[rc * (CB + 1) + j] : 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] += li[a] * lc[b];
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int ri = ti * 4 + a, rc = tc * 4 + b;
+          if (ri < m && rc <= ri) A[(size_t)(k0 + kb + ri) * ld + k0 + kb + rc] -= acc[a][b];
+        }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) info[0] = s_fail;
+  __syncthreads();
+  if (!s_fail)
+    for (long long e = tid; e < (long long)n * n; e += nt) {
+      const int i = (int)(e / n), k = (int)(e % n);
+      if (k > i) A[(size_t)i * ld + k] = 0.0;
+    }
+}
+
+int cholesky_blocked(double* A, int n, int ld, int* info_dev, cudaStream_t st) {
+  const size_t smem = sizeof(double) * ((size_t)CB * (CB + 1) + (size_t)n * (CB + 1));
+  static bool attr = false;
+  if (!attr) {
+    DKG_CUDA_OK(cudaFuncSetAttribute(cholesky_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(double) * ((size_t)CB * (CB + 1) + (size_t)CHOL_FAST_MAX * (CB + 1)))));
+    attr = true;
+  }
+  cholesky_blocked_kernel<<<1, 1024, smem, st>>>(A, n, ld, info_dev);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// X = L^-1 (lower triangular), by block columns: CTA jb computes X[:, jb-block].
+//   X[jb][jb] = L[jb][jb]^-1 ;  X[ib][jb] = -L[ib][ib]^-1 * sum_{kb=jb}^{ib-1} L[ib][kb] X[kb][jb]
+// Every CTA inverts the diagonal blocks it needs itself (cheap, avoids a second kernel).
+__global__ void __launch_bounds__(1024, 1)
+tri_inverse_kernel(const double* __restrict__ L, int n, int ldl, double* __restrict__ X, int ldx) {
+  extern __shared__ __align__(16) double ts[];
+  const int nb = (n + CB - 1) / CB;
+  const int jb = blockIdx.x;
+  double* Xs = ts;                              // [nb][CB][CB+1] blocks X[kb][jb] computed so far
+  double* Dinv = Xs + (size_t)nb * CB * (CB + 1);  // [CB][CB+1] inverse of the current diagonal block
+  double* Sb = Dinv + CB * (CB + 1);            // [CB][CB+1] accumulated product
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = tid >> 5, cidx = tid & 31;      // one output element per thread: (r, cidx)
+  for (int ib = jb; ib < nb; ++ib) {
+    const int rb = min(CB, n - ib * CB);        // rows of this block
+    // ---- Dinv = L[ib][ib]^-1 : warp w solves column w (forward substitution, lane = row) ----
+    {
+      // column `warp` of the inverse: solve L d = e_warp ; serial over rows, done by lane 0..: small
+      if (warp < rb) {
+        double dcol = 0.0;  // value of row `lane`
+        for (int i = 0; i < rb; ++i) {
+          // row i: d_i = (delta_{i,warp} - sum_{k<i} L[i][k] d_k) / L[i][i] ; lanes hold d_k
+          double part = (lane < i) ? L[(size_t)(ib * CB + i) * ldl + ib * CB + lane] * dcol : 0.0;
+          part = warp_sum(part);
+          const double di = ((i == warp ? 1.0 : 0.0) - part) / L[(size_t)(ib * CB + i) * ldl + ib * CB + i];
+          if (lane == i) dcol = di;
+        }
+        if (lane < rb) Dinv[lane * (CB + 1) + warp] = dcol;
+      }
+    }
+    // ---- S = sum_{kb=jb}^{ib-1} L[ib][kb] X[kb][jb] ----
+    double acc = 0.0;
+    const int cb = min(CB, n - jb * CB);        // columns of the block column
+    for (int kb = jb; kb < ib; ++kb) {
+      const int kk = min(CB, n - kb * CB);
+      if (r < rb && cidx < cb) {
+        const double* lrow = L + (size_t)(ib * CB + r) * ldl + kb * CB;
+        const double* xcol = Xs + (size_t)kb * CB * (CB + 1) + cidx;
+        for (int q = 0; q < kk; ++q) acc += lrow[q] * xcol[q * (CB + 1)];
+      }
+    }
+    __syncthreads();  // Dinv ready
+    if (ib > jb) Sb[r * (CB + 1) + cidx] = acc;
+    __syncthreads();
+    double v = 0.0;
+    if (r < rb && cidx < cb) {
+      if (ib == jb) v = Dinv[r * (CB + 1) + cidx];
+      else {
+        for (int q = 0; q < rb; ++q) v -= Dinv[r * (CB + 1) + q] * Sb[q * (CB + 1) + cidx];
+      }
+      Xs[(size_t)ib * CB * (CB + 1) + r * (CB + 1) + cidx] = v;
+      X[(size_t)(ib * CB + r) * ldx + jb * CB + cidx] = v;
+    }
+    __syncthreads();
+  }
+}
+
+int tri_inverse(const double* L, int n, int ldl, double* X, int ldx, cudaStream_t st) {
+  const int nb = ceil_div(n, CB);
+  const size_t smem = sizeof(double) * ((size_t)nb + 2) * CB * (CB + 1);
+  static bool attr = false;
+  if (!attr) {
+    const int nbmax = ceil_div(CHOL_FAST_MAX, CB);
+    DKG_CUDA_OK(cudaFuncSetAttribute(tri_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(double) * ((size_t)nbmax + 2) * CB * (CB + 1))));
+    attr = true;
+  }
+  tri_inverse_kernel<<<nb, 1024, smem, st>>>(L, n, ldl, X, ldx);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// y = A x  (rows x cols, row-major, one warp per row)
+__global__ void matvec_kernel(const double* __restrict__ A, int lda, int rows, int cols,
+                              const double* __restrict__ x, double* __restrict__ y) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  double acc = 0.0;
+  for (int k = lane; k < cols; k += 32) acc += A[(size_t)row * lda + k] * x[k];
+  acc = warp_sum(acc);
+  if (lane == 0) y[row] = acc;
+}
+
+int matvec(const double* A, int lda, int rows, int cols, const double* x, double* y, cudaStream_t st) {
+  if (rows == 0) return DKG_OK;
+  matvec_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(A, lda, rows, cols, x, y);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+int chol_fast_max() { return CHOL_FAST_MAX; }
+
+}  // namespace dkg

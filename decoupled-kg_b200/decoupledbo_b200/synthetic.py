@@ -33,6 +33,8 @@ def sobol(n: int, d: int, seed: int) -> Tensor:
 def simplex_weights(n_scal: int, n_obj: int = 2, seed: int = 0) -> Tensor:
     """What ``sample_simplex(n_obj, n_scal, qmc=True)`` yields (``bo_loop.py:98-116``): scrambled
     Sobol in ``n_obj-1`` dims, sorted, consecutive differences.  For two objectives: (u, 1-u)."""
+    if n_obj == 1:
+        return torch.ones(n_scal, 1, dtype=torch.double)
     u = sobol(n_scal, n_obj - 1, seed)
     u, _ = torch.sort(u, dim=-1)
     pad0 = torch.zeros(n_scal, 1, dtype=torch.double)

@@ -658,7 +658,12 @@ int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev, int32_t
 int64_t dkg_plan_read(dkg_plan* plan, const char* name, double* out_dev, int64_t capacity,
                       void* stream) {
   if (!plan || !name) { set_error("NULL argument"); return DKG_EINVAL; }
-  const ObjState& ot = plan->obj[plan->target];
+  const std::string nm0(name);
+  if (plan->target < 0 && (nm0 == "B" || nm0 == "Kinv" || nm0 == "chol" || nm0 == "slopes" || nm0 == "var")) {
+    set_error("tensor '%s' is per target objective; not available for the coupled plan", name);
+    return DKG_EINVAL;
+  }
+  const ObjState& ot = plan->obj[plan->target < 0 ? 0 : plan->target];
   const Workspace& w = plan->ws;
   const double* src = nullptr;
   int64_t rows = 0, cols = 0, ld = 0;

@@ -246,7 +246,7 @@ __device__ __forceinline__ unsigned long long append_survivor(const LineBatch& l
 }
 
 template <int G, int R, bool SHARED_A>
-__global__ void __launch_bounds__(E_THREADS, 3)
+__global__ void __launch_bounds__(E_THREADS, (G * R > 16) ? 2 : 3)
 filter_kernel(LineBatch lb, EmaxScratch sc) {
   extern __shared__ __align__(16) unsigned char e_smem[];
   const int S = lb.S;
@@ -393,7 +393,7 @@ int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st) {
   if (lb.C == 0 || lb.NA == 0) return DKG_OK;
   // big batches: 4 lines per thread (fewer parameter loads per test); small ones: more CTAs
   const long long ctas4 = (long long)ceil_div(lb.C, 4) * ceil_div(lb.NA, E_THREADS * 4);
-  if (getenv("DKG_FILTER_G8") && ctas4 >= 3 * 148) return launch_filter<8, 2>(lb, sc, st);
+  if (getenv("DKG_FILTER_R8") && ctas4 >= 6 * 148) return launch_filter<4, 8>(lb, sc, st);
   if (ctas4 >= 3 * 148) return launch_filter<4, 4>(lb, sc, st);
   return launch_filter<4, 1>(lb, sc, st);
 }

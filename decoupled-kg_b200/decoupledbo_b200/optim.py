@@ -66,7 +66,7 @@ def _lbfgsb_chunk(acq_function, X0: Tensor, bounds: Tensor, maxiter: int) -> Ten
         X = torch.from_numpy(x_np.reshape(shape)).to(X0).contiguous().requires_grad_(True)
         loss = -acq_function(X).sum()
         (g,) = torch.autograd.grad(loss, X)
-        return float(loss), g.reshape(-1).cpu().numpy().astype(np.float64)
+        return float(loss.detach()), g.reshape(-1).cpu().numpy().astype(np.float64)
 
     res = minimize(
         f_and_g, X0.reshape(-1).cpu().numpy().astype(np.float64), jac=True, method="L-BFGS-B",

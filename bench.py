@@ -45,7 +45,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=["c4", "c2"])
-    ap.add_argument("--candidates", type=int, default=None, help="candidates per GPU")
+    ap.add_argument("--candidates", type=int, default=None, help="candidates per GPU (weak) / in total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU gets its own full batch (default); strong: one batch split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -258,7 +260,21 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     n_cand = args.candidates or (4096 if args.workload == "c4" else 512)
-    P = build_problem(args.workload, n_cand, seed_shift=rank)
+    n_total = n_cand
+    if args.scaling == "strong":
+        from decoupledbo_b200.distributed import shard_bounds
+
+        P_all = build_problem(args.workload, n_cand)
+        lo, hi = shard_bounds(n_cand, world, rank)
+        P = P_all
+        P.candidates = P_all.candidates[lo:hi].contiguous()
+        n_total = n_cand
+        n_cand = max_rows = -(-n_total // world)
+        if hi - lo < n_cand:  # keep shards equal (pad with a repeated row) so the all-gather is regular
+            pad = P.candidates[-1:].expand(n_cand - (hi - lo), -1)
+            P.candidates = torch.cat([P.candidates, pad])
+    else:
+        P = build_problem(args.workload, n_cand, seed_shift=rank)
     S = int(P.weights.shape[0])
     M = P.model.num_outputs
     d = P.d
@@ -306,7 +322,8 @@ def main():
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_step = float(ms_total) / args.steps
-    evals_step = world * n_cand * M * S
+    n_global = n_total if args.scaling == "strong" else world * n_cand
+    evals_step = n_global * M * S
     value = evals_step / (ms_step * 1e-3)
 
     # ---- end-to-end through the public API with HOST buffers ----
@@ -420,7 +437,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload, P, n_cand, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline,

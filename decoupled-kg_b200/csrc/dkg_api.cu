@@ -384,6 +384,7 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     out.hull_cap = HULL_CAP;
     out.amax_is_own = w.amax_is_new;
     out.kg = kg + c0;
+    out.truncated = w.stats + 6;
     BackwardArgs bw{};
     if (dX != nullptr) {
       bw.dX = dX + (size_t)c0 * d;
@@ -487,6 +488,7 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
     out.hull_cnt = w.hull_cnt; out.hull_idx = w.hull_idx; out.hull_p = w.hull_p; out.hull_q = w.hull_q;
     out.hull_x = nullptr; out.hull_cap = HULL_CAP; out.amax_is_own = w.amax_is_new;
     out.kg = kg + c0;
+    out.truncated = w.stats + 6;
     DKG_TRY(emax_hull(lb, sc, out, st));
     DKG_TRY(emax_overflow(lb, sc, out, st));
     CoupledBackward bw;
@@ -713,7 +715,7 @@ int dkg_profile_read(double* ms_host, int64_t* count_host, int32_t ncat) {
   return DKG_OK;
 }
 
-int dkg_plan_stats(dkg_plan* plan, int64_t* out5_host, void* stream) {
+int dkg_plan_stats(dkg_plan* plan, int64_t* out5_host /* [8] */, void* stream) {
   if (!plan || !out5_host) { set_error("NULL argument"); return DKG_EINVAL; }
   long long h[8] = {0};
   if (plan->ws.stats) {
@@ -721,8 +723,7 @@ int dkg_plan_stats(dkg_plan* plan, int64_t* out5_host, void* stream) {
     DKG_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
   }
   out5_host[0] = plan->ws.last_C;
-  for (int k = 1; k < 5; ++k) out5_host[k] = h[k];
-  out5_host[2] = h[2];
+  for (int k = 1; k < 8; ++k) out5_host[k] = h[k];
   return DKG_OK;
 }
 

@@ -594,6 +594,9 @@ __device__ HullResult warp_march(int total, Fetch fetch, const Recorder& rec) {
 __device__ __forceinline__ void finish_set(const LineBatch& lb, const EmaxOut& out, size_t set,
                                            const SetInfo& s, double E, int h) {
   if (out.hull_cnt) out.hull_cnt[set] = h;
+  // more hull vertices than record slots: E is exact, but the backward would miss vertices
+  if (out.truncated != nullptr && out.hull_p != nullptr && h > out.hull_cap)
+    atomicAdd((unsigned long long*)out.truncated, 1ull);
   out.terms[set] = out.subtract_max ? (E - s.amax) : E;  // kg[j] = E - max(intercepts) (:336)
 }
 

@@ -62,6 +62,7 @@ struct EmaxOut {
   int hull_cap = 0;
   int* amax_is_own = nullptr;  // [C, S] (optional)
   double* kg = nullptr;        // [C] mean over scalarisations of terms (optional)
+  long long* truncated = nullptr;  // [1] counts sets with more hull vertices than hull_cap (optional)
   double* dense_da = nullptr;  // [C*S, NL] dE/da scattered by line index (optional, pre-zeroed)
   double* dense_db = nullptr;  // [C*S, NL] dE/db (optional, pre-zeroed)
 };

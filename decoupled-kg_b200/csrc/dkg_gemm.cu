@@ -207,13 +207,17 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
 }
 
 static int ensure_gemm_attr() {
-  static bool done = false;
-  if (!done) {
+  // per device (the attribute lives in the context of the current device); cheap enough to
+  // repeat, and correct when one process drives several GPUs
+  static int done_for_device[64] = {0};
+  int dev = 0;
+  DKG_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !done_for_device[dev]) {
     DKG_CUDA_OK(cudaFuncSetAttribute(dmma_gemm_kernel<true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     DKG_CUDA_OK(cudaFuncSetAttribute(dmma_gemm_kernel<false>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    done = true;
+    if (dev >= 0 && dev < 64) done_for_device[dev] = 1;
   }
   return DKG_OK;
 }

@@ -476,12 +476,8 @@ cholesky_blocked_kernel(double* __restrict__ A, int n, int ld, int* __restrict__
 
 int cholesky_blocked(double* A, int n, int ld, int* info_dev, cudaStream_t st) {
   const size_t smem = sizeof(double) * ((size_t)CB * (CB + 1) + (size_t)n * (CB + 1));
-  static bool attr = false;
-  if (!attr) {
-    DKG_CUDA_OK(cudaFuncSetAttribute(cholesky_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(sizeof(double) * ((size_t)CB * (CB + 1) + (size_t)CHOL_FAST_MAX * (CB + 1)))));
-    attr = true;
-  }
+  DKG_CUDA_OK(cudaFuncSetAttribute(cholesky_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(sizeof(double) * ((size_t)CB * (CB + 1) + (size_t)CHOL_FAST_MAX * (CB + 1)))));
   cholesky_blocked_kernel<<<1, 1024, smem, st>>>(A, n, ld, info_dev);
   DKG_LAUNCH_CHECK();
   return DKG_OK;
@@ -547,13 +543,9 @@ tri_inverse_kernel(const double* __restrict__ L, int n, int ldl, double* __restr
 int tri_inverse(const double* L, int n, int ldl, double* X, int ldx, cudaStream_t st) {
   const int nb = ceil_div(n, CB);
   const size_t smem = sizeof(double) * ((size_t)nb + 2) * CB * (CB + 1);
-  static bool attr = false;
-  if (!attr) {
-    const int nbmax = ceil_div(CHOL_FAST_MAX, CB);
-    DKG_CUDA_OK(cudaFuncSetAttribute(tri_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(sizeof(double) * ((size_t)nbmax + 2) * CB * (CB + 1))));
-    attr = true;
-  }
+  const int nbmax = ceil_div(CHOL_FAST_MAX, CB);
+  DKG_CUDA_OK(cudaFuncSetAttribute(tri_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(sizeof(double) * ((size_t)nbmax + 2) * CB * (CB + 1))));
   tri_inverse_kernel<<<nb, 1024, smem, st>>>(L, n, ldl, X, ldx);
   DKG_LAUNCH_CHECK();
   return DKG_OK;

@@ -20,7 +20,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_PKG_DIR), "lib", "libdkg_b200.so")
 
 DKG_OK, DKG_EINVAL, DKG_ECUDA, DKG_ENOTPD, DKG_ENOMEM, DKG_EEMPTY = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTED_SYMBOLS = (
     "dkg_abi_version",
@@ -290,7 +290,7 @@ class Plan:
         return out.reshape(shape)
 
     def stats(self):
-        buf = (c_int64 * 5)()
+        buf = (c_int64 * 8)()
         with torch.cuda.device(self.device):
             rc = load_library().dkg_plan_stats(self._handle, buf, _stream_ptr())
         _check(rc, "dkg_plan_stats")

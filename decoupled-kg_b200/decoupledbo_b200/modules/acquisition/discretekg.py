@@ -26,6 +26,7 @@ Both evaluation modes of the reference are covered: ``target_output_ix=i`` (deco
 from __future__ import annotations
 
 import logging
+import os
 from typing import Optional
 
 import torch
@@ -57,6 +58,16 @@ class _KGFunction(torch.autograd.Function):
             kg, dX = plan.forward_host(X_flat.detach(), need_grad)
         ctx.has_grad = need_grad
         if need_grad:
+            # a set with more hull vertices than the library records (64) would silently lose part
+            # of its gradient: fail loudly instead.  The host path is synchronous anyway; the
+            # device path only checks on request (it would force a sync).
+            if (not X_flat.is_cuda) or os.environ.get("DKG_CHECK") == "1":
+                truncated = plan.stats()[6]
+                if truncated:
+                    raise RuntimeError(
+                        f"{truncated} (candidate, scalarisation) sets have more than 64 upper-envelope "
+                        f"vertices; their gradient would be incomplete"
+                    )
             ctx.save_for_backward(dX)
         return kg
 

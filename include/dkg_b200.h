@@ -33,7 +33,7 @@ extern "C" {
 #define DKG_API
 #endif
 
-#define DKG_ABI_VERSION 1
+#define DKG_ABI_VERSION 2
 
 /* error codes */
 #define DKG_OK 0
@@ -163,10 +163,13 @@ DKG_API void dkg_launch_count_reset(void);
 DKG_API void dkg_profile_enable(int on);
 DKG_API int dkg_profile_read(double* ms_host, int64_t* count_host, int32_t ncat);
 
-/* per-plan statistics of the last forward (host ints): [0] candidates, [1] lines surviving the
- * chord filter (sum over candidates x scalarisations), [2] (candidate, scalarisation) pairs sent
- * to the slow exact path, [3] total hull vertices, [4] pairs taking the |slope|<1e-9 shortcut */
-DKG_API int dkg_plan_stats(dkg_plan* plan, int64_t* out5_host, void* stream);
+/* per-plan statistics of the last forward (8 host ints): [0] candidates, [1] lines surviving the
+ * chord filter (sum over the sets finished by the warp kernel), [2] (candidate, scalarisation) sets
+ * handled by the cooperative overflow kernel, [3] total hull vertices, [4] sets taking the
+ * |slope| < 1e-9 shortcut, [5] sets that needed the block-wide exact march, [6] sets with more hull
+ * vertices than the 64 record slots (their value is exact; their gradient omits the extra
+ * vertices -- the Python layer raises if this is ever non-zero), [7] reserved */
+DKG_API int dkg_plan_stats(dkg_plan* plan, int64_t* out8_host, void* stream);
 
 #ifdef __cplusplus
 }

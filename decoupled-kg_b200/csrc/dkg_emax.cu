@@ -875,27 +875,41 @@ overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
       }
       if (tid == 0) s_list = 0;
       __syncthreads();
-      for (int n = tid; n < lb.NL; n += blockDim.x) {
-        const double zn = lb.Z[(size_t)c * lb.ldz + n];
-        const Line L = make_line(lb, w, line_intercept(lb, c, j, n), zn, n);
-        bool keep;
-        if (L.b < v_b[0]) keep = true;  // outside the chain: cannot be dropped
-        else {
-          const int k = chain_locate(v_b, nv, L.b);
-          if (L.b == v_b[k]) keep = L.a > v_a[k];  // same slope as a vertex: only if higher
-          else if (k == nv - 1) keep = true;       // beyond the last vertex
-          else {
-            const double e = L.a - fma(v_m[k], L.b - v_b[k], v_a[k]);
-            keep = e > -v_slack[k];
-            if (e > 0.0) atomicMax(&v_best[k], pack_excess(e, n));
-          }
+      for (int n0 = tid; n0 < lb.NL; n0 += 4 * blockDim.x) {
+        // four lines per trip: all eight loads are issued before any of them is consumed
+        double zq[4], aq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int n = n0 + u * blockDim.x;
+          const bool ok = n < lb.NL;
+          zq[u] = ok ? lb.Z[(size_t)c * lb.ldz + n] : 0.0;
+          aq[u] = ok ? line_intercept(lb, c, j, n) : -INFINITY;
         }
-        if (keep) {
-          const int pos = atomicAdd(&s_list, 1);
-          if (pos < SURV_CAP) {
-            SurvEntry e;
-            e.a = L.a; e.z = zn; e.idx = n; e.pad = 0;
-            list[pos] = e;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int n = n0 + u * blockDim.x;
+          if (n >= lb.NL) break;
+          const double zn = zq[u];
+          const Line L = make_line(lb, w, aq[u], zn, n);
+          bool keep;
+          if (L.b < v_b[0]) keep = true;  // outside the chain: cannot be dropped
+          else {
+            const int k = chain_locate(v_b, nv, L.b);
+            if (L.b == v_b[k]) keep = L.a > v_a[k];  // same slope as a vertex: only if higher
+            else if (k == nv - 1) keep = true;       // beyond the last vertex
+            else {
+              const double e = L.a - fma(v_m[k], L.b - v_b[k], v_a[k]);
+              keep = e > -v_slack[k];
+              if (e > 0.0) atomicMax(&v_best[k], pack_excess(e, n));
+            }
+          }
+          if (keep) {
+            const int pos = atomicAdd(&s_list, 1);
+            if (pos < SURV_CAP) {
+              SurvEntry e;
+              e.a = L.a; e.z = zn; e.idx = n; e.pad = 0;
+              list[pos] = e;
+            }
           }
         }
       }

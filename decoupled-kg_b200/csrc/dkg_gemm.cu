@@ -43,6 +43,37 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: used for the B
+// operand, whose tile rows are 512 contiguous bytes.  (The A rows of a K-slice are only 128 bytes,
+// and dense / swizzled cp.async.bulk.tensor tiles cannot be read by fp64 DMMA fragments without
+// bank conflicts, so A stays on cp.async with padded rows: see DESIGN.md.)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE_%=;\n"
+      "bra MBAR_WAIT_%=;\n"
+      "MBAR_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
   asm volatile(
       "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -57,6 +88,7 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
   double* Bs = smem + G_STAGES * A_STAGE;
+  __shared__ __align__(8) unsigned long long b_full[G_STAGES];  // "B tile of this stage has landed"
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -81,11 +113,12 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
       int row = c >> 3, ch = c & 7;
       cp_async16(as + row * LDA_S + ch * 2, Ag + (size_t)row * lda + k0 + ch * 2);
     }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {  // B: 16 rows x 64 doubles = 512 chunks
-      int c = tid + i * G_THREADS;
-      int row = c >> 5, ch = c & 31;
-      cp_async16(bs + row * LDB_S + ch * 2, Bg + (size_t)(k0 + row) * ldb + ch * 2);
+    if (warp == 0) {  // B: 16 rows x 512 bytes, one TMA bulk copy per row into the padded tile
+      if (lane == 0) mbar_arrive_expect_tx(&b_full[stage], GEMM_BK * G_BN * (unsigned)sizeof(double));
+      __syncwarp();
+      if (lane < GEMM_BK)
+        bulk_copy_g2s(bs + lane * LDB_S, Bg + (size_t)(k0 + lane) * ldb, G_BN * (unsigned)sizeof(double),
+                      &b_full[stage]);
     }
   };
 
@@ -95,6 +128,13 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < G_STAGES; ++s) mbar_init(&b_full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
   const int KT = K / GEMM_BK;
 #pragma unroll
   for (int s = 0; s < G_STAGES - 1; ++s) {
@@ -103,8 +143,9 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
   }
 
   for (int kt = 0; kt < KT; ++kt) {
-    cp_async_wait<G_STAGES - 2>();
-    __syncthreads();
+    cp_async_wait<G_STAGES - 2>();                                  // this thread's A chunks
+    mbar_wait(&b_full[kt % G_STAGES], (kt / G_STAGES) & 1);         // the stage's B rows (TMA)
+    __syncthreads();                                                // everyone's A chunks
     {
       int nk = kt + G_STAGES - 1;
       if (nk < KT) load_stage(nk % G_STAGES, nk * GEMM_BK);

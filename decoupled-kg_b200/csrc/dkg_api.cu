@@ -66,7 +66,7 @@ static void dev_free(T*& p) {
 }
 
 static void free_workspace(Workspace& w) {
-  dev_free(w.X); dev_free(w.kg); dev_free(w.dX); dev_free(w.KX); dev_free(w.T); dev_free(w.var);
+  dev_free(w.X); dev_free(w.kg); dev_free(w.dX); dev_free(w.KX); dev_free(w.T); dev_free(w.R); dev_free(w.var);
   dev_free(w.sd); dev_free(w.zown); dev_free(w.Xs); dev_free(w.a_new); dev_free(w.kg_terms);
   dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } { double4* t = (double4*)w.chain; dev_free(t); w.chain = nullptr; } dev_free(w.far); dev_free(w.ovf_sets); dev_free(w.ovf_count);
   dev_free(w.hull_cnt); dev_free(w.hull_idx); dev_free(w.hull_p); dev_free(w.hull_q);
@@ -83,7 +83,6 @@ static int ensure_workspace(dkg_plan* p, int C) {
   free_workspace(w);
   const int cap = round_up(C, GEMM_BM);
   const bool coupled = p->target < 0;
-  const int n_pad = coupled ? GEMM_BK : p->obj[p->target].n_pad;
   // Candidates are processed in chunks that bound the scratch memory (slope rows + survivor
   // lists).  DKG_CHUNK_MB (default 6144) is the budget for both; at c4 shapes it covers all 4096
   // candidates in one chunk (0.5 GB of slope rows + 1.6 GB of survivor lists).
@@ -100,8 +99,11 @@ static int ensure_workspace(dkg_plan* p, int C) {
   DKG_TRY(dev_alloc(&w.X, (size_t)cap * p->d));
   DKG_TRY(dev_alloc(&w.kg, (size_t)cap));
   DKG_TRY(dev_alloc(&w.dX, (size_t)cap * p->d));
-  DKG_TRY(dev_alloc(&w.KX, (size_t)cap * n_pad));
+  int ldk_max = p->ldk;
+  if (coupled) for (int m = 0; m < p->M; ++m) ldk_max = ldk_max > p->obj[m].ldk ? ldk_max : p->obj[m].ldk;
+  DKG_TRY(dev_alloc(&w.KX, (size_t)cap * (coupled ? GEMM_BN : p->ldk)));
   DKG_TRY(dev_alloc(&w.T, (size_t)cap * (coupled ? GEMM_BN : p->ldk)));
+  DKG_TRY(dev_alloc(&w.R, (size_t)cap * ldk_max));
   DKG_TRY(dev_alloc(&w.var, (size_t)cap));
   DKG_TRY(dev_alloc(&w.sd, (size_t)cap));
   DKG_TRY(dev_alloc(&w.zown, (size_t)cap));
@@ -116,7 +118,7 @@ static int ensure_workspace(dkg_plan* p, int C) {
   DKG_TRY(dev_alloc(&w.zarg, (size_t)chunk * rows_per_cand * 2));
   if (coupled) {
     for (int m = 0; m < p->M; ++m) {
-      DKG_TRY(dev_alloc(&w.KXm[m], (size_t)cap * p->obj[m].n_pad));
+      DKG_TRY(dev_alloc(&w.KXm[m], (size_t)cap * p->obj[m].ldk));
       DKG_TRY(dev_alloc(&w.Tm[m], (size_t)cap * p->obj[m].ldk));
       DKG_TRY(dev_alloc(&w.varlat[m], (size_t)cap));
       DKG_TRY(dev_alloc(&w.COVm[m], (size_t)chunk * p->ldz));
@@ -146,7 +148,7 @@ static void destroy_plan(dkg_plan* p) {
   cudaDeviceSynchronize();
   for (int m = 0; m < p->M; ++m) {
     ObjState& o = p->obj[m];
-    dev_free(o.xs); dev_free(o.alpha); dev_free(o.chol); dev_free(o.Kinv); dev_free(o.B);
+    dev_free(o.xs); dev_free(o.alpha); dev_free(o.chol); dev_free(o.Kinv); dev_free(o.Kmat); dev_free(o.B); dev_free(o.Kxd);
     dev_free(o.BT); dev_free(o.xd_s);
   }
   dev_free(p->W); dev_free(p->wt); dev_free(p->xd); dev_free(p->alpha_all);
@@ -161,7 +163,7 @@ static int factor_objective(const ObjState& o, int d, double* Lbuf, int* info_de
                             cudaStream_t st, bool blocked) {
   const double jitters[4] = {0.0, 1e-8, 1e-7, 1e-6};
   for (int k = 0; k < 4; ++k) {
-    DKG_TRY(kmat_train(o, d, jitters[k], Lbuf, st));
+    DKG_TRY(kmat_train(o, d, jitters[k], Lbuf, o.n, st));
     if (blocked) DKG_TRY(cholesky_blocked(Lbuf, o.n, o.n, info_dev, st));
     else DKG_TRY(cholesky_inplace(Lbuf, o.n, info_dev, st));
     int info = 0;
@@ -215,7 +217,7 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
     const bool need_state = (m == tgt || tgt < 0);
     const int n = o.n;
     double jit = 0.0;
-    if (n <= chol_fast_max()) {
+    if (n <= chol_fast_max() && getenv("DKG_SLOW_PREPARE") == nullptr) {
       // ---- fast path: blocked Cholesky, explicit L^-1, solves as DMMA GEMMs ----
       if ((rc = factor_objective(o, d, Lbuf, info_dev, &jit, st, /*blocked=*/true)) != DKG_OK) break;
       const int np = round_up(n, GEMM_BM);  // 128-padded square buffers for the GEMM operands
@@ -240,14 +242,20 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
         // Kinv = L^-T L^-1
         if ((rc = dev_alloc(&o.Kinv, (size_t)np * o.ldk)) != DKG_OK) { cleanup(); break; }
         if ((rc = gemm_store(LinvT, np, Linv, np, np, o.ldk, o.n_pad, o.Kinv, o.ldk, st)) != DKG_OK) { cleanup(); break; }
+        if ((rc = dev_alloc(&o.Kmat, (size_t)np * o.ldk)) != DKG_OK) { cleanup(); break; }
+        if ((rc = kmat_train(o, d, jit, o.Kmat, o.ldk, st)) != DKG_OK) { cleanup(); break; }
         // B = K^-1 k(X_train, X_disc) = L^-T (L^-1 Kxd)
         if ((rc = dev_alloc(&o.xd_s, (size_t)p->N_pad * d)) != DKG_OK) { cleanup(); break; }
         if ((rc = scale_rows(p->xd, N, d, o.ls, o.xd_s, st)) != DKG_OK) { cleanup(); break; }
         if ((rc = dev_alloc(&o.B, (size_t)np * p->N_pad)) != DKG_OK) { cleanup(); break; }
         if ((rc = dev_alloc(&Ybuf, (size_t)np * p->N_pad)) != DKG_OK) { cleanup(); break; }
-        if ((rc = kcross(o, o.xd_s, N, d, o.B, p->N_pad, st)) != DKG_OK) { cleanup(); break; }
-        if ((rc = gemm_store(Linv, np, o.B, p->N_pad, np, p->N_pad, o.n_pad, Ybuf, p->N_pad, st)) != DKG_OK) { cleanup(); break; }
+        if ((rc = dev_alloc(&o.Kxd, (size_t)np * p->N_pad)) != DKG_OK) { cleanup(); break; }
+        if ((rc = kcross(o, o.xd_s, N, d, o.Kxd, p->N_pad, st)) != DKG_OK) { cleanup(); break; }
+        if ((rc = gemm_store(Linv, np, o.Kxd, p->N_pad, np, p->N_pad, o.n_pad, Ybuf, p->N_pad, st)) != DKG_OK) { cleanup(); break; }
         if ((rc = gemm_store(LinvT, np, Ybuf, p->N_pad, np, p->N_pad, o.n_pad, o.B, p->N_pad, st)) != DKG_OK) { cleanup(); break; }
+        // one refinement step (see solve_T): R = Kxd - K B;  B += Kinv R
+        if ((rc = gemm_axpy(o.Kmat, o.ldk, o.B, p->N_pad, np, p->N_pad, o.n_pad, o.Kxd, p->N_pad, -1.0, Ybuf, p->N_pad, st)) != DKG_OK) { cleanup(); break; }
+        if ((rc = gemm_axpy(o.Kinv, o.ldk, Ybuf, p->N_pad, np, p->N_pad, o.n_pad, o.B, p->N_pad, 1.0, o.B, p->N_pad, st)) != DKG_OK) { cleanup(); break; }
         if ((rc = dev_alloc(&o.BT, (size_t)N * o.n_pad)) != DKG_OK) { cleanup(); break; }
         if ((rc = transpose(o.B, o.n_pad, N, p->N_pad, o.BT, o.n_pad, st)) != DKG_OK) { cleanup(); break; }
       }
@@ -268,10 +276,14 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
         if ((rc = dev_alloc(&o.Kinv, (size_t)o.n_pad * o.ldk)) != DKG_OK) break;
         if ((rc = set_identity(o.Kinv, n, o.ldk, st)) != DKG_OK) break;
         if ((rc = cholesky_solve_inplace(Lbuf, LTbuf, n, o.Kinv, n, o.ldk, st)) != DKG_OK) break;
+        if ((rc = dev_alloc(&o.Kmat, (size_t)o.n_pad * o.ldk)) != DKG_OK) break;
+        if ((rc = kmat_train(o, d, jit, o.Kmat, o.ldk, st)) != DKG_OK) break;
         if ((rc = dev_alloc(&o.xd_s, (size_t)p->N_pad * d)) != DKG_OK) break;
         if ((rc = scale_rows(p->xd, N, d, o.ls, o.xd_s, st)) != DKG_OK) break;
         if ((rc = dev_alloc(&o.B, (size_t)o.n_pad * p->N_pad)) != DKG_OK) break;
-        if ((rc = kcross(o, o.xd_s, N, d, o.B, p->N_pad, st)) != DKG_OK) break;
+        if ((rc = dev_alloc(&o.Kxd, (size_t)o.n_pad * p->N_pad)) != DKG_OK) break;
+        if ((rc = kcross(o, o.xd_s, N, d, o.Kxd, p->N_pad, st)) != DKG_OK) break;
+        cudaMemcpyAsync(o.B, o.Kxd, sizeof(double) * (size_t)o.n_pad * p->N_pad, cudaMemcpyDeviceToDevice, st);
         if ((rc = cholesky_solve_inplace(Lbuf, LTbuf, n, o.B, N, p->N_pad, st)) != DKG_OK) break;
         if ((rc = dev_alloc(&o.BT, (size_t)N * o.n_pad)) != DKG_OK) break;
         if ((rc = transpose(o.B, o.n_pad, N, p->N_pad, o.BT, o.n_pad, st)) != DKG_OK) break;
@@ -310,6 +322,38 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
   return rc;
 }
 
+// T = KX K^-1 for a batch of cross-kernel rows (KX, T, R all with row stride o.ldk).
+//
+// A plain product with the explicit inverse loses kappa(K) * eps of *backward* accuracy: on the
+// survey-c2 target objective (kappa 4.6e7) the quadratic form kx^T K^-1 kx came out with 2e-4
+// relative error in the predictive variance.  One step of fixed-precision iterative refinement,
+//     T0 = KX Kinv;   R = KX - T0 K;   T = T0 + R Kinv,
+// restores the residual KX - T K to O(eps |T||K|), i.e. the accuracy of the two triangular
+// solves the reference performs (gpytorch cholesky_solve), while staying on the DMMA GEMM.
+// DKG_T_SOLVE=trsm selects the batched substitution kernel, =kinv the unrefined product.
+static int t_solve_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("DKG_T_SOLVE");
+    mode = 0;
+    if (e != nullptr && strcmp(e, "trsm") == 0) mode = 1;
+    if (e != nullptr && strcmp(e, "kinv") == 0) mode = 2;
+  }
+  return mode;
+}
+
+static int solve_T(const ObjState& o, const double* KX, double* T, double* R, int C, int C_pad,
+                   cudaStream_t st) {
+  const int mode = t_solve_mode();
+  if (mode == 1 && o.n <= batched_solve_max_n())
+    return launch_batched_cholesky_solve(o.chol, o.n, KX, o.ldk, C, T, o.ldk, st);
+  DKG_TRY(gemm_store(KX, o.ldk, o.Kinv, o.ldk, C_pad, o.ldk, o.n_pad, T, o.ldk, st));
+  if (mode == 2) return DKG_OK;
+  DKG_TRY(gemm_axpy(T, o.ldk, o.Kmat, o.ldk, C_pad, o.ldk, o.n_pad, KX, o.ldk, -1.0, R, o.ldk, st));
+  DKG_TRY(gemm_axpy(R, o.ldk, o.Kinv, o.ldk, C_pad, o.ldk, o.n_pad, T, o.ldk, 1.0, T, o.ldk, st));
+  return DKG_OK;
+}
+
 static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st);
 
 static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st) {
@@ -332,14 +376,14 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     xa.y_mean[m] = o.y_mean; xa.y_std[m] = o.y_std;
     for (int k = 0; k < MAX_D; ++k) xa.ls[m][k] = o.ls[k];
   }
-  xa.W = p->W; xa.Xs = w.Xs; xa.KX = w.KX; xa.n_pad = ot.n_pad; xa.a_new = w.a_new;
+  xa.W = p->W; xa.Xs = w.Xs; xa.KX = w.KX; xa.n_pad = p->ldk; xa.a_new = w.a_new;
   { ProfScope ps(0, st); DKG_TRY(launch_xprep(xa, st)); }
 
-  // T = KX @ Kinv, then the predictive variance
-  { ProfScope ps(1, st); DKG_TRY(gemm_store(w.KX, ot.n_pad, p->Kinv, p->ldk, C_pad, p->ldk, ot.n_pad, w.T, p->ldk, st)); }
+  // T = KX K^-1 (backward stable), then the predictive variance
+  { ProfScope ps(1, st); DKG_TRY(solve_T(ot, w.KX, w.T, w.R, C, C_pad, st)); }
   const double ystd2 = ot.y_std * ot.y_std;
   { ProfScope ps(2, st);
-    DKG_TRY(launch_var(w.KX, ot.n_pad, w.T, p->ldk, ot.n, C, ot.kernel, ot.outputscale, ot.noise,
+    DKG_TRY(launch_var(w.KX, p->ldk, w.T, p->ldk, ot.n, C, ot.kernel, ot.outputscale, ot.noise,
                        ystd2, w.var, w.sd, w.zown, st)); }
 
   for (int c0 = 0; c0 < C; c0 += w.chunk_C) {
@@ -353,7 +397,8 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     ep.ldz = p->ldz; ep.C = cc; ep.N = N; ep.d = d; ep.kind = ot.kernel;
     ep.outputscale = ot.outputscale; ep.ystd2 = ystd2;
     { ProfScope ps(3, st);
-      DKG_TRY(gemm_cov(w.KX + (size_t)c0 * ot.n_pad, ot.n_pad, p->B, p->N_pad, cc_pad, p->N_pad,
+      // cov[c, n] = k(x_c, x_n) - T[c, :] . k(X_train, x_n)   with T = K^-1 k(X_train, x_c)
+      DKG_TRY(gemm_cov(w.T + (size_t)c0 * p->ldk, p->ldk, ot.Kxd, p->N_pad, cc_pad, p->N_pad,
                        ot.n_pad, ep, st)); }
     { ProfScope ps(4, st); DKG_TRY(launch_place_own(w.zown + c0, cc, w.Z, p->ldz, N, st)); }
 
@@ -431,11 +476,11 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
       xa.y_mean[q] = oq.y_mean; xa.y_std[q] = oq.y_std;
       for (int k = 0; k < MAX_D; ++k) xa.ls[q][k] = oq.ls[k];
     }
-    xa.W = p->W; xa.Xs = w.Xs; xa.KX = w.KXm[m]; xa.n_pad = o.n_pad; xa.a_new = w.a_new;
+    xa.W = p->W; xa.Xs = w.Xs; xa.KX = w.KXm[m]; xa.n_pad = o.ldk; xa.a_new = w.a_new;
     DKG_TRY(launch_xprep(xa, st));  // (a_new / means are recomputed identically each time)
-    DKG_TRY(gemm_store(w.KXm[m], o.n_pad, o.Kinv, o.ldk, C_pad, o.ldk, o.n_pad, w.Tm[m], o.ldk, st));
+    DKG_TRY(solve_T(o, w.KXm[m], w.Tm[m], w.R, C, C_pad, st));
     // var = noisy variance (un-standardised) -> w.var reused per objective below via varlat
-    DKG_TRY(launch_var(w.KXm[m], o.n_pad, w.Tm[m], o.ldk, o.n, C, o.kernel, o.outputscale, o.noise,
+    DKG_TRY(launch_var(w.KXm[m], o.ldk, w.Tm[m], o.ldk, o.n, C, o.kernel, o.outputscale, o.noise,
                        o.y_std * o.y_std, w.varlat[m], w.sd, w.zown, st));
     // launch_var wrote: varlat[m] <- noisy variance, sd <- sqrt, zown <- Cov(x,x)/sd.  Recover the
     // covariance Cov_m(x, x) (un-standardised) into column N of COV_m per chunk below: zown * sd.
@@ -456,9 +501,9 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
       ep.xs = w.Xs; ep.xd_s = o.xd_s; ep.sd = w.sd; ep.Z = w.COVm[m];
       ep.ldz = p->ldz; ep.C = cc; ep.N = N; ep.d = d; ep.kind = o.kernel;
       ep.outputscale = o.outputscale; ep.ystd2 = o.y_std * o.y_std;
-      DKG_TRY(gemm_cov(w.KXm[m] + (size_t)c0 * o.n_pad, o.n_pad, o.B, p->N_pad, cc_pad, p->N_pad,
+      DKG_TRY(gemm_cov(w.Tm[m] + (size_t)c0 * o.ldk, o.ldk, o.Kxd, p->N_pad, cc_pad, p->N_pad,
                        o.n_pad, ep, st));
-      DKG_TRY(place_latent_var(w.KXm[m] + (size_t)c0 * o.n_pad, o.n_pad, w.Tm[m] + (size_t)c0 * o.ldk,
+      DKG_TRY(place_latent_var(w.KXm[m] + (size_t)c0 * o.ldk, o.ldk, w.Tm[m] + (size_t)c0 * o.ldk,
                                o.ldk, o.n, cc, o.kernel, o.outputscale, o.y_std * o.y_std,
                                w.COVm[m], p->ldz, N, st));
       ca.COV[m] = w.COVm[m];
@@ -594,6 +639,21 @@ int dkg_forward_host(dkg_plan* plan, const double* X_host, int32_t C, double* kg
     DKG_CUDA_OK(cudaMemcpyAsync(dX_host, w.dX, sizeof(double) * (size_t)C * d, cudaMemcpyDeviceToHost, st));
   DKG_CUDA_OK(cudaStreamSynchronize(st));
   return DKG_OK;
+}
+
+int dkg_posterior_mean_dev(dkg_plan* plan, const double* X_dev, int32_t C, double* mu_dev, void* stream) {
+  if (!plan || (C > 0 && (!X_dev || !mu_dev))) { set_error("NULL argument"); return DKG_EINVAL; }
+  if (C < 0) { set_error("C=%d is negative", C); return DKG_EINVAL; }
+  XprepArgs xa{};
+  xa.X = X_dev; xa.C = C; xa.d = plan->d; xa.M = plan->M; xa.S = plan->S; xa.target = 0;
+  for (int m = 0; m < plan->M; ++m) {
+    const ObjState& o = plan->obj[m];
+    xa.xs[m] = o.xs; xa.alpha[m] = o.alpha; xa.ntr[m] = o.n; xa.kind[m] = o.kernel;
+    xa.outputscale[m] = o.outputscale; xa.mean_const[m] = o.mean_const;
+    xa.y_mean[m] = o.y_mean; xa.y_std[m] = o.y_std;
+    for (int k = 0; k < MAX_D; ++k) xa.ls[m][k] = o.ls[k];
+  }
+  return launch_mean(xa, mu_dev, (cudaStream_t)stream);
 }
 
 int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev, int32_t P, int32_t L,

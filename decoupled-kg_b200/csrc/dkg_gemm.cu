@@ -170,14 +170,22 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
   __syncthreads();
 
   if (!COV) {
+    // store mode: D = acc, or D = Cin + alpha * acc when an addend is given (ep.xs doubles as the
+    // addend pointer with leading dimension ep.ldz and ep.ystd2 as alpha)
+    const double* Cin = ep.xs;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int row = m_base + wm + i * 8 + g;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         int col = n_base + wn + j * 8 + q * 2;
-        *reinterpret_cast<double2*>(D + (size_t)row * ldd + col) =
-            make_double2(acc[i][j][0], acc[i][j][1]);
+        double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+        if (Cin != nullptr) {
+          const double2 cin = *reinterpret_cast<const double2*>(Cin + (size_t)row * ep.ldz + col);
+          v.x = fma(ep.ystd2, v.x, cin.x);
+          v.y = fma(ep.ystd2, v.y, cin.y);
+        }
+        *reinterpret_cast<double2*>(D + (size_t)row * ldd + col) = v;
       }
     }
     return;
@@ -266,9 +274,18 @@ static int ensure_gemm_attr() {
 // D[M_pad, N_pad] = A[M_pad, K] @ B[K, N_pad]; all dims multiples of the tile sizes.
 int gemm_store(const double* A, int lda, const double* B, int ldb, int M_pad, int N_pad, int K,
                double* D, int ldd, cudaStream_t st) {
+  return gemm_axpy(A, lda, B, ldb, M_pad, N_pad, K, nullptr, 0, 1.0, D, ldd, st);
+}
+
+// D = Cin + alpha * (A @ B)   (Cin == nullptr: D = A @ B).  Cin / D may alias.
+int gemm_axpy(const double* A, int lda, const double* B, int ldb, int M_pad, int N_pad, int K,
+              const double* Cin, int ldc, double alpha, double* D, int ldd, cudaStream_t st) {
   DKG_TRY(ensure_gemm_attr());
   dim3 grid(N_pad / G_BN, M_pad / GEMM_BM);
   CovEpilogue ep{};
+  ep.xs = Cin;
+  ep.ldz = ldc;
+  ep.ystd2 = alpha;
   dmma_gemm_kernel<false><<<grid, G_THREADS, GEMM_SMEM, st>>>(A, lda, B, ldb, K, D, ldd, ep);
   DKG_LAUNCH_CHECK();
   return DKG_OK;

@@ -7,7 +7,7 @@ namespace dkg {
 
 // ---- dkg_prepare.cu --------------------------------------------------------------------------
 int scale_rows(const double* x, int rows, int d, const double* ls_host, double* out, cudaStream_t st);
-int kmat_train(const ObjState& o, int d, double jitter, double* K, cudaStream_t st);
+int kmat_train(const ObjState& o, int d, double jitter, double* K, int ld, cudaStream_t st);
 int cholesky_inplace(double* A, int n, int* info_dev, cudaStream_t st);
 int transpose(const double* in, int rows, int cols, int ld_in, double* out, int ld_out, cudaStream_t st);
 int cholesky_solve_inplace(const double* L, const double* LT, int n, double* R, int ncols, int ld,
@@ -40,6 +40,8 @@ struct CovEpilogue {
 };
 int gemm_store(const double* A, int lda, const double* B, int ldb, int M_pad, int N_pad, int K,
                double* D, int ldd, cudaStream_t st);
+int gemm_axpy(const double* A, int lda, const double* B, int ldb, int M_pad, int N_pad, int K,
+              const double* Cin, int ldc, double alpha, double* D, int ldd, cudaStream_t st);
 int gemm_cov(const double* KX, int lda, const double* B, int ldb, int M_pad, int N_pad, int K,
              const CovEpilogue& ep, cudaStream_t st);
 
@@ -60,10 +62,14 @@ struct XprepArgs {
   double* a_new;    // [C, S]
 };
 int launch_xprep(const XprepArgs& p, cudaStream_t st);
+int launch_mean(const XprepArgs& p, double* mu_out, cudaStream_t st);
 int launch_var(const double* KX, int n_pad, const double* T, int ldk, int ntr, int C, int kind,
                double outputscale, double noise, double ystd2, double* var, double* sd,
                double* zown, cudaStream_t st);
 int launch_place_own(const double* zown, int rows, double* Z, int ldz, int N, cudaStream_t st);
+int launch_batched_cholesky_solve(const double* L, int n, const double* KX, int n_pad, int C,
+                                  double* T, int ldk, cudaStream_t st);
+int batched_solve_max_n();
 int launch_xprep_scaled(const double* X, int C, int d, const double* ls_host, double* Xs, cudaStream_t st);
 int fill_ones(double* p, int n, cudaStream_t st);
 int place_latent_var(const double* KX, int n_pad, const double* T, int ldk, int ntr, int C, int kind,

@@ -23,7 +23,9 @@ struct ObjState {
   int ldk = 0;               // row stride of Kinv / T (n rounded up to GEMM_BN)
   double* chol = nullptr;    // [n, n]        lower Cholesky of K + noise I
   double* Kinv = nullptr;    // [n_pad, ldk]
-  double* B = nullptr;       // [n_pad, N_pad]  K^-1 k(X_train, X_disc), zero padded
+  double* Kmat = nullptr;    // [n_pad, ldk]  K + (noise + jitter) I, zero padded (refinement residual)
+  double* Kxd = nullptr;     // [n_pad, N_pad]  k(X_train, X_disc) (raw cross-kernel, GEMM B operand)
+  double* B = nullptr;       // [n_pad, N_pad]  K^-1 k(X_train, X_disc), zero padded (backward only)
   double* BT = nullptr;      // [N, n_pad]
   double* xd_s = nullptr;    // [N_pad, d]    discretisation / lengthscale
 };
@@ -34,13 +36,14 @@ struct Workspace {
   double* X = nullptr;      // [cap_C, d]    staging for host-buffer calls
   double* kg = nullptr;     // [cap_C]
   double* dX = nullptr;     // [cap_C, d]
-  double* KX = nullptr;     // [cap_C, n_pad]    k_i(x_c, X_train)   (target objective)
-  double* T = nullptr;      // [cap_C, ldk]      KX @ Kinv
+  double* KX = nullptr;     // [cap_C, ldk]      k_i(x_c, X_train)   (target objective)
+  double* T = nullptr;      // [cap_C, ldk]      KX K^-1 (Kinv product + one refinement step)
+  double* R = nullptr;      // [cap_C, ldk_max]  refinement residual KX - T K
   double* var = nullptr;    // [cap_C]           noisy predictive variance (un-standardised)
   double* sd = nullptr;     // [cap_C]           sqrt(var)
   double* zown = nullptr;   // [cap_C]           slope of the candidate's own line
   // coupled path only (per objective m, capacity cap_C each)
-  double* KXm[MAX_M] = {};   // [cap_C, n_pad_m]
+  double* KXm[MAX_M] = {};   // [cap_C, ldk_m]
   double* Tm[MAX_M] = {};    // [cap_C, ldk_m]
   double* varlat[MAX_M] = {};// [cap_C]  latent predictive variance (model space)
   double* COVm[MAX_M] = {};  // [chunk_C, ldz]  covariance rows Cov_m(x_c, .), column N = Cov_m(x_c, x_c)

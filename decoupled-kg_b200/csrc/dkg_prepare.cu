@@ -37,7 +37,8 @@ int scale_rows(const double* x, int rows, int d, const double* ls_host, double* 
 
 // K[t, u] = k(xs_t, xs_u) + noise * [t == u]
 __global__ void kmat_train_kernel(const double* __restrict__ xs, int n, int d, int kind,
-                                  double outputscale, double noise, double* __restrict__ K) {
+                                  double outputscale, double noise, double* __restrict__ K,
+                                  int ld) {
   int u = blockIdx.x * blockDim.x + threadIdx.x;
   int t = blockIdx.y;
   if (u >= n) return;
@@ -48,13 +49,13 @@ __global__ void kmat_train_kernel(const double* __restrict__ xs, int n, int d, i
   }
   double v = stationary_from_sq(kind, outputscale, sq);
   if (t == u) v += noise;
-  K[(size_t)t * n + u] = v;
+  K[(size_t)t * ld + u] = v;
 }
 
-int kmat_train(const ObjState& o, int d, double jitter, double* K, cudaStream_t st) {
+int kmat_train(const ObjState& o, int d, double jitter, double* K, int ld, cudaStream_t st) {
   dim3 grid(ceil_div(o.n, 128), o.n);
   kmat_train_kernel<<<grid, 128, 0, st>>>(o.xs, o.n, d, o.kernel, o.outputscale,
-                                          o.noise + jitter, K);
+                                          o.noise + jitter, K, ld);
   DKG_LAUNCH_CHECK();
   return DKG_OK;
 }

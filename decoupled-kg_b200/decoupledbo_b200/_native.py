@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "dkg_forward_dev",
     "dkg_forward_host",
     "dkg_expected_max_lines_dev",
+    "dkg_posterior_mean_dev",
     "dkg_plan_read",
     "dkg_launch_count",
     "dkg_launch_count_reset",
@@ -92,6 +93,8 @@ def load_library() -> ctypes.CDLL:
         c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
         c_void_p, c_void_p, c_void_p,
     ]
+    lib.dkg_posterior_mean_dev.restype = ctypes.c_int
+    lib.dkg_posterior_mean_dev.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]
     lib.dkg_plan_read.restype = c_int64
     lib.dkg_plan_read.argtypes = [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]
     lib.dkg_launch_count.restype = c_int64
@@ -259,6 +262,17 @@ class Plan:
         if need_grad:
             dX = dX_pin.clone() if out_dX is None else out_dX.copy_(dX_pin)
         return kg, dX
+
+    def posterior_mean(self, X: Tensor) -> Tensor:
+        """Posterior means of all objectives at the rows of X (C, d) -> (C, M) on X's device
+        (``BoTorchModel.batch_fitness`` of the reference's metrics, pareto/sample.py:138-144)."""
+        on_host = not X.is_cuda
+        Xd = X.detach().to(device=self.device, dtype=torch.double).contiguous()
+        mu = torch.empty(Xd.shape[0], self.M, dtype=torch.double, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = load_library().dkg_posterior_mean_dev(self._handle, _ptr(Xd), Xd.shape[0], _ptr(mu), _stream_ptr())
+        _check(rc, "dkg_posterior_mean_dev")
+        return mu.cpu() if on_host else mu
 
     # -- introspection ---------------------------------------------------------------------
     _SHAPES = {

@@ -111,6 +111,17 @@ DKG_API int dkg_forward_host(dkg_plan* plan, const double* X_host, int32_t C, do
                      double* dX_host, void* stream);
 
 /*
+ * dkg_posterior_mean_dev -- posterior means of all objectives at a batch of points,
+ *   mu[c, m] = (c_m + k_m(x_c, X_train_m) . alpha_m) * y_std_m + y_mean_m,
+ *   i.e. what model.posterior(X).mean returns (the intercept side of discretekg.py:300), exposed
+ *   because the reference's metrics evaluate it for whole NSGA-II populations
+ *   (src/decoupledbo/modules/pareto/sample.py:138-144 BoTorchModel.batch_fitness).
+ *   X_dev [C, d] -> mu_dev [C, M]
+ */
+DKG_API int dkg_posterior_mean_dev(dkg_plan* plan, const double* X_dev, int32_t C, double* mu_dev,
+                                   void* stream);
+
+/*
  * dkg_expected_max_lines_dev -- replaces, for P independent sets of L lines each,
  *   calculate_epigraph_indices (discretekg.py:341-412) followed by
  *   calculate_expected_value_of_piecewise_linear_function (discretekg.py:415-452):

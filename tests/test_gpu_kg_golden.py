@@ -114,3 +114,15 @@ def test_candidate_on_training_point_and_outside_unit_cube():
         kg = acq(X.unsqueeze(1))
     want = odk.forward(om, X.unsqueeze(1), P.x_disc, P.weights, 0, dense=True)
     np.testing.assert_allclose(kg.numpy(), want.numpy(), rtol=1e-7, atol=1e-11)
+
+
+def test_posterior_mean_entry_point():
+    """dkg_posterior_mean_dev == model.posterior(X).mean (oracle), incl. Standardize and ragged n."""
+    for name in ("std_d2", "ragged_d2", "rbf_d3"):
+        P = small_problem(**GOLDEN_KG_SPECS[name])
+        om = oracle_model(P.model)
+        plan = _acqf(P, 0)._get_plan()
+        X = torch.rand(37, P.d, dtype=torch.double)
+        got = plan.posterior_mean(X)
+        want = torch.stack([ogp.posterior(o, X)[0] for o in om.models], dim=-1)
+        np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-10, atol=1e-12)

@@ -66,7 +66,7 @@ static void dev_free(T*& p) {
 }
 
 static void free_workspace(Workspace& w) {
-  dev_free(w.X); dev_free(w.kg); dev_free(w.dX); dev_free(w.KX); dev_free(w.T); dev_free(w.R); dev_free(w.var);
+  dev_free(w.X); dev_free(w.kg); dev_free(w.dX); dev_free(w.KX); dev_free(w.T); dev_free(w.R); dev_free(w.T_dig); dev_free(w.T_scale); dev_free(w.var);
   dev_free(w.sd); dev_free(w.zown); dev_free(w.Xs); dev_free(w.a_new); dev_free(w.kg_terms);
   dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } { double4* t = (double4*)w.chain; dev_free(t); w.chain = nullptr; } dev_free(w.far); dev_free(w.ovf_sets); dev_free(w.ovf_count);
   dev_free(w.hull_cnt); dev_free(w.hull_idx); dev_free(w.hull_p); dev_free(w.hull_q);
@@ -104,6 +104,13 @@ static int ensure_workspace(dkg_plan* p, int C) {
   DKG_TRY(dev_alloc(&w.KX, (size_t)cap * (coupled ? GEMM_BN : p->ldk)));
   DKG_TRY(dev_alloc(&w.T, (size_t)cap * (coupled ? GEMM_BN : p->ldk)));
   DKG_TRY(dev_alloc(&w.R, (size_t)cap * ldk_max));
+  {
+    int n_max = 1;
+    for (int m = 0; m < p->M; ++m)
+      if (coupled || m == p->target) n_max = n_max > p->obj[m].n ? n_max : p->obj[m].n;
+    DKG_TRY(dev_alloc(&w.T_dig, ozaki_digit_bytes(chunk, n_max, OZ_DEFAULT_DIGITS)));
+    DKG_TRY(dev_alloc(&w.T_scale, (size_t)chunk));
+  }
   DKG_TRY(dev_alloc(&w.var, (size_t)cap));
   DKG_TRY(dev_alloc(&w.sd, (size_t)cap));
   DKG_TRY(dev_alloc(&w.zown, (size_t)cap));
@@ -148,13 +155,50 @@ static void destroy_plan(dkg_plan* p) {
   cudaDeviceSynchronize();
   for (int m = 0; m < p->M; ++m) {
     ObjState& o = p->obj[m];
-    dev_free(o.xs); dev_free(o.alpha); dev_free(o.chol); dev_free(o.Kinv); dev_free(o.Kmat); dev_free(o.B); dev_free(o.Kxd);
+    dev_free(o.xs); dev_free(o.alpha); dev_free(o.chol); dev_free(o.Kinv); dev_free(o.Kmat); dev_free(o.Kxd_dig); dev_free(o.Kxd_scale); dev_free(o.B); dev_free(o.Kxd);
     dev_free(o.BT); dev_free(o.xd_s);
   }
   dev_free(p->W); dev_free(p->wt); dev_free(p->xd); dev_free(p->alpha_all);
   dev_free(p->mu_disc); dev_free(p->A0); dev_free(p->A0max); dev_free(p->A0arg);
   free_workspace(p->ws);
   delete p;
+}
+
+// The covariance contraction runs on the int8 tensor cores (dkg_ozaki.cu) unless DKG_COV_GEMM=dmma
+// asks for the fp64 DMMA kernel (dkg_gemm.cu), which also serves n > OZ_MAX_K.
+static bool use_int8_cov() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DKG_COV_GEMM");
+    v = (e != nullptr && strcmp(e, "dmma") == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+
+// digit planes of Kxd^T (one row per discretisation point) for the int8 path
+static int make_kxd_digits(ObjState& o, const dkg_plan* p, cudaStream_t st) {
+  if (!use_int8_cov() || o.n > OZ_MAX_K) return DKG_OK;
+  double* KT = nullptr;
+  DKG_TRY(dev_alloc(&KT, (size_t)p->N * o.n_pad, false));
+  int rc = transpose(o.Kxd, o.n, p->N, p->N_pad, KT, o.n_pad, st);
+  if (rc == DKG_OK) rc = dev_alloc(&o.Kxd_dig, ozaki_digit_bytes(p->N_pad, o.n, OZ_DEFAULT_DIGITS));
+  if (rc == DKG_OK) rc = dev_alloc(&o.Kxd_scale, (size_t)p->N_pad);
+  if (rc == DKG_OK)
+    rc = ozaki_slice_rows(KT, o.n_pad, p->N, o.n, p->N_pad, OZ_DEFAULT_DIGITS, o.Kxd_dig, o.Kxd_scale, st);
+  cudaStreamSynchronize(st);
+  dev_free(KT);
+  return rc;
+}
+
+// Z rows of one chunk: (k(x_c, x_n) - T[c, :] . k(X_train, x_n)) ystd^2 / sd[c]
+static int cov_rows(const ObjState& o, const dkg_plan* p, Workspace& w, const double* T, int cc, int cc_pad,
+                    const CovEpilogue& ep, cudaStream_t st) {
+  if (o.Kxd_dig != nullptr) {
+    DKG_TRY(ozaki_slice_rows(T, o.ldk, cc, o.n, cc_pad, OZ_DEFAULT_DIGITS, w.T_dig, w.T_scale, st));
+    return ozaki_cov(w.T_dig, w.T_scale, cc_pad, o.Kxd_dig, o.Kxd_scale, p->N_pad, o.n, OZ_DEFAULT_DIGITS,
+                     OZ_DEFAULT_DIAGONALS, ep, st);
+  }
+  return gemm_cov(T, o.ldk, o.Kxd, p->N_pad, cc_pad, p->N_pad, o.n_pad, ep, st);
 }
 
 // Cholesky of K_m + noise I with GPyTorch's jitter retries (psd_safe_cholesky: 1e-8 * 10^k,
@@ -251,6 +295,7 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
         if ((rc = dev_alloc(&Ybuf, (size_t)np * p->N_pad)) != DKG_OK) { cleanup(); break; }
         if ((rc = dev_alloc(&o.Kxd, (size_t)np * p->N_pad)) != DKG_OK) { cleanup(); break; }
         if ((rc = kcross(o, o.xd_s, N, d, o.Kxd, p->N_pad, st)) != DKG_OK) { cleanup(); break; }
+        if ((rc = make_kxd_digits(o, p, st)) != DKG_OK) { cleanup(); break; }
         if ((rc = gemm_store(Linv, np, o.Kxd, p->N_pad, np, p->N_pad, o.n_pad, Ybuf, p->N_pad, st)) != DKG_OK) { cleanup(); break; }
         if ((rc = gemm_store(LinvT, np, Ybuf, p->N_pad, np, p->N_pad, o.n_pad, o.B, p->N_pad, st)) != DKG_OK) { cleanup(); break; }
         // one refinement step (see solve_T): R = Kxd - K B;  B += Kinv R
@@ -283,6 +328,7 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
         if ((rc = dev_alloc(&o.B, (size_t)o.n_pad * p->N_pad)) != DKG_OK) break;
         if ((rc = dev_alloc(&o.Kxd, (size_t)o.n_pad * p->N_pad)) != DKG_OK) break;
         if ((rc = kcross(o, o.xd_s, N, d, o.Kxd, p->N_pad, st)) != DKG_OK) break;
+        if ((rc = make_kxd_digits(o, p, st)) != DKG_OK) break;
         cudaMemcpyAsync(o.B, o.Kxd, sizeof(double) * (size_t)o.n_pad * p->N_pad, cudaMemcpyDeviceToDevice, st);
         if ((rc = cholesky_solve_inplace(Lbuf, LTbuf, n, o.B, N, p->N_pad, st)) != DKG_OK) break;
         if ((rc = dev_alloc(&o.BT, (size_t)N * o.n_pad)) != DKG_OK) break;
@@ -398,8 +444,7 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     ep.outputscale = ot.outputscale; ep.ystd2 = ystd2;
     { ProfScope ps(3, st);
       // cov[c, n] = k(x_c, x_n) - T[c, :] . k(X_train, x_n)   with T = K^-1 k(X_train, x_c)
-      DKG_TRY(gemm_cov(w.T + (size_t)c0 * p->ldk, p->ldk, ot.Kxd, p->N_pad, cc_pad, p->N_pad,
-                       ot.n_pad, ep, st)); }
+      DKG_TRY(cov_rows(ot, p, w, w.T + (size_t)c0 * p->ldk, cc, cc_pad, ep, st)); }
     { ProfScope ps(4, st); DKG_TRY(launch_place_own(w.zown + c0, cc, w.Z, p->ldz, N, st)); }
 
     LineBatch lb;
@@ -501,8 +546,7 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
       ep.xs = w.Xs; ep.xd_s = o.xd_s; ep.sd = w.sd; ep.Z = w.COVm[m];
       ep.ldz = p->ldz; ep.C = cc; ep.N = N; ep.d = d; ep.kind = o.kernel;
       ep.outputscale = o.outputscale; ep.ystd2 = o.y_std * o.y_std;
-      DKG_TRY(gemm_cov(w.Tm[m] + (size_t)c0 * o.ldk, o.ldk, o.Kxd, p->N_pad, cc_pad, p->N_pad,
-                       o.n_pad, ep, st));
+      DKG_TRY(cov_rows(o, p, w, w.Tm[m] + (size_t)c0 * o.ldk, cc, cc_pad, ep, st));
       DKG_TRY(place_latent_var(w.KXm[m] + (size_t)c0 * o.ldk, o.ldk, w.Tm[m] + (size_t)c0 * o.ldk,
                                o.ldk, o.n, cc, o.kernel, o.outputscale, o.y_std * o.y_std,
                                w.COVm[m], p->ldz, N, st));
@@ -654,6 +698,36 @@ int dkg_posterior_mean_dev(dkg_plan* plan, const double* X_dev, int32_t C, doubl
     for (int k = 0; k < MAX_D; ++k) xa.ls[m][k] = o.ls[k];
   }
   return launch_mean(xa, mu_dev, (cudaStream_t)stream);
+}
+
+int dkg_int8_matmul_dev(const double* A_dev, int32_t lda, const double* Bt_dev, int32_t ldb, int32_t M,
+                        int32_t N, int32_t K, int32_t n_digits, int32_t n_diagonals, double* D_dev,
+                        int32_t ldd, void* stream) {
+  if (n_digits == 0) n_digits = OZ_DEFAULT_DIGITS;
+  if (n_diagonals == 0) n_diagonals = OZ_DEFAULT_DIAGONALS < 2 * n_digits - 1 ? OZ_DEFAULT_DIAGONALS : 2 * n_digits - 1;
+  if (!A_dev || !Bt_dev || !D_dev || M <= 0 || N <= 0 || K <= 0 || K > OZ_MAX_K || lda < K || ldb < K ||
+      ldd < N || n_digits < 1 || n_digits > 8 || n_diagonals < 1 || n_diagonals > 2 * n_digits - 1) {
+    set_error("dkg_int8_matmul_dev: invalid argument");
+    return DKG_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M_pad = round_up(M, GEMM_BM), N_pad = round_up(N, GEMM_BN);
+  unsigned char *da = nullptr, *db = nullptr;
+  double *sa = nullptr, *sb = nullptr;
+  int rc = dev_alloc(&da, ozaki_digit_bytes(M_pad, K, n_digits));
+  if (rc == DKG_OK) rc = dev_alloc(&db, ozaki_digit_bytes(N_pad, K, n_digits));
+  if (rc == DKG_OK) rc = dev_alloc(&sa, (size_t)M_pad);
+  if (rc == DKG_OK) rc = dev_alloc(&sb, (size_t)N_pad);
+  if (rc == DKG_OK) rc = ozaki_slice_rows(A_dev, lda, M, K, M_pad, n_digits, da, sa, st);
+  if (rc == DKG_OK) rc = ozaki_slice_rows(Bt_dev, ldb, N, K, N_pad, n_digits, db, sb, st);
+  if (rc == DKG_OK) rc = ozaki_store(da, sa, M_pad, db, sb, N_pad, K, n_digits, n_diagonals, D_dev, ldd, M, N, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == DKG_OK && e != cudaSuccess) {
+    set_error("dkg_int8_matmul_dev: %s", cudaGetErrorString(e));
+    rc = DKG_ECUDA;
+  }
+  dev_free(da); dev_free(db); dev_free(sa); dev_free(sb);
+  return rc;
 }
 
 int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev, int32_t P, int32_t L,

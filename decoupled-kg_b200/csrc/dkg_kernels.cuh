@@ -45,6 +45,20 @@ int gemm_axpy(const double* A, int lda, const double* B, int ldb, int M_pad, int
 int gemm_cov(const double* KX, int lda, const double* B, int ldb, int M_pad, int N_pad, int K,
              const CovEpilogue& ep, cudaStream_t st);
 
+// ---- dkg_ozaki.cu ----------------------------------------------------------------------------
+constexpr int OZ_DEFAULT_DIGITS = 7;
+constexpr int OZ_DEFAULT_DIAGONALS = 8;
+constexpr int OZ_MAX_K = 4096;
+int ozaki_kp(int K);
+size_t ozaki_digit_bytes(int rows_pad, int K, int NS);
+int ozaki_slice_rows(const double* X, int ld, int rows, int K, int slice_rows, int NS, unsigned char* digits,
+                     double* scale, cudaStream_t st);
+int ozaki_cov(const unsigned char* a_digits, const double* sa, int M_pad, const unsigned char* b_digits,
+              const double* sb, int N_pad, int K, int NS, int NG, const CovEpilogue& ep, cudaStream_t st);
+int ozaki_store(const unsigned char* a_digits, const double* sa, int M_pad, const unsigned char* b_digits,
+                const double* sb, int N_pad, int K, int NS, int NG, double* D, int ldd, int M, int N,
+                cudaStream_t st);
+
 // ---- dkg_forward.cu --------------------------------------------------------------------------
 struct XprepArgs {
   const double* X;  // [C, d]

@@ -1,0 +1,486 @@
+// fp64-accurate GP-conditioning contraction on the 5th-generation tensor cores (tcgen05, int8).
+//
+//   cov-mode  : Z[c, n] = ( k_i(x_c, xd_n) - sum_t T[c, t] * Kxd[t, n] ) * ystd^2 / sd[c]
+//               (the fantasy-conditioned cross-covariance row of discretekg.py:301 over the
+//               predictive standard deviation, discretekg.py:313)
+//   store-mode: D = A @ B^T   (test hook)
+//
+// tcgen05.mma has no f64 kind, and the fp64 DMMA pipe of B200 tops out at 37 TFLOP/s.  The int8
+// kind runs at ~4.5 POP/s, so the product is evaluated with the Ozaki scheme: every row of T and
+// every column of Kxd is scaled by a power of two into (-128, 128) and cut into NS base-256
+// digits,
+//     x = d_0 + d_1 256^-1 + d_2 256^-2 + ...      d_0 = floor(x) in [-128, 127]  (signed),
+//                                                  d_s in [0, 255] for s >= 1     (unsigned),
+// which is EXACT in fp64 (floor / subtract / scale by 256) once x has been rounded to its last
+// digit (round-to-nearest, so the representation error is unbiased, <= 2^-56 of full scale).  Then
+//     sum_t x_t y_t = sum_g 256^-g  sum_{i+j=g} sum_t d_i(t) e_j(t),
+// and every inner sum is an integer GEMM whose int32 accumulator cannot overflow
+// (7 pairs * K <= 4096 * 255^2 < 2^31).  Diagonals g < NG are kept; with NS = 7, NG = 8 the
+// dropped terms are below 2^-64 * K of full scale (1e-16 relative to |row|max * |col|max), i.e.
+// under the rounding error of an fp64 dot product of that length.
+//
+// Kernel: persistent, one CTA per SM, 128 x 128 output tile.
+//   warp 0    : TMA producer - cp.async.bulk.tensor.2d of the A digit block (128 rows x 128 B)
+//               and the B digit block into a 4-stage ring (SWIZZLE_128B), mbarrier complete_tx.
+//   warp 1    : one thread issues tcgen05.mma.cta_group::1.kind::i8 (M128 N128 K32), 4 per
+//               stage; tcgen05.commit frees the stage and, at the end of a diagonal, publishes
+//               the TMEM accumulator (2 x 128 columns, double buffered).
+//   warps 2-9 : tcgen05.ld the int32 diagonal sums, fold them into 64 fp64 registers per thread
+//               (acc += 256^-g * S_g) while the MMA warp already runs the next diagonal; after
+//               the last one apply the row / column scales, evaluate the kernel term and write
+//               coalesced rows through a per-warp shared-memory transpose.
+// Signed / unsigned digits only differ in the instruction descriptor (a_format / b_format), so
+// the first digit of each operand is multiplied as INT8 and the others as UINT8.
+#include <cuda.h>
+
+#include "dkg_kernels.cuh"
+
+namespace dkg {
+
+namespace {
+
+constexpr int OZ_BM = 128;
+constexpr int OZ_BN = 128;
+constexpr int OZ_KB = 128;  // bytes of K per stage (one SWIZZLE_128B row)
+constexpr int OZ_STAGES = 4;
+constexpr int OZ_THREADS = 320;
+constexpr int OZ_EPI_WARPS = 8;
+constexpr int OZ_A_BYTES = OZ_BM * OZ_KB;
+constexpr int OZ_B_BYTES = OZ_BN * OZ_KB;
+constexpr int OZ_STAGE_BYTES = OZ_A_BYTES + OZ_B_BYTES;
+constexpr int OZ_EPI_LD = 33;
+constexpr int OZ_EPI_STAGE = 32 * OZ_EPI_LD;                 // doubles per warp
+constexpr int OZ_ROWDATA = 32 * (MAX_D + 1);                 // doubles per warp
+constexpr size_t OZ_SMEM = 1024 + (size_t)OZ_STAGES * OZ_STAGE_BYTES +
+                           (size_t)OZ_EPI_WARPS * (OZ_EPI_STAGE + OZ_ROWDATA) * sizeof(double) + 256;
+constexpr int OZ_TMEM_COLS = 256;
+
+struct OzakiArgs {
+  int NS, NG;
+  int KP;             // digits per row (bytes), multiple of 32
+  int a_slice_rows;   // rows between consecutive digit planes of A
+  int b_slice_rows;
+  int m_tiles, n_tiles;
+  const double* sa;   // [rows] power-of-two row scale of A
+  const double* sb;   // [cols] power-of-two row scale of B
+  int cov;            // 1: covariance epilogue, 0: plain store
+  CovEpilogue ep;
+  double* D;          // store mode
+  int ldd;
+  int M, N;           // valid rows / cols (store mode)
+};
+
+__device__ __forceinline__ unsigned s_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra D_%=;\n"
+      "bra W_%=;\n"
+      "D_%=:\n"
+      "}\n" ::"r"(s_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(s_u32(dst)),
+      "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_i8(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned idesc,
+                                        unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand tile, rows of 128 bytes, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO);
+// LBO is unused for a swizzled K-major tile; descriptor version 1 (sm_100); layout type 2.
+__device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
+  unsigned long long d = 0;
+  d |= (unsigned long long)((smem_addr & 0x3FFFF) >> 4);
+  d |= (unsigned long long)1 << 16;
+  d |= (unsigned long long)(1024 >> 4) << 32;
+  d |= (unsigned long long)1 << 46;
+  d |= (unsigned long long)2 << 61;
+  return d;
+}
+// c_format S32 (2) | a_format | b_format (1 = signed, 0 = unsigned) | K-major both | N >> 3 | M >> 4
+__device__ __forceinline__ unsigned umma_idesc(int a_signed, int b_signed) {
+  return (2u << 4) | ((unsigned)a_signed << 7) | ((unsigned)b_signed << 10) | ((unsigned)(OZ_BN >> 3) << 17) |
+         ((unsigned)(OZ_BM >> 4) << 24);
+}
+
+#define OZ_TMEM_LD32(r, taddr)                                                                                         \
+  asm volatile(                                                                                                        \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                        \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                        \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"                      \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),    \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),         \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),        \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                      \
+      : "r"(taddr))
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+             const OzakiArgs args) {
+  extern __shared__ unsigned char oz_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)oz_smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* s_stage = smem;
+  double* s_epi = reinterpret_cast<double*>(smem + (size_t)OZ_STAGES * OZ_STAGE_BYTES);
+  double* s_rowdata = s_epi + OZ_EPI_WARPS * OZ_EPI_STAGE;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_rowdata + OZ_EPI_WARPS * OZ_ROWDATA);
+  unsigned long long* full = bars;                   // [OZ_STAGES]
+  unsigned long long* empty = bars + OZ_STAGES;      // [OZ_STAGES]
+  unsigned long long* tfull = bars + 2 * OZ_STAGES;  // [2]
+  unsigned long long* tempty = tfull + 2;            // [2]
+  unsigned* s_tmem = reinterpret_cast<unsigned*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NS = args.NS, NG = args.NG;
+  const int KB = (args.KP + OZ_KB - 1) / OZ_KB;
+  const int last_chunks = (args.KP - (KB - 1) * OZ_KB) / 32;
+  const int n_tiles_total = args.m_tiles * args.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < OZ_STAGES; ++s) {
+      bar_init(&full[s], 1);
+      bar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      bar_init(&tfull[b], 1);
+      bar_init(&tempty[b], OZ_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_u32(s_tmem)), "n"(OZ_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int s = 0;
+      unsigned ph = 0;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        const int m_blk = tile % args.m_tiles, n_blk = tile / args.m_tiles;
+        for (int g = NG - 1; g >= 0; --g) {
+          const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
+          for (int i = ilo; i <= ihi; ++i) {
+            const int j = g - i;
+            const int ra = i * args.a_slice_rows + m_blk * OZ_BM;
+            const int rb = j * args.b_slice_rows + n_blk * OZ_BN;
+            for (int kb = 0; kb < KB; ++kb) {
+              bar_wait(&empty[s], ph ^ 1);
+              bar_expect_tx(&full[s], OZ_STAGE_BYTES);
+              unsigned char* st = s_stage + (size_t)s * OZ_STAGE_BYTES;
+              tma_load_2d(st, &mapA, &full[s], kb * OZ_KB, ra);
+              tma_load_2d(st + OZ_A_BYTES, &mapB, &full[s], kb * OZ_KB, rb);
+              if (++s == OZ_STAGES) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      int s = 0;
+      unsigned ph = 0;
+      unsigned gcount = 0;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        for (int g = NG - 1; g >= 0; --g, ++gcount) {
+          const unsigned b = gcount & 1, tph = (gcount >> 1) & 1;
+          bar_wait(&tempty[b], tph ^ 1);
+          tc_fence_after();
+          const unsigned d_tmem = tmem_base + b * OZ_BN;
+          unsigned accumulate = 0;
+          const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
+          for (int i = ilo; i <= ihi; ++i) {
+            const int j = g - i;
+            const unsigned idesc = umma_idesc(i == 0, j == 0);
+            for (int kb = 0; kb < KB; ++kb) {
+              bar_wait(&full[s], ph);
+              tc_fence_after();
+              const unsigned a_addr = s_u32(s_stage + (size_t)s * OZ_STAGE_BYTES);
+              const unsigned long long adesc = umma_desc(a_addr);
+              const unsigned long long bdesc = umma_desc(a_addr + OZ_A_BYTES);
+              const int nch = (kb == KB - 1) ? last_chunks : OZ_KB / 32;
+              for (int c = 0; c < nch; ++c) {
+                umma_i8(d_tmem, adesc + (unsigned long long)(c * 2), bdesc + (unsigned long long)(c * 2), idesc, accumulate);
+                accumulate = 1;
+              }
+              umma_commit(&empty[s]);
+              if (++s == OZ_STAGES) { s = 0; ph ^= 1; }
+            }
+          }
+          umma_commit(&tfull[b]);
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int ew = warp - 2;
+    const int q = warp & 3;       // TMEM lane quarter this warp may read
+    const int half = ew >> 2;     // which 64 of the 128 accumulator columns
+    double* my_stage = s_epi + ew * OZ_EPI_STAGE;
+    double* my_rows = s_rowdata + ew * OZ_ROWDATA;
+    unsigned gcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+      const int m_blk = tile % args.m_tiles, n_blk = tile / args.m_tiles;
+      double acc[64];
+#pragma unroll
+      for (int c = 0; c < 64; ++c) acc[c] = 0.0;
+      double w = 1.0;
+      for (int g = 0; g < NG - 1; ++g) w *= 0.00390625;  // 256^-(NG-1)
+      for (int g = NG - 1; g >= 0; --g, ++gcount) {
+        const unsigned b = gcount & 1, tph = (gcount >> 1) & 1;
+        bar_wait(&tfull[b], tph);
+        tc_fence_after();
+        const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + b * OZ_BN + half * 64;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          int r[32];
+          OZ_TMEM_LD32(r, taddr + h * 32);
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < 32; ++c) acc[h * 32 + c] = fma((double)r[c], w, acc[h * 32 + c]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) bar_arrive(&tempty[b]);
+        w *= 256.0;
+      }
+      // ---- final epilogue: scales, kernel term, coalesced stores ----
+      const int row0 = m_blk * OZ_BM + q * 32;
+      const int col0 = n_blk * OZ_BN + half * 64;
+      const double sa_r = args.sa[row0 + lane];
+      if (args.cov) {
+        const CovEpilogue& ep = args.ep;
+        const int d = ep.d;
+        // row data of this warp's 32 candidates: scaled coordinates and ystd^2 / sd
+        for (int e = lane; e < 32 * MAX_D; e += 32) {
+          const int r = e / MAX_D, k = e - r * MAX_D;
+          my_rows[r * (MAX_D + 1) + k] = (k < d && row0 + r < ep.C) ? ep.xs[(size_t)(row0 + r) * d + k] : 0.0;
+        }
+        my_rows[lane * (MAX_D + 1) + MAX_D] = (row0 + lane < ep.C) ? ep.ystd2 / ep.sd[row0 + lane] : 0.0;
+        const int kind = ep.kind;
+        const double os = ep.outputscale;
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) my_stage[lane * OZ_EPI_LD + c] = acc[cb * 32 + c] * sa_r;
+          __syncwarp();
+          const int col = col0 + cb * 32 + lane;
+          const double sb_c = args.sb[col];
+          double xc[MAX_D];
+#pragma unroll
+          for (int k = 0; k < MAX_D; ++k) xc[k] = (k < d) ? ep.xd_s[(size_t)col * d + k] : 0.0;
+#pragma unroll 4
+          for (int r = 0; r < 32; ++r) {
+            double sq = 0.0;
+#pragma unroll
+            for (int k = 0; k < MAX_D; ++k)
+              if (k < d) {
+                const double df = my_rows[r * (MAX_D + 1) + k] - xc[k];
+                sq += df * df;
+              }
+            const double v = my_stage[r * OZ_EPI_LD + lane] * sb_c;
+            const double z = (stationary_from_sq(kind, os, sq) - v) * my_rows[r * (MAX_D + 1) + MAX_D];
+            if (row0 + r < ep.C && col < ep.N) ep.Z[(size_t)(row0 + r) * ep.ldz + col] = z;
+          }
+        }
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) my_stage[lane * OZ_EPI_LD + c] = acc[cb * 32 + c] * sa_r;
+          __syncwarp();
+          const int col = col0 + cb * 32 + lane;
+          const double sb_c = args.sb[col];
+          for (int r = 0; r < 32; ++r)
+            if (row0 + r < args.M && col < args.N)
+              args.D[(size_t)(row0 + r) * args.ldd + col] = my_stage[r * OZ_EPI_LD + lane] * sb_c;
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(OZ_TMEM_COLS));
+  }
+}
+
+// One warp per row: power-of-two scale into (-128, 128), then NS exact base-256 digits.
+__global__ void slice_rows_kernel(const double* __restrict__ X, int ld, int rows, int K, int KP, int slice_rows, int NS,
+                                  unsigned char* __restrict__ out, double* __restrict__ scale) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const double* x = X + (size_t)r * ld;
+  double m = 0.0;
+  for (int k = lane; k < K; k += 32) m = fmax(m, fabs(x[k]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  int e = 0;
+  if (m > 0.0 && m < 1e300) frexp(m, &e);  // m = f 2^e, f in [0.5, 1)
+  const int e7 = e - 7;                     // |x| 2^-e7 < 128
+  if (lane == 0) scale[r] = scalbn(1.0, e7);
+  for (int k = lane; k < KP; k += 32) {
+    // round to the last digit first (exact: |v| 256^(NS-1) < 2^55 and fp64 has no fraction bits
+    // left above 2^52), so that the digit expansion terminates and the error is unbiased
+    double v = (k < K) ? scalbn(rint(scalbn(x[k], 8 * (NS - 1) - e7)), -8 * (NS - 1)) : 0.0;
+    for (int s = 0; s < NS; ++s) {
+      const double dg = floor(v);
+      out[((size_t)s * slice_rows + r) * KP + k] = (unsigned char)(int)dg;  // two's complement byte for s = 0
+      v = (v - dg) * 256.0;
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_digit_map(CUtensorMap* map, const unsigned char* base, int KP, long long total_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return DKG_ECUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)KP, (cuuint64_t)total_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)KP};
+  cuuint32_t box[2] = {(cuuint32_t)OZ_KB, (cuuint32_t)OZ_BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<unsigned char*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with code %d (KP=%d rows=%lld)", (int)rc, KP, total_rows);
+    return DKG_ECUDA;
+  }
+  return DKG_OK;
+}
+
+int ensure_ozaki_attr(int* n_sm) {
+  static int done_for_device[64] = {0};
+  static int sms[64] = {0};
+  int dev = 0;
+  DKG_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!done_for_device[dev]) {
+    DKG_CUDA_OK(cudaFuncSetAttribute(ozaki_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+    DKG_CUDA_OK(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+    done_for_device[dev] = 1;
+  }
+  *n_sm = sms[dev];
+  return DKG_OK;
+}
+
+}  // namespace
+
+int ozaki_kp(int K) { return round_up(K, 32); }
+
+size_t ozaki_digit_bytes(int rows_pad, int K, int NS) { return (size_t)NS * rows_pad * ozaki_kp(K); }
+
+// digits[NS][slice_rows][KP] and scale[rows] of the row-major matrix X[rows, K] (leading dim ld)
+int ozaki_slice_rows(const double* X, int ld, int rows, int K, int slice_rows, int NS, unsigned char* digits,
+                     double* scale, cudaStream_t st) {
+  if (rows == 0) return DKG_OK;
+  const int threads = 256;
+  slice_rows_kernel<<<ceil_div(rows * 32, threads), threads, 0, st>>>(X, ld, rows, K, ozaki_kp(K), slice_rows, NS,
+                                                                       digits, scale);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+static int ozaki_launch(const unsigned char* a_digits, const double* sa, int M_pad, const unsigned char* b_digits,
+                        const double* sb, int N_pad, int K, int NS, int NG, OzakiArgs& args, cudaStream_t st) {
+  int n_sm = 0;
+  DKG_TRY(ensure_ozaki_attr(&n_sm));
+  const int KP = ozaki_kp(K);
+  alignas(64) CUtensorMap mapA, mapB;
+  DKG_TRY(make_digit_map(&mapA, a_digits, KP, (long long)NS * M_pad));
+  DKG_TRY(make_digit_map(&mapB, b_digits, KP, (long long)NS * N_pad));
+  args.NS = NS;
+  args.NG = NG;
+  args.KP = KP;
+  args.a_slice_rows = M_pad;
+  args.b_slice_rows = N_pad;
+  args.m_tiles = M_pad / OZ_BM;
+  args.n_tiles = N_pad / OZ_BN;
+  args.sa = sa;
+  args.sb = sb;
+  const int tiles = args.m_tiles * args.n_tiles;
+  const int grid = tiles < n_sm ? tiles : n_sm;
+  ozaki_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(mapA, mapB, args);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// Z = (k(x_c, xd_n) - A B^T) ystd^2 / sd from digit planes (see the file header)
+int ozaki_cov(const unsigned char* a_digits, const double* sa, int M_pad, const unsigned char* b_digits,
+              const double* sb, int N_pad, int K, int NS, int NG, const CovEpilogue& ep, cudaStream_t st) {
+  OzakiArgs args{};
+  args.cov = 1;
+  args.ep = ep;
+  return ozaki_launch(a_digits, sa, M_pad, b_digits, sb, N_pad, K, NS, NG, args, st);
+}
+
+// D[M, N] = A B^T from digit planes (test hook)
+int ozaki_store(const unsigned char* a_digits, const double* sa, int M_pad, const unsigned char* b_digits,
+                const double* sb, int N_pad, int K, int NS, int NG, double* D, int ldd, int M, int N,
+                cudaStream_t st) {
+  OzakiArgs args{};
+  args.cov = 0;
+  args.D = D;
+  args.ldd = ldd;
+  args.M = M;
+  args.N = N;
+  return ozaki_launch(a_digits, sa, M_pad, b_digits, sb, N_pad, K, NS, NG, args, st);
+}
+
+}  // namespace dkg

@@ -25,6 +25,8 @@ struct ObjState {
   double* Kinv = nullptr;    // [n_pad, ldk]
   double* Kmat = nullptr;    // [n_pad, ldk]  K + (noise + jitter) I, zero padded (refinement residual)
   double* Kxd = nullptr;     // [n_pad, N_pad]  k(X_train, X_disc) (raw cross-kernel, GEMM B operand)
+  unsigned char* Kxd_dig = nullptr;  // [digits][N_pad][KP] base-256 digit planes of Kxd^T (int8 tensor-core path)
+  double* Kxd_scale = nullptr;       // [N_pad] power-of-two scale of each discretisation point's column
   double* B = nullptr;       // [n_pad, N_pad]  K^-1 k(X_train, X_disc), zero padded (backward only)
   double* BT = nullptr;      // [N, n_pad]
   double* xd_s = nullptr;    // [N_pad, d]    discretisation / lengthscale
@@ -39,6 +41,8 @@ struct Workspace {
   double* KX = nullptr;     // [cap_C, ldk]      k_i(x_c, X_train)   (target objective)
   double* T = nullptr;      // [cap_C, ldk]      KX K^-1 (Kinv product + one refinement step)
   double* R = nullptr;      // [cap_C, ldk_max]  refinement residual KX - T K
+  unsigned char* T_dig = nullptr;  // [digits][chunk_C][KP_max] digit planes of the T rows of one chunk
+  double* T_scale = nullptr;       // [chunk_C]
   double* var = nullptr;    // [cap_C]           noisy predictive variance (un-standardised)
   double* sd = nullptr;     // [cap_C]           sqrt(var)
   double* zown = nullptr;   // [cap_C]           slope of the candidate's own line

@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "dkg_forward_host",
     "dkg_expected_max_lines_dev",
     "dkg_posterior_mean_dev",
+    "dkg_int8_matmul_dev",
     "dkg_plan_read",
     "dkg_launch_count",
     "dkg_launch_count_reset",
@@ -95,6 +96,11 @@ def load_library() -> ctypes.CDLL:
     ]
     lib.dkg_posterior_mean_dev.restype = ctypes.c_int
     lib.dkg_posterior_mean_dev.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]
+    lib.dkg_int8_matmul_dev.restype = ctypes.c_int
+    lib.dkg_int8_matmul_dev.argtypes = [
+        c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
+        c_int32, c_void_p,
+    ]
     lib.dkg_plan_read.restype = c_int64
     lib.dkg_plan_read.argtypes = [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]
     lib.dkg_launch_count.restype = c_int64
@@ -309,6 +315,25 @@ class Plan:
             rc = load_library().dkg_plan_stats(self._handle, buf, _stream_ptr())
         _check(rc, "dkg_plan_stats")
         return [int(v) for v in buf]
+
+
+def int8_matmul(A: Tensor, Bt: Tensor, n_digits: int = 0, n_diagonals: int = 0) -> Tensor:
+    """``A @ Bt.T`` in float64 accuracy on the int8 tensor cores (``dkg_int8_matmul_dev``): the
+    contraction engine of the covariance rows, exposed for its own parity tests."""
+    dev = require_cuda()
+    A = A.detach().to(device=dev, dtype=torch.double).contiguous()
+    Bt = Bt.detach().to(device=dev, dtype=torch.double).contiguous()
+    if A.dim() != 2 or Bt.dim() != 2 or A.shape[1] != Bt.shape[1]:
+        raise ValueError(f"A (M, K) and Bt (N, K) expected; got {tuple(A.shape)}, {tuple(Bt.shape)}")
+    M, K = A.shape
+    N = Bt.shape[0]
+    D = torch.empty(M, N, dtype=torch.double, device=dev)
+    with torch.cuda.device(dev):
+        rc = load_library().dkg_int8_matmul_dev(
+            _ptr(A), K, _ptr(Bt), K, M, N, K, n_digits, n_diagonals, _ptr(D), N, _stream_ptr()
+        )
+    _check(rc, "dkg_int8_matmul_dev")
+    return D
 
 
 def expected_max_lines(a: Tensor, b: Tensor, hull_cap: int = 64, want_grad: bool = False):

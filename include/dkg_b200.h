@@ -141,6 +141,17 @@ DKG_API int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev,
                                double* dE_db_dev, void* stream);
 
 /*
+ * dkg_int8_matmul_dev -- D[M, N] = A[M, K] . Bt[N, K]^T in fp64 accuracy on the int8 tensor cores
+ *   (tcgen05.mma.kind::i8 over exact base-256 digit planes; csrc/dkg_ozaki.cu).  This is the
+ *   contraction engine behind the covariance rows of discretekg.py:301, exposed so that it can
+ *   be checked on its own.  n_digits in [1, 8]; n_diagonals in [1, 2 n_digits - 1]
+ *   (0, 0 selects the defaults 7 / 8).  K <= 4096.
+ */
+DKG_API int dkg_int8_matmul_dev(const double* A_dev, int32_t lda, const double* Bt_dev, int32_t ldb,
+                                int32_t M, int32_t N, int32_t K, int32_t n_digits,
+                                int32_t n_diagonals, double* D_dev, int32_t ldd, void* stream);
+
+/*
  * Introspection for parity tests (all copies are device-to-device on `stream`).
  * name is one of:
  *   "B"        [n_i, N]   K_i^-1 k_i(X_train, X_disc)            (target objective i)

@@ -1,0 +1,50 @@
+"""The int8 tensor-core contraction (csrc/dkg_ozaki.cu) against exact / extended-precision products.
+
+Digits are exact, so with integer inputs small enough for one digit the product must be bit-exact;
+with real inputs the error must stay at the level of an fp64 dot product (relative to
+|row|max * |col|max * K, the bound of the fixed-point scheme)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mm(A, Bt, **kw):
+    from decoupledbo_b200 import _native
+
+    return _native.int8_matmul(A, Bt, **kw).cpu()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 128), (128, 256, 416), (300, 200, 100), (1, 1, 1), (257, 129, 800)])
+def test_small_integers_are_exact(M, N, K):
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randint(-100, 100, (M, K), generator=g).double()
+    B = torch.randint(-100, 100, (N, K), generator=g).double()
+    want = A @ B.T
+    got = _mm(A, B)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("nd", [1, 2, 3])
+def test_digit_planes_and_signs(nd):
+    # values with exactly `nd` base-256 digits below the leading one, both signs
+    g = torch.Generator().manual_seed(nd)
+    A = torch.randint(-(2 ** (8 * nd - 2)), 2 ** (8 * nd - 2), (128, 64), generator=g).double()
+    B = torch.randint(-(2 ** (8 * nd - 2)), 2 ** (8 * nd - 2), (128, 64), generator=g).double()
+    want = A @ B.T  # exact in fp64 while 2 * (8 nd - 2) + 6 <= 53
+    got = _mm(A, B, n_digits=nd + 1, n_diagonals=2 * nd + 1)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 384, 400), (128, 128, 1000)])
+def test_real_inputs_match_extended_precision(M, N, K):
+    rng = np.random.default_rng(K)
+    A = rng.standard_normal((M, K)) * np.exp(rng.standard_normal((M, 1)) * 3)
+    B = rng.standard_normal((N, K)) * np.exp(rng.standard_normal((N, 1)) * 3)
+    truth = (A.astype(np.longdouble) @ B.astype(np.longdouble).T).astype(np.float64)
+    got = _mm(torch.from_numpy(A), torch.from_numpy(B)).numpy()
+    bound = np.abs(A).max(1)[:, None] * np.abs(B).max(1)[None, :] * K
+    err = np.abs(got - truth) / bound
+    ref = np.abs(A @ B.T - truth) / bound  # plain fp64 GEMM on the host
+    assert err.max() < 4e-16, (err.max(), ref.max())

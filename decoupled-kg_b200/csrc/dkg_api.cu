@@ -706,7 +706,7 @@ int dkg_int8_matmul_dev(const double* A_dev, int32_t lda, const double* Bt_dev, 
   if (n_digits == 0) n_digits = OZ_DEFAULT_DIGITS;
   if (n_diagonals == 0) n_diagonals = OZ_DEFAULT_DIAGONALS < 2 * n_digits - 1 ? OZ_DEFAULT_DIAGONALS : 2 * n_digits - 1;
   if (!A_dev || !Bt_dev || !D_dev || M <= 0 || N <= 0 || K <= 0 || K > OZ_MAX_K || lda < K || ldb < K ||
-      ldd < N || n_digits < 1 || n_digits > 8 || n_diagonals < 1 || n_diagonals > 2 * n_digits - 1) {
+      ldd < N || n_digits < 1 || n_digits > 7 || n_diagonals < 1 || n_diagonals > 2 * n_digits - 1) {
     set_error("dkg_int8_matmul_dev: invalid argument");
     return DKG_EINVAL;
   }

@@ -41,19 +41,20 @@ namespace {
 
 constexpr int OZ_BM = 128;
 constexpr int OZ_BN = 128;
-constexpr int OZ_KB = 128;  // bytes of K per stage (one SWIZZLE_128B row)
-constexpr int OZ_STAGES = 4;
-constexpr int OZ_THREADS = 320;
-constexpr int OZ_EPI_WARPS = 8;
-constexpr int OZ_A_BYTES = OZ_BM * OZ_KB;
-constexpr int OZ_B_BYTES = OZ_BN * OZ_KB;
-constexpr int OZ_STAGE_BYTES = OZ_A_BYTES + OZ_B_BYTES;
-constexpr int OZ_EPI_LD = 33;
-constexpr int OZ_EPI_STAGE = 32 * OZ_EPI_LD;                 // doubles per warp
-constexpr int OZ_ROWDATA = 32 * (MAX_D + 1);                 // doubles per warp
-constexpr size_t OZ_SMEM = 1024 + (size_t)OZ_STAGES * OZ_STAGE_BYTES +
+constexpr int OZ_KB = 32;             // bytes of K per stage = one MMA (K32), SWIZZLE_32B rows
+constexpr int OZ_BLK_BYTES = OZ_BM * OZ_KB;  // one digit block (A or B) of a stage: 4 KB
+constexpr int OZ_MAX_DIGITS = 7;
+constexpr int OZ_STAGES = 2;          // x (2 * digits * 4 KB) = 112 KB at 7 digits
+constexpr int OZ_ACC = 4;             // TMEM accumulators (diagonals) per pass: 4 x 128 = all 512 columns
+constexpr int OZ_THREADS = 640;       // warp 0 TMA, warp 1 MMA, (2, 3 idle), warps 4..19 epilogue
+constexpr int OZ_EPI_WARPS = 16;
+constexpr int OZ_EPI_LD = 17;
+constexpr int OZ_EPI_STAGE = 32 * OZ_EPI_LD;  // doubles per warp (32 rows x 16 columns, padded)
+constexpr int OZ_ROWDATA = 32 * (MAX_D + 1);  // doubles per warp
+constexpr size_t OZ_SMEM = 1024 + (size_t)OZ_STAGES * 2 * OZ_MAX_DIGITS * OZ_BLK_BYTES +
                            (size_t)OZ_EPI_WARPS * (OZ_EPI_STAGE + OZ_ROWDATA) * sizeof(double) + 256;
-constexpr int OZ_TMEM_COLS = 256;
+constexpr int OZ_TMEM_COLS = 512;
+static_assert(OZ_SMEM <= 227 * 1024, "shared memory budget");
 
 struct OzakiArgs {
   int NS, NG;
@@ -113,15 +114,15 @@ __device__ __forceinline__ void umma_i8(unsigned d_tmem, unsigned long long ades
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major operand tile, rows of 128 bytes, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO);
-// LBO is unused for a swizzled K-major tile; descriptor version 1 (sm_100); layout type 2.
+// K-major operand tile, rows of 32 bytes, SWIZZLE_32B: 8-row groups are 256 B apart (SBO);
+// LBO is unused for a swizzled K-major tile; descriptor version 1 (sm_100); layout type 6.
 __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
   unsigned long long d = 0;
   d |= (unsigned long long)((smem_addr & 0x3FFFF) >> 4);
   d |= (unsigned long long)1 << 16;
-  d |= (unsigned long long)(1024 >> 4) << 32;
+  d |= (unsigned long long)(256 >> 4) << 32;
   d |= (unsigned long long)1 << 46;
-  d |= (unsigned long long)2 << 61;
+  d |= (unsigned long long)6 << 61;
   return d;
 }
 // c_format S32 (2) | a_format | b_format (1 = signed, 0 = unsigned) | K-major both | N >> 3 | M >> 4
@@ -141,36 +142,41 @@ __device__ __forceinline__ unsigned umma_idesc(int a_signed, int b_signed) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                      \
       : "r"(taddr))
 
+// exact int32 -> fp64 without the (slow, XU-pipe) I2F.F64: 2^52 + 2^31 + v has the integer in its
+// low mantissa word; one DADD removes the offset
+__device__ __forceinline__ double i32_to_f64(int v) {
+  return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0;
+}
+
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
              const OzakiArgs args) {
   extern __shared__ unsigned char oz_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)oz_smem_raw + 1023) & ~(uintptr_t)1023);
+  const int NS = args.NS, NG = args.NG;
+  const int stage_bytes = 2 * NS * OZ_BLK_BYTES;
   unsigned char* s_stage = smem;
-  double* s_epi = reinterpret_cast<double*>(smem + (size_t)OZ_STAGES * OZ_STAGE_BYTES);
+  double* s_epi = reinterpret_cast<double*>(smem + (size_t)OZ_STAGES * 2 * OZ_MAX_DIGITS * OZ_BLK_BYTES);
   double* s_rowdata = s_epi + OZ_EPI_WARPS * OZ_EPI_STAGE;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_rowdata + OZ_EPI_WARPS * OZ_ROWDATA);
-  unsigned long long* full = bars;                   // [OZ_STAGES]
-  unsigned long long* empty = bars + OZ_STAGES;      // [OZ_STAGES]
-  unsigned long long* tfull = bars + 2 * OZ_STAGES;  // [2]
-  unsigned long long* tempty = tfull + 2;            // [2]
-  unsigned* s_tmem = reinterpret_cast<unsigned*>(tempty + 2);
+  unsigned long long* full = bars;               // [OZ_STAGES]
+  unsigned long long* empty = bars + OZ_STAGES;  // [OZ_STAGES]
+  unsigned long long* tfull = bars + 2 * OZ_STAGES;
+  unsigned long long* tempty = tfull + 1;
+  unsigned* s_tmem = reinterpret_cast<unsigned*>(tempty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int NS = args.NS, NG = args.NG;
-  const int KB = (args.KP + OZ_KB - 1) / OZ_KB;
-  const int last_chunks = (args.KP - (KB - 1) * OZ_KB) / 32;
+  const int KB = args.KP / OZ_KB;
   const int n_tiles_total = args.m_tiles * args.n_tiles;
+  const int n_pass = (NG + OZ_ACC - 1) / OZ_ACC;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < OZ_STAGES; ++s) {
       bar_init(&full[s], 1);
       bar_init(&empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      bar_init(&tfull[b], 1);
-      bar_init(&tempty[b], OZ_EPI_WARPS);
-    }
+    bar_init(tfull, 1);
+    bar_init(tempty, OZ_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
@@ -182,108 +188,107 @@ ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   tc_fence_after();
   const unsigned tmem_base = *s_tmem;
 
-  if (warp == 0) {
-    if (lane == 0) {
+  // Pass p folds the diagonals g_hi(p) .. g_lo(p) (at most OZ_ACC of them, one TMEM accumulator
+  // each), lowest weights first.  Digits needed by a pass: i, j in [max(0, g_lo - NS + 1), min(g_hi, NS - 1)].
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    if (warp == 0 && lane == 0) {
       // ===== TMA producer =====
       int s = 0;
       unsigned ph = 0;
       for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
         const int m_blk = tile % args.m_tiles, n_blk = tile / args.m_tiles;
-        for (int g = NG - 1; g >= 0; --g) {
-          const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
-          for (int i = ilo; i <= ihi; ++i) {
-            const int j = g - i;
-            const int ra = i * args.a_slice_rows + m_blk * OZ_BM;
-            const int rb = j * args.b_slice_rows + n_blk * OZ_BN;
-            for (int kb = 0; kb < KB; ++kb) {
-              bar_wait(&empty[s], ph ^ 1);
-              bar_expect_tx(&full[s], OZ_STAGE_BYTES);
-              unsigned char* st = s_stage + (size_t)s * OZ_STAGE_BYTES;
-              tma_load_2d(st, &mapA, &full[s], kb * OZ_KB, ra);
-              tma_load_2d(st + OZ_A_BYTES, &mapB, &full[s], kb * OZ_KB, rb);
-              if (++s == OZ_STAGES) { s = 0; ph ^= 1; }
+        for (int p = 0; p < n_pass; ++p) {
+          const int g_hi = NG - 1 - p * OZ_ACC;
+          const int g_lo = g_hi - OZ_ACC + 1 > 0 ? g_hi - OZ_ACC + 1 : 0;
+          const int dlo = g_lo - NS + 1 > 0 ? g_lo - NS + 1 : 0, dhi = g_hi < NS - 1 ? g_hi : NS - 1;
+          const unsigned bytes = (unsigned)(2 * (dhi - dlo + 1) * OZ_BLK_BYTES);
+          for (int kb = 0; kb < KB; ++kb) {
+            bar_wait(&empty[s], ph ^ 1);
+            bar_expect_tx(&full[s], bytes);
+            unsigned char* st = s_stage + (size_t)s * stage_bytes;
+            for (int dg = dlo; dg <= dhi; ++dg) {
+              tma_load_2d(st + dg * OZ_BLK_BYTES, &mapA, &full[s], kb * OZ_KB, dg * args.a_slice_rows + m_blk * OZ_BM);
+              tma_load_2d(st + (NS + dg) * OZ_BLK_BYTES, &mapB, &full[s], kb * OZ_KB,
+                          dg * args.b_slice_rows + n_blk * OZ_BN);
             }
+            if (++s == OZ_STAGES) { s = 0; ph ^= 1; }
           }
         }
       }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
+    } else if (warp == 1 && lane == 0) {
       // ===== MMA issuer =====
       int s = 0;
       unsigned ph = 0;
-      unsigned gcount = 0;
+      unsigned pcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-        for (int g = NG - 1; g >= 0; --g, ++gcount) {
-          const unsigned b = gcount & 1, tph = (gcount >> 1) & 1;
-          bar_wait(&tempty[b], tph ^ 1);
+        for (int p = 0; p < n_pass; ++p, ++pcount) {
+          const int g_hi = NG - 1 - p * OZ_ACC;
+          const int g_lo = g_hi - OZ_ACC + 1 > 0 ? g_hi - OZ_ACC + 1 : 0;
+          bar_wait(tempty, (pcount & 1) ^ 1);
           tc_fence_after();
-          const unsigned d_tmem = tmem_base + b * OZ_BN;
-          unsigned accumulate = 0;
-          const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
-          for (int i = ilo; i <= ihi; ++i) {
-            const int j = g - i;
-            const unsigned idesc = umma_idesc(i == 0, j == 0);
-            for (int kb = 0; kb < KB; ++kb) {
-              bar_wait(&full[s], ph);
-              tc_fence_after();
-              const unsigned a_addr = s_u32(s_stage + (size_t)s * OZ_STAGE_BYTES);
-              const unsigned long long adesc = umma_desc(a_addr);
-              const unsigned long long bdesc = umma_desc(a_addr + OZ_A_BYTES);
-              const int nch = (kb == KB - 1) ? last_chunks : OZ_KB / 32;
-              for (int c = 0; c < nch; ++c) {
-                umma_i8(d_tmem, adesc + (unsigned long long)(c * 2), bdesc + (unsigned long long)(c * 2), idesc, accumulate);
-                accumulate = 1;
+          for (int kb = 0; kb < KB; ++kb) {
+            bar_wait(&full[s], ph);
+            tc_fence_after();
+            const unsigned st_addr = s_u32(s_stage + (size_t)s * stage_bytes);
+            for (int g = g_hi; g >= g_lo; --g) {
+              const unsigned d_tmem = tmem_base + (unsigned)(g_hi - g) * OZ_BN;
+              const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
+              for (int i = ilo; i <= ihi; ++i) {
+                const int j = g - i;
+                umma_i8(d_tmem, umma_desc(st_addr + i * OZ_BLK_BYTES), umma_desc(st_addr + (NS + j) * OZ_BLK_BYTES),
+                        umma_idesc(i == 0, j == 0), (kb > 0 || i > ilo) ? 1u : 0u);
               }
-              umma_commit(&empty[s]);
-              if (++s == OZ_STAGES) { s = 0; ph ^= 1; }
             }
+            umma_commit(&empty[s]);
+            if (++s == OZ_STAGES) { s = 0; ph ^= 1; }
           }
-          umma_commit(&tfull[b]);
+          umma_commit(tfull);
         }
       }
     }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n");
     // ===== epilogue warps =====
-    const int ew = warp - 2;
-    const int q = warp & 3;       // TMEM lane quarter this warp may read
-    const int half = ew >> 2;     // which 64 of the 128 accumulator columns
+    const int ew = warp - 4;
+    const int q = warp & 3;    // TMEM lane quarter this warp may read
+    const int cg = ew >> 2;    // which 32 of the 128 accumulator columns
     double* my_stage = s_epi + ew * OZ_EPI_STAGE;
     double* my_rows = s_rowdata + ew * OZ_ROWDATA;
-    unsigned gcount = 0;
+    unsigned pcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
       const int m_blk = tile % args.m_tiles, n_blk = tile / args.m_tiles;
-      double acc[64];
+      double acc[32];
 #pragma unroll
-      for (int c = 0; c < 64; ++c) acc[c] = 0.0;
-      double w = 1.0;
-      for (int g = 0; g < NG - 1; ++g) w *= 0.00390625;  // 256^-(NG-1)
-      for (int g = NG - 1; g >= 0; --g, ++gcount) {
-        const unsigned b = gcount & 1, tph = (gcount >> 1) & 1;
-        bar_wait(&tfull[b], tph);
+      for (int c = 0; c < 32; ++c) acc[c] = 0.0;
+      for (int p = 0; p < n_pass; ++p, ++pcount) {
+        const int g_hi = NG - 1 - p * OZ_ACC;
+        const int g_lo = g_hi - OZ_ACC + 1 > 0 ? g_hi - OZ_ACC + 1 : 0;
+        double w = 1.0;
+        for (int g = 0; g < g_hi; ++g) w *= 0.00390625;  // 256^-g_hi
+        bar_wait(tfull, pcount & 1);
         tc_fence_after();
-        const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + b * OZ_BN + half * 64;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + cg * 32;
+        for (int g = g_hi; g >= g_lo; --g) {
           int r[32];
-          OZ_TMEM_LD32(r, taddr + h * 32);
+          OZ_TMEM_LD32(r, taddr + (unsigned)(g_hi - g) * OZ_BN);
           asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-          for (int c = 0; c < 32; ++c) acc[h * 32 + c] = fma((double)r[c], w, acc[h * 32 + c]);
+          for (int c = 0; c < 32; ++c) acc[c] = fma(i32_to_f64(r[c]), w, acc[c]);
+          w *= 256.0;
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) bar_arrive(&tempty[b]);
-        w *= 256.0;
+        if (lane == 0) bar_arrive(tempty);
       }
-      // ---- final epilogue: scales, kernel term, coalesced stores ----
+      // ---- final epilogue: scales, kernel term, coalesced stores (two rows of 16 columns per pass) ----
       const int row0 = m_blk * OZ_BM + q * 32;
-      const int col0 = n_blk * OZ_BN + half * 64;
+      const int col0 = n_blk * OZ_BN + cg * 32;
       const double sa_r = args.sa[row0 + lane];
+      const int hr = lane >> 4, hc = lane & 15;
       if (args.cov) {
         const CovEpilogue& ep = args.ep;
         const int d = ep.d;
-        // row data of this warp's 32 candidates: scaled coordinates and ystd^2 / sd
         for (int e = lane; e < 32 * MAX_D; e += 32) {
           const int r = e / MAX_D, k = e - r * MAX_D;
           my_rows[r * (MAX_D + 1) + k] = (k < d && row0 + r < ep.C) ? ep.xs[(size_t)(row0 + r) * d + k] : 0.0;
@@ -292,18 +297,19 @@ ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const int kind = ep.kind;
         const double os = ep.outputscale;
 #pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {
+        for (int h = 0; h < 2; ++h) {
           __syncwarp();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) my_stage[lane * OZ_EPI_LD + c] = acc[cb * 32 + c] * sa_r;
+          for (int c = 0; c < 16; ++c) my_stage[lane * OZ_EPI_LD + c] = acc[h * 16 + c] * sa_r;
           __syncwarp();
-          const int col = col0 + cb * 32 + lane;
+          const int col = col0 + h * 16 + hc;
           const double sb_c = args.sb[col];
           double xc[MAX_D];
 #pragma unroll
           for (int k = 0; k < MAX_D; ++k) xc[k] = (k < d) ? ep.xd_s[(size_t)col * d + k] : 0.0;
 #pragma unroll 4
-          for (int r = 0; r < 32; ++r) {
+          for (int it = 0; it < 16; ++it) {
+            const int r = 2 * it + hr;
             double sq = 0.0;
 #pragma unroll
             for (int k = 0; k < MAX_D; ++k)
@@ -311,7 +317,7 @@ ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                 const double df = my_rows[r * (MAX_D + 1) + k] - xc[k];
                 sq += df * df;
               }
-            const double v = my_stage[r * OZ_EPI_LD + lane] * sb_c;
+            const double v = my_stage[r * OZ_EPI_LD + hc] * sb_c;
             const double z = (stationary_from_sq(kind, os, sq) - v) * my_rows[r * (MAX_D + 1) + MAX_D];
             if (row0 + r < ep.C && col < ep.N) ep.Z[(size_t)(row0 + r) * ep.ldz + col] = z;
           }
@@ -319,16 +325,18 @@ ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         __syncwarp();
       } else {
 #pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {
+        for (int h = 0; h < 2; ++h) {
           __syncwarp();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) my_stage[lane * OZ_EPI_LD + c] = acc[cb * 32 + c] * sa_r;
+          for (int c = 0; c < 16; ++c) my_stage[lane * OZ_EPI_LD + c] = acc[h * 16 + c] * sa_r;
           __syncwarp();
-          const int col = col0 + cb * 32 + lane;
+          const int col = col0 + h * 16 + hc;
           const double sb_c = args.sb[col];
-          for (int r = 0; r < 32; ++r)
+          for (int it = 0; it < 16; ++it) {
+            const int r = 2 * it + hr;
             if (row0 + r < args.M && col < args.N)
-              args.D[(size_t)(row0 + r) * args.ldd + col] = my_stage[r * OZ_EPI_LD + lane] * sb_c;
+              args.D[(size_t)(row0 + r) * args.ldd + col] = my_stage[r * OZ_EPI_LD + hc] * sb_c;
+          }
         }
         __syncwarp();
       }
@@ -396,7 +404,7 @@ int make_digit_map(CUtensorMap* map, const unsigned char* base, int KP, long lon
   cuuint32_t box[2] = {(cuuint32_t)OZ_KB, (cuuint32_t)OZ_BM};
   cuuint32_t estr[2] = {1, 1};
   CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<unsigned char*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with code %d (KP=%d rows=%lld)", (int)rc, KP, total_rows);

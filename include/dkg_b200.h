@@ -144,7 +144,7 @@ DKG_API int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev,
  * dkg_int8_matmul_dev -- D[M, N] = A[M, K] . Bt[N, K]^T in fp64 accuracy on the int8 tensor cores
  *   (tcgen05.mma.kind::i8 over exact base-256 digit planes; csrc/dkg_ozaki.cu).  This is the
  *   contraction engine behind the covariance rows of discretekg.py:301, exposed so that it can
- *   be checked on its own.  n_digits in [1, 8]; n_diagonals in [1, 2 n_digits - 1]
+ *   be checked on its own.  n_digits in [1, 7]; n_diagonals in [1, 2 n_digits - 1]
  *   (0, 0 selects the defaults 7 / 8).  K <= 4096.
  */
 DKG_API int dkg_int8_matmul_dev(const double* A_dev, int32_t lda, const double* Bt_dev, int32_t ldb,

@@ -444,7 +444,16 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     ep.outputscale = ot.outputscale; ep.ystd2 = ystd2;
     { ProfScope ps(3, st);
       // cov[c, n] = k(x_c, x_n) - T[c, :] . k(X_train, x_n)   with T = K^-1 k(X_train, x_c)
-      DKG_TRY(cov_rows(ot, p, w, w.T + (size_t)c0 * p->ldk, cc, cc_pad, ep, st)); }
+      if (ot.Kxd_dig != nullptr) {
+        // int8 tensor cores in product mode: Z <- T . Kxd; the row-statistics pass below turns
+        // the products into slopes while it reads them (CovFinish)
+        DKG_TRY(ozaki_slice_rows(w.T + (size_t)c0 * p->ldk, p->ldk, cc, ot.n, cc_pad, OZ_DEFAULT_DIGITS, w.T_dig,
+                                 w.T_scale, st));
+        DKG_TRY(ozaki_store(w.T_dig, w.T_scale, cc_pad, ot.Kxd_dig, ot.Kxd_scale, p->N_pad, ot.n, OZ_DEFAULT_DIGITS,
+                            OZ_DEFAULT_DIAGONALS, w.Z, p->ldz, cc, N, st));
+      } else {
+        DKG_TRY(cov_rows(ot, p, w, w.T + (size_t)c0 * p->ldk, cc, cc_pad, ep, st));
+      } }
     { ProfScope ps(4, st); DKG_TRY(launch_place_own(w.zown + c0, cc, w.Z, p->ldz, N, st)); }
 
     LineBatch lb;
@@ -461,7 +470,11 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     DKG_CUDA_OK(cudaMemsetAsync(w.surv_cnt, 0, sizeof(int) * (size_t)cc * S, st));
     DKG_CUDA_OK(cudaMemsetAsync(w.far, 0, sizeof(unsigned long long) * (size_t)cc * S * 2, st));
     DKG_CUDA_OK(cudaMemsetAsync(w.ovf_count, 0, sizeof(int), st));
-    { ProfScope ps(5, st); DKG_TRY(emax_zstat(lb, sc, nullptr, nullptr, st)); }
+    CovFinish fin{};
+    fin.xs = ep.xs; fin.xd_s = ep.xd_s; fin.sd = ep.sd; fin.d = d; fin.kind = ep.kind; fin.N = N;
+    fin.outputscale = ep.outputscale; fin.ystd2 = ep.ystd2;
+    { ProfScope ps(5, st);
+      DKG_TRY(emax_zstat(lb, sc, nullptr, nullptr, st, ot.Kxd_dig != nullptr ? &fin : nullptr)); }
     { ProfScope ps(6, st); DKG_TRY(emax_filter(lb, sc, st)); }
     EmaxOut out;
     out.terms = w.kg_terms + (size_t)c0 * S;

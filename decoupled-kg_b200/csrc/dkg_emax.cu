@@ -79,20 +79,49 @@ __device__ double4 chain_params(const LineBatch& lb, const EmaxScratch& sc, int 
 
 // one CTA per row: min / max (with first index) of the slope row; optionally the max intercept;
 // then the chord-chain parameters of the row's S sets (consumed by the filter kernel)
+template <int D>
 __global__ void __launch_bounds__(E_THREADS)
 zstat_kernel(LineBatch lb, EmaxScratch sc, double* __restrict__ zst, int* __restrict__ zarg,
-             double* __restrict__ amax_out, int* __restrict__ aarg_out) {
+             double* __restrict__ amax_out, int* __restrict__ aarg_out, CovFinish fin) {
   __shared__ double s_v[E_THREADS / 32];
   __shared__ int s_i[E_THREADS / 32];
   const int c = blockIdx.x;
-  const double* z = lb.Z + (size_t)c * lb.ldz;
   double vmin = INFINITY, vmax = -INFINITY;
   int imin = 0x7fffffff, imax = 0x7fffffff;
+  if (D > 0) {
+    // finish the slopes in place (see CovFinish), then the statistics of the finished values
+    double* zw = const_cast<double*>(lb.Z) + (size_t)c * lb.ldz;
+    double xr[D > 0 ? D : 1];
+#pragma unroll
+    for (int k = 0; k < D; ++k) xr[k] = fin.xs[(size_t)c * D + k];
+    const double rsd = fin.ystd2 / fin.sd[c];
+    const int kind = fin.kind;
+    const double os = fin.outputscale;
+#pragma unroll 4
+    for (int n = threadIdx.x; n < lb.NL; n += blockDim.x) {
+      double v = zw[n];
+      if (n < fin.N) {
+        double sq = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double df = xr[k] - fin.xd_s[(size_t)n * D + k];
+          sq = fma(df, df, sq);
+        }
+        v = (stationary_from_sq(kind, os, sq) - v) * rsd;
+        zw[n] = v;
+      }
+      if (v < vmin) { vmin = v; imin = n; }
+      if (v > vmax) { vmax = v; imax = n; }
+    }
+    __threadfence_block();
+  } else {
+    const double* z = lb.Z + (size_t)c * lb.ldz;
 #pragma unroll 8
-  for (int n = threadIdx.x; n < lb.NL; n += blockDim.x) {
-    double v = z[n];
-    if (v < vmin) { vmin = v; imin = n; }
-    if (v > vmax) { vmax = v; imax = n; }
+    for (int n = threadIdx.x; n < lb.NL; n += blockDim.x) {
+      double v = z[n];
+      if (v < vmin) { vmin = v; imin = n; }
+      if (v > vmax) { vmax = v; imax = n; }
+    }
   }
   block_arg_reduce<MinOp>(vmin, imin, s_v, s_i);
   block_arg_reduce<MaxOp>(vmax, imax, s_v, s_i);
@@ -122,9 +151,23 @@ zstat_kernel(LineBatch lb, EmaxScratch sc, double* __restrict__ zst, int* __rest
 }
 
 int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int* aarg_out,
-               cudaStream_t st) {
+               cudaStream_t st, const CovFinish* fin) {
   if (lb.C == 0) return DKG_OK;
-  zstat_kernel<<<lb.C, E_THREADS, 0, st>>>(lb, sc, sc.zst, sc.zarg, amax_out, aarg_out);
+  CovFinish f{};
+  if (fin != nullptr) f = *fin;
+#define DKG_ZSTAT(DD) zstat_kernel<DD><<<lb.C, E_THREADS, 0, st>>>(lb, sc, sc.zst, sc.zarg, amax_out, aarg_out, f)
+  switch (fin != nullptr ? fin->d : 0) {
+    case 0: DKG_ZSTAT(0); break;
+    case 1: DKG_ZSTAT(1); break;
+    case 2: DKG_ZSTAT(2); break;
+    case 3: DKG_ZSTAT(3); break;
+    case 4: DKG_ZSTAT(4); break;
+    case 5: DKG_ZSTAT(5); break;
+    case 6: DKG_ZSTAT(6); break;
+    case 7: DKG_ZSTAT(7); break;
+    default: DKG_ZSTAT(8); break;
+  }
+#undef DKG_ZSTAT
   DKG_LAUNCH_CHECK();
   return DKG_OK;
 }

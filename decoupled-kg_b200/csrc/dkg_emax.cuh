@@ -90,8 +90,19 @@ struct BackwardArgs {
   double ls[MAX_M][MAX_D];
 };
 
+// Optional fused completion of the slope rows: when the covariance contraction ran on the int8
+// tensor cores in product mode, Z holds P[c, n] = T[c, :] . k(X_train, x_n) and the row statistics
+// pass turns it into the slopes  (k(x_c, x_n) - P) ystd^2 / sd[c]  (discretekg.py:301, :313) in
+// place while it reads the row anyway.
+struct CovFinish {
+  const double* xs;    // [C, d] candidates / lengthscale
+  const double* xd_s;  // [N_pad, d] discretisation / lengthscale
+  const double* sd;    // [C]
+  int d, kind, N;
+  double outputscale, ystd2;
+};
 int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int* aarg_out,
-               cudaStream_t st);
+               cudaStream_t st, const CovFinish* fin = nullptr);
 int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st);
 // warp-per-set exact hull + closed-form expectation; sets it cannot finish go to the queue
 int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cudaStream_t st);

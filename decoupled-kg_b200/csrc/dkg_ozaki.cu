@@ -31,8 +31,6 @@
 //               coalesced rows through a per-warp shared-memory transpose.
 // Signed / unsigned digits only differ in the instruction descriptor (a_format / b_format), so
 // the first digit of each operand is multiplied as INT8 and the others as UINT8.
-#include <cuda.h>
-
 #include "dkg_kernels.cuh"
 
 namespace dkg {
@@ -46,21 +44,24 @@ constexpr int OZ_BLK_BYTES = OZ_BM * OZ_KB;  // one digit block (A or B) of a st
 constexpr int OZ_MAX_DIGITS = 7;
 constexpr int OZ_STAGES = 2;          // x (2 * digits * 4 KB) = 112 KB at 7 digits
 constexpr int OZ_ACC = 4;             // TMEM accumulators (diagonals) per pass: 4 x 128 = all 512 columns
+constexpr int OZ_MAX_ENT = OZ_ACC * OZ_MAX_DIGITS;  // MMAs per k block of one pass
 constexpr int OZ_THREADS = 640;       // warp 0 TMA, warp 1 MMA, (2, 3 idle), warps 4..19 epilogue
 constexpr int OZ_EPI_WARPS = 16;
 constexpr int OZ_EPI_LD = 17;
 constexpr int OZ_EPI_STAGE = 32 * OZ_EPI_LD;  // doubles per warp (32 rows x 16 columns, padded)
 constexpr int OZ_ROWDATA = 32 * (MAX_D + 1);  // doubles per warp
 constexpr size_t OZ_SMEM = 1024 + (size_t)OZ_STAGES * 2 * OZ_MAX_DIGITS * OZ_BLK_BYTES +
-                           (size_t)OZ_EPI_WARPS * (OZ_EPI_STAGE + OZ_ROWDATA) * sizeof(double) + 256;
+                           (size_t)OZ_EPI_WARPS * (OZ_EPI_STAGE + OZ_ROWDATA) * sizeof(double) + 128 +
+                           (size_t)4 * OZ_MAX_ENT * 16;  // barriers + MMA programs of up to 4 passes (13 diagonals)
 constexpr int OZ_TMEM_COLS = 512;
+
 static_assert(OZ_SMEM <= 227 * 1024, "shared memory budget");
 
 struct OzakiArgs {
   int NS, NG;
   int KP;             // digits per row (bytes), multiple of 32
-  int a_slice_rows;   // rows between consecutive digit planes of A
-  int b_slice_rows;
+  const unsigned char* a_digits;  // [row block][k block][digit][4 KB block image]
+  const unsigned char* b_digits;
   int m_tiles, n_tiles;
   const double* sa;   // [rows] power-of-two row scale of A
   const double* sb;   // [cols] power-of-two row scale of B
@@ -92,11 +93,10 @@ __device__ __forceinline__ void bar_wait(unsigned long long* bar, unsigned parit
       "D_%=:\n"
       "}\n" ::"r"(s_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(s_u32(dst)),
-      "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(s_u32(dst)),
+               "l"(src), "r"(bytes), "r"(s_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -114,15 +114,16 @@ __device__ __forceinline__ void umma_i8(unsigned d_tmem, unsigned long long ades
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major operand tile, rows of 32 bytes, SWIZZLE_32B: 8-row groups are 256 B apart (SBO);
-// LBO is unused for a swizzled K-major tile; descriptor version 1 (sm_100); layout type 6.
+// K-major operand block of 128 rows x 32 bytes in the canonical NO-SWIZZLE layout: 8 x 16-byte core
+// matrices (128 contiguous bytes), ordered [row group][k chunk]: K-adjacent core matrices are
+// 128 B apart (LBO), row-group-adjacent ones 256 B (SBO).  The digit planes are stored in global
+// memory in exactly this image, so a block arrives with one linear bulk copy.
 __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
   unsigned long long d = 0;
   d |= (unsigned long long)((smem_addr & 0x3FFFF) >> 4);
-  d |= (unsigned long long)1 << 16;
+  d |= (unsigned long long)(128 >> 4) << 16;
   d |= (unsigned long long)(256 >> 4) << 32;
   d |= (unsigned long long)1 << 46;
-  d |= (unsigned long long)6 << 61;
   return d;
 }
 // c_format S32 (2) | a_format | b_format (1 = signed, 0 = unsigned) | K-major both | N >> 3 | M >> 4
@@ -148,11 +149,57 @@ __device__ __forceinline__ double i32_to_f64(int v) {
   return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0;
 }
 
+// Final epilogue of one warp's 32 x 32 block: apply the row / column scales, evaluate the kernel
+// term and write Z.  The products go through a shared-memory transpose 16 columns at a time so
+// that lanes map to (row parity, column): two 128-byte row segments per store instruction.
+template <int D>
+__device__ __forceinline__ void cov_tail(const double (&acc)[32], double sa_r, const OzakiArgs& args, double* my_stage,
+                                         double* my_rows, int row0, int col0, int lane) {
+  const CovEpilogue& ep = args.ep;
+  const int hr = lane >> 4, hc = lane & 15;
+  for (int e = lane; e < 32 * D; e += 32) {
+    const int r = e / D, k = e - r * D;
+    my_rows[r * (MAX_D + 1) + k] = (row0 + r < ep.C) ? ep.xs[(size_t)(row0 + r) * D + k] : 0.0;
+  }
+  my_rows[lane * (MAX_D + 1) + MAX_D] = (row0 + lane < ep.C) ? ep.ystd2 / ep.sd[row0 + lane] : 0.0;
+  const int kind = ep.kind;
+  const double os = ep.outputscale;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) my_stage[lane * OZ_EPI_LD + c] = acc[h * 16 + c] * sa_r;
+    __syncwarp();
+    const int col = col0 + h * 16 + hc;
+    const double sb_c = args.sb[col];
+    double xc[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) xc[k] = ep.xd_s[(size_t)col * D + k];
+    double* zrow = ep.Z + (size_t)(row0 + hr) * ep.ldz + col;
+    const bool col_ok = col < ep.N;
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int r = 2 * it + hr;
+      double sq = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const double df = my_rows[r * (MAX_D + 1) + k] - xc[k];
+        sq = fma(df, df, sq);
+      }
+      const double v = my_stage[r * OZ_EPI_LD + hc] * sb_c;
+      const double z = (stationary_from_sq(kind, os, sq) - v) * my_rows[r * (MAX_D + 1) + MAX_D];
+      if (col_ok && row0 + r < ep.C) zrow[(size_t)(2 * it) * ep.ldz] = z;
+    }
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(OZ_THREADS, 1)
-ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-             const OzakiArgs args) {
+ozaki_kernel(const OzakiArgs args) {
   extern __shared__ unsigned char oz_smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)oz_smem_raw + 1023) & ~(uintptr_t)1023);
+  // (offset arithmetic on the __shared__ array itself, so that the compiler keeps the shared address
+  // space and emits LDS / STS instead of generic loads)
+  unsigned char* smem = oz_smem_raw + ((1024u - (s_u32(oz_smem_raw) & 1023u)) & 1023u);
   const int NS = args.NS, NG = args.NG;
   const int stage_bytes = 2 * NS * OZ_BLK_BYTES;
   unsigned char* s_stage = smem;
@@ -164,6 +211,8 @@ ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   unsigned long long* tfull = bars + 2 * OZ_STAGES;
   unsigned long long* tempty = tfull + 1;
   unsigned* s_tmem = reinterpret_cast<unsigned*>(tempty + 1);
+  int* s_nent = reinterpret_cast<int*>(s_tmem + 2);            // [4]
+  uint4* s_prog = reinterpret_cast<uint4*>(bars + 16);         // [4][OZ_MAX_ENT]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = args.KP / OZ_KB;
@@ -178,6 +227,26 @@ ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     bar_init(tfull, 1);
     bar_init(tempty, OZ_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 2) {
+    // the MMA "program" of every pass: per MMA the two descriptor offsets, the instruction
+    // descriptor and the accumulator column, so that the issuing thread only adds and fires
+    for (int p = 0; p < n_pass; ++p) {
+      const int g_hi = NG - 1 - p * OZ_ACC;
+      const int g_lo = g_hi - OZ_ACC + 1 > 0 ? g_hi - OZ_ACC + 1 : 0;
+      int ne = 0;
+      for (int g = g_hi; g >= g_lo; --g) {
+        const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
+        for (int i = ilo; i <= ihi; ++i, ++ne) {
+          const int j = g - i;
+          if (lane == 0)
+            s_prog[p * OZ_MAX_ENT + ne] = make_uint4((unsigned)(i * OZ_BLK_BYTES) >> 4, (unsigned)((NS + j) * OZ_BLK_BYTES) >> 4,
+                                                     umma_idesc(i == 0, j == 0),
+                                                     (unsigned)((g_hi - g) * OZ_BN) | (i > ilo ? 0x80000000u : 0u));
+        }
+      }
+      if (lane == 0) s_nent[p] = ne;
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_u32(s_tmem)), "n"(OZ_TMEM_COLS));
@@ -200,18 +269,16 @@ ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const int m_blk = tile % args.m_tiles, n_blk = tile / args.m_tiles;
         for (int p = 0; p < n_pass; ++p) {
           const int g_hi = NG - 1 - p * OZ_ACC;
-          const int g_lo = g_hi - OZ_ACC + 1 > 0 ? g_hi - OZ_ACC + 1 : 0;
-          const int dlo = g_lo - NS + 1 > 0 ? g_lo - NS + 1 : 0, dhi = g_hi < NS - 1 ? g_hi : NS - 1;
-          const unsigned bytes = (unsigned)(2 * (dhi - dlo + 1) * OZ_BLK_BYTES);
+          const int dhi = g_hi < NS - 1 ? g_hi : NS - 1;
+          const unsigned bytes = (unsigned)(2 * (dhi + 1) * OZ_BLK_BYTES);
           for (int kb = 0; kb < KB; ++kb) {
             bar_wait(&empty[s], ph ^ 1);
             bar_expect_tx(&full[s], bytes);
             unsigned char* st = s_stage + (size_t)s * stage_bytes;
-            for (int dg = dlo; dg <= dhi; ++dg) {
-              tma_load_2d(st + dg * OZ_BLK_BYTES, &mapA, &full[s], kb * OZ_KB, dg * args.a_slice_rows + m_blk * OZ_BM);
-              tma_load_2d(st + (NS + dg) * OZ_BLK_BYTES, &mapB, &full[s], kb * OZ_KB,
-                          dg * args.b_slice_rows + n_blk * OZ_BN);
-            }
+            // digits 0 .. dhi of this (row block, k block) are one contiguous run in global memory
+            bulk_g2s(st, args.a_digits + ((size_t)(m_blk * KB + kb) * NS) * OZ_BLK_BYTES, bytes / 2, &full[s]);
+            bulk_g2s(st + NS * OZ_BLK_BYTES, args.b_digits + ((size_t)(n_blk * KB + kb) * NS) * OZ_BLK_BYTES,
+                     bytes / 2, &full[s]);
             if (++s == OZ_STAGES) { s = 0; ph ^= 1; }
           }
         }
@@ -223,22 +290,19 @@ ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       unsigned pcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
         for (int p = 0; p < n_pass; ++p, ++pcount) {
-          const int g_hi = NG - 1 - p * OZ_ACC;
-          const int g_lo = g_hi - OZ_ACC + 1 > 0 ? g_hi - OZ_ACC + 1 : 0;
           bar_wait(tempty, (pcount & 1) ^ 1);
           tc_fence_after();
+          const uint4* prog = s_prog + p * OZ_MAX_ENT;
+          const int ne = s_nent[p];
           for (int kb = 0; kb < KB; ++kb) {
             bar_wait(&full[s], ph);
             tc_fence_after();
-            const unsigned st_addr = s_u32(s_stage + (size_t)s * stage_bytes);
-            for (int g = g_hi; g >= g_lo; --g) {
-              const unsigned d_tmem = tmem_base + (unsigned)(g_hi - g) * OZ_BN;
-              const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
-              for (int i = ilo; i <= ihi; ++i) {
-                const int j = g - i;
-                umma_i8(d_tmem, umma_desc(st_addr + i * OZ_BLK_BYTES), umma_desc(st_addr + (NS + j) * OZ_BLK_BYTES),
-                        umma_idesc(i == 0, j == 0), (kb > 0 || i > ilo) ? 1u : 0u);
-              }
+            const unsigned long long base = umma_desc(s_u32(s_stage + (size_t)s * stage_bytes));
+            const unsigned kacc = kb > 0 ? 1u : 0u;
+#pragma unroll 4
+            for (int e = 0; e < ne; ++e) {
+              const uint4 en = prog[e];
+              umma_i8(tmem_base + (en.w & 0xFFFFu), base + en.x, base + en.y, en.z, kacc | (en.w >> 31));
             }
             umma_commit(&empty[s]);
             if (++s == OZ_STAGES) { s = 0; ph ^= 1; }
@@ -287,42 +351,16 @@ ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       const double sa_r = args.sa[row0 + lane];
       const int hr = lane >> 4, hc = lane & 15;
       if (args.cov) {
-        const CovEpilogue& ep = args.ep;
-        const int d = ep.d;
-        for (int e = lane; e < 32 * MAX_D; e += 32) {
-          const int r = e / MAX_D, k = e - r * MAX_D;
-          my_rows[r * (MAX_D + 1) + k] = (k < d && row0 + r < ep.C) ? ep.xs[(size_t)(row0 + r) * d + k] : 0.0;
+        switch (args.ep.d) {
+          case 1: cov_tail<1>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
+          case 2: cov_tail<2>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
+          case 3: cov_tail<3>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
+          case 4: cov_tail<4>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
+          case 5: cov_tail<5>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
+          case 6: cov_tail<6>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
+          case 7: cov_tail<7>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
+          default: cov_tail<8>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
         }
-        my_rows[lane * (MAX_D + 1) + MAX_D] = (row0 + lane < ep.C) ? ep.ystd2 / ep.sd[row0 + lane] : 0.0;
-        const int kind = ep.kind;
-        const double os = ep.outputscale;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < 16; ++c) my_stage[lane * OZ_EPI_LD + c] = acc[h * 16 + c] * sa_r;
-          __syncwarp();
-          const int col = col0 + h * 16 + hc;
-          const double sb_c = args.sb[col];
-          double xc[MAX_D];
-#pragma unroll
-          for (int k = 0; k < MAX_D; ++k) xc[k] = (k < d) ? ep.xd_s[(size_t)col * d + k] : 0.0;
-#pragma unroll 4
-          for (int it = 0; it < 16; ++it) {
-            const int r = 2 * it + hr;
-            double sq = 0.0;
-#pragma unroll
-            for (int k = 0; k < MAX_D; ++k)
-              if (k < d) {
-                const double df = my_rows[r * (MAX_D + 1) + k] - xc[k];
-                sq += df * df;
-              }
-            const double v = my_stage[r * OZ_EPI_LD + hc] * sb_c;
-            const double z = (stationary_from_sq(kind, os, sq) - v) * my_rows[r * (MAX_D + 1) + MAX_D];
-            if (row0 + r < ep.C && col < ep.N) ep.Z[(size_t)(row0 + r) * ep.ldz + col] = z;
-          }
-        }
-        __syncwarp();
       } else {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -351,7 +389,7 @@ ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 }
 
 // One warp per row: power-of-two scale into (-128, 128), then NS exact base-256 digits.
-__global__ void slice_rows_kernel(const double* __restrict__ X, int ld, int rows, int K, int KP, int slice_rows, int NS,
+__global__ void slice_rows_kernel(const double* __restrict__ X, int ld, int rows, int K, int KP, int NS,
                                   unsigned char* __restrict__ out, double* __restrict__ scale) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -371,46 +409,13 @@ __global__ void slice_rows_kernel(const double* __restrict__ X, int ld, int rows
     double v = (k < K) ? scalbn(rint(scalbn(x[k], 8 * (NS - 1) - e7)), -8 * (NS - 1)) : 0.0;
     for (int s = 0; s < NS; ++s) {
       const double dg = floor(v);
-      out[((size_t)s * slice_rows + r) * KP + k] = (unsigned char)(int)dg;  // two's complement byte for s = 0
+      // block image: [row block][k block][digit][row group (16)][k chunk (2)][row in group (8)][16 B]
+      const size_t blk = ((size_t)(r >> 7) * (KP >> 5) + (k >> 5)) * NS + s;
+      const int in_blk = ((((r & 127) >> 3) * 2 + ((k & 31) >> 4)) * 8 + (r & 7)) * 16 + (k & 15);
+      out[blk * OZ_BLK_BYTES + in_blk] = (unsigned char)(int)dg;  // two's complement byte for s = 0
       v = (v - dg) * 256.0;
     }
   }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-int make_digit_map(CUtensorMap* map, const unsigned char* base, int KP, long long total_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (fn == nullptr) {
-    set_error("cuTensorMapEncodeTiled is not available from this driver");
-    return DKG_ECUDA;
-  }
-  cuuint64_t dims[2] = {(cuuint64_t)KP, (cuuint64_t)total_rows};
-  cuuint64_t strides[1] = {(cuuint64_t)KP};
-  cuuint32_t box[2] = {(cuuint32_t)OZ_KB, (cuuint32_t)OZ_BM};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<unsigned char*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (rc != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with code %d (KP=%d rows=%lld)", (int)rc, KP, total_rows);
-    return DKG_ECUDA;
-  }
-  return DKG_OK;
 }
 
 int ensure_ozaki_attr(int* n_sm) {
@@ -434,13 +439,13 @@ int ozaki_kp(int K) { return round_up(K, 32); }
 
 size_t ozaki_digit_bytes(int rows_pad, int K, int NS) { return (size_t)NS * rows_pad * ozaki_kp(K); }
 
-// digits[NS][slice_rows][KP] and scale[rows] of the row-major matrix X[rows, K] (leading dim ld)
+// block-image digit planes (see slice_rows_kernel) and scale[rows] of the row-major matrix X[rows, K]
 int ozaki_slice_rows(const double* X, int ld, int rows, int K, int slice_rows, int NS, unsigned char* digits,
                      double* scale, cudaStream_t st) {
   if (rows == 0) return DKG_OK;
   const int threads = 256;
-  slice_rows_kernel<<<ceil_div(rows * 32, threads), threads, 0, st>>>(X, ld, rows, K, ozaki_kp(K), slice_rows, NS,
-                                                                       digits, scale);
+  (void)slice_rows;
+  slice_rows_kernel<<<ceil_div(rows * 32, threads), threads, 0, st>>>(X, ld, rows, K, ozaki_kp(K), NS, digits, scale);
   DKG_LAUNCH_CHECK();
   return DKG_OK;
 }
@@ -450,21 +455,18 @@ static int ozaki_launch(const unsigned char* a_digits, const double* sa, int M_p
   int n_sm = 0;
   DKG_TRY(ensure_ozaki_attr(&n_sm));
   const int KP = ozaki_kp(K);
-  alignas(64) CUtensorMap mapA, mapB;
-  DKG_TRY(make_digit_map(&mapA, a_digits, KP, (long long)NS * M_pad));
-  DKG_TRY(make_digit_map(&mapB, b_digits, KP, (long long)NS * N_pad));
   args.NS = NS;
   args.NG = NG;
   args.KP = KP;
-  args.a_slice_rows = M_pad;
-  args.b_slice_rows = N_pad;
+  args.a_digits = a_digits;
+  args.b_digits = b_digits;
   args.m_tiles = M_pad / OZ_BM;
   args.n_tiles = N_pad / OZ_BN;
   args.sa = sa;
   args.sb = sb;
   const int tiles = args.m_tiles * args.n_tiles;
   const int grid = tiles < n_sm ? tiles : n_sm;
-  ozaki_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(mapA, mapB, args);
+  ozaki_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(args);
   DKG_LAUNCH_CHECK();
   return DKG_OK;
 }

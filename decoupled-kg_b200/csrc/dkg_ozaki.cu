@@ -149,6 +149,26 @@ __device__ __forceinline__ double i32_to_f64(int v) {
   return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0;
 }
 
+// all MMAs of one k block of pass P, unrolled at compile time
+template <int NS, int NG, int P>
+__device__ __forceinline__ void issue_pass(unsigned tmem_base, unsigned long long base, unsigned kacc) {
+  constexpr int g_hi = NG - 1 - P * OZ_ACC;
+  constexpr int g_lo = g_hi - OZ_ACC + 1 > 0 ? g_hi - OZ_ACC + 1 : 0;
+#pragma unroll
+  for (int g = g_hi; g >= g_lo; --g) {
+    const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      if (i >= ilo && i <= ihi) {
+        const int j = g - i;
+        umma_i8(tmem_base + (unsigned)((g_hi - g) * OZ_BN), base + (unsigned long long)((i * OZ_BLK_BYTES) >> 4),
+                base + (unsigned long long)(((NS + j) * OZ_BLK_BYTES) >> 4), umma_idesc(i == 0, j == 0),
+                i > ilo ? 1u : kacc);
+      }
+    }
+  }
+}
+
 // Final epilogue of one warp's 32 x 32 block: apply the row / column scales, evaluate the kernel
 // term and write Z.  The products go through a shared-memory transpose 16 columns at a time so
 // that lanes map to (row parity, column): two 128-byte row segments per store instruction.
@@ -294,15 +314,24 @@ ozaki_kernel(const OzakiArgs args) {
           tc_fence_after();
           const uint4* prog = s_prog + p * OZ_MAX_ENT;
           const int ne = s_nent[p];
+          const bool std_cfg = NS == OZ_DEFAULT_DIGITS && NG == OZ_DEFAULT_DIAGONALS;
           for (int kb = 0; kb < KB; ++kb) {
             bar_wait(&full[s], ph);
             tc_fence_after();
             const unsigned long long base = umma_desc(s_u32(s_stage + (size_t)s * stage_bytes));
             const unsigned kacc = kb > 0 ? 1u : 0u;
+            if (std_cfg) {
+              // default digit configuration: the MMA list is unrolled at compile time (offsets and
+              // instruction descriptors become immediates; ~5 SASS instructions per MMA instead
+              // of ~23 through the table, which left the tensor pipe waiting on the issuing thread)
+              if (p == 0) issue_pass<OZ_DEFAULT_DIGITS, OZ_DEFAULT_DIAGONALS, 0>(tmem_base, base, kacc);
+              else issue_pass<OZ_DEFAULT_DIGITS, OZ_DEFAULT_DIAGONALS, 1>(tmem_base, base, kacc);
+            } else {
 #pragma unroll 4
-            for (int e = 0; e < ne; ++e) {
-              const uint4 en = prog[e];
-              umma_i8(tmem_base + (en.w & 0xFFFFu), base + en.x, base + en.y, en.z, kacc | (en.w >> 31));
+              for (int e = 0; e < ne; ++e) {
+                const uint4 en = prog[e];
+                umma_i8(tmem_base + (en.w & 0xFFFFu), base + en.x, base + en.y, en.z, kacc | (en.w >> 31));
+              }
             }
             umma_commit(&empty[s]);
             if (++s == OZ_STAGES) { s = 0; ph ^= 1; }

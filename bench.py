@@ -383,19 +383,55 @@ def main():
         # objective) (F = 2 n (N+1) + 2 n^2 + 2 n M; the contraction is the 2 n N term)
         flops_total = 3.0 * sum(2.0 * m.n * N * n_cand for m in P.model.models)
         achieved = flops_total / (ms_g * 1e-3) / 1e12
-        peak = measure_dgemm_peak(dev)
+        dgemm_peak = measure_dgemm_peak(dev)
         tot_prof = sum(v[0] for v in prof.values())
-        roofline = {
-            "kernel": "dmma_gemm_kernel<cov> (GP conditioning contraction, fp64 DMMA)",
-            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak,
-            "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (burst, best of 5); "
-                           "MEASURED_PEAKS.json has no fp64 figure",
-            "flops_per_launch": flops_total / max(n_g, 1),
-            "avg_launch_ms": ms_g / max(n_g, 1),
-            "share_of_step": ms_g / tot_prof if tot_prof > 0 else None,
-            "traffic": None,
-        }
+        int8_engine = all(p.stats()[7] == 1 for p in plans)
+        if int8_engine:
+            # The contraction runs on the int8 tensor cores as 34 exact digit-plane products
+            # (7 base-256 digits, 8 diagonals; csrc/dkg_ozaki.cu) of K padded to 32.  Its roofline is
+            # the int8 tensor peak; B200's dense i8 rate is twice its bf16 rate, and the bf16 rate
+            # is the measured cuBLAS figure of MEASURED_PEAKS.json (burst: this kernel is timed alone).
+            bf16 = None
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    bf16 = float(json.load(f)["bf16_tflops"])
+                src = "2 x MEASURED_PEAKS.json bf16_tflops (burst)"
+            except Exception:
+                bf16, src = 2250.0, "2 x 2250 TFLOP/s nominal dense bf16 (B200_PROFILING.md fallback)"
+            products = 34.0
+            kp = sum(-(-m.n // 32) * 32 for m in P.model.models) / sum(m.n for m in P.model.models)
+            int8_ops = flops_total * products * kp
+            int8_peak = 2.0 * bf16
+            peak = int8_peak / (products * kp)  # the int8 roofline in fp64-equivalent TFLOP/s
+            roofline = {
+                "kernel": "ozaki_kernel (tcgen05.mma.kind::i8 over base-256 digit planes: the fp64 GP "
+                          "conditioning contraction as 34 exact int8 products)",
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak,
+                "peak_source": f"int8 tensor peak = {src} = {int8_peak:.0f} TOP/s, divided by the "
+                               f"{products * kp:.1f} int8 ops the scheme spends per algorithmic fp64 flop",
+                "int8_top_s_executed": int8_ops / (ms_g * 1e-3) / 1e12,
+                "int8_peak_top_s": int8_peak,
+                "dgemm_peak_tflops": dgemm_peak,
+                "frac_vs_dgemm_peak": achieved / dgemm_peak,
+                "flops_per_launch": flops_total / max(n_g, 1),
+                "avg_launch_ms": ms_g / max(n_g, 1),
+                "share_of_step": ms_g / tot_prof if tot_prof > 0 else None,
+                "traffic": None,
+            }
+        else:
+            roofline = {
+                "kernel": "dmma_gemm_kernel<cov> (GP conditioning contraction, fp64 DMMA)",
+                "bound": "tensor", "achieved": achieved, "peak": dgemm_peak, "unit": "TFLOP/s",
+                "frac": achieved / dgemm_peak,
+                "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (burst, best of 5); "
+                               "MEASURED_PEAKS.json has no fp64 figure",
+                "flops_per_launch": flops_total / max(n_g, 1),
+                "avg_launch_ms": ms_g / max(n_g, 1),
+                "share_of_step": ms_g / tot_prof if tot_prof > 0 else None,
+                "traffic": None,
+            }
+        peak = dgemm_peak
         extra["kernel_ms_per_step"] = {k: v[0] / 3.0 for k, v in prof.items()}
         extra["kernel_launches_per_step"] = {k: v[1] // 3 for k, v in prof.items()}
         whole = 1.03 * sum((2.0 * m.n * (N + 1) + 2.0 * m.n**2 + 2.0 * m.n * M) * n_cand for m in P.model.models)

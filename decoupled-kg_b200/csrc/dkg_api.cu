@@ -442,16 +442,19 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     ep.Z = w.Z;
     ep.ldz = p->ldz; ep.C = cc; ep.N = N; ep.d = d; ep.kind = ot.kernel;
     ep.outputscale = ot.outputscale; ep.ystd2 = ystd2;
-    { ProfScope ps(3, st);
+    {
       // cov[c, n] = k(x_c, x_n) - T[c, :] . k(X_train, x_n)   with T = K^-1 k(X_train, x_c)
       if (ot.Kxd_dig != nullptr) {
         // int8 tensor cores in product mode: Z <- T . Kxd; the row-statistics pass below turns
         // the products into slopes while it reads them (CovFinish)
-        DKG_TRY(ozaki_slice_rows(w.T + (size_t)c0 * p->ldk, p->ldk, cc, ot.n, cc_pad, OZ_DEFAULT_DIGITS, w.T_dig,
-                                 w.T_scale, st));
+        { ProfScope pd(10, st);
+          DKG_TRY(ozaki_slice_rows(w.T + (size_t)c0 * p->ldk, p->ldk, cc, ot.n, cc_pad, OZ_DEFAULT_DIGITS, w.T_dig,
+                                   w.T_scale, st)); }
+        ProfScope ps(3, st);
         DKG_TRY(ozaki_store(w.T_dig, w.T_scale, cc_pad, ot.Kxd_dig, ot.Kxd_scale, p->N_pad, ot.n, OZ_DEFAULT_DIGITS,
                             OZ_DEFAULT_DIAGONALS, w.Z, p->ldz, cc, N, st));
       } else {
+        ProfScope ps(3, st);
         DKG_TRY(cov_rows(ot, p, w, w.T + (size_t)c0 * p->ldk, cc, cc_pad, ep, st));
       } }
     { ProfScope ps(4, st); DKG_TRY(launch_place_own(w.zown + c0, cc, w.Z, p->ldz, N, st)); }
@@ -871,6 +874,10 @@ int dkg_plan_stats(dkg_plan* plan, int64_t* out5_host /* [8] */, void* stream) {
   }
   out5_host[0] = plan->ws.last_C;
   for (int k = 1; k < 8; ++k) out5_host[k] = h[k];
+  // [7]: 1 when the covariance contraction of this plan runs on the int8 tensor cores
+  bool int8 = false;
+  for (int m = 0; m < plan->M; ++m) int8 = int8 || plan->obj[m].Kxd_dig != nullptr;
+  out5_host[7] = int8 ? 1 : 0;
   return DKG_OK;
 }
 

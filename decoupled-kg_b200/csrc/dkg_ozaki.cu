@@ -31,6 +31,8 @@
 //               coalesced rows through a per-warp shared-memory transpose.
 // Signed / unsigned digits only differ in the instruction descriptor (a_format / b_format), so
 // the first digit of each operand is multiplied as INT8 and the others as UINT8.
+#include <cstdlib>
+
 #include "dkg_kernels.cuh"
 
 namespace dkg {
@@ -42,20 +44,22 @@ constexpr int OZ_BN = 128;
 constexpr int OZ_KB = 32;             // bytes of K per stage = one MMA (K32), SWIZZLE_32B rows
 constexpr int OZ_BLK_BYTES = OZ_BM * OZ_KB;  // one digit block (A or B) of a stage: 4 KB
 constexpr int OZ_MAX_DIGITS = 7;
-constexpr int OZ_STAGES = 2;          // x (2 * digits * 4 KB) = 112 KB at 7 digits
-constexpr int OZ_ACC = 4;             // TMEM accumulators (diagonals) per pass: 4 x 128 = all 512 columns
+constexpr int OZ_STAGES = 2;
+constexpr int OZ_STAGE_CAP = 65536;   // bytes per stage: 1 k block of 7+7 digit blocks, or 2 of 4+4
+constexpr int OZ_MAX_KPS = 2;         // k blocks per stage
+constexpr int OZ_ACC = 4;             // TMEM accumulator slots (diagonals) per pass: 4 x 128 = all 512 columns
 constexpr int OZ_MAX_ENT = OZ_ACC * OZ_MAX_DIGITS;  // MMAs per k block of one pass
-constexpr int OZ_THREADS = 640;       // warp 0 TMA, warp 1 MMA, (2, 3 idle), warps 4..19 epilogue
+constexpr int OZ_THREADS = 640;       // warp 0 bulk copies, warp 1 MMA, (2, 3 idle), warps 4..19 epilogue
 constexpr int OZ_EPI_WARPS = 16;
-constexpr int OZ_EPI_LD = 17;
-constexpr int OZ_EPI_STAGE = 32 * OZ_EPI_LD;  // doubles per warp (32 rows x 16 columns, padded)
-constexpr int OZ_ROWDATA = 32 * (MAX_D + 1);  // doubles per warp
-constexpr size_t OZ_SMEM = 1024 + (size_t)OZ_STAGES * 2 * OZ_MAX_DIGITS * OZ_BLK_BYTES +
-                           (size_t)OZ_EPI_WARPS * (OZ_EPI_STAGE + OZ_ROWDATA) * sizeof(double) + 128 +
-                           (size_t)4 * OZ_MAX_ENT * 16;  // barriers + MMA programs of up to 4 passes (13 diagonals)
+constexpr int OZ_EPI_LD = 9;
+constexpr int OZ_EPI_STAGE = 32 * OZ_EPI_LD;  // doubles per warp (32 rows x 8 columns, padded)
+constexpr int OZ_ROWDATA = 32 * (MAX_D + 1);  // doubles per warp (covariance mode)
+constexpr size_t OZ_SMEM = 1024 + (size_t)OZ_STAGES * OZ_STAGE_CAP +
+                           (size_t)OZ_EPI_WARPS * (OZ_EPI_STAGE + OZ_ROWDATA) * sizeof(double) + 256 +
+                           (size_t)4 * OZ_MAX_ENT * 16;  // barriers, slot table, MMA programs of up to 4 passes
 constexpr int OZ_TMEM_COLS = 512;
-
 static_assert(OZ_SMEM <= 227 * 1024, "shared memory budget");
+static_assert(2 * OZ_MAX_DIGITS * OZ_BLK_BYTES <= OZ_STAGE_CAP, "a stage must hold one k block of all digits");
 
 struct OzakiArgs {
   int NS, NG;
@@ -70,6 +74,8 @@ struct OzakiArgs {
   double* D;          // store mode
   int ldd;
   int M, N;           // valid rows / cols (store mode)
+  int max_kps;        // k blocks per stage (tuning knob)
+  int slot_wait;      // wait per accumulator slot (1) or for all slots before the first MMA (0)
 };
 
 __device__ __forceinline__ unsigned s_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -97,6 +103,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(s_u32(dst)),
                "l"(src), "r"(bytes), "r"(s_u32(bar))
                : "memory");
+}
+// one lane of a converged warp (ptxas knows the predicate of elect.sync selects a single lane and
+// issues the tcgen05 instructions under it without a per-lane serialisation loop)
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -149,34 +168,66 @@ __device__ __forceinline__ double i32_to_f64(int v) {
   return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0;
 }
 
-// all MMAs of one k block of pass P, unrolled at compile time
-template <int NS, int NG, int P>
-__device__ __forceinline__ void issue_pass(unsigned tmem_base, unsigned long long base, unsigned kacc) {
+// All MMAs of one k block of pass P, unrolled at compile time.  Accumulator slot a holds the
+// diagonal g_hi - a.  On the first k block of a pass the issuing thread waits per slot until the
+// epilogue has drained it (so the drain of the previous pass overlaps the first MMAs), on the last
+// one it publishes each slot as soon as its MMAs are queued.
+template <int NS, int NG, int P, bool FIRST, bool LAST>
+__device__ __forceinline__ void issue_pass_k(unsigned tmem_base, unsigned long long base, unsigned long long* tfull,
+                                             unsigned long long* tempty, unsigned par, bool slot_wait) {
   constexpr int g_hi = NG - 1 - P * OZ_ACC;
   constexpr int g_lo = g_hi - OZ_ACC + 1 > 0 ? g_hi - OZ_ACC + 1 : 0;
+  constexpr int nd = (g_hi < NS - 1 ? g_hi : NS - 1) + 1;  // digits 0 .. nd-1 of both operands are staged
+  if (FIRST && !slot_wait) {
+    for (int a = 0; a < OZ_ACC; ++a) bar_wait(&tempty[a], par ^ 1);
+    tc_fence_after();
+  }
 #pragma unroll
-  for (int g = g_hi; g >= g_lo; --g) {
-    const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
+  for (int a = 0; a < OZ_ACC; ++a) {
+    const int g = g_hi - a;
+    if (FIRST && slot_wait) {
+      bar_wait(&tempty[a], par ^ 1);
+      tc_fence_after();
+    }
+    if (g >= g_lo) {
+      const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
 #pragma unroll
-    for (int i = 0; i < NS; ++i) {
-      if (i >= ilo && i <= ihi) {
-        const int j = g - i;
-        umma_i8(tmem_base + (unsigned)((g_hi - g) * OZ_BN), base + (unsigned long long)((i * OZ_BLK_BYTES) >> 4),
-                base + (unsigned long long)(((NS + j) * OZ_BLK_BYTES) >> 4), umma_idesc(i == 0, j == 0),
-                i > ilo ? 1u : kacc);
+      for (int i = 0; i < NS; ++i) {
+        if (i >= ilo && i <= ihi) {
+          const int j = g - i;
+          umma_i8(tmem_base + (unsigned)(a * OZ_BN), base + (unsigned long long)((i * OZ_BLK_BYTES) >> 4),
+                  base + (unsigned long long)(((nd + j) * OZ_BLK_BYTES) >> 4), umma_idesc(i == 0, j == 0),
+                  (i > ilo || !FIRST) ? 1u : 0u);
+        }
       }
     }
+    if (LAST) umma_commit(&tfull[a]);
   }
 }
 
-// Final epilogue of one warp's 32 x 32 block: apply the row / column scales, evaluate the kernel
-// term and write Z.  The products go through a shared-memory transpose 16 columns at a time so
-// that lanes map to (row parity, column): two 128-byte row segments per store instruction.
+// (the k block position is a template parameter so that the steady-state instantiation is a
+// straight run of MMAs whose descriptors stay in uniform registers)
+template <int NS, int NG, int P>
+__device__ __forceinline__ void issue_pass(unsigned tmem_base, unsigned long long base, bool first_k, bool last_k,
+                                           unsigned long long* tfull, unsigned long long* tempty, unsigned par,
+                                           bool slot_wait) {
+  if (first_k) {
+    if (last_k) issue_pass_k<NS, NG, P, true, true>(tmem_base, base, tfull, tempty, par, slot_wait);
+    else issue_pass_k<NS, NG, P, true, false>(tmem_base, base, tfull, tempty, par, slot_wait);
+  } else {
+    if (last_k) issue_pass_k<NS, NG, P, false, true>(tmem_base, base, tfull, tempty, par, slot_wait);
+    else issue_pass_k<NS, NG, P, false, false>(tmem_base, base, tfull, tempty, par, slot_wait);
+  }
+}
+
+// Final epilogue of one warp's 32 x 32 block in covariance mode: apply the row / column scales,
+// evaluate the kernel term and write Z.  The products go through a shared-memory transpose 8
+// columns at a time so that lanes map to (row mod 4, column): four 64-byte row segments per store.
 template <int D>
 __device__ __forceinline__ void cov_tail(const double (&acc)[32], double sa_r, const OzakiArgs& args, double* my_stage,
                                          double* my_rows, int row0, int col0, int lane) {
   const CovEpilogue& ep = args.ep;
-  const int hr = lane >> 4, hc = lane & 15;
+  const int hr = lane >> 3, hc = lane & 7;
   for (int e = lane; e < 32 * D; e += 32) {
     const int r = e / D, k = e - r * D;
     my_rows[r * (MAX_D + 1) + k] = (row0 + r < ep.C) ? ep.xs[(size_t)(row0 + r) * D + k] : 0.0;
@@ -185,12 +236,12 @@ __device__ __forceinline__ void cov_tail(const double (&acc)[32], double sa_r, c
   const int kind = ep.kind;
   const double os = ep.outputscale;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
+  for (int h = 0; h < 4; ++h) {
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 16; ++c) my_stage[lane * OZ_EPI_LD + c] = acc[h * 16 + c] * sa_r;
+    for (int c = 0; c < 8; ++c) my_stage[lane * OZ_EPI_LD + c] = acc[h * 8 + c] * sa_r;
     __syncwarp();
-    const int col = col0 + h * 16 + hc;
+    const int col = col0 + h * 8 + hc;
     const double sb_c = args.sb[col];
     double xc[D];
 #pragma unroll
@@ -198,8 +249,8 @@ __device__ __forceinline__ void cov_tail(const double (&acc)[32], double sa_r, c
     double* zrow = ep.Z + (size_t)(row0 + hr) * ep.ldz + col;
     const bool col_ok = col < ep.N;
 #pragma unroll 4
-    for (int it = 0; it < 16; ++it) {
-      const int r = 2 * it + hr;
+    for (int it = 0; it < 8; ++it) {
+      const int r = 4 * it + hr;
       double sq = 0.0;
 #pragma unroll
       for (int k = 0; k < D; ++k) {
@@ -208,7 +259,7 @@ __device__ __forceinline__ void cov_tail(const double (&acc)[32], double sa_r, c
       }
       const double v = my_stage[r * OZ_EPI_LD + hc] * sb_c;
       const double z = (stationary_from_sq(kind, os, sq) - v) * my_rows[r * (MAX_D + 1) + MAX_D];
-      if (col_ok && row0 + r < ep.C) zrow[(size_t)(2 * it) * ep.ldz] = z;
+      if (col_ok && row0 + r < ep.C) zrow[(size_t)(4 * it) * ep.ldz] = z;
     }
   }
   __syncwarp();
@@ -221,18 +272,17 @@ ozaki_kernel(const OzakiArgs args) {
   // space and emits LDS / STS instead of generic loads)
   unsigned char* smem = oz_smem_raw + ((1024u - (s_u32(oz_smem_raw) & 1023u)) & 1023u);
   const int NS = args.NS, NG = args.NG;
-  const int stage_bytes = 2 * NS * OZ_BLK_BYTES;
   unsigned char* s_stage = smem;
-  double* s_epi = reinterpret_cast<double*>(smem + (size_t)OZ_STAGES * 2 * OZ_MAX_DIGITS * OZ_BLK_BYTES);
+  double* s_epi = reinterpret_cast<double*>(smem + (size_t)OZ_STAGES * OZ_STAGE_CAP);
   double* s_rowdata = s_epi + OZ_EPI_WARPS * OZ_EPI_STAGE;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_rowdata + OZ_EPI_WARPS * OZ_ROWDATA);
   unsigned long long* full = bars;               // [OZ_STAGES]
   unsigned long long* empty = bars + OZ_STAGES;  // [OZ_STAGES]
-  unsigned long long* tfull = bars + 2 * OZ_STAGES;
-  unsigned long long* tempty = tfull + 1;
-  unsigned* s_tmem = reinterpret_cast<unsigned*>(tempty + 1);
-  int* s_nent = reinterpret_cast<int*>(s_tmem + 2);            // [4]
-  uint4* s_prog = reinterpret_cast<uint4*>(bars + 16);         // [4][OZ_MAX_ENT]
+  unsigned long long* tfull = bars + 2 * OZ_STAGES;  // [OZ_ACC]
+  unsigned long long* tempty = tfull + OZ_ACC;       // [OZ_ACC]
+  unsigned* s_tmem = reinterpret_cast<unsigned*>(tempty + OZ_ACC);
+  int* s_slotend = reinterpret_cast<int*>(s_tmem + 2);  // [4 passes][OZ_ACC] end of each slot's program entries
+  uint4* s_prog = reinterpret_cast<uint4*>(bars + 32);  // [4][OZ_MAX_ENT]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = args.KP / OZ_KB;
@@ -244,28 +294,32 @@ ozaki_kernel(const OzakiArgs args) {
       bar_init(&full[s], 1);
       bar_init(&empty[s], 1);
     }
-    bar_init(tfull, 1);
-    bar_init(tempty, OZ_EPI_WARPS);
+    for (int a = 0; a < OZ_ACC; ++a) {
+      bar_init(&tfull[a], 1);
+      bar_init(&tempty[a], OZ_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 2) {
-    // the MMA "program" of every pass: per MMA the two descriptor offsets, the instruction
-    // descriptor and the accumulator column, so that the issuing thread only adds and fires
+  if (warp == 2 && lane == 0) {
+    // generic digit configurations: the MMA "program" of every pass (descriptor offsets, instruction
+    // descriptor, accumulate flag), grouped by accumulator slot
     for (int p = 0; p < n_pass; ++p) {
       const int g_hi = NG - 1 - p * OZ_ACC;
       const int g_lo = g_hi - OZ_ACC + 1 > 0 ? g_hi - OZ_ACC + 1 : 0;
+      const int nd = (g_hi < NS - 1 ? g_hi : NS - 1) + 1;
       int ne = 0;
-      for (int g = g_hi; g >= g_lo; --g) {
-        const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
-        for (int i = ilo; i <= ihi; ++i, ++ne) {
-          const int j = g - i;
-          if (lane == 0)
-            s_prog[p * OZ_MAX_ENT + ne] = make_uint4((unsigned)(i * OZ_BLK_BYTES) >> 4, (unsigned)((NS + j) * OZ_BLK_BYTES) >> 4,
-                                                     umma_idesc(i == 0, j == 0),
-                                                     (unsigned)((g_hi - g) * OZ_BN) | (i > ilo ? 0x80000000u : 0u));
+      for (int a = 0; a < OZ_ACC; ++a) {
+        const int g = g_hi - a;
+        if (g >= g_lo) {
+          const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
+          for (int i = ilo; i <= ihi; ++i, ++ne) {
+            const int j = g - i;
+            s_prog[p * OZ_MAX_ENT + ne] = make_uint4((unsigned)(i * OZ_BLK_BYTES) >> 4, (unsigned)((nd + j) * OZ_BLK_BYTES) >> 4,
+                                                     umma_idesc(i == 0, j == 0), i > ilo ? 1u : 0u);
+          }
         }
+        s_slotend[p * OZ_ACC + a] = ne;
       }
-      if (lane == 0) s_nent[p] = ne;
     }
   }
   if (warp == 1) {
@@ -278,65 +332,90 @@ ozaki_kernel(const OzakiArgs args) {
   const unsigned tmem_base = *s_tmem;
 
   // Pass p folds the diagonals g_hi(p) .. g_lo(p) (at most OZ_ACC of them, one TMEM accumulator
-  // each), lowest weights first.  Digits needed by a pass: i, j in [max(0, g_lo - NS + 1), min(g_hi, NS - 1)].
+  // slot each), lowest weights first.  It needs the digits 0 .. nd-1 of both operands; a stage
+  // holds as many k blocks of them as fit in OZ_STAGE_CAP (two in the second pass of the default
+  // configuration, which keeps the short stages of that pass ahead of the copy latency).
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
     if (warp == 0 && lane == 0) {
-      // ===== TMA producer =====
+      // ===== bulk-copy producer =====
       int s = 0;
       unsigned ph = 0;
       for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
         const int m_blk = tile % args.m_tiles, n_blk = tile / args.m_tiles;
         for (int p = 0; p < n_pass; ++p) {
           const int g_hi = NG - 1 - p * OZ_ACC;
-          const int dhi = g_hi < NS - 1 ? g_hi : NS - 1;
-          const unsigned bytes = (unsigned)(2 * (dhi + 1) * OZ_BLK_BYTES);
-          for (int kb = 0; kb < KB; ++kb) {
+          const int nd = (g_hi < NS - 1 ? g_hi : NS - 1) + 1;
+          const unsigned kbytes = (unsigned)(nd * OZ_BLK_BYTES);  // per operand per k block
+          const int kps = (OZ_STAGE_CAP / (2 * (int)kbytes)) < args.max_kps ? (OZ_STAGE_CAP / (2 * (int)kbytes)) : args.max_kps;
+          for (int kb = 0; kb < KB; kb += kps) {
+            const int nk = KB - kb < kps ? KB - kb : kps;
             bar_wait(&empty[s], ph ^ 1);
-            bar_expect_tx(&full[s], bytes);
-            unsigned char* st = s_stage + (size_t)s * stage_bytes;
-            // digits 0 .. dhi of this (row block, k block) are one contiguous run in global memory
-            bulk_g2s(st, args.a_digits + ((size_t)(m_blk * KB + kb) * NS) * OZ_BLK_BYTES, bytes / 2, &full[s]);
-            bulk_g2s(st + NS * OZ_BLK_BYTES, args.b_digits + ((size_t)(n_blk * KB + kb) * NS) * OZ_BLK_BYTES,
-                     bytes / 2, &full[s]);
+            bar_expect_tx(&full[s], 2u * kbytes * nk);
+            unsigned char* st = s_stage + (size_t)s * OZ_STAGE_CAP;
+            for (int kk = 0; kk < nk; ++kk) {
+              // digits 0 .. nd-1 of one (row block, k block) are one contiguous run in global memory
+              bulk_g2s(st + (size_t)kk * 2 * kbytes, args.a_digits + ((size_t)(m_blk * KB + kb + kk) * NS) * OZ_BLK_BYTES,
+                       kbytes, &full[s]);
+              bulk_g2s(st + (size_t)kk * 2 * kbytes + kbytes,
+                       args.b_digits + ((size_t)(n_blk * KB + kb + kk) * NS) * OZ_BLK_BYTES, kbytes, &full[s]);
+            }
             if (++s == OZ_STAGES) { s = 0; ph ^= 1; }
           }
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ===== MMA issuer =====
+    } else if (warp == 1) {
+      // ===== MMA issuer (the whole warp runs the loops, one elected lane issues) =====
       int s = 0;
       unsigned ph = 0;
       unsigned pcount = 0;
+      const bool std_cfg = NS == OZ_DEFAULT_DIGITS && NG == OZ_DEFAULT_DIAGONALS;
       for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
         for (int p = 0; p < n_pass; ++p, ++pcount) {
-          bar_wait(tempty, (pcount & 1) ^ 1);
-          tc_fence_after();
+          const unsigned par = pcount & 1;
+          const int g_hi = NG - 1 - p * OZ_ACC;
+          const int nd = (g_hi < NS - 1 ? g_hi : NS - 1) + 1;
+          const unsigned kbytes = (unsigned)(nd * OZ_BLK_BYTES);
+          const int kps = (OZ_STAGE_CAP / (2 * (int)kbytes)) < args.max_kps ? (OZ_STAGE_CAP / (2 * (int)kbytes)) : args.max_kps;
           const uint4* prog = s_prog + p * OZ_MAX_ENT;
-          const int ne = s_nent[p];
-          const bool std_cfg = NS == OZ_DEFAULT_DIGITS && NG == OZ_DEFAULT_DIAGONALS;
-          for (int kb = 0; kb < KB; ++kb) {
+          const int* slotend = s_slotend + p * OZ_ACC;
+          for (int kb = 0; kb < KB; kb += kps) {
+            const int nk = KB - kb < kps ? KB - kb : kps;
             bar_wait(&full[s], ph);
             tc_fence_after();
-            const unsigned long long base = umma_desc(s_u32(s_stage + (size_t)s * stage_bytes));
-            const unsigned kacc = kb > 0 ? 1u : 0u;
-            if (std_cfg) {
-              // default digit configuration: the MMA list is unrolled at compile time (offsets and
-              // instruction descriptors become immediates; ~5 SASS instructions per MMA instead
-              // of ~23 through the table, which left the tensor pipe waiting on the issuing thread)
-              if (p == 0) issue_pass<OZ_DEFAULT_DIGITS, OZ_DEFAULT_DIAGONALS, 0>(tmem_base, base, kacc);
-              else issue_pass<OZ_DEFAULT_DIGITS, OZ_DEFAULT_DIAGONALS, 1>(tmem_base, base, kacc);
-            } else {
-#pragma unroll 4
-              for (int e = 0; e < ne; ++e) {
-                const uint4 en = prog[e];
-                umma_i8(tmem_base + (en.w & 0xFFFFu), base + en.x, base + en.y, en.z, kacc | (en.w >> 31));
+            const unsigned st_addr = s_u32(s_stage + (size_t)s * OZ_STAGE_CAP);
+            if (elect_one()) {
+            for (int kk = 0; kk < nk; ++kk) {
+              const unsigned long long base = umma_desc(st_addr + kk * 2 * kbytes);
+              const bool first_k = kb + kk == 0, last_k = kb + kk == KB - 1;
+              if (std_cfg) {
+                // default digit configuration: offsets and instruction descriptors are immediates
+                // (~10 uniform-datapath instructions per MMA; through the table the issuing thread
+                // needed ~23 and the tensor pipe waited on it)
+                if (p == 0)
+                  issue_pass<OZ_DEFAULT_DIGITS, OZ_DEFAULT_DIAGONALS, 0>(tmem_base, base, first_k, last_k, tfull, tempty, par, args.slot_wait != 0);
+                else
+                  issue_pass<OZ_DEFAULT_DIGITS, OZ_DEFAULT_DIAGONALS, 1>(tmem_base, base, first_k, last_k, tfull, tempty, par, args.slot_wait != 0);
+              } else {
+                int e = 0;
+                for (int a = 0; a < OZ_ACC; ++a) {
+                  if (first_k) {
+                    bar_wait(&tempty[a], par ^ 1);
+                    tc_fence_after();
+                  }
+                  for (; e < slotend[a]; ++e) {
+                    const uint4 en = prog[e];
+                    umma_i8(tmem_base + (unsigned)(a * OZ_BN), base + en.x, base + en.y, en.z, (first_k ? 0u : 1u) | en.w);
+                  }
+                  if (last_k) umma_commit(&tfull[a]);
+                }
               }
             }
             umma_commit(&empty[s]);
+            }
+            __syncwarp();
             if (++s == OZ_STAGES) { s = 0; ph ^= 1; }
           }
-          umma_commit(tfull);
         }
       }
     }
@@ -355,30 +434,32 @@ ozaki_kernel(const OzakiArgs args) {
 #pragma unroll
       for (int c = 0; c < 32; ++c) acc[c] = 0.0;
       for (int p = 0; p < n_pass; ++p, ++pcount) {
+        const unsigned par = pcount & 1;
         const int g_hi = NG - 1 - p * OZ_ACC;
         const int g_lo = g_hi - OZ_ACC + 1 > 0 ? g_hi - OZ_ACC + 1 : 0;
         double w = 1.0;
         for (int g = 0; g < g_hi; ++g) w *= 0.00390625;  // 256^-g_hi
-        bar_wait(tfull, pcount & 1);
-        tc_fence_after();
         const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + cg * 32;
-        for (int g = g_hi; g >= g_lo; --g) {
-          int r[32];
-          OZ_TMEM_LD32(r, taddr + (unsigned)(g_hi - g) * OZ_BN);
-          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        for (int a = 0; a < OZ_ACC; ++a) {
+          bar_wait(&tfull[a], par);
+          tc_fence_after();
+          if (g_hi - a >= g_lo) {
+            int r[32];
+            OZ_TMEM_LD32(r, taddr + (unsigned)(a * OZ_BN));
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-          for (int c = 0; c < 32; ++c) acc[c] = fma(i32_to_f64(r[c]), w, acc[c]);
+            for (int c = 0; c < 32; ++c) acc[c] = fma(i32_to_f64(r[c]), w, acc[c]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) bar_arrive(&tempty[a]);
           w *= 256.0;
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) bar_arrive(tempty);
       }
-      // ---- final epilogue: scales, kernel term, coalesced stores (two rows of 16 columns per pass) ----
+      // ---- final epilogue ----
       const int row0 = m_blk * OZ_BM + q * 32;
       const int col0 = n_blk * OZ_BN + cg * 32;
       const double sa_r = args.sa[row0 + lane];
-      const int hr = lane >> 4, hc = lane & 15;
       if (args.cov) {
         switch (args.ep.d) {
           case 1: cov_tail<1>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
@@ -391,16 +472,19 @@ ozaki_kernel(const OzakiArgs args) {
           default: cov_tail<8>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
         }
       } else {
+        // product mode: scale and store through the 8-column transpose
+        const int hr = lane >> 3, hc = lane & 7;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 4; ++h) {
           __syncwarp();
 #pragma unroll
-          for (int c = 0; c < 16; ++c) my_stage[lane * OZ_EPI_LD + c] = acc[h * 16 + c] * sa_r;
+          for (int c = 0; c < 8; ++c) my_stage[lane * OZ_EPI_LD + c] = acc[h * 8 + c] * sa_r;
           __syncwarp();
-          const int col = col0 + h * 16 + hc;
+          const int col = col0 + h * 8 + hc;
           const double sb_c = args.sb[col];
-          for (int it = 0; it < 16; ++it) {
-            const int r = 2 * it + hr;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = 4 * it + hr;
             if (row0 + r < args.M && col < args.N)
               args.D[(size_t)(row0 + r) * args.ldd + col] = my_stage[r * OZ_EPI_LD + hc] * sb_c;
           }
@@ -493,6 +577,14 @@ static int ozaki_launch(const unsigned char* a_digits, const double* sa, int M_p
   args.n_tiles = N_pad / OZ_BN;
   args.sa = sa;
   args.sb = sb;
+  {
+    const char* e = getenv("DKG_OZ_KPS");
+    args.max_kps = e != nullptr ? atoi(e) : OZ_MAX_KPS;
+    if (args.max_kps < 1) args.max_kps = 1;
+    if (args.max_kps > OZ_MAX_KPS) args.max_kps = OZ_MAX_KPS;
+    e = getenv("DKG_OZ_SLOTWAIT");
+    args.slot_wait = e != nullptr ? atoi(e) : 1;
+  }
   const int tiles = args.m_tiles * args.n_tiles;
   const int grid = tiles < n_sm ? tiles : n_sm;
   ozaki_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(args);

@@ -39,7 +39,9 @@ EXPORTED_SYMBOLS = (
     "dkg_profile_enable",
     "dkg_profile_read",
 )
-PROFILE_CATEGORIES = ("xprep", "gemm_T", "var", "gemm_cov", "place_own", "zstat", "filter", "hull", "overflow", "finalize")
+PROFILE_CATEGORIES = (
+    "xprep", "gemm_T", "var", "gemm_cov", "place_own", "zstat", "filter", "hull", "overflow", "finalize", "digits",
+)
 
 
 class NativeLibraryError(RuntimeError):

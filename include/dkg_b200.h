@@ -179,9 +179,11 @@ DKG_API void dkg_launch_count_reset(void);
 /* Optional per-kernel timing for bench.py's roofline line: when enabled, every launch of a
  * forward is bracketed by CUDA events on the launching stream.  dkg_profile_read synchronises the
  * device, sums the elapsed milliseconds and launch counts per category and clears the samples.
- * Categories: 0 xprep, 1 gemm_T (KX @ Kinv), 2 var, 3 gemm_cov (the conditioning contraction),
- * 4 place_own, 5 zstat, 6 filter, 7 hull, 8 overflow (cooperative path), 9 finalize (+ backward). */
-#define DKG_PROFILE_CATEGORIES 10
+ * Categories: 0 xprep, 1 gemm_T (KX K^-1), 2 var, 3 gemm_cov (the conditioning contraction:
+ * int8 tensor-core kernel, or the DMMA kernel), 4 place_own, 5 zstat (+ slope completion),
+ * 6 filter, 7 hull, 8 overflow (cooperative path), 9 finalize (+ backward), 10 digits (base-256
+ * digit planes of the T rows for the int8 contraction). */
+#define DKG_PROFILE_CATEGORIES 11
 DKG_API void dkg_profile_enable(int on);
 DKG_API int dkg_profile_read(double* ms_host, int64_t* count_host, int32_t ncat);
 
@@ -190,7 +192,8 @@ DKG_API int dkg_profile_read(double* ms_host, int64_t* count_host, int32_t ncat)
  * handled by the cooperative overflow kernel, [3] total hull vertices, [4] sets taking the
  * |slope| < 1e-9 shortcut, [5] sets that needed the block-wide exact march, [6] sets with more hull
  * vertices than the 64 record slots (their value is exact; their gradient omits the extra
- * vertices -- the Python layer raises if this is ever non-zero), [7] reserved */
+ * vertices -- the Python layer raises if this is ever non-zero), [7] 1 when the covariance
+ * contraction of this plan runs on the int8 tensor cores (0: fp64 DMMA kernel) */
 DKG_API int dkg_plan_stats(dkg_plan* plan, int64_t* out8_host, void* stream);
 
 #ifdef __cplusplus

@@ -23,6 +23,7 @@ struct ObjState {
   int ldk = 0;               // row stride of Kinv / T (n rounded up to GEMM_BN)
   double* chol = nullptr;    // [n, n]        lower Cholesky of K + noise I
   double* Kinv = nullptr;    // [n_pad, ldk]
+  bool refine = true;        // T = KX K^-1 needs the refinement step (set at plan time from a bound on cond(K))
   double* Kmat = nullptr;    // [n_pad, ldk]  K + (noise + jitter) I, zero padded (refinement residual)
   double* Kxd = nullptr;     // [n_pad, N_pad]  k(X_train, X_disc) (raw cross-kernel, GEMM B operand)
   unsigned char* Kxd_dig = nullptr;  // [digits][N_pad][KP] base-256 digit planes of Kxd^T (int8 tensor-core path)

@@ -109,7 +109,7 @@ static int ensure_workspace(dkg_plan* p, int C) {
     for (int m = 0; m < p->M; ++m)
       if (coupled || m == p->target) n_max = n_max > p->obj[m].n ? n_max : p->obj[m].n;
     DKG_TRY(dev_alloc(&w.T_dig, ozaki_digit_bytes(chunk, n_max, OZ_DEFAULT_DIGITS)));
-    DKG_TRY(dev_alloc(&w.T_scale, (size_t)chunk));
+    DKG_TRY(dev_alloc(&w.T_scale, (size_t)chunk + 128));  // + one row block: the CTA-pair kernel reads 256-row pairs
   }
   DKG_TRY(dev_alloc(&w.var, (size_t)cap));
   DKG_TRY(dev_alloc(&w.sd, (size_t)cap));
@@ -184,7 +184,8 @@ static int make_kxd_digits(ObjState& o, const dkg_plan* p, cudaStream_t st) {
   if (rc == DKG_OK) rc = dev_alloc(&o.Kxd_dig, ozaki_digit_bytes(p->N_pad, o.n, OZ_DEFAULT_DIGITS));
   if (rc == DKG_OK) rc = dev_alloc(&o.Kxd_scale, (size_t)p->N_pad);
   if (rc == DKG_OK)
-    rc = ozaki_slice_rows(KT, o.n_pad, p->N, o.n, p->N_pad, OZ_DEFAULT_DIGITS, o.Kxd_dig, o.Kxd_scale, st);
+    rc = ozaki_slice_rows(KT, o.n_pad, p->N, o.n, ozaki_b_block_rows(OZ_DEFAULT_DIGITS, OZ_DEFAULT_DIAGONALS), OZ_DEFAULT_DIGITS,
+                          o.Kxd_dig, o.Kxd_scale, st);
   cudaStreamSynchronize(st);
   dev_free(KT);
   return rc;
@@ -194,7 +195,7 @@ static int make_kxd_digits(ObjState& o, const dkg_plan* p, cudaStream_t st) {
 static int cov_rows(const ObjState& o, const dkg_plan* p, Workspace& w, const double* T, int cc, int cc_pad,
                     const CovEpilogue& ep, cudaStream_t st) {
   if (o.Kxd_dig != nullptr) {
-    DKG_TRY(ozaki_slice_rows(T, o.ldk, cc, o.n, cc_pad, OZ_DEFAULT_DIGITS, w.T_dig, w.T_scale, st));
+    DKG_TRY(ozaki_slice_rows(T, o.ldk, cc, o.n, 128, OZ_DEFAULT_DIGITS, w.T_dig, w.T_scale, st));
     return ozaki_cov(w.T_dig, w.T_scale, cc_pad, o.Kxd_dig, o.Kxd_scale, p->N_pad, o.n, OZ_DEFAULT_DIGITS,
                      OZ_DEFAULT_DIAGONALS, ep, st);
   }
@@ -462,7 +463,7 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
         // int8 tensor cores in product mode: Z <- T . Kxd; the row-statistics pass below turns
         // the products into slopes while it reads them (CovFinish)
         { ProfScope pd(10, st);
-          DKG_TRY(ozaki_slice_rows(w.T + (size_t)c0 * p->ldk, p->ldk, cc, ot.n, cc_pad, OZ_DEFAULT_DIGITS, w.T_dig,
+          DKG_TRY(ozaki_slice_rows(w.T + (size_t)c0 * p->ldk, p->ldk, cc, ot.n, 128, OZ_DEFAULT_DIGITS, w.T_dig,
                                    w.T_scale, st)); }
         ProfScope ps(3, st);
         DKG_TRY(ozaki_store(w.T_dig, w.T_scale, cc_pad, ot.Kxd_dig, ot.Kxd_scale, p->N_pad, ot.n, OZ_DEFAULT_DIGITS,
@@ -746,10 +747,10 @@ int dkg_int8_matmul_dev(const double* A_dev, int32_t lda, const double* Bt_dev, 
   double *sa = nullptr, *sb = nullptr;
   int rc = dev_alloc(&da, ozaki_digit_bytes(M_pad, K, n_digits));
   if (rc == DKG_OK) rc = dev_alloc(&db, ozaki_digit_bytes(N_pad, K, n_digits));
-  if (rc == DKG_OK) rc = dev_alloc(&sa, (size_t)M_pad);
+  if (rc == DKG_OK) rc = dev_alloc(&sa, (size_t)M_pad + 128);
   if (rc == DKG_OK) rc = dev_alloc(&sb, (size_t)N_pad);
-  if (rc == DKG_OK) rc = ozaki_slice_rows(A_dev, lda, M, K, M_pad, n_digits, da, sa, st);
-  if (rc == DKG_OK) rc = ozaki_slice_rows(Bt_dev, ldb, N, K, N_pad, n_digits, db, sb, st);
+  if (rc == DKG_OK) rc = ozaki_slice_rows(A_dev, lda, M, K, 128, n_digits, da, sa, st);
+  if (rc == DKG_OK) rc = ozaki_slice_rows(Bt_dev, ldb, N, K, ozaki_b_block_rows(n_digits, n_diagonals), n_digits, db, sb, st);
   if (rc == DKG_OK) rc = ozaki_store(da, sa, M_pad, db, sb, N_pad, K, n_digits, n_diagonals, D_dev, ldd, M, N, st);
   cudaError_t e = cudaStreamSynchronize(st);
   if (rc == DKG_OK && e != cudaSuccess) {

@@ -51,7 +51,9 @@ constexpr int OZ_DEFAULT_DIAGONALS = 8;
 constexpr int OZ_MAX_K = 4096;
 int ozaki_kp(int K);
 size_t ozaki_digit_bytes(int rows_pad, int K, int NS);
-int ozaki_slice_rows(const double* X, int ld, int rows, int K, int slice_rows, int NS, unsigned char* digits,
+// rows per digit block of the B operand: 64 when the CTA-pair kernel serves this configuration, else 128
+int ozaki_b_block_rows(int NS, int NG);
+int ozaki_slice_rows(const double* X, int ld, int rows, int K, int block_rows, int NS, unsigned char* digits,
                      double* scale, cudaStream_t st);
 int ozaki_cov(const unsigned char* a_digits, const double* sa, int M_pad, const unsigned char* b_digits,
               const double* sb, int N_pad, int K, int NS, int NG, const CovEpilogue& ep, cudaStream_t st);

@@ -178,30 +178,34 @@ __device__ __forceinline__ void issue_pass_k(unsigned tmem_base, unsigned long l
   constexpr int g_hi = NG - 1 - P * OZ_ACC;
   constexpr int g_lo = g_hi - OZ_ACC + 1 > 0 ? g_hi - OZ_ACC + 1 : 0;
   constexpr int nd = (g_hi < NS - 1 ? g_hi : NS - 1) + 1;  // digits 0 .. nd-1 of both operands are staged
-  if (FIRST && !slot_wait) {
+  (void)slot_wait;
+  if (FIRST) {
+#pragma unroll
     for (int a = 0; a < OZ_ACC; ++a) bar_wait(&tempty[a], par ^ 1);
     tc_fence_after();
   }
+  // round-robin over the accumulator slots: consecutive MMAs never accumulate into the same slot, so the
+  // read-modify-write latency of a 64-cycle N = 128 MMA on its TMEM accumulator is not exposed
 #pragma unroll
-  for (int a = 0; a < OZ_ACC; ++a) {
-    const int g = g_hi - a;
-    if (FIRST && slot_wait) {
-      bar_wait(&tempty[a], par ^ 1);
-      tc_fence_after();
-    }
-    if (g >= g_lo) {
-      const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
+  for (int t = 0; t < NS; ++t) {
 #pragma unroll
-      for (int i = 0; i < NS; ++i) {
-        if (i >= ilo && i <= ihi) {
+    for (int a = 0; a < OZ_ACC; ++a) {
+      const int g = g_hi - a;
+      if (g >= g_lo) {
+        const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
+        const int i = ilo + t;
+        if (i <= ihi) {
           const int j = g - i;
           umma_i8(tmem_base + (unsigned)(a * OZ_BN), base + (unsigned long long)((i * OZ_BLK_BYTES) >> 4),
                   base + (unsigned long long)(((nd + j) * OZ_BLK_BYTES) >> 4), umma_idesc(i == 0, j == 0),
-                  (i > ilo || !FIRST) ? 1u : 0u);
+                  (t > 0 || !FIRST) ? 1u : 0u);
         }
       }
     }
-    if (LAST) umma_commit(&tfull[a]);
+  }
+  if (LAST) {
+#pragma unroll
+    for (int a = 0; a < OZ_ACC; ++a) umma_commit(&tfull[a]);
   }
 }
 
@@ -260,6 +264,28 @@ __device__ __forceinline__ void cov_tail(const double (&acc)[32], double sa_r, c
       const double v = my_stage[r * OZ_EPI_LD + hc] * sb_c;
       const double z = (stationary_from_sq(kind, os, sq) - v) * my_rows[r * (MAX_D + 1) + MAX_D];
       if (col_ok && row0 + r < ep.C) zrow[(size_t)(4 * it) * ep.ldz] = z;
+    }
+  }
+  __syncwarp();
+}
+
+// product mode: scale and store the warp's 32 x 32 block through the 8-column transpose
+__device__ __forceinline__ void store_tail(const double (&acc)[32], double sa_r, const OzakiArgs& args, double* my_stage,
+                                           int row0, int col0, int lane) {
+  const int hr = lane >> 3, hc = lane & 7;
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) my_stage[lane * OZ_EPI_LD + c] = acc[h * 8 + c] * sa_r;
+    __syncwarp();
+    const int col = col0 + h * 8 + hc;
+    const double sb_c = args.sb[col];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = 4 * it + hr;
+      if (row0 + r < args.M && col < args.N)
+        args.D[(size_t)(row0 + r) * args.ldd + col] = my_stage[r * OZ_EPI_LD + hc] * sb_c;
     }
   }
   __syncwarp();
@@ -472,24 +498,7 @@ ozaki_kernel(const OzakiArgs args) {
           default: cov_tail<8>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
         }
       } else {
-        // product mode: scale and store through the 8-column transpose
-        const int hr = lane >> 3, hc = lane & 7;
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < 8; ++c) my_stage[lane * OZ_EPI_LD + c] = acc[h * 8 + c] * sa_r;
-          __syncwarp();
-          const int col = col0 + h * 8 + hc;
-          const double sb_c = args.sb[col];
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = 4 * it + hr;
-            if (row0 + r < args.M && col < args.N)
-              args.D[(size_t)(row0 + r) * args.ldd + col] = my_stage[r * OZ_EPI_LD + hc] * sb_c;
-          }
-        }
-        __syncwarp();
+        store_tail(acc, sa_r, args, my_stage, row0, col0, lane);
       }
     }
   }
@@ -501,8 +510,307 @@ ozaki_kernel(const OzakiArgs args) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant (cluster of 2, tcgen05.mma.cta_group::2, M = 256 across the two SMs).
+// With N = 128 a single-CTA MMA reads 8 KB of operands per 64 cycles - all of the 128 B/clk of
+// shared-memory bandwidth, which it shares with the bulk copies and the epilogue.  In pair mode
+// each SM feeds its own 128 rows of A and only HALF of B (64 rows, 2 KB per digit): 96 B/clk.
+//   rank 0 (leader): issues every MMA; its tcgen05.commit multicasts to both CTAs' barriers.
+//   rank 1         : warp 1 relays "my stage has landed" to the leader (remote mbarrier arrive),
+//                    since a linear bulk copy can only signal a barrier of its own CTA.
+//   both           : producer (own A rows + own B half), 16 epilogue warps draining the local
+//                    TMEM; slot releases (tempty) are remote arrivals on the leader's barriers.
+// Default digit configuration only (7 digits, 8 diagonals: two passes of four slots).
+// ------------------------------------------------------------------------------------------
+constexpr int OZP_STAGES = 3;
+constexpr int OZP_STAGE_CAP = 49152;  // one k block of 7 x (4 KB + 2 KB), or two of 4 x (4 KB + 2 KB)
+constexpr int OZP_HALF_BYTES = OZ_BLK_BYTES / 2;
+constexpr size_t OZP_SMEM = 1024 + (size_t)OZP_STAGES * OZP_STAGE_CAP +
+                            (size_t)OZ_EPI_WARPS * (OZ_EPI_STAGE + OZ_ROWDATA) * sizeof(double) + 256;
+static_assert(OZP_SMEM <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned map_to_rank(unsigned smem_addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void bar_arrive_cluster(unsigned cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void bar_wait_cluster(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra D_%=;\n"
+      "bra W_%=;\n"
+      "D_%=:\n"
+      "}\n" ::"r"(s_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(unsigned long long* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(s_u32(bar)),
+      "h"((unsigned short)3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc,
+                                             unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ unsigned umma_idesc_pair(int a_signed, int b_signed) {
+  return (2u << 4) | ((unsigned)a_signed << 7) | ((unsigned)b_signed << 10) | ((unsigned)(OZ_BN >> 3) << 17) |
+         ((unsigned)(256 >> 4) << 24);
+}
+
+template <int NS, int NG, int P, bool FIRST, bool LAST>
+__device__ __forceinline__ void issue_pass_pair_k(unsigned tmem_base, unsigned long long base, unsigned long long* tfull,
+                                                  unsigned long long* tempty, unsigned par) {
+  constexpr int g_hi = NG - 1 - P * OZ_ACC;
+  constexpr int g_lo = g_hi - OZ_ACC + 1 > 0 ? g_hi - OZ_ACC + 1 : 0;
+  constexpr int nd = (g_hi < NS - 1 ? g_hi : NS - 1) + 1;
+#pragma unroll
+  for (int a = 0; a < OZ_ACC; ++a) {
+    const int g = g_hi - a;
+    if (FIRST) {
+      bar_wait_cluster(&tempty[a], par ^ 1);
+      tc_fence_after();
+    }
+    if (g >= g_lo) {
+      const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        if (i >= ilo && i <= ihi) {
+          const int j = g - i;
+          umma_i8_pair(tmem_base + (unsigned)(a * OZ_BN), base + (unsigned long long)((i * OZ_BLK_BYTES) >> 4),
+                       base + (unsigned long long)((nd * OZ_BLK_BYTES + j * OZP_HALF_BYTES) >> 4),
+                       umma_idesc_pair(i == 0, j == 0), (i > ilo || !FIRST) ? 1u : 0u);
+        }
+      }
+    }
+    if (LAST) umma_commit_pair(&tfull[a]);
+  }
+}
+template <int NS, int NG, int P>
+__device__ __forceinline__ void issue_pass_pair(unsigned tmem_base, unsigned long long base, bool first_k, bool last_k,
+                                                unsigned long long* tfull, unsigned long long* tempty, unsigned par) {
+  if (first_k) {
+    if (last_k) issue_pass_pair_k<NS, NG, P, true, true>(tmem_base, base, tfull, tempty, par);
+    else issue_pass_pair_k<NS, NG, P, true, false>(tmem_base, base, tfull, tempty, par);
+  } else {
+    if (last_k) issue_pass_pair_k<NS, NG, P, false, true>(tmem_base, base, tfull, tempty, par);
+    else issue_pass_pair_k<NS, NG, P, false, false>(tmem_base, base, tfull, tempty, par);
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1)
+ozaki_pair_kernel(const OzakiArgs args) {
+  constexpr int NS = OZ_DEFAULT_DIGITS, NG = OZ_DEFAULT_DIAGONALS;
+  constexpr int n_pass = (NG + OZ_ACC - 1) / OZ_ACC;
+  extern __shared__ unsigned char oz_smem_raw[];
+  unsigned char* smem = oz_smem_raw + ((1024u - (s_u32(oz_smem_raw) & 1023u)) & 1023u);
+  unsigned char* s_stage = smem;
+  double* s_epi = reinterpret_cast<double*>(smem + (size_t)OZP_STAGES * OZP_STAGE_CAP);
+  double* s_rowdata = s_epi + OZ_EPI_WARPS * OZ_EPI_STAGE;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_rowdata + OZ_EPI_WARPS * OZ_ROWDATA);
+  unsigned long long* full = bars;                    // [OZP_STAGES] own stage landed
+  unsigned long long* pfull = full + OZP_STAGES;      // [OZP_STAGES] (leader) peer's stage landed
+  unsigned long long* empty = pfull + OZP_STAGES;     // [OZP_STAGES] stage consumed (multicast commit)
+  unsigned long long* tfull = empty + OZP_STAGES;     // [OZ_ACC] slot ready (multicast commit)
+  unsigned long long* tempty = tfull + OZ_ACC;        // [OZ_ACC] (leader) slot drained by both CTAs
+  unsigned* s_tmem = reinterpret_cast<unsigned*>(tempty + OZ_ACC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned rank = cluster_ctarank();
+  const int KB = args.KP / OZ_KB;
+  const int m_pairs = (args.m_tiles + 1) / 2;
+  const int n_tiles_total = m_pairs * args.n_tiles;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < OZP_STAGES; ++s) {
+      bar_init(&full[s], 1);
+      bar_init(&pfull[s], 1);
+      bar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < OZ_ACC; ++a) {
+      bar_init(&tfull[a], 1);
+      bar_init(&tempty[a], 2 * OZ_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_u32(s_tmem)), "n"(OZ_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const unsigned tmem_base = *s_tmem;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
+    if (warp == 0 && lane == 0) {
+      // ===== producer: own 128 rows of A, own 64-row half of B =====
+      int s = 0;
+      unsigned ph = 0;
+      for (int tile = cluster_id; tile < n_tiles_total; tile += n_clusters) {
+        const int m_blk = (tile % m_pairs) * 2 + (int)rank, n_half = (tile / m_pairs) * 2 + (int)rank;
+        for (int p = 0; p < n_pass; ++p) {
+          const int g_hi = NG - 1 - p * OZ_ACC;
+          const int nd = (g_hi < NS - 1 ? g_hi : NS - 1) + 1;
+          const unsigned abytes = (unsigned)(nd * OZ_BLK_BYTES), bbytes = (unsigned)(nd * OZP_HALF_BYTES);
+          const int kps = OZP_STAGE_CAP / (int)(abytes + bbytes) < OZ_MAX_KPS ? OZP_STAGE_CAP / (int)(abytes + bbytes) : OZ_MAX_KPS;
+          for (int kb = 0; kb < KB; kb += kps) {
+            const int nk = KB - kb < kps ? KB - kb : kps;
+            bar_wait_cluster(&empty[s], ph ^ 1);
+            bar_expect_tx(&full[s], (abytes + bbytes) * nk);
+            unsigned char* st = s_stage + (size_t)s * OZP_STAGE_CAP;
+            for (int kk = 0; kk < nk; ++kk) {
+              bulk_g2s(st + (size_t)kk * (abytes + bbytes), args.a_digits + ((size_t)(m_blk * KB + kb + kk) * NS) * OZ_BLK_BYTES,
+                       abytes, &full[s]);
+              bulk_g2s(st + (size_t)kk * (abytes + bbytes) + abytes,
+                       args.b_digits + ((size_t)(n_half * KB + kb + kk) * NS) * OZP_HALF_BYTES, bbytes, &full[s]);
+            }
+            if (++s == OZP_STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      int s = 0;
+      unsigned ph = 0;
+      unsigned pcount = 0;
+      if (rank == 0) {
+        // ===== leader: MMA issuer for the pair =====
+        for (int tile = cluster_id; tile < n_tiles_total; tile += n_clusters) {
+          for (int p = 0; p < n_pass; ++p, ++pcount) {
+            const unsigned par = pcount & 1;
+            const int g_hi = NG - 1 - p * OZ_ACC;
+            const int nd = (g_hi < NS - 1 ? g_hi : NS - 1) + 1;
+            const unsigned kbytes = (unsigned)(nd * (OZ_BLK_BYTES + OZP_HALF_BYTES));
+            const int kps = OZP_STAGE_CAP / (int)kbytes < OZ_MAX_KPS ? OZP_STAGE_CAP / (int)kbytes : OZ_MAX_KPS;
+            for (int kb = 0; kb < KB; kb += kps) {
+              const int nk = KB - kb < kps ? KB - kb : kps;
+              bar_wait(&full[s], ph);
+              bar_wait_cluster(&pfull[s], ph);
+              tc_fence_after();
+              if (elect_one()) {
+                const unsigned st_addr = s_u32(s_stage + (size_t)s * OZP_STAGE_CAP);
+                for (int kk = 0; kk < nk; ++kk) {
+                  const unsigned long long base = umma_desc(st_addr + kk * kbytes);
+                  const bool first_k = kb + kk == 0, last_k = kb + kk == KB - 1;
+                  if (p == 0) issue_pass_pair<NS, NG, 0>(tmem_base, base, first_k, last_k, tfull, tempty, par);
+                  else issue_pass_pair<NS, NG, 1>(tmem_base, base, first_k, last_k, tfull, tempty, par);
+                }
+                umma_commit_pair(&empty[s]);
+              }
+              __syncwarp();
+              if (++s == OZP_STAGES) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      } else if (lane == 0) {
+        // ===== peer: tell the leader when this CTA's stage has landed =====
+        for (int tile = cluster_id; tile < n_tiles_total; tile += n_clusters) {
+          for (int p = 0; p < n_pass; ++p) {
+            const int g_hi = NG - 1 - p * OZ_ACC;
+            const int nd = (g_hi < NS - 1 ? g_hi : NS - 1) + 1;
+            const unsigned kbytes = (unsigned)(nd * (OZ_BLK_BYTES + OZP_HALF_BYTES));
+            const int kps = OZP_STAGE_CAP / (int)kbytes < OZ_MAX_KPS ? OZP_STAGE_CAP / (int)kbytes : OZ_MAX_KPS;
+            for (int kb = 0; kb < KB; kb += kps) {
+              bar_wait(&full[s], ph);
+              bar_arrive_cluster(map_to_rank(s_u32(&pfull[s]), 0));
+              if (++s == OZP_STAGES) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n");
+    // ===== epilogue warps (both CTAs drain their own TMEM) =====
+    const int ew = warp - 4;
+    const int q = warp & 3;
+    const int cg = ew >> 2;
+    double* my_stage = s_epi + ew * OZ_EPI_STAGE;
+    double* my_rows = s_rowdata + ew * OZ_ROWDATA;
+    unsigned tempty_leader[OZ_ACC];
+#pragma unroll
+    for (int a = 0; a < OZ_ACC; ++a) tempty_leader[a] = map_to_rank(s_u32(&tempty[a]), 0);
+    unsigned pcount = 0;
+    for (int tile = cluster_id; tile < n_tiles_total; tile += n_clusters) {
+      const int m_blk = (tile % m_pairs) * 2 + (int)rank, n_blk = tile / m_pairs;
+      double acc[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = 0.0;
+      for (int p = 0; p < n_pass; ++p, ++pcount) {
+        const unsigned par = pcount & 1;
+        const int g_hi = NG - 1 - p * OZ_ACC;
+        const int g_lo = g_hi - OZ_ACC + 1 > 0 ? g_hi - OZ_ACC + 1 : 0;
+        double w = 1.0;
+        for (int g = 0; g < g_hi; ++g) w *= 0.00390625;
+        const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + cg * 32;
+#pragma unroll
+        for (int a = 0; a < OZ_ACC; ++a) {
+          bar_wait_cluster(&tfull[a], par);
+          tc_fence_after();
+          if (g_hi - a >= g_lo) {
+            int r[32];
+            OZ_TMEM_LD32(r, taddr + (unsigned)(a * OZ_BN));
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[c] = fma(i32_to_f64(r[c]), w, acc[c]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) bar_arrive_cluster(tempty_leader[a]);
+          w *= 256.0;
+        }
+      }
+      const int row0 = m_blk * OZ_BM + q * 32;
+      const int col0 = n_blk * OZ_BN + cg * 32;
+      const double sa_r = args.sa[row0 + lane];
+      if (args.cov) {
+        switch (args.ep.d) {
+          case 1: cov_tail<1>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
+          case 2: cov_tail<2>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
+          case 3: cov_tail<3>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
+          case 4: cov_tail<4>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
+          case 5: cov_tail<5>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
+          case 6: cov_tail<6>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
+          case 7: cov_tail<7>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
+          default: cov_tail<8>(acc, sa_r, args, my_stage, my_rows, row0, col0, lane); break;
+        }
+      } else {
+        store_tail(acc, sa_r, args, my_stage, row0, col0, lane);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(OZ_TMEM_COLS));
+  }
+}
+
 // One warp per row: power-of-two scale into (-128, 128), then NS exact base-256 digits.
-__global__ void slice_rows_kernel(const double* __restrict__ X, int ld, int rows, int K, int KP, int NS,
+__global__ void slice_rows_kernel(const double* __restrict__ X, int ld, int rows, int K, int KP, int NS, int block_rows,
                                   unsigned char* __restrict__ out, double* __restrict__ scale) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -522,10 +830,12 @@ __global__ void slice_rows_kernel(const double* __restrict__ X, int ld, int rows
     double v = (k < K) ? scalbn(rint(scalbn(x[k], 8 * (NS - 1) - e7)), -8 * (NS - 1)) : 0.0;
     for (int s = 0; s < NS; ++s) {
       const double dg = floor(v);
-      // block image: [row block][k block][digit][row group (16)][k chunk (2)][row in group (8)][16 B]
-      const size_t blk = ((size_t)(r >> 7) * (KP >> 5) + (k >> 5)) * NS + s;
-      const int in_blk = ((((r & 127) >> 3) * 2 + ((k & 31) >> 4)) * 8 + (r & 7)) * 16 + (k & 15);
-      out[blk * OZ_BLK_BYTES + in_blk] = (unsigned char)(int)dg;  // two's complement byte for s = 0
+      // block image: [row block][k block][digit][row group][k chunk (2)][row in group (8)][16 B]
+      // with block_rows (128, or 64 for the B halves of the CTA-pair kernel) rows x 32 bytes per block
+      const int rb = r / block_rows, ri = r - rb * block_rows;
+      const size_t blk = ((size_t)rb * (KP >> 5) + (k >> 5)) * NS + s;
+      const int in_blk = (((ri >> 3) * 2 + ((k & 31) >> 4)) * 8 + (ri & 7)) * 16 + (k & 15);
+      out[blk * (size_t)(block_rows * OZ_KB) + in_blk] = (unsigned char)(int)dg;  // two's complement byte for s = 0
       v = (v - dg) * 256.0;
     }
   }
@@ -539,6 +849,7 @@ int ensure_ozaki_attr(int* n_sm) {
   if (dev < 0 || dev >= 64) dev = 0;
   if (!done_for_device[dev]) {
     DKG_CUDA_OK(cudaFuncSetAttribute(ozaki_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+    DKG_CUDA_OK(cudaFuncSetAttribute(ozaki_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZP_SMEM));
     DKG_CUDA_OK(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
     done_for_device[dev] = 1;
   }
@@ -548,17 +859,34 @@ int ensure_ozaki_attr(int* n_sm) {
 
 }  // namespace
 
+// DKG_OZ_PAIR=1 selects the CTA-pair kernel for the default digit configuration.  Measured at c4 it
+// is no faster than the single-CTA kernel (0.751 vs 0.747 ms), i.e. the shared-memory operand
+// bandwidth is not what holds the tensor pipe at ~60 %, so the simpler kernel stays the default.
+static bool pair_mode(int NS, int NG) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DKG_OZ_PAIR");
+    v = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+  }
+  return v != 0 && NS == OZ_DEFAULT_DIGITS && NG == OZ_DEFAULT_DIAGONALS;
+}
+
+int ozaki_b_block_rows(int NS, int NG) {
+  if (NG == 0) NG = OZ_DEFAULT_DIAGONALS;
+  return pair_mode(NS, NG) ? 64 : 128;
+}
+
 int ozaki_kp(int K) { return round_up(K, 32); }
 
-size_t ozaki_digit_bytes(int rows_pad, int K, int NS) { return (size_t)NS * rows_pad * ozaki_kp(K); }
+size_t ozaki_digit_bytes(int rows_pad, int K, int NS) { return (size_t)NS * round_up(rows_pad, 256) * ozaki_kp(K); }
 
 // block-image digit planes (see slice_rows_kernel) and scale[rows] of the row-major matrix X[rows, K]
-int ozaki_slice_rows(const double* X, int ld, int rows, int K, int slice_rows, int NS, unsigned char* digits,
+int ozaki_slice_rows(const double* X, int ld, int rows, int K, int block_rows, int NS, unsigned char* digits,
                      double* scale, cudaStream_t st) {
   if (rows == 0) return DKG_OK;
   const int threads = 256;
-  (void)slice_rows;
-  slice_rows_kernel<<<ceil_div(rows * 32, threads), threads, 0, st>>>(X, ld, rows, K, ozaki_kp(K), NS, digits, scale);
+  slice_rows_kernel<<<ceil_div(rows * 32, threads), threads, 0, st>>>(X, ld, rows, K, ozaki_kp(K), NS, block_rows, digits,
+                                                                       scale);
   DKG_LAUNCH_CHECK();
   return DKG_OK;
 }
@@ -584,6 +912,30 @@ static int ozaki_launch(const unsigned char* a_digits, const double* sa, int M_p
     if (args.max_kps > OZ_MAX_KPS) args.max_kps = OZ_MAX_KPS;
     e = getenv("DKG_OZ_SLOTWAIT");
     args.slot_wait = e != nullptr ? atoi(e) : 1;
+  }
+  if (pair_mode(NS, NG)) {
+    const int tiles = ((args.m_tiles + 1) / 2) * args.n_tiles;
+    // how many CTA pairs can be co-resident (SMs pair up within a GPC; an odd SM is left over)
+    static int max_clusters[64] = {0};
+    int dev = 0;
+    DKG_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (max_clusters[dev] == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(n_sm & ~1);
+      cfg.blockDim = dim3(OZ_THREADS);
+      cfg.dynamicSmemBytes = OZP_SMEM;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, ozaki_pair_kernel, &cfg) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = n_sm / 2;
+      }
+      max_clusters[dev] = n;
+    }
+    const int clusters = tiles < max_clusters[dev] ? tiles : max_clusters[dev];
+    ozaki_pair_kernel<<<2 * clusters, OZ_THREADS, OZP_SMEM, st>>>(args);
+    DKG_LAUNCH_CHECK();
+    return DKG_OK;
   }
   const int tiles = args.m_tiles * args.n_tiles;
   const int grid = tiles < n_sm ? tiles : n_sm;

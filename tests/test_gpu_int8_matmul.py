@@ -48,3 +48,24 @@ def test_real_inputs_match_extended_precision(M, N, K):
     err = np.abs(got - truth) / bound
     ref = np.abs(A @ B.T - truth) / bound  # plain fp64 GEMM on the host
     assert err.max() < 4e-16, (err.max(), ref.max())
+
+
+def test_cta_pair_kernel_is_exact_too():
+    """DKG_OZ_PAIR=1 routes the default digit configuration through the cluster-of-2 kernel
+    (tcgen05.mma.cta_group::2); the mode is latched per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); from decoupledbo_b200 import _native;"
+        "g = torch.Generator().manual_seed(5);"
+        "A = torch.randint(-100, 100, (300, 416), generator=g).double();"
+        "B = torch.randint(-100, 100, (200, 416), generator=g).double();"
+        "assert torch.equal(_native.int8_matmul(A, B).cpu(), A @ B.T);"
+        "A = torch.randn(257, 400, generator=g).double(); B = torch.randn(129, 400, generator=g).double();"
+        "d = (_native.int8_matmul(A, B).cpu() - A @ B.T).abs().max().item(); assert d < 1e-12, d; print('ok')"
+    ) % os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "decoupled-kg_b200")
+    env = dict(os.environ, DKG_OZ_PAIR="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

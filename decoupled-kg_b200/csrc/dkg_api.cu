@@ -197,7 +197,7 @@ static int cov_rows(const ObjState& o, const dkg_plan* p, Workspace& w, const do
   if (o.Kxd_dig != nullptr) {
     DKG_TRY(ozaki_slice_rows(T, o.ldk, cc, o.n, 128, OZ_DEFAULT_DIGITS, w.T_dig, w.T_scale, st));
     return ozaki_cov(w.T_dig, w.T_scale, cc_pad, o.Kxd_dig, o.Kxd_scale, p->N_pad, o.n, OZ_DEFAULT_DIGITS,
-                     OZ_DEFAULT_DIAGONALS, ep, st);
+                     OZ_DEFAULT_DIAGONALS, /*b_nonneg=*/true, ep, st);  // stationary kernel values are positive
   }
   return gemm_cov(T, o.ldk, o.Kxd, p->N_pad, cc_pad, p->N_pad, o.n_pad, ep, st);
 }
@@ -467,7 +467,7 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
                                    w.T_scale, st)); }
         ProfScope ps(3, st);
         DKG_TRY(ozaki_store(w.T_dig, w.T_scale, cc_pad, ot.Kxd_dig, ot.Kxd_scale, p->N_pad, ot.n, OZ_DEFAULT_DIGITS,
-                            OZ_DEFAULT_DIAGONALS, w.Z, p->ldz, cc, N, st));
+                            OZ_DEFAULT_DIAGONALS, /*b_nonneg=*/true, w.Z, p->ldz, cc, N, st));
       } else {
         ProfScope ps(3, st);
         DKG_TRY(cov_rows(ot, p, w, w.T + (size_t)c0 * p->ldk, cc, cc_pad, ep, st));
@@ -751,13 +751,22 @@ int dkg_int8_matmul_dev(const double* A_dev, int32_t lda, const double* Bt_dev, 
   if (rc == DKG_OK) rc = dev_alloc(&sb, (size_t)N_pad);
   if (rc == DKG_OK) rc = ozaki_slice_rows(A_dev, lda, M, K, 128, n_digits, da, sa, st);
   if (rc == DKG_OK) rc = ozaki_slice_rows(Bt_dev, ldb, N, K, ozaki_b_block_rows(n_digits, n_diagonals), n_digits, db, sb, st);
-  if (rc == DKG_OK) rc = ozaki_store(da, sa, M_pad, db, sb, N_pad, K, n_digits, n_diagonals, D_dev, ldd, M, N, st);
+  int* neg_dev = nullptr;
+  int neg = 1;
+  if (rc == DKG_OK) rc = dev_alloc(&neg_dev, 1);
+  if (rc == DKG_OK) rc = ozaki_any_negative(Bt_dev, ldb, N, K, neg_dev, st);
+  if (rc == DKG_OK) {
+    cudaMemcpyAsync(&neg, neg_dev, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+  }
+  if (rc == DKG_OK)
+    rc = ozaki_store(da, sa, M_pad, db, sb, N_pad, K, n_digits, n_diagonals, /*b_nonneg=*/neg == 0, D_dev, ldd, M, N, st);
   cudaError_t e = cudaStreamSynchronize(st);
   if (rc == DKG_OK && e != cudaSuccess) {
     set_error("dkg_int8_matmul_dev: %s", cudaGetErrorString(e));
     rc = DKG_ECUDA;
   }
-  dev_free(da); dev_free(db); dev_free(sa); dev_free(sb);
+  dev_free(da); dev_free(db); dev_free(sa); dev_free(sb); dev_free(neg_dev);
   return rc;
 }
 

@@ -56,10 +56,14 @@ int ozaki_b_block_rows(int NS, int NG);
 int ozaki_slice_rows(const double* X, int ld, int rows, int K, int block_rows, int NS, unsigned char* digits,
                      double* scale, cudaStream_t st);
 int ozaki_cov(const unsigned char* a_digits, const double* sa, int M_pad, const unsigned char* b_digits,
-              const double* sb, int N_pad, int K, int NS, int NG, const CovEpilogue& ep, cudaStream_t st);
+              const double* sb, int N_pad, int K, int NS, int NG, bool b_nonneg, const CovEpilogue& ep,
+              cudaStream_t st);
 int ozaki_store(const unsigned char* a_digits, const double* sa, int M_pad, const unsigned char* b_digits,
-                const double* sb, int N_pad, int K, int NS, int NG, double* D, int ldd, int M, int N,
-                cudaStream_t st);
+                const double* sb, int N_pad, int K, int NS, int NG, bool b_nonneg, double* D, int ldd, int M,
+                int N, cudaStream_t st);
+// b_nonneg: every entry of the B operand is >= 0 (true for kernel values), which lets all its digit planes be
+// multiplied as UINT8 and pairs of them be merged into N = 256 instructions
+int ozaki_any_negative(const double* X, int ld, int rows, int cols, int* flag_dev, cudaStream_t st);
 
 // ---- dkg_forward.cu --------------------------------------------------------------------------
 struct XprepArgs {

@@ -76,6 +76,8 @@ struct OzakiArgs {
   int M, N;           // valid rows / cols (store mode)
   int max_kps;        // k blocks per stage (tuning knob)
   int slot_wait;      // wait per accumulator slot (1) or for all slots before the first MMA (0)
+  int b_unsigned;     // every B digit plane is non-negative (kernel values): enables the merged N = 256 MMAs
+  int dbg;            // measurement only: 1 = no operand copies (MMAs run on stale smem), 2 = no TMEM drain
 };
 
 __device__ __forceinline__ unsigned s_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -146,8 +148,8 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
   return d;
 }
 // c_format S32 (2) | a_format | b_format (1 = signed, 0 = unsigned) | K-major both | N >> 3 | M >> 4
-__device__ __forceinline__ unsigned umma_idesc(int a_signed, int b_signed) {
-  return (2u << 4) | ((unsigned)a_signed << 7) | ((unsigned)b_signed << 10) | ((unsigned)(OZ_BN >> 3) << 17) |
+__device__ __forceinline__ unsigned umma_idesc(int a_signed, int b_signed, int n = OZ_BN) {
+  return (2u << 4) | ((unsigned)a_signed << 7) | ((unsigned)b_signed << 10) | ((unsigned)(n >> 3) << 17) |
          ((unsigned)(OZ_BM >> 4) << 24);
 }
 
@@ -172,33 +174,55 @@ __device__ __forceinline__ double i32_to_f64(int v) {
 // diagonal g_hi - a.  On the first k block of a pass the issuing thread waits per slot until the
 // epilogue has drained it (so the drain of the previous pass overlaps the first MMAs), on the last
 // one it publishes each slot as soon as its MMAs are queued.
-template <int NS, int NG, int P, bool FIRST, bool LAST>
+template <int NS, int NG, int P, bool FIRST, bool LAST, bool MERGE>
 __device__ __forceinline__ void issue_pass_k(unsigned tmem_base, unsigned long long base, unsigned long long* tfull,
-                                             unsigned long long* tempty, unsigned par, bool slot_wait) {
+                                             unsigned long long* tempty, unsigned par) {
   constexpr int g_hi = NG - 1 - P * OZ_ACC;
   constexpr int g_lo = g_hi - OZ_ACC + 1 > 0 ? g_hi - OZ_ACC + 1 : 0;
   constexpr int nd = (g_hi < NS - 1 ? g_hi : NS - 1) + 1;  // digits 0 .. nd-1 of both operands are staged
-  (void)slot_wait;
+  // accumulator slot a holds the diagonal g_lo + a
   if (FIRST) {
 #pragma unroll
     for (int a = 0; a < OZ_ACC; ++a) bar_wait(&tempty[a], par ^ 1);
     tc_fence_after();
   }
-  // round-robin over the accumulator slots: consecutive MMAs never accumulate into the same slot, so the
-  // read-modify-write latency of a 64-cycle N = 128 MMA on its TMEM accumulator is not exposed
+  if (MERGE && !FIRST) {
+    // B digit planes are all unsigned here, so for a fixed A digit i the products with two
+    // consecutive B digits j, j+1 (diagonals i+j, i+j+1 = adjacent slots; the two digit blocks are
+    // adjacent in the stage) go out as ONE M128 N256 K32 instruction: 19 instead of 34 MMAs per
+    // k block.  The tensor pipe needs ~98 cycles per N = 128 instruction where the arithmetic
+    // takes 64 (measured with operand copies and TMEM drains switched off), i.e. there is a
+    // fixed cost per instruction that the wider shape amortises.
 #pragma unroll
-  for (int t = 0; t < NS; ++t) {
+    for (int i = 0; i < NS; ++i) {
+      const int jlo = g_lo - i > 0 ? g_lo - i : 0, jhi = g_hi - i < NS - 1 ? g_hi - i : NS - 1;
 #pragma unroll
-    for (int a = 0; a < OZ_ACC; ++a) {
-      const int g = g_hi - a;
-      if (g >= g_lo) {
-        const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
-        const int i = ilo + t;
-        if (i <= ihi) {
-          const int j = g - i;
-          umma_i8(tmem_base + (unsigned)(a * OZ_BN), base + (unsigned long long)((i * OZ_BLK_BYTES) >> 4),
-                  base + (unsigned long long)(((nd + j) * OZ_BLK_BYTES) >> 4), umma_idesc(i == 0, j == 0),
-                  (t > 0 || !FIRST) ? 1u : 0u);
+      for (int t = 0; t < (NS + 1) / 2; ++t) {
+        const int j = jlo + 2 * t;
+        if (j <= jhi) {
+          const bool wide = j + 1 <= jhi;
+          umma_i8(tmem_base + (unsigned)((i + j - g_lo) * OZ_BN), base + (unsigned long long)((i * OZ_BLK_BYTES) >> 4),
+                  base + (unsigned long long)(((nd + j) * OZ_BLK_BYTES) >> 4), umma_idesc(i == 0, 0, wide ? 2 * OZ_BN : OZ_BN),
+                  1u);
+        }
+      }
+    }
+  } else {
+    // one N = 128 instruction per digit pair, round-robin over the slots
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+#pragma unroll
+      for (int a = 0; a < OZ_ACC; ++a) {
+        const int g = g_lo + a;
+        if (g <= g_hi) {
+          const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
+          const int i = ilo + t;
+          if (i <= ihi) {
+            const int j = g - i;
+            umma_i8(tmem_base + (unsigned)(a * OZ_BN), base + (unsigned long long)((i * OZ_BLK_BYTES) >> 4),
+                    base + (unsigned long long)(((nd + j) * OZ_BLK_BYTES) >> 4), umma_idesc(i == 0, MERGE ? 0 : j == 0),
+                    (t > 0 || !FIRST) ? 1u : 0u);
+          }
         }
       }
     }
@@ -211,17 +235,23 @@ __device__ __forceinline__ void issue_pass_k(unsigned tmem_base, unsigned long l
 
 // (the k block position is a template parameter so that the steady-state instantiation is a
 // straight run of MMAs whose descriptors stay in uniform registers)
+template <int NS, int NG, int P, bool MERGE>
+__device__ __forceinline__ void issue_pass_m(unsigned tmem_base, unsigned long long base, bool first_k, bool last_k,
+                                             unsigned long long* tfull, unsigned long long* tempty, unsigned par) {
+  if (first_k) {
+    if (last_k) issue_pass_k<NS, NG, P, true, true, MERGE>(tmem_base, base, tfull, tempty, par);
+    else issue_pass_k<NS, NG, P, true, false, MERGE>(tmem_base, base, tfull, tempty, par);
+  } else {
+    if (last_k) issue_pass_k<NS, NG, P, false, true, MERGE>(tmem_base, base, tfull, tempty, par);
+    else issue_pass_k<NS, NG, P, false, false, MERGE>(tmem_base, base, tfull, tempty, par);
+  }
+}
 template <int NS, int NG, int P>
 __device__ __forceinline__ void issue_pass(unsigned tmem_base, unsigned long long base, bool first_k, bool last_k,
                                            unsigned long long* tfull, unsigned long long* tempty, unsigned par,
-                                           bool slot_wait) {
-  if (first_k) {
-    if (last_k) issue_pass_k<NS, NG, P, true, true>(tmem_base, base, tfull, tempty, par, slot_wait);
-    else issue_pass_k<NS, NG, P, true, false>(tmem_base, base, tfull, tempty, par, slot_wait);
-  } else {
-    if (last_k) issue_pass_k<NS, NG, P, false, true>(tmem_base, base, tfull, tempty, par, slot_wait);
-    else issue_pass_k<NS, NG, P, false, false>(tmem_base, base, tfull, tempty, par, slot_wait);
-  }
+                                           bool merge) {
+  if (merge) issue_pass_m<NS, NG, P, true>(tmem_base, base, first_k, last_k, tfull, tempty, par);
+  else issue_pass_m<NS, NG, P, false>(tmem_base, base, first_k, last_k, tfull, tempty, par);
 }
 
 // Final epilogue of one warp's 32 x 32 block in covariance mode: apply the row / column scales,
@@ -335,8 +365,8 @@ ozaki_kernel(const OzakiArgs args) {
       const int nd = (g_hi < NS - 1 ? g_hi : NS - 1) + 1;
       int ne = 0;
       for (int a = 0; a < OZ_ACC; ++a) {
-        const int g = g_hi - a;
-        if (g >= g_lo) {
+        const int g = g_lo + a;
+        if (g <= g_hi) {
           const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
           for (int i = ilo; i <= ihi; ++i, ++ne) {
             const int j = g - i;
@@ -363,7 +393,7 @@ ozaki_kernel(const OzakiArgs args) {
   // configuration, which keeps the short stages of that pass ahead of the copy latency).
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && lane == 0 && !(args.dbg & 1)) {
       // ===== bulk-copy producer =====
       int s = 0;
       unsigned ph = 0;
@@ -407,7 +437,7 @@ ozaki_kernel(const OzakiArgs args) {
           const int* slotend = s_slotend + p * OZ_ACC;
           for (int kb = 0; kb < KB; kb += kps) {
             const int nk = KB - kb < kps ? KB - kb : kps;
-            bar_wait(&full[s], ph);
+            if (!(args.dbg & 1)) bar_wait(&full[s], ph);
             tc_fence_after();
             const unsigned st_addr = s_u32(s_stage + (size_t)s * OZ_STAGE_CAP);
             if (elect_one()) {
@@ -419,9 +449,9 @@ ozaki_kernel(const OzakiArgs args) {
                 // (~10 uniform-datapath instructions per MMA; through the table the issuing thread
                 // needed ~23 and the tensor pipe waited on it)
                 if (p == 0)
-                  issue_pass<OZ_DEFAULT_DIGITS, OZ_DEFAULT_DIAGONALS, 0>(tmem_base, base, first_k, last_k, tfull, tempty, par, args.slot_wait != 0);
+                  issue_pass<OZ_DEFAULT_DIGITS, OZ_DEFAULT_DIAGONALS, 0>(tmem_base, base, first_k, last_k, tfull, tempty, par, args.b_unsigned != 0);
                 else
-                  issue_pass<OZ_DEFAULT_DIGITS, OZ_DEFAULT_DIAGONALS, 1>(tmem_base, base, first_k, last_k, tfull, tempty, par, args.slot_wait != 0);
+                  issue_pass<OZ_DEFAULT_DIGITS, OZ_DEFAULT_DIAGONALS, 1>(tmem_base, base, first_k, last_k, tfull, tempty, par, args.b_unsigned != 0);
               } else {
                 int e = 0;
                 for (int a = 0; a < OZ_ACC; ++a) {
@@ -437,7 +467,7 @@ ozaki_kernel(const OzakiArgs args) {
                 }
               }
             }
-            umma_commit(&empty[s]);
+            if (!(args.dbg & 1)) umma_commit(&empty[s]);
             }
             __syncwarp();
             if (++s == OZ_STAGES) { s = 0; ph ^= 1; }
@@ -466,20 +496,22 @@ ozaki_kernel(const OzakiArgs args) {
         double w = 1.0;
         for (int g = 0; g < g_hi; ++g) w *= 0.00390625;  // 256^-g_hi
         const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + cg * 32;
-        for (int a = 0; a < OZ_ACC; ++a) {
+        for (int a = OZ_ACC - 1; a >= 0; --a) {  // slot a = diagonal g_lo + a; smallest weights first
           bar_wait(&tfull[a], par);
           tc_fence_after();
-          if (g_hi - a >= g_lo) {
-            int r[32];
-            OZ_TMEM_LD32(r, taddr + (unsigned)(a * OZ_BN));
-            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+          if (g_lo + a <= g_hi) {
+            if (!(args.dbg & 2)) {
+              int r[32];
+              OZ_TMEM_LD32(r, taddr + (unsigned)(a * OZ_BN));
+              asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-            for (int c = 0; c < 32; ++c) acc[c] = fma(i32_to_f64(r[c]), w, acc[c]);
+              for (int c = 0; c < 32; ++c) acc[c] = fma(i32_to_f64(r[c]), w, acc[c]);
+            }
+            w *= 256.0;
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) bar_arrive(&tempty[a]);
-          w *= 256.0;
         }
       }
       // ---- final epilogue ----
@@ -876,6 +908,22 @@ int ozaki_b_block_rows(int NS, int NG) {
   return pair_mode(NS, NG) ? 64 : 128;
 }
 
+__global__ void any_negative_kernel(const double* __restrict__ X, int ld, int rows, int cols, int* __restrict__ flag) {
+  const long long total = (long long)rows * cols;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / cols), c = (int)(e - (long long)r * cols);
+    if (X[(size_t)r * ld + c] < 0.0) *flag = 1;
+  }
+}
+
+// flag_dev[0] = 1 if any entry of X[rows, cols] is negative (flag_dev must be zero on entry)
+int ozaki_any_negative(const double* X, int ld, int rows, int cols, int* flag_dev, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return DKG_OK;
+  any_negative_kernel<<<296, 256, 0, st>>>(X, ld, rows, cols, flag_dev);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
 int ozaki_kp(int K) { return round_up(K, 32); }
 
 size_t ozaki_digit_bytes(int rows_pad, int K, int NS) { return (size_t)NS * round_up(rows_pad, 256) * ozaki_kp(K); }
@@ -912,6 +960,10 @@ static int ozaki_launch(const unsigned char* a_digits, const double* sa, int M_p
     if (args.max_kps > OZ_MAX_KPS) args.max_kps = OZ_MAX_KPS;
     e = getenv("DKG_OZ_SLOTWAIT");
     args.slot_wait = e != nullptr ? atoi(e) : 1;
+    e = getenv("DKG_OZ_DBG");
+    args.dbg = e != nullptr ? atoi(e) : 0;
+    e = getenv("DKG_OZ_MERGE");
+    if (e != nullptr && atoi(e) == 0) args.b_unsigned = 0;
   }
   if (pair_mode(NS, NG)) {
     const int tiles = ((args.m_tiles + 1) / 2) * args.n_tiles;
@@ -946,8 +998,10 @@ static int ozaki_launch(const unsigned char* a_digits, const double* sa, int M_p
 
 // Z = (k(x_c, xd_n) - A B^T) ystd^2 / sd from digit planes (see the file header)
 int ozaki_cov(const unsigned char* a_digits, const double* sa, int M_pad, const unsigned char* b_digits,
-              const double* sb, int N_pad, int K, int NS, int NG, const CovEpilogue& ep, cudaStream_t st) {
+              const double* sb, int N_pad, int K, int NS, int NG, bool b_nonneg, const CovEpilogue& ep,
+              cudaStream_t st) {
   OzakiArgs args{};
+  args.b_unsigned = b_nonneg ? 1 : 0;
   args.cov = 1;
   args.ep = ep;
   return ozaki_launch(a_digits, sa, M_pad, b_digits, sb, N_pad, K, NS, NG, args, st);
@@ -955,9 +1009,10 @@ int ozaki_cov(const unsigned char* a_digits, const double* sa, int M_pad, const 
 
 // D[M, N] = A B^T from digit planes (test hook)
 int ozaki_store(const unsigned char* a_digits, const double* sa, int M_pad, const unsigned char* b_digits,
-                const double* sb, int N_pad, int K, int NS, int NG, double* D, int ldd, int M, int N,
-                cudaStream_t st) {
+                const double* sb, int N_pad, int K, int NS, int NG, bool b_nonneg, double* D, int ldd, int M,
+                int N, cudaStream_t st) {
   OzakiArgs args{};
+  args.b_unsigned = b_nonneg ? 1 : 0;
   args.cov = 0;
   args.D = D;
   args.ldd = ldd;

@@ -75,7 +75,7 @@ struct Workspace {
   int last_C = 0;
 };
 
-constexpr int SURV_CAP = 1024;  // survivors per (candidate, scalarisation) before the slow path
+constexpr int SURV_CAP = 2048;  // survivors per (candidate, scalarisation) before the slow path
 constexpr int HULL_CAP = 64;    // hull vertices recorded per (candidate, scalarisation)
 
 }  // namespace dkg

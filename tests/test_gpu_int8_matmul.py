@@ -69,3 +69,19 @@ def test_cta_pair_kernel_is_exact_too():
     env = dict(os.environ, DKG_OZ_PAIR="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (300, 200, 416), (257, 129, 800)])
+def test_nonnegative_b_takes_the_merged_n256_path_and_stays_exact(M, N, K):
+    """With B >= 0 (as for kernel values) all B digit planes are unsigned and pairs of them are issued
+    as single N = 256 MMAs; integers of up to 3 digits must still come out bit-exact."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randint(-(2**20), 2**20, (M, K), generator=g).double()
+    B = torch.randint(0, 2**20, (N, K), generator=g).double()
+    want = A @ B.T  # |sum| < 2^50: exact in fp64
+    assert torch.equal(_mm(A, B), want)
+    Br = torch.rand(N, K, generator=g, dtype=torch.double)
+    Ar = torch.randn(M, K, generator=g, dtype=torch.double)
+    truth = (Ar.numpy().astype(np.longdouble) @ Br.numpy().astype(np.longdouble).T).astype(np.float64)
+    err = np.abs(_mm(Ar, Br).numpy() - truth).max() / (np.abs(Ar.numpy()).max() * K)
+    assert err < 4e-16, err

@@ -718,8 +718,15 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
   };
 
   HullResult r;
+  int staged = 0;
   if (total <= STAGE_CAP) {
-    r = warp_march(total, fetch_global, rec);
+    // short list: stage it as it is (one march instantiation for both branches keeps this kernel's
+    // code, and its instruction-cache footprint, a third smaller)
+    for (int k = lane; k < total; k += 32) {
+      const Line L = fetch_global(k);
+      s_a[warp][k] = L.a; s_b[warp][k] = L.b; s_i[warp][k] = L.idx;
+    }
+    staged = total;
   } else {
     // ---- one QuickHull-style refinement over the list, compacting into shared memory ----
     // chain in the (b, a) plane: P (min slope), T (max intercept), Q (max slope) plus the
@@ -763,7 +770,7 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
       }
     }
     // the staged list starts with the chain vertices themselves
-    int staged = 0;
+    staged = 0;
     if (lane == 0) {
       const Line vs[5] = {P, F1, T, F2, Q};
       for (int v = 0; v < 5; ++v)
@@ -798,15 +805,15 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
       if (lane == 0) sc.ovf_sets[atomicAdd(sc.ovf_count, 1)] = (int)set;
       return;
     }
-    __syncwarp();
-    auto fetch_smem = [&](int k) -> Line {
-      Line L;
-      L.a = s_a[warp][k]; L.b = s_b[warp][k]; L.idx = s_i[warp][k];
-      L.ref = ref_index(lb, L.idx);
-      return L;
-    };
-    r = warp_march(staged, fetch_smem, rec);
   }
+  __syncwarp();
+  auto fetch_smem = [&](int k) -> Line {
+    Line L;
+    L.a = s_a[warp][k]; L.b = s_b[warp][k]; L.idx = s_i[warp][k];
+    L.ref = ref_index(lb, L.idx);
+    return L;
+  };
+  r = warp_march(staged, fetch_smem, rec);
   if (lane == 0) {
     finish_set(lb, out, set, s, r.E, r.h);
     if (sc.stats) {

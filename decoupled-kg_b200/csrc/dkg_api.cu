@@ -68,7 +68,7 @@ static void dev_free(T*& p) {
 static void free_workspace(Workspace& w) {
   dev_free(w.X); dev_free(w.kg); dev_free(w.dX); dev_free(w.KX); dev_free(w.T); dev_free(w.R); dev_free(w.T_dig); dev_free(w.T_scale); dev_free(w.var);
   dev_free(w.sd); dev_free(w.zown); dev_free(w.Xs); dev_free(w.a_new); dev_free(w.kg_terms);
-  dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } { double4* t = (double4*)w.chain; dev_free(t); w.chain = nullptr; } dev_free(w.far); dev_free(w.ovf_sets); dev_free(w.ovf_count);
+  dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } { double4* t = (double4*)w.chain; dev_free(t); w.chain = nullptr; } { float4* t = (float4*)w.chain32; dev_free(t); w.chain32 = nullptr; } { double4* t = (double4*)w.chainv; dev_free(t); w.chainv = nullptr; } dev_free(w.far); dev_free(w.ovf_sets); dev_free(w.ovf_count);
   dev_free(w.hull_cnt); dev_free(w.hull_idx); dev_free(w.hull_p); dev_free(w.hull_q);
   dev_free(w.amax_is_new); dev_free(w.stats); dev_free(w.sdj); dev_free(w.Zc);
   for (int m = 0; m < MAX_M; ++m) { dev_free(w.KXm[m]); dev_free(w.Tm[m]); dev_free(w.varlat[m]); dev_free(w.COVm[m]); }
@@ -137,6 +137,8 @@ static int ensure_workspace(dkg_plan* p, int C) {
   { SurvEntry* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * SURV_CAP, false)); w.surv = t; }
   DKG_TRY(dev_alloc(&w.far, (size_t)chunk * S * 2));
   { double4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S, false)); w.chain = t; }
+  if (!coupled) { float4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * 2, false)); w.chain32 = t; }
+  if (!coupled) { double4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * 2, false)); w.chainv = t; }
   DKG_TRY(dev_alloc(&w.ovf_sets, (size_t)chunk * S, false));
   DKG_TRY(dev_alloc(&w.ovf_count, (size_t)1));
   DKG_TRY(dev_alloc(&w.hull_cnt, (size_t)chunk * S));
@@ -159,7 +161,7 @@ static void destroy_plan(dkg_plan* p) {
     dev_free(o.BT); dev_free(o.xd_s);
   }
   dev_free(p->W); dev_free(p->wt); dev_free(p->xd); dev_free(p->alpha_all);
-  dev_free(p->mu_disc); dev_free(p->A0); dev_free(p->A0max); dev_free(p->A0arg);
+  dev_free(p->mu_disc); dev_free(p->A0); dev_free(p->A0f); dev_free(p->A0max); dev_free(p->A0arg);
   free_workspace(p->ws);
   delete p;
 }
@@ -355,6 +357,7 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
     rc = dev_alloc(&p->W, (size_t)S * M);
     if (rc == DKG_OK) rc = dev_alloc(&p->wt, (size_t)S);
     if (rc == DKG_OK) rc = dev_alloc(&p->A0, (size_t)S * p->N_pad);
+    if (rc == DKG_OK) rc = dev_alloc(&p->A0f, (size_t)S * p->N_pad);
     if (rc == DKG_OK) rc = dev_alloc(&p->A0max, (size_t)S);
     if (rc == DKG_OK) rc = dev_alloc(&p->A0arg, (size_t)S);
     if (rc == DKG_OK) {
@@ -363,7 +366,7 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
       cudaMemcpyAsync(p->W, p->W_host, sizeof(double) * S * M, cudaMemcpyHostToDevice, st);
       cudaMemcpyAsync(p->wt, wt_host, sizeof(double) * S, cudaMemcpyHostToDevice, st);
       cudaStreamSynchronize(st);  // wt_host is a stack buffer
-      rc = build_a0(p->mu_disc, N, M, p->W, S, p->A0, p->N_pad, p->A0max, p->A0arg, st);
+      rc = build_a0(p->mu_disc, N, M, p->W, S, p->A0, p->A0f, p->N_pad, p->A0max, p->A0arg, st);
     }
   }
   cudaStreamSynchronize(st);
@@ -477,6 +480,7 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     LineBatch lb;
     lb.Z = w.Z; lb.ldz = p->ldz;
     lb.A = p->A0; lb.a_sc = 0; lb.a_sj = p->N_pad;
+    lb.A32 = p->A0f;
     lb.a_own = w.a_new + (size_t)c0 * S;
     lb.wt = p->wt;
     lb.Amax = p->A0max; lb.Aarg = p->A0arg; lb.am_sc = 0;
@@ -484,6 +488,8 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     EmaxScratch sc;
     sc.zst = w.zst; sc.zarg = w.zarg; sc.surv_cnt = w.surv_cnt; sc.surv = (SurvEntry*)w.surv;
     sc.ovf_sets = w.ovf_sets; sc.ovf_count = w.ovf_count; sc.far = w.far; sc.chain = (double4*)w.chain;
+    sc.chain32 = (float4*)w.chain32;
+    sc.chainv = (double4*)w.chainv;
     sc.stats = w.stats;
     DKG_CUDA_OK(cudaMemsetAsync(w.surv_cnt, 0, sizeof(int) * (size_t)cc * S, st));
     DKG_CUDA_OK(cudaMemsetAsync(w.far, 0, sizeof(unsigned long long) * (size_t)cc * S * 2, st));
@@ -896,6 +902,7 @@ int dkg_plan_stats(dkg_plan* plan, int64_t* out5_host /* [8] */, void* stream) {
     DKG_CUDA_OK(cudaMemcpyAsync(h, plan->ws.stats, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     DKG_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
   }
+  if (getenv("DKG_DEBUG_STATS")) fprintf(stderr, "[dkg] sets with a truncated survivor list: %lld\n", h[0]);
   out5_host[0] = plan->ws.last_C;
   for (int k = 1; k < 8; ++k) out5_host[k] = h[k];
   // [7]: 1 when the covariance contraction of this plan runs on the int8 tensor cores

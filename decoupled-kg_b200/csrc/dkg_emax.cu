@@ -26,12 +26,15 @@
 #include "dkg_emax.cuh"
 
 #include <cstdlib>
+#include <cstring>
 
 namespace dkg {
 
 constexpr int E_THREADS = 256;
 constexpr double SHORTCUT_TOL = 1e-9;  // discretekg.py:363
 constexpr int STAGE_CAP = 128;         // lines a warp marches over from registers
+constexpr int CHAIN_MAXV = 32;         // vertices of a warp's refinement chain (one lane each)
+constexpr int HULL_LEVELS = 5;         // refinement passes of the warp kernel before a set is queued
 constexpr double EPS128 = 2.84217094304040074e-14;  // 128 * 2^-52
 
 // ------------------------------------------------------------------------------------------
@@ -75,10 +78,12 @@ __device__ void block_arg_reduce(double& v, int& i, double* s_v, int* s_i) {
     }
 }
 
-__device__ double4 chain_params(const LineBatch& lb, const EmaxScratch& sc, int c, int j);
+struct ChainMag { double amag, zmag; };  // magnitudes of the intercepts / slope coordinates on the chain
+__device__ double4 chain_params(const LineBatch& lb, const EmaxScratch& sc, int c, int j, ChainMag* mag,
+                                double4* verts = nullptr);
+__device__ float4 chord32(double c, double m, const ChainMag& mag);
 
-// one CTA per row: min / max (with first index) of the slope row; optionally the max intercept;
-// then the chord-chain parameters of the row's S sets (consumed by the filter kernel)
+// one CTA per row: min / max (with first index) of the slope row; optionally the max intercept
 template <int D>
 __global__ void __launch_bounds__(E_THREADS)
 zstat_kernel(LineBatch lb, EmaxScratch sc, double* __restrict__ zst, int* __restrict__ zarg,
@@ -145,9 +150,27 @@ zstat_kernel(LineBatch lb, EmaxScratch sc, double* __restrict__ zst, int* __rest
       aarg_out[c] = ai;
     }
   }
-  __syncthreads();  // the row statistics written above are read back through global memory
-  for (int j = threadIdx.x; j < lb.S; j += blockDim.x)
-    sc.chain[(size_t)c * lb.S + j] = chain_params(lb, sc, c, j);
+}
+
+// chord-chain parameters of every set (one thread per set), consumed by the filter kernels: the fp64
+// chain, its conservatively rounded float image and the chord end points (second-level chain)
+__global__ void __launch_bounds__(E_THREADS)
+chain_kernel(LineBatch lb, EmaxScratch sc) {
+  const size_t set = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (set >= (size_t)lb.C * lb.S) return;
+  const int c = (int)(set / lb.S), j = (int)(set - (size_t)c * lb.S);
+  ChainMag mag;
+  double4 verts[2];
+  const double4 par = chain_params(lb, sc, c, j, &mag, verts);
+  sc.chain[set] = par;
+  if (sc.chainv != nullptr) {
+    sc.chainv[set * 2 + 0] = verts[0];
+    sc.chainv[set * 2 + 1] = verts[1];
+  }
+  if (sc.chain32 != nullptr) {
+    sc.chain32[set * 2 + 0] = chord32(par.x, par.y, mag);
+    sc.chain32[set * 2 + 1] = chord32(par.z, par.w, mag);
+  }
 }
 
 int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int* aarg_out,
@@ -168,6 +191,9 @@ int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int
     default: DKG_ZSTAT(8); break;
   }
 #undef DKG_ZSTAT
+  DKG_LAUNCH_CHECK();
+  const long long sets = (long long)lb.C * lb.S;
+  chain_kernel<<<(unsigned)((sets + E_THREADS - 1) / E_THREADS), E_THREADS, 0, st>>>(lb, sc);
   DKG_LAUNCH_CHECK();
   return DKG_OK;
 }
@@ -223,9 +249,12 @@ __device__ __forceinline__ SetInfo set_info(const LineBatch& lb, const EmaxScrat
 // (left chord P->T and right chord T->Q in the dual plane; the chain is concave because T has
 // the maximum intercept).  A slack of 128 eps of every magnitude entering c + m*z keeps all
 // lines within rounding of the chain: extra survivors cost time, never accuracy.
-__device__ double4 chain_params(const LineBatch& lb, const EmaxScratch& sc, int c, int j) {
+__device__ double4 chain_params(const LineBatch& lb, const EmaxScratch& sc, int c, int j, ChainMag* mag,
+                                double4* verts) {
   const double inf = INFINITY;
   const SetInfo s = set_info(lb, sc, c, j);
+  if (mag != nullptr) mag->amag = mag->zmag = 0.0;
+  if (verts != nullptr) verts[0] = verts[1] = make_double4(0.0, 0.0, 0.0, 0.0);
   if (s.shortcut) return make_double4(inf, 0.0, inf, 0.0);
   const double sgn = s.w < 0.0 ? -1.0 : 1.0;  // effective slope coordinate z' = sgn * z
   const int iP = sgn > 0 ? s.iP : s.iQ;
@@ -236,6 +265,14 @@ __device__ double4 chain_params(const LineBatch& lb, const EmaxScratch& sc, int 
   const double zT = sgn * lb.Z[(size_t)c * lb.ldz + s.iT];
   const double aP = line_intercept(lb, c, j, iP);
   const double aQ = line_intercept(lb, c, j, iQ);
+  if (mag != nullptr) {
+    mag->amag = fmax(fabs(aT), fmax(fabs(aP), fabs(aQ)));
+    mag->zmag = fmax(fabs(s.zmin), fabs(s.zmax));
+  }
+  if (verts != nullptr) {  // chord end points in the RAW slope coordinate: (z0, a0, z1, a1) per side
+    verts[0] = make_double4(sgn * zP, aP, sgn * zT, aT);
+    verts[1] = make_double4(sgn * zT, aT, sgn * zQ, aQ);
+  }
   double c1 = inf, m1 = 0.0, c2 = inf, m2 = 0.0;
   if (zT > zP) {
     m1 = (aT - aP) / (zT - zP);
@@ -250,6 +287,26 @@ __device__ double4 chain_params(const LineBatch& lb, const EmaxScratch& sc, int 
   return make_double4(c1, m1 * sgn, c2, m2 * sgn);
 }
 
+// Float image (m, m, c, c) of one chord for the fp32 filter, which keeps a line iff
+//   float(a) > fmaf(m32, float(z), c32)      (either chord).
+// Every line that passes the fp64 test  a > c + m z  must pass this one (extra survivors only cost
+// time).  Error budget, all relative to  mag = |c| + |m| zmag + amag  (|z| <= zmag on the row; a
+// true survivor has |a| <= amag because the concave chain runs between members of the set):
+// a, z, m rounded to nearest float (2^-24 each), c32 rounded DOWN, the float fma (2^-24 |t|):
+// together < 4.1 * 2^-24 mag.  c32 is lowered by 2^-21 mag = 8 * 2^-24 mag.  Sets whose magnitudes
+// leave the range where those float bounds hold get (0, 0, -inf, -inf): every line survives and
+// the exact overflow path takes the set.
+__device__ float4 chord32(double c, double m, const ChainMag& mag) {
+  if (c == INFINITY) return make_float4(0.f, 0.f, INFINITY, INFINITY);  // no chord / shortcut set
+  const double g = fabs(c) + fabs(m) * mag.zmag + mag.amag;
+  const bool ok = g > 1e-30 && g < 1e30 && fabs(m) < 1e30 && mag.zmag < 1e30 &&
+                  (mag.zmag + fabs(m)) <= g * 1e37;  // float denormal losses stay below the slack
+  if (!ok) return make_float4(0.f, 0.f, -INFINITY, -INFINITY);
+  const float cf = __double2float_rd(c - 4.76837158203125e-07 * g);  // 2^-21
+  const float mf = __double2float_rn(m);
+  return make_float4(mf, mf, cf, cf);
+}
+
 // Each CTA owns G candidates x (E_THREADS * R) lines; each thread keeps the slope coordinates of
 // its R lines for the G candidates in registers (G*R doubles), then walks the scalarisations:
 // per scalarisation it loads the chain parameters of the G sets once (shared-memory broadcast)
@@ -260,6 +317,8 @@ __device__ __forceinline__ unsigned long long pack_excess(double e, int n) {
   // chord is a valid chain vertex, so the float rounding is harmless
   return ((unsigned long long)__float_as_uint((float)e) << 32) | (unsigned)n;
 }
+
+
 
 // Survivors are first collected in a CTA-local shared-memory pool (shared atomics are ~30 cycles;
 // a global atomicAdd whose return value is needed stalls the warp for a full L2 round trip, and
@@ -413,6 +472,216 @@ filter_kernel(LineBatch lb, EmaxScratch sc) {
   }
 }
 
+// ---- fp32 variant (KG path: one intercept table shared by all candidates) --------------------
+// The same test in float arithmetic against the conservatively rounded chain (chord32): 64-bit
+// compares and FMAs run at half rate on the fp64 pipe, the float test issues as one packed FFMA2
+// per chord for two lines plus two FSETP and one predicated add per line.  Survivors are stored
+// from the fp64 tables as before, so the hull stage sees exact values; false positives (lines
+// within ~5e-7 of the chain) only lengthen the lists.  Each thread owns 4 CONSECUTIVE lines
+// (one 16-byte load of the float intercepts per scalarisation, two of the slope row per candidate).
+typedef unsigned long long u64;
+
+template <unsigned BIT>
+__device__ __forceinline__ unsigned pair_test32(unsigned mask, u64 mm1, u64 cc1, u64 mm2, u64 cc2, u64 zz,
+                                                float a0, float a1) {
+  asm("{\n"
+      ".reg .b64 t1, t2;\n .reg .f32 t1l, t1h, t2l, t2h;\n .reg .pred p, q;\n"
+      "fma.rn.f32x2 t1, %1, %5, %2;\n"
+      "fma.rn.f32x2 t2, %3, %5, %4;\n"
+      "mov.b64 {t1l, t1h}, t1;\n mov.b64 {t2l, t2h}, t2;\n"
+      "setp.gt.f32 p, %6, t1l;\n setp.gt.or.f32 p, %6, t2l, p;\n @p add.u32 %0, %0, %8;\n"
+      "setp.gt.f32 q, %7, t1h;\n setp.gt.or.f32 q, %7, t2h, q;\n @q add.u32 %0, %0, %9;\n"
+      "}"
+      : "+r"(mask)
+      : "l"(mm1), "l"(cc1), "l"(mm2), "l"(cc2), "l"(zz), "f"(a0), "f"(a1), "n"(BIT), "n"(BIT << 1));
+  return mask;
+}
+
+__device__ __forceinline__ u64 pack_f32x2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+
+// line through two members of a set as (c, m): t(z) = c + m z, lowered by the same 128-ulp slack as
+// the 3-point chain (the end points themselves pass the test  a > t)
+__device__ __forceinline__ double2 chord_through(double z0, double a0, double z1, double a1) {
+  const double m = (a1 - a0) / (z1 - z0);
+  const double slack = EPS128 * (fabs(a0) + fabs(a1) + fabs(m) * fmax(fabs(z0), fabs(z1)));
+  return make_double2(a0 - m * z0 - slack, m);
+}
+
+// Survivors are parked in a per-WARP shared-memory pool (position = ballot prefix, no atomics, no
+// CTA barrier) and written out by the warp itself: one global slot claim per survivor, all lanes in
+// flight at once, so the L2 round trip is paid per 32 survivors, not per survivor.
+constexpr int F32_THREADS = 128;
+constexpr int WPOOL = 256;
+
+// Before a parked line is stored it is re-tested, exactly (fp64), against a SECOND-LEVEL chain: pass A
+// records, per set and side, the parked line farthest above the 3-point chord (this CTA's lines
+// only -- any member of the set is a valid chain vertex; the choice only decides how tight the chain
+// is); pass B keeps a line only if it is above  P -> U -> T  (or  T -> V -> Q)  with U / V that
+// farthest line.  On smooth GP posteriors this removes ~3/4 of the stored survivors.  The same
+// per-side maxima seed the QuickHull refinement of the hull stage (sc.far).
+template <int G>
+__device__ __forceinline__ void flush_warp_pool(const LineBatch& lb, const EmaxScratch& sc, int2* pool,
+                                                int cnt, int c0, unsigned long long* s_far) {
+  __syncwarp();
+  const int S = lb.S;
+  for (int e = threadIdx.x & 31; e < cnt; e += 32) {  // pass A
+    const int2 it = pool[e];
+    const int setl = it.y;
+    const int j = setl / G, g = setl - j * G;
+    const int c = c0 + g;
+    const int n = it.x;
+    const double av = lb.A[a_base(lb, c, j) + n];
+    const double zv = lb.Z[(size_t)c * lb.ldz + n];
+    const double4 par = sc.chain[(size_t)c * S + j];
+    const double t1 = fma(par.y, zv, par.x), t2 = fma(par.w, zv, par.z);
+    const int side = t1 <= t2 ? 0 : 1;
+    const double ex = av - (side == 0 ? t1 : t2);
+    if (ex > 0.0) atomicMax(&s_far[2 * setl + side], pack_excess(ex, n));
+    pool[e].y = setl | (side << 30);
+  }
+  __syncwarp();
+  for (int e = threadIdx.x & 31; e < cnt; e += 32) {  // pass B
+    const int2 it = pool[e];
+    const int setl = it.y & 0x3fffffff, side = (it.y >> 30) & 1;
+    const int j = setl / G, g = setl - j * G;
+    const int c = c0 + g;
+    const size_t set = (size_t)c * S + j;
+    const int n = it.x;
+    const double av = lb.A[a_base(lb, c, j) + n];
+    const double zv = lb.Z[(size_t)c * lb.ldz + n];
+    const unsigned long long key = s_far[2 * setl + side];
+    if (sc.chainv != nullptr && key != 0ull) {
+      const int nu = (int)(key & 0xffffffffull);
+      const double au = lb.A[a_base(lb, c, j) + nu];
+      const double zu = lb.Z[(size_t)c * lb.ldz + nu];
+      const double4 v = sc.chainv[set * 2 + side];  // (z0, a0, z1, a1), raw slope coordinate
+      if ((zu - v.x) * (v.z - zu) > 0.0) {          // U strictly between the chord's end points
+        const double2 c0u = chord_through(v.x, v.y, zu, au), cu1 = chord_through(zu, au, v.z, v.w);
+        if (!((av > fma(c0u.y, zv, c0u.x)) | (av > fma(cu1.y, zv, cu1.x)))) continue;
+      }
+    }
+    const int pos = atomicAdd(&sc.surv_cnt[set], 1);
+    if (pos < SURV_CAP) {
+      SurvEntry en;
+      en.a = av; en.z = zv; en.idx = n; en.pad = 0;
+      sc.surv[set * SURV_CAP + pos] = en;
+    }
+  }
+  __syncwarp();
+}
+
+template <int G>
+__global__ void __launch_bounds__(F32_THREADS, 7)
+filter32_kernel(LineBatch lb, EmaxScratch sc) {
+  static_assert(G == 4, "bit layout below assumes 4 candidates x 4 lines");
+  extern __shared__ __align__(16) unsigned char e_smem[];
+  const int S = lb.S;
+  ulonglong2* s_p32 = reinterpret_cast<ulonglong2*>(e_smem);  // [S][G][2] (m,m | c,c) per chord
+  unsigned long long* s_far = reinterpret_cast<unsigned long long*>(s_p32 + 2 * G * S);  // [S*G][2]
+  int2* pool = reinterpret_cast<int2*>(s_far + 2 * G * S) + (threadIdx.x >> 5) * WPOOL;  // this warp's
+  const int c0 = blockIdx.y * G;
+  const ulonglong2* g_p32 = reinterpret_cast<const ulonglong2*>(sc.chain32);
+  const ulonglong2 none = make_ulonglong2(0ull, 0x7f8000007f800000ull);  // (0, 0, +inf, +inf)
+  for (int e = threadIdx.x; e < G * S; e += blockDim.x) {
+    const int j = e / G, g = e - j * G;
+    const int c = c0 + g;
+    const bool in = c < lb.C;
+    s_p32[2 * e] = in ? g_p32[((size_t)c * S + j) * 2] : none;
+    s_p32[2 * e + 1] = in ? g_p32[((size_t)c * S + j) * 2 + 1] : none;
+    s_far[2 * e] = 0ull;
+    s_far[2 * e + 1] = 0ull;
+  }
+  const int n0 = (blockIdx.x * F32_THREADS + (int)threadIdx.x) * 4;
+  const bool live = n0 < lb.NA;  // lines n0..n0+3; beyond NA the float table holds -inf (never kept)
+  u64 zp[G][2];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    double2 v0 = make_double2(0.0, 0.0), v1 = v0;
+    if (live) {
+      const double* zr = lb.Z + (size_t)min(c0 + g, lb.C - 1) * lb.ldz + n0;
+      v0 = *reinterpret_cast<const double2*>(zr);
+      v1 = *reinterpret_cast<const double2*>(zr + 2);
+    }
+    zp[g][0] = pack_f32x2(__double2float_rn(v0.x), __double2float_rn(v0.y));
+    zp[g][1] = pack_f32x2(__double2float_rn(v1.x), __double2float_rn(v1.y));
+  }
+  const float ninf = -INFINITY;
+  float4 a_nx = make_float4(ninf, ninf, ninf, ninf);
+  const float* ap = lb.A32 + n0;
+  if (live) a_nx = *reinterpret_cast<const float4*>(ap);
+  const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+  int wcnt = 0;  // entries in this warp's pool (warp-uniform)
+  __syncthreads();
+
+  for (int j = 0; j < S; ++j) {
+    const float4 a = a_nx;
+    ap += lb.a_sj;
+    if (live && j + 1 < S) a_nx = *reinterpret_cast<const float4*>(ap);
+    const ulonglong2* pj = s_p32 + (size_t)j * (2 * G);
+    unsigned mask = 0u;
+    {
+      const ulonglong2 q1 = pj[0], q2 = pj[1];
+      mask = pair_test32<1u << 0>(mask, q1.x, q1.y, q2.x, q2.y, zp[0][0], a.x, a.y);
+      mask = pair_test32<1u << 2>(mask, q1.x, q1.y, q2.x, q2.y, zp[0][1], a.z, a.w);
+    }
+    {
+      const ulonglong2 q1 = pj[2], q2 = pj[3];
+      mask = pair_test32<1u << 4>(mask, q1.x, q1.y, q2.x, q2.y, zp[1][0], a.x, a.y);
+      mask = pair_test32<1u << 6>(mask, q1.x, q1.y, q2.x, q2.y, zp[1][1], a.z, a.w);
+    }
+    {
+      const ulonglong2 q1 = pj[4], q2 = pj[5];
+      mask = pair_test32<1u << 8>(mask, q1.x, q1.y, q2.x, q2.y, zp[2][0], a.x, a.y);
+      mask = pair_test32<1u << 10>(mask, q1.x, q1.y, q2.x, q2.y, zp[2][1], a.z, a.w);
+    }
+    {
+      const ulonglong2 q1 = pj[6], q2 = pj[7];
+      mask = pair_test32<1u << 12>(mask, q1.x, q1.y, q2.x, q2.y, zp[3][0], a.x, a.y);
+      mask = pair_test32<1u << 14>(mask, q1.x, q1.y, q2.x, q2.y, zp[3][1], a.z, a.w);
+    }
+    for (;;) {  // survivors are rare (~1 % of the tests)
+      const unsigned vote = __ballot_sync(0xffffffffu, mask != 0u);
+      if (vote == 0u) break;
+      if (wcnt + 32 > WPOOL) {
+        flush_warp_pool<G>(lb, sc, pool, wcnt, c0, s_far);
+        wcnt = 0;
+      }
+      if (mask) {
+        const int bit = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        pool[wcnt + __popc(vote & lt)] = make_int2(n0 + (bit & 3), j * G + (bit >> 2));
+      }
+      wcnt += __popc(vote);
+    }
+  }
+  flush_warp_pool<G>(lb, sc, pool, wcnt, c0, s_far);
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * G * S; e += blockDim.x) {
+    const unsigned long long key = s_far[e];
+    if (key) {
+      const int setl = e >> 1;
+      const int j = setl / G, g = setl - j * G;
+      atomicMax(&sc.far[((size_t)(c0 + g) * S + j) * 2 + (e & 1)], key);
+    }
+  }
+}
+
+static int launch_filter32(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st) {
+  constexpr int G = 4;
+  dim3 grid(ceil_div(lb.NA, F32_THREADS * 4), ceil_div(lb.C, G));
+  const size_t smem = (size_t)G * lb.S * (2 * sizeof(ulonglong2) + 2 * sizeof(unsigned long long)) +
+                      (F32_THREADS / 32) * WPOOL * sizeof(int2);
+  if (smem > 48 * 1024)
+    DKG_CUDA_OK(cudaFuncSetAttribute(filter32_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  filter32_kernel<G><<<grid, F32_THREADS, smem, st>>>(lb, sc);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
 template <int G, int R>
 static int launch_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st) {
   dim3 grid(ceil_div(lb.NA, E_THREADS * R), ceil_div(lb.C, G));
@@ -436,6 +705,14 @@ int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st) {
   if (lb.C == 0 || lb.NA == 0) return DKG_OK;
   // big batches: 4 lines per thread (fewer parameter loads per test); small ones: more CTAs
   const long long ctas4 = (long long)ceil_div(lb.C, 4) * ceil_div(lb.NA, E_THREADS * 4);
+  // KG path with a shared intercept table: the float test (DKG_FILTER=f64 keeps the fp64 kernel)
+  // (DKG_FILTER=f32 uses it for small batches too: tests)
+  const char* fe = getenv("DKG_FILTER");  // read per launch so tests can compare the two kernels
+  const int mode = fe == nullptr ? 0 : strcmp(fe, "f64") == 0 ? 1 : strcmp(fe, "f32") == 0 ? 2 : 0;
+  if (mode != 1 && lb.A32 != nullptr && sc.chain32 != nullptr && lb.a_sc == 0 && lb.row_mod == 0 &&
+      (lb.ldz & 1) == 0 && (lb.a_sj & 3) == 0 && lb.ldz >= ((lb.NA + 3) & ~3) && lb.a_sj >= ((lb.NA + 3) & ~3) &&
+      (ctas4 >= 148 || mode == 2))
+    return launch_filter32(lb, sc, st);
   if (getenv("DKG_FILTER_R8") && ctas4 >= 6 * 148) return launch_filter<4, 8>(lb, sc, st);
   if (ctas4 >= 3 * 148) return launch_filter<4, 4>(lb, sc, st);
   return launch_filter<4, 1>(lb, sc, st);
@@ -673,6 +950,9 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
   __shared__ double s_a[E_THREADS / 32][STAGE_CAP];
   __shared__ double s_b[E_THREADS / 32][STAGE_CAP];
   __shared__ int s_i[E_THREADS / 32][STAGE_CAP];
+  __shared__ double s_cm[E_THREADS / 32][CHAIN_MAXV];  // chord slopes / slacks of the refinement chain
+  __shared__ double s_cs[E_THREADS / 32][CHAIN_MAXV];
+  __shared__ unsigned long long s_fk[E_THREADS / 32][CHAIN_MAXV];  // farthest line above every chord
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long set_ll = (long long)blockIdx.x * (E_THREADS / 32) + warp;
@@ -697,7 +977,10 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
   }
   const int cnt = sc.surv_cnt[set];
   if (cnt > SURV_CAP) {  // list truncated: the cooperative kernel redoes this set from all lines
-    if (lane == 0) sc.ovf_sets[atomicAdd(sc.ovf_count, 1)] = (int)set;
+    if (lane == 0) {
+      sc.ovf_sets[atomicAdd(sc.ovf_count, 1)] = (int)set;
+      if (sc.stats) atomicAdd((unsigned long long*)&sc.stats[0], 1ull);  // (debug: DKG_DEBUG_STATS)
+    }
     return;
   }
   const SurvEntry* list = sc.surv + set * SURV_CAP;
@@ -728,9 +1011,13 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
     }
     staged = total;
   } else {
-    // ---- one QuickHull-style refinement over the list, compacting into shared memory ----
+    // ---- QuickHull-style refinement over the list, compacting into shared memory ----
     // chain in the (b, a) plane: P (min slope), T (max intercept), Q (max slope) plus the
-    // farthest late survivors F1 / F2 recorded by the filter (any set member is a valid vertex)
+    // farthest late survivors F1 / F2 recorded by the filter (any set member is a valid vertex).
+    // The chain vertices (strictly increasing slope) are the head of the staging arrays; every
+    // pass classifies the list against the current chain, optimistically compacts the lines that
+    // stay into the tail and records the farthest line above every chord; if the result does
+    // not fit, those lines become vertices (the chain stays concave) and the pass is repeated.
     const bool posw = !(w < 0.0);
     const Line P = gather_line(lb, c, j, w, posw ? s.iP : s.iQ);
     const Line Q = gather_line(lb, c, j, w, posw ? s.iQ : s.iP);
@@ -741,67 +1028,68 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
     const bool hasL = T.b > P.b, hasR = Q.b > T.b;
     if (!(hasL && F1.idx >= 0 && F1.b > P.b && F1.b < T.b)) F1 = empty_line();
     if (!(hasR && F2.idx >= 0 && F2.b > T.b && F2.b < Q.b)) F2 = empty_line();
-    Chord cl, cr;
-    cl.b0 = cl.a0 = cl.m = cl.slack = 0.0;
-    cr = cl;
-    if (hasL) cl.set(P, T);
-    if (hasR) cr.set(T, Q);
-    if (F1.idx >= 0 && !(cl.excess(F1) > 0.0)) F1 = empty_line();  // keep the chain concave
-    if (F2.idx >= 0 && !(cr.excess(F2) > 0.0)) F2 = empty_line();
-    // refined chain: P [F1] T [F2] Q  -> up to 4 chords; unused slots have an empty slope range
-    Chord ch[4];
-    double lo_b[4], hi_b[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { ch[q] = cl; lo_b[q] = INFINITY; hi_b[q] = -INFINITY; }
-    if (hasL) {
-      if (F1.idx >= 0) {
-        ch[0].set(P, F1); lo_b[0] = P.b; hi_b[0] = F1.b;
-        ch[1].set(F1, T); lo_b[1] = F1.b; hi_b[1] = T.b;
-      } else {
-        ch[0] = cl; lo_b[0] = P.b; hi_b[0] = T.b;
-      }
-    }
-    if (hasR) {
-      if (F2.idx >= 0) {
-        ch[2].set(T, F2); lo_b[2] = T.b; hi_b[2] = F2.b;
-        ch[3].set(F2, Q); lo_b[3] = F2.b; hi_b[3] = Q.b;
-      } else {
-        ch[2] = cr; lo_b[2] = T.b; hi_b[2] = Q.b;
-      }
-    }
-    // the staged list starts with the chain vertices themselves
-    staged = 0;
+    if (F1.idx >= 0) { Chord ch; ch.set(P, T); if (!(ch.excess(F1) > 0.0)) F1 = empty_line(); }  // concave
+    if (F2.idx >= 0) { Chord ch; ch.set(T, Q); if (!(ch.excess(F2) > 0.0)) F2 = empty_line(); }
+    double* vb = s_b[warp];
+    double* va = s_a[warp];
+    int* vi = s_i[warp];
+    int nv = 0;
     if (lane == 0) {
-      const Line vs[5] = {P, F1, T, F2, Q};
+      const Line vs[5] = {hasL ? P : empty_line(), F1, T, F2, hasR ? Q : empty_line()};
       for (int v = 0; v < 5; ++v)
-        if (vs[v].idx >= 0) {
-          s_a[warp][staged] = vs[v].a; s_b[warp][staged] = vs[v].b; s_i[warp][staged] = vs[v].idx;
-          ++staged;
-        }
+        if (vs[v].idx >= 0) { va[nv] = vs[v].a; vb[nv] = vs[v].b; vi[nv] = vs[v].idx; ++nv; }
     }
-    staged = __shfl_sync(0xffffffffu, staged, 0);
-    bool too_many = false;
-    for (int k0 = 0; k0 < total; k0 += 32) {
-      const int k = k0 + lane;
-      bool keep = false;
-      Line L = empty_line();
-      if (k < total) {
-        L = fetch_global(k);
-        // a line strictly inside a chord's slope range survives only above that chord; a line
-        // at a vertex slope is kept (the march discards it if it is dominated)
-        keep = true;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (L.b > lo_b[q] && L.b < hi_b[q]) keep = ch[q].excess(L) > -ch[q].slack;
+    nv = __shfl_sync(0xffffffffu, nv, 0);
+    bool fits = false;
+    for (int level = 0; level < HULL_LEVELS; ++level) {
+      __syncwarp();
+      if (lane < nv - 1) {  // chord lane: vertex lane -> vertex lane + 1
+        const double m = (va[lane + 1] - va[lane]) / (vb[lane + 1] - vb[lane]);
+        s_cm[warp][lane] = m;
+        s_cs[warp][lane] = EPS128 * (fabs(va[lane]) + fabs(va[lane + 1]) + fabs(m) * fmax(fabs(vb[lane]), fabs(vb[lane + 1])));
       }
-      const unsigned m = __ballot_sync(0xffffffffu, keep);
-      const int pos = staged + __popc(m & ((1u << lane) - 1u));
-      const int add = __popc(m);
-      if (staged + add > STAGE_CAP) { too_many = true; break; }
-      if (keep) { s_a[warp][pos] = L.a; s_b[warp][pos] = L.b; s_i[warp][pos] = L.idx; }
-      staged += add;
+      if (lane < CHAIN_MAXV) s_fk[warp][lane] = 0ull;
+      __syncwarp();
+      staged = nv;
+      for (int k0 = 0; k0 < total; k0 += 32) {
+        const int k = k0 + lane;
+        bool keep = false;
+        Line L = empty_line();
+        if (k < total) {
+          L = fetch_global(k);
+          // a line strictly inside a chord's slope range survives only above that chord; a line
+          // at a vertex slope is kept (the march discards it if it is dominated)
+          keep = true;
+          int q = 0;  // largest vertex with vb[q] <= L.b (P / Q are the extreme slopes of the set)
+          for (int step = CHAIN_MAXV / 2; step > 0; step >>= 1)
+            if (q + step < nv && vb[q + step] <= L.b) q += step;
+          if (q < nv - 1 && L.b > vb[q]) {
+            const double ex = L.a - fma(s_cm[warp][q], L.b - vb[q], va[q]);
+            keep = ex > -s_cs[warp][q];
+            if (ex > 0.0) atomicMax(&s_fk[warp][q], pack_excess(ex, k));
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int pos = staged + __popc(m & ((1u << lane) - 1u));
+        if (keep && pos < STAGE_CAP) { s_a[warp][pos] = L.a; s_b[warp][pos] = L.b; s_i[warp][pos] = L.idx; }
+        staged += __popc(m);
+      }
+      if (staged <= STAGE_CAP) { fits = true; break; }
+      // the farthest line above every chord becomes a vertex
+      __syncwarp();
+      const unsigned long long key = lane < nv - 1 ? s_fk[warp][lane] : 0ull;
+      const unsigned ins = __ballot_sync(0xffffffffu, key != 0ull);
+      if (ins == 0u || nv + __popc(ins) > CHAIN_MAXV || level + 1 == HULL_LEVELS) break;
+      const Line F = key ? fetch_global((int)(key & 0xffffffffull)) : empty_line();
+      const double oa = lane < nv ? va[lane] : 0.0, ob = lane < nv ? vb[lane] : 0.0;
+      const int oi = lane < nv ? vi[lane] : -1;
+      const int before = __popc(ins & ((1u << lane) - 1u));  // inserts from chords 0 .. lane-1
+      __syncwarp();
+      if (lane < nv) { va[lane + before] = oa; vb[lane + before] = ob; vi[lane + before] = oi; }
+      if (key) { va[lane + before + 1] = F.a; vb[lane + before + 1] = F.b; vi[lane + before + 1] = F.idx; }
+      nv += __popc(ins);
     }
-    if (too_many) {
+    if (!fits) {
       if (lane == 0) sc.ovf_sets[atomicAdd(sc.ovf_count, 1)] = (int)set;
       return;
     }

@@ -17,6 +17,7 @@ struct LineBatch {
   const double* Z = nullptr;
   int ldz = 0;
   const double* A = nullptr;
+  const float* A32 = nullptr;      // optional float copy of A (same strides; shared table only): fp32 chord filter
   long long a_sc = 0;
   int a_sj = 0;
   const double* a_own = nullptr;
@@ -42,6 +43,10 @@ struct EmaxScratch {
   double* zst = nullptr;        // [C, 2] min / max of the slope row
   int* zarg = nullptr;          // [C, 2] their first indices
   double4* chain = nullptr;     // [C, S] chord-chain parameters of every set (zstat -> filter)
+  double4* chainv = nullptr;    // [C, S, 2] end points (z0, a0, z1, a1) of the left / right chord in the raw
+                                // slope coordinate (optional; second-level chain of the fp32 filter)
+  float4* chain32 = nullptr;    // [C, S, 2] the same chain rounded conservatively to float, (m, m, c, c)
+                                // per chord (optional; enables the fp32 filter)
   int* surv_cnt = nullptr;      // [C, S]  lines that passed the filter (may exceed SURV_CAP)
   SurvEntry* surv = nullptr;    // [C, S, SURV_CAP]
   unsigned long long* far = nullptr;  // [C, S, 2] farthest late survivor above the left / right

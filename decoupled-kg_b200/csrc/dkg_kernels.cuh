@@ -16,7 +16,7 @@ int kcross(const ObjState& o, const double* xd_s, int N, int d, double* R, int l
 int set_identity(double* A, int n, int ld, cudaStream_t st);
 int residual(const double* y, int n, double c, double* out, cudaStream_t st);
 int mu_disc(const double* xd, int N, int d, const ObjState& o, double* mu, int M, int m, cudaStream_t st);
-int build_a0(const double* mu, int N, int M, const double* W, int S, double* A0, int ld,
+int build_a0(const double* mu, int N, int M, const double* W, int S, double* A0, float* A0f, int ld,
              double* A0max, int* A0arg, cudaStream_t st);
 
 int cholesky_blocked(double* A, int n, int ld, int* info_dev, cudaStream_t st);

@@ -61,6 +61,8 @@ struct Workspace {
   double* zst = nullptr;    // [chunk_C, 2]      min / max of the slope row
   int* zarg = nullptr;      // [chunk_C, 2]      argmin, argmax of the slope row
   void* chain = nullptr;    // [chunk_C, S] double4 chord-chain parameters
+  void* chainv = nullptr;   // [chunk_C, S, 2] double4 end points of the two chords (second-level chain)
+  void* chain32 = nullptr;  // [chunk_C, S, 2] float4: the chain rounded conservatively for the fp32 filter
   int* surv_cnt = nullptr;  // [chunk_C, S]      chord-filter survivors per (candidate, scal.)
   void* surv = nullptr;     // [chunk_C, S, SURV_CAP] SurvEntry (intercept, slope, index)
   unsigned long long* far = nullptr;  // [chunk_C, S, 2] farthest late survivors (chain seeds)
@@ -100,6 +102,7 @@ struct dkg_plan {
   double* alpha_all = nullptr;  // concatenated mean caches (exposed by dkg_plan_read)
   double* mu_disc = nullptr;  // [N, M]
   double* A0 = nullptr;       // [S, N_pad]   scalarised intercepts of the discretisation lines
+  float* A0f = nullptr;       // [S, N_pad]   float copy of A0 (fp32 chord filter; padding = -inf)
   double* A0max = nullptr;    // [S]
   int* A0arg = nullptr;       // [S]
   double jitter = 0.0;        // Cholesky jitter that was needed (0 normally)

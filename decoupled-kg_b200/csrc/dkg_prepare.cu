@@ -276,7 +276,7 @@ int mu_disc(const double* xd, int N, int d, const ObjState& o, double* mu, int M
 // A0[j, n] = sum_m W[j, m] * mu[n, m]  (products rounded, summed left to right -- matches
 // torch.sum(weights * means, dim=-1) at discretekg.py:320 for the discretisation lines).
 __global__ void a0_kernel(const double* __restrict__ mu, int N, int M, const double* __restrict__ W,
-                          int S, double* __restrict__ A0, int ld) {
+                          int S, double* __restrict__ A0, float* __restrict__ A0f, int ld) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   int j = blockIdx.y;
   if (n >= ld) return;
@@ -288,6 +288,7 @@ __global__ void a0_kernel(const double* __restrict__ mu, int N, int M, const dou
     acc = -INFINITY;  // padding lines can never win a max
   }
   A0[(size_t)j * ld + n] = acc;
+  A0f[(size_t)j * ld + n] = (float)acc;  // the fp32 chord filter budgets for this rounding
 }
 
 // A0max[j], A0arg[j] (first index of the maximum); one CTA per scalarisation.
@@ -338,10 +339,10 @@ __global__ void a0max_kernel(const double* __restrict__ A0, int N, int ld, doubl
   }
 }
 
-int build_a0(const double* mu, int N, int M, const double* W, int S, double* A0, int ld,
+int build_a0(const double* mu, int N, int M, const double* W, int S, double* A0, float* A0f, int ld,
              double* A0max, int* A0arg, cudaStream_t st) {
   dim3 grid(ceil_div(ld, 128), S);
-  a0_kernel<<<grid, 128, 0, st>>>(mu, N, M, W, S, A0, ld);
+  a0_kernel<<<grid, 128, 0, st>>>(mu, N, M, W, S, A0, A0f, ld);
   DKG_LAUNCH_CHECK();
   a0max_kernel<<<S, 256, 0, st>>>(A0, N, ld, A0max, A0arg);
   DKG_LAUNCH_CHECK();

@@ -1,0 +1,77 @@
+"""The fp32 chord filter (filter32_kernel) must keep every line the fp64 filter keeps: the exact
+march then sees a superset of the fp64 survivors and the results are identical to the last bit."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _eval(P, target, X, mode, xd=None):
+    from decoupledbo_b200.modules.acquisition.discretekg import DiscreteKnowledgeGradient
+
+    old = os.environ.get("DKG_FILTER")
+    os.environ["DKG_FILTER"] = mode
+    try:
+        acq = DiscreteKnowledgeGradient(P.model, P.x_disc if xd is None else xd, P.weights, target_output_ix=target)
+        Xg = X.clone().requires_grad_(True)
+        kg = acq(Xg.unsqueeze(1))
+        (g,) = torch.autograd.grad(kg.sum(), Xg)
+        torch.cuda.synchronize()
+        st = acq._get_plan().stats()
+        return kg.detach().clone(), g.clone(), st
+    finally:
+        if old is None:
+            del os.environ["DKG_FILTER"]
+        else:
+            os.environ["DKG_FILTER"] = old
+
+
+def test_c4_bits_equal_and_survivors_superset():
+    from decoupledbo_b200 import synthetic
+
+    P = synthetic.problem_c4(n_cand=1024)
+    dev = torch.device("cuda")
+    X = P.candidates.to(dev)
+    for target in (0, 1):
+        kg64, g64, st64 = _eval(P, target, X, "f64", P.x_disc.to(dev))
+        kg32, g32, st32 = _eval(P, target, X, "f32", P.x_disc.to(dev))
+        assert torch.equal(kg64, kg32)
+        assert torch.equal(g64, g32)
+        # stats[1] = survivors seen by the hull kernel: the float test adds only a few lines
+        assert st32[1] <= 1.10 * st64[1] + 4096
+
+
+@pytest.mark.parametrize("shape", [(2, 40, 121, 16, 33), (3, 33, 129, 2, 130), (2, 16, 1000, 17, 4), (4, 50, 4099, 8, 64)],
+                         ids=lambda s: "d%dn%dN%dS%dC%d" % s)
+def test_small_and_ragged_shapes(shape):
+    from decoupledbo_b200 import synthetic
+
+    d, n_train, N, S, C = shape
+    P = synthetic.make_problem(
+        "f32", d, n_train, [0.3, 0.5], [1.0, 2.0], [0.05, 0.05], [1e-2, 1e-4],
+        synthetic.sobol(N, d, 5), S, C, seed_train=6, seed_cand=7, seed_w=1)
+    for target in (0, 1):
+        kg64, g64, _ = _eval(P, target, P.candidates, "f64")
+        kg32, g32, _ = _eval(P, target, P.candidates, "f32")
+        assert torch.equal(kg64, kg32)
+        assert torch.equal(g64, g32)
+
+
+def test_huge_scales_fall_back_to_keeping_everything():
+    """Intercept / slope magnitudes near or outside the float-safe range must not lose lines
+    (1e64: every chord falls back to 'all lines survive' and the exact overflow path runs)."""
+    from decoupledbo_b200 import synthetic
+
+    for osc in (1e40, 1e64):
+        P = synthetic.make_problem(
+            "f32s", 2, 30, [0.3, 0.5], [osc, osc], [0.05, 0.05], [1e-2 * osc, 1e-2 * osc],
+            synthetic.sobol(600, 2, 5), 4, 40, seed_train=6, seed_cand=7, seed_w=1)
+        for o in P.model.models:  # targets scaled with the prior
+            o.train_y = o.train_y * (osc ** 0.5)
+        for target in (0, 1):
+            kg64, g64, _ = _eval(P, target, P.candidates, "f64")
+            kg32, g32, _ = _eval(P, target, P.candidates, "f32")
+            assert torch.equal(kg64, kg32)
+            assert torch.equal(g64, g32)

@@ -517,52 +517,33 @@ __device__ __forceinline__ double2 chord_through(double z0, double a0, double z1
 constexpr int F32_THREADS = 128;
 constexpr int WPOOL = 256;
 
-// Before a parked line is stored it is re-tested, exactly (fp64), against a SECOND-LEVEL chain: pass A
-// records, per set and side, the parked line farthest above the 3-point chord (this CTA's lines
-// only -- any member of the set is a valid chain vertex; the choice only decides how tight the chain
-// is); pass B keeps a line only if it is above  P -> U -> T  (or  T -> V -> Q)  with U / V that
-// farthest line.  On smooth GP posteriors this removes ~3/4 of the stored survivors.  The same
-// per-side maxima seed the QuickHull refinement of the hull stage (sc.far).
-template <int G>
-__device__ __forceinline__ void flush_warp_pool(const LineBatch& lb, const EmaxScratch& sc, int2* pool,
+// The filter runs in two launches.  Phase 1 covers a SAMPLE of the lines (a few line blocks spread
+// over the row) and stores its survivors as they are; the per-set, per-side farthest sampled line
+// above the 3-point chord (sc.far) then becomes a vertex U / V of a SECOND-LEVEL chain
+// (chain5_kernel: P -> U -> T and T -> V -> Q; any member of the set is a valid vertex, the sample
+// only decides how tight the chain is).  Phase 2 covers the remaining lines and re-tests every
+// parked line, exactly (fp64), against that chain before it claims a slot: on smooth GP posteriors
+// this removes ~70 % of the stored survivors (and the hull-stage work that follows them).
+template <int G, bool REFINE>
+__device__ __forceinline__ void flush_warp_pool(const LineBatch& lb, const EmaxScratch& sc, const int2* pool,
                                                 int cnt, int c0, unsigned long long* s_far) {
   __syncwarp();
   const int S = lb.S;
-  for (int e = threadIdx.x & 31; e < cnt; e += 32) {  // pass A
+  for (int e = threadIdx.x & 31; e < cnt; e += 32) {
     const int2 it = pool[e];
     const int setl = it.y;
-    const int j = setl / G, g = setl - j * G;
-    const int c = c0 + g;
-    const int n = it.x;
-    const double av = lb.A[a_base(lb, c, j) + n];
-    const double zv = lb.Z[(size_t)c * lb.ldz + n];
-    const double4 par = sc.chain[(size_t)c * S + j];
-    const double t1 = fma(par.y, zv, par.x), t2 = fma(par.w, zv, par.z);
-    const int side = t1 <= t2 ? 0 : 1;
-    const double ex = av - (side == 0 ? t1 : t2);
-    if (ex > 0.0) atomicMax(&s_far[2 * setl + side], pack_excess(ex, n));
-    pool[e].y = setl | (side << 30);
-  }
-  __syncwarp();
-  for (int e = threadIdx.x & 31; e < cnt; e += 32) {  // pass B
-    const int2 it = pool[e];
-    const int setl = it.y & 0x3fffffff, side = (it.y >> 30) & 1;
     const int j = setl / G, g = setl - j * G;
     const int c = c0 + g;
     const size_t set = (size_t)c * S + j;
     const int n = it.x;
     const double av = lb.A[a_base(lb, c, j) + n];
     const double zv = lb.Z[(size_t)c * lb.ldz + n];
-    const unsigned long long key = s_far[2 * setl + side];
-    if (sc.chainv != nullptr && key != 0ull) {
-      const int nu = (int)(key & 0xffffffffull);
-      const double au = lb.A[a_base(lb, c, j) + nu];
-      const double zu = lb.Z[(size_t)c * lb.ldz + nu];
-      const double4 v = sc.chainv[set * 2 + side];  // (z0, a0, z1, a1), raw slope coordinate
-      if ((zu - v.x) * (v.z - zu) > 0.0) {          // U strictly between the chord's end points
-        const double2 c0u = chord_through(v.x, v.y, zu, au), cu1 = chord_through(zu, au, v.z, v.w);
-        if (!((av > fma(c0u.y, zv, c0u.x)) | (av > fma(cu1.y, zv, cu1.x)))) continue;
-      }
+    const double4 par = sc.chain[set];
+    const double t1 = fma(par.y, zv, par.x), t2 = fma(par.w, zv, par.z);
+    const int side = t1 <= t2 ? 0 : 1;
+    if (REFINE) {
+      const double4 q = sc.chain5[set * 2 + side];
+      if (!((av > fma(q.y, zv, q.x)) | (av > fma(q.w, zv, q.z)))) continue;
     }
     const int pos = atomicAdd(&sc.surv_cnt[set], 1);
     if (pos < SURV_CAP) {
@@ -570,13 +551,53 @@ __device__ __forceinline__ void flush_warp_pool(const LineBatch& lb, const EmaxS
       en.a = av; en.z = zv; en.idx = n; en.pad = 0;
       sc.surv[set * SURV_CAP + pos] = en;
     }
+    // the farthest survivor above each 3-point chord: second-level chain vertex (phase 1) and seed
+    // of the QuickHull refinement in the hull stage
+    const double ex = av - (side == 0 ? t1 : t2);
+    if (ex > 0.0) atomicMax(&s_far[2 * setl + side], pack_excess(ex, n));
   }
   __syncwarp();
 }
 
-template <int G>
+// second-level chain of every set from the phase-1 maxima: chain5[set] = (c_PU, m_PU, c_UT, m_UT),
+// (c_TV, m_TV, c_VQ, m_VQ); a missing vertex repeats the 3-point chord
+__global__ void __launch_bounds__(E_THREADS)
+chain5_kernel(LineBatch lb, EmaxScratch sc) {
+  const size_t set = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (set >= (size_t)lb.C * lb.S) return;
+  const int c = (int)(set / lb.S), j = (int)(set - (size_t)c * lb.S);
+  const double4 par = sc.chain[set];
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const double pc = side == 0 ? par.x : par.z, pm = side == 0 ? par.y : par.w;
+    double4 q = make_double4(pc, pm, pc, pm);
+    const unsigned long long key = sc.far[set * 2 + side];
+    if (key != 0ull && pc != INFINITY) {
+      const int nu = (int)(key & 0xffffffffull);
+      const double au = lb.A[a_base(lb, c, j) + nu];
+      const double zu = lb.Z[(size_t)c * lb.ldz + nu];
+      const double4 v = sc.chainv[set * 2 + side];  // (z0, a0, z1, a1), raw slope coordinate
+      if ((zu - v.x) * (v.z - zu) > 0.0) {          // U strictly between the chord's end points
+        const double2 c0u = chord_through(v.x, v.y, zu, au), cu1 = chord_through(zu, au, v.z, v.w);
+        q = make_double4(c0u.x, c0u.y, cu1.x, cu1.y);
+      }
+    }
+    sc.chain5[set * 2 + side] = q;
+  }
+}
+
+// blk_first / blk_step / blk_skip map blockIdx.x to a line block: phase 1 visits blocks
+// i * blk_step (blk_skip == 0), phase 2 the others (blk_skip == number of sampled blocks)
+__device__ __forceinline__ int line_block(int i, int step, int nsb, bool phase2) {
+  if (!phase2) return i * step;
+  const int body = (step - 1) * nsb;  // non-sampled blocks inside the sampled stretch
+  if (i < body) return (i / (step - 1)) * step + 1 + i % (step - 1);
+  return nsb * step + (i - body);
+}
+
+template <int G, bool REFINE>
 __global__ void __launch_bounds__(F32_THREADS, 7)
-filter32_kernel(LineBatch lb, EmaxScratch sc) {
+filter32_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb) {
   static_assert(G == 4, "bit layout below assumes 4 candidates x 4 lines");
   extern __shared__ __align__(16) unsigned char e_smem[];
   const int S = lb.S;
@@ -595,7 +616,7 @@ filter32_kernel(LineBatch lb, EmaxScratch sc) {
     s_far[2 * e] = 0ull;
     s_far[2 * e + 1] = 0ull;
   }
-  const int n0 = (blockIdx.x * F32_THREADS + (int)threadIdx.x) * 4;
+  const int n0 = (line_block(blockIdx.x, blk_step, nsb, REFINE) * F32_THREADS + (int)threadIdx.x) * 4;
   const bool live = n0 < lb.NA;  // lines n0..n0+3; beyond NA the float table holds -inf (never kept)
   u64 zp[G][2];
 #pragma unroll
@@ -647,7 +668,7 @@ filter32_kernel(LineBatch lb, EmaxScratch sc) {
       const unsigned vote = __ballot_sync(0xffffffffu, mask != 0u);
       if (vote == 0u) break;
       if (wcnt + 32 > WPOOL) {
-        flush_warp_pool<G>(lb, sc, pool, wcnt, c0, s_far);
+        flush_warp_pool<G, REFINE>(lb, sc, pool, wcnt, c0, s_far);
         wcnt = 0;
       }
       if (mask) {
@@ -658,7 +679,7 @@ filter32_kernel(LineBatch lb, EmaxScratch sc) {
       wcnt += __popc(vote);
     }
   }
-  flush_warp_pool<G>(lb, sc, pool, wcnt, c0, s_far);
+  flush_warp_pool<G, REFINE>(lb, sc, pool, wcnt, c0, s_far);
   __syncthreads();
   for (int e = threadIdx.x; e < 2 * G * S; e += blockDim.x) {
     const unsigned long long key = s_far[e];
@@ -672,13 +693,26 @@ filter32_kernel(LineBatch lb, EmaxScratch sc) {
 
 static int launch_filter32(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st) {
   constexpr int G = 4;
-  dim3 grid(ceil_div(lb.NA, F32_THREADS * 4), ceil_div(lb.C, G));
+  const int nblk = ceil_div(lb.NA, F32_THREADS * 4);
+  const unsigned gy = ceil_div(lb.C, G);
   const size_t smem = (size_t)G * lb.S * (2 * sizeof(ulonglong2) + 2 * sizeof(unsigned long long)) +
                       (F32_THREADS / 32) * WPOOL * sizeof(int2);
-  if (smem > 48 * 1024)
-    DKG_CUDA_OK(cudaFuncSetAttribute(filter32_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  filter32_kernel<G><<<grid, F32_THREADS, smem, st>>>(lb, sc);
+  if (smem > 48 * 1024) {
+    DKG_CUDA_OK(cudaFuncSetAttribute(filter32_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DKG_CUDA_OK(cudaFuncSetAttribute(filter32_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  // two sampled blocks (1024 lines) out of >= 8; smaller rows are filtered in one launch
+  const bool two_phase = sc.chain5 != nullptr && sc.chainv != nullptr && nblk >= 8;
+  const int nsb = two_phase ? 2 : nblk, step = two_phase ? nblk / 2 : 1;
+  filter32_kernel<G, false><<<dim3(nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
   DKG_LAUNCH_CHECK();
+  if (two_phase) {
+    const long long sets = (long long)lb.C * lb.S;
+    chain5_kernel<<<(unsigned)((sets + E_THREADS - 1) / E_THREADS), E_THREADS, 0, st>>>(lb, sc);
+    DKG_LAUNCH_CHECK();
+    filter32_kernel<G, true><<<dim3(nblk - nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
+    DKG_LAUNCH_CHECK();
+  }
   return DKG_OK;
 }
 

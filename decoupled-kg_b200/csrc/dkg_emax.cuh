@@ -45,6 +45,8 @@ struct EmaxScratch {
   double4* chain = nullptr;     // [C, S] chord-chain parameters of every set (zstat -> filter)
   double4* chainv = nullptr;    // [C, S, 2] end points (z0, a0, z1, a1) of the left / right chord in the raw
                                 // slope coordinate (optional; second-level chain of the fp32 filter)
+  double4* chain5 = nullptr;    // [C, S, 2] second-level chain (c_PU, m_PU, c_UT, m_UT), (c_TV, m_TV, c_VQ, m_VQ)
+                                // built from the sampled phase of the fp32 filter (optional)
   float4* chain32 = nullptr;    // [C, S, 2] the same chain rounded conservatively to float, (m, m, c, c)
                                 // per chord (optional; enables the fp32 filter)
   int* surv_cnt = nullptr;      // [C, S]  lines that passed the filter (may exceed SURV_CAP)

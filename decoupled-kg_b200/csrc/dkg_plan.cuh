@@ -62,6 +62,7 @@ struct Workspace {
   int* zarg = nullptr;      // [chunk_C, 2]      argmin, argmax of the slope row
   void* chain = nullptr;    // [chunk_C, S] double4 chord-chain parameters
   void* chainv = nullptr;   // [chunk_C, S, 2] double4 end points of the two chords (second-level chain)
+  void* chain5 = nullptr;   // [chunk_C, S, 2] double4 second-level chain
   void* chain32 = nullptr;  // [chunk_C, S, 2] float4: the chain rounded conservatively for the fp32 filter
   int* surv_cnt = nullptr;  // [chunk_C, S]      chord-filter survivors per (candidate, scal.)
   void* surv = nullptr;     // [chunk_C, S, SURV_CAP] SurvEntry (intercept, slope, index)

@@ -68,7 +68,7 @@ static void dev_free(T*& p) {
 static void free_workspace(Workspace& w) {
   dev_free(w.X); dev_free(w.kg); dev_free(w.dX); dev_free(w.KX); dev_free(w.T); dev_free(w.R); dev_free(w.T_dig); dev_free(w.T_scale); dev_free(w.var);
   dev_free(w.sd); dev_free(w.zown); dev_free(w.Xs); dev_free(w.a_new); dev_free(w.kg_terms);
-  dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } { double4* t = (double4*)w.chain; dev_free(t); w.chain = nullptr; } { float4* t = (float4*)w.chain32; dev_free(t); w.chain32 = nullptr; } { double4* t = (double4*)w.chainv; dev_free(t); w.chainv = nullptr; } { double4* t = (double4*)w.chain5; dev_free(t); w.chain5 = nullptr; } dev_free(w.far); dev_free(w.ovf_sets); dev_free(w.ovf_count);
+  dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.zpv); dev_free(w.zpi); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } { double4* t = (double4*)w.chain; dev_free(t); w.chain = nullptr; } { float4* t = (float4*)w.chain32; dev_free(t); w.chain32 = nullptr; } { double4* t = (double4*)w.chainv; dev_free(t); w.chainv = nullptr; } { double4* t = (double4*)w.chain5; dev_free(t); w.chain5 = nullptr; } dev_free(w.far); dev_free(w.ovf_sets); dev_free(w.ovf_count);
   dev_free(w.hull_cnt); dev_free(w.hull_idx); dev_free(w.hull_p); dev_free(w.hull_q);
   dev_free(w.amax_is_new); dev_free(w.stats); dev_free(w.sdj); dev_free(w.Zc);
   for (int m = 0; m < MAX_M; ++m) { dev_free(w.KXm[m]); dev_free(w.Tm[m]); dev_free(w.varlat[m]); dev_free(w.COVm[m]); }
@@ -123,6 +123,11 @@ static int ensure_workspace(dkg_plan* p, int C) {
   DKG_TRY(dev_alloc(&w.Z, coupled ? (size_t)1 : (size_t)chunk * p->ldz));
   DKG_TRY(dev_alloc(&w.zst, (size_t)chunk * rows_per_cand * 2));
   DKG_TRY(dev_alloc(&w.zarg, (size_t)chunk * rows_per_cand * 2));
+  if (!coupled) {  // tiles of >= 1024 lines (64 KB of points at d <= 8)
+    const size_t tiles = (size_t)(p->N / 1024 + 1);
+    DKG_TRY(dev_alloc(&w.zpv, (size_t)chunk * tiles * 2));
+    DKG_TRY(dev_alloc(&w.zpi, (size_t)chunk * tiles * 2));
+  }
   if (coupled) {
     for (int m = 0; m < p->M; ++m) {
       DKG_TRY(dev_alloc(&w.KXm[m], (size_t)cap * p->obj[m].ldk));
@@ -491,6 +496,7 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     sc.ovf_sets = w.ovf_sets; sc.ovf_count = w.ovf_count; sc.far = w.far; sc.chain = (double4*)w.chain;
     sc.chain32 = (float4*)w.chain32;
     sc.chainv = (double4*)w.chainv;
+    sc.zpv = w.zpv; sc.zpi = w.zpi;
     sc.chain5 = (double4*)w.chain5;
     sc.stats = w.stats;
     DKG_CUDA_OK(cudaMemsetAsync(w.surv_cnt, 0, sizeof(int) * (size_t)cc * S, st));

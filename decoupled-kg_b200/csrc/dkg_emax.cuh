@@ -42,6 +42,8 @@ struct SurvEntry {
 struct EmaxScratch {
   double* zst = nullptr;        // [C, 2] min / max of the slope row
   int* zarg = nullptr;          // [C, 2] their first indices
+  double* zpv = nullptr;        // [C, tiles, 2] per-tile min / max of the slope row (tiled statistics pass;
+  int* zpi = nullptr;           //               optional) and their line indices
   double4* chain = nullptr;     // [C, S] chord-chain parameters of every set (zstat -> filter)
   double4* chainv = nullptr;    // [C, S, 2] end points (z0, a0, z1, a1) of the left / right chord in the raw
                                 // slope coordinate (optional; second-level chain of the fp32 filter)

@@ -60,6 +60,8 @@ struct Workspace {
   double* Z = nullptr;      // [chunk_C, ldz]    slopes cov/sd; column N = candidate's own line
   double* zst = nullptr;    // [chunk_C, 2]      min / max of the slope row
   int* zarg = nullptr;      // [chunk_C, 2]      argmin, argmax of the slope row
+  double* zpv = nullptr;    // [chunk_C, ZP_TILES, 2] per-tile min / max (tiled row-statistics pass)
+  int* zpi = nullptr;       // [chunk_C, ZP_TILES, 2]
   void* chain = nullptr;    // [chunk_C, S] double4 chord-chain parameters
   void* chainv = nullptr;   // [chunk_C, S, 2] double4 end points of the two chords (second-level chain)
   void* chain5 = nullptr;   // [chunk_C, S, 2] double4 second-level chain

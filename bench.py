@@ -76,7 +76,8 @@ def workload_config(workload: str, P, n_cand: int, world: int):
         "x_disc": int(P.x_disc.shape[0]),
         "n_train": o.n,
         "d": P.d,
-        "parallelism": f"candidate-sharded x{world}, replicated GP state, one all-gather of values+grads",
+        "parallelism": f"candidate-sharded x{world}, replicated GP state, one all-gather of values+grads; "
+                       "the two objectives' evaluations run on two CUDA streams",
         "l2": "no flush: per-step working set (slope rows 0.5 GB/objective + B, B^T 105 MB) exceeds the 126 MB L2",
     }
 
@@ -284,10 +285,22 @@ def main():
     X_dev = P.candidates.to(dev).contiguous()
     gather_buf = torch.empty(world * n_cand, 1 + d, dtype=torch.double, device=dev) if world > 1 else None
 
+    # The objectives are independent acquisition functions (strategy.py:208): each plan runs on its
+    # own stream so the latency-bound stages of one (hull march, backward gathers) overlap the
+    # other's streaming stages; the gathers / argmax follow on the main stream.
+    streams = [torch.cuda.Stream(device=dev) for _ in plans]
+
     def step_device():
         best = []
-        for plan in plans:
-            kg, dX = plan.forward_device(X_dev, True)
+        cur = torch.cuda.current_stream()
+        outs = []
+        for plan, s in zip(plans, streams):
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                outs.append(plan.forward_device(X_dev, True))
+        for s in streams:
+            cur.wait_stream(s)
+        for kg, dX in outs:
             if world > 1:
                 send = torch.cat([kg.unsqueeze(1), dX], dim=1)
                 dist.all_gather_into_tensor(gather_buf, send)

@@ -1297,7 +1297,8 @@ int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cu
 // overflow kernel: one CTA per queued set, all lines, always terminates
 // ------------------------------------------------------------------------------------------
 constexpr int OVF_MAXV = 130;  // chain vertices
-constexpr int FIN_RMAX = 1024; // hull records per candidate merged in shared memory
+constexpr int FIN_RMAX = 1024; // most hull records per candidate merged in shared memory (32 per scalarisation)
+__host__ __device__ inline int fin_rmax(int S) { const int r = 32 * S; return r < 256 ? 256 : r > FIN_RMAX ? FIN_RMAX : r; }
 constexpr int OVF_ROUNDS = 6;
 constexpr int OVF_CTAS_PER_SM = 4;
 
@@ -1605,12 +1606,13 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
   // ---- gather the hull records of this candidate and merge duplicates: the same few lines are
   // hull vertices for most scalarisations, so the B^T row gathers and kernel-gradient evaluations
   // below run once per DISTINCT line (order = first occurrence, hence deterministic) ----
-  int* s_ridx = reinterpret_cast<int*>(s_red + nwarps * MAX_D);  // [FIN_RMAX] record line index
-  int* s_uidx = s_ridx + FIN_RMAX;                               // [FIN_RMAX] distinct line index
-  int* s_flag = s_uidx + FIN_RMAX;                               // [FIN_RMAX] first occurrence?
-  int* s_roff = s_flag + FIN_RMAX;                               // [S + 1] record offsets per set
-  double* s_rcz = reinterpret_cast<double*>(s_roff + ((S + 2) & ~1));  // [FIN_RMAX] w_j q / S
-  double* s_ucz = s_rcz + FIN_RMAX;                              // [FIN_RMAX] merged coefficient
+  const int RM = fin_rmax(S);
+  int* s_ridx = reinterpret_cast<int*>(s_red + (E_THREADS / 32) * MAX_D);  // [RM] record line index
+  int* s_uidx = s_ridx + RM;                               // [RM] distinct line index
+  int* s_flag = s_uidx + RM;                               // [RM] first occurrence?
+  int* s_roff = s_flag + RM;                               // [S + 1] record offsets per set
+  double* s_rcz = reinterpret_cast<double*>(s_roff + ((S + 2) & ~1));  // [RM] w_j q / S
+  double* s_ucz = s_rcz + RM;                              // [RM] merged coefficient
   __shared__ int s_nrec, s_nuniq;
   for (int j = threadIdx.x; j < S; j += blockDim.x)
     s_roff[j + 1] = min(out.hull_cnt[(size_t)c * S + j], hcap);  // counts first, scanned below
@@ -1628,7 +1630,7 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
   }
   __syncthreads();
   const int nrec = s_nrec;
-  const bool merged = nrec <= FIN_RMAX;
+  const bool merged = nrec <= RM;
   if (merged) {
     for (int j = warp; j < S; j += nwarps) {
       const size_t set = (size_t)c * S + j;
@@ -1797,12 +1799,14 @@ int emax_finalize(const LineBatch& lb, const EmaxOut& out, const BackwardArgs& b
   size_t smem = sizeof(double) * lb.S;
   if (bw.dX != nullptr)
     smem = sizeof(double) * ((size_t)bw.n_pad + 2 * lb.S + 2 + MAX_D + MAX_M + (E_THREADS / 32) * MAX_D) +
-           sizeof(int) * (3 * FIN_RMAX + ((lb.S + 2) & ~1)) + sizeof(double) * 2 * FIN_RMAX;
+           sizeof(int) * (3 * fin_rmax(lb.S) + ((lb.S + 2) & ~1)) + sizeof(double) * 2 * fin_rmax(lb.S);
+  const char* fte = getenv("DKG_FIN_THREADS");
+  const int fin_threads = fte != nullptr && (atoi(fte) == 256 || atoi(fte) == 64) ? atoi(fte) : 128;
 #define DKG_FINALIZE(DD)                                                                                       \
   do {                                                                                                         \
     if (smem > 48 * 1024)                                                                                      \
       DKG_CUDA_OK(cudaFuncSetAttribute(finalize_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    finalize_kernel<DD><<<lb.C, E_THREADS, smem, st>>>(lb, out, bw);                                           \
+    finalize_kernel<DD><<<lb.C, fin_threads, smem, st>>>(lb, out, bw);                                         \
   } while (0)
   switch (bw.dX != nullptr ? bw.d : 1) {
     case 1: DKG_FINALIZE(1); break;

@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--candidates", type=int, default=None, help="candidates per GPU (weak) / in total (strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every GPU gets its own full batch (default); strong: one batch split over the GPUs")
+    ap.add_argument("--precision", default="float64", choices=["float64", "float32"],
+                    help="float32: reduced-precision mode (4-digit covariance contraction; not the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -281,6 +283,8 @@ def main():
     d = P.d
     xd = P.x_disc.to(dev)
     acqs = [DiscreteKnowledgeGradient(P.model, xd, P.weights, target_output_ix=i) for i in range(M)]
+    for a in acqs:
+        a.precision = args.precision
     plans = [a._get_plan() for a in acqs]
     X_dev = P.candidates.to(dev).contiguous()
     gather_buf = torch.empty(world * n_cand, 1 + d, dtype=torch.double, device=dev) if world > 1 else None
@@ -411,14 +415,14 @@ def main():
                 src = "2 x MEASURED_PEAKS.json bf16_tflops (burst)"
             except Exception:
                 bf16, src = 2250.0, "2 x 2250 TFLOP/s nominal dense bf16 (B200_PROFILING.md fallback)"
-            products = 34.0
+            products = 34.0 if args.precision == "float64" else 10.0  # digit-pair products (7/8 or 4/4 digits/diagonals)
             kp = sum(-(-m.n // 32) * 32 for m in P.model.models) / sum(m.n for m in P.model.models)
             int8_ops = flops_total * products * kp
             int8_peak = 2.0 * bf16
             peak = int8_peak / (products * kp)  # the int8 roofline in fp64-equivalent TFLOP/s
             roofline = {
                 "kernel": "ozaki_kernel (tcgen05.mma.kind::i8 over base-256 digit planes: the fp64 GP "
-                          "conditioning contraction as 34 exact int8 products)",
+                          f"conditioning contraction as {int(products)} exact int8 digit products)",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak,
                 "peak_source": f"int8 tensor peak = {src} = {int8_peak:.0f} TOP/s, divided by the "
@@ -433,7 +437,7 @@ def main():
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this shape from
                 # the ncu --set full capture profiles/r01j_ozaki_ncu.csv (60.6 MB + 490.1 MB; algorithmic:
                 # 537 MB of product rows written once, digit planes served from L2)
-                "traffic": 550.7e6 if (n_cand == 4096 and N == 16384) else None,
+                "traffic": 550.7e6 if (n_cand == 4096 and N == 16384 and args.precision == "float64") else None,
                 "traffic_source": "profiles/r01j_ozaki_ncu.csv (ncu --set full, one launch, c4 shape)",
             }
         else:
@@ -490,7 +494,9 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f64" if args.precision == "float64" else "f64 (covariance contraction: 4 base-256 int8 digits)",
+            "data": "synthetic",
             "config": workload_config(args.workload, P, n_cand, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline,

@@ -108,7 +108,7 @@ static int ensure_workspace(dkg_plan* p, int C) {
     int n_max = 1;
     for (int m = 0; m < p->M; ++m)
       if (coupled || m == p->target) n_max = n_max > p->obj[m].n ? n_max : p->obj[m].n;
-    DKG_TRY(dev_alloc(&w.T_dig, ozaki_digit_bytes(chunk, n_max, OZ_DEFAULT_DIGITS)));
+    DKG_TRY(dev_alloc(&w.T_dig, ozaki_digit_bytes(chunk, n_max, p->cov_digits)));
     DKG_TRY(dev_alloc(&w.T_scale, (size_t)chunk + 128));  // + one row block: the CTA-pair kernel reads 256-row pairs
   }
   DKG_TRY(dev_alloc(&w.var, (size_t)cap));
@@ -189,10 +189,10 @@ static int make_kxd_digits(ObjState& o, const dkg_plan* p, cudaStream_t st) {
   double* KT = nullptr;
   DKG_TRY(dev_alloc(&KT, (size_t)p->N * o.n_pad, false));
   int rc = transpose(o.Kxd, o.n, p->N, p->N_pad, KT, o.n_pad, st);
-  if (rc == DKG_OK) rc = dev_alloc(&o.Kxd_dig, ozaki_digit_bytes(p->N_pad, o.n, OZ_DEFAULT_DIGITS));
+  if (rc == DKG_OK) rc = dev_alloc(&o.Kxd_dig, ozaki_digit_bytes(p->N_pad, o.n, p->cov_digits));
   if (rc == DKG_OK) rc = dev_alloc(&o.Kxd_scale, (size_t)p->N_pad);
   if (rc == DKG_OK)
-    rc = ozaki_slice_rows(KT, o.n_pad, p->N, o.n, ozaki_b_block_rows(OZ_DEFAULT_DIGITS, OZ_DEFAULT_DIAGONALS), OZ_DEFAULT_DIGITS,
+    rc = ozaki_slice_rows(KT, o.n_pad, p->N, o.n, ozaki_b_block_rows(p->cov_digits, p->cov_diagonals), p->cov_digits,
                           o.Kxd_dig, o.Kxd_scale, st);
   cudaStreamSynchronize(st);
   dev_free(KT);
@@ -203,9 +203,9 @@ static int make_kxd_digits(ObjState& o, const dkg_plan* p, cudaStream_t st) {
 static int cov_rows(const ObjState& o, const dkg_plan* p, Workspace& w, const double* T, int cc, int cc_pad,
                     const CovEpilogue& ep, cudaStream_t st) {
   if (o.Kxd_dig != nullptr) {
-    DKG_TRY(ozaki_slice_rows(T, o.ldk, cc, o.n, 128, OZ_DEFAULT_DIGITS, w.T_dig, w.T_scale, st));
-    return ozaki_cov(w.T_dig, w.T_scale, cc_pad, o.Kxd_dig, o.Kxd_scale, p->N_pad, o.n, OZ_DEFAULT_DIGITS,
-                     OZ_DEFAULT_DIAGONALS, /*b_nonneg=*/true, ep, st);  // stationary kernel values are positive
+    DKG_TRY(ozaki_slice_rows(T, o.ldk, cc, o.n, 128, p->cov_digits, w.T_dig, w.T_scale, st));
+    return ozaki_cov(w.T_dig, w.T_scale, cc_pad, o.Kxd_dig, o.Kxd_scale, p->N_pad, o.n, p->cov_digits,
+                     p->cov_diagonals, /*b_nonneg=*/true, ep, st);  // stationary kernel values are positive
   }
   return gemm_cov(T, o.ldk, o.Kxd, p->N_pad, cc_pad, p->N_pad, o.n_pad, ep, st);
 }
@@ -472,11 +472,11 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
         // int8 tensor cores in product mode: Z <- T . Kxd; the row-statistics pass below turns
         // the products into slopes while it reads them (CovFinish)
         { ProfScope pd(10, st);
-          DKG_TRY(ozaki_slice_rows(w.T + (size_t)c0 * p->ldk, p->ldk, cc, ot.n, 128, OZ_DEFAULT_DIGITS, w.T_dig,
+          DKG_TRY(ozaki_slice_rows(w.T + (size_t)c0 * p->ldk, p->ldk, cc, ot.n, 128, p->cov_digits, w.T_dig,
                                    w.T_scale, st)); }
         ProfScope ps(3, st);
-        DKG_TRY(ozaki_store(w.T_dig, w.T_scale, cc_pad, ot.Kxd_dig, ot.Kxd_scale, p->N_pad, ot.n, OZ_DEFAULT_DIGITS,
-                            OZ_DEFAULT_DIAGONALS, /*b_nonneg=*/true, w.Z, p->ldz, cc, N, st));
+        DKG_TRY(ozaki_store(w.T_dig, w.T_scale, cc_pad, ot.Kxd_dig, ot.Kxd_scale, p->N_pad, ot.n, p->cov_digits,
+                            p->cov_diagonals, /*b_nonneg=*/true, w.Z, p->ldz, cc, N, st));
       } else {
         ProfScope ps(3, st);
         DKG_TRY(cov_rows(ot, p, w, w.T + (size_t)c0 * p->ldk, cc, cc_pad, ep, st));
@@ -656,7 +656,6 @@ void dkg_launch_count_reset(void) { g_launches.store(0); }
 int dkg_plan_create(const dkg_objective* objs, int32_t M, int32_t d, const double* x_disc_dev,
                     int32_t N, const double* weights_host, int32_t S, int32_t target_ix,
                     uint32_t flags, void* stream, dkg_plan** out_plan) {
-  (void)flags;
   if (!out_plan) { set_error("out_plan is NULL"); return DKG_EINVAL; }
   *out_plan = nullptr;
   if (!objs || !x_disc_dev || !weights_host) { set_error("NULL argument"); return DKG_EINVAL; }
@@ -690,6 +689,7 @@ int dkg_plan_create(const dkg_objective* objs, int32_t M, int32_t d, const doubl
   dkg_plan* p = new (std::nothrow) dkg_plan();
   if (!p) { set_error("out of host memory"); return DKG_ENOMEM; }
   p->M = M; p->d = d; p->N = N; p->S = S; p->target = target_ix;
+  if (flags & DKG_PLAN_FAST32) { p->cov_digits = 4; p->cov_diagonals = 4; }
   p->N_pad = round_up(N, GEMM_BN);
   p->ldz = round_up(N + 1, 16);
   cudaGetDevice(&p->device);

@@ -35,6 +35,7 @@ constexpr double SHORTCUT_TOL = 1e-9;  // discretekg.py:363
 constexpr int STAGE_CAP = 128;         // lines a warp marches over from registers
 constexpr int CHAIN_MAXV = 32;         // vertices of a warp's refinement chain (one lane each)
 constexpr int HULL_LEVELS = 5;         // refinement passes of the warp kernel before a set is queued
+constexpr int HULL_CTAS = 3;           // resident CTAs per SM the warp hull kernel is compiled for
 constexpr double EPS128 = 2.84217094304040074e-14;  // 128 * 2^-52
 
 // ------------------------------------------------------------------------------------------
@@ -1118,7 +1119,7 @@ __device__ __forceinline__ bool higher_intercept(const Line& p, const Line& q) {
 // ------------------------------------------------------------------------------------------
 // hull kernel: one warp per set
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(E_THREADS, 3)
+__global__ void __launch_bounds__(E_THREADS, HULL_CTAS)
 hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
   __shared__ double s_a[E_THREADS / 32][STAGE_CAP];
   __shared__ double s_b[E_THREADS / 32][STAGE_CAP];

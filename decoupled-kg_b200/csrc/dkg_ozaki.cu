@@ -426,6 +426,7 @@ ozaki_kernel(const OzakiArgs args) {
       unsigned ph = 0;
       unsigned pcount = 0;
       const bool std_cfg = NS == OZ_DEFAULT_DIGITS && NG == OZ_DEFAULT_DIAGONALS;
+      const bool fast_cfg = NS == 4 && NG == 4;
       for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
         for (int p = 0; p < n_pass; ++p, ++pcount) {
           const unsigned par = pcount & 1;
@@ -452,6 +453,9 @@ ozaki_kernel(const OzakiArgs args) {
                   issue_pass<OZ_DEFAULT_DIGITS, OZ_DEFAULT_DIAGONALS, 0>(tmem_base, base, first_k, last_k, tfull, tempty, par, args.b_unsigned != 0);
                 else
                   issue_pass<OZ_DEFAULT_DIGITS, OZ_DEFAULT_DIAGONALS, 1>(tmem_base, base, first_k, last_k, tfull, tempty, par, args.b_unsigned != 0);
+              } else if (fast_cfg) {
+                // reduced-precision configuration (DKG_PLAN_FAST32): 4 digits, 4 diagonals, one pass
+                issue_pass<4, 4, 0>(tmem_base, base, first_k, last_k, tfull, tempty, par, args.b_unsigned != 0);
               } else {
                 int e = 0;
                 for (int a = 0; a < OZ_ACC; ++a) {

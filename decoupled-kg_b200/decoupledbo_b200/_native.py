@@ -170,6 +170,10 @@ def profile_read():
     return {name: (float(ms[k]), int(cnt[k])) for k, name in enumerate(PROFILE_CATEGORIES)}
 
 
+PLAN_DEFAULT = 0
+PLAN_FAST32 = 1  # DKG_PLAN_FAST32: 4-digit covariance contraction (float32-class accuracy of that term)
+
+
 class Plan:
     """Candidate-independent state of one acquisition function (``dkg_plan``)."""
 
@@ -179,6 +183,7 @@ class Plan:
         x_discretisation: Tensor,
         scalarisation_weights: Tensor,
         target_output_ix: Optional[int],
+        flags: int = 0,
     ):
         self._handle = c_void_p(0)
         lib = load_library()
@@ -218,7 +223,7 @@ class Plan:
         with torch.cuda.device(dev):
             rc = lib.dkg_plan_create(
                 objs, M, d, _ptr(xd), self.N, ctypes.cast(w_host, POINTER(c_double)), self.S,
-                self.target, 0, _stream_ptr(), byref(handle),
+                self.target, int(flags), _stream_ptr(), byref(handle),
             )
         _check(rc, "dkg_plan_create")
         self._handle = handle

@@ -150,9 +150,26 @@ class DiscreteKnowledgeGradient(AcquisitionFunction):
         self.scalarisation_weights = scalarisation_weights
         self.target_output_ix = target_output_ix
         self._plan = None
+        self._precision = "float64"
 
     def set_X_pending(self, X_pending: Optional[Tensor] = None) -> None:
         raise UnsupportedError(f"{type(self).__name__} does not account for X_pending yet.")
+
+    # -- precision (an addition to the reference surface; the constructor is unchanged) ---------
+    @property
+    def precision(self) -> str:
+        """``"float64"`` (default; rel 1e-9 against the reference) or ``"float32"``: the covariance
+        contraction keeps 4 base-256 digits per operand (10 int8 digit products instead of 34), the
+        rest of the path stays float64.  Tolerance in that mode: ``|dKG| <= 1e-4 |KG| + 1e-7 max|a|``."""
+        return self._precision
+
+    @precision.setter
+    def precision(self, value: str) -> None:
+        if value not in ("float64", "float32"):
+            raise ValueError(f"precision must be 'float64' or 'float32'; got {value!r}")
+        if value != self._precision:
+            self.invalidate()
+            self._precision = value
 
     # -- native state -------------------------------------------------------------------------
     def _get_plan(self) -> "_native.Plan":
@@ -163,8 +180,9 @@ class DiscreteKnowledgeGradient(AcquisitionFunction):
                     f"Input 'model' must be a 'ModelListGP'. Got {type(self.model)=}."
                 )
             state: GPModelList = extract_gp_state(self.model)
+            flags = _native.PLAN_FAST32 if self._precision == "float32" else _native.PLAN_DEFAULT
             self._plan = _native.Plan(
-                state, self.x_discretisation, self.scalarisation_weights, self.target_output_ix
+                state, self.x_discretisation, self.scalarisation_weights, self.target_output_ix, flags
             )
         return self._plan
 

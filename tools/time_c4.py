@@ -13,6 +13,7 @@ dev = torch.device("cuda")
 X = P.candidates.to(dev)
 for tgt in (0, 1):
     acq = DiscreteKnowledgeGradient(P.model, P.x_disc.to(dev), P.weights, target_output_ix=tgt)
+    acq.precision = os.environ.get("PREC", "float64")
     torch.cuda.synchronize(); t0 = time.time(); plan = acq._get_plan(); torch.cuda.synchronize(); print("plan %.1f ms" % ((time.time() - t0) * 1e3))
     for grad in (False, True):
         for rep in range(3):

@@ -260,6 +260,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (VERSION prints a banner there)
         dist.init_process_group("nccl", device_id=dev)
 
     n_cand = args.candidates or (4096 if args.workload == "c4" else 512)

@@ -350,15 +350,27 @@ def main():
     if not args.no_e2e:
         X_host = P.candidates.clone().pin_memory()
 
-        def step_host():
-            out = []
-            for acq in acqs:
+        # one host thread + CUDA stream per objective: the objectives are independent acquisition
+        # functions, ctypes releases the GIL inside dkg_forward_host, so their copies and kernels overlap
+        from concurrent.futures import ThreadPoolExecutor
+
+        pool = ThreadPoolExecutor(max_workers=len(acqs))
+        host_streams = [torch.cuda.Stream(device=dev) for _ in acqs]
+
+        def eval_objective(i):
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(host_streams[i]):
                 X = X_host.detach().requires_grad_(True)  # fresh leaf over the pinned buffer
-                kg = acq(X.unsqueeze(1))  # public API: (*b) x 1 x d -> (*b)
+                kg = acqs[i](X.unsqueeze(1))  # public API: (*b) x 1 x d -> (*b)
                 loss = -kg.sum()
                 (g,) = torch.autograd.grad(loss, X)
+            return kg.detach(), g
+
+        def step_host():
+            out = []
+            for kg, g in pool.map(eval_objective, range(len(acqs))):
                 if world > 1:
-                    send = torch.cat([kg.detach().unsqueeze(1), g], dim=1).to(dev)
+                    send = torch.cat([kg.unsqueeze(1), g], dim=1).to(dev)
                     dist.all_gather_into_tensor(gather_buf, send)
                     out.append(int(gather_buf[:, 0].argmax()))
                 else:
@@ -381,7 +393,8 @@ def main():
             "h2d_bytes_per_step": M * n_cand * d * 8,
             "d2h_bytes_per_step": M * n_cand * (1 + d) * 8,
             "ms_per_step": 1e3 * float(t_e2e) / args.steps,
-            "api": "DiscreteKnowledgeGradient.forward(X_host) + autograd.grad -> dkg_forward_host",
+            "api": "DiscreteKnowledgeGradient.forward(X_host) + autograd.grad -> dkg_forward_host; one host "
+                   "thread and CUDA stream per objective",
         }
 
     # ---- roofline of the dominant kernel (separate profiled steps, CUDA events per launch) ----

@@ -142,9 +142,9 @@ static int ensure_workspace(dkg_plan* p, int C) {
   { SurvEntry* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * SURV_CAP, false)); w.surv = t; }
   DKG_TRY(dev_alloc(&w.far, (size_t)chunk * S * 2));
   { double4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S, false)); w.chain = t; }
-  if (!coupled) { float4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * 2, false)); w.chain32 = t; }
-  if (!coupled) { double4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * 2, false)); w.chainv = t; }
-  if (!coupled) { double4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * 2, false)); w.chain5 = t; }
+  { float4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * 2, false)); w.chain32 = t; }
+  { double4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * 2, false)); w.chainv = t; }
+  { double4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * 2, false)); w.chain5 = t; }
   DKG_TRY(dev_alloc(&w.ovf_sets, (size_t)chunk * S, false));
   DKG_TRY(dev_alloc(&w.ovf_count, (size_t)1));
   DKG_TRY(dev_alloc(&w.hull_cnt, (size_t)chunk * S));
@@ -567,8 +567,8 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
       for (int k = 0; k < MAX_D; ++k) xa.ls[q][k] = oq.ls[k];
     }
     xa.W = p->W; xa.Xs = w.Xs; xa.KX = w.KXm[m]; xa.n_pad = o.ldk; xa.a_new = w.a_new;
-    DKG_TRY(launch_xprep(xa, st));  // (a_new / means are recomputed identically each time)
-    DKG_TRY(solve_T(o, w.KXm[m], w.Tm[m], w.R, C, C_pad, st));
+    { ProfScope ps(0, st); DKG_TRY(launch_xprep(xa, st)); }  // (a_new / means are recomputed identically each time)
+    { ProfScope ps(1, st); DKG_TRY(solve_T(o, w.KXm[m], w.Tm[m], w.R, C, C_pad, st)); }
     // var = noisy variance (un-standardised) -> w.var reused per objective below via varlat
     DKG_TRY(launch_var(w.KXm[m], o.ldk, w.Tm[m], o.ldk, o.n, C, o.kernel, o.outputscale, o.noise,
                        o.y_std * o.y_std, w.varlat[m], w.sd, w.zown, st));
@@ -591,18 +591,19 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
       ep.xs = w.Xs; ep.xd_s = o.xd_s; ep.sd = w.sd; ep.Z = w.COVm[m];
       ep.ldz = p->ldz; ep.C = cc; ep.N = N; ep.d = d; ep.kind = o.kernel;
       ep.outputscale = o.outputscale; ep.ystd2 = o.y_std * o.y_std;
-      DKG_TRY(cov_rows(o, p, w, w.Tm[m] + (size_t)c0 * o.ldk, cc, cc_pad, ep, st));
+      { ProfScope ps(3, st); DKG_TRY(cov_rows(o, p, w, w.Tm[m] + (size_t)c0 * o.ldk, cc, cc_pad, ep, st)); }
       DKG_TRY(place_latent_var(w.KXm[m] + (size_t)c0 * o.ldk, o.ldk, w.Tm[m] + (size_t)c0 * o.ldk,
                                o.ldk, o.n, cc, o.kernel, o.outputscale, o.y_std * o.y_std,
                                w.COVm[m], p->ldz, N, st));
       ca.COV[m] = w.COVm[m];
       ca.varn[m] = w.varlat[m] + c0;
     }
-    DKG_TRY(coupled_slopes(ca, st));
+    { ProfScope ps(4, st); DKG_TRY(coupled_slopes(ca, st)); }  // (profile category 4: slope assembly)
 
     LineBatch lb;
     lb.Z = w.Zc; lb.ldz = p->ldz;
     lb.A = p->A0; lb.a_sc = 0; lb.a_sj = p->N_pad;
+    lb.A32 = p->A0f;
     lb.a_own = w.a_new + (size_t)c0 * S;
     lb.wt = nullptr;
     lb.Amax = p->A0max; lb.Aarg = p->A0arg; lb.am_sc = 0;
@@ -610,12 +611,13 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
     EmaxScratch sc;
     sc.zst = w.zst; sc.zarg = w.zarg; sc.surv_cnt = w.surv_cnt; sc.surv = (SurvEntry*)w.surv;
     sc.ovf_sets = w.ovf_sets; sc.ovf_count = w.ovf_count; sc.far = w.far; sc.chain = (double4*)w.chain;
+    sc.chain32 = (float4*)w.chain32; sc.chainv = (double4*)w.chainv; sc.chain5 = (double4*)w.chain5;
     sc.stats = w.stats;
     DKG_CUDA_OK(cudaMemsetAsync(w.surv_cnt, 0, sizeof(int) * (size_t)cc * S, st));
     DKG_CUDA_OK(cudaMemsetAsync(w.far, 0, sizeof(unsigned long long) * (size_t)cc * S * 2, st));
     DKG_CUDA_OK(cudaMemsetAsync(w.ovf_count, 0, sizeof(int), st));
-    DKG_TRY(emax_zstat(lb, sc, nullptr, nullptr, st));
-    DKG_TRY(emax_filter(lb, sc, st));
+    { ProfScope ps(5, st); DKG_TRY(emax_zstat(lb, sc, nullptr, nullptr, st)); }
+    { ProfScope ps(6, st); DKG_TRY(emax_filter(lb, sc, st)); }
     EmaxOut out;
     out.terms = w.kg_terms + (size_t)c0 * S;
     out.subtract_max = 1;
@@ -623,8 +625,8 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
     out.hull_x = nullptr; out.hull_cap = HULL_CAP; out.amax_is_own = w.amax_is_new;
     out.kg = kg + c0;
     out.truncated = w.stats + 6;
-    DKG_TRY(emax_hull(lb, sc, out, st));
-    DKG_TRY(emax_overflow(lb, sc, out, st));
+    { ProfScope ps(7, st); DKG_TRY(emax_hull(lb, sc, out, st)); }
+    { ProfScope ps(8, st); DKG_TRY(emax_overflow(lb, sc, out, st)); }
     CoupledBackward bw;
     if (dX != nullptr) {
       bw.dX = dX + (size_t)c0 * d; bw.X = X + (size_t)c0 * d; bw.W = p->W; bw.Zc = w.Zc;
@@ -637,7 +639,7 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
         for (int k = 0; k < MAX_D; ++k) bw.ls[m][k] = o.ls[k];
       }
     }
-    DKG_TRY(emax_finalize_coupled(cc, S, out, bw, st));
+    { ProfScope ps(9, st); DKG_TRY(emax_finalize_coupled(cc, S, out, bw, st)); }
   }
   return DKG_OK;
 }

@@ -735,7 +735,9 @@ __device__ __forceinline__ int line_block(int i, int step, int nsb, bool phase2)
   return nsb * step + (i - body);
 }
 
-template <int G, bool REFINE>
+// ROWS: the coupled path -- every row is its own set (S == 1) and row r reads the intercept row
+// r % row_mod of the shared table, so the G rows of a CTA carry G different intercept rows.
+template <int G, bool REFINE, bool ROWS>
 __global__ void __launch_bounds__(F32_THREADS, 7)
 filter32_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb) {
   static_assert(G == 4, "bit layout below assumes 4 candidates x 4 lines");
@@ -773,36 +775,45 @@ filter32_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb) {
   const float ninf = -INFINITY;
   float4 a_nx = make_float4(ninf, ninf, ninf, ninf);
   const float* ap = lb.A32 + n0;
-  if (live) a_nx = *reinterpret_cast<const float4*>(ap);
+  if (live && !ROWS) a_nx = *reinterpret_cast<const float4*>(ap);
   const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
   int wcnt = 0;  // entries in this warp's pool (warp-uniform)
   __syncthreads();
 
   for (int j = 0; j < S; ++j) {
-    const float4 a = a_nx;
-    ap += lb.a_sj;
-    if (live && j + 1 < S) a_nx = *reinterpret_cast<const float4*>(ap);
+    float4 ag[G];
+    if (ROWS) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        ag[g] = make_float4(ninf, ninf, ninf, ninf);
+        if (live) ag[g] = *reinterpret_cast<const float4*>(lb.A32 + (size_t)(min(c0 + g, lb.C - 1) % lb.row_mod) * lb.a_sj + n0);
+      }
+    } else {
+      ag[0] = ag[1] = ag[2] = ag[3] = a_nx;
+      ap += lb.a_sj;
+      if (live && j + 1 < S) a_nx = *reinterpret_cast<const float4*>(ap);
+    }
     const ulonglong2* pj = s_p32 + (size_t)j * (2 * G);
     unsigned mask = 0u;
     {
       const ulonglong2 q1 = pj[0], q2 = pj[1];
-      mask = pair_test32<1u << 0>(mask, q1.x, q1.y, q2.x, q2.y, zp[0][0], a.x, a.y);
-      mask = pair_test32<1u << 2>(mask, q1.x, q1.y, q2.x, q2.y, zp[0][1], a.z, a.w);
+      mask = pair_test32<1u << 0>(mask, q1.x, q1.y, q2.x, q2.y, zp[0][0], ag[0].x, ag[0].y);
+      mask = pair_test32<1u << 2>(mask, q1.x, q1.y, q2.x, q2.y, zp[0][1], ag[0].z, ag[0].w);
     }
     {
       const ulonglong2 q1 = pj[2], q2 = pj[3];
-      mask = pair_test32<1u << 4>(mask, q1.x, q1.y, q2.x, q2.y, zp[1][0], a.x, a.y);
-      mask = pair_test32<1u << 6>(mask, q1.x, q1.y, q2.x, q2.y, zp[1][1], a.z, a.w);
+      mask = pair_test32<1u << 4>(mask, q1.x, q1.y, q2.x, q2.y, zp[1][0], ag[1].x, ag[1].y);
+      mask = pair_test32<1u << 6>(mask, q1.x, q1.y, q2.x, q2.y, zp[1][1], ag[1].z, ag[1].w);
     }
     {
       const ulonglong2 q1 = pj[4], q2 = pj[5];
-      mask = pair_test32<1u << 8>(mask, q1.x, q1.y, q2.x, q2.y, zp[2][0], a.x, a.y);
-      mask = pair_test32<1u << 10>(mask, q1.x, q1.y, q2.x, q2.y, zp[2][1], a.z, a.w);
+      mask = pair_test32<1u << 8>(mask, q1.x, q1.y, q2.x, q2.y, zp[2][0], ag[2].x, ag[2].y);
+      mask = pair_test32<1u << 10>(mask, q1.x, q1.y, q2.x, q2.y, zp[2][1], ag[2].z, ag[2].w);
     }
     {
       const ulonglong2 q1 = pj[6], q2 = pj[7];
-      mask = pair_test32<1u << 12>(mask, q1.x, q1.y, q2.x, q2.y, zp[3][0], a.x, a.y);
-      mask = pair_test32<1u << 14>(mask, q1.x, q1.y, q2.x, q2.y, zp[3][1], a.z, a.w);
+      mask = pair_test32<1u << 12>(mask, q1.x, q1.y, q2.x, q2.y, zp[3][0], ag[3].x, ag[3].y);
+      mask = pair_test32<1u << 14>(mask, q1.x, q1.y, q2.x, q2.y, zp[3][1], ag[3].z, ag[3].w);
     }
     for (;;) {  // survivors are rare (~1 % of the tests)
       const unsigned vote = __ballot_sync(0xffffffffu, mask != 0u);
@@ -837,20 +848,25 @@ static int launch_filter32(const LineBatch& lb, const EmaxScratch& sc, cudaStrea
   const unsigned gy = ceil_div(lb.C, G);
   const size_t smem = (size_t)G * lb.S * (2 * sizeof(ulonglong2) + 2 * sizeof(unsigned long long)) +
                       (F32_THREADS / 32) * WPOOL * sizeof(int2);
+  const bool rows = lb.row_mod > 0;
   if (smem > 48 * 1024) {
-    DKG_CUDA_OK(cudaFuncSetAttribute(filter32_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DKG_CUDA_OK(cudaFuncSetAttribute(filter32_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DKG_CUDA_OK(cudaFuncSetAttribute(filter32_kernel<G, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DKG_CUDA_OK(cudaFuncSetAttribute(filter32_kernel<G, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   // two sampled blocks (1024 lines) out of >= 8; smaller rows are filtered in one launch
   const bool two_phase = sc.chain5 != nullptr && sc.chainv != nullptr && nblk >= 8;
-  const int nsb = two_phase ? 2 : nblk, step = two_phase ? nblk / 2 : 1;
-  filter32_kernel<G, false><<<dim3(nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
+  int sample_blocks = 2;
+  if (const char* e = getenv("DKG_FILTER_NSB")) sample_blocks = atoi(e) >= 1 && atoi(e) <= nblk / 4 ? atoi(e) : 2;
+  const int nsb = two_phase ? sample_blocks : nblk, step = two_phase ? nblk / sample_blocks : 1;
+  if (rows) filter32_kernel<G, false, true><<<dim3(nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
+  else filter32_kernel<G, false, false><<<dim3(nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
   DKG_LAUNCH_CHECK();
   if (two_phase) {
     const long long sets = (long long)lb.C * lb.S;
     chain5_kernel<<<(unsigned)((sets + E_THREADS - 1) / E_THREADS), E_THREADS, 0, st>>>(lb, sc);
     DKG_LAUNCH_CHECK();
-    filter32_kernel<G, true><<<dim3(nblk - nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
+    if (rows) filter32_kernel<G, true, true><<<dim3(nblk - nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
+    else filter32_kernel<G, true, false><<<dim3(nblk - nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
     DKG_LAUNCH_CHECK();
   }
   return DKG_OK;
@@ -883,7 +899,7 @@ int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st) {
   // (DKG_FILTER=f32 uses it for small batches too: tests)
   const char* fe = getenv("DKG_FILTER");  // read per launch so tests can compare the two kernels
   const int mode = fe == nullptr ? 0 : strcmp(fe, "f64") == 0 ? 1 : strcmp(fe, "f32") == 0 ? 2 : 0;
-  if (mode != 1 && lb.A32 != nullptr && sc.chain32 != nullptr && lb.a_sc == 0 && lb.row_mod == 0 &&
+  if (mode != 1 && lb.A32 != nullptr && sc.chain32 != nullptr && lb.a_sc == 0 && (lb.row_mod == 0 || lb.S == 1) &&
       (lb.ldz & 1) == 0 && (lb.a_sj & 3) == 0 && lb.ldz >= ((lb.NA + 3) & ~3) && lb.a_sj >= ((lb.NA + 3) & ~3) &&
       (ctas4 >= 148 || mode == 2))
     return launch_filter32(lb, sc, st);

@@ -75,3 +75,16 @@ def test_huge_scales_fall_back_to_keeping_everything():
             kg32, g32, _ = _eval(P, target, P.candidates, "f32")
             assert torch.equal(kg64, kg32)
             assert torch.equal(g64, g32)
+
+
+def test_coupled_rows_bits_equal():
+    """Coupled evaluation (target_output_ix=None): every (candidate, scalarisation) row is its own set."""
+    from decoupledbo_b200 import synthetic
+
+    P = synthetic.make_problem(
+        "f32c", 3, 60, [0.3, 0.5], [1.0, 2.0], [0.3, 0.05], [1e-1, 1e-3],
+        synthetic.sobol(5000, 3, 5), 8, 96, seed_train=6, seed_cand=7, seed_w=1)
+    kg64, g64, _ = _eval(P, None, P.candidates, "f64")
+    kg32, g32, _ = _eval(P, None, P.candidates, "f32")
+    assert torch.equal(kg64, kg32)
+    assert torch.equal(g64, g32)

@@ -123,10 +123,10 @@ static int ensure_workspace(dkg_plan* p, int C) {
   DKG_TRY(dev_alloc(&w.Z, coupled ? (size_t)1 : (size_t)chunk * p->ldz));
   DKG_TRY(dev_alloc(&w.zst, (size_t)chunk * rows_per_cand * 2));
   DKG_TRY(dev_alloc(&w.zarg, (size_t)chunk * rows_per_cand * 2));
-  if (!coupled) {  // tiles of >= 1024 lines (64 KB of points at d <= 8)
-    const size_t tiles = (size_t)(p->N / 1024 + 1);
-    DKG_TRY(dev_alloc(&w.zpv, (size_t)chunk * tiles * 2));
-    DKG_TRY(dev_alloc(&w.zpi, (size_t)chunk * tiles * 2));
+  {  // tiles of >= 1024 lines (64 KB of points at d <= 8); coupled: one row per (candidate, scalarisation)
+    const size_t tiles = (size_t)(p->N / 1024 + 2);
+    DKG_TRY(dev_alloc(&w.zpv, (size_t)chunk * rows_per_cand * tiles * 2));
+    DKG_TRY(dev_alloc(&w.zpi, (size_t)chunk * rows_per_cand * tiles * 2));
   }
   if (coupled) {
     for (int m = 0; m < p->M; ++m) {
@@ -582,6 +582,7 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
     CoupledArgs ca;
     ca.C = cc; ca.S = S; ca.M = M; ca.d = d; ca.N = N; ca.ldz = p->ldz;
     ca.W = p->W; ca.sdj = w.sdj + (size_t)c0 * S; ca.Zc = w.Zc;
+    ca.zpv = w.zpv; ca.zpi = w.zpi;
     for (int m = 0; m < M; ++m) {
       const ObjState& o = p->obj[m];
       // covariance rows of objective m: same GEMM as the decoupled path with sd = 1
@@ -616,7 +617,8 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
     DKG_CUDA_OK(cudaMemsetAsync(w.surv_cnt, 0, sizeof(int) * (size_t)cc * S, st));
     DKG_CUDA_OK(cudaMemsetAsync(w.far, 0, sizeof(unsigned long long) * (size_t)cc * S * 2, st));
     DKG_CUDA_OK(cudaMemsetAsync(w.ovf_count, 0, sizeof(int), st));
-    { ProfScope ps(5, st); DKG_TRY(emax_zstat(lb, sc, nullptr, nullptr, st)); }
+    sc.zpv = w.zpv; sc.zpi = w.zpi;
+    { ProfScope ps(5, st); DKG_TRY(emax_zstat_from_partials(lb, sc, (N + 1 + CS_TILE_LINES - 1) / CS_TILE_LINES, st)); }
     { ProfScope ps(6, st); DKG_TRY(emax_filter(lb, sc, st)); }
     EmaxOut out;
     out.terms = w.kg_terms + (size_t)c0 * S;

@@ -338,6 +338,16 @@ int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int
   return DKG_OK;
 }
 
+int emax_zstat_from_partials(const LineBatch& lb, const EmaxScratch& sc, int ntiles, cudaStream_t st) {
+  if (lb.C == 0) return DKG_OK;
+  zreduce_kernel<<<ceil_div(lb.C, 128), 128, 0, st>>>(lb, lb.NL, ntiles, sc.zpv, sc.zpi, sc.zst, sc.zarg);
+  DKG_LAUNCH_CHECK();
+  const long long sets = (long long)lb.C * lb.S;
+  chain_kernel<<<(unsigned)((sets + E_THREADS - 1) / E_THREADS), E_THREADS, 0, st>>>(lb, sc);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // per-set facts shared by all stages
 // ------------------------------------------------------------------------------------------
@@ -849,7 +859,7 @@ static int launch_filter32(const LineBatch& lb, const EmaxScratch& sc, cudaStrea
   const size_t smem = (size_t)G * lb.S * (2 * sizeof(ulonglong2) + 2 * sizeof(unsigned long long)) +
                       (F32_THREADS / 32) * WPOOL * sizeof(int2);
   const bool rows = lb.row_mod > 0;
-  if (smem > 48 * 1024) {
+  if (smem > 47 * 1024) {
     DKG_CUDA_OK(cudaFuncSetAttribute(filter32_kernel<G, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DKG_CUDA_OK(cudaFuncSetAttribute(filter32_kernel<G, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
@@ -877,7 +887,7 @@ static int launch_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_
   dim3 grid(ceil_div(lb.NA, E_THREADS * R), ceil_div(lb.C, G));
   const size_t smem = (size_t)G * lb.S * (sizeof(double4) + 3 * sizeof(int) + 2 * sizeof(unsigned long long)) +
                       POOL_CAP * sizeof(int2);
-  if (smem > 48 * 1024) {  // many scalarisations: opt in to large dynamic shared memory
+  if (smem > 47 * 1024) {  // many scalarisations: opt in to large dynamic shared memory
     DKG_CUDA_OK(cudaFuncSetAttribute(filter_kernel<G, R, true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DKG_CUDA_OK(cudaFuncSetAttribute(filter_kernel<G, R, false>,
@@ -1821,7 +1831,7 @@ int emax_finalize(const LineBatch& lb, const EmaxOut& out, const BackwardArgs& b
   const int fin_threads = fte != nullptr && (atoi(fte) == 256 || atoi(fte) == 64) ? atoi(fte) : 128;
 #define DKG_FINALIZE(DD)                                                                                       \
   do {                                                                                                         \
-    if (smem > 48 * 1024)                                                                                      \
+    if (smem > 47 * 1024)                                                                                      \
       DKG_CUDA_OK(cudaFuncSetAttribute(finalize_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     finalize_kernel<DD><<<lb.C, fin_threads, smem, st>>>(lb, out, bw);                                         \
   } while (0)

@@ -112,6 +112,9 @@ struct CovFinish {
 };
 int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int* aarg_out,
                cudaStream_t st, const CovFinish* fin = nullptr);
+// row statistics from per-tile partials (sc.zpv / sc.zpi filled by the producer of the slope rows),
+// then the chord chains: replaces emax_zstat when the producer already saw every slope
+int emax_zstat_from_partials(const LineBatch& lb, const EmaxScratch& sc, int ntiles, cudaStream_t st);
 int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st);
 // warp-per-set exact hull + closed-form expectation; sets it cannot finish go to the queue
 int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cudaStream_t st);
@@ -129,7 +132,12 @@ struct CoupledArgs {
   const double* varn[MAX_M] = {};   // [C] noisy predictive variance of objective m (un-standardised)
   double* sdj = nullptr;            // [C, S] out: sqrt of the scalarised noisy variance
   double* Zc = nullptr;             // [C * S, ldz] out: slope rows
+  // optional: per-(row, tile) min / max of the finished slope rows (first index wins ties), so the row
+  // statistics need no second pass over Zc; tile = CS_TILE_LINES consecutive entries of the N + 1
+  double* zpv = nullptr;            // [C * S, tiles, 2]
+  int* zpi = nullptr;               // [C * S, tiles, 2]
 };
+constexpr int CS_TILE_LINES = 2048;
 int coupled_slopes(const CoupledArgs& a, cudaStream_t st);
 
 struct CoupledBackward {

@@ -88,3 +88,34 @@ def test_coupled_rows_bits_equal():
     kg32, g32, _ = _eval(P, None, P.candidates, "f32")
     assert torch.equal(kg64, kg32)
     assert torch.equal(g64, g32)
+
+
+def test_tiled_statistics_pass_matches_row_pass_on_ragged_sizes():
+    """zfinish_tiled_kernel (large batches) against zstat_kernel (DKG_ZSTAT_ROWS=1): same bits, with N
+    and C that are not multiples of any tile."""
+    from decoupledbo_b200 import synthetic
+    from decoupledbo_b200.modules.acquisition.discretekg import DiscreteKnowledgeGradient
+
+    P = synthetic.make_problem(
+        "tile", 3, 45, [0.3, 0.5], [1.0, 2.0], [0.3, 0.05], [1e-1, 1e-3],
+        synthetic.sobol(4099, 3, 5), 6, 1100, seed_train=6, seed_cand=7, seed_w=1)
+    dev = torch.device("cuda")
+    X = P.candidates.to(dev)
+    out = {}
+    for mode in ("tiled", "rows"):
+        if mode == "rows":
+            os.environ["DKG_ZSTAT_ROWS"] = "1"
+        try:
+            res = []
+            for target in (0, 1):
+                acq = DiscreteKnowledgeGradient(P.model, P.x_disc.to(dev), P.weights, target_output_ix=target)
+                Xg = X.clone().requires_grad_(True)
+                kg = acq(Xg.unsqueeze(1))
+                (g,) = torch.autograd.grad(kg.sum(), Xg)
+                res.append((kg.detach().clone(), g.clone()))
+            out[mode] = res
+        finally:
+            os.environ.pop("DKG_ZSTAT_ROWS", None)
+    for (kg_t, g_t), (kg_r, g_r) in zip(out["tiled"], out["rows"]):
+        assert torch.equal(kg_t, kg_r)
+        assert torch.equal(g_t, g_r)

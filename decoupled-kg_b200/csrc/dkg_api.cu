@@ -124,7 +124,7 @@ static int ensure_workspace(dkg_plan* p, int C) {
   DKG_TRY(dev_alloc(&w.zst, (size_t)chunk * rows_per_cand * 2));
   DKG_TRY(dev_alloc(&w.zarg, (size_t)chunk * rows_per_cand * 2));
   {  // tiles of >= 1024 lines (64 KB of points at d <= 8); coupled: one row per (candidate, scalarisation)
-    const size_t tiles = (size_t)(p->N / 1024 + 2);
+    const size_t tiles = coupled ? (size_t)((p->N + 1) / CS_TILE_LINES + 2) : (size_t)(p->N / 1024 + 2);
     DKG_TRY(dev_alloc(&w.zpv, (size_t)chunk * rows_per_cand * tiles * 2));
     DKG_TRY(dev_alloc(&w.zpi, (size_t)chunk * rows_per_cand * tiles * 2));
   }

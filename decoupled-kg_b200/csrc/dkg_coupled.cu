@@ -48,41 +48,26 @@ coupled_slopes_kernel(CoupledArgs a) {
   }
 }
 
-// Same slope rows, plus the row statistics while the values are in registers: a CTA keeps the M
-// covariance segments of one (candidate, tile of lines) in shared memory, walks the scalarisations,
-// writes each slope once and reduces min / max (first index wins ties) per (row, tile).  The separate
-// statistics pass re-read all of Zc (8.6 GB at c4: 2.6 ms).
-__device__ __forceinline__ void cs_block_arg(double& v, int& i, bool is_min, double* s_v, int* s_i) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-    if ((is_min ? ov < v : ov > v) || (ov == v && oi < i)) { v = ov; i = oi; }
-  }
-  __syncthreads();
-  if (lane == 0) { s_v[warp] = v; s_i[warp] = i; }
-  __syncthreads();
-  v = s_v[0]; i = s_i[0];
-  for (int k = 1; k < nw; ++k) {
-    const double ov = s_v[k];
-    const int oi = s_i[k];
-    if ((is_min ? ov < v : ov > v) || (ov == v && oi < i)) { v = ov; i = oi; }
-  }
-}
-
+// Same slope rows, plus the row statistics while the values are in registers.  Every WARP owns one
+// segment of CS_TILE_LINES lines of one candidate: it keeps the M covariance segments in shared
+// memory, walks the scalarisations, writes each slope once and reduces min / max (first index wins
+// ties) with shuffles only -- no CTA barrier after the load.  The separate statistics pass re-read
+// all of Zc (8.6 GB at c4: 2.6 ms).
+// The quotient s / sd uses the correctly rounded reciprocal of the row's sd and one residual step,
+//   q = s r;  q' = q + (s - q sd) r      (Markstein: q' = RN(s / sd) for r = RN(1 / sd)),
+// 3 fp64 instructions instead of the ~25 of a full division, of which this kernel would need 1.07e9.
 __global__ void __launch_bounds__(CP_THREADS)
-coupled_slopes_stats_kernel(CoupledArgs a, int ntiles) {
+coupled_slopes_stats_kernel(CoupledArgs a, int nseg) {
   extern __shared__ __align__(16) unsigned char c_smem[];
-  double* s_cov = reinterpret_cast<double*>(c_smem);  // [M][CS_TILE_LINES]
-  __shared__ double s_v[CP_THREADS / 32];
-  __shared__ int s_i[CP_THREADS / 32];
-  const int tile = blockIdx.x, c = blockIdx.y;
-  const int n_lo = tile * CS_TILE_LINES;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int seg = blockIdx.x * nwarp + warp, c = blockIdx.y;
+  if (seg >= nseg) return;
+  double* s_cov = reinterpret_cast<double*>(c_smem) + (size_t)warp * a.M * CS_TILE_LINES;  // [M][CS_TILE_LINES]
+  const int n_lo = seg * CS_TILE_LINES;
   const int n_cnt = min(CS_TILE_LINES, a.N + 1 - n_lo);  // column N is the candidate's own line
   for (int m = 0; m < a.M; ++m)
-    for (int i = threadIdx.x; i < n_cnt; i += blockDim.x)
-      s_cov[m * CS_TILE_LINES + i] = a.COV[m][(size_t)c * a.ldz + n_lo + i];
-  __syncthreads();
+    for (int i = lane; i < n_cnt; i += 32) s_cov[m * CS_TILE_LINES + i] = a.COV[m][(size_t)c * a.ldz + n_lo + i];
+  __syncwarp();
   for (int j = 0; j < a.S; ++j) {
     double w2[MAX_M];
 #pragma unroll
@@ -92,23 +77,38 @@ coupled_slopes_stats_kernel(CoupledArgs a, int ntiles) {
     }
     const size_t row = (size_t)c * a.S + j;
     const double sd = a.sdj[row];
+    const double rinv = 1.0 / sd;
+    const bool fast = sd > 1e-290 && sd < 1e290;  // otherwise: plain division (same special values)
     double* zrow = a.Zc + row * a.ldz + n_lo;
     double vmin = INFINITY, vmax = -INFINITY;
     int imin = 0x7fffffff, imax = 0x7fffffff;
-    for (int i = threadIdx.x; i < n_cnt; i += blockDim.x) {
+#pragma unroll 4
+    for (int i = lane; i < n_cnt; i += 32) {
       double s = 0.0;
 #pragma unroll
       for (int m = 0; m < MAX_M; ++m)
         if (m < a.M) s += w2[m] * s_cov[m * CS_TILE_LINES + i];
-      const double z = s / sd;
+      double z;
+      if (fast) {
+        const double q = s * rinv;
+        z = fma(fma(-q, sd, s), rinv, q);
+      } else {
+        z = s / sd;
+      }
       zrow[i] = z;
       if (z < vmin) { vmin = z; imin = n_lo + i; }
       if (z > vmax) { vmax = z; imax = n_lo + i; }
     }
-    cs_block_arg(vmin, imin, true, s_v, s_i);
-    cs_block_arg(vmax, imax, false, s_v, s_i);
-    if (threadIdx.x == 0) {
-      const size_t q = (row * ntiles + tile) * 2;
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, vmin, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, imin, o);
+      if (ov < vmin || (ov == vmin && oi < imin)) { vmin = ov; imin = oi; }
+      const double pv = __shfl_xor_sync(0xffffffffu, vmax, o);
+      const int pi = __shfl_xor_sync(0xffffffffu, imax, o);
+      if (pv > vmax || (pv == vmax && pi < imax)) { vmax = pv; imax = pi; }
+    }
+    if (lane == 0) {
+      const size_t q = (row * nseg + seg) * 2;
       a.zpv[q] = vmin; a.zpv[q + 1] = vmax;
       a.zpi[q] = imin; a.zpi[q + 1] = imax;
     }
@@ -120,11 +120,12 @@ int coupled_slopes(const CoupledArgs& a, cudaStream_t st) {
   coupled_sd_kernel<<<ceil_div(a.C * a.S, CP_THREADS), CP_THREADS, 0, st>>>(a);
   DKG_LAUNCH_CHECK();
   if (a.zpv != nullptr && a.zpi != nullptr) {
-    const int ntiles = ceil_div(a.N + 1, CS_TILE_LINES);
-    const size_t smem = sizeof(double) * (size_t)a.M * CS_TILE_LINES;
-    if (smem > 40 * 1024)  // (the kernel also has a little static shared memory)
+    const int nseg = ceil_div(a.N + 1, CS_TILE_LINES);
+    const int nwarp = CP_THREADS / 32;
+    const size_t smem = sizeof(double) * (size_t)nwarp * a.M * CS_TILE_LINES;
+    if (smem > 47 * 1024)
       DKG_CUDA_OK(cudaFuncSetAttribute(coupled_slopes_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    coupled_slopes_stats_kernel<<<dim3(ntiles, a.C), CP_THREADS, smem, st>>>(a, ntiles);
+    coupled_slopes_stats_kernel<<<dim3(ceil_div(nseg, nwarp), a.C), CP_THREADS, smem, st>>>(a, nseg);
     DKG_LAUNCH_CHECK();
     return DKG_OK;
   }

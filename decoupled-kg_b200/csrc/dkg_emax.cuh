@@ -137,7 +137,7 @@ struct CoupledArgs {
   double* zpv = nullptr;            // [C * S, tiles, 2]
   int* zpi = nullptr;               // [C * S, tiles, 2]
 };
-constexpr int CS_TILE_LINES = 2048;
+constexpr int CS_TILE_LINES = 256;  // one warp's segment
 int coupled_slopes(const CoupledArgs& a, cudaStream_t st);
 
 struct CoupledBackward {

@@ -145,3 +145,21 @@ def test_synthetic_problem_shapes():
     assert torch.allclose(P.weights.sum(-1), torch.ones(16, dtype=torch.double))
     P2 = synthetic.problem_c2(n_cand=8)
     assert torch.equal(P.candidates, P2.candidates) and torch.equal(P.model.models[1].train_y, P2.model.models[1].train_y)
+
+
+def test_precision_attribute_is_an_addition_not_a_signature_change(problem):
+    """The constructor keeps the reference signature (discretekg.py:62-68); the reduced-precision mode is
+    an attribute, validated on the host, and switching it drops the cached native state."""
+    import inspect
+
+    from decoupledbo_b200.modules.acquisition.discretekg import DiscreteKnowledgeGradient
+
+    params = list(inspect.signature(DiscreteKnowledgeGradient.__init__).parameters)
+    assert params == ["self", "model", "x_discretisation", "scalarisation_weights", "target_output_ix"]
+    P = problem
+    acq = DiscreteKnowledgeGradient(P.model, P.x_disc, P.weights, target_output_ix=0)
+    assert acq.precision == "float64"
+    acq.precision = "float32"
+    assert acq.precision == "float32" and acq._plan is None
+    with pytest.raises(ValueError):
+        acq.precision = "tf32"

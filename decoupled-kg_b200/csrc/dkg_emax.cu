@@ -1324,8 +1324,11 @@ int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cu
 // overflow kernel: one CTA per queued set, all lines, always terminates
 // ------------------------------------------------------------------------------------------
 constexpr int OVF_MAXV = 130;  // chain vertices
-constexpr int FIN_RMAX = 1024; // most hull records per candidate merged in shared memory (32 per scalarisation)
-__host__ __device__ inline int fin_rmax(int S) { const int r = 32 * S; return r < 256 ? 256 : r > FIN_RMAX ? FIN_RMAX : r; }
+constexpr int FIN_RMAX = 2560; // most hull records per candidate merged in shared memory (10 per scalarisation)
+// slots of the distinct-line hash table (a power of two; distinct hull lines per candidate: tens at S = 16,
+// many hundreds at S = 256)
+__host__ __device__ inline int fin_hash_bits(int S) { return S <= 32 ? 10 : 12; }
+__host__ __device__ inline int fin_rmax(int S) { const int r = 10 * S; return r < 256 ? 256 : r > FIN_RMAX ? FIN_RMAX : r; }
 constexpr int OVF_ROUNDS = 6;
 constexpr int OVF_CTAS_PER_SM = 4;
 
@@ -1640,7 +1643,10 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
   int* s_roff = s_flag + RM;                               // [S + 1] record offsets per set
   double* s_rcz = reinterpret_cast<double*>(s_roff + ((S + 2) & ~1));  // [RM] w_j q / S
   double* s_ucz = s_rcz + RM;                              // [RM] merged coefficient
-  __shared__ int s_nrec, s_nuniq;
+  int* s_hkey = reinterpret_cast<int*>(s_ucz + RM);        // [HN] line index held by a slot (-1: free)
+  const int HB = fin_hash_bits(S), HN = 1 << HB;
+  int* s_hfirst = s_hkey + HN;                             // [HN] first record of that line
+  __shared__ int s_nrec, s_nuniq, s_hovf;
   for (int j = threadIdx.x; j < S; j += blockDim.x)
     s_roff[j + 1] = min(out.hull_cnt[(size_t)c * S + j], hcap);  // counts first, scanned below
   __syncthreads();
@@ -1654,10 +1660,12 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
     s_roff[S] = off;
     s_nrec = off;
     s_nuniq = 0;
+    s_hovf = 0;
   }
+  for (int h = threadIdx.x; h < HN; h += blockDim.x) { s_hkey[h] = -1; s_hfirst[h] = 0x7fffffff; }
   __syncthreads();
   const int nrec = s_nrec;
-  const bool merged = nrec <= RM;
+  bool merged = nrec <= RM;
   if (merged) {
     for (int j = warp; j < S; j += nwarps) {
       const size_t set = (size_t)c * S + j;
@@ -1669,14 +1677,27 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
       }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < nrec; e += blockDim.x) {  // first occurrence of its line?
+    // first occurrence of every line through a small hash table: slot claim by compare-and-swap,
+    // first record by atomicMin (order independent, hence deterministic); a quadratic scan here cost
+    // 17 % of the kernel at S = 16 and made S = 256 unusable
+    for (int e = threadIdx.x; e < nrec; e += blockDim.x) {
       const int idx = s_ridx[e];
-      int first = 1;
-      for (int f = 0; f < e; ++f)
-        if (s_ridx[f] == idx) { first = 0; break; }
-      s_flag[e] = first;
+      unsigned h = ((unsigned)idx * 2654435761u) >> (32 - HB);
+      int probes = 0;
+      for (;; h = (h + 1) & (HN - 1)) {
+        const int prev = atomicCAS(&s_hkey[h], -1, idx);
+        if (prev == -1 || prev == idx) break;
+        if (++probes >= HN) { s_hovf = 1; break; }
+      }
+      atomicMin(&s_hfirst[h], e);
+      s_flag[e] = (int)h;
     }
     __syncthreads();
+    for (int e = threadIdx.x; e < nrec; e += blockDim.x) s_flag[e] = s_hfirst[s_flag[e]] == e ? 1 : 0;
+    __syncthreads();
+    if (s_hovf) merged = false;  // more distinct lines than slots: the unmerged loops below
+  }
+  if (merged) {
     for (int e = threadIdx.x; e < nrec; e += blockDim.x) {
       if (!s_flag[e]) continue;
       const int idx = s_ridx[e];
@@ -1826,9 +1847,12 @@ int emax_finalize(const LineBatch& lb, const EmaxOut& out, const BackwardArgs& b
   size_t smem = sizeof(double) * lb.S;
   if (bw.dX != nullptr)
     smem = sizeof(double) * ((size_t)bw.n_pad + 2 * lb.S + 2 + MAX_D + MAX_M + (E_THREADS / 32) * MAX_D) +
-           sizeof(int) * (3 * fin_rmax(lb.S) + ((lb.S + 2) & ~1)) + sizeof(double) * 2 * fin_rmax(lb.S);
+           sizeof(int) * (3 * fin_rmax(lb.S) + ((lb.S + 2) & ~1) + (2 << fin_hash_bits(lb.S))) + sizeof(double) * 2 * fin_rmax(lb.S);
   const char* fte = getenv("DKG_FIN_THREADS");
-  const int fin_threads = fte != nullptr && (atoi(fte) == 256 || atoi(fte) == 64) ? atoi(fte) : 128;
+  // 128-thread CTAs (6 per SM) hide the short barrier-separated phases best; with many scalarisations
+  // the hull records exceed the merge capacity and the per-record loops want the wider CTA
+  const int fin_default = lb.S > 64 ? 256 : 128;
+  const int fin_threads = fte != nullptr && (atoi(fte) == 256 || atoi(fte) == 128 || atoi(fte) == 64) ? atoi(fte) : fin_default;
 #define DKG_FINALIZE(DD)                                                                                       \
   do {                                                                                                         \
     if (smem > 47 * 1024)                                                                                      \

@@ -666,6 +666,9 @@ __device__ __forceinline__ double2 chord_through(double z0, double a0, double z1
 // flight at once, so the L2 round trip is paid per 32 survivors, not per survivor.
 constexpr int F32_THREADS = 128;
 constexpr int WPOOL = 256;
+// scalarisations per CTA (blockIdx.z walks the batches): all of them up to 64 (20 KB of chain
+// parameters, 7 CTAs per SM), batches of 32 beyond
+static inline int f32_jb(int S) { return S <= 64 ? S : 32; }
 
 // The filter runs in two launches.  Phase 1 covers a SAMPLE of the lines (a few line blocks spread
 // over the row) and stores its survivors as they are; the per-set, per-side farthest sampled line
@@ -676,7 +679,7 @@ constexpr int WPOOL = 256;
 // this removes ~70 % of the stored survivors (and the hull-stage work that follows them).
 template <int G, bool REFINE>
 __device__ __forceinline__ void flush_warp_pool(const LineBatch& lb, const EmaxScratch& sc, const int2* pool,
-                                                int cnt, int c0, unsigned long long* s_far) {
+                                                int cnt, int c0, int j_lo, unsigned long long* s_far) {
   __syncwarp();
   const int S = lb.S;
   for (int e = threadIdx.x & 31; e < cnt; e += 32) {
@@ -704,7 +707,7 @@ __device__ __forceinline__ void flush_warp_pool(const LineBatch& lb, const EmaxS
     // the farthest survivor above each 3-point chord: second-level chain vertex (phase 1) and seed
     // of the QuickHull refinement in the hull stage
     const double ex = av - (side == 0 ? t1 : t2);
-    if (ex > 0.0) atomicMax(&s_far[2 * setl + side], pack_excess(ex, n));
+    if (ex > 0.0) atomicMax(&s_far[2 * (setl - j_lo * G) + side], pack_excess(ex, n));
   }
   __syncwarp();
 }
@@ -749,18 +752,21 @@ __device__ __forceinline__ int line_block(int i, int step, int nsb, bool phase2)
 // r % row_mod of the shared table, so the G rows of a CTA carry G different intercept rows.
 template <int G, bool REFINE, bool ROWS>
 __global__ void __launch_bounds__(F32_THREADS, 7)
-filter32_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb) {
+filter32_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb, int F32_JB) {
   static_assert(G == 4, "bit layout below assumes 4 candidates x 4 lines");
   extern __shared__ __align__(16) unsigned char e_smem[];
   const int S = lb.S;
-  ulonglong2* s_p32 = reinterpret_cast<ulonglong2*>(e_smem);  // [S][G][2] (m,m | c,c) per chord
-  unsigned long long* s_far = reinterpret_cast<unsigned long long*>(s_p32 + 2 * G * S);  // [S*G][2]
-  int2* pool = reinterpret_cast<int2*>(s_far + 2 * G * S) + (threadIdx.x >> 5) * WPOOL;  // this warp's
+  // blockIdx.z selects a batch of F32_JB scalarisations: shared memory (and with it the number of
+  // resident CTAs) does not grow with S; the slope rows are re-read once per batch (mostly from L2)
+  const int j_lo = blockIdx.z * F32_JB, j_hi = min(S, j_lo + F32_JB), SB = j_hi - j_lo;
+  ulonglong2* s_p32 = reinterpret_cast<ulonglong2*>(e_smem);  // [SB][G][2] (m,m | c,c) per chord
+  unsigned long long* s_far = reinterpret_cast<unsigned long long*>(s_p32 + 2 * G * F32_JB);  // [SB*G][2]
+  int2* pool = reinterpret_cast<int2*>(s_far + 2 * G * F32_JB) + (threadIdx.x >> 5) * WPOOL;  // this warp's
   const int c0 = blockIdx.y * G;
   const ulonglong2* g_p32 = reinterpret_cast<const ulonglong2*>(sc.chain32);
   const ulonglong2 none = make_ulonglong2(0ull, 0x7f8000007f800000ull);  // (0, 0, +inf, +inf)
-  for (int e = threadIdx.x; e < G * S; e += blockDim.x) {
-    const int j = e / G, g = e - j * G;
+  for (int e = threadIdx.x; e < G * SB; e += blockDim.x) {
+    const int j = j_lo + e / G, g = e % G;
     const int c = c0 + g;
     const bool in = c < lb.C;
     s_p32[2 * e] = in ? g_p32[((size_t)c * S + j) * 2] : none;
@@ -784,13 +790,13 @@ filter32_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb) {
   }
   const float ninf = -INFINITY;
   float4 a_nx = make_float4(ninf, ninf, ninf, ninf);
-  const float* ap = lb.A32 + n0;
+  const float* ap = lb.A32 + (size_t)j_lo * lb.a_sj + n0;
   if (live && !ROWS) a_nx = *reinterpret_cast<const float4*>(ap);
   const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
   int wcnt = 0;  // entries in this warp's pool (warp-uniform)
   __syncthreads();
 
-  for (int j = 0; j < S; ++j) {
+  for (int j = j_lo; j < j_hi; ++j) {
     float4 ag[G];
     if (ROWS) {
 #pragma unroll
@@ -801,9 +807,9 @@ filter32_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb) {
     } else {
       ag[0] = ag[1] = ag[2] = ag[3] = a_nx;
       ap += lb.a_sj;
-      if (live && j + 1 < S) a_nx = *reinterpret_cast<const float4*>(ap);
+      if (live && j + 1 < j_hi) a_nx = *reinterpret_cast<const float4*>(ap);
     }
-    const ulonglong2* pj = s_p32 + (size_t)j * (2 * G);
+    const ulonglong2* pj = s_p32 + (size_t)(j - j_lo) * (2 * G);
     unsigned mask = 0u;
     {
       const ulonglong2 q1 = pj[0], q2 = pj[1];
@@ -829,7 +835,7 @@ filter32_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb) {
       const unsigned vote = __ballot_sync(0xffffffffu, mask != 0u);
       if (vote == 0u) break;
       if (wcnt + 32 > WPOOL) {
-        flush_warp_pool<G, REFINE>(lb, sc, pool, wcnt, c0, s_far);
+        flush_warp_pool<G, REFINE>(lb, sc, pool, wcnt, c0, j_lo, s_far);
         wcnt = 0;
       }
       if (mask) {
@@ -840,13 +846,13 @@ filter32_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb) {
       wcnt += __popc(vote);
     }
   }
-  flush_warp_pool<G, REFINE>(lb, sc, pool, wcnt, c0, s_far);
+  flush_warp_pool<G, REFINE>(lb, sc, pool, wcnt, c0, j_lo, s_far);
   __syncthreads();
-  for (int e = threadIdx.x; e < 2 * G * S; e += blockDim.x) {
+  for (int e = threadIdx.x; e < 2 * G * SB; e += blockDim.x) {
     const unsigned long long key = s_far[e];
     if (key) {
       const int setl = e >> 1;
-      const int j = setl / G, g = setl - j * G;
+      const int j = j_lo + setl / G, g = setl % G;
       atomicMax(&sc.far[((size_t)(c0 + g) * S + j) * 2 + (e & 1)], key);
     }
   }
@@ -856,8 +862,10 @@ static int launch_filter32(const LineBatch& lb, const EmaxScratch& sc, cudaStrea
   constexpr int G = 4;
   const int nblk = ceil_div(lb.NA, F32_THREADS * 4);
   const unsigned gy = ceil_div(lb.C, G);
-  const size_t smem = (size_t)G * lb.S * (2 * sizeof(ulonglong2) + 2 * sizeof(unsigned long long)) +
+  const int F32_JB = f32_jb(lb.S);
+  const size_t smem = (size_t)G * F32_JB * (2 * sizeof(ulonglong2) + 2 * sizeof(unsigned long long)) +
                       (F32_THREADS / 32) * WPOOL * sizeof(int2);
+  const unsigned gz = ceil_div(lb.S, F32_JB);
   const bool rows = lb.row_mod > 0;
   if (smem > 47 * 1024) {
     DKG_CUDA_OK(cudaFuncSetAttribute(filter32_kernel<G, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -868,15 +876,15 @@ static int launch_filter32(const LineBatch& lb, const EmaxScratch& sc, cudaStrea
   int sample_blocks = 2;
   if (const char* e = getenv("DKG_FILTER_NSB")) sample_blocks = atoi(e) >= 1 && atoi(e) <= nblk / 4 ? atoi(e) : 2;
   const int nsb = two_phase ? sample_blocks : nblk, step = two_phase ? nblk / sample_blocks : 1;
-  if (rows) filter32_kernel<G, false, true><<<dim3(nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
-  else filter32_kernel<G, false, false><<<dim3(nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
+  if (rows) filter32_kernel<G, false, true><<<dim3(nsb, gy, gz), F32_THREADS, smem, st>>>(lb, sc, step, nsb, F32_JB);
+  else filter32_kernel<G, false, false><<<dim3(nsb, gy, gz), F32_THREADS, smem, st>>>(lb, sc, step, nsb, F32_JB);
   DKG_LAUNCH_CHECK();
   if (two_phase) {
     const long long sets = (long long)lb.C * lb.S;
     chain5_kernel<<<(unsigned)((sets + E_THREADS - 1) / E_THREADS), E_THREADS, 0, st>>>(lb, sc);
     DKG_LAUNCH_CHECK();
-    if (rows) filter32_kernel<G, true, true><<<dim3(nblk - nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
-    else filter32_kernel<G, true, false><<<dim3(nblk - nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
+    if (rows) filter32_kernel<G, true, true><<<dim3(nblk - nsb, gy, gz), F32_THREADS, smem, st>>>(lb, sc, step, nsb, F32_JB);
+    else filter32_kernel<G, true, false><<<dim3(nblk - nsb, gy, gz), F32_THREADS, smem, st>>>(lb, sc, step, nsb, F32_JB);
     DKG_LAUNCH_CHECK();
   }
   return DKG_OK;
@@ -1327,7 +1335,7 @@ constexpr int OVF_MAXV = 130;  // chain vertices
 constexpr int FIN_RMAX = 2560; // most hull records per candidate merged in shared memory (10 per scalarisation)
 // slots of the distinct-line hash table (a power of two; distinct hull lines per candidate: tens at S = 16,
 // many hundreds at S = 256)
-__host__ __device__ inline int fin_hash_bits(int S) { return S <= 32 ? 10 : 12; }
+__host__ __device__ inline int fin_hash_bits(int S) { return S <= 64 ? 10 : 12; }
 __host__ __device__ inline int fin_rmax(int S) { const int r = 10 * S; return r < 256 ? 256 : r > FIN_RMAX ? FIN_RMAX : r; }
 constexpr int OVF_ROUNDS = 6;
 constexpr int OVF_CTAS_PER_SM = 4;

@@ -3,17 +3,24 @@
 //
 // The reference finds each upper envelope with a Python Jarvis march over ALL lines.  Here:
 //   1. zstat   : min / max slope of each candidate's slope row (shared by all scalarisations,
-//                because slopes are w_j * z with one z row per candidate, discretekg.py:321).
+//                because slopes are w_j * z with one z row per candidate, discretekg.py:321); in
+//                the KG path the same pass turns the int8 products into slopes (tiled over lines
+//                for large batches: zfinish_tiled_kernel + zreduce_kernel).  chain_kernel then
+//                writes every set's chord chain (fp64, a conservatively rounded float image, the
+//                chord end points).
 //   2. filter  : one streaming, coalesced pass over the slope rows and the (L2-resident)
 //                intercept table.  A line whose dual point (slope, intercept) lies on or below
 //                the chain P -> T -> Q (P/Q = extreme-slope lines, T = max-intercept line; all
 //                three are lines of the set) is inside the convex hull of the set, hence can
-//                never be a strict vertex of the upper envelope and is dropped.  On GP-shaped
-//                inputs this leaves ~1% of the lines; survivors are appended (intercept, slope,
-//                index) to a per-set list.
-//   3. hull    : one warp per (candidate, scalarisation).  Long lists get one QuickHull-style
-//                refinement (farthest survivor above each chord becomes a new chain vertex, the
-//                list is re-filtered); then the warp runs the reference's march EXACTLY (same
+//                never be a strict vertex of the upper envelope and is dropped.  filter32_kernel
+//                runs the test in float arithmetic (packed FFMA2) against the rounded chain and
+//                re-tests the ~1 % that pass exactly (fp64) against a second-level chain found in
+//                a sampled first launch (chain5_kernel); filter_kernel is the all-fp64 form for
+//                per-row intercepts.  Survivors are appended (intercept, slope, index) to a
+//                per-set list.
+//   3. hull    : one warp per (candidate, scalarisation).  Long lists get up to five QuickHull-
+//                style refinements (farthest survivor above each chord becomes a new chain vertex,
+//                the list is re-filtered); then the warp runs the reference's march EXACTLY (same
 //                ordering rule, strict-slope filter, division and tie-breaks) on what is left,
 //                accumulating the closed-form expectation segment by segment and recording
 //                dE/da, dE/db for the backward.
@@ -22,7 +29,8 @@
 //                the same warp march; if even that keeps too many lines (e.g. every line is a
 //                hull vertex) a block-wide exact march over all lines finishes the job.
 //   5. finalize: kg[c] = mean_j (E_j - max_n a_jn) and the envelope-theorem backward, sparse
-//                over the recorded hull vertices (one CTA per candidate).
+//                over the recorded hull vertices (one CTA per candidate; distinct lines merged
+//                through a shared-memory hash table).
 #include "dkg_emax.cuh"
 
 #include <cstdlib>

@@ -1867,7 +1867,7 @@ int emax_finalize(const LineBatch& lb, const EmaxOut& out, const BackwardArgs& b
   const char* fte = getenv("DKG_FIN_THREADS");
   // 128-thread CTAs (6 per SM) hide the short barrier-separated phases best; with many scalarisations
   // the hull records exceed the merge capacity and the per-record loops want the wider CTA
-  const int fin_default = lb.S > 64 ? 256 : 128;
+  const int fin_default = lb.S > 32 ? 256 : 128;
   const int fin_threads = fte != nullptr && (atoi(fte) == 256 || atoi(fte) == 128 || atoi(fte) == 64) ? atoi(fte) : fin_default;
 #define DKG_FINALIZE(DD)                                                                                       \
   do {                                                                                                         \

@@ -450,10 +450,10 @@ def main():
                 "avg_launch_ms": ms_g / max(n_g, 1),
                 "share_of_step": ms_g / tot_prof if tot_prof > 0 else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this shape from
-                # the ncu --set full capture profiles/r01j_ozaki_ncu.csv (60.6 MB + 490.1 MB; algorithmic:
+                # the ncu --set full capture profiles/r01q_final_kernels_ncu.csv (60.3 MB + 489.5 MB; algorithmic:
                 # 537 MB of product rows written once, digit planes served from L2)
-                "traffic": 550.7e6 if (n_cand == 4096 and N == 16384 and args.precision == "float64") else None,
-                "traffic_source": "profiles/r01j_ozaki_ncu.csv (ncu --set full, one launch, c4 shape)",
+                "traffic": 549.8e6 if (n_cand == 4096 and N == 16384 and args.precision == "float64") else None,
+                "traffic_source": "profiles/r01q_final_kernels_ncu.csv (ncu --set full, one launch, c4 shape)",
             }
         else:
             roofline = {

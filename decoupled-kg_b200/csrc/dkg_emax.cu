@@ -218,12 +218,20 @@ zfinish_tiled_kernel(LineBatch lb, CovFinish fin, double* __restrict__ zpv, int*
     double* zw = const_cast<double*>(lb.Z) + (size_t)r * lb.ldz + n_lo;
     double vmin = INFINITY, vmax = -INFINITY;
     int imin = 0x7fffffff, imax = 0x7fffffff;
+    double vn[U];  // the next trip's products are requested before this trip's kernel evaluations
+#pragma unroll
+    for (int u = 0; u < U; ++u) vn[u] = lane < n_cnt ? zw[lane + 32 * u < n_cnt ? lane + 32 * u : lane] : 0.0;
     for (int i0 = lane; i0 < n_cnt; i0 += 32 * U) {
       double v[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + 32 * u;
-        v[u] = zw[i < n_cnt ? i : i0];
+      for (int u = 0; u < U; ++u) v[u] = vn[u];
+      const int j0 = i0 + 32 * U;
+      if (j0 < n_cnt) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = j0 + 32 * u;
+          vn[u] = zw[i < n_cnt ? i : j0];
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {

@@ -90,15 +90,16 @@ def test_coupled_rows_bits_equal():
     assert torch.equal(g64, g32)
 
 
-def test_tiled_statistics_pass_matches_row_pass_on_ragged_sizes():
+@pytest.mark.parametrize("d", [1, 3, 8])
+def test_tiled_statistics_pass_matches_row_pass_on_ragged_sizes(d):
     """zfinish_tiled_kernel (large batches) against zstat_kernel (DKG_ZSTAT_ROWS=1): same bits, with N
-    and C that are not multiples of any tile."""
+    and C that are not multiples of any tile, at the smallest / an odd / the largest input dimension."""
     from decoupledbo_b200 import synthetic
     from decoupledbo_b200.modules.acquisition.discretekg import DiscreteKnowledgeGradient
 
     P = synthetic.make_problem(
-        "tile", 3, 45, [0.3, 0.5], [1.0, 2.0], [0.3, 0.05], [1e-1, 1e-3],
-        synthetic.sobol(4099, 3, 5), 6, 1100, seed_train=6, seed_cand=7, seed_w=1)
+        "tile", d, 45, [0.3, 0.5], [1.0, 2.0], [0.3, 0.05], [1e-1, 1e-3],
+        synthetic.sobol(4099, d, 5), 6, 1100, seed_train=6, seed_cand=7, seed_w=1)
     dev = torch.device("cuda")
     X = P.candidates.to(dev)
     out = {}

@@ -70,6 +70,7 @@ static void free_workspace(Workspace& w) {
   dev_free(w.sd); dev_free(w.zown); dev_free(w.Xs); dev_free(w.a_new); dev_free(w.kg_terms);
   dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.zpv); dev_free(w.zpi); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } { double4* t = (double4*)w.chain; dev_free(t); w.chain = nullptr; } { float4* t = (float4*)w.chain32; dev_free(t); w.chain32 = nullptr; } { double4* t = (double4*)w.chainv; dev_free(t); w.chainv = nullptr; } { double4* t = (double4*)w.chain5; dev_free(t); w.chain5 = nullptr; } dev_free(w.far); dev_free(w.ovf_sets); dev_free(w.ovf_count);
   dev_free(w.hull_cnt); dev_free(w.hull_idx); dev_free(w.hull_p); dev_free(w.hull_q);
+  dev_free(w.spill_head); dev_free(w.spill_next); dev_free(w.spill_idx); dev_free(w.spill_p); dev_free(w.spill_q); dev_free(w.spill_used);
   dev_free(w.amax_is_new); dev_free(w.stats); dev_free(w.sdj); dev_free(w.Zc);
   for (int m = 0; m < MAX_M; ++m) { dev_free(w.KXm[m]); dev_free(w.Tm[m]); dev_free(w.varlat[m]); dev_free(w.COVm[m]); }
   w.cap_C = w.chunk_C = 0;
@@ -151,6 +152,18 @@ static int ensure_workspace(dkg_plan* p, int C) {
   DKG_TRY(dev_alloc(&w.hull_idx, (size_t)chunk * S * HULL_CAP, false));
   DKG_TRY(dev_alloc(&w.hull_p, (size_t)chunk * S * HULL_CAP, false));
   DKG_TRY(dev_alloc(&w.hull_q, (size_t)chunk * S * HULL_CAP, false));
+  {  // spill pool for sets with more than HULL_CAP hull vertices: one block per 8 sets by default
+    long long blocks = (long long)chunk * (long long)S / 8;
+    if (blocks < 256) blocks = 256;
+    if (const char* e = getenv("DKG_SPILL_BLOCKS")) blocks = atoll(e) >= 0 ? atoll(e) : blocks;
+    w.spill_blocks = (int)(blocks > 0x3fffffff ? 0x3fffffff : blocks);
+    DKG_TRY(dev_alloc(&w.spill_head, (size_t)chunk * S, false));
+    DKG_TRY(dev_alloc(&w.spill_next, (size_t)w.spill_blocks, false));
+    DKG_TRY(dev_alloc(&w.spill_idx, (size_t)w.spill_blocks * SPILL_BLOCK, false));
+    DKG_TRY(dev_alloc(&w.spill_p, (size_t)w.spill_blocks * SPILL_BLOCK, false));
+    DKG_TRY(dev_alloc(&w.spill_q, (size_t)w.spill_blocks * SPILL_BLOCK, false));
+    DKG_TRY(dev_alloc(&w.spill_used, (size_t)1));
+  }
   DKG_TRY(dev_alloc(&w.amax_is_new, (size_t)chunk * S));
   DKG_TRY(dev_alloc(&w.stats, (size_t)8));
   w.cap_C = cap;
@@ -499,9 +512,7 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     sc.zpv = w.zpv; sc.zpi = w.zpi;
     sc.chain5 = (double4*)w.chain5;
     sc.stats = w.stats;
-    DKG_CUDA_OK(cudaMemsetAsync(w.surv_cnt, 0, sizeof(int) * (size_t)cc * S, st));
-    DKG_CUDA_OK(cudaMemsetAsync(w.far, 0, sizeof(unsigned long long) * (size_t)cc * S * 2, st));
-    DKG_CUDA_OK(cudaMemsetAsync(w.ovf_count, 0, sizeof(int), st));
+    sc.spill_used = w.spill_used;
     CovFinish fin{};
     fin.xs = ep.xs; fin.xd_s = ep.xd_s; fin.sd = ep.sd; fin.d = d; fin.kind = ep.kind; fin.N = N;
     fin.outputscale = ep.outputscale; fin.ystd2 = ep.ystd2;
@@ -512,14 +523,21 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     out.terms = w.kg_terms + (size_t)c0 * S;
     out.subtract_max = 1;
     out.hull_cnt = w.hull_cnt;  // hull records are per chunk (consumed by finalize below)
-    out.hull_idx = w.hull_idx;
-    out.hull_p = w.hull_p;
-    out.hull_q = w.hull_q;
+    if (dX != nullptr) {        // only the backward reads the records
+      out.hull_idx = w.hull_idx;
+      out.hull_p = w.hull_p;
+      out.hull_q = w.hull_q;
+    }
     out.hull_x = nullptr;
     out.hull_cap = HULL_CAP;
     out.amax_is_own = w.amax_is_new;
     out.kg = kg + c0;
     out.truncated = w.stats + 6;
+    if (dX != nullptr) {
+      out.spill_head = w.spill_head; out.spill_next = w.spill_next; out.spill_idx = w.spill_idx;
+      out.spill_p = w.spill_p; out.spill_q = w.spill_q; out.spill_used = w.spill_used;
+      out.spill_blocks = w.spill_blocks;
+    }
     BackwardArgs bw{};
     if (dX != nullptr) {
       bw.dX = dX + (size_t)c0 * d;
@@ -614,19 +632,23 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
     sc.ovf_sets = w.ovf_sets; sc.ovf_count = w.ovf_count; sc.far = w.far; sc.chain = (double4*)w.chain;
     sc.chain32 = (float4*)w.chain32; sc.chainv = (double4*)w.chainv; sc.chain5 = (double4*)w.chain5;
     sc.stats = w.stats;
-    DKG_CUDA_OK(cudaMemsetAsync(w.surv_cnt, 0, sizeof(int) * (size_t)cc * S, st));
-    DKG_CUDA_OK(cudaMemsetAsync(w.far, 0, sizeof(unsigned long long) * (size_t)cc * S * 2, st));
-    DKG_CUDA_OK(cudaMemsetAsync(w.ovf_count, 0, sizeof(int), st));
+    sc.spill_used = w.spill_used;
     sc.zpv = w.zpv; sc.zpi = w.zpi;
     { ProfScope ps(5, st); DKG_TRY(emax_zstat_from_partials(lb, sc, (N + 1 + CS_TILE_LINES - 1) / CS_TILE_LINES, st)); }
     { ProfScope ps(6, st); DKG_TRY(emax_filter(lb, sc, st)); }
     EmaxOut out;
     out.terms = w.kg_terms + (size_t)c0 * S;
     out.subtract_max = 1;
-    out.hull_cnt = w.hull_cnt; out.hull_idx = w.hull_idx; out.hull_p = w.hull_p; out.hull_q = w.hull_q;
+    out.hull_cnt = w.hull_cnt;
+    if (dX != nullptr) { out.hull_idx = w.hull_idx; out.hull_p = w.hull_p; out.hull_q = w.hull_q; }
     out.hull_x = nullptr; out.hull_cap = HULL_CAP; out.amax_is_own = w.amax_is_new;
     out.kg = kg + c0;
     out.truncated = w.stats + 6;
+    if (dX != nullptr) {
+      out.spill_head = w.spill_head; out.spill_next = w.spill_next; out.spill_idx = w.spill_idx;
+      out.spill_p = w.spill_p; out.spill_q = w.spill_q; out.spill_used = w.spill_used;
+      out.spill_blocks = w.spill_blocks;
+    }
     { ProfScope ps(7, st); DKG_TRY(emax_hull(lb, sc, out, st)); }
     { ProfScope ps(8, st); DKG_TRY(emax_overflow(lb, sc, out, st)); }
     CoupledBackward bw;
@@ -847,6 +869,20 @@ int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev, int32_t
   dev_free(zst); dev_free(zarg); dev_free(amax); dev_free(aarg); dev_free(scnt); dev_free(surv);
   dev_free(oset); dev_free(ocnt); dev_free(far); dev_free(chain);
   return rc;
+}
+
+int dkg_piecewise_expectation_dev(const double* a_dev, const double* b_dev, const double* z_dev, int32_t P,
+                                  int32_t H, double* e_dev, double* dE_da_dev, double* dE_db_dev,
+                                  double* dE_dz_dev, void* stream) {
+  if (H == 0) {
+    set_error("Expected inputs to specify at least one line. Got intercepts.shape[-1]=0.");
+    return DKG_EEMPTY;
+  }
+  if (P < 0 || H < 0) { set_error("negative size"); return DKG_EINVAL; }
+  if (P == 0) return DKG_OK;
+  if (!a_dev || !b_dev || !e_dev || (H > 1 && !z_dev)) { set_error("NULL argument"); return DKG_EINVAL; }
+  return piecewise_expectation(a_dev, b_dev, z_dev, P, H, e_dev, dE_da_dev, dE_db_dev, dE_dz_dev,
+                               (cudaStream_t)stream);
 }
 
 int64_t dkg_plan_read(dkg_plan* plan, const char* name, double* out_dev, int64_t capacity,

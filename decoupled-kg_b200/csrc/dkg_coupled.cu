@@ -156,7 +156,10 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
   }
   if (bw.dX == nullptr) return;
 
-  const int d = bw.d, M = bw.M, hcap = out.hull_cap, NA = bw.N;
+  const int d = bw.d, M = bw.M, NA = bw.N;
+  __shared__ int s_broken;
+  if (threadIdx.x == 0) s_broken = 0;
+  __syncthreads();
   const double invS = 1.0 / (double)S;
   int n_pad_max = 0;
   for (int m = 0; m < M; ++m) n_pad_max = max(n_pad_max, bw.n_pad[m]);
@@ -174,10 +177,13 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
     for (int m = 0; m < MAX_M; ++m) gm[m] = 0.0;
     for (int j = lane; j < S; j += 32) {
       const size_t set = (size_t)c * S + j;
-      const int h = min(out.hull_cnt[set], hcap);
+      const int h = out.hull_cnt[set];
       double ga = out.amax_is_own[set] ? -invS : 0.0;
-      for (int k = 0; k < h; ++k)
-        if (out.hull_idx[set * hcap + k] == NA) ga += out.hull_p[set * hcap + k] * invS;
+      HullReader rd(out, set);
+      for (int k = 0; k < h; ++k) {
+        if (!rd.seek(k)) { s_broken = 1; break; }
+        if (rd.idx() == NA) ga += rd.p() * invS;
+      }
 #pragma unroll
       for (int m = 0; m < MAX_M; ++m)
         if (m < M) gm[m] += ga * bw.W[j * M + m];
@@ -196,12 +202,14 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
       double acc = 0.0;
       for (int j = 0; j < S; ++j) {
         const size_t set = (size_t)c * S + j;
-        const int h = min(out.hull_cnt[set], hcap);
+        const int h = out.hull_cnt[set];
         const double w = bw.W[j * M + m];
         const double om = (w * w) / bw.sdj[set];
+        HullReader rd(out, set);
         for (int k = 0; k < h; ++k) {
-          const int idx = out.hull_idx[set * hcap + k];
-          if (idx < NA) acc += om * out.hull_q[set * hcap + k] * invS * bw.BT[m][(size_t)idx * bw.n_pad[m] + t];
+          if (!rd.seek(k)) { s_broken = 1; break; }
+          const int idx = rd.idx();
+          if (idx < NA) acc += om * rd.q() * invS * bw.BT[m][(size_t)idx * bw.n_pad[m] + t];
         }
       }
       s_r[t] = acc;
@@ -215,15 +223,17 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
       for (int k = 0; k < MAX_D; ++k) xm[k] = k < d ? bw.X[(size_t)c * d + k] / bw.ls[m][k] : 0.0;
       for (int j = lane; j < S; j += 32) {
         const size_t set = (size_t)c * S + j;
-        const int h = min(out.hull_cnt[set], hcap);
+        const int h = out.hull_cnt[set];
         const double w = bw.W[j * M + m];
         const double sd = bw.sdj[set];
         const double om = (w * w) / sd;
         const double* zrow = bw.Zc + set * (size_t)bw.ldz;
         double qb = 0.0;  // sum_n (q / S) b_jn
+        HullReader rd(out, set);
         for (int k = 0; k < h; ++k) {
-          const int idx = out.hull_idx[set * hcap + k];
-          const double qs = out.hull_q[set * hcap + k] * invS;
+          if (!rd.seek(k)) { s_broken = 1; break; }
+          const int idx = rd.idx();
+          const double qs = rd.q() * invS;
           qb += qs * zrow[idx];
           if (idx == NA) {
             gzown += om * qs;
@@ -285,7 +295,8 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
   if (threadIdx.x < d) {
     double acc = 0.0;
     for (int wv = 0; wv < nwarps; ++wv) acc += s_red[wv * MAX_D + threadIdx.x];
-    bw.dX[(size_t)c * d + threadIdx.x] = acc;
+    // hull records lost to an exhausted spill pool: fail loudly (NaN) instead of a partial gradient
+    bw.dX[(size_t)c * d + threadIdx.x] = s_broken ? __longlong_as_double(0x7ff8000000000000ll) : acc;
   }
 }
 

@@ -168,6 +168,13 @@ chain_kernel(LineBatch lb, EmaxScratch sc) {
   const size_t set = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (set >= (size_t)lb.C * lb.S) return;
   const int c = (int)(set / lb.S), j = (int)(set - (size_t)c * lb.S);
+  // per-forward counters of the stages that follow (saves three memset launches per chunk)
+  sc.surv_cnt[set] = 0;
+  if (sc.far != nullptr) { sc.far[set * 2] = 0ull; sc.far[set * 2 + 1] = 0ull; }
+  if (set == 0) {
+    *sc.ovf_count = 0;
+    if (sc.spill_used != nullptr) *sc.spill_used = 0;
+  }
   ChainMag mag;
   double4 verts[2];
   const double4 par = chain_params(lb, sc, c, j, &mag, verts);
@@ -1011,22 +1018,71 @@ __device__ __forceinline__ void merge_next(Next& best, const Next& o) {
     best = o;
 }
 
-// per-set output sink
+// per-set output sink: the first hull_cap records inline, the rest in chained spill blocks
+static_assert(HULL_CAP % SPILL_BLOCK == 0, "a march batch must map to one spill block");
 struct Recorder {
   const EmaxOut* out;
   size_t set;
   int NL;
-  __device__ void operator()(int k, const Line& L, double p, double q, double x, bool last) const {
+  int blk = -1;          // current spill block
+  bool dropped = false;  // the pool ran dry for this set
+
+  __device__ __forceinline__ void dense(const Line& L, double p, double q) const {
     const EmaxOut& o = *out;
-    if (k < o.hull_cap) {
-      const size_t r = set * (size_t)o.hull_cap + k;
-      if (o.hull_idx) o.hull_idx[r] = L.idx;
-      if (o.hull_p) o.hull_p[r] = p;
-      if (o.hull_q) o.hull_q[r] = q;
-      if (o.hull_x && !last) o.hull_x[r] = x;
-    }
     if (o.dense_da) o.dense_da[set * (size_t)NL + L.idx] = p;
     if (o.dense_db) o.dense_db[set * (size_t)NL + L.idx] = q;
+  }
+  __device__ __forceinline__ void store_inline(int k, const Line& L, double p, double q, double x, bool last) const {
+    const EmaxOut& o = *out;
+    const size_t r = set * (size_t)o.hull_cap + k;
+    if (o.hull_idx) o.hull_idx[r] = L.idx;
+    if (o.hull_p) o.hull_p[r] = p;
+    if (o.hull_q) o.hull_q[r] = q;
+    if (o.hull_x && !last) o.hull_x[r] = x;
+  }
+  // claim the block holding records k .. (called by ONE thread); links it behind the current one
+  __device__ __forceinline__ int claim(int k) {
+    const EmaxOut& o = *out;
+    int nb = atomicAdd(o.spill_used, 1);
+    if (nb >= o.spill_blocks) nb = -1;
+    else o.spill_next[nb] = -1;
+    if (k == o.hull_cap) o.spill_head[set] = nb;
+    else o.spill_next[blk] = nb;
+    if (nb < 0 && o.truncated != nullptr) atomicAdd((unsigned long long*)o.truncated, 1ull);
+    return nb;
+  }
+  __device__ __forceinline__ void store_spill(int k, const Line& L, double p, double q) const {
+    const EmaxOut& o = *out;
+    const size_t r = (size_t)blk * SPILL_BLOCK + (k - o.hull_cap) % SPILL_BLOCK;
+    o.spill_idx[r] = L.idx;
+    o.spill_p[r] = p;
+    o.spill_q[r] = q;
+  }
+  // one record, from a single thread that calls this for k = 0, 1, 2, ... in order
+  __device__ void single(int k, const Line& L, double p, double q, double x, bool last) {
+    const EmaxOut& o = *out;
+    if (k < o.hull_cap) store_inline(k, L, p, q, x, last);
+    else if (o.spill_head != nullptr && !dropped) {
+      if ((k - o.hull_cap) % SPILL_BLOCK == 0) { blk = claim(k); dropped = blk < 0; }
+      if (!dropped) store_spill(k, L, p, q);
+    }
+    dense(L, p, q);
+  }
+  // warp-wide: lane l holds record k0 + l of a march batch (l < cnt); k0 is a multiple of 32
+  __device__ void batch(int k0, int cnt, const Line& L, double p, double q, double x, bool last_batch) {
+    const EmaxOut& o = *out;
+    const int lane = threadIdx.x & 31;
+    const bool act = lane < cnt;
+    const int k = k0 + lane;
+    if (act && k < o.hull_cap) store_inline(k, L, p, q, x, last_batch && lane == cnt - 1);
+    if (o.spill_head != nullptr && k0 >= o.hull_cap && !dropped) {
+      int nb = 0;
+      if (lane == 0) nb = claim(k0);
+      blk = __shfl_sync(0xffffffffu, nb, 0);
+      dropped = blk < 0;
+      if (act && !dropped) store_spill(k, L, p, q);
+    }
+    if (act) dense(L, p, q);
   }
 };
 
@@ -1040,7 +1096,7 @@ struct HullResult {
 constexpr int LANE_LINES = STAGE_CAP / 32;
 
 template <class Fetch>
-__device__ HullResult warp_march(int total, Fetch fetch, const Recorder& rec) {
+__device__ HullResult warp_march(int total, Fetch fetch, Recorder& rec) {
   const int lane = threadIdx.x & 31;
   Line cache[LANE_LINES];
 #pragma unroll
@@ -1121,7 +1177,7 @@ __device__ HullResult warp_march(int total, Fetch fetch, const Recorder& rec) {
       const double dP = cdf - lcdf, dp = pdf - lpdf;
       // intercepts * (cdf[1:] - cdf[:-1]) - slopes * (pdf[1:] - pdf[:-1])   (:449-451)
       const double term = act ? __dsub_rn(__dmul_rn(mine.a, dP), __dmul_rn(mine.b, dp)) : 0.0;
-      if (act) rec(h - cnt + lane, mine, dP, -dp, mine_x, last && lane == cnt - 1);
+      rec.batch(h - cnt, cnt, mine, dP, -dp, mine_x, last);
       for (int k = 0; k < cnt; ++k) E += __shfl_sync(0xffffffffu, term, k);
       carry_cdf = __shfl_sync(0xffffffffu, cdf, cnt - 1);
       carry_pdf = __shfl_sync(0xffffffffu, pdf, cnt - 1);
@@ -1138,8 +1194,9 @@ __device__ HullResult warp_march(int total, Fetch fetch, const Recorder& rec) {
 __device__ __forceinline__ void finish_set(const LineBatch& lb, const EmaxOut& out, size_t set,
                                            const SetInfo& s, double E, int h) {
   if (out.hull_cnt) out.hull_cnt[set] = h;
-  // more hull vertices than record slots: E is exact, but the backward would miss vertices
-  if (out.truncated != nullptr && out.hull_p != nullptr && h > out.hull_cap)
+  // more hull vertices than record slots and no spill chain: E is exact, but a backward would miss
+  // vertices (with a chain the Recorder counts the sets whose blocks could not be claimed)
+  if (out.truncated != nullptr && out.hull_p != nullptr && out.spill_head == nullptr && h > out.hull_cap)
     atomicAdd((unsigned long long*)out.truncated, 1ull);
   out.terms[set] = out.subtract_max ? (E - s.amax) : E;  // kg[j] = E - max(intercepts) (:336)
 }
@@ -1193,7 +1250,7 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
     if (lane == 0) {
       Line L;
       L.idx = s.iT; L.a = s.amax; L.b = 0; L.ref = 0;
-      rec(0, L, 1.0, 0.0, 0.0, true);
+      rec.single(0, L, 1.0, 0.0, 0.0, true);
       finish_set(lb, out, set, s, s.amax, 1);
       if (sc.stats) atomicAdd((unsigned long long*)&sc.stats[4], 1ull);
     }
@@ -1588,7 +1645,7 @@ overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
         E += __dsub_rn(__dmul_rn(cur.a, dP), __dmul_rn(cur.b, dp));
         __syncthreads();  // everyone has consumed c_* and r_* of this step
         if (tid == 0) {
-          rec(h, cur, dP, -dp, nx.x, last);
+          rec.single(h, cur, dP, -dp, nx.x, last);
           c_a = nx.L.a; c_b = nx.L.b; c_idx = nx.L.idx; c_ref = nx.L.ref;
         }
         ++h;
@@ -1655,7 +1712,6 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
   constexpr int d = D;
   const double invS = 1.0 / (double)S;
   const double* zrow = lb.Z + (size_t)c * lb.ldz;
-  const int hcap = out.hull_cap;
 
   // ---- gather the hull records of this candidate and merge duplicates: the same few lines are
   // hull vertices for most scalarisations, so the B^T row gathers and kernel-gradient evaluations
@@ -1670,9 +1726,9 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
   int* s_hkey = reinterpret_cast<int*>(s_ucz + RM);        // [HN] line index held by a slot (-1: free)
   const int HB = fin_hash_bits(S), HN = 1 << HB;
   int* s_hfirst = s_hkey + HN;                             // [HN] first record of that line
-  __shared__ int s_nrec, s_nuniq, s_hovf;
+  __shared__ int s_nrec, s_nuniq, s_hovf, s_broken;
   for (int j = threadIdx.x; j < S; j += blockDim.x)
-    s_roff[j + 1] = min(out.hull_cnt[(size_t)c * S + j], hcap);  // counts first, scanned below
+    s_roff[j + 1] = out.hull_cnt[(size_t)c * S + j];  // counts first, scanned below
   __syncthreads();
   if (threadIdx.x == 0) {
     int off = 0;
@@ -1685,6 +1741,7 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
     s_nrec = off;
     s_nuniq = 0;
     s_hovf = 0;
+    s_broken = 0;
   }
   for (int h = threadIdx.x; h < HN; h += blockDim.x) { s_hkey[h] = -1; s_hfirst[h] = 0x7fffffff; }
   __syncthreads();
@@ -1695,9 +1752,11 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
       const size_t set = (size_t)c * S + j;
       const double wj = bw.W[j * bw.M + tgt];
       const int h = s_roff[j + 1] - s_roff[j];
+      HullReader rd(out, set);
       for (int k = lane; k < h; k += 32) {
-        s_ridx[s_roff[j] + k] = out.hull_idx[set * hcap + k];
-        s_rcz[s_roff[j] + k] = wj * out.hull_q[set * hcap + k] * invS;
+        if (!rd.seek(k)) { s_broken = 1; s_ridx[s_roff[j] + k] = lb.NA; s_rcz[s_roff[j] + k] = 0.0; continue; }
+        s_ridx[s_roff[j] + k] = rd.idx();
+        s_rcz[s_roff[j] + k] = wj * rd.q() * invS;
       }
     }
     __syncthreads();
@@ -1749,12 +1808,14 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
     } else {
       for (int j = 0; j < S; ++j) {
         const size_t set = (size_t)c * S + j;
-        const int h = min(out.hull_cnt[set], hcap);
+        const int h = out.hull_cnt[set];
         const double wj = bw.W[j * bw.M + tgt];
+        HullReader rd(out, set);
         for (int k = 0; k < h; ++k) {
-          const int idx = out.hull_idx[set * hcap + k];
+          if (!rd.seek(k)) { s_broken = 1; break; }
+          const int idx = rd.idx();
           if (idx < lb.NA) {
-            const double cz = wj * out.hull_q[set * hcap + k] * invS;
+            const double cz = wj * rd.q() * invS;
             acc += cz * bw.BT[(size_t)idx * bw.n_pad + t];
           }
         }
@@ -1796,13 +1857,15 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
       for (int u = lane; u < nuniq; u += 32) slope_terms(s_uidx[u], s_ucz[u]);
     for (int j = lane; j < S; j += 32) {  // lane l owns scalarisations l, l+32, ...
       const size_t set = (size_t)c * S + j;
-      const int h = min(out.hull_cnt[set], hcap);
+      const int h = out.hull_cnt[set];
       const double wj = bw.W[j * bw.M + tgt];
       double ga = out.amax_is_own[set] ? -invS : 0.0;
+      HullReader rd(out, set);
       for (int k = 0; k < h; ++k) {
-        const int idx = out.hull_idx[set * hcap + k];
-        if (idx == lb.NA) ga += out.hull_p[set * hcap + k] * invS;
-        if (!merged) slope_terms(idx, wj * out.hull_q[set * hcap + k] * invS);
+        if (!rd.seek(k)) { s_broken = 1; break; }
+        const int idx = rd.idx();
+        if (idx == lb.NA) ga += rd.p() * invS;
+        if (!merged) slope_terms(idx, wj * rd.q() * invS);
       }
       s_ga[j] = ga;
 #pragma unroll
@@ -1862,7 +1925,8 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
     double acc = 0.0;
     for (int wv = 0; wv < nwarps; ++wv) acc += s_red[wv * MAX_D + threadIdx.x];
     acc += (s2 / sd) * s_sc[2 + threadIdx.x];
-    bw.dX[(size_t)c * d + threadIdx.x] = acc;
+    // hull records lost to an exhausted spill pool: fail loudly (NaN) instead of a partial gradient
+    bw.dX[(size_t)c * d + threadIdx.x] = s_broken ? __longlong_as_double(0x7ff8000000000000ll) : acc;
   }
 }
 
@@ -1894,6 +1958,62 @@ int emax_finalize(const LineBatch& lb, const EmaxOut& out, const BackwardArgs& b
     default: DKG_FINALIZE(8); break;
   }
 #undef DKG_FINALIZE
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone expectation of a piecewise-linear function of Z ~ N(0, 1) with caller-given break
+// points (discretekg.py:415-452): E = sum_k a_k (Phi_{k+1} - Phi_k) - b_k (phi_{k+1} - phi_k) with
+// z_0 = -inf, z_H = +inf, summed in piece order; and its gradient
+//   dE/da_k = Phi_{k+1} - Phi_k,  dE/db_k = -(phi_{k+1} - phi_k),
+//   dE/dz_k = phi(z_k) ((a_{k-1} - a_k) + z_k (b_{k-1} - b_k))      (phi'(z) = -z phi(z)).
+// One warp per function: the lanes evaluate Phi / phi of 32 break points at a time, lane 0 adds the
+// terms in order (same association as a sequential sum).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(E_THREADS)
+piecewise_kernel(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ z,
+                 int P, int H, double* __restrict__ e, double* __restrict__ de_da, double* __restrict__ de_db,
+                 double* __restrict__ de_dz) {
+  const int lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * (E_THREADS / 32) + (threadIdx.x >> 5);
+  if (p >= P) return;
+  const double* ap = a + (size_t)p * H;
+  const double* bp = b + (size_t)p * H;
+  const double* zp = z + (size_t)p * (H - 1);
+  double E = 0.0, carry_cdf = 0.0, carry_pdf = 0.0;
+  for (int k0 = 0; k0 < H; k0 += 32) {
+    const int k = k0 + lane;
+    const bool act = k < H;
+    const double zr = (act && k < H - 1) ? zp[k] : INFINITY;  // right break point of piece k
+    const double cdf = act ? std_normal_cdf(zr) : 0.0;
+    const double pdf = act ? std_normal_pdf(zr) : 0.0;
+    double lcdf = __shfl_up_sync(0xffffffffu, cdf, 1);
+    double lpdf = __shfl_up_sync(0xffffffffu, pdf, 1);
+    if (lane == 0) { lcdf = carry_cdf; lpdf = carry_pdf; }
+    const double dP = cdf - lcdf, dp = pdf - lpdf;
+    const double ak = act ? ap[k] : 0.0, bk = act ? bp[k] : 0.0;
+    const double term = act ? __dsub_rn(__dmul_rn(ak, dP), __dmul_rn(bk, dp)) : 0.0;
+    if (act) {
+      if (de_da) de_da[(size_t)p * H + k] = dP;
+      if (de_db) de_db[(size_t)p * H + k] = -dp;
+      if (de_dz && k < H - 1) {
+        const double an = ap[k + 1], bn = bp[k + 1];
+        de_dz[(size_t)p * (H - 1) + k] = pdf * ((ak - an) + zr * (bk - bn));
+      }
+    }
+    const int cnt = min(32, H - k0);
+    for (int q = 0; q < cnt; ++q) E += __shfl_sync(0xffffffffu, term, q);
+    carry_cdf = __shfl_sync(0xffffffffu, cdf, cnt - 1);
+    carry_pdf = __shfl_sync(0xffffffffu, pdf, cnt - 1);
+  }
+  if (lane == 0) e[p] = E;
+}
+
+int piecewise_expectation(const double* a, const double* b, const double* z, int P, int H, double* e,
+                          double* de_da, double* de_db, double* de_dz, cudaStream_t st) {
+  const int wpb = E_THREADS / 32;
+  piecewise_kernel<<<(unsigned)(((long long)P + wpb - 1) / wpb), E_THREADS, 0, st>>>(a, b, z, P, H, e, de_da, de_db, de_dz);
   DKG_LAUNCH_CHECK();
   return DKG_OK;
 }

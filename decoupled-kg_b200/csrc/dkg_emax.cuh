@@ -57,7 +57,10 @@ struct EmaxScratch {
                                       // chord, packed (float excess << 32 | line); 0 = none
   int* ovf_sets = nullptr;      // [C * S] queue of sets for the cooperative kernel
   int* ovf_count = nullptr;     // [1]
+  int* spill_used = nullptr;    // [1] blocks claimed from the hull-record spill pool (optional)
   long long* stats = nullptr;   // [8] (optional)
+  // surv_cnt, far, ovf_count and spill_used are zeroed by chain_kernel (emax_zstat*), i.e. before the
+  // filter of the same batch runs
 };
 
 struct EmaxOut {
@@ -71,10 +74,49 @@ struct EmaxOut {
   int hull_cap = 0;
   int* amax_is_own = nullptr;  // [C, S] (optional)
   double* kg = nullptr;        // [C] mean over scalarisations of terms (optional)
-  long long* truncated = nullptr;  // [1] counts sets with more hull vertices than hull_cap (optional)
+  long long* truncated = nullptr;  // [1] counts sets whose hull records could not all be stored (optional)
+  // Spill chain for sets with more than hull_cap vertices (optional; KG path): records k >= hull_cap
+  // live in 32-record blocks claimed from a pool as the march proceeds and chained per set, so the
+  // backward sees EVERY vertex (the reference handles any hull size, discretekg.py:378-412).
+  int* spill_head = nullptr;   // [C, S] first block of the set (-1: claim failed); valid iff hull_cnt > hull_cap
+  int* spill_next = nullptr;   // [spill_blocks] next block of the same set (-1: none / claim failed)
+  int* spill_idx = nullptr;    // [spill_blocks * 32]
+  double* spill_p = nullptr;   // [spill_blocks * 32]
+  double* spill_q = nullptr;   // [spill_blocks * 32]
+  int* spill_used = nullptr;   // [1] blocks claimed so far (zeroed per forward)
+  int spill_blocks = 0;
   double* dense_da = nullptr;  // [C*S, NL] dE/da scattered by line index (optional, pre-zeroed)
   double* dense_db = nullptr;  // [C*S, NL] dE/db (optional, pre-zeroed)
 };
+
+constexpr int SPILL_BLOCK = 32;  // records per spill block (one march batch)
+
+#ifdef __CUDACC__
+// Sequential reader of one set's hull records (k must not decrease between seek() calls).
+struct HullReader {
+  const EmaxOut* o;
+  size_t set;
+  int blk, bno;   // current spill block and its ordinal in the set's chain (bno < 0: chain not entered)
+  size_t cur;
+  bool spill;
+  __device__ HullReader(const EmaxOut& out, size_t set_) : o(&out), set(set_), blk(-1), bno(-1), cur(0), spill(false) {}
+  // false: the record was dropped because the spill pool was exhausted
+  __device__ __forceinline__ bool seek(int k) {
+    if (k < o->hull_cap) { cur = set * (size_t)o->hull_cap + k; spill = false; return true; }
+    if (o->spill_head == nullptr) return false;
+    const int b = (k - o->hull_cap) / SPILL_BLOCK;
+    if (bno < 0) { blk = o->spill_head[set]; bno = 0; }
+    while (bno < b && blk >= 0) { blk = o->spill_next[blk]; ++bno; }
+    if (blk < 0) return false;
+    cur = (size_t)blk * SPILL_BLOCK + (k - o->hull_cap) % SPILL_BLOCK;
+    spill = true;
+    return true;
+  }
+  __device__ __forceinline__ int idx() const { return spill ? o->spill_idx[cur] : o->hull_idx[cur]; }
+  __device__ __forceinline__ double p() const { return spill ? o->spill_p[cur] : o->hull_p[cur]; }
+  __device__ __forceinline__ double q() const { return spill ? o->spill_q[cur] : o->hull_q[cur]; }
+};
+#endif
 
 // Backward of the KG path (finalize kernel, one CTA per candidate).
 struct BackwardArgs {
@@ -122,6 +164,11 @@ int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cu
 int emax_overflow(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cudaStream_t st);
 // kg[c] = mean_j terms[c, j] and, if bw.dX, the fused envelope-theorem backward
 int emax_finalize(const LineBatch& lb, const EmaxOut& out, const BackwardArgs& bw, cudaStream_t st);
+
+// E[f(Z)] for P piecewise-linear functions with H pieces each and ARBITRARY break points z [P, H-1]
+// (calculate_expected_value_of_piecewise_linear_function, discretekg.py:415-452) and its gradient
+int piecewise_expectation(const double* a, const double* b, const double* z, int P, int H, double* e,
+                          double* de_da, double* de_db, double* de_dz, cudaStream_t st);
 
 // Coupled evaluation (reference calculate_discrete_kg, discretekg.py:162-235): the slope of line n
 // for scalarisation j is  sum_m W[j,m]^2 Cov_m(x, x_n) / sqrt(sum_m W[j,m]^2 var_m(x)).

@@ -75,6 +75,13 @@ struct Workspace {
   int* hull_idx = nullptr;  // [chunk_C, S, HULL_CAP]
   double* hull_p = nullptr; // [chunk_C, S, HULL_CAP]  dE/da  (Phi differences)
   double* hull_q = nullptr; // [chunk_C, S, HULL_CAP]  dE/db  (-phi differences)
+  int spill_blocks = 0;        // 32-record blocks of the hull-record spill pool (sets with > HULL_CAP vertices)
+  int* spill_head = nullptr;   // [chunk_C, S]
+  int* spill_next = nullptr;   // [spill_blocks]
+  int* spill_idx = nullptr;    // [spill_blocks * 32]
+  double* spill_p = nullptr;   // [spill_blocks * 32]
+  double* spill_q = nullptr;   // [spill_blocks * 32]
+  int* spill_used = nullptr;   // [1]
   int* amax_is_new = nullptr;  // [chunk_C, S]  1 if the max intercept is the candidate's own line
   long long* stats = nullptr;  // [8] device counters
   int last_C = 0;

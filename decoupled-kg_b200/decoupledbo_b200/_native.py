@@ -20,7 +20,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_PKG_DIR), "lib", "libdkg_b200.so")
 
 DKG_OK, DKG_EINVAL, DKG_ECUDA, DKG_ENOTPD, DKG_ENOMEM, DKG_EEMPTY = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTED_SYMBOLS = (
     "dkg_abi_version",
@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "dkg_forward_dev",
     "dkg_forward_host",
     "dkg_expected_max_lines_dev",
+    "dkg_piecewise_expectation_dev",
     "dkg_posterior_mean_dev",
     "dkg_int8_matmul_dev",
     "dkg_plan_read",
@@ -95,6 +96,10 @@ def load_library() -> ctypes.CDLL:
     lib.dkg_expected_max_lines_dev.argtypes = [
         c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
         c_void_p, c_void_p, c_void_p,
+    ]
+    lib.dkg_piecewise_expectation_dev.restype = ctypes.c_int
+    lib.dkg_piecewise_expectation_dev.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
     ]
     lib.dkg_posterior_mean_dev.restype = ctypes.c_int
     lib.dkg_posterior_mean_dev.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]
@@ -241,13 +246,22 @@ class Plan:
             pass
 
     # -- forward ---------------------------------------------------------------------------
-    def forward_device(self, X: Tensor, need_grad: bool):
-        """X: (C, d) float64 CUDA tensor -> (kg (C,), dX (C, d) | None) on the same device."""
+    def forward_device(self, X: Tensor, need_grad: bool, out_kg: Optional[Tensor] = None,
+                       out_dX: Optional[Tensor] = None):
+        """X: (C, d) float64 CUDA tensor -> (kg (C,), dX (C, d) | None) on the same device.
+        ``out_kg`` / ``out_dX`` (contiguous CUDA float64 tensors of those shapes) receive the results
+        in place, e.g. slices of a packed buffer that is all-gathered afterwards."""
         assert X.is_cuda and X.dtype == torch.double and X.dim() == 2 and X.shape[1] == self.d
         X = X.contiguous()
         C = X.shape[0]
-        kg = torch.empty(C, dtype=torch.double, device=X.device)
-        dX = torch.empty(C, self.d, dtype=torch.double, device=X.device) if need_grad else None
+        if out_kg is not None:
+            assert out_kg.is_cuda and out_kg.dtype == torch.double and out_kg.is_contiguous() and out_kg.numel() == C
+        if out_dX is not None:
+            assert out_dX.is_cuda and out_dX.dtype == torch.double and out_dX.is_contiguous() and out_dX.numel() == C * self.d
+        kg = out_kg if out_kg is not None else torch.empty(C, dtype=torch.double, device=X.device)
+        dX = None
+        if need_grad:
+            dX = out_dX if out_dX is not None else torch.empty(C, self.d, dtype=torch.double, device=X.device)
         with torch.cuda.device(X.device):
             rc = load_library().dkg_forward_dev(self._handle, _ptr(X), C, _ptr(kg), _ptr(dX), _stream_ptr())
         _check(rc, "dkg_forward_dev")
@@ -370,4 +384,34 @@ def expected_max_lines(a: Tensor, b: Tensor, hull_cap: int = 64, want_grad: bool
     out = dict(emax=emax, hull_count=cnt, hull_idx=idx, hull_x=hx)
     if want_grad:
         out["dE_da"], out["dE_db"] = da, db
+    return out
+
+
+def piecewise_expectation(a: Tensor, b: Tensor, z: Tensor, want_grad: bool = False):
+    """Device equivalent of ``calculate_expected_value_of_piecewise_linear_function``
+    (discretekg.py:415-452) for P functions: a, b are (P, H), the break points z are (P, H-1).
+
+    Returns dict(e (P,), [dE_da (P, H), dE_db (P, H), dE_dz (P, H-1)]) on the CUDA device.
+    """
+    dev = require_cuda()
+    a = a.detach().to(device=dev, dtype=torch.double).contiguous()
+    b = b.detach().to(device=dev, dtype=torch.double).contiguous()
+    z = z.detach().to(device=dev, dtype=torch.double).contiguous()
+    if a.dim() != 2 or a.shape != b.shape or z.shape != (a.shape[0], max(a.shape[1] - 1, 0)):
+        raise ValueError(
+            f"a, b must be (P, H) and z (P, H-1); got {tuple(a.shape)}, {tuple(b.shape)}, {tuple(z.shape)}"
+        )
+    P, H = a.shape
+    e = torch.empty(P, dtype=torch.double, device=dev)
+    da = torch.empty(P, H, dtype=torch.double, device=dev) if want_grad else None
+    db = torch.empty(P, H, dtype=torch.double, device=dev) if want_grad else None
+    dz = torch.empty(P, max(H - 1, 0), dtype=torch.double, device=dev) if want_grad else None
+    with torch.cuda.device(dev):
+        rc = load_library().dkg_piecewise_expectation_dev(
+            _ptr(a), _ptr(b), _ptr(z), P, H, _ptr(e), _ptr(da), _ptr(db), _ptr(dz), _stream_ptr()
+        )
+    _check(rc, "dkg_piecewise_expectation_dev")
+    out = dict(e=e)
+    if want_grad:
+        out["dE_da"], out["dE_db"], out["dE_dz"] = da, db, dz
     return out

@@ -87,11 +87,29 @@ def _scalar(x: Any) -> float:
 
 
 def _extract_single(gp: Any) -> GPObjective:
-    """Read one (duck-typed) ``SingleTaskGP``."""
+    """Read one (duck-typed) ``SingleTaskGP``.
+
+    Supported surface (what ``factory.py:63-135`` builds): unbatched exact GP, ``ConstantMean``,
+    ``ScaleKernel(Matern-5/2 | RBF)``, homoskedastic ``GaussianLikelihood``, optional
+    ``Standardize(m=1)`` outcome transform, NO input transform.  Anything else raises
+    ``NotImplementedError`` rather than being mis-read (the reference goes through
+    ``model.posterior`` and is correct for any model).
+    """
     train_x = gp.train_inputs[0]
     train_y = gp.train_targets
     if train_x.dim() != 2:
         raise NotImplementedError("batched sub-models are not supported")
+    if getattr(gp, "input_transform", None) is not None:
+        raise NotImplementedError("models with an input_transform are not supported (factory.py:65 normalises the data itself)")
+    noise = torch.as_tensor(gp.likelihood.noise).detach()
+    if noise.numel() != 1:
+        raise NotImplementedError(
+            f"only a homoskedastic GaussianLikelihood is supported; got a noise tensor of shape {tuple(noise.shape)} "
+            f"(FixedNoise / heteroskedastic likelihoods are not)"
+        )
+    mean_module = gp.mean_module
+    if not hasattr(mean_module, "constant") or torch.as_tensor(mean_module.constant).numel() != 1:
+        raise NotImplementedError(f"only ConstantMean is supported (factory.py:72); got {type(mean_module).__name__}")
     covar = gp.covar_module
     base = getattr(covar, "base_kernel", None)
     if base is None:
@@ -121,6 +139,40 @@ def _extract_single(gp: Any) -> GPObjective:
         y_mean=y_mean,
         y_std=y_std,
     )
+
+
+def _fp_tensor(t: Tensor):
+    return (t.data_ptr(), t._version, tuple(t.shape))
+
+
+def _fp_objective(o: GPObjective):
+    return (_fp_tensor(o.train_x), _fp_tensor(o.train_y), _fp_tensor(o.lengthscale), o.outputscale,
+            o.mean_const, o.noise, o.kernel, o.y_mean, o.y_std)
+
+
+def model_fingerprint(model: Any):
+    """Cheap identity of everything ``extract_gp_state`` reads: storage pointers and in-place version
+    counters of the training data and of every parameter / buffer (plain floats by value).  The
+    acquisition function compares it on every call and rebuilds its cached GPU state when the model
+    was re-fitted, re-conditioned in place or had hyper-parameters changed -- the reference queries
+    the model on every call (``discretekg.py:275-284``), so a stale cache would be a silent divergence."""
+    subs = getattr(model, "models", None)
+    if subs is None:
+        raise TypeError(f"expected a model list with a '.models' attribute; got {type(model)}")
+    out = []
+    for gp in subs:
+        if isinstance(gp, GPObjective):
+            out.append(_fp_objective(gp))
+        elif isinstance(gp, torch.nn.Module):
+            fp = [id(gp), _fp_tensor(gp.train_inputs[0]), _fp_tensor(gp.train_targets)]
+            fp += [(t.data_ptr(), t._version) for t in gp.parameters()]
+            fp += [(t.data_ptr(), t._version) for t in gp.buffers()]
+            out.append(tuple(fp))
+        else:  # duck-typed stand-in without parameters(): hyper-parameters by value
+            o = _extract_single(gp)
+            out.append((_fp_tensor(gp.train_inputs[0]), _fp_tensor(gp.train_targets), tuple(o.lengthscale.tolist()),
+                        o.outputscale, o.mean_const, o.noise, o.kernel, o.y_mean, o.y_std))
+    return tuple(out)
 
 
 def extract_gp_state(model: Any) -> GPModelList:

@@ -18,8 +18,3 @@ def make_torch_std_grid(n_points_per_axis, n_dimensions, tkwargs=None):
     mesh = torch.meshgrid(*([axis] * n_dimensions), indexing="ij")
     return torch.stack([m.reshape(-1) for m in mesh], dim=-1)
 
-
-def is_power_of_2(n):
-    if not isinstance(n, int):
-        raise TypeError(f"Expected n to be an int. Got {type(n)}.")
-    return (n & (n - 1) == 0) and n != 0

@@ -1,0 +1,123 @@
+"""Several acquisition functions at the same candidates in ONE pass.
+
+The decoupled strategy evaluates one ``DiscreteKnowledgeGradient`` per objective
+(``acquisition_optimisation_strategy.py:208``); the reference does so one after the other, one
+candidate at a time.  Here the acquisition functions run concurrently -- one CUDA stream per plan,
+so the latency-bound stages of one (hull march, backward gathers) overlap the streaming stages of
+the other -- on one upload of the candidates, write into one packed result buffer, and -- under
+``torch.distributed`` with a shard group -- each rank evaluates its contiguous share of the rows and
+ONE all-gather (on the device, before the single device-to-host copy) gives every rank all values
+and gradients of all objectives.
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import distributed as _dist
+
+
+class _Scratch:
+    """Streams and staging buffers reused across calls (keyed by device / shapes)."""
+
+    def __init__(self):
+        self.streams = {}
+        self.pinned = {}
+
+    def streams_for(self, dev, n):
+        key = (dev.index, n)
+        if key not in self.streams:
+            self.streams[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        return self.streams[key]
+
+    def pinned_like(self, shape):
+        key = tuple(shape)
+        if key not in self.pinned:
+            self.pinned[key] = torch.empty(shape, dtype=torch.double).pin_memory()
+        return self.pinned[key]
+
+
+_scratch = _Scratch()
+
+
+def evaluate_objectives(
+    acqfs: Sequence, X: Tensor, need_grad: bool = False, group=None
+) -> Tuple[Tensor, Optional[Tensor]]:
+    """``acqfs``: M ``DiscreteKnowledgeGradient`` instances over the same input space;
+    ``X``: ``(C, d)`` candidates (host or CUDA tensor; identical on every rank of ``group``).
+
+    Returns ``kg (M, C)`` and, if ``need_grad``, ``dX (M, C, d)`` with ``dX[m, c] = d kg[m, c] / d X[c]``,
+    on ``X``'s device, identical on every rank."""
+    plans = [a._get_plan() for a in acqfs]
+    M = len(plans)
+    dev = plans[0].device
+    d = plans[0].d
+    if X.dim() != 2 or X.shape[1] != d:
+        raise ValueError(f"X must be (C, {d}); got {tuple(X.shape)}")
+    on_host = not X.is_cuda
+    C = X.shape[0]
+    shard = group is not None and _dist.should_shard(C, group)
+    world = dist.get_world_size(group) if shard else 1
+    rank = dist.get_rank(group) if shard else 0
+    lo, hi = _dist.shard_bounds(C, world, rank)
+    rows = _dist.max_shard_rows(C, world)
+    width = 1 + (d if need_grad else 0)
+    import contextlib
+
+    cuda = dev.type == "cuda"  # (CPU "plans" exist only in the gloo tests of this host logic)
+    with (torch.cuda.device(dev) if cuda else contextlib.nullcontext()):
+        Xs = X[lo:hi]
+        if Xs.dtype != torch.double:
+            Xs = Xs.to(torch.double)
+        Xd = Xs.to(device=dev, non_blocking=True).contiguous()
+        # packed per objective as [kg (rows) | dX (rows x d)] so that both are contiguous views
+        buf = torch.empty(M, rows * width, dtype=torch.double, device=dev)
+        if hi - lo < rows:
+            buf.zero_()
+        cur = torch.cuda.current_stream() if cuda else None
+        streams = _scratch.streams_for(dev, M) if (cuda and M > 1) else [cur] * M
+        n = hi - lo
+        for m, (plan, s) in enumerate(zip(plans, streams)):
+            if s is not cur:
+                s.wait_stream(cur)
+            with (torch.cuda.stream(s) if cuda else contextlib.nullcontext()):
+                plan.forward_device(Xd, need_grad, out_kg=buf[m, :n],
+                                    out_dX=buf[m, rows: rows + n * d] if need_grad else None)
+        for s in streams:
+            if s is not cur:
+                cur.wait_stream(s)
+        if shard:
+            backend_cpu = dist.get_backend(group) == "gloo"
+            send = buf.cpu() if backend_cpu else buf
+            recv = torch.empty(world * send.numel(), dtype=buf.dtype, device=send.device)
+            dist.all_gather_into_tensor(recv, send.reshape(-1), group=group)
+            recv = recv.view((world,) + tuple(buf.shape))
+        else:
+            recv = buf.unsqueeze(0)
+        if on_host and recv.is_cuda:
+            host = _scratch.pinned_like(recv.shape)
+            host.copy_(recv, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            recv = host
+        elif not on_host and not recv.is_cuda:
+            recv = recv.to(dev)
+    # (world, M, rows * width) -> kg (M, C), dX (M, C, d) in row order
+    kg_parts, dX_parts = [], []
+    for r in range(world):
+        rlo, rhi = _dist.shard_bounds(C, world, r)
+        k = rhi - rlo
+        kg_parts.append(recv[r, :, :k])
+        if need_grad:
+            dX_parts.append(recv[r, :, rows: rows + k * d].reshape(M, k, d))
+    kg = kg_parts[0] if world == 1 else torch.cat(kg_parts, dim=1)
+    dX = None
+    if need_grad:
+        dX = dX_parts[0] if world == 1 else torch.cat(dX_parts, dim=1)
+    if on_host:  # the pinned staging buffer is reused by the next call
+        kg = kg.clone()
+        dX = dX.clone() if dX is not None else None
+    return kg, dX

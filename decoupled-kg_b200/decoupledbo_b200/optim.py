@@ -76,32 +76,53 @@ def _lbfgsb_chunk(acq_function, X0: Tensor, bounds: Tensor, maxiter: int) -> Ten
     return torch.max(torch.min(X, bounds[1]), bounds[0])
 
 
-def optimize_acqf(
-    acq_function,
-    bounds: Tensor,
-    q: int,
-    num_restarts: int,
-    raw_samples: int,
-    options: Optional[Dict] = None,
-) -> Tuple[Tensor, Tensor]:
-    """Same call as the reference makes (``q=1``); returns ``(candidate 1 x d, value)``."""
+def gen_batch_initial_conditions(
+    acq_function, bounds: Tensor, q: int, num_restarts: int, raw_samples: int, options: Optional[Dict] = None
+) -> Tensor:
+    """Steps 1-2 above (BoTorch's function of the same name): ``num_restarts x q x d`` starting points.
+    Draws from the global torch RNG (Sobol seed, multinomial), like BoTorch's."""
     if HAVE_BOTORCH:  # pragma: no cover
-        from botorch.optim import optimize_acqf as _botorch_optimize_acqf
+        from botorch.optim.initializers import gen_batch_initial_conditions as _botorch_gen
 
-        return _botorch_optimize_acqf(
-            acq_function=acq_function, bounds=bounds, q=q, num_restarts=num_restarts,
-            raw_samples=raw_samples, options=options,
-        )
+        return _botorch_gen(acq_function=acq_function, bounds=bounds, q=q, num_restarts=num_restarts,
+                            raw_samples=raw_samples, options=options)
     if q != 1:
         raise NotImplementedError("only q=1 is used by DiscreteKgOptimisationSpec")
     options = dict(options or {})
     batch_limit = int(options.get("batch_limit", num_restarts))
     init_limit = int(options.get("init_batch_limit", batch_limit))
-    maxiter = int(options.get("maxiter", 200))
     seed = int(torch.randint(0, 2**31 - 1, (1,)).item())
     X_raw = draw_sobol_samples(bounds=bounds, n=raw_samples, q=q, seed=seed)  # raw x 1 x d
     Y_raw = _batched_values(acq_function, X_raw, init_limit)
-    X_init = initialize_q_batch(X_raw, Y_raw, n=num_restarts, eta=float(options.get("eta", 2.0)))
+    return initialize_q_batch(X_raw, Y_raw, n=num_restarts, eta=float(options.get("eta", 2.0)))
+
+
+def optimize_acqf(
+    acq_function,
+    bounds: Tensor,
+    q: int,
+    num_restarts: int,
+    raw_samples: Optional[int] = None,
+    options: Optional[Dict] = None,
+    batch_initial_conditions: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor]:
+    """Same call as the reference makes (``q=1``); returns ``(candidate 1 x d, value)``.
+    ``batch_initial_conditions`` (``num_restarts x 1 x d``) skips the raw-sample phase, as in BoTorch."""
+    if HAVE_BOTORCH:  # pragma: no cover
+        from botorch.optim import optimize_acqf as _botorch_optimize_acqf
+
+        return _botorch_optimize_acqf(
+            acq_function=acq_function, bounds=bounds, q=q, num_restarts=num_restarts,
+            raw_samples=raw_samples, options=options, batch_initial_conditions=batch_initial_conditions,
+        )
+    if q != 1:
+        raise NotImplementedError("only q=1 is used by DiscreteKgOptimisationSpec")
+    options = dict(options or {})
+    batch_limit = int(options.get("batch_limit", num_restarts))
+    maxiter = int(options.get("maxiter", 200))
+    X_init = batch_initial_conditions
+    if X_init is None:
+        X_init = gen_batch_initial_conditions(acq_function, bounds, q, num_restarts, raw_samples, options)
     chunks = []
     for lo in range(0, num_restarts, batch_limit):
         chunks.append(_lbfgsb_chunk(acq_function, X_init[lo : lo + batch_limit], bounds, maxiter))

@@ -33,7 +33,7 @@ extern "C" {
 #define DKG_API
 #endif
 
-#define DKG_ABI_VERSION 2
+#define DKG_ABI_VERSION 3
 
 /* error codes */
 #define DKG_OK 0
@@ -146,6 +146,20 @@ DKG_API int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev,
                                double* dE_db_dev, void* stream);
 
 /*
+ * dkg_piecewise_expectation_dev -- replaces calculate_expected_value_of_piecewise_linear_function
+ *   (discretekg.py:415-452) for P piecewise-linear functions of H pieces each with CALLER-GIVEN break
+ *   points: E[f(Z)], Z ~ N(0,1), f = a[p,k] + b[p,k] z on (z[p,k-1], z[p,k]), z[p,-1] = -inf,
+ *   z[p,H-1] = +inf.  Also the gradient autograd would produce (optional outputs):
+ *   dE/da [P, H], dE/db [P, H], dE/dz [P, H-1].
+ *
+ *   a_dev, b_dev [P, H]; z_dev [P, H-1] (may be NULL when H == 1); e_dev [P]
+ *   H == 0 -> DKG_EEMPTY (the reference raises ValueError, discretekg.py:466-470)
+ */
+DKG_API int dkg_piecewise_expectation_dev(const double* a_dev, const double* b_dev, const double* z_dev,
+                                          int32_t P, int32_t H, double* e_dev, double* dE_da_dev,
+                                          double* dE_db_dev, double* dE_dz_dev, void* stream);
+
+/*
  * dkg_int8_matmul_dev -- D[M, N] = A[M, K] . Bt[N, K]^T in fp64 accuracy on the int8 tensor cores
  *   (tcgen05.mma.kind::i8 over exact base-256 digit planes; csrc/dkg_ozaki.cu).  This is the
  *   contraction engine behind the covariance rows of discretekg.py:301, exposed so that it can
@@ -195,9 +209,9 @@ DKG_API int dkg_profile_read(double* ms_host, int64_t* count_host, int32_t ncat)
 /* per-plan statistics of the last forward (8 host ints): [0] candidates, [1] lines surviving the
  * chord filter (sum over the sets finished by the warp kernel), [2] (candidate, scalarisation) sets
  * handled by the cooperative overflow kernel, [3] total hull vertices, [4] sets taking the
- * |slope| < 1e-9 shortcut, [5] sets that needed the block-wide exact march, [6] sets with more hull
- * vertices than the 64 record slots (their value is exact; their gradient omits the extra
- * vertices -- the Python layer raises if this is ever non-zero), [7] 1 when the covariance
+ * |slope| < 1e-9 shortcut, [5] sets that needed the block-wide exact march, [6] sets whose hull
+ * records did not all fit (more than 64 vertices AND the spill pool, DKG_SPILL_BLOCKS, exhausted:
+ * their value is exact, the gradient rows of their candidates are NaN), [7] 1 when the covariance
  * contraction of this plan runs on the int8 tensor cores (0: fp64 DMMA kernel) */
 DKG_API int dkg_plan_stats(dkg_plan* plan, int64_t* out8_host, void* stream);
 

@@ -110,9 +110,18 @@ def main():
     print("coupled          :", np.round(cpl.numpy(), 4).tolist(), " golden [[0.0383, 0.0224, 0.0130], [0.0005, 0.0058, 0.0015]]")
     print("scalar decoupled :", float(dec[0, 0]), " golden 0.02968190595713936")
     print("scalar coupled   :", float(cpl[0, 0]), " golden 0.038261974207699244")
+    # the "noiseless" variant of the fixture (conftest.py:41-44: noise fixed at 1e-4, not trained);
+    # no goldens depend on it -- the reference only runs gradcheck on it (test_discretekg.py:110-135)
+    res_nl = fit(x, Y, fixed_noise=1e-4)
+    model_nl = build_model(res_nl.x, x, Y, fixed_noise=1e-4)
+    print("noiseless fit:", res_nl.message, "loss", res_nl.fun, "nit", res_nl.nit)
     out = os.path.join(ROOT, "tests", "golden", "reference_fixture_refit.npz")
     np.savez_compressed(
         out, train_x=x.numpy(), train_y=Y.numpy(),
+        nl_lengthscale=np.stack([o.lengthscale.numpy() for o in model_nl.models]),
+        nl_outputscale=np.array([o.outputscale for o in model_nl.models]),
+        nl_mean_const=np.array([o.mean_const for o in model_nl.models]),
+        nl_noise=np.array([o.noise for o in model_nl.models]),
         lengthscale=np.stack([o.lengthscale.numpy() for o in model.models]),
         outputscale=np.array([o.outputscale for o in model.models]),
         mean_const=np.array([o.mean_const for o in model.models]),

@@ -13,7 +13,7 @@ from decoupledbo_b200.modules.acquisition_optimisation_strategy import (
     DiscreteKgOptimisationSpec,
     choose_best_objective,
 )
-from decoupledbo_b200.modules.utils import is_power_of_2, make_torch_std_grid
+from decoupledbo_b200.modules.utils import make_torch_std_grid
 from helpers import small_problem
 
 
@@ -111,13 +111,6 @@ def test_std_grid_order():  # utils.py:83-92 docstring example
     assert g.tolist() == want
     with pytest.raises(ValueError):
         make_torch_std_grid(3, 0)
-
-
-def test_is_power_of_2():  # tests/modules/test_utils.py:6-27
-    assert [is_power_of_2(n) for n in (1, 2, 4, 1024)] == [True] * 4
-    assert [is_power_of_2(n) for n in (0, 3, 6, 1000, -2)] == [False] * 5
-    with pytest.raises(TypeError):
-        is_power_of_2(2.0)
 
 
 def test_choose_best_objective_tie_breaking():  # strategy.py:143-163

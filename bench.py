@@ -9,9 +9,12 @@ forward + backward.  Workload = BASELINE.json configs[3] ("c4", the configuratio
 quoted on: 2-obj d=4 GP, n_train=400, |X_disc|=16384, 16 scalarisations, 4096 candidates), which
 fits one GPU.  A "step" is one pass of DiscreteKnowledgeGradient forward+backward over the batch
 of candidates for BOTH objectives (two acquisition functions, target_output_ix = 0 and 1), as
-DiscreteKgOptimisationSpec.optimize_for_single_objective drives it.  Multi-GPU: weak scaling --
-every rank evaluates its own 4096-candidate shard with replicated GP state and the values (+
-gradients) are all-gathered over NCCL for the argmax, inside the timed step.
+DiscreteKgOptimisationSpec.optimize_for_single_objective drives it, through the product API
+`decoupledbo_b200.multi.evaluate_objectives` (both objectives on one upload of the candidates, one
+CUDA stream per objective, one packed result buffer).  Multi-GPU: ONE problem, the global batch of
+N x 4096 candidates (weak scaling) is split into contiguous shards with replicated GP state and the
+values + gradients of BOTH objectives are all-gathered with ONE NCCL collective on the device, inside
+the timed step; a "strong" block (4096 candidates in total over the N GPUs) is reported next to it.
 
 Prints ONE JSON line on rank 0.
 """
@@ -55,16 +58,12 @@ def parse_args():
     return ap.parse_args()
 
 
-def build_problem(workload: str, n_cand: int, seed_shift: int = 0):
+def build_problem(workload: str, n_cand: int):
     from decoupledbo_b200 import synthetic
 
     if workload == "c4":
-        P = synthetic.problem_c4(n_cand=n_cand)
-    else:
-        P = synthetic.problem_c2(n_cand=n_cand)
-    if seed_shift:
-        P.candidates = synthetic.sobol(n_cand, P.d, 8 + 1000 * seed_shift)
-    return P
+        return synthetic.problem_c4(n_cand=n_cand)
+    return synthetic.problem_c2(n_cand=n_cand)
 
 
 def workload_config(workload: str, P, n_cand: int, world: int):
@@ -78,8 +77,9 @@ def workload_config(workload: str, P, n_cand: int, world: int):
         "x_disc": int(P.x_disc.shape[0]),
         "n_train": o.n,
         "d": P.d,
-        "parallelism": f"candidate-sharded x{world}, replicated GP state, one all-gather of values+grads; "
-                       "the two objectives' evaluations run on two CUDA streams",
+        "parallelism": f"candidate-sharded x{world} (one problem, contiguous shards of the global batch), replicated "
+                       "GP state, ONE all-gather of [objectives, values+grads] on the device per step; the two "
+                       "objectives' evaluations run on two CUDA streams",
         "l2": "no flush: per-step working set (slope rows 0.5 GB/objective + B, B^T 105 MB) exceeds the 126 MB L2",
     }
 
@@ -213,6 +213,10 @@ def run_reference_arm(args, rank: int, world: int):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference repo is pure Python on botorch/gpytorch (absent here): oracle port timed",
+        "warmup_requested": args.warmup,
+        "warmup_note": ("warm-up cut to 1 step: one step of this arm costs > 5 s of CPU time (it only warms caches; "
+                        "every step does the same work)") if warm != args.warmup else None,
+        "gpus_note": "CPU arm: rank 0 alone runs it whatever --gpus says (task contract); it does not scale with N",
     }
     print(json.dumps(line), flush=True)
 
@@ -251,35 +255,28 @@ def main():
 
     import torch.distributed as dist
     from decoupledbo_b200 import _native
-    from decoupledbo_b200.distributed import first_argmax
+    from decoupledbo_b200.distributed import shard_bounds
     from decoupledbo_b200.modules.acquisition.discretekg import DiscreteKnowledgeGradient
+    from decoupledbo_b200.multi import evaluate_objectives
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (VERSION prints a banner there)
         dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
 
-    n_cand = args.candidates or (4096 if args.workload == "c4" else 512)
-    n_total = n_cand
-    if args.scaling == "strong":
-        from decoupledbo_b200.distributed import shard_bounds
-
-        P_all = build_problem(args.workload, n_cand)
-        lo, hi = shard_bounds(n_cand, world, rank)
-        P = P_all
-        P.candidates = P_all.candidates[lo:hi].contiguous()
-        n_total = n_cand
-        n_cand = max_rows = -(-n_total // world)
-        if hi - lo < n_cand:  # keep shards equal (pad with a repeated row) so the all-gather is regular
-            pad = P.candidates[-1:].expand(n_cand - (hi - lo), -1)
-            P.candidates = torch.cat([P.candidates, pad])
-    else:
-        P = build_problem(args.workload, n_cand, seed_shift=rank)
+    per_gpu = args.candidates or (4096 if args.workload == "c4" else 512)
+    # weak scaling (the headline `value`): the global batch grows with the GPU count; strong: it is fixed
+    n_weak = per_gpu * world
+    n_strong = per_gpu
+    n_main = n_weak if args.scaling == "weak" else n_strong
+    P = build_problem(args.workload, n_weak)  # one problem; the strong batch is its first n_strong candidates
     S = int(P.weights.shape[0])
     M = P.model.num_outputs
     d = P.d
@@ -288,124 +285,117 @@ def main():
     for a in acqs:
         a.precision = args.precision
     plans = [a._get_plan() for a in acqs]
-    X_dev = P.candidates.to(dev).contiguous()
-    gather_buf = torch.empty(world * n_cand, 1 + d, dtype=torch.double, device=dev) if world > 1 else None
-
-    # The objectives are independent acquisition functions (strategy.py:208): each plan runs on its
-    # own stream so the latency-bound stages of one (hull march, backward gathers) overlap the
-    # other's streaming stages; the gathers / argmax follow on the main stream.
-    streams = [torch.cuda.Stream(device=dev) for _ in plans]
-
-    def step_device():
-        best = []
-        cur = torch.cuda.current_stream()
-        outs = []
-        for plan, s in zip(plans, streams):
-            s.wait_stream(cur)
-            with torch.cuda.stream(s):
-                outs.append(plan.forward_device(X_dev, True))
-        for s in streams:
-            cur.wait_stream(s)
-        for kg, dX in outs:
-            if world > 1:
-                send = torch.cat([kg.unsqueeze(1), dX], dim=1)
-                dist.all_gather_into_tensor(gather_buf, send)
-                best.append(gather_buf[:, 0].argmax())
-            else:
-                best.append(kg.argmax())
-        return best
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
+    def timed(step, steps):
+        """W >= 3 warm-ups, then `steps` steps bracketed by barrier + synchronize; CUDA events on the
+        launching stream, max over ranks.  Returns ms per step."""
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        _native.launch_count_reset()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier()
+        timed.launches = _native.launch_count()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.double, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    def timed_wall(step, steps):
+        for _ in range(3):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.double, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return 1e3 * float(t) / steps
+
+    # ---- device-resident inputs: the global candidate batch lives in HBM on every rank ----
+    def make_device_step(n_global):
+        X_dev = P.candidates[:n_global].to(dev).contiguous()
+
+        def step():
+            kg, dX = evaluate_objectives(acqs, X_dev, need_grad=True, group=group)
+            return kg.argmax(dim=1)  # first-index argmax per objective, identical on every rank
+
+        return step
+
+    # ---- host buffers: H2D of this rank's shard, kernels, ONE collective, ONE D2H, host argmax ----
+    def make_host_step(n_global):
+        X_host = P.candidates[:n_global].clone().pin_memory()
+
+        def step():
+            kg, dX = evaluate_objectives(acqs, X_host, need_grad=True, group=group)
+            return [int(kg[m].argmax()) for m in range(M)]
+
+        return step
+
+    step_main = make_device_step(n_main)
+    for _ in range(2):
+        step_main()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    _native.launch_count_reset()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step_device()
-    e1.record()
-    barrier()
-    launches = _native.launch_count()
+    ms_step = timed(step_main, args.steps)
+    launches = timed.launches
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.double, device=dev)
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_step = float(ms_total) / args.steps
-    n_global = n_total if args.scaling == "strong" else world * n_cand
-    evals_step = n_global * M * S
+    evals_step = n_main * M * S
     value = evals_step / (ms_step * 1e-3)
+    lo, hi = shard_bounds(n_main, world, rank)
+    n_cand = hi - lo  # candidates this rank evaluates per step
 
-    # ---- end-to-end through the public API with HOST buffers ----
     e2e = None
     if not args.no_e2e:
-        X_host = P.candidates.clone().pin_memory()
-
-        # one host thread + CUDA stream per objective: the objectives are independent acquisition
-        # functions, ctypes releases the GIL inside dkg_forward_host, so their copies and kernels overlap
-        from concurrent.futures import ThreadPoolExecutor
-
-        pool = ThreadPoolExecutor(max_workers=len(acqs))
-        host_streams = [torch.cuda.Stream(device=dev) for _ in acqs]
-
-        def eval_objective(i):
-            torch.cuda.set_device(dev)
-            with torch.cuda.stream(host_streams[i]):
-                X = X_host.detach().requires_grad_(True)  # fresh leaf over the pinned buffer
-                kg = acqs[i](X.unsqueeze(1))  # public API: (*b) x 1 x d -> (*b)
-                loss = -kg.sum()
-                (g,) = torch.autograd.grad(loss, X)
-            return kg.detach(), g
-
-        def step_host():
-            out = []
-            for kg, g in pool.map(eval_objective, range(len(acqs))):
-                if world > 1:
-                    send = torch.cat([kg.unsqueeze(1), g], dim=1).to(dev)
-                    dist.all_gather_into_tensor(gather_buf, send)
-                    out.append(int(gather_buf[:, 0].argmax()))
-                else:
-                    out.append(int(kg.argmax()))
-            return out
-
-        for _ in range(3):
-            step_host()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_host()
-        barrier()
-        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.double, device=dev)
-        if world > 1:
-            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        ms_e2e = timed_wall(make_host_step(n_main), args.steps)
+        rows = -(-n_main // world)
         e2e = {
-            "value": evals_step * args.steps / float(t_e2e),
+            "value": evals_step / (ms_e2e * 1e-3),
             "unit": UNIT,
-            "h2d_bytes_per_step": M * n_cand * d * 8,
-            "d2h_bytes_per_step": M * n_cand * (1 + d) * 8,
-            "ms_per_step": 1e3 * float(t_e2e) / args.steps,
-            "api": "DiscreteKnowledgeGradient.forward(X_host) + autograd.grad -> dkg_forward_host; one host "
-                   "thread and CUDA stream per objective",
+            "h2d_bytes_per_step": rows * d * 8,
+            "d2h_bytes_per_step": world * M * rows * (1 + d) * 8,
+            "ms_per_step": ms_e2e,
+            "api": "decoupledbo_b200.multi.evaluate_objectives(acqfs, X_host, need_grad=True, group): pinned host "
+                   "candidates -> H2D of this rank's shard -> both objectives' kernels (dkg_forward_dev, one stream "
+                   "each) -> one NCCL all-gather on the device (N > 1) -> one D2H of every rank's values + gradients "
+                   "-> host argmax; bytes are per rank",
         }
+
+    strong = None
+    if world > 1 and args.scaling == "weak":
+        ms_s = timed(make_device_step(n_strong), args.steps)
+        strong = {"candidates_total": n_strong, "ms_per_step": ms_s, "value": n_strong * M * S / (ms_s * 1e-3),
+                  "unit": UNIT}
+        if not args.no_e2e:
+            ms_se = timed_wall(make_host_step(n_strong), args.steps)
+            strong["e2e_ms_per_step"] = ms_se
+            strong["e2e_value"] = n_strong * M * S / (ms_se * 1e-3)
 
     # ---- roofline of the dominant kernel (separate profiled steps, CUDA events per launch) ----
     roofline = None
     cpu_baseline = None
     extra = {}
     if rank == 0:
+        X_loc = P.candidates[lo:hi].to(dev).contiguous()
         _native.profile_enable(True)
         for _ in range(3):
             for plan in plans:
-                plan.forward_device(X_dev, True)
+                plan.forward_device(X_loc, True)
         prof = _native.profile_read()
         _native.profile_enable(False)
         ms_g, n_g = prof["gemm_cov"]
@@ -434,6 +424,14 @@ def main():
             kp = sum(-(-m.n // 32) * 32 for m in P.model.models) / sum(m.n for m in P.model.models)
             int8_ops = flops_total * products * kp
             int8_peak = 2.0 * bf16
+            # the same kernel's MMA instruction stream with operand copies and accumulator drains switched
+            # off: what the tensor pipe retires on THIS box under its power / clock conditions
+            mma_peak = None
+            if args.precision == "float64":
+                try:
+                    mma_peak, _ = _native.int8_peak(n_cand, N, max(m.n for m in P.model.models), 10)
+                except Exception as exc:  # noqa: BLE001
+                    extra["int8_peak_error"] = str(exc)
             peak = int8_peak / (products * kp)  # the int8 roofline in fp64-equivalent TFLOP/s
             roofline = {
                 "kernel": "ozaki_kernel (tcgen05.mma.kind::i8 over base-256 digit planes: the fp64 GP "
@@ -444,6 +442,10 @@ def main():
                                f"{products * kp:.1f} int8 ops the scheme spends per algorithmic fp64 flop",
                 "int8_top_s_executed": int8_ops / (ms_g * 1e-3) / 1e12,
                 "int8_peak_top_s": int8_peak,
+                "int8_mma_peak_top_s_measured": mma_peak,
+                "frac_vs_measured_int8_mma_peak": (int8_ops / (ms_g * 1e-3) / 1e12 / mma_peak) if mma_peak else None,
+                "frac_vs_nominal_int8_4500_top_s": int8_ops / (ms_g * 1e-3) / 1e12 / 4500.0,
+                "tensor_pipe_active_ncu": "see profiles/ (ncu sm__pipe_tensor_subpipe... of the same launch)",
                 "dgemm_peak_tflops": dgemm_peak,
                 "frac_vs_dgemm_peak": achieved / dgemm_peak,
                 "flops_per_launch": flops_total / max(n_g, 1),
@@ -504,6 +506,26 @@ def main():
                 n2 += 1
             extra["cpu_baseline_row_only"] = {"value": S * n2 / t_acc2, "unit": UNIT, "cores": cores,
                                               "kind": "port", "sample": f"{n2} pairs, row-only posterior"}
+            # (V) of BASELINE.md section 3: vectorised, row-only, batched CPU implementation with the
+            # candidate-independent work hoisted out (oracle/vectorised.py) -- the strong host baseline
+            from oracle import vectorised as ov
+
+            t0 = time.perf_counter()
+            preps = [ov.Prepared(om, P.x_disc, P.weights, t) for t in range(M)]
+            t_prep = time.perf_counter() - t0
+            nb, t_acc3, n3 = 32, 0.0, 0
+            while t_acc3 < 8.0 and n3 < 8:
+                t0 = time.perf_counter()
+                ov.kg_batch(preps[n3 % M], P.candidates[(n3 // M) * nb:(n3 // M + 1) * nb], need_grad=True)
+                t_acc3 += time.perf_counter() - t0
+                n3 += 1
+            extra["cpu_baseline_vectorised"] = {
+                "value": S * nb * n3 / t_acc3, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{n3} batches of {nb} candidates x 1 objective x {S} scalarisations, fwd+bwd, batched row-only "
+                          f"posterior (one GEMM per batch), chord prefilter + exact march per set, envelope-theorem "
+                          f"gradient; candidate-independent preparation ({t_prep:.2f} s for both objectives) not timed, "
+                          f"as on the GPU",
+            }
 
     if rank == 0:
         line = {
@@ -512,10 +534,12 @@ def main():
             "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64" if args.precision == "float64" else "f64 (covariance contraction: 4 base-256 int8 digits)",
             "data": "synthetic",
-            "config": workload_config(args.workload, P, n_cand, world),
+            "config": workload_config(args.workload, P, per_gpu, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
+        if strong is not None:
+            line["strong"] = strong
         line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:

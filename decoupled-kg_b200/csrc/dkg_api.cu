@@ -5,6 +5,8 @@
 #include <cstring>
 #include <vector>
 
+#include <algorithm>
+#include <numeric>
 #include <string>
 
 #include "dkg_emax.cuh"
@@ -73,7 +75,38 @@ static void free_workspace(Workspace& w) {
   dev_free(w.spill_head); dev_free(w.spill_next); dev_free(w.spill_idx); dev_free(w.spill_p); dev_free(w.spill_q); dev_free(w.spill_used);
   dev_free(w.amax_is_new); dev_free(w.stats); dev_free(w.sdj); dev_free(w.Zc);
   for (int m = 0; m < MAX_M; ++m) { dev_free(w.KXm[m]); dev_free(w.Tm[m]); dev_free(w.varlat[m]); dev_free(w.COVm[m]); }
+  if (w.stats_pinned) { cudaFreeHost(w.stats_pinned); w.stats_pinned = nullptr; }
+  if (w.stats_ev) { cudaEventDestroy(w.stats_ev); w.stats_ev = nullptr; }
+  w.stats_pending = false;
+  w.spill_checked = false;
   w.cap_C = w.chunk_C = 0;
+}
+
+static int alloc_spill(Workspace& w, long long blocks) {
+  dev_free(w.spill_next); dev_free(w.spill_idx); dev_free(w.spill_p); dev_free(w.spill_q);
+  if (blocks < 1) blocks = 1;
+  w.spill_blocks = (int)(blocks > 0x03ffffff ? 0x03ffffff : blocks);
+  DKG_TRY(dev_alloc(&w.spill_next, (size_t)w.spill_blocks, false));
+  DKG_TRY(dev_alloc(&w.spill_idx, (size_t)w.spill_blocks * SPILL_BLOCK, false));
+  DKG_TRY(dev_alloc(&w.spill_p, (size_t)w.spill_blocks * SPILL_BLOCK, false));
+  DKG_TRY(dev_alloc(&w.spill_q, (size_t)w.spill_blocks * SPILL_BLOCK, false));
+  return DKG_OK;
+}
+
+// The last forward dropped hull records (spill pool exhausted): size the pool from what that forward
+// saw -- its total hull-vertex count bounds the records that can spill -- with 50 % headroom.
+// Returns 1 when the pool was grown (the caller may re-run), 0 if there was nothing to do.
+static int grow_spill_if_needed(dkg_plan* p, const long long* h, int* grew) {
+  *grew = 0;
+  Workspace& w = p->ws;
+  if (h[6] <= 0 || getenv("DKG_SPILL_BLOCKS") != nullptr) return DKG_OK;  // an explicit size is never overridden
+  const long long sets = (long long)w.chunk_C * p->S;
+  long long need = (h[3] / SPILL_BLOCK + sets) * 3 / 2;
+  if (need <= w.spill_blocks) need = 2ll * w.spill_blocks;
+  DKG_CUDA_OK(cudaDeviceSynchronize());
+  DKG_TRY(alloc_spill(w, need));
+  *grew = 1;
+  return DKG_OK;
 }
 
 static int ensure_workspace(dkg_plan* p, int C) {
@@ -152,17 +185,19 @@ static int ensure_workspace(dkg_plan* p, int C) {
   DKG_TRY(dev_alloc(&w.hull_idx, (size_t)chunk * S * HULL_CAP, false));
   DKG_TRY(dev_alloc(&w.hull_p, (size_t)chunk * S * HULL_CAP, false));
   DKG_TRY(dev_alloc(&w.hull_q, (size_t)chunk * S * HULL_CAP, false));
-  {  // spill pool for sets with more than HULL_CAP hull vertices: one block per 8 sets by default
-    long long blocks = (long long)chunk * (long long)S / 8;
-    if (blocks < 256) blocks = 256;
+  {  // spill pool for sets with more than HULL_CAP hull vertices: one block per 4 sets to start with;
+     // it grows on demand (grow_spill_if_needed) unless DKG_SPILL_BLOCKS pins its size
+    long long blocks = (long long)chunk * (long long)S / 4;
+    if (blocks < 512) blocks = 512;
     if (const char* e = getenv("DKG_SPILL_BLOCKS")) blocks = atoll(e) >= 0 ? atoll(e) : blocks;
-    w.spill_blocks = (int)(blocks > 0x3fffffff ? 0x3fffffff : blocks);
     DKG_TRY(dev_alloc(&w.spill_head, (size_t)chunk * S, false));
-    DKG_TRY(dev_alloc(&w.spill_next, (size_t)w.spill_blocks, false));
-    DKG_TRY(dev_alloc(&w.spill_idx, (size_t)w.spill_blocks * SPILL_BLOCK, false));
-    DKG_TRY(dev_alloc(&w.spill_p, (size_t)w.spill_blocks * SPILL_BLOCK, false));
-    DKG_TRY(dev_alloc(&w.spill_q, (size_t)w.spill_blocks * SPILL_BLOCK, false));
+    DKG_TRY(alloc_spill(w, blocks));
     DKG_TRY(dev_alloc(&w.spill_used, (size_t)1));
+    DKG_CUDA_OK(cudaHostAlloc((void**)&w.stats_pinned, sizeof(long long) * 8, cudaHostAllocDefault));
+    memset(w.stats_pinned, 0, sizeof(long long) * 8);
+    DKG_CUDA_OK(cudaEventCreateWithFlags(&w.stats_ev, cudaEventDisableTiming));
+    w.stats_pending = false;
+    w.spill_checked = false;
   }
   DKG_TRY(dev_alloc(&w.amax_is_new, (size_t)chunk * S));
   DKG_TRY(dev_alloc(&w.stats, (size_t)8));
@@ -181,6 +216,7 @@ static void destroy_plan(dkg_plan* p) {
   }
   dev_free(p->W); dev_free(p->wt); dev_free(p->xd); dev_free(p->alpha_all);
   dev_free(p->mu_disc); dev_free(p->A0); dev_free(p->A0f); dev_free(p->A0max); dev_free(p->A0arg);
+  dev_free(p->A0tmax); dev_free(p->perm);
   free_workspace(p->ws);
   delete p;
 }
@@ -251,6 +287,48 @@ static bool needs_refinement(const ObjState& o, double jitter) {
   return !(bound < 1e-11);
 }
 
+// p->xd <- the discretisation in the plan's internal line order (see dkg_plan::perm): sorted by the
+// Morton code of the points (bits interleaved across the d coordinates, as many bits per coordinate as
+// fit into 63).  DKG_NO_REORDER=1 keeps the caller's order.
+static int order_discretisation(dkg_plan* p, const double* x_disc_dev, cudaStream_t st) {
+  const int N = p->N, d = p->d;
+  if (N < 2 * FILTER_TILE || getenv("DKG_NO_REORDER") != nullptr) {
+    DKG_CUDA_OK(cudaMemcpyAsync(p->xd, x_disc_dev, sizeof(double) * N * d, cudaMemcpyDeviceToDevice, st));
+    return DKG_OK;
+  }
+  std::vector<double> h((size_t)N * d);
+  DKG_CUDA_OK(cudaMemcpyAsync(h.data(), x_disc_dev, sizeof(double) * N * d, cudaMemcpyDeviceToHost, st));
+  DKG_CUDA_OK(cudaStreamSynchronize(st));
+  std::vector<double> lo(d, INFINITY), hi(d, -INFINITY);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < d; ++k) {
+      const double v = h[(size_t)n * d + k];
+      if (v < lo[k]) lo[k] = v;
+      if (v > hi[k]) hi[k] = v;
+    }
+  const int bits = 63 / d < 16 ? 63 / d : 16;
+  std::vector<unsigned long long> code(N, 0ull);
+  for (int n = 0; n < N; ++n) {
+    unsigned long long c = 0ull;
+    for (int k = 0; k < d; ++k) {
+      const double span = hi[k] - lo[k];
+      double u = span > 0.0 ? (h[(size_t)n * d + k] - lo[k]) / span : 0.0;
+      if (!(u >= 0.0)) u = 0.0;  // NaN coordinates sort first
+      unsigned long long q = (unsigned long long)(u * (double)((1ull << bits) - 1) + 0.5);
+      for (int b = 0; b < bits; ++b) c |= ((q >> b) & 1ull) << (b * d + k);
+    }
+    code[n] = c;
+  }
+  std::vector<int> perm(N);
+  std::iota(perm.begin(), perm.end(), 0);
+  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return code[a] < code[b]; });
+  DKG_TRY(dev_alloc(&p->perm, (size_t)N, false));
+  DKG_CUDA_OK(cudaMemcpyAsync(p->perm, perm.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
+  DKG_TRY(gather_rows(x_disc_dev, p->perm, N, d, p->xd, st));
+  DKG_CUDA_OK(cudaStreamSynchronize(st));  // `perm` is a stack-lifetime host buffer
+  return DKG_OK;
+}
+
 static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_disc_dev,
                       cudaStream_t st) {
   const int d = p->d, N = p->N, M = p->M, S = p->S, tgt = p->target;
@@ -268,7 +346,7 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
   DKG_TRY(dev_alloc(&p->alpha_all, (size_t)n_sum));
   DKG_TRY(dev_alloc(&p->mu_disc, (size_t)N * M));
   DKG_TRY(dev_alloc(&p->xd, (size_t)N * d));
-  DKG_CUDA_OK(cudaMemcpyAsync(p->xd, x_disc_dev, sizeof(double) * N * d, cudaMemcpyDeviceToDevice, st));
+  DKG_TRY(order_discretisation(p, x_disc_dev, st));
 
   int rc = DKG_OK;
   int off = 0;
@@ -386,6 +464,9 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
       cudaMemcpyAsync(p->wt, wt_host, sizeof(double) * S, cudaMemcpyHostToDevice, st);
       cudaStreamSynchronize(st);  // wt_host is a stack buffer
       rc = build_a0(p->mu_disc, N, M, p->W, S, p->A0, p->A0f, p->N_pad, p->A0max, p->A0arg, st);
+      p->a0_tiles = ceil_div(p->N_pad, FILTER_TILE);
+      if (rc == DKG_OK) rc = dev_alloc(&p->A0tmax, (size_t)S * p->a0_tiles);
+      if (rc == DKG_OK) rc = build_a0_tilemax(p->A0f, p->N_pad, S, FILTER_TILE, p->a0_tiles, p->A0tmax, st);
     }
   }
   cudaStreamSynchronize(st);
@@ -439,9 +520,47 @@ static int solve_T(const ObjState& o, const double* KX, double* T, double* R, in
 
 static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st);
 
+static int forward_once(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st);
+static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st);
+
+// outcome of an EARLIER forward (copied asynchronously, looked at without a sync): grow the pool if
+// that forward dropped records
+static int spill_precheck(dkg_plan* p) {
+  Workspace& w = p->ws;
+  if (w.stats_pending && w.stats_ev != nullptr && cudaEventQuery(w.stats_ev) == cudaSuccess) {
+    w.stats_pending = false;
+    int grew = 0;
+    DKG_TRY(grow_spill_if_needed(p, w.stats_pinned, &grew));
+  }
+  return DKG_OK;
+}
+
+// One forward (+ backward) on device buffers with the spill-pool bookkeeping around it: the first
+// forward with gradients on a workspace is checked synchronously (and re-run with a larger pool if
+// records were dropped), later ones leave their outcome for the next call's precheck -- no host sync.
 static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st) {
   if (C == 0) return DKG_OK;
+  DKG_TRY(spill_precheck(p));
   DKG_TRY(ensure_workspace(p, C));
+  Workspace& w = p->ws;
+  for (int attempt = 0;; ++attempt) {
+    DKG_TRY(forward_once(p, X, C, kg, dX, st));
+    if (dX == nullptr) return DKG_OK;
+    DKG_CUDA_OK(cudaMemcpyAsync(w.stats_pinned, w.stats, sizeof(long long) * 8, cudaMemcpyDeviceToHost, st));
+    if (w.spill_checked) {
+      DKG_CUDA_OK(cudaEventRecord(w.stats_ev, st));
+      w.stats_pending = true;
+      return DKG_OK;
+    }
+    DKG_CUDA_OK(cudaStreamSynchronize(st));
+    w.spill_checked = true;
+    int grew = 0;
+    DKG_TRY(grow_spill_if_needed(p, w.stats_pinned, &grew));
+    if (!grew || attempt >= 3) return DKG_OK;
+  }
+}
+
+static int forward_once(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st) {
   if (p->target < 0) return forward_coupled(p, X, C, kg, dX, st);
   Workspace& w = p->ws;
   const ObjState& ot = p->obj[p->target];
@@ -500,6 +619,7 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
     lb.Z = w.Z; lb.ldz = p->ldz;
     lb.A = p->A0; lb.a_sc = 0; lb.a_sj = p->N_pad;
     lb.A32 = p->A0f;
+    lb.A32tmax = p->A0tmax; lb.a32_tiles = p->a0_tiles;
     lb.a_own = w.a_new + (size_t)c0 * S;
     lb.wt = p->wt;
     lb.Amax = p->A0max; lb.Aarg = p->A0arg; lb.am_sc = 0;
@@ -623,6 +743,7 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
     lb.Z = w.Zc; lb.ldz = p->ldz;
     lb.A = p->A0; lb.a_sc = 0; lb.a_sj = p->N_pad;
     lb.A32 = p->A0f;
+    lb.A32tmax = p->A0tmax; lb.a32_tiles = p->a0_tiles;
     lb.a_own = w.a_new + (size_t)c0 * S;
     lb.wt = nullptr;
     lb.Amax = p->A0max; lb.Aarg = p->A0arg; lb.am_sc = 0;
@@ -744,15 +865,28 @@ int dkg_forward_host(dkg_plan* plan, const double* X_host, int32_t C, double* kg
   if (C < 0) { set_error("C=%d is negative", C); return DKG_EINVAL; }
   if (C == 0) return DKG_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  DKG_TRY(spill_precheck(plan));
   DKG_TRY(ensure_workspace(plan, C));
   Workspace& w = plan->ws;
   const int d = plan->d;
   DKG_CUDA_OK(cudaMemcpyAsync(w.X, X_host, sizeof(double) * (size_t)C * d, cudaMemcpyHostToDevice, st));
-  DKG_TRY(forward_impl(plan, w.X, C, w.kg, dX_host ? w.dX : nullptr, st));
-  DKG_CUDA_OK(cudaMemcpyAsync(kg_host, w.kg, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, st));
-  if (dX_host)
-    DKG_CUDA_OK(cudaMemcpyAsync(dX_host, w.dX, sizeof(double) * (size_t)C * d, cudaMemcpyDeviceToHost, st));
-  DKG_CUDA_OK(cudaStreamSynchronize(st));
+  for (int attempt = 0;; ++attempt) {
+    DKG_TRY(forward_once(plan, w.X, C, w.kg, dX_host ? w.dX : nullptr, st));
+    DKG_CUDA_OK(cudaMemcpyAsync(kg_host, w.kg, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, st));
+    if (dX_host) {
+      DKG_CUDA_OK(cudaMemcpyAsync(dX_host, w.dX, sizeof(double) * (size_t)C * d, cudaMemcpyDeviceToHost, st));
+      DKG_CUDA_OK(cudaMemcpyAsync(w.stats_pinned, w.stats, sizeof(long long) * 8, cudaMemcpyDeviceToHost, st));
+    }
+    DKG_CUDA_OK(cudaStreamSynchronize(st));
+    if (!dX_host) break;
+    // the one sync of this entry point also tells whether hull records were dropped: re-run with a
+    // larger spill pool instead of handing back NaN gradient rows
+    w.spill_checked = true;
+    w.stats_pending = false;
+    int grew = 0;
+    DKG_TRY(grow_spill_if_needed(plan, w.stats_pinned, &grew));
+    if (!grew || attempt >= 3) break;
+  }
   return DKG_OK;
 }
 
@@ -871,6 +1005,13 @@ int dkg_expected_max_lines_dev(const double* a_dev, const double* b_dev, int32_t
   return rc;
 }
 
+int dkg_int8_peak(int32_t M, int32_t N, int32_t K, int32_t reps, int32_t mode, double* tops_host, double* ms_host,
+                  void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || K > OZ_MAX_K || reps < 1 || !tops_host) { set_error("dkg_int8_peak: invalid argument"); return DKG_EINVAL; }
+  return ozaki_mma_peak(round_up(M, 256), round_up(N, GEMM_BN), K, OZ_DEFAULT_DIGITS, OZ_DEFAULT_DIAGONALS, reps, mode, tops_host,
+                        ms_host, (cudaStream_t)stream);
+}
+
 int dkg_piecewise_expectation_dev(const double* a_dev, const double* b_dev, const double* z_dev, int32_t P,
                                   int32_t H, double* e_dev, double* dE_da_dev, double* dE_db_dev,
                                   double* dE_dz_dev, void* stream) {
@@ -919,6 +1060,13 @@ int64_t dkg_plan_read(dkg_plan* plan, const char* name, double* out_dev, int64_t
   if (out_dev && count > 0) {
     if (capacity < count) { set_error("capacity %lld < %lld", (long long)capacity, (long long)count); return DKG_EINVAL; }
     if (!src) { set_error("tensor '%s' not available yet", name); return DKG_EINVAL; }
+    // tensors indexed by discretisation line are handed out in the CALLER's line order
+    const bool by_cols = nm == "B" || nm == "A0" || nm == "slopes";
+    const bool by_rows = nm == "mu_disc";
+    if (plan->perm != nullptr && (by_cols || by_rows)) {
+      int rc = unpermute(src, ld, rows, cols, plan->perm, plan->N, by_rows, out_dev, (cudaStream_t)stream);
+      return rc == DKG_OK ? count : rc;
+    }
     cudaError_t e = cudaMemcpy2DAsync(out_dev, cols * sizeof(double), src, ld * sizeof(double),
                                       cols * sizeof(double), rows, cudaMemcpyDeviceToDevice,
                                       (cudaStream_t)stream);

@@ -18,6 +18,8 @@ struct LineBatch {
   int ldz = 0;
   const double* A = nullptr;
   const float* A32 = nullptr;      // optional float copy of A (same strides; shared table only): fp32 chord filter
+  const float* A32tmax = nullptr;  // optional [S, a32_tiles] max of A32 over tiles of FILTER_TILE lines (tile culling)
+  int a32_tiles = 0;
   long long a_sc = 0;
   int a_sj = 0;
   const double* a_own = nullptr;

@@ -19,6 +19,10 @@ int mu_disc(const double* xd, int N, int d, const ObjState& o, double* mu, int M
 int build_a0(const double* mu, int N, int M, const double* W, int S, double* A0, float* A0f, int ld,
              double* A0max, int* A0arg, cudaStream_t st);
 
+int build_a0_tilemax(const float* A0f, int ld, int S, int tile, int ntiles, float* out, cudaStream_t st);
+int gather_rows(const double* in, const int* perm, int rows, int d, double* out, cudaStream_t st);
+int unpermute(const double* src, long long ld, long long rows, long long cols, const int* perm, int n_perm, bool by_rows,
+              double* out, cudaStream_t st);
 int cholesky_blocked(double* A, int n, int ld, int* info_dev, cudaStream_t st);
 int tri_inverse(const double* L, int n, int ldl, double* X, int ldx, cudaStream_t st);
 int matvec(const double* A, int lda, int rows, int cols, const double* x, double* y, cudaStream_t st);
@@ -63,6 +67,8 @@ int ozaki_store(const unsigned char* a_digits, const double* sa, int M_pad, cons
                 int N, cudaStream_t st);
 // b_nonneg: every entry of the B operand is >= 0 (true for kernel values), which lets all its digit planes be
 // multiplied as UINT8 and pairs of them be merged into N = 256 instructions
+int ozaki_mma_peak(int M_pad, int N_pad, int K, int NS, int NG, int reps, int mode, double* tops_out, double* ms_out,
+                   cudaStream_t st);
 int ozaki_any_negative(const double* X, int ld, int rows, int cols, int* flag_dev, cudaStream_t st);
 
 // ---- dkg_forward.cu --------------------------------------------------------------------------

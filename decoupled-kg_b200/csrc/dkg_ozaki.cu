@@ -19,18 +19,27 @@
 // dropped terms are below 2^-64 * K of full scale (1e-16 relative to |row|max * |col|max), i.e.
 // under the rounding error of an fp64 dot product of that length.
 //
-// Kernel: persistent, one CTA per SM, 128 x 128 output tile.
-//   warp 0    : TMA producer - cp.async.bulk.tensor.2d of the A digit block (128 rows x 128 B)
-//               and the B digit block into a 4-stage ring (SWIZZLE_128B), mbarrier complete_tx.
-//   warp 1    : one thread issues tcgen05.mma.cta_group::1.kind::i8 (M128 N128 K32), 4 per
-//               stage; tcgen05.commit frees the stage and, at the end of a diagonal, publishes
-//               the TMEM accumulator (2 x 128 columns, double buffered).
-//   warps 2-9 : tcgen05.ld the int32 diagonal sums, fold them into 64 fp64 registers per thread
-//               (acc += 256^-g * S_g) while the MMA warp already runs the next diagonal; after
-//               the last one apply the row / column scales, evaluate the kernel term and write
-//               coalesced rows through a per-warp shared-memory transpose.
+// Kernel (ozaki_kernel): persistent, one CTA per SM (grid = #SMs), 128 x 128 output tile, 640 threads.
+//   warp 0      : producer - per k block (K = 32 bytes) two LINEAR cp.async.bulk copies (the digits
+//                 0..nd-1 of one (row block, k block) are one contiguous run of ready-made UMMA operand
+//                 images in global memory: 128 rows x 32 B, canonical NO-SWIZZLE core-matrix order),
+//                 into a 2-stage ring of 64 KB stages, mbarrier complete_tx.
+//   warp 1      : MMA issuer - one lane chosen with elect.sync issues tcgen05.mma.cta_group::1.kind::i8
+//                 (M128 N128 K32, or N256 when two adjacent B digit planes are merged).  The loop is
+//                 k-outer with one TMEM accumulator slot (128 columns) per DIAGONAL: pass 0 folds the
+//                 diagonals 7..4 into the four slots (all 512 TMEM columns), pass 1 the diagonals 3..0,
+//                 so every digit block is fetched once per pass.  tcgen05.commit frees the stage and
+//                 publishes each slot.  The first and the last k block of a pass are issued slot by
+//                 slot in the order the epilogue drains them, so the drain of one pass overlaps the
+//                 MMAs at the seam of two passes instead of stalling the tensor pipe.
+//   warps 4..19 : epilogue (setmaxnreg 104) - tcgen05.ld the int32 diagonal sums (32 lanes x 32
+//                 columns per warp), convert exactly to fp64 and fold acc += 256^-g * S_g into 32 fp64
+//                 registers per thread; after the last pass apply the two power-of-two scales and
+//                 write the 32 x 32 block through an 8-column shared-memory transpose.
+//   (warps 2, 3 idle; setmaxnreg 56 for warps 0..3.)
 // Signed / unsigned digits only differ in the instruction descriptor (a_format / b_format), so
 // the first digit of each operand is multiplied as INT8 and the others as UINT8.
+// ozaki_pair_kernel is the cta_group::2 variant (cluster of 2, M = 256); measured no faster, not default.
 #include <cstdlib>
 
 #include "dkg_kernels.cuh"
@@ -41,7 +50,7 @@ namespace {
 
 constexpr int OZ_BM = 128;
 constexpr int OZ_BN = 128;
-constexpr int OZ_KB = 32;             // bytes of K per stage = one MMA (K32), SWIZZLE_32B rows
+constexpr int OZ_KB = 32;             // bytes of K per k block = one MMA (K32); no-swizzle core-matrix images
 constexpr int OZ_BLK_BYTES = OZ_BM * OZ_KB;  // one digit block (A or B) of a stage: 4 KB
 constexpr int OZ_MAX_DIGITS = 7;
 constexpr int OZ_STAGES = 2;
@@ -181,12 +190,36 @@ __device__ __forceinline__ void issue_pass_k(unsigned tmem_base, unsigned long l
   constexpr int g_lo = g_hi - OZ_ACC + 1 > 0 ? g_hi - OZ_ACC + 1 : 0;
   constexpr int nd = (g_hi < NS - 1 ? g_hi : NS - 1) + 1;  // digits 0 .. nd-1 of both operands are staged
   // accumulator slot a holds the diagonal g_lo + a
-  if (FIRST) {
+  if (FIRST || LAST) {
+    // Seam of two passes.  The epilogue drains the slots in the order a = OZ_ACC-1 .. 0 and needs
+    // ~800 cycles per slot; waiting for all four before the first MMA (and publishing all four after
+    // the last) left the tensor pipe idle for a full drain per pass (~15 % of the kernel).  Here
+    // the last k block finishes slot by slot in drain order and publishes each slot at once, and
+    // the first k block of the next pass restarts each slot as soon as IT has been drained.
 #pragma unroll
-    for (int a = 0; a < OZ_ACC; ++a) bar_wait(&tempty[a], par ^ 1);
-    tc_fence_after();
+    for (int a = OZ_ACC - 1; a >= 0; --a) {
+      const int g = g_lo + a;
+      if (FIRST) {
+        bar_wait(&tempty[a], par ^ 1);
+        tc_fence_after();
+      }
+      if (g <= g_hi) {
+        const int ilo = g - NS + 1 > 0 ? g - NS + 1 : 0, ihi = g < NS - 1 ? g : NS - 1;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          if (i >= ilo && i <= ihi) {
+            const int j = g - i;
+            umma_i8(tmem_base + (unsigned)(a * OZ_BN), base + (unsigned long long)((i * OZ_BLK_BYTES) >> 4),
+                    base + (unsigned long long)(((nd + j) * OZ_BLK_BYTES) >> 4), umma_idesc(i == 0, MERGE ? 0 : j == 0),
+                    (i > ilo || !FIRST) ? 1u : 0u);
+          }
+        }
+      }
+      if (LAST) umma_commit(&tfull[a]);
+    }
+    return;
   }
-  if (MERGE && !FIRST) {
+  if (MERGE) {
     // B digit planes are all unsigned here, so for a fixed A digit i the products with two
     // consecutive B digits j, j+1 (diagonals i+j, i+j+1 = adjacent slots; the two digit blocks are
     // adjacent in the stage) go out as ONE M128 N256 K32 instruction: 19 instead of 34 MMAs per
@@ -221,15 +254,11 @@ __device__ __forceinline__ void issue_pass_k(unsigned tmem_base, unsigned long l
             const int j = g - i;
             umma_i8(tmem_base + (unsigned)(a * OZ_BN), base + (unsigned long long)((i * OZ_BLK_BYTES) >> 4),
                     base + (unsigned long long)(((nd + j) * OZ_BLK_BYTES) >> 4), umma_idesc(i == 0, MERGE ? 0 : j == 0),
-                    (t > 0 || !FIRST) ? 1u : 0u);
+                    1u);
           }
         }
       }
     }
-  }
-  if (LAST) {
-#pragma unroll
-    for (int a = 0; a < OZ_ACC; ++a) umma_commit(&tfull[a]);
   }
 }
 
@@ -958,16 +987,23 @@ static int ozaki_launch(const unsigned char* a_digits, const double* sa, int M_p
   args.sa = sa;
   args.sb = sb;
   {
-    const char* e = getenv("DKG_OZ_KPS");
-    args.max_kps = e != nullptr ? atoi(e) : OZ_MAX_KPS;
-    if (args.max_kps < 1) args.max_kps = 1;
-    if (args.max_kps > OZ_MAX_KPS) args.max_kps = OZ_MAX_KPS;
-    e = getenv("DKG_OZ_SLOTWAIT");
-    args.slot_wait = e != nullptr ? atoi(e) : 1;
-    e = getenv("DKG_OZ_DBG");
-    args.dbg = e != nullptr ? atoi(e) : 0;
-    e = getenv("DKG_OZ_MERGE");
-    if (e != nullptr && atoi(e) == 0) args.b_unsigned = 0;
+    // tuning / measurement switches, read once per process
+    static int kps = 0, slot_wait = 1, dbg = 0, merge = 1;
+    if (kps == 0) {
+      const char* e = getenv("DKG_OZ_KPS");
+      int v = e != nullptr ? atoi(e) : OZ_MAX_KPS;
+      e = getenv("DKG_OZ_SLOTWAIT");
+      slot_wait = e != nullptr ? atoi(e) : 1;
+      e = getenv("DKG_OZ_DBG");
+      dbg = e != nullptr ? atoi(e) : 0;
+      e = getenv("DKG_OZ_MERGE");
+      merge = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+      kps = v < 1 ? 1 : v > OZ_MAX_KPS ? OZ_MAX_KPS : v;
+    }
+    args.max_kps = kps;
+    args.slot_wait = slot_wait;
+    args.dbg |= dbg;
+    if (!merge) args.b_unsigned = 0;
   }
   if (pair_mode(NS, NG)) {
     const int tiles = ((args.m_tiles + 1) / 2) * args.n_tiles;
@@ -1023,6 +1059,54 @@ int ozaki_store(const unsigned char* a_digits, const double* sa, int M_pad, cons
   args.M = M;
   args.N = N;
   return ozaki_launch(a_digits, sa, M_pad, b_digits, sb, N_pad, K, NS, NG, args, st);
+}
+
+// Measured int8 tensor peak of THIS kernel's instruction stream: the same launch with the operand
+// copies and the TMEM drains switched off (MMAs run on whatever the stages hold; results discarded),
+// i.e. the rate at which the tensor pipe retires M128 N128/256 K32 kind::i8 instructions under the
+// box's power / clock conditions.  Returns executed int8 TOP/s over `reps` launches (CUDA events).
+int ozaki_mma_peak(int M_pad, int N_pad, int K, int NS, int NG, int reps, int mode, double* tops_out, double* ms_out,
+                   cudaStream_t st) {
+  const int KP = ozaki_kp(K);
+  unsigned char* dig = nullptr;
+  double* sc = nullptr;
+  const size_t bytes = ozaki_digit_bytes(M_pad > N_pad ? M_pad : N_pad, K, NS);
+  DKG_CUDA_OK(cudaMalloc((void**)&dig, bytes));
+  DKG_CUDA_OK(cudaMalloc((void**)&sc, sizeof(double) * (size_t)((M_pad > N_pad ? M_pad : N_pad) + 256)));
+  DKG_CUDA_OK(cudaMemsetAsync(dig, 1, bytes, st));
+  DKG_CUDA_OK(cudaMemsetAsync(sc, 0, sizeof(double) * (size_t)((M_pad > N_pad ? M_pad : N_pad) + 256), st));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  int rc = DKG_OK;
+  for (int it = 0; it < reps + 2 && rc == DKG_OK; ++it) {
+    if (it == 2) cudaEventRecord(e0, st);
+    OzakiArgs args{};
+    args.b_unsigned = 1;
+    args.cov = 0;
+    args.D = nullptr;
+    args.M = 0;  // store_tail writes nothing
+    args.N = 0;
+    args.ldd = 0;
+    args.dbg = mode & 3;  // bit 0: no operand copies, bit 1: no accumulator drains (3 = MMA stream only)
+    rc = ozaki_launch(dig, sc, M_pad, dig, sc, N_pad, K, NS, NG, args, st);
+  }
+  cudaEventRecord(e1, st);
+  cudaError_t e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(dig);
+  cudaFree(sc);
+  if (rc != DKG_OK) return rc;
+  if (e != cudaSuccess) { set_error("ozaki_mma_peak: %s", cudaGetErrorString(e)); return DKG_ECUDA; }
+  int pairs = 0;
+  for (int g = 0; g < NG; ++g) pairs += (g < NS - 1 ? g : NS - 1) - (g - NS + 1 > 0 ? g - NS + 1 : 0) + 1;
+  const double ops = 2.0 * (double)M_pad * (double)N_pad * (double)KP * pairs * reps;
+  if (ms_out) *ms_out = ms / reps;
+  if (tops_out) *tops_out = ops / (ms * 1e-3) / 1e12;
+  return DKG_OK;
 }
 
 }  // namespace dkg

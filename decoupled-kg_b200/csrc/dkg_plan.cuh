@@ -84,9 +84,17 @@ struct Workspace {
   int* spill_used = nullptr;   // [1]
   int* amax_is_new = nullptr;  // [chunk_C, S]  1 if the max intercept is the candidate's own line
   long long* stats = nullptr;  // [8] device counters
+  // host mirror of `stats`, copied asynchronously after every forward with gradients: the NEXT call
+  // (or the host-buffer entry point, which synchronises anyway) sees whether the spill pool ran dry
+  // and grows it -- without a host sync on the device-resident path
+  long long* stats_pinned = nullptr;  // [8] pinned host memory
+  cudaEvent_t stats_ev = nullptr;
+  bool stats_pending = false;
+  bool spill_checked = false;  // the first forward with gradients after a (re)allocation is checked synchronously
   int last_C = 0;
 };
 
+constexpr int FILTER_TILE = 128;  // lines per warp of the fp32 chord filter (4 per lane)
 constexpr int SURV_CAP = 2048;  // survivors per (candidate, scalarisation) before the slow path
 constexpr int HULL_CAP = 64;    // hull vertices recorded per (candidate, scalarisation)
 
@@ -114,6 +122,13 @@ struct dkg_plan {
   double* mu_disc = nullptr;  // [N, M]
   double* A0 = nullptr;       // [S, N_pad]   scalarised intercepts of the discretisation lines
   float* A0f = nullptr;       // [S, N_pad]   float copy of A0 (fp32 chord filter; padding = -inf)
+  float* A0tmax = nullptr;    // [S, a0_tiles] max of A0f over tiles of FILTER_TILE consecutive lines (tile culling)
+  int a0_tiles = 0;
+  // Internal line order: the discretisation is re-ordered along a Morton curve at plan time, so that
+  // FILTER_TILE consecutive lines are neighbours in input space -- similar posterior means and similar
+  // covariance with any candidate -- and the chord filter can drop most tiles with one test.  Line n of
+  // every internal table is line perm[n] of the caller's x_discretisation (nullptr: identity).
+  int* perm = nullptr;        // [N]
   double* A0max = nullptr;    // [S]
   int* A0arg = nullptr;       // [S]
   double jitter = 0.0;        // Cholesky jitter that was needed (0 normally)

@@ -339,6 +339,57 @@ __global__ void a0max_kernel(const double* __restrict__ A0, int N, int ld, doubl
   }
 }
 
+// A0tmax[j, t] = max of the float intercepts of scalarisation j over the lines [t * tile, (t + 1) * tile):
+// the fp32 chord filter culls a whole warp tile of lines with one test against it
+__global__ void a0_tilemax_kernel(const float* __restrict__ A0f, int ld, int tile, int ntiles, float* __restrict__ out) {
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), j = blockIdx.y, lane = threadIdx.x & 31;
+  if (t >= ntiles) return;
+  float m = -INFINITY;
+  for (int n = t * tile + lane; n < min((t + 1) * tile, ld); n += 32) m = fmaxf(m, A0f[(size_t)j * ld + n]);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) out[(size_t)j * ntiles + t] = m;
+}
+
+int build_a0_tilemax(const float* A0f, int ld, int S, int tile, int ntiles, float* out, cudaStream_t st) {
+  dim3 grid(ceil_div(ntiles, 4), S);
+  a0_tilemax_kernel<<<grid, 128, 0, st>>>(A0f, ld, tile, ntiles, out);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// out[i, :] = in[perm[i], :]
+__global__ void gather_rows_kernel(const double* __restrict__ in, const int* __restrict__ perm, int rows, int d,
+                                   double* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * d) return;
+  const int i = e / d, k = e - i * d;
+  out[e] = in[(size_t)perm[i] * d + k];
+}
+int gather_rows(const double* in, const int* perm, int rows, int d, double* out, cudaStream_t st) {
+  gather_rows_kernel<<<ceil_div(rows * d, 256), 256, 0, st>>>(in, perm, rows, d, out);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// undo the plan's internal line order for introspection: element (r, n) of src (row stride ld) belongs to
+// original line perm[n]; by_rows: the permuted index is the ROW (src is [n_perm, cols])
+__global__ void unpermute_kernel(const double* __restrict__ src, long long ld, long long rows, long long cols,
+                                 const int* __restrict__ perm, int n_perm, int by_rows, double* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * cols) return;
+  const long long r = e / cols, c = e - r * cols;
+  const double v = src[r * ld + c];
+  if (by_rows) out[(r < n_perm ? (long long)perm[r] : r) * cols + c] = v;
+  else out[r * cols + (c < n_perm ? (long long)perm[c] : c)] = v;
+}
+int unpermute(const double* src, long long ld, long long rows, long long cols, const int* perm, int n_perm, bool by_rows,
+              double* out, cudaStream_t st) {
+  if (rows * cols == 0) return DKG_OK;
+  unpermute_kernel<<<(unsigned)((rows * cols + 255) / 256), 256, 0, st>>>(src, ld, rows, cols, perm, n_perm, by_rows ? 1 : 0, out);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
 int build_a0(const double* mu, int N, int M, const double* W, int S, double* A0, float* A0f, int ld,
              double* A0max, int* A0arg, cudaStream_t st) {
   dim3 grid(ceil_div(ld, 128), S);

@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = (
     "dkg_piecewise_expectation_dev",
     "dkg_posterior_mean_dev",
     "dkg_int8_matmul_dev",
+    "dkg_int8_peak",
     "dkg_plan_read",
     "dkg_launch_count",
     "dkg_launch_count_reset",
@@ -108,6 +109,8 @@ def load_library() -> ctypes.CDLL:
         c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
         c_int32, c_void_p,
     ]
+    lib.dkg_int8_peak.restype = ctypes.c_int
+    lib.dkg_int8_peak.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(c_double), POINTER(c_double), c_void_p]
     lib.dkg_plan_read.restype = c_int64
     lib.dkg_plan_read.argtypes = [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]
     lib.dkg_launch_count.restype = c_int64
@@ -415,3 +418,14 @@ def piecewise_expectation(a: Tensor, b: Tensor, z: Tensor, want_grad: bool = Fal
     if want_grad:
         out["dE_da"], out["dE_db"], out["dE_dz"] = da, db, dz
     return out
+
+
+def int8_peak(M: int, N: int, K: int, reps: int = 10, mode: int = 3):
+    """Measured int8 tensor peak of the library's own MMA stream (``dkg_int8_peak``): (TOP/s, ms per launch).
+    mode 3 = MMA stream only; 1 = no operand copies; 2 = no accumulator drains; 0 = full kernel on dummy digits."""
+    dev = require_cuda()
+    tops, ms = c_double(0.0), c_double(0.0)
+    with torch.cuda.device(dev):
+        rc = load_library().dkg_int8_peak(M, N, K, reps, mode, byref(tops), byref(ms), _stream_ptr())
+    _check(rc, "dkg_int8_peak")
+    return float(tops.value), float(ms.value)

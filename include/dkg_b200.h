@@ -171,6 +171,18 @@ DKG_API int dkg_int8_matmul_dev(const double* A_dev, int32_t lda, const double* 
                                 int32_t n_diagonals, double* D_dev, int32_t ldd, void* stream);
 
 /*
+ * dkg_int8_peak -- measured int8 tensor-core peak of this library's own MMA instruction stream: the
+ *   contraction kernel of dkg_int8_matmul_dev launched `reps` times on an M x N x K problem with the
+ *   operand copies and the accumulator drains switched off (results discarded).  Used by bench.py as the
+ *   roofline denominator of the conditioning contraction; not part of the hot path.
+ *   mode: 3 = MMA stream only (the peak); 1 = no operand copies; 2 = no accumulator drains; 0 = the full
+ *   kernel on dummy digits (mode 0..2 decompose what keeps the real launch below the peak).
+ *   tops_host: executed int8 TOP/s; ms_host (optional): average launch duration.  Synchronises.
+ */
+DKG_API int dkg_int8_peak(int32_t M, int32_t N, int32_t K, int32_t reps, int32_t mode, double* tops_host,
+                          double* ms_host, void* stream);
+
+/*
  * Introspection for parity tests (all copies are device-to-device on `stream`).
  * name is one of:
  *   "B"        [n_i, N]   K_i^-1 k_i(X_train, X_disc)            (target objective i)

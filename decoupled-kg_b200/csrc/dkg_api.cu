@@ -70,7 +70,7 @@ static void dev_free(T*& p) {
 static void free_workspace(Workspace& w) {
   dev_free(w.X); dev_free(w.kg); dev_free(w.dX); dev_free(w.KX); dev_free(w.T); dev_free(w.R); dev_free(w.T_dig); dev_free(w.T_scale); dev_free(w.var);
   dev_free(w.sd); dev_free(w.zown); dev_free(w.Xs); dev_free(w.a_new); dev_free(w.kg_terms);
-  dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.zpv); dev_free(w.zpi); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } { double4* t = (double4*)w.chain; dev_free(t); w.chain = nullptr; } { float4* t = (float4*)w.chain32; dev_free(t); w.chain32 = nullptr; } { double4* t = (double4*)w.chainv; dev_free(t); w.chainv = nullptr; } { double4* t = (double4*)w.chain5; dev_free(t); w.chain5 = nullptr; } dev_free(w.far); dev_free(w.ovf_sets); dev_free(w.ovf_count);
+  dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.zpv); dev_free(w.zpi); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } { double4* t = (double4*)w.chain; dev_free(t); w.chain = nullptr; } { float4* t = (float4*)w.chain32; dev_free(t); w.chain32 = nullptr; } { double4* t = (double4*)w.chainv; dev_free(t); w.chainv = nullptr; } { double4* t = (double4*)w.chain5; dev_free(t); w.chain5 = nullptr; } { float4* t = (float4*)w.chain5f; dev_free(t); w.chain5f = nullptr; } { float2* t = (float2*)w.ztile; dev_free(t); w.ztile = nullptr; } dev_free(w.far); dev_free(w.ovf_sets); dev_free(w.ovf_count);
   dev_free(w.hull_cnt); dev_free(w.hull_idx); dev_free(w.hull_p); dev_free(w.hull_q);
   dev_free(w.spill_head); dev_free(w.spill_next); dev_free(w.spill_idx); dev_free(w.spill_p); dev_free(w.spill_q); dev_free(w.spill_used);
   dev_free(w.amax_is_new); dev_free(w.stats); dev_free(w.sdj); dev_free(w.Zc);
@@ -179,6 +179,11 @@ static int ensure_workspace(dkg_plan* p, int C) {
   { float4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * 2, false)); w.chain32 = t; }
   { double4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * 2, false)); w.chainv = t; }
   { double4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * 2, false)); w.chain5 = t; }
+  if (!coupled) {
+    { float4* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * 2, false)); w.chain5f = t; }
+    w.ztiles = ceil_div(p->N, FILTER_TILE);
+    { float2* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * w.ztiles, false)); w.ztile = t; }
+  }
   DKG_TRY(dev_alloc(&w.ovf_sets, (size_t)chunk * S, false));
   DKG_TRY(dev_alloc(&w.ovf_count, (size_t)1));
   DKG_TRY(dev_alloc(&w.hull_cnt, (size_t)chunk * S));
@@ -631,14 +636,17 @@ static int forward_once(dkg_plan* p, const double* X, int C, double* kg, double*
     sc.chainv = (double4*)w.chainv;
     sc.zpv = w.zpv; sc.zpi = w.zpi;
     sc.chain5 = (double4*)w.chain5;
+    sc.chain5f = (float4*)w.chain5f;
+    sc.ztile = (float2*)w.ztile; sc.ztiles = w.ztiles;
     sc.stats = w.stats;
     sc.spill_used = w.spill_used;
     CovFinish fin{};
     fin.xs = ep.xs; fin.xd_s = ep.xd_s; fin.sd = ep.sd; fin.d = d; fin.kind = ep.kind; fin.N = N;
     fin.outputscale = ep.outputscale; fin.ystd2 = ep.ystd2;
+    bool ztile_valid = false;
     { ProfScope ps(5, st);
-      DKG_TRY(emax_zstat(lb, sc, nullptr, nullptr, st, ot.Kxd_dig != nullptr ? &fin : nullptr)); }
-    { ProfScope ps(6, st); DKG_TRY(emax_filter(lb, sc, st)); }
+      DKG_TRY(emax_zstat(lb, sc, nullptr, nullptr, st, ot.Kxd_dig != nullptr ? &fin : nullptr, &ztile_valid)); }
+    { ProfScope ps(6, st); DKG_TRY(emax_filter(lb, sc, st, ztile_valid)); }
     EmaxOut out;
     out.terms = w.kg_terms + (size_t)c0 * S;
     out.subtract_max = 1;

@@ -201,7 +201,7 @@ constexpr int ZT_BYTES = 64 * 1024;
 template <int D>
 __global__ void __launch_bounds__(E_THREADS, 3)
 zfinish_tiled_kernel(LineBatch lb, CovFinish fin, double* __restrict__ zpv, int* __restrict__ zpi,
-                     int tile_lines, int rows_per_cta) {
+                     int tile_lines, int rows_per_cta, float2* __restrict__ ztile, int ztiles) {
   extern __shared__ __align__(16) unsigned char e_smem[];
   double* s_xd = reinterpret_cast<double*>(e_smem);  // [D][tile_lines]
   const int ntiles = gridDim.x, tile = blockIdx.x;
@@ -227,23 +227,23 @@ zfinish_tiled_kernel(LineBatch lb, CovFinish fin, double* __restrict__ zpv, int*
     int imin = 0x7fffffff, imax = 0x7fffffff;
     double vn[U];  // the next trip's products are requested before this trip's kernel evaluations
 #pragma unroll
-    for (int u = 0; u < U; ++u) vn[u] = lane < n_cnt ? zw[lane + 32 * u < n_cnt ? lane + 32 * u : lane] : 0.0;
-    for (int i0 = lane; i0 < n_cnt; i0 += 32 * U) {
+    for (int u = 0; u < U; ++u) vn[u] = lane + 32 * u < n_cnt ? zw[lane + 32 * u] : 0.0;
+    // (warp-uniform trip count: the tile statistics below use warp shuffles)
+    for (int b0 = 0; b0 < n_cnt; b0 += 32 * U) {
+      const int i0 = b0 + lane;
       double v[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) v[u] = vn[u];
       const int j0 = i0 + 32 * U;
-      if (j0 < n_cnt) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = j0 + 32 * u;
-          vn[u] = zw[i < n_cnt ? i : j0];
-        }
+      for (int u = 0; u < U; ++u) {
+        const int i = j0 + 32 * u;
+        if (i < n_cnt) vn[u] = zw[i];
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int i = i0 + 32 * u;
-        const int il = i < n_cnt ? i : i0;
+        const int il = i < n_cnt ? i : 0;
         double sq = 0.0;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
@@ -252,6 +252,7 @@ zfinish_tiled_kernel(LineBatch lb, CovFinish fin, double* __restrict__ zpv, int*
         }
         v[u] = (stationary_from_sq(kind, os, sq) - v[u]) * rsd;
       }
+      double tmin = INFINITY, tmax = -INFINITY;  // this trip's 128 consecutive lines = one filter tile
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int i = i0 + 32 * u;
@@ -259,7 +260,20 @@ zfinish_tiled_kernel(LineBatch lb, CovFinish fin, double* __restrict__ zpv, int*
           zw[i] = v[u];
           if (v[u] < vmin) { vmin = v[u]; imin = n_lo + i; }
           if (v[u] > vmax) { vmax = v[u]; imax = n_lo + i; }
+          tmin = fmin(tmin, v[u]);
+          tmax = fmax(tmax, v[u]);
         }
+      }
+      if (ztile != nullptr) {
+        // (min, max) of the tile's slopes as the chord filter will see them (rounded to nearest float;
+        // rounding is monotone, so these bracket every rounded slope of the tile)
+        float flo = __double2float_rn(tmin), fhi = __double2float_rn(tmax);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          flo = fminf(flo, __shfl_xor_sync(0xffffffffu, flo, o));
+          fhi = fmaxf(fhi, __shfl_xor_sync(0xffffffffu, fhi, o));
+        }
+        if (lane == 0) ztile[(size_t)r * ztiles + (n_lo + b0) / FILTER_TILE] = make_float2(flo, fhi);
       }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -302,7 +316,7 @@ __global__ void zreduce_kernel(LineBatch lb, int N, int ntiles, const double* __
 
 template <int D>
 static int launch_zfinish_tiled(const LineBatch& lb, const EmaxScratch& sc, const CovFinish& f, cudaStream_t st) {
-  const int tile_lines = (ZT_BYTES / (int)sizeof(double) / D) & ~31;
+  const int tile_lines = (ZT_BYTES / (int)sizeof(double) / D) & ~(FILTER_TILE - 1);  // whole filter tiles per CTA tile
   const int ntiles = ceil_div(f.N, tile_lines);
   int gy = ceil_div(3 * 148, ntiles);
   if (gy > ceil_div(lb.C, E_THREADS / 32)) gy = ceil_div(lb.C, E_THREADS / 32);
@@ -310,7 +324,8 @@ static int launch_zfinish_tiled(const LineBatch& lb, const EmaxScratch& sc, cons
   gy = ceil_div(lb.C, rows_per_cta);
   const size_t smem = (size_t)tile_lines * D * sizeof(double);
   DKG_CUDA_OK(cudaFuncSetAttribute(zfinish_tiled_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  zfinish_tiled_kernel<D><<<dim3(ntiles, gy), E_THREADS, smem, st>>>(lb, f, sc.zpv, sc.zpi, tile_lines, rows_per_cta);
+  zfinish_tiled_kernel<D><<<dim3(ntiles, gy), E_THREADS, smem, st>>>(lb, f, sc.zpv, sc.zpi, tile_lines, rows_per_cta, sc.ztile,
+                                                                       sc.ztiles);
   DKG_LAUNCH_CHECK();
   zreduce_kernel<<<ceil_div(lb.C, 128), 128, 0, st>>>(lb, f.N, ntiles, sc.zpv, sc.zpi, sc.zst, sc.zarg);
   DKG_LAUNCH_CHECK();
@@ -318,7 +333,8 @@ static int launch_zfinish_tiled(const LineBatch& lb, const EmaxScratch& sc, cons
 }
 
 int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int* aarg_out,
-               cudaStream_t st, const CovFinish* fin) {
+               cudaStream_t st, const CovFinish* fin, bool* ztile_written) {
+  if (ztile_written != nullptr) *ztile_written = false;
   if (lb.C == 0) return DKG_OK;
   CovFinish f{};
   if (fin != nullptr) f = *fin;
@@ -336,6 +352,7 @@ int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int
       default: rc = launch_zfinish_tiled<8>(lb, sc, f, st); break;
     }
     if (rc != DKG_OK) return rc;
+    if (ztile_written != nullptr) *ztile_written = sc.ztile != nullptr;
     const long long sets = (long long)lb.C * lb.S;
     chain_kernel<<<(unsigned)((sets + E_THREADS - 1) / E_THREADS), E_THREADS, 0, st>>>(lb, sc);
     DKG_LAUNCH_CHECK();
@@ -743,6 +760,13 @@ chain5_kernel(LineBatch lb, EmaxScratch sc) {
   if (set >= (size_t)lb.C * lb.S) return;
   const int c = (int)(set / lb.S), j = (int)(set - (size_t)c * lb.S);
   const double4 par = sc.chain[set];
+  float mf[4], cf[4];
+  ChainMag mag;
+  {  // magnitudes for the conservative float rounding (chord32): as in chain_params
+    const double4 v0 = sc.chainv[set * 2 + 0], v1 = sc.chainv[set * 2 + 1];
+    mag.amag = fmax(fabs(v0.w), fmax(fabs(v0.y), fabs(v1.w)));
+    mag.zmag = fmax(fabs(sc.zst[c * 2 + 0]), fabs(sc.zst[c * 2 + 1]));
+  }
 #pragma unroll
   for (int side = 0; side < 2; ++side) {
     const double pc = side == 0 ? par.x : par.z, pm = side == 0 ? par.y : par.w;
@@ -759,7 +783,279 @@ chain5_kernel(LineBatch lb, EmaxScratch sc) {
       }
     }
     sc.chain5[set * 2 + side] = q;
+    const float4 f0 = chord32(q.x, q.y, mag), f1 = chord32(q.z, q.w, mag);
+    mf[2 * side] = f0.x; cf[2 * side] = f0.z;
+    mf[2 * side + 1] = f1.x; cf[2 * side + 1] = f1.z;
   }
+  if (sc.chain5f != nullptr) {
+    sc.chain5f[set * 2 + 0] = make_float4(mf[0], mf[1], mf[2], mf[3]);
+    sc.chain5f[set * 2 + 1] = make_float4(cf[0], cf[1], cf[2], cf[3]);
+  }
+}
+
+// ---- tile-first fp32 filter (KG path, N >= 1024) ------------------------------------------------
+// The plan orders the discretisation along a Morton curve, so FILTER_TILE consecutive lines are
+// neighbours in input space: their slopes span a short interval [zlo, zhi] (written per (row, tile)
+// by the row-statistics pass) and their intercepts are bounded by the tile maximum of the shared
+// table (plan time).  The per-line test keeps a line iff  a > fma(m_k, z, c_k)  for one of the chords
+// k of the (second-level) chain; fma is monotone in z, so
+//     amax_tile <= min(fma(m_k, zlo, c_k), fma(m_k, zhi, c_k))   for EVERY chord k
+// proves that no line of the tile passes: the (tile, set) pair is dropped with one test and the
+// survivor lists are exactly those of the per-line filter.  At c4 81 % / 92 % of the (tile, set) pairs
+// and 64 % / 85 % of the (tile, row) pairs -- whose slopes are then not even read -- go this way.
+//
+// 1. probe32_kernel: 16 consecutive lines out of every 256 (a spatially spread sample in Morton order) against
+//    the 3-point chain; records the farthest line above each chord (sc.far) -> chain5_kernel builds the
+//    second-level chain P-U-T-V-Q (fp64) and its conservatively rounded float image.
+// 2. tilefilter_kernel: one warp per (row, 16 scalarisations, range of tile pairs); lane (half, j)
+//    decides tile 2 tp + half for scalarisation j; surviving (tile, set) pairs are tested line by line
+//    (4 consecutive lines per lane) against the 4 float chords, parked in a per-warp pool and written out
+//    after the exact fp64 re-test against the same chain.
+// the sample: PROBE_CHUNK consecutive lines (one 128-byte segment of the slope row) out of every
+// PROBE_PERIOD -- a spatially spread sample in Morton order that costs 1/16 of a pass over the rows
+// (single lines at a stride of 16 pull every 128-byte segment of the rows through DRAM: measured)
+constexpr int PROBE_CHUNK = 16;
+constexpr int PROBE_PERIOD = 256;
+constexpr int PROBE_THREADS = 128;
+constexpr int PROBE_G = 4;
+
+__global__ void __launch_bounds__(PROBE_THREADS)
+probe32_kernel(LineBatch lb, EmaxScratch sc, int JB) {
+  extern __shared__ __align__(16) unsigned char e_smem[];
+  const int S = lb.S;
+  const int j_lo = blockIdx.z * JB, j_hi = min(S, j_lo + JB), SB = j_hi - j_lo;
+  float4* s_p32 = reinterpret_cast<float4*>(e_smem);  // [SB][G][2] (m, m, c, c) per chord
+  unsigned long long* s_far = reinterpret_cast<unsigned long long*>(s_p32 + 2 * PROBE_G * JB);  // [SB * G][2]
+  const int c0 = blockIdx.y * PROBE_G;
+  for (int e = threadIdx.x; e < PROBE_G * SB; e += blockDim.x) {
+    const int j = j_lo + e / PROBE_G, g = e % PROBE_G;
+    const int c = c0 + g;
+    const bool in = c < lb.C;
+    const float4 none = make_float4(0.f, 0.f, INFINITY, INFINITY);
+    s_p32[2 * e] = in ? sc.chain32[((size_t)c * S + j) * 2] : none;
+    s_p32[2 * e + 1] = in ? sc.chain32[((size_t)c * S + j) * 2 + 1] : none;
+    s_far[2 * e] = 0ull;
+    s_far[2 * e + 1] = 0ull;
+  }
+  __syncthreads();
+  const int sample = blockIdx.x * PROBE_THREADS + (int)threadIdx.x;
+  const int n = (sample / PROBE_CHUNK) * PROBE_PERIOD + sample % PROBE_CHUNK;
+  if (n < lb.NA) {
+    float z[PROBE_G];
+#pragma unroll
+    for (int g = 0; g < PROBE_G; ++g) z[g] = __double2float_rn(lb.Z[(size_t)min(c0 + g, lb.C - 1) * lb.ldz + n]);
+    float a_nx = lb.A32[(size_t)j_lo * lb.a_sj + n];
+    for (int j = j_lo; j < j_hi; ++j) {
+      const float a = a_nx;
+      if (j + 1 < j_hi) a_nx = lb.A32[(size_t)(j + 1) * lb.a_sj + n];
+#pragma unroll
+      for (int g = 0; g < PROBE_G; ++g) {
+        const float4 q1 = s_p32[2 * ((j - j_lo) * PROBE_G + g)], q2 = s_p32[2 * ((j - j_lo) * PROBE_G + g) + 1];
+        if ((a > fmaf(q1.x, z[g], q1.z)) | (a > fmaf(q2.x, z[g], q2.z))) {  // rare (~1 %)
+          const int c = c0 + g;
+          if (c < lb.C) {
+            const size_t set = (size_t)c * S + j;
+            const double av = lb.A[a_base(lb, c, j) + n];
+            const double zv = lb.Z[(size_t)c * lb.ldz + n];
+            const double4 par = sc.chain[set];
+            const double t1 = fma(par.y, zv, par.x), t2 = fma(par.w, zv, par.z);
+            const int side = t1 <= t2 ? 0 : 1;
+            const double ex = av - (side == 0 ? t1 : t2);
+            if (ex > 0.0) atomicMax(&s_far[2 * ((j - j_lo) * PROBE_G + g) + side], pack_excess(ex, n));
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * PROBE_G * SB; e += blockDim.x) {
+    const unsigned long long key = s_far[e];
+    if (key) {
+      const int setl = e >> 1;
+      const int j = j_lo + setl / PROBE_G, g = setl % PROBE_G;
+      atomicMax(&sc.far[((size_t)(c0 + g) * S + j) * 2 + (e & 1)], key);
+    }
+  }
+}
+
+constexpr int TF_THREADS = 256;
+constexpr int TF_POOL = 128;  // parked (line, scalarisation) entries per warp
+
+// write out this warp's parked lines of row c after the exact (fp64) re-test against the second-level chain
+__device__ __forceinline__ void tf_flush(const LineBatch& lb, const EmaxScratch& sc, const int2* pool, int cnt, int c) {
+  __syncwarp();
+  const int S = lb.S;
+  for (int e = threadIdx.x & 31; e < cnt; e += 32) {
+    const int2 it = pool[e];
+    const int n = it.x, j = it.y;
+    const size_t set = (size_t)c * S + j;
+    const double av = lb.A[a_base(lb, c, j) + n];
+    const double zv = lb.Z[(size_t)c * lb.ldz + n];
+    const double4 par = sc.chain[set];
+    const double t1 = fma(par.y, zv, par.x), t2 = fma(par.w, zv, par.z);
+    const int side = t1 <= t2 ? 0 : 1;
+    const double4 q = sc.chain5[set * 2 + side];
+    if (!((av > fma(q.y, zv, q.x)) | (av > fma(q.w, zv, q.z)))) continue;
+    const int pos = atomicAdd(&sc.surv_cnt[set], 1);
+    if (pos < SURV_CAP) {
+      SurvEntry en;
+      en.a = av; en.z = zv; en.idx = n; en.pad = 0;
+      sc.surv[set * SURV_CAP + pos] = en;
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(TF_THREADS, 3)
+tilefilter_kernel(LineBatch lb, EmaxScratch sc, int pairs_per_warp, int njb, int use_ztile) {
+  __shared__ int2 s_pool[TF_THREADS / 32][TF_POOL];
+  __shared__ ulonglong2 s_ch[TF_THREADS / 32][16][4];  // per warp, per scalarisation: (m_k, m_k | c_k, c_k) of chord k
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int S = lb.S;
+  const int ntiles = (lb.NA + FILTER_TILE - 1) / FILTER_TILE, ntp = (ntiles + 1) / 2;
+  const int chunks = (ntp + pairs_per_warp - 1) / pairs_per_warp;
+  // work item = (row, scalarisation batch, chunk of tile pairs); chunk fastest so that neighbouring
+  // warps share a row's chain parameters and slope row in L1 / L2
+  const long long item = (long long)blockIdx.x * (TF_THREADS / 32) + warp;
+  if (item >= (long long)lb.C * njb * chunks) return;
+  const int chunk = (int)(item % chunks);
+  const int jb = (int)((item / chunks) % njb);
+  const int c = (int)(item / ((long long)chunks * njb));
+  const int half = lane >> 4, jl = lane & 15;
+  const int j_mine = jb * 16 + jl;
+  const bool j_ok = j_mine < S;
+  // chain of (c, j_mine): slopes m[4], intercepts c[4] of the chords P-U, U-T, T-V, V-Q (float, conservative)
+  float4 mm = make_float4(0.f, 0.f, 0.f, 0.f), cc = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+  if (j_ok) {
+    mm = sc.chain5f[((size_t)c * S + j_mine) * 2 + 0];
+    cc = sc.chain5f[((size_t)c * S + j_mine) * 2 + 1];
+  }
+  if (half == 0) {  // packed copies for the per-line tests (one broadcast LDS.128 per chord)
+    s_ch[warp][jl][0] = make_ulonglong2(pack_f32x2(mm.x, mm.x), pack_f32x2(cc.x, cc.x));
+    s_ch[warp][jl][1] = make_ulonglong2(pack_f32x2(mm.y, mm.y), pack_f32x2(cc.y, cc.y));
+    s_ch[warp][jl][2] = make_ulonglong2(pack_f32x2(mm.z, mm.z), pack_f32x2(cc.z, cc.z));
+    s_ch[warp][jl][3] = make_ulonglong2(pack_f32x2(mm.w, mm.w), pack_f32x2(cc.w, cc.w));
+  }
+  __syncwarp();
+  const double* zrow = lb.Z + (size_t)c * lb.ldz;
+  int2* pool = s_pool[warp];
+  int wcnt = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  const int tp_lo = chunk * pairs_per_warp, tp_hi = min(ntp, tp_lo + pairs_per_warp);
+  // tile statistics of the NEXT pair are requested before this pair is worked on (L2 latency)
+  float2 zr_nx = make_float2(-INFINITY, INFINITY);  // (no tile statistics: nothing can be culled)
+  float am_nx = INFINITY;
+  {
+    const int tile = 2 * tp_lo + half;
+    if (j_ok && tile < ntiles) {
+      if (use_ztile) zr_nx = sc.ztile[(size_t)c * sc.ztiles + tile];
+      am_nx = lb.A32tmax[(size_t)tile * S + j_mine];
+    }
+  }
+  for (int tp = tp_lo; tp < tp_hi; ++tp) {
+    const int tile = 2 * tp + half;
+    const float2 zr = zr_nx;
+    const float am = am_nx;
+    {
+      const int tn = tile + 2;
+      if (tp + 1 < tp_hi && j_ok && tn < ntiles) {
+        if (use_ztile) zr_nx = sc.ztile[(size_t)c * sc.ztiles + tn];
+        am_nx = lb.A32tmax[(size_t)tn * S + j_mine];
+      }
+    }
+    bool culled = true;
+    if (j_ok && tile < ntiles) {
+      const float lo = zr.x, hi = zr.y;
+      culled = (am <= fminf(fmaf(mm.x, lo, cc.x), fmaf(mm.x, hi, cc.x))) & (am <= fminf(fmaf(mm.y, lo, cc.y), fmaf(mm.y, hi, cc.y))) &
+               (am <= fminf(fmaf(mm.z, lo, cc.z), fmaf(mm.z, hi, cc.z))) & (am <= fminf(fmaf(mm.w, lo, cc.w), fmaf(mm.w, hi, cc.w)));
+    }
+    const unsigned live = ~__ballot_sync(0xffffffffu, culled);  // bit (half * 16 + jl): this (tile, set) pair needs the lines
+    if (live == 0u) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      unsigned bits = (live >> (16 * h)) & 0xffffu;
+      if (bits == 0u) continue;
+      const int t = 2 * tp + h;
+      const int n0 = t * FILTER_TILE + lane * 4;  // 4 consecutive lines per lane
+      u64 z01 = 0ull, z23 = 0ull;
+      const bool in = n0 < lb.NA;  // lines past NA carry -inf in the float intercept table: never kept
+      if (in) {
+        const double2 v0 = *reinterpret_cast<const double2*>(zrow + n0);
+        const double2 v1 = *reinterpret_cast<const double2*>(zrow + n0 + 2);
+        z01 = pack_f32x2(__double2float_rn(v0.x), __double2float_rn(v0.y));
+        z23 = pack_f32x2(__double2float_rn(v1.x), __double2float_rn(v1.y));
+      }
+      // (lanes past the last line read line 0 of the tile and are masked out below: no predicate on the loads)
+      const float* arow = lb.A32 + (size_t)jb * 16 * lb.a_sj + (in ? n0 : t * FILTER_TILE);
+      const unsigned inmask = in ? 0xfu : 0u;
+      const ulonglong2* chw = &s_ch[warp][0][0];
+      const size_t a_sj = (size_t)lb.a_sj;
+      float4 a_nx = *reinterpret_cast<const float4*>(arow + (size_t)(__ffs(bits) - 1) * a_sj);
+      while (bits) {
+        const int jj = __ffs(bits) - 1;
+        bits &= bits - 1u;
+        const int j = jb * 16 + jj;
+        const float4 a = a_nx;
+        if (bits) a_nx = *reinterpret_cast<const float4*>(arow + (size_t)(__ffs(bits) - 1) * a_sj);
+        const ulonglong2 q0 = chw[jj * 4 + 0], q1 = chw[jj * 4 + 1], q2 = chw[jj * 4 + 2], q3 = chw[jj * 4 + 3];
+        unsigned mask = 0u;
+        // a line is kept iff a > fma(m_k, z, c_k) for one of the four chords: two pairs of chords per
+        // pair of lines, each as in filter32_kernel (one packed FFMA2 per chord)
+        mask = pair_test32<1u>(mask, q0.x, q0.y, q1.x, q1.y, z01, a.x, a.y);
+        mask = pair_test32<4u>(mask, q0.x, q0.y, q1.x, q1.y, z23, a.z, a.w);
+        unsigned mask2 = 0u;
+        mask2 = pair_test32<1u>(mask2, q2.x, q2.y, q3.x, q3.y, z01, a.x, a.y);
+        mask2 = pair_test32<4u>(mask2, q2.x, q2.y, q3.x, q3.y, z23, a.z, a.w);
+        mask = (mask | mask2) & inmask;
+        for (;;) {  // survivors are rare
+          const unsigned vote = __ballot_sync(0xffffffffu, mask != 0u);
+          if (vote == 0u) break;
+          if (wcnt + 32 > TF_POOL) {
+            tf_flush(lb, sc, pool, wcnt, c);
+            wcnt = 0;
+          }
+          if (mask) {
+            const int bit = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            pool[wcnt + __popc(vote & lt)] = make_int2(n0 + bit, j);
+          }
+          wcnt += __popc(vote);
+        }
+      }
+    }
+  }
+  tf_flush(lb, sc, pool, wcnt, c);
+}
+
+static int launch_tilefilter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st, bool ztile_valid) {
+  const long long sets = (long long)lb.C * lb.S;
+  {  // probe: every PROBE_STRIDE-th line against the 3-point chain -> farthest line above each chord
+    const int nsamp = ceil_div(lb.NA, PROBE_PERIOD) * PROBE_CHUNK;
+    const int JB = lb.S <= 64 ? lb.S : 32;
+    const size_t smem = (size_t)PROBE_G * JB * (2 * sizeof(float4) + 2 * sizeof(unsigned long long));
+    dim3 grid(ceil_div(nsamp, PROBE_THREADS), ceil_div(lb.C, PROBE_G), ceil_div(lb.S, JB));
+    probe32_kernel<<<grid, PROBE_THREADS, smem, st>>>(lb, sc, JB);
+    DKG_LAUNCH_CHECK();
+  }
+  chain5_kernel<<<(unsigned)((sets + E_THREADS - 1) / E_THREADS), E_THREADS, 0, st>>>(lb, sc);
+  DKG_LAUNCH_CHECK();
+  const int ntiles = ceil_div(lb.NA, FILTER_TILE), ntp = (ntiles + 1) / 2;
+  const int njb = ceil_div(lb.S, 16);
+  // enough warps to fill the machine several times over, but as many tile pairs per warp as that allows
+  // (the chain parameters are loaded once per warp)
+  // (4 pairs per warp measured best at c4: 0.62 ms vs 0.72 at 16 and 1.08 at 64 -- short items balance the
+  // very uneven work per row and keep more loads in flight)
+  long long ppw = (long long)lb.C * njb * ntp / (148ll * 64);
+  if (ppw > 4) ppw = 4;
+  if (const char* e = getenv("DKG_TF_PPW")) ppw = atoi(e);
+  if (ppw < 1) ppw = 1;
+  if (ppw > ntp) ppw = ntp;
+  const int chunks = ceil_div(ntp, (int)ppw);
+  const long long items = (long long)lb.C * njb * chunks;
+  const int wpb = TF_THREADS / 32;
+  tilefilter_kernel<<<(unsigned)((items + wpb - 1) / wpb), TF_THREADS, 0, st>>>(lb, sc, (int)ppw, njb, ztile_valid ? 1 : 0);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
 }
 
 // blk_first / blk_step / blk_skip map blockIdx.x to a line block: phase 1 visits blocks
@@ -932,8 +1228,17 @@ static int launch_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_
   return DKG_OK;
 }
 
-int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st) {
+int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st, bool ztile_valid) {
   if (lb.C == 0 || lb.NA == 0) return DKG_OK;
+  {
+    // KG path on a large discretisation: the tile-first filter (DKG_FILTER=f64 / f32 / line32 select the older kernels)
+    const char* fe0 = getenv("DKG_FILTER");
+    if (fe0 == nullptr && ztile_valid && lb.A32 != nullptr && lb.A32tmax != nullptr && sc.chain32 != nullptr &&
+        sc.chain5 != nullptr && sc.chain5f != nullptr && sc.chainv != nullptr && lb.a_sc == 0 && lb.row_mod == 0 &&
+        lb.NA >= 8 * FILTER_TILE && (lb.ldz & 1) == 0 && (lb.a_sj & 3) == 0 && lb.ldz >= ((lb.NA + 3) & ~3) &&
+        lb.a_sj >= ((lb.NA + 3) & ~3))
+      return launch_tilefilter(lb, sc, st, ztile_valid);
+  }
   // big batches: 4 lines per thread (fewer parameter loads per test); small ones: more CTAs
   const long long ctas4 = (long long)ceil_div(lb.C, 4) * ceil_div(lb.NA, E_THREADS * 4);
   // KG path with a shared intercept table: the float test (DKG_FILTER=f64 keeps the fp64 kernel)

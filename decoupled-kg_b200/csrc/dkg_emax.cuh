@@ -18,7 +18,7 @@ struct LineBatch {
   int ldz = 0;
   const double* A = nullptr;
   const float* A32 = nullptr;      // optional float copy of A (same strides; shared table only): fp32 chord filter
-  const float* A32tmax = nullptr;  // optional [S, a32_tiles] max of A32 over tiles of FILTER_TILE lines (tile culling)
+  const float* A32tmax = nullptr;  // optional [a32_tiles, S] max of A32 over tiles of FILTER_TILE lines (tile culling)
   int a32_tiles = 0;
   long long a_sc = 0;
   int a_sj = 0;
@@ -53,6 +53,10 @@ struct EmaxScratch {
                                 // built from the sampled phase of the fp32 filter (optional)
   float4* chain32 = nullptr;    // [C, S, 2] the same chain rounded conservatively to float, (m, m, c, c)
                                 // per chord (optional; enables the fp32 filter)
+  float4* chain5f = nullptr;    // [C, S, 2] float image of the second-level chain: (m_PU, m_UT, m_TV, m_VQ),
+                                // (c_PU, c_UT, c_TV, c_VQ) (optional; tile-first filter)
+  float2* ztile = nullptr;      // [C, ztiles] (min, max) of the float-rounded slopes of every FILTER_TILE
+  int ztiles = 0;               // consecutive lines, written by the row-statistics pass (optional)
   int* surv_cnt = nullptr;      // [C, S]  lines that passed the filter (may exceed SURV_CAP)
   SurvEntry* surv = nullptr;    // [C, S, SURV_CAP]
   unsigned long long* far = nullptr;  // [C, S, 2] farthest late survivor above the left / right
@@ -155,11 +159,12 @@ struct CovFinish {
   double outputscale, ystd2;
 };
 int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int* aarg_out,
-               cudaStream_t st, const CovFinish* fin = nullptr);
+               cudaStream_t st, const CovFinish* fin = nullptr, bool* ztile_written = nullptr);
 // row statistics from per-tile partials (sc.zpv / sc.zpi filled by the producer of the slope rows),
 // then the chord chains: replaces emax_zstat when the producer already saw every slope
 int emax_zstat_from_partials(const LineBatch& lb, const EmaxScratch& sc, int ntiles, cudaStream_t st);
-int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st);
+// ztile_valid: sc.ztile holds the per-tile slope ranges of this batch (written by emax_zstat)
+int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st, bool ztile_valid = false);
 // warp-per-set exact hull + closed-form expectation; sets it cannot finish go to the queue
 int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cudaStream_t st);
 // CTA-per-set cooperative path for the queued sets (any input; always terminates)

@@ -66,6 +66,9 @@ struct Workspace {
   void* chainv = nullptr;   // [chunk_C, S, 2] double4 end points of the two chords (second-level chain)
   void* chain5 = nullptr;   // [chunk_C, S, 2] double4 second-level chain
   void* chain32 = nullptr;  // [chunk_C, S, 2] float4: the chain rounded conservatively for the fp32 filter
+  void* chain5f = nullptr;  // [chunk_C, S, 2] float4: float image of the second-level chain (tile-first filter)
+  void* ztile = nullptr;    // [chunk_C, ztiles] float2: per-tile (min, max) of the float-rounded slope row
+  int ztiles = 0;
   int* surv_cnt = nullptr;  // [chunk_C, S]      chord-filter survivors per (candidate, scal.)
   void* surv = nullptr;     // [chunk_C, S, SURV_CAP] SurvEntry (intercept, slope, index)
   unsigned long long* far = nullptr;  // [chunk_C, S, 2] farthest late survivors (chain seeds)
@@ -122,7 +125,7 @@ struct dkg_plan {
   double* mu_disc = nullptr;  // [N, M]
   double* A0 = nullptr;       // [S, N_pad]   scalarised intercepts of the discretisation lines
   float* A0f = nullptr;       // [S, N_pad]   float copy of A0 (fp32 chord filter; padding = -inf)
-  float* A0tmax = nullptr;    // [S, a0_tiles] max of A0f over tiles of FILTER_TILE consecutive lines (tile culling)
+  float* A0tmax = nullptr;    // [a0_tiles, S] max of A0f over tiles of FILTER_TILE consecutive lines (tile culling)
   int a0_tiles = 0;
   // Internal line order: the discretisation is re-ordered along a Morton curve at plan time, so that
   // FILTER_TILE consecutive lines are neighbours in input space -- similar posterior means and similar

@@ -339,7 +339,7 @@ __global__ void a0max_kernel(const double* __restrict__ A0, int N, int ld, doubl
   }
 }
 
-// A0tmax[j, t] = max of the float intercepts of scalarisation j over the lines [t * tile, (t + 1) * tile):
+// A0tmax[t, j] = max of the float intercepts of scalarisation j over the lines [t * tile, (t + 1) * tile):
 // the fp32 chord filter culls a whole warp tile of lines with one test against it
 __global__ void a0_tilemax_kernel(const float* __restrict__ A0f, int ld, int tile, int ntiles, float* __restrict__ out) {
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), j = blockIdx.y, lane = threadIdx.x & 31;
@@ -347,7 +347,7 @@ __global__ void a0_tilemax_kernel(const float* __restrict__ A0f, int ld, int til
   float m = -INFINITY;
   for (int n = t * tile + lane; n < min((t + 1) * tile, ld); n += 32) m = fmaxf(m, A0f[(size_t)j * ld + n]);
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if (lane == 0) out[(size_t)j * ntiles + t] = m;
+  if (lane == 0) out[(size_t)t * gridDim.y + j] = m;  // [tile][S]: a half-warp of the tile filter reads 16 neighbours
 }
 
 int build_a0_tilemax(const float* A0f, int ld, int S, int tile, int ntiles, float* out, cudaStream_t st) {

@@ -12,7 +12,10 @@ def _eval(P, target, X, mode, xd=None):
     from decoupledbo_b200.modules.acquisition.discretekg import DiscreteKnowledgeGradient
 
     old = os.environ.get("DKG_FILTER")
-    os.environ["DKG_FILTER"] = mode
+    if mode == "tile":  # the default: tile-first filter wherever its preconditions hold
+        os.environ.pop("DKG_FILTER", None)
+    else:
+        os.environ["DKG_FILTER"] = mode
     try:
         acq = DiscreteKnowledgeGradient(P.model, P.x_disc if xd is None else xd, P.weights, target_output_ix=target)
         Xg = X.clone().requires_grad_(True)
@@ -23,7 +26,7 @@ def _eval(P, target, X, mode, xd=None):
         return kg.detach().clone(), g.clone(), st
     finally:
         if old is None:
-            del os.environ["DKG_FILTER"]
+            os.environ.pop("DKG_FILTER", None)
         else:
             os.environ["DKG_FILTER"] = old
 
@@ -41,6 +44,33 @@ def test_c4_bits_equal_and_survivors_superset():
         assert torch.equal(g64, g32)
         # stats[1] = survivors seen by the hull kernel: the float test adds only a few lines
         assert st32[1] <= 1.10 * st64[1] + 4096
+        # default path: Morton-ordered tiles culled against the second-level chain, then the per-line test
+        kgt, gt, stt = _eval(P, target, X, "tile", P.x_disc.to(dev))
+        assert torch.equal(kg64, kgt)
+        assert torch.equal(g64, gt)
+        assert stt[1] <= st64[1]  # the tighter chain can only drop more lines
+        assert stt[3] == st64[3]  # identical hulls
+
+
+@pytest.mark.parametrize("shape", [(1, 30, 5000, 16, 900), (4, 50, 4099, 8, 1100), (8, 40, 2000, 3, 2200), (2, 60, 1030, 20, 4200)],
+                         ids=lambda s: "d%dn%dN%dS%dC%d" % s)
+def test_tile_filter_bits_equal_on_ragged_shapes(shape):
+    """Tile-first filter (needs C * N >= 2^22 for the tiled statistics pass that feeds it) against the fp64
+    per-line filter: N not a multiple of the tile, S below / above 16, d = 1 (hundreds of hull vertices)."""
+    from decoupledbo_b200 import synthetic
+
+    d, n_train, N, S, C = shape
+    P = synthetic.make_problem(
+        "tile", d, n_train, [0.3, 0.5], [1.0, 2.0], [0.05, 0.05], [1e-2, 1e-4],
+        synthetic.sobol(N, d, 5), S, C, seed_train=6, seed_cand=7, seed_w=1)
+    dev = torch.device("cuda")
+    X = P.candidates.to(dev)
+    for target in (0, 1):
+        kg64, g64, st64 = _eval(P, target, X, "f64", P.x_disc.to(dev))
+        kgt, gt, stt = _eval(P, target, X, "tile", P.x_disc.to(dev))
+        assert torch.equal(kg64, kgt)
+        assert torch.equal(g64, gt)
+        assert stt[3] == st64[3]
 
 
 @pytest.mark.parametrize("shape", [(2, 40, 121, 16, 33), (3, 33, 129, 2, 130), (2, 16, 1000, 17, 4), (4, 50, 4099, 8, 64)],

@@ -266,8 +266,10 @@ def main():
     group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (VERSION prints a banner there)
+        # keep stdout to the one JSON line: NCCL's version banner / debug lines go to stderr
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
 
@@ -399,6 +401,9 @@ def main():
         prof = _native.profile_read()
         _native.profile_enable(False)
         ms_g, n_g = prof["gemm_cov"]
+        small_path = n_g == 0  # small discretisations: one fused CTA-per-candidate kernel (timed as "hull")
+        if small_path:
+            ms_g, n_g = prof["hull"]
         o = P.model.models[0]
         N = int(P.x_disc.shape[0])
         # algorithmic flops of the conditioning contraction: 2 * n_train * N per (candidate,
@@ -407,8 +412,19 @@ def main():
         achieved = flops_total / (ms_g * 1e-3) / 1e12
         dgemm_peak = measure_dgemm_peak(dev)
         tot_prof = sum(v[0] for v in prof.values())
-        int8_engine = all(p.stats()[7] == 1 for p in plans)
-        if int8_engine:
+        int8_engine = all(p.stats()[7] == 1 for p in plans) and not small_path
+        if small_path:
+            roofline = {
+                "kernel": "small_kg_kernel (one CTA per candidate: kernel rows, K^-1 k_x, covariance row as fp64 dot "
+                          "products, one warp per scalarisation marching over all lines)",
+                "bound": "tensor", "achieved": achieved, "peak": dgemm_peak, "unit": "TFLOP/s",
+                "frac": achieved / dgemm_peak,
+                "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (burst, best of 5); at this size the path is "
+                               "latency bound by construction (SURVEY 8d), the fraction is reported for completeness",
+                "flops_per_launch": flops_total / max(n_g, 1), "avg_launch_ms": ms_g / max(n_g, 1),
+                "share_of_step": ms_g / tot_prof if tot_prof > 0 else None, "traffic": None,
+            }
+        elif int8_engine:
             # The contraction runs on the int8 tensor cores as 34 exact digit-plane products
             # (7 base-256 digits, 8 diagonals; csrc/dkg_ozaki.cu) of K padded to 32.  Its roofline is
             # the int8 tensor peak; B200's dense i8 rate is twice its bf16 rate, and the bf16 rate

@@ -67,12 +67,22 @@ static void dev_free(T*& p) {
   p = nullptr;
 }
 
+static void drop_graphs(Workspace& w) {
+  for (auto& g : w.graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g = Workspace::GraphSlot();
+  }
+}
+
 static void free_workspace(Workspace& w) {
+  drop_graphs(w);
+  if (w.cap_stream) { cudaStreamDestroy(w.cap_stream); w.cap_stream = nullptr; }
   dev_free(w.X); dev_free(w.kg); dev_free(w.dX); dev_free(w.KX); dev_free(w.T); dev_free(w.R); dev_free(w.T_dig); dev_free(w.T_scale); dev_free(w.var);
   dev_free(w.sd); dev_free(w.zown); dev_free(w.Xs); dev_free(w.a_new); dev_free(w.kg_terms);
   dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.zpv); dev_free(w.zpi); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } { double4* t = (double4*)w.chain; dev_free(t); w.chain = nullptr; } { float4* t = (float4*)w.chain32; dev_free(t); w.chain32 = nullptr; } { double4* t = (double4*)w.chainv; dev_free(t); w.chainv = nullptr; } { double4* t = (double4*)w.chain5; dev_free(t); w.chain5 = nullptr; } { float4* t = (float4*)w.chain5f; dev_free(t); w.chain5f = nullptr; } { float2* t = (float2*)w.ztile; dev_free(t); w.ztile = nullptr; } dev_free(w.far); dev_free(w.ovf_sets); dev_free(w.ovf_count);
   dev_free(w.hull_cnt); dev_free(w.hull_idx); dev_free(w.hull_p); dev_free(w.hull_q);
-  dev_free(w.spill_head); dev_free(w.spill_next); dev_free(w.spill_idx); dev_free(w.spill_p); dev_free(w.spill_q); dev_free(w.spill_used);
+  dev_free(w.spill_head); dev_free(w.spill_next); dev_free(w.spill_idx); dev_free(w.spill_p); dev_free(w.spill_q);
+  w.spill_used = nullptr;  // (part of the stats allocation)
   dev_free(w.amax_is_new); dev_free(w.stats); dev_free(w.sdj); dev_free(w.Zc);
   for (int m = 0; m < MAX_M; ++m) { dev_free(w.KXm[m]); dev_free(w.Tm[m]); dev_free(w.varlat[m]); dev_free(w.COVm[m]); }
   if (w.stats_pinned) { cudaFreeHost(w.stats_pinned); w.stats_pinned = nullptr; }
@@ -83,6 +93,7 @@ static void free_workspace(Workspace& w) {
 }
 
 static int alloc_spill(Workspace& w, long long blocks) {
+  drop_graphs(w);  // captured launches carry the pool's addresses and size
   dev_free(w.spill_next); dev_free(w.spill_idx); dev_free(w.spill_p); dev_free(w.spill_q);
   if (blocks < 1) blocks = 1;
   w.spill_blocks = (int)(blocks > 0x03ffffff ? 0x03ffffff : blocks);
@@ -141,7 +152,10 @@ static int ensure_workspace(dkg_plan* p, int C) {
   {
     int n_max = 1;
     for (int m = 0; m < p->M; ++m)
-      if (coupled || m == p->target) n_max = n_max > p->obj[m].n ? n_max : p->obj[m].n;
+      if (coupled || m == p->target) {
+        const int nc = p->obj[m].cap > p->obj[m].n ? p->obj[m].cap : p->obj[m].n;  // (room for appended points)
+        n_max = n_max > nc ? n_max : nc;
+      }
     DKG_TRY(dev_alloc(&w.T_dig, ozaki_digit_bytes(chunk, n_max, p->cov_digits)));
     DKG_TRY(dev_alloc(&w.T_scale, (size_t)chunk + 128));  // + one row block: the CTA-pair kernel reads 256-row pairs
   }
@@ -197,7 +211,6 @@ static int ensure_workspace(dkg_plan* p, int C) {
     if (const char* e = getenv("DKG_SPILL_BLOCKS")) blocks = atoll(e) >= 0 ? atoll(e) : blocks;
     DKG_TRY(dev_alloc(&w.spill_head, (size_t)chunk * S, false));
     DKG_TRY(alloc_spill(w, blocks));
-    DKG_TRY(dev_alloc(&w.spill_used, (size_t)1));
     DKG_CUDA_OK(cudaHostAlloc((void**)&w.stats_pinned, sizeof(long long) * 8, cudaHostAllocDefault));
     memset(w.stats_pinned, 0, sizeof(long long) * 8);
     DKG_CUDA_OK(cudaEventCreateWithFlags(&w.stats_ev, cudaEventDisableTiming));
@@ -205,7 +218,8 @@ static int ensure_workspace(dkg_plan* p, int C) {
     w.spill_checked = false;
   }
   DKG_TRY(dev_alloc(&w.amax_is_new, (size_t)chunk * S));
-  DKG_TRY(dev_alloc(&w.stats, (size_t)8));
+  DKG_TRY(dev_alloc(&w.stats, (size_t)STATS_WORDS));  // 8 counters + the spill pool's fill count (one memset clears all)
+  w.spill_used = reinterpret_cast<int*>(w.stats + 8);
   w.cap_C = cap;
   w.chunk_C = chunk;
   return DKG_OK;
@@ -216,7 +230,7 @@ static void destroy_plan(dkg_plan* p) {
   cudaDeviceSynchronize();
   for (int m = 0; m < p->M; ++m) {
     ObjState& o = p->obj[m];
-    dev_free(o.xs); dev_free(o.alpha); dev_free(o.chol); dev_free(o.Kinv); dev_free(o.Kmat); dev_free(o.Kxd_dig); dev_free(o.Kxd_scale); dev_free(o.B); dev_free(o.Kxd);
+    dev_free(o.xs); dev_free(o.alpha); dev_free(o.resid); dev_free(o.chol); dev_free(o.Kinv); dev_free(o.Kmat); dev_free(o.Kxd_dig); dev_free(o.Kxd_scale); dev_free(o.B); dev_free(o.Kxd);
     dev_free(o.BT); dev_free(o.xd_s);
   }
   dev_free(p->W); dev_free(p->wt); dev_free(p->xd); dev_free(p->alpha_all);
@@ -243,8 +257,10 @@ static int make_kxd_digits(ObjState& o, const dkg_plan* p, cudaStream_t st) {
   double* KT = nullptr;
   DKG_TRY(dev_alloc(&KT, (size_t)p->N * o.n_pad, false));
   int rc = transpose(o.Kxd, o.n, p->N, p->N_pad, KT, o.n_pad, st);
-  if (rc == DKG_OK) rc = dev_alloc(&o.Kxd_dig, ozaki_digit_bytes(p->N_pad, o.n, p->cov_digits));
-  if (rc == DKG_OK) rc = dev_alloc(&o.Kxd_scale, (size_t)p->N_pad);
+  // (sized for the objective's row capacity, so that an appended training point only needs a re-slice)
+  const int k_cap = o.cap > o.n ? (o.cap < OZ_MAX_K ? o.cap : OZ_MAX_K) : o.n;
+  if (rc == DKG_OK && o.Kxd_dig == nullptr) rc = dev_alloc(&o.Kxd_dig, ozaki_digit_bytes(p->N_pad, k_cap, p->cov_digits));
+  if (rc == DKG_OK && o.Kxd_scale == nullptr) rc = dev_alloc(&o.Kxd_scale, (size_t)p->N_pad);
   if (rc == DKG_OK)
     rc = ozaki_slice_rows(KT, o.n_pad, p->N, o.n, ozaki_b_block_rows(p->cov_digits, p->cov_diagonals), p->cov_digits,
                           o.Kxd_dig, o.Kxd_scale, st);
@@ -348,7 +364,11 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
   DKG_TRY(dev_alloc(&Lbuf, (size_t)n_max * n_max));
   DKG_TRY(dev_alloc(&LTbuf, (size_t)n_max * n_max));
   DKG_TRY(dev_alloc(&info_dev, 1));
-  DKG_TRY(dev_alloc(&p->alpha_all, (size_t)n_sum));
+  {
+    int cap_sum = 0;
+    for (int m = 0; m < M; ++m) cap_sum += round_up(objs[m].n, GEMM_BM);
+    DKG_TRY(dev_alloc(&p->alpha_all, (size_t)(cap_sum > n_sum ? cap_sum : n_sum)));
+  }
   DKG_TRY(dev_alloc(&p->mu_disc, (size_t)N * M));
   DKG_TRY(dev_alloc(&p->xd, (size_t)N * d));
   DKG_TRY(order_discretisation(p, x_disc_dev, st));
@@ -367,13 +387,17 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
     o.y_mean = s.y_mean;
     o.y_std = s.y_std;
     for (int k = 0; k < MAX_D; ++k) o.ls[k] = k < d ? s.lengthscale_host[k] : 1.0;
-    if ((rc = dev_alloc(&o.xs, (size_t)o.n * d)) != DKG_OK) break;
-    if ((rc = dev_alloc(&o.alpha, (size_t)o.n_pad)) != DKG_OK) break;
+    const bool fast = o.n <= chol_fast_max() && getenv("DKG_SLOW_PREPARE") == nullptr;
+    o.cap = fast ? round_up(o.n, GEMM_BM) : o.n_pad;  // the fast path's 128-padded buffers leave room for appends
+    if ((rc = dev_alloc(&o.xs, (size_t)o.cap * d)) != DKG_OK) break;
+    if ((rc = dev_alloc(&o.alpha, (size_t)o.cap)) != DKG_OK) break;
+    if ((rc = dev_alloc(&o.resid, (size_t)o.cap)) != DKG_OK) break;
     if ((rc = scale_rows(s.train_x_dev, o.n, d, o.ls, o.xs, st)) != DKG_OK) break;
+    if ((rc = residual(s.train_y_dev, o.n, o.mean_const, o.resid, st)) != DKG_OK) break;
     const bool need_state = (m == tgt || tgt < 0);
     const int n = o.n;
     double jit = 0.0;
-    if (n <= chol_fast_max() && getenv("DKG_SLOW_PREPARE") == nullptr) {
+    if (fast) {
       // ---- fast path: blocked Cholesky, explicit L^-1, solves as DMMA GEMMs ----
       if ((rc = factor_objective(o, d, Lbuf, info_dev, &jit, st, /*blocked=*/true)) != DKG_OK) break;
       o.refine = needs_refinement(o, jit);
@@ -392,15 +416,20 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
       cudaMemcpyAsync(p->alpha_all + off, o.alpha, sizeof(double) * n, cudaMemcpyDeviceToDevice, st);
       off += n;
       if ((rc = mu_disc(p->xd, N, d, o, p->mu_disc, M, m, st)) != DKG_OK) { cleanup(); break; }
-      if (need_state) {
+      o.jitter = jit;
+      {
+        // K and K^-1 of EVERY objective are kept (n^2 doubles each): the mean cache of any objective can
+        // then be refreshed in O(n^2) when a training point is appended (dkg_plan_append_point)
         o.ldk = np;
-        if ((rc = dev_alloc(&o.chol, (size_t)n * n)) != DKG_OK) { cleanup(); break; }
-        cudaMemcpyAsync(o.chol, Lbuf, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st);
         // Kinv = L^-T L^-1
         if ((rc = dev_alloc(&o.Kinv, (size_t)np * o.ldk)) != DKG_OK) { cleanup(); break; }
         if ((rc = gemm_store(LinvT, np, Linv, np, np, o.ldk, o.n_pad, o.Kinv, o.ldk, st)) != DKG_OK) { cleanup(); break; }
         if ((rc = dev_alloc(&o.Kmat, (size_t)np * o.ldk)) != DKG_OK) { cleanup(); break; }
         if ((rc = kmat_train(o, d, jit, o.Kmat, o.ldk, st)) != DKG_OK) { cleanup(); break; }
+      }
+      if (need_state) {
+        if ((rc = dev_alloc(&o.chol, (size_t)n * n)) != DKG_OK) { cleanup(); break; }
+        cudaMemcpyAsync(o.chol, Lbuf, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st);
         // B = K^-1 k(X_train, X_disc) = L^-T (L^-1 Kxd)
         if ((rc = dev_alloc(&o.xd_s, (size_t)p->N_pad * d)) != DKG_OK) { cleanup(); break; }
         if ((rc = scale_rows(p->xd, N, d, o.ls, o.xd_s, st)) != DKG_OK) { cleanup(); break; }
@@ -414,8 +443,9 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
         // one refinement step (see solve_T): R = Kxd - K B;  B += Kinv R
         if ((rc = gemm_axpy(o.Kmat, o.ldk, o.B, p->N_pad, np, p->N_pad, o.n_pad, o.Kxd, p->N_pad, -1.0, Ybuf, p->N_pad, st)) != DKG_OK) { cleanup(); break; }
         if ((rc = gemm_axpy(o.Kinv, o.ldk, Ybuf, p->N_pad, np, p->N_pad, o.n_pad, o.B, p->N_pad, 1.0, o.B, p->N_pad, st)) != DKG_OK) { cleanup(); break; }
-        if ((rc = dev_alloc(&o.BT, (size_t)N * o.n_pad)) != DKG_OK) { cleanup(); break; }
-        if ((rc = transpose(o.B, o.n_pad, N, p->N_pad, o.BT, o.n_pad, st)) != DKG_OK) { cleanup(); break; }
+        o.ldbt = np;
+        if ((rc = dev_alloc(&o.BT, (size_t)N * o.ldbt)) != DKG_OK) { cleanup(); break; }
+        if ((rc = transpose(o.B, o.n_pad, N, p->N_pad, o.BT, o.ldbt, st)) != DKG_OK) { cleanup(); break; }
       }
       cleanup();
     } else {
@@ -445,8 +475,9 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
         if ((rc = make_kxd_digits(o, p, st)) != DKG_OK) break;
         cudaMemcpyAsync(o.B, o.Kxd, sizeof(double) * (size_t)o.n_pad * p->N_pad, cudaMemcpyDeviceToDevice, st);
         if ((rc = cholesky_solve_inplace(Lbuf, LTbuf, n, o.B, N, p->N_pad, st)) != DKG_OK) break;
-        if ((rc = dev_alloc(&o.BT, (size_t)N * o.n_pad)) != DKG_OK) break;
-        if ((rc = transpose(o.B, o.n_pad, N, p->N_pad, o.BT, o.n_pad, st)) != DKG_OK) break;
+        o.ldbt = o.n_pad;
+        if ((rc = dev_alloc(&o.BT, (size_t)N * o.ldbt)) != DKG_OK) break;
+        if ((rc = transpose(o.B, o.n_pad, N, p->N_pad, o.BT, o.ldbt, st)) != DKG_OK) break;
       }
     }
     if (need_state) p->jitter = jit > p->jitter ? jit : p->jitter;
@@ -514,7 +545,7 @@ static int t_solve_mode() {
 static int solve_T(const ObjState& o, const double* KX, double* T, double* R, int C, int C_pad,
                    cudaStream_t st) {
   const int mode = t_solve_mode();
-  if (mode == 1 && o.n <= batched_solve_max_n())
+  if (mode == 1 && o.chol != nullptr && o.n <= batched_solve_max_n())
     return launch_batched_cholesky_solve(o.chol, o.n, KX, o.ldk, C, T, o.ldk, st);
   DKG_TRY(gemm_store(KX, o.ldk, o.Kinv, o.ldk, C_pad, o.ldk, o.n_pad, T, o.ldk, st));
   if (mode == 2 || (!o.refine && mode != 3)) return DKG_OK;
@@ -527,6 +558,86 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
 
 static int forward_once(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st);
 static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st);
+
+// ---- CUDA graphs for small batches -------------------------------------------------------------
+static bool graphs_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DKG_GRAPHS");
+    v = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+
+static bool graph_eligible(const dkg_plan* p, int C) {
+  // launch-bound sizes only: a few hundred microseconds of kernels at most
+  return graphs_enabled() && !g_prof_on && C <= p->ws.chunk_C && (long long)C * p->N <= (1ll << 21);
+}
+
+// Replays (capturing at first use) the launch sequence of one forward over the staging buffers
+// w.X -> w.kg, w.dX.  Returns DKG_OK with *done = false when capture is not possible (the caller
+// then launches the kernels directly).
+static int forward_graph(dkg_plan* p, int C, bool grad, cudaStream_t st, bool* done) {
+  Workspace& w = p->ws;
+  *done = false;
+  Workspace::GraphSlot* slot = nullptr;
+  for (auto& g : w.graphs)
+    if (g.exec != nullptr && g.C == C && g.grad == (grad ? 1 : 0)) slot = &g;
+  if (slot == nullptr) {
+    if (w.cap_stream == nullptr) DKG_CUDA_OK(cudaStreamCreateWithFlags(&w.cap_stream, cudaStreamNonBlocking));
+    // everything the kernels of this forward were given before must have been consumed: the capture
+    // itself runs nothing, but first-use attribute calls inside it are not stream ordered
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(w.cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      return DKG_OK;
+    }
+    const int rc = forward_once(p, w.X, C, w.kg, grad ? w.dX : nullptr, w.cap_stream);
+    const cudaError_t ce = cudaStreamEndCapture(w.cap_stream, &graph);
+    if (rc != DKG_OK || ce != cudaSuccess || graph == nullptr) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      return rc != DKG_OK ? rc : DKG_OK;
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess || exec == nullptr) {
+      cudaGetLastError();
+      return DKG_OK;
+    }
+    slot = &w.graphs[0];
+    for (auto& g : w.graphs)
+      if (g.exec == nullptr) { slot = &g; break; }
+      else if (g.used < slot->used) slot = &g;
+    if (slot->exec) cudaGraphExecDestroy(slot->exec);
+    slot->C = C; slot->grad = grad ? 1 : 0; slot->exec = exec;
+  }
+  slot->used = ++w.graph_clock;
+  w.last_C = C;
+  DKG_CUDA_OK(cudaGraphLaunch(slot->exec, st));
+  count_launch();
+  *done = true;
+  return DKG_OK;
+}
+
+// one forward on device buffers: through a graph over the staging buffers when the batch is small
+static int enqueue_forward(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st) {
+  Workspace& w = p->ws;
+  if (graph_eligible(p, C)) {
+    const size_t xb = sizeof(double) * (size_t)C * p->d;
+    if (X != w.X) DKG_CUDA_OK(cudaMemcpyAsync(w.X, X, xb, cudaMemcpyDeviceToDevice, st));
+    bool done = false;
+    DKG_TRY(forward_graph(p, C, dX != nullptr, st, &done));
+    if (done) {
+      if (kg != w.kg) DKG_CUDA_OK(cudaMemcpyAsync(kg, w.kg, sizeof(double) * (size_t)C, cudaMemcpyDeviceToDevice, st));
+      if (dX != nullptr && dX != w.dX) DKG_CUDA_OK(cudaMemcpyAsync(dX, w.dX, xb, cudaMemcpyDeviceToDevice, st));
+      return DKG_OK;
+    }
+    return forward_once(p, X != w.X ? w.X : X, C, kg, dX, st);
+  }
+  return forward_once(p, X, C, kg, dX, st);
+}
 
 // outcome of an EARLIER forward (copied asynchronously, looked at without a sync): grow the pool if
 // that forward dropped records
@@ -549,7 +660,7 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
   DKG_TRY(ensure_workspace(p, C));
   Workspace& w = p->ws;
   for (int attempt = 0;; ++attempt) {
-    DKG_TRY(forward_once(p, X, C, kg, dX, st));
+    DKG_TRY(enqueue_forward(p, X, C, kg, dX, st));
     if (dX == nullptr) return DKG_OK;
     DKG_CUDA_OK(cudaMemcpyAsync(w.stats_pinned, w.stats, sizeof(long long) * 8, cudaMemcpyDeviceToHost, st));
     if (w.spill_checked) {
@@ -565,14 +676,85 @@ static int forward_impl(dkg_plan* p, const double* X, int C, double* kg, double*
   }
 }
 
+// Small discretisations (SmallArgs in dkg_emax.cuh): one CTA per candidate does the whole forward,
+// then the usual finalize kernel -- two launches instead of ~17.  The rule depends on the PLAN only,
+// so a sub-batch and the full batch of the same plan always take the same path (identical bits).
+static bool small_path(const dkg_plan* p) {
+  const char* e = getenv("DKG_SMALL");  // (read per forward so that tests can compare the two paths)
+  if ((e != nullptr && atoi(e) == 0) || p->target < 0 || p->N + 1 > SMALL_MAX_LINES) return false;
+  if (p->cov_digits != OZ_DEFAULT_DIGITS) return false;  // DKG_PLAN_FAST32 asks for the reduced-precision contraction
+  for (int m = 0; m < p->M; ++m)
+    if (p->obj[m].n > SMALL_MAX_TRAIN) return false;
+  return p->obj[p->target].Kxd != nullptr;
+}
+
+static int forward_small(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st) {
+  Workspace& w = p->ws;
+  const ObjState& ot = p->obj[p->target];
+  const int d = p->d, N = p->N, S = p->S, M = p->M;
+  w.last_C = C;
+  DKG_CUDA_OK(cudaMemsetAsync(w.stats, 0, sizeof(long long) * STATS_WORDS, st));
+  for (int c0 = 0; c0 < C; c0 += w.chunk_C) {
+    const int cc = (C - c0) < w.chunk_C ? (C - c0) : w.chunk_C;
+    SmallArgs a;
+    a.X = X + (size_t)c0 * d; a.C = cc; a.d = d; a.M = M; a.target = p->target;
+    for (int m = 0; m < M; ++m) {
+      const ObjState& o = p->obj[m];
+      a.xs[m] = o.xs; a.alpha[m] = o.alpha; a.ntr[m] = o.n; a.kind[m] = o.kernel;
+      a.outputscale[m] = o.outputscale; a.mean_const[m] = o.mean_const; a.y_mean[m] = o.y_mean; a.y_std[m] = o.y_std;
+      for (int k = 0; k < MAX_D; ++k) a.ls[m][k] = o.ls[k];
+    }
+    a.W = p->W; a.Kinv = ot.Kinv; a.Kmat = ot.Kmat; a.ldk = ot.ldk; a.refine = ot.refine ? 1 : 0;
+    a.Kxd = ot.Kxd; a.ldx = p->N_pad; a.xd_s = p->xd_s; a.noise = ot.noise;
+    a.a_new = w.a_new + (size_t)c0 * S; a.T = w.T + (size_t)c0 * p->ldk; a.var = w.var + c0; a.sd = w.sd + c0;
+    LineBatch lb;
+    lb.Z = w.Z; lb.ldz = p->ldz;
+    lb.A = p->A0; lb.a_sc = 0; lb.a_sj = p->N_pad;
+    lb.a_own = a.a_new;
+    lb.wt = p->wt;
+    lb.Amax = p->A0max; lb.Aarg = p->A0arg; lb.am_sc = 0;
+    lb.NA = N; lb.NL = N + 1; lb.S = S; lb.C = cc;
+    EmaxScratch sc;
+    sc.stats = w.stats; sc.spill_used = w.spill_used;
+    EmaxOut out;
+    out.terms = w.kg_terms + (size_t)c0 * S;
+    out.subtract_max = 1;
+    out.hull_cnt = w.hull_cnt;
+    out.hull_cap = HULL_CAP;
+    out.amax_is_own = w.amax_is_new;
+    out.kg = kg + c0;
+    out.truncated = w.stats + 6;
+    BackwardArgs bw{};
+    if (dX != nullptr) {
+      out.hull_idx = w.hull_idx; out.hull_p = w.hull_p; out.hull_q = w.hull_q;
+      out.spill_head = w.spill_head; out.spill_next = w.spill_next; out.spill_idx = w.spill_idx;
+      out.spill_p = w.spill_p; out.spill_q = w.spill_q; out.spill_used = w.spill_used;
+      out.spill_blocks = w.spill_blocks;
+      if (c0 > 0) DKG_CUDA_OK(cudaMemsetAsync(w.spill_used, 0, sizeof(int), st));  // the pool is per chunk
+      bw.dX = dX + (size_t)c0 * d; bw.X = a.X; bw.T = a.T; bw.ldk = p->ldk; bw.BT = p->BT; bw.n_pad = ot.n_pad; bw.ldbt = ot.ldbt;
+      bw.xd_s = p->xd_s; bw.var = a.var; bw.sd = a.sd; bw.W = p->W; bw.M = M; bw.d = d; bw.target = p->target;
+      for (int m = 0; m < M; ++m) {
+        const ObjState& o = p->obj[m];
+        bw.xs[m] = o.xs; bw.alpha[m] = o.alpha; bw.ntr[m] = o.n; bw.kind[m] = o.kernel;
+        bw.outputscale[m] = o.outputscale; bw.y_std[m] = o.y_std;
+        for (int k = 0; k < MAX_D; ++k) bw.ls[m][k] = o.ls[k];
+      }
+    }
+    { ProfScope ps(7, st); DKG_TRY(emax_small_forward(a, lb, sc, out, st)); }
+    { ProfScope ps(9, st); DKG_TRY(emax_finalize(lb, out, bw, st)); }
+  }
+  return DKG_OK;
+}
+
 static int forward_once(dkg_plan* p, const double* X, int C, double* kg, double* dX, cudaStream_t st) {
   if (p->target < 0) return forward_coupled(p, X, C, kg, dX, st);
+  if (small_path(p)) return forward_small(p, X, C, kg, dX, st);
   Workspace& w = p->ws;
   const ObjState& ot = p->obj[p->target];
   const int d = p->d, N = p->N, S = p->S, M = p->M;
   const int C_pad = round_up(C, GEMM_BM);
   w.last_C = C;
-  DKG_CUDA_OK(cudaMemsetAsync(w.stats, 0, sizeof(long long) * 8, st));
+  DKG_CUDA_OK(cudaMemsetAsync(w.stats, 0, sizeof(long long) * STATS_WORDS, st));
 
   XprepArgs xa{};
   xa.X = X; xa.C = C; xa.d = d; xa.M = M; xa.S = S; xa.target = p->target;
@@ -674,6 +856,7 @@ static int forward_once(dkg_plan* p, const double* X, int C, double* kg, double*
       bw.ldk = p->ldk;
       bw.BT = p->BT;
       bw.n_pad = ot.n_pad;
+      bw.ldbt = ot.ldbt;
       bw.xd_s = p->xd_s;
       bw.var = w.var + c0;
       bw.sd = w.sd + c0;
@@ -699,7 +882,7 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
   const int d = p->d, N = p->N, S = p->S, M = p->M;
   const int C_pad = round_up(C, GEMM_BM);
   w.last_C = C;
-  DKG_CUDA_OK(cudaMemsetAsync(w.stats, 0, sizeof(long long) * 8, st));
+  DKG_CUDA_OK(cudaMemsetAsync(w.stats, 0, sizeof(long long) * STATS_WORDS, st));
   // per objective: k_m(x, X_train), means, T_m = KX_m Kinv_m, latent variance
   for (int m = 0; m < M; ++m) {
     const ObjState& o = p->obj[m];
@@ -786,7 +969,7 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
       bw.sdj = w.sdj + (size_t)c0 * S; bw.ldz = p->ldz; bw.M = M; bw.d = d; bw.S = S; bw.N = N;
       for (int m = 0; m < M; ++m) {
         const ObjState& o = p->obj[m];
-        bw.T[m] = w.Tm[m] + (size_t)c0 * o.ldk; bw.ldk[m] = o.ldk; bw.BT[m] = o.BT; bw.n_pad[m] = o.n_pad;
+        bw.T[m] = w.Tm[m] + (size_t)c0 * o.ldk; bw.ldk[m] = o.ldk; bw.BT[m] = o.BT; bw.n_pad[m] = o.n_pad; bw.ldbt[m] = o.ldbt;
         bw.xd_s[m] = o.xd_s; bw.xs[m] = o.xs; bw.alpha[m] = o.alpha; bw.ntr[m] = o.n; bw.kind[m] = o.kernel;
         bw.outputscale[m] = o.outputscale; bw.y_std[m] = o.y_std;
         for (int k = 0; k < MAX_D; ++k) bw.ls[m][k] = o.ls[k];
@@ -860,6 +1043,80 @@ int dkg_plan_create(const dkg_objective* objs, int32_t M, int32_t d, const doubl
 
 void dkg_plan_destroy(dkg_plan* plan) { destroy_plan(plan); }
 
+int dkg_plan_append_point(dkg_plan* plan, int32_t m, const double* x_host, double y, void* stream) {
+  if (!plan || !x_host) { set_error("NULL argument"); return DKG_EINVAL; }
+  if (m < 0 || m >= plan->M) { set_error("objective %d outside [0, %d)", m, plan->M); return DKG_EINVAL; }
+  dkg_plan* p = plan;
+  ObjState& o = p->obj[m];
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = o.n, d = p->d, N = p->N;
+  const bool state = (m == p->target || p->target < 0);
+  if (o.Kinv == nullptr || o.Kmat == nullptr || n + 1 > o.cap || n + 1 > o.ldk || (state && o.Kxd_dig != nullptr && n + 1 > OZ_MAX_K)) {
+    set_error("no room for another training point of objective %d (n = %d, capacity %d): build a new plan", m, n, o.cap);
+    return DKG_ECAPACITY;
+  }
+  DKG_CUDA_OK(cudaStreamSynchronize(st));  // nothing in flight may still read the tables that change
+  double xq[MAX_D];
+  for (int k = 0; k < d; ++k) xq[k] = x_host[k] / o.ls[k];
+  double *scr = nullptr;  // [kv | v | tmp | scal(4)] + [rrow | w] for a state objective
+  const size_t nv = (size_t)round_up(n + 1, 16);
+  DKG_TRY(dev_alloc(&scr, 3 * nv + 4 + (state ? 2 * (size_t)p->N_pad : 0)));
+  double *kv = scr, *v = scr + nv, *tmp = scr + 2 * nv, *scal = scr + 3 * nv, *rrow = scal + 4, *wv = rrow + p->N_pad;
+  int rc = DKG_OK;
+  auto A = [&](int r) { if (rc == DKG_OK) rc = r; };
+  // the new row of the scaled inputs is written first: nothing reads beyond row n - 1 until n grows
+  if (cudaMemcpyAsync(o.xs + (size_t)n * d, xq, sizeof(double) * d, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = DKG_ECUDA;
+  if (rc == DKG_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = DKG_ECUDA;  // xq is a stack buffer
+  const double* xq_dev = o.xs + (size_t)n * d;
+  const double kappa = o.outputscale + o.noise + o.jitter;  // k(x, x) of a stationary kernel + noise
+  A(kernel_row(xq_dev, o.xs, n, d, o.kernel, o.outputscale, kv, st));
+  // v = K^-1 k with one refinement step (as solve_T)
+  A(matvec_axpy(o.Kinv, o.ldk, n, n, kv, nullptr, 1.0, v, st));
+  A(matvec_axpy(o.Kmat, o.ldk, n, n, v, kv, -1.0, tmp, st));
+  A(matvec_axpy(o.Kinv, o.ldk, n, n, tmp, v, 1.0, v, st));
+  const double yc = y - o.mean_const;
+  A(append_scalars(kv, v, o.alpha, n, kappa, yc, scal, st));
+  double sh[4] = {0, 0, 0, 0};
+  if (rc == DKG_OK) {
+    if (cudaMemcpyAsync(sh, scal, sizeof(double) * 3, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) rc = DKG_ECUDA;
+  }
+  if (rc == DKG_OK && !(sh[0] > 0.0)) {
+    set_error("the covariance extended by the new point is not positive definite (Schur complement %g)", sh[0]);
+    rc = DKG_ENOTPD;
+  }
+  if (rc != DKG_OK) { cudaStreamSynchronize(st); dev_free(scr); return rc; }
+  // ---- from here on the plan changes ----
+  A(append_update_k(o.Kinv, o.Kmat, o.ldk, n, kv, v, scal, kappa, st));
+  A(append_update_alpha(o.alpha, v, scal, n, st));
+  if (rc == DKG_OK && cudaMemcpyAsync(o.resid + n, &yc, sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = DKG_ECUDA;
+  if (rc == DKG_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = DKG_ECUDA;
+  // mean cache: one refinement step on the extended system  alpha += K'^-1 (r - K' alpha)
+  A(matvec_axpy(o.Kmat, o.ldk, n + 1, n + 1, o.alpha, o.resid, -1.0, tmp, st));
+  A(matvec_axpy(o.Kinv, o.ldk, n + 1, n + 1, tmp, o.alpha, 1.0, o.alpha, st));
+  if (state) {
+    A(kernel_row(xq_dev, o.xd_s, N, d, o.kernel, o.outputscale, rrow, st));
+    A(append_w(o.Kxd, p->N_pad, n, N, v, rrow, scal, wv, st));
+    A(append_update_b(o.B, p->N_pad, o.BT, o.ldbt, n, N, v, wv, st));
+  }
+  o.n = n + 1;
+  o.n_pad = round_up(o.n, GEMM_BK);
+  // repeated block updates drift by ~eps cond(K) per step: the forward's refinement step (solve_T) makes
+  // T = K^-1 k_x insensitive to that, so it is switched on for good once a plan has been extended
+  o.refine = true;
+  dev_free(o.chol);  // the Cholesky factor is not maintained (only the DKG_T_SOLVE=trsm experiment reads it)
+  if (state) A(make_kxd_digits(o, p, st));
+  A(mu_disc(p->xd, N, d, o, p->mu_disc, p->M, m, st));
+  A(build_a0(p->mu_disc, N, p->M, p->W, p->S, p->A0, p->A0f, p->N_pad, p->A0max, p->A0arg, st));
+  A(build_a0_tilemax(p->A0f, p->N_pad, p->S, FILTER_TILE, p->a0_tiles, p->A0tmax, st));
+  if (m == p->target) { p->chol = o.chol; }
+  drop_graphs(p->ws);  // captured launches carry n
+  cudaError_t e = cudaStreamSynchronize(st);
+  dev_free(scr);
+  if (rc == DKG_OK && e != cudaSuccess) { set_error("dkg_plan_append_point: %s", cudaGetErrorString(e)); rc = DKG_ECUDA; }
+  return rc;
+}
+
 int dkg_forward_dev(dkg_plan* plan, const double* X_dev, int32_t C, double* kg_dev, double* dX_dev,
                     void* stream) {
   if (!plan || (C > 0 && (!X_dev || !kg_dev))) { set_error("NULL argument"); return DKG_EINVAL; }
@@ -879,7 +1136,7 @@ int dkg_forward_host(dkg_plan* plan, const double* X_host, int32_t C, double* kg
   const int d = plan->d;
   DKG_CUDA_OK(cudaMemcpyAsync(w.X, X_host, sizeof(double) * (size_t)C * d, cudaMemcpyHostToDevice, st));
   for (int attempt = 0;; ++attempt) {
-    DKG_TRY(forward_once(plan, w.X, C, w.kg, dX_host ? w.dX : nullptr, st));
+    DKG_TRY(enqueue_forward(plan, w.X, C, w.kg, dX_host ? w.dX : nullptr, st));
     DKG_CUDA_OK(cudaMemcpyAsync(kg_host, w.kg, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, st));
     if (dX_host) {
       DKG_CUDA_OK(cudaMemcpyAsync(dX_host, w.dX, sizeof(double) * (size_t)C * d, cudaMemcpyDeviceToHost, st));
@@ -893,7 +1150,15 @@ int dkg_forward_host(dkg_plan* plan, const double* X_host, int32_t C, double* kg
     w.stats_pending = false;
     int grew = 0;
     DKG_TRY(grow_spill_if_needed(plan, w.stats_pinned, &grew));
-    if (!grew || attempt >= 3) break;
+    if (!grew || attempt >= 3) {
+      if (w.stats_pinned[6] > 0) {
+        set_error("%lld (candidate, scalarisation) sets have more upper-envelope vertices than the hull-record spill "
+                  "pool holds; their gradient rows are NaN.  Raise or unset DKG_SPILL_BLOCKS (32 vertices per block).",
+                  w.stats_pinned[6]);
+        return DKG_ETRUNC;
+      }
+      break;
+    }
   }
   return DKG_OK;
 }
@@ -1052,7 +1317,15 @@ int64_t dkg_plan_read(dkg_plan* plan, const char* name, double* out_dev, int64_t
   if (nm == "B") { src = plan->B; rows = ot.n; cols = plan->N; ld = plan->N_pad; }
   else if (nm == "Kinv") { src = plan->Kinv; rows = ot.n; cols = ot.n; ld = plan->ldk; }
   else if (nm == "chol") { src = plan->chol; rows = ot.n; cols = ot.n; ld = ot.n; }
-  else if (nm == "alpha") { src = plan->alpha_all; rows = 1; cols = n_sum; ld = n_sum; }
+  else if (nm == "alpha") {
+    int off = 0;  // (gathered at read time: appends change the objectives' lengths)
+    for (int m = 0; m < plan->M; ++m) {
+      if (out_dev) cudaMemcpyAsync(plan->alpha_all + off, plan->obj[m].alpha, sizeof(double) * plan->obj[m].n,
+                                   cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+      off += plan->obj[m].n;
+    }
+    src = plan->alpha_all; rows = 1; cols = n_sum; ld = n_sum;
+  }
   else if (nm == "mu_disc") { src = plan->mu_disc; rows = plan->N; cols = plan->M; ld = plan->M; }
   else if (nm == "A0") { src = plan->A0; rows = plan->S; cols = plan->N; ld = plan->N_pad; }
   else if (nm == "A0max") { src = plan->A0max; rows = 1; cols = plan->S; ld = plan->S; }

@@ -209,7 +209,7 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
         for (int k = 0; k < h; ++k) {
           if (!rd.seek(k)) { s_broken = 1; break; }
           const int idx = rd.idx();
-          if (idx < NA) acc += om * rd.q() * invS * bw.BT[m][(size_t)idx * bw.n_pad[m] + t];
+          if (idx < NA) acc += om * rd.q() * invS * bw.BT[m][(size_t)idx * bw.ldbt[m] + t];
         }
       }
       s_r[t] = acc;

@@ -2108,7 +2108,7 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
     if (merged) {
       for (int u = 0; u < nuniq; ++u) {
         const int idx = s_uidx[u];
-        if (idx < lb.NA) acc += s_ucz[u] * bw.BT[(size_t)idx * bw.n_pad + t];
+        if (idx < lb.NA) acc += s_ucz[u] * bw.BT[(size_t)idx * bw.ldbt + t];
       }
     } else {
       for (int j = 0; j < S; ++j) {
@@ -2121,7 +2121,7 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
           const int idx = rd.idx();
           if (idx < lb.NA) {
             const double cz = wj * rd.q() * invS;
-            acc += cz * bw.BT[(size_t)idx * bw.n_pad + t];
+            acc += cz * bw.BT[(size_t)idx * bw.ldbt + t];
           }
         }
       }
@@ -2263,6 +2263,216 @@ int emax_finalize(const LineBatch& lb, const EmaxOut& out, const BackwardArgs& b
     default: DKG_FINALIZE(8); break;
   }
 #undef DKG_FINALIZE
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// small discretisations: one CTA per candidate (see SmallArgs in dkg_emax.cuh)
+// ------------------------------------------------------------------------------------------
+constexpr int SM_THREADS = 256;
+
+__device__ __forceinline__ double block_sum(double v, double* s_red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) s_red[w] = v;
+  __syncthreads();
+  double tot = 0.0;
+  for (int k = 0; k < SM_THREADS / 32; ++k) tot += s_red[k];  // fixed order: deterministic
+  return tot;
+}
+
+template <int D>
+__global__ void __launch_bounds__(SM_THREADS)
+small_kg_kernel(SmallArgs a, LineBatch lb, EmaxScratch sc, EmaxOut out) {
+  extern __shared__ __align__(16) unsigned char e_smem[];
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int S = lb.S, N = lb.NA, tgt = a.target;
+  const int n = a.ntr[tgt];
+  const int n_al = (n + 1) & ~1;
+  double* zs = reinterpret_cast<double*>(e_smem);  // [NL] slope row
+  double* kx = zs + ((lb.NL + 1) & ~1);            // [n]  k(x, X_train)
+  double* t0 = kx + n_al;                          // [n]
+  double* rr = t0 + n_al;                          // [n]
+  double* tt = rr + n_al;                          // [n]  T
+  double* aw = tt + n_al + (size_t)warp * ((lb.NL + 1) & ~1);  // [NL] this warp's intercept row (march stage)
+  __shared__ double s_red[SM_THREADS / 32], s_mu[MAX_M], s_scal[4];
+  __shared__ double s_zmin[SM_THREADS / 32], s_zmax[SM_THREADS / 32];
+
+  // ---- kernel rows and posterior means of every objective (xprep_kernel) ----
+  for (int m = 0; m < a.M; ++m) {
+    double xm[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) xm[k] = a.X[(size_t)c * D + k] / a.ls[m][k];
+    double acc = 0.0;
+    for (int t = tid; t < a.ntr[m]; t += SM_THREADS) {
+      double sq = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const double df = xm[k] - a.xs[m][(size_t)t * D + k];
+        sq += df * df;
+      }
+      const double kv = stationary_from_sq(a.kind[m], a.outputscale[m], sq);
+      if (m == tgt) kx[t] = kv;
+      acc += kv * a.alpha[m][t];
+    }
+    const double tot = block_sum(acc, s_red);
+    if (tid == 0) s_mu[m] = (a.mean_const[m] + tot) * a.y_std[m] + a.y_mean[m];
+  }
+  __syncthreads();
+  for (int j = tid; j < S; j += SM_THREADS) {  // own-line intercepts (discretekg.py:320, row 0)
+    double v = __dmul_rn(a.W[j * a.M + 0], s_mu[0]);
+    for (int m = 1; m < a.M; ++m) v = __dadd_rn(v, __dmul_rn(a.W[j * a.M + m], s_mu[m]));
+    a.a_new[(size_t)c * S + j] = v;
+  }
+  // ---- T = K^-1 k_x with one refinement step (solve_T): T0 = Kinv kx; R = kx - K T0; T = T0 + Kinv R ----
+  // (thread t walks column t of the symmetric matrices: coalesced across the threads.  A warp-per-row
+  // variant with shuffle reductions measured SLOWER at these sizes: 48 vs 36 us per forward at n = 60)
+  for (int t = tid; t < n; t += SM_THREADS) {
+    double acc = 0.0;
+    for (int s2 = 0; s2 < n; ++s2) acc = fma(kx[s2], a.Kinv[(size_t)s2 * a.ldk + t], acc);
+    t0[t] = acc;
+  }
+  __syncthreads();
+  if (a.refine) {
+    for (int t = tid; t < n; t += SM_THREADS) {
+      double acc = 0.0;
+      for (int s2 = 0; s2 < n; ++s2) acc = fma(t0[s2], a.Kmat[(size_t)s2 * a.ldk + t], acc);
+      rr[t] = kx[t] - acc;
+    }
+    __syncthreads();
+    for (int t = tid; t < n; t += SM_THREADS) {
+      double acc = 0.0;
+      for (int s2 = 0; s2 < n; ++s2) acc = fma(rr[s2], a.Kinv[(size_t)s2 * a.ldk + t], acc);
+      tt[t] = t0[t] + acc;
+    }
+  } else {
+    for (int t = tid; t < n; t += SM_THREADS) tt[t] = t0[t];
+  }
+  __syncthreads();
+  for (int t = tid; t < n; t += SM_THREADS) a.T[(size_t)c * a.ldk + t] = tt[t];
+  // ---- noisy predictive variance and the own line's slope (var_kernel) ----
+  {
+    double acc = 0.0;
+    for (int t = tid; t < n; t += SM_THREADS) acc += kx[t] * tt[t];
+    const double dot = block_sum(acc, s_red);
+    if (tid == 0) {
+      const double ystd2 = a.y_std[tgt] * a.y_std[tgt];
+      const double kxx = stationary_from_sq(a.kind[tgt], a.outputscale[tgt], 0.0);
+      const double var_lat = kxx - dot;
+      const double v = (var_lat + a.noise) * ystd2;
+      const double sdv = sqrt(v);
+      a.var[c] = v;
+      a.sd[c] = sdv;
+      s_scal[0] = ystd2 / sdv;
+      s_scal[1] = (var_lat * ystd2) / sdv;  // znew_coefficients[0] (:313)
+    }
+    __syncthreads();
+  }
+  // ---- covariance row over the predictive sd: z_n = (k(x, x_n) - T . k(X_train, x_n)) ystd^2 / sd ----
+  {
+    const double rsd = s_scal[0];
+    double xt[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) xt[k] = a.X[(size_t)c * D + k] / a.ls[tgt][k];
+    double* zg = const_cast<double*>(lb.Z) + (size_t)c * lb.ldz;
+    double vmin = INFINITY, vmax = -INFINITY;
+    for (int nn = tid; nn < N; nn += SM_THREADS) {
+      double sq = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const double df = xt[k] - a.xd_s[(size_t)nn * D + k];
+        sq = fma(df, df, sq);
+      }
+      double dot = 0.0;
+      for (int t = 0; t < n; ++t) dot = fma(tt[t], a.Kxd[(size_t)t * a.ldx + nn], dot);
+      const double z = (stationary_from_sq(a.kind[tgt], a.outputscale[tgt], sq) - dot) * rsd;
+      zs[nn] = z;
+      zg[nn] = z;
+      vmin = fmin(vmin, z);
+      vmax = fmax(vmax, z);
+    }
+    if (tid == 0) {
+      zs[N] = s_scal[1];
+      zg[N] = s_scal[1];
+      vmin = fmin(vmin, s_scal[1]);
+      vmax = fmax(vmax, s_scal[1]);
+    }
+    vmin = warp_min(vmin);
+    vmax = warp_max(vmax);
+    if (lane == 0) { s_zmin[warp] = vmin; s_zmax[warp] = vmax; }
+    __syncthreads();
+  }
+  double zmin = s_zmin[0], zmax = s_zmax[0];
+  for (int k = 1; k < SM_THREADS / 32; ++k) { zmin = fmin(zmin, s_zmin[k]); zmax = fmax(zmax, s_zmax[k]); }
+
+  // ---- one warp per scalarisation: the reference's march over ALL lines (no filter needed) ----
+  for (int j = warp; j < S; j += SM_THREADS / 32) {
+    const size_t set = (size_t)c * S + j;
+    const double w = lb.wt ? lb.wt[j] : 1.0;
+    SetInfo s;
+    s.w = w;
+    s.zmin = zmin; s.zmax = zmax; s.iP = s.iQ = 0;
+    s.amax = lb.Amax[j];
+    s.iT = lb.Aarg[j];
+    s.own_is_max = 0;
+    const double ao = a.a_new[(size_t)c * S + j];
+    if (ao >= s.amax) { s.amax = ao; s.iT = N; s.own_is_max = 1; }
+    s.shortcut = fabs(__dmul_rn(w, zmin)) < SHORTCUT_TOL && fabs(__dmul_rn(w, zmax)) < SHORTCUT_TOL;
+    if (out.amax_is_own != nullptr && lane == 0) out.amax_is_own[set] = s.own_is_max;
+    Recorder rec{&out, set, lb.NL};
+    if (s.shortcut) {
+      if (lane == 0) {
+        Line L;
+        L.idx = s.iT; L.a = s.amax; L.b = 0; L.ref = 0;
+        rec.single(0, L, 1.0, 0.0, 0.0, true);
+        finish_set(lb, out, set, s, s.amax, 1);
+        if (sc.stats) atomicAdd((unsigned long long*)&sc.stats[4], 1ull);
+      }
+      continue;
+    }
+    // the set's intercepts go to shared memory first: the march re-reads every line once per hull
+    // vertex, and from L2 each of those reads is a dependent ~700-cycle access
+    const double* arow = lb.A + (size_t)j * lb.a_sj;
+    __syncwarp();
+    for (int k = lane; k < N; k += 32) aw[k] = arow[k];
+    if (lane == 0) aw[N] = ao;
+    __syncwarp();
+    auto fetch = [&](int k) -> Line {
+      return make_line(lb, w, aw[k], zs[k], k);
+    };
+    const HullResult r = warp_march(lb.NL, fetch, rec);
+    if (lane == 0) {
+      finish_set(lb, out, set, s, r.E, r.h);
+      if (sc.stats) atomicAdd((unsigned long long*)&sc.stats[3], (unsigned long long)r.h);
+    }
+  }
+}
+
+int emax_small_forward(const SmallArgs& a, const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out,
+                       cudaStream_t st) {
+  if (a.C == 0) return DKG_OK;
+  const int n_al = (a.ntr[a.target] + 1) & ~1;
+  const size_t smem = sizeof(double) * ((size_t)((lb.NL + 1) & ~1) * (1 + SM_THREADS / 32) + 4 * (size_t)n_al);
+#define DKG_SMALL(DD)                                                                                              \
+  do {                                                                                                             \
+    if (smem > 47 * 1024)                                                                                          \
+      DKG_CUDA_OK(cudaFuncSetAttribute(small_kg_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    small_kg_kernel<DD><<<a.C, SM_THREADS, smem, st>>>(a, lb, sc, out);                                            \
+  } while (0)
+  switch (a.d) {
+    case 1: DKG_SMALL(1); break;
+    case 2: DKG_SMALL(2); break;
+    case 3: DKG_SMALL(3); break;
+    case 4: DKG_SMALL(4); break;
+    case 5: DKG_SMALL(5); break;
+    case 6: DKG_SMALL(6); break;
+    case 7: DKG_SMALL(7); break;
+    default: DKG_SMALL(8); break;
+  }
+#undef DKG_SMALL
   DKG_LAUNCH_CHECK();
   return DKG_OK;
 }

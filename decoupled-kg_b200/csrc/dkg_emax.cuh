@@ -130,8 +130,9 @@ struct BackwardArgs {
   const double* X = nullptr;     // [C, d] raw candidates
   const double* T = nullptr;     // [C, ldk]  Kinv k_i(X_train, x_c)
   int ldk = 0;
-  const double* BT = nullptr;    // [N, n_pad]
+  const double* BT = nullptr;    // [N, ldbt]
   int n_pad = 0;
+  int ldbt = 0;
   const double* xd_s = nullptr;  // [N_pad, d]
   const double* var = nullptr;   // [C]
   const double* sd = nullptr;    // [C]
@@ -172,6 +173,43 @@ int emax_overflow(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out
 // kg[c] = mean_j terms[c, j] and, if bw.dX, the fused envelope-theorem backward
 int emax_finalize(const LineBatch& lb, const EmaxOut& out, const BackwardArgs& bw, cudaStream_t st);
 
+// ---- small discretisations: the whole forward of one candidate in ONE CTA ----------------------
+// At the sizes the reference's BO loop runs (11 x 11 grid, 10 restarts; bo_loop.py:123-131) the
+// staged pipeline is ~17 dependent launches of a few microseconds each: ~100 us of pure kernel-chain
+// latency per call whatever the batch (93 us device-side at C = 10 even when replayed as a CUDA graph).
+// For N + 1 <= SMALL_MAX_LINES lines one CTA does everything up to the hull records: kernel rows and
+// posterior means, T = K^-1 k_x (same refinement step), the variance, the covariance row (plain fp64
+// dot products), and one warp per scalarisation running the reference's march over ALL lines: 36 us.
+// (Measured limit: at N = 1024 the unfiltered marches make this path 2x SLOWER than the staged one --
+// c2 at 512 candidates 0.57 vs 0.25 ms -- so it is kept to discretisations of a few hundred lines.)
+constexpr int SMALL_MAX_LINES = 256;
+constexpr int SMALL_MAX_TRAIN = 512;
+struct SmallArgs {
+  const double* X = nullptr;  // [C, d]
+  int C = 0, d = 0, M = 0, target = 0;
+  const double* xs[MAX_M] = {};     // [n_m, d] training inputs / lengthscale
+  const double* alpha[MAX_M] = {};  // [n_m]
+  int ntr[MAX_M] = {};
+  int kind[MAX_M] = {};
+  double outputscale[MAX_M] = {}, mean_const[MAX_M] = {}, y_mean[MAX_M] = {}, y_std[MAX_M] = {};
+  double ls[MAX_M][MAX_D] = {};
+  const double* W = nullptr;      // [S, M]
+  const double* Kinv = nullptr;   // [n_pad, ldk]   target objective
+  const double* Kmat = nullptr;   // [n_pad, ldk]
+  int ldk = 0, refine = 0;
+  const double* Kxd = nullptr;    // [n_pad, ldx]   k(X_train, X_disc)
+  int ldx = 0;
+  const double* xd_s = nullptr;   // [N_pad, d]
+  double noise = 0.0;
+  double* a_new = nullptr;        // [C, S] out
+  double* T = nullptr;            // [C, ldk] out
+  double* var = nullptr;          // [C] out
+  double* sd = nullptr;           // [C] out
+};
+// writes lb.Z rows (non-const in practice), a_new, T, var, sd, the per-set terms and hull records
+int emax_small_forward(const SmallArgs& a, const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out,
+                       cudaStream_t st);
+
 // E[f(Z)] for P piecewise-linear functions with H pieces each and ARBITRARY break points z [P, H-1]
 // (calculate_expected_value_of_piecewise_linear_function, discretekg.py:415-452) and its gradient
 int piecewise_expectation(const double* a, const double* b, const double* z, int P, int H, double* e,
@@ -203,8 +241,9 @@ struct CoupledBackward {
   int ldz = 0, M = 0, d = 0, S = 0, N = 0;
   const double* T[MAX_M] = {};      // [C, ldk_m]
   int ldk[MAX_M] = {};
-  const double* BT[MAX_M] = {};     // [N, n_pad_m]
+  const double* BT[MAX_M] = {};     // [N, ldbt_m]
   int n_pad[MAX_M] = {};
+  int ldbt[MAX_M] = {};
   const double* xd_s[MAX_M] = {};   // [N_pad, d]
   const double* xs[MAX_M] = {};
   const double* alpha[MAX_M] = {};

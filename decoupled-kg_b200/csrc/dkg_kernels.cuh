@@ -27,6 +27,20 @@ int cholesky_blocked(double* A, int n, int ld, int* info_dev, cudaStream_t st);
 int tri_inverse(const double* L, int n, int ldl, double* X, int ldx, cudaStream_t st);
 int matvec(const double* A, int lda, int rows, int cols, const double* x, double* y, cudaStream_t st);
 int chol_fast_max();
+// incremental refresh (dkg_plan_append_point)
+int kernel_row(const double* xq_dev, const double* pts, int npts, int d, int kind, double outputscale, double* out,
+               cudaStream_t st);
+int matvec_axpy(const double* A, int lda, int rows, int cols, const double* x, const double* y_in, double alpha,
+                double* y_out, cudaStream_t st);
+int append_scalars(const double* kv, const double* v, const double* alpha, int n, double kappa, double yc, double* scal,
+                   cudaStream_t st);
+int append_update_k(double* Kinv, double* Kmat, int ld, int n, const double* kv, const double* v, const double* scal,
+                    double kappa, cudaStream_t st);
+int append_update_alpha(double* alpha, const double* v, const double* scal, int n, cudaStream_t st);
+int append_w(double* Kxd, int ld, int n, int N, const double* v, const double* rrow, const double* scal, double* w,
+             cudaStream_t st);
+int append_update_b(double* B, int ldb, double* BT, int ldbt, int n, int N, const double* v, const double* w,
+                    cudaStream_t st);
 
 // ---- dkg_gemm.cu -----------------------------------------------------------------------------
 struct CovEpilogue {

@@ -16,8 +16,11 @@ struct ObjState {
   int kernel = 0;
   double outputscale = 1, mean_const = 0, noise = 0, y_mean = 0, y_std = 1;
   double ls[MAX_D];
-  double* xs = nullptr;     // [n, d]   train inputs / lengthscale
-  double* alpha = nullptr;  // [n_pad]  mean cache K^-1 (y - c), zero padded
+  int cap = 0;        // rows the n-dependent buffers below can hold (dkg_plan_append_point grows n up to it)
+  double jitter = 0;  // Cholesky jitter this objective needed (0 normally)
+  double* xs = nullptr;     // [cap, d] train inputs / lengthscale
+  double* alpha = nullptr;  // [cap]    mean cache K^-1 (y - c), zero padded
+  double* resid = nullptr;  // [cap]    y - c (kept for the mean-cache refresh of an append)
   // conditioning state (only for objectives whose observation is fantasised: the target in the
   // decoupled path, every objective in the coupled path)
   int ldk = 0;               // row stride of Kinv / T (n rounded up to GEMM_BN)
@@ -29,7 +32,8 @@ struct ObjState {
   unsigned char* Kxd_dig = nullptr;  // [digits][N_pad][KP] base-256 digit planes of Kxd^T (int8 tensor-core path)
   double* Kxd_scale = nullptr;       // [N_pad] power-of-two scale of each discretisation point's column
   double* B = nullptr;       // [n_pad, N_pad]  K^-1 k(X_train, X_disc), zero padded (backward only)
-  double* BT = nullptr;      // [N, n_pad]
+  double* BT = nullptr;      // [N, ldbt]
+  int ldbt = 0;              // row stride of BT (>= n_pad; the capacity, so that appends stay in place)
   double* xd_s = nullptr;    // [N_pad, d]    discretisation / lengthscale
 };
 
@@ -94,9 +98,18 @@ struct Workspace {
   cudaEvent_t stats_ev = nullptr;
   bool stats_pending = false;
   bool spill_checked = false;  // the first forward with gradients after a (re)allocation is checked synchronously
+  // Small batches are launch-bound (~17 kernels of a few microseconds each): their launch sequence is
+  // captured once per (C, with / without gradient) into a CUDA graph over the plan's own staging
+  // buffers (X, kg, dX above) and replayed with one launch.
+  struct GraphSlot { int C = 0; int grad = 0; cudaGraphExec_t exec = nullptr; unsigned long long used = 0; };
+  static constexpr int GRAPH_SLOTS = 8;
+  GraphSlot graphs[GRAPH_SLOTS];
+  unsigned long long graph_clock = 0;
+  cudaStream_t cap_stream = nullptr;  // capture stream (the caller's stream may be the legacy default stream)
   int last_C = 0;
 };
 
+constexpr int STATS_WORDS = 10;   // 8 counters (dkg_plan_stats) + the spill pool's fill count + padding
 constexpr int FILTER_TILE = 128;  // lines per warp of the fp32 chord filter (4 per lane)
 constexpr int SURV_CAP = 2048;  // survivors per (candidate, scalarisation) before the slow path
 constexpr int HULL_CAP = 64;    // hull vertices recorded per (candidate, scalarisation)

@@ -625,4 +625,159 @@ int matvec(const double* A, int lda, int rows, int cols, const double* x, double
 
 int chol_fast_max() { return CHOL_FAST_MAX; }
 
+// ==========================================================================================
+// Incremental refresh: one training point appended to one objective (dkg_plan_append_point).
+// With K' = [[K, k], [k^T, kappa]], v = K^-1 k and s = kappa - k^T v (the Schur complement):
+//   K'^-1 = [[K^-1 + v v^T / s, -v / s], [-v^T / s, 1 / s]]
+//   alpha' = [alpha - beta v; beta],                 beta = (y - c - k^T alpha) / s
+//   B' = K'^-1 [Kxd; r] = [B - v w^T; w^T],          w = (r - Kxd^T v) / s,  r = k(x_new, X_disc)
+// i.e. O(n^2) for the training side and O(n N) for the discretisation side, instead of the
+// O(n^3 + n^2 N) of a fresh plan.
+// ==========================================================================================
+__global__ void kernel_row_kernel(const double* __restrict__ xq, const double* __restrict__ pts, int npts, int d,
+                                  int kind, double outputscale, double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npts) return;
+  double sq = 0.0;
+  for (int k = 0; k < d; ++k) {
+    const double df = xq[k] - pts[(size_t)t * d + k];
+    sq += df * df;
+  }
+  out[t] = stationary_from_sq(kind, outputscale, sq);
+}
+int kernel_row(const double* xq_dev, const double* pts, int npts, int d, int kind, double outputscale, double* out,
+               cudaStream_t st) {
+  if (npts == 0) return DKG_OK;
+  kernel_row_kernel<<<ceil_div(npts, 128), 128, 0, st>>>(xq_dev, pts, npts, d, kind, outputscale, out);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// y_out = (y_in or 0) + alpha * A x ; one warp per row
+__global__ void matvec_axpy_kernel(const double* __restrict__ A, int lda, int rows, int cols, const double* __restrict__ x,
+                                   const double* __restrict__ y_in, double alpha, double* __restrict__ y_out) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  double acc = 0.0;
+  for (int k = lane; k < cols; k += 32) acc += A[(size_t)row * lda + k] * x[k];
+  acc = warp_sum(acc);
+  if (lane == 0) y_out[row] = (y_in != nullptr ? y_in[row] : 0.0) + alpha * acc;
+}
+int matvec_axpy(const double* A, int lda, int rows, int cols, const double* x, const double* y_in, double alpha,
+                double* y_out, cudaStream_t st) {
+  if (rows == 0) return DKG_OK;
+  matvec_axpy_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(A, lda, rows, cols, x, y_in, alpha, y_out);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// scal[0] = s = kappa - kv . v ; scal[1] = beta = (yc - kv . alpha) / s ; scal[2] = 1 / s   (one CTA)
+__global__ void append_scalars_kernel(const double* __restrict__ kv, const double* __restrict__ v,
+                                      const double* __restrict__ alpha, int n, double kappa, double yc,
+                                      double* __restrict__ scal) {
+  __shared__ double s1[8], s2[8];
+  double a = 0.0, b = 0.0;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    a += kv[t] * v[t];
+    b += kv[t] * alpha[t];
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = a; s2[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { ta += s1[k]; tb += s2[k]; }
+    const double s = kappa - ta;
+    scal[0] = s;
+    scal[1] = (yc - tb) / s;
+    scal[2] = 1.0 / s;
+  }
+}
+int append_scalars(const double* kv, const double* v, const double* alpha, int n, double kappa, double yc, double* scal,
+                   cudaStream_t st) {
+  append_scalars_kernel<<<1, 256, 0, st>>>(kv, v, alpha, n, kappa, yc, scal);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+__global__ void append_update_k_kernel(double* __restrict__ Kinv, double* __restrict__ Kmat, int ld, int n,
+                                       const double* __restrict__ kv, const double* __restrict__ v,
+                                       const double* __restrict__ scal, double kappa) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j > n) return;
+  const double rs = scal[2];
+  if (i < n && j < n) {
+    Kinv[(size_t)i * ld + j] += v[i] * v[j] * rs;
+  } else if (i == n && j == n) {
+    Kinv[(size_t)n * ld + n] = rs;
+    Kmat[(size_t)n * ld + n] = kappa;
+  } else if (i == n) {
+    Kinv[(size_t)n * ld + j] = -v[j] * rs;
+    Kmat[(size_t)n * ld + j] = kv[j];
+  } else {  // j == n
+    Kinv[(size_t)i * ld + n] = -v[i] * rs;
+    Kmat[(size_t)i * ld + n] = kv[i];
+  }
+}
+int append_update_k(double* Kinv, double* Kmat, int ld, int n, const double* kv, const double* v, const double* scal,
+                    double kappa, cudaStream_t st) {
+  dim3 grid(ceil_div(n + 1, 128), n + 1);
+  append_update_k_kernel<<<grid, 128, 0, st>>>(Kinv, Kmat, ld, n, kv, v, scal, kappa);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+__global__ void append_update_alpha_kernel(double* __restrict__ alpha, const double* __restrict__ v,
+                                           const double* __restrict__ scal, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) alpha[t] -= scal[1] * v[t];
+  else if (t == n) alpha[n] = scal[1];
+}
+int append_update_alpha(double* alpha, const double* v, const double* scal, int n, cudaStream_t st) {
+  append_update_alpha_kernel<<<ceil_div(n + 1, 128), 128, 0, st>>>(alpha, v, scal, n);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// w[j] = (r[j] - sum_t v[t] Kxd[t, j]) / s, and the new row of Kxd
+__global__ void append_w_kernel(double* __restrict__ Kxd, int ld, int n, int N, const double* __restrict__ v,
+                                const double* __restrict__ rrow, const double* __restrict__ scal, double* __restrict__ w) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  double acc = 0.0;
+  for (int t = 0; t < n; ++t) acc = fma(v[t], Kxd[(size_t)t * ld + j], acc);
+  w[j] = (rrow[j] - acc) * scal[2];
+  Kxd[(size_t)n * ld + j] = rrow[j];
+}
+int append_w(double* Kxd, int ld, int n, int N, const double* v, const double* rrow, const double* scal, double* w,
+             cudaStream_t st) {
+  append_w_kernel<<<ceil_div(N, 128), 128, 0, st>>>(Kxd, ld, n, N, v, rrow, scal, w);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// B[t, j] -= v[t] w[j] (t < n), B[n, j] = w[j];  BT likewise (transposed copy for the backward's row gathers)
+__global__ void append_update_b_kernel(double* __restrict__ B, int ldb, double* __restrict__ BT, int ldbt, int n, int N,
+                                       const double* __restrict__ v, const double* __restrict__ w) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+  if (j >= N) return;
+  if (t < n) {
+    const double nv = B[(size_t)t * ldb + j] - v[t] * w[j];
+    B[(size_t)t * ldb + j] = nv;
+    BT[(size_t)j * ldbt + t] = nv;
+  } else {
+    B[(size_t)n * ldb + j] = w[j];
+    BT[(size_t)j * ldbt + n] = w[j];
+  }
+}
+int append_update_b(double* B, int ldb, double* BT, int ldbt, int n, int N, const double* v, const double* w,
+                    cudaStream_t st) {
+  dim3 grid(ceil_div(N, 128), n + 1);
+  append_update_b_kernel<<<grid, 128, 0, st>>>(B, ldb, BT, ldbt, n, N, v, w);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
 }  // namespace dkg

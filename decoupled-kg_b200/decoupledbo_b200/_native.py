@@ -19,14 +19,15 @@ from .gp_state import GPModelList
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_PKG_DIR), "lib", "libdkg_b200.so")
 
-DKG_OK, DKG_EINVAL, DKG_ECUDA, DKG_ENOTPD, DKG_ENOMEM, DKG_EEMPTY = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 3
+DKG_OK, DKG_EINVAL, DKG_ECUDA, DKG_ENOTPD, DKG_ENOMEM, DKG_EEMPTY, DKG_ETRUNC, DKG_ECAPACITY = 0, -1, -2, -3, -4, -5, -6, -7
+ABI_VERSION = 4
 
 EXPORTED_SYMBOLS = (
     "dkg_abi_version",
     "dkg_last_error",
     "dkg_plan_create",
     "dkg_plan_destroy",
+    "dkg_plan_append_point",
     "dkg_forward_dev",
     "dkg_forward_host",
     "dkg_expected_max_lines_dev",
@@ -48,6 +49,10 @@ PROFILE_CATEGORIES = (
 
 class NativeLibraryError(RuntimeError):
     pass
+
+
+class PlanCapacityError(RuntimeError):
+    """``Plan.append_point``: no room left for another training point -- build a new plan."""
 
 
 class _Objective(Structure):
@@ -89,6 +94,8 @@ def load_library() -> ctypes.CDLL:
     ]
     lib.dkg_plan_destroy.restype = None
     lib.dkg_plan_destroy.argtypes = [c_void_p]
+    lib.dkg_plan_append_point.restype = ctypes.c_int
+    lib.dkg_plan_append_point.argtypes = [c_void_p, c_int32, POINTER(c_double), c_double, c_void_p]
     lib.dkg_forward_dev.restype = ctypes.c_int
     lib.dkg_forward_dev.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
     lib.dkg_forward_host.restype = ctypes.c_int
@@ -237,6 +244,25 @@ class Plan:
         self._handle = handle
         self._keep = keep  # the library copies what it needs, but keep inputs alive until here
 
+    def append_point(self, m: int, x: Tensor, y: float) -> None:
+        """Incremental refresh (``dkg_plan_append_point``): objective ``m`` received the observation
+        ``(x, y)`` (``y`` in the space of ``train_y``) and the hyper-parameters are unchanged -- what the
+        reference's BO loop does between iterations (``bo_loop.py:403-405``, fixed hyper-parameters
+        ``:574-589``).  O(n^2 + n N) instead of a new plan's O(n^3 + n^2 N).  Raises
+        ``PlanCapacityError`` when the plan has no room left (then build a new one)."""
+        xs = [float(v) for v in torch.as_tensor(x, dtype=torch.double).reshape(-1).tolist()]
+        if len(xs) != self.d:
+            raise ValueError(f"x must have {self.d} coordinates; got {len(xs)}")
+        xb = (c_double * self.d)(*xs)
+        with torch.cuda.device(self.device):
+            rc = load_library().dkg_plan_append_point(self._handle, int(m), xb, float(y), _stream_ptr())
+        if rc == DKG_ECAPACITY:
+            raise PlanCapacityError(load_library().dkg_last_error().decode("utf-8", "replace"))
+        _check(rc, "dkg_plan_append_point")
+        self.n_total += 1
+        if int(m) == self.target:
+            self.n_target += 1
+
     def close(self) -> None:
         if getattr(self, "_handle", None) is not None and self._handle.value:
             load_library().dkg_plan_destroy(self._handle)
@@ -276,6 +302,15 @@ class Plan:
         assert (not X.is_cuda) and X.dtype == torch.double and X.dim() == 2 and X.shape[1] == self.d
         X = X.contiguous()
         C = X.shape[0]
+        if out_kg is None and out_dX is None and C * (1 + self.d) <= 8192:
+            # small batch (the optimiser's restarts): the few hundred bytes go straight into fresh
+            # tensors -- a pinned staging copy plus a clone costs more than the transfer
+            kg = torch.empty(C, dtype=torch.double)
+            dX = torch.empty(C, self.d, dtype=torch.double) if need_grad else None
+            with torch.cuda.device(self.device):
+                rc = load_library().dkg_forward_host(self._handle, _ptr(X), C, _ptr(kg), _ptr(dX), _stream_ptr())
+            _check(rc, "dkg_forward_host")
+            return kg, dX
         # results land in pinned staging buffers owned by the plan (fast D2H), then are copied
         # into fresh tensors so callers may keep them across calls
         if getattr(self, "_pin_cap", 0) < C:

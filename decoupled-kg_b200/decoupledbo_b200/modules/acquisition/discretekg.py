@@ -74,11 +74,12 @@ class _KGFunction(torch.autograd.Function):
             kg, dX = plan.forward_host(Xd, need_grad)
         ctx.has_grad = need_grad
         if need_grad:
-            # Sets with more than 64 hull vertices keep their extra records in a spill pool; only if
-            # that pool runs dry are records lost, and then the kernel writes NaN into the gradient
-            # rows concerned.  Host results are inspected here (free); device results carry the NaN
-            # to the caller without forcing a sync (DKG_CHECK=1 checks them as well).
-            if (not dX.is_cuda) or os.environ.get("DKG_CHECK") == "1":
+            # Sets with more than 64 hull vertices keep their extra records in a spill pool that grows on
+            # demand; only if its size is pinned (DKG_SPILL_BLOCKS) can records be lost, and then the kernel
+            # writes NaN into the gradient rows concerned.  The host entry point raises by itself (it
+            # synchronises anyway); device results carry the NaN to the caller without forcing a sync
+            # (DKG_CHECK=1 checks them here as well).
+            if dX.is_cuda and os.environ.get("DKG_CHECK") == "1":
                 if bool(torch.isnan(dX).any()) and not bool(torch.isnan(Xd).any()):
                     _raise_if_truncated(plan)
             ctx.save_for_backward(dX)
@@ -220,6 +221,38 @@ class DiscreteKnowledgeGradient(AcquisitionFunction):
             )
             self._plan_key = key
         return self._plan
+
+    def append_observation(self, objective_ix: int, x: Tensor, y, model=None) -> bool:
+        """Incremental refresh between BO iterations (an addition to the reference surface): objective
+        ``objective_ix`` received the observation ``(x, y)`` and the hyper-parameters did not change
+        (``--fit-hyperparams=never`` / ``once``: ``bo_loop.py:403-405``, ``:574-589``).  The cached GPU state
+        is extended in O(n^2 + n N) instead of being rebuilt in O(n^3 + n^2 N).
+
+        ``y`` is in the space of the model's ``train_targets`` (standardised if an outcome transform is
+        used).  ``model``: the model that now includes the point -- it replaces ``self.model``; if omitted
+        and ``self.model`` is a ``GPModelList`` the point is appended to it here.  Returns True when the
+        state was extended in place, False when it has to be rebuilt at the next call (no plan yet, no
+        room left, or the extended covariance is not positive definite without new jitter)."""
+        x = torch.as_tensor(x, dtype=torch.double).detach().reshape(-1)
+        yv = float(torch.as_tensor(y).reshape(-1)[0])
+        if model is not None:
+            if isinstance(model, torch.nn.Module):
+                self.model = model
+            else:  # tensor-only GP state containers are plain objects (see botorch_compat.AcquisitionFunction)
+                object.__setattr__(self, "model", model)
+        elif isinstance(self.model, GPModelList):
+            o = self.model.models[objective_ix]
+            o.train_x = torch.cat([o.train_x, x.reshape(1, -1).to(o.train_x)])
+            o.train_y = torch.cat([o.train_y, torch.tensor([yv], dtype=o.train_y.dtype)])
+        if self._plan is None:
+            return False
+        try:
+            self._plan.append_point(objective_ix, x, yv)
+        except (_native.PlanCapacityError, RuntimeError):
+            self.invalidate()
+            return False
+        self._plan_key = self._state_key()  # the model now matches the extended plan
+        return True
 
     def invalidate(self) -> None:
         """Drop the cached GPU state (done automatically when the model state changes)."""

@@ -98,26 +98,29 @@ def evaluate_objectives(
             recv = recv.view((world,) + tuple(buf.shape))
         else:
             recv = buf.unsqueeze(0)
-        if on_host and recv.is_cuda:
-            host = _scratch.pinned_like(recv.shape)
-            host.copy_(recv, non_blocking=True)
+        # (world, M, rows * width) -> one flat [kg (M, C) | dX (M, C, d)] block in row order, assembled where
+        # the data is (on the device for NCCL) so that a host caller pays exactly ONE device-to-host copy
+        flat = torch.empty(M * C * width, dtype=torch.double, device=recv.device)
+        kg_v = flat[: M * C].view(M, C)
+        dX_v = flat[M * C:].view(M, C, d) if need_grad else None
+        if C == world * rows:
+            kg_v.view(M, world, rows).copy_(recv[:, :, :rows].permute(1, 0, 2))
+            if need_grad:
+                dX_v.view(M, world, rows, d).copy_(recv[:, :, rows:].reshape(world, M, rows, d).permute(1, 0, 2, 3))
+        else:
+            for r in range(world):
+                rlo, rhi = _dist.shard_bounds(C, world, r)
+                k = rhi - rlo
+                kg_v[:, rlo:rhi] = recv[r, :, :k]
+                if need_grad:
+                    dX_v[:, rlo:rhi] = recv[r, :, rows: rows + k * d].reshape(M, k, d)
+        if on_host and flat.is_cuda:
+            host = torch.empty(flat.shape, dtype=torch.double, pin_memory=True)  # (cached pinned allocator)
+            host.copy_(flat, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            recv = host
-        elif not on_host and not recv.is_cuda:
-            recv = recv.to(dev)
-    # (world, M, rows * width) -> kg (M, C), dX (M, C, d) in row order
-    kg_parts, dX_parts = [], []
-    for r in range(world):
-        rlo, rhi = _dist.shard_bounds(C, world, r)
-        k = rhi - rlo
-        kg_parts.append(recv[r, :, :k])
-        if need_grad:
-            dX_parts.append(recv[r, :, rows: rows + k * d].reshape(M, k, d))
-    kg = kg_parts[0] if world == 1 else torch.cat(kg_parts, dim=1)
-    dX = None
-    if need_grad:
-        dX = dX_parts[0] if world == 1 else torch.cat(dX_parts, dim=1)
-    if on_host:  # the pinned staging buffer is reused by the next call
-        kg = kg.clone()
-        dX = dX.clone() if dX is not None else None
+            flat = host
+        elif not on_host and not flat.is_cuda:
+            flat = flat.to(dev)
+    kg = flat[: M * C].view(M, C)
+    dX = flat[M * C:].view(M, C, d) if need_grad else None
     return kg, dX

@@ -33,7 +33,7 @@ extern "C" {
 #define DKG_API
 #endif
 
-#define DKG_ABI_VERSION 3
+#define DKG_ABI_VERSION 4
 
 /* error codes */
 #define DKG_OK 0
@@ -42,6 +42,11 @@ extern "C" {
 #define DKG_ENOTPD (-3)   /* training covariance not positive definite even with 1e-6 jitter   */
 #define DKG_ENOMEM (-4)
 #define DKG_EEMPTY (-5)   /* zero lines given to the expected-max stage (ValueError upstream)  */
+#define DKG_ECAPACITY (-7) /* dkg_plan_append_point: the plan's buffers have no room for another training point
+                             of that objective (or the plan was built by the large-n path): build a new plan   */
+#define DKG_ETRUNC (-6)   /* hull records lost (spill pool pinned too small by DKG_SPILL_BLOCKS): values are
+                             exact, the gradient rows concerned are NaN (dkg_forward_host only; the device
+                             entry point reports it through dkg_plan_stats()[6] and the NaN rows)          */
 
 /* stationary kernels of the reference's model factory
  * (src/decoupledbo/modules/model/factory.py:116-135: ScaleKernel(MaternKernel(nu=2.5)|RBFKernel)) */
@@ -95,6 +100,25 @@ DKG_API int dkg_plan_create(const dkg_objective* objs, int32_t M, int32_t d, con
                     uint32_t flags, void* stream, dkg_plan** out_plan);
 
 DKG_API void dkg_plan_destroy(dkg_plan* plan);
+
+/*
+ * dkg_plan_append_point -- incremental refresh of a plan when ONE observation is added to ONE objective
+ *   with unchanged hyper-parameters: what the reference's BO loop does between iterations
+ *   (src/decoupledbo/pipeline/nodes/bo_loop.py:403-405 appends the point, :457-465 rebuilds the model;
+ *   with --fit-hyperparams=never/once the hyper-parameters stay fixed, :574-589).  Block-inverse update of
+ *   (K + noise I)^-1, the mean cache, K^-1 k(X_train, X_disc) and the digit planes, then the posterior
+ *   means at the discretisation and the intercept table: O(n^2 + n N) instead of the O(n^3 + n^2 N) of
+ *   dkg_plan_create.  Works for decoupled and coupled plans and for any objective m
+ *   (the fantasised one or not; objectives may have different numbers of points).
+ *
+ *   m        objective that received the observation, in [0, M)
+ *   x_host   [d] the new input (unit cube, as train_x)
+ *   y        the new target in the same space as train_y (standardised if an outcome transform is used)
+ *   returns DKG_ECAPACITY when there is no room left (rows are padded to a multiple of 128, so a plan
+ *   built with n points takes up to 128 - n % 128 appends) and DKG_ENOTPD when the extended covariance is
+ *   not positive definite; the plan is unchanged in both cases.  Synchronises the stream.
+ */
+DKG_API int dkg_plan_append_point(dkg_plan* plan, int32_t m, const double* x_host, double y, void* stream);
 
 /*
  * dkg_forward_dev -- replaces DiscreteKnowledgeGradient.forward (discretekg.py:131-159), i.e. the

@@ -12,6 +12,7 @@ def _eval(P, target, X, mode, xd=None):
     from decoupledbo_b200.modules.acquisition.discretekg import DiscreteKnowledgeGradient
 
     old = os.environ.get("DKG_FILTER")
+    os.environ["DKG_SMALL"] = "0"  # these tests are about the staged pipeline's filters, whatever the size
     if mode == "tile":  # the default: tile-first filter wherever its preconditions hold
         os.environ.pop("DKG_FILTER", None)
     else:
@@ -25,6 +26,7 @@ def _eval(P, target, X, mode, xd=None):
         st = acq._get_plan().stats()
         return kg.detach().clone(), g.clone(), st
     finally:
+        os.environ.pop("DKG_SMALL", None)
         if old is None:
             os.environ.pop("DKG_FILTER", None)
         else:

@@ -27,22 +27,39 @@ def _counting(self, X):
     return _orig(self, X)
 DiscreteKnowledgeGradient.forward = _counting
 
-spec = DiscreteKgOptimisationSpec(32, num_restarts=64, raw_samples=512, batch_limit=64, max_iter=200)
-rows = []
-for rep in range(4):
-    torch.manual_seed(rep)
-    for k in calls: calls[k] = 0
-    _native.launch_count_reset()
+# host / GPU split: time spent inside the native call (H2D + kernels + D2H + sync) vs everything else
+native_s = {"t": 0.0}
+_fh = _native.Plan.forward_host
+def _timed_fh(self, *a, **k):
     t0 = time.perf_counter()
-    x, i, v = spec.optimize_for_single_objective(P.model, [1.0, 1.0], 2, scalarisation_weights=P.weights)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    evals = (calls["cand_fwd"] + calls["cand_fwd_bwd"]) * S
-    rows.append({"seconds": dt, "calls_fwd": calls["fwd"], "calls_fwd_bwd": calls["fwd_bwd"],
-                 "kg_evals": evals, "kg_evals_per_s": evals / dt, "kernel_launches": _native.launch_count(),
-                 "chosen_objective": int(i), "value_per_cost": float(v)})
-    print(json.dumps(rows[-1]))
-warm = rows[1:]
-print(json.dumps({"config": "c3: c2 problem, optimize_acqf 64 restarts x 512 raw samples, maxiter 200, both objectives",
-                  "median_seconds": sorted(r["seconds"] for r in warm)[len(warm) // 2],
-                  "median_kg_evals_per_s": sorted(r["kg_evals_per_s"] for r in warm)[len(warm) // 2]}))
+    try:
+        return _fh(self, *a, **k)
+    finally:
+        native_s["t"] += time.perf_counter() - t0
+_native.Plan.forward_host = _timed_fh
+
+for concurrent in (True, False):
+    spec = DiscreteKgOptimisationSpec(32, num_restarts=64, raw_samples=512, batch_limit=64, max_iter=200)
+    spec.concurrent_objectives = concurrent
+    rows = []
+    for rep in range(6):  # SAME seed every time: the spread is the machine's, not the optimiser's path
+        torch.manual_seed(0)
+        for k in calls: calls[k] = 0
+        native_s["t"] = 0.0
+        _native.launch_count_reset()
+        t0 = time.perf_counter()
+        x, i, v = spec.optimize_for_single_objective(P.model, [1.0, 1.0], 2, scalarisation_weights=P.weights)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        evals = (calls["cand_fwd"] + calls["cand_fwd_bwd"]) * S
+        rows.append({"concurrent_objectives": concurrent, "seconds": dt, "seconds_in_native_calls": native_s["t"],
+                     "calls_fwd": calls["fwd"], "calls_fwd_bwd": calls["fwd_bwd"],
+                     "kg_evals": evals, "kg_evals_per_s": evals / dt, "launches": _native.launch_count(),
+                     "chosen_objective": int(i), "value_per_cost": float(v)})
+        print(json.dumps(rows[-1]))
+    warm = sorted(r["seconds"] for r in rows[1:])
+    print(json.dumps({"config": "c3: c2 problem, optimize_acqf 64 restarts x 512 raw samples, maxiter 200, both objectives",
+                      "concurrent_objectives": concurrent, "median_seconds": warm[len(warm) // 2],
+                      "min_seconds": warm[0], "max_seconds": warm[-1],
+                      "spread": (warm[-1] - warm[0]) / warm[len(warm) // 2],
+                      "median_kg_evals_per_s": sorted(r["kg_evals_per_s"] for r in rows[1:])[(len(rows) - 1) // 2]}))

@@ -544,6 +544,10 @@ def main():
             }
 
     if rank == 0:
+        from decoupledbo_b200 import multi as _multi
+
+        if _multi.TIMING is not None:  # DKG_MULTI_TIMING=1: diagnosis of the e2e path (numbers of such a run are not bench values)
+            extra["multi_timing_ms"] = {k: 1e3 * v[0] / max(v[1], 1) for k, v in _multi.TIMING.items()}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,

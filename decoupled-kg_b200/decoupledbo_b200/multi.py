@@ -34,14 +34,36 @@ class _Scratch:
             self.streams[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
         return self.streams[key]
 
-    def pinned_like(self, shape):
-        key = tuple(shape)
-        if key not in self.pinned:
-            self.pinned[key] = torch.empty(shape, dtype=torch.double).pin_memory()
-        return self.pinned[key]
+    def pinned_next(self, shape):
+        """Two pinned staging buffers per shape, handed out alternately: a result stays valid until the
+        second-next call with the same shapes (a fresh pinned allocation costs ~0.2 ms per call: measured)."""
+        pair = self.pinned.setdefault(tuple(shape), [None, None, 0])
+        k = pair[2]
+        if pair[k] is None:
+            pair[k] = torch.empty(shape, dtype=torch.double).pin_memory()
+        pair[2] = 1 - k
+        return pair[k]
 
 
 _scratch = _Scratch()
+
+# DKG_MULTI_TIMING=1: per-phase host wall times (a device sync after every phase; diagnosis only)
+import os as _os
+import time as _time
+
+TIMING = {} if _os.environ.get("DKG_MULTI_TIMING") == "1" else None
+
+
+def _mark(name, t0, dev):
+    if TIMING is None:
+        return t0
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    t1 = _time.perf_counter()
+    acc = TIMING.setdefault(name, [0.0, 0])
+    acc[0] += t1 - t0
+    acc[1] += 1
+    return t1
 
 
 def evaluate_objectives(
@@ -51,7 +73,9 @@ def evaluate_objectives(
     ``X``: ``(C, d)`` candidates (host or CUDA tensor; identical on every rank of ``group``).
 
     Returns ``kg (M, C)`` and, if ``need_grad``, ``dX (M, C, d)`` with ``dX[m, c] = d kg[m, c] / d X[c]``,
-    on ``X``'s device, identical on every rank."""
+    on ``X``'s device, identical on every rank.  Both are VIEWS into one result block (not necessarily
+    contiguous); for host inputs that block is one of two alternating pinned staging buffers, i.e. the
+    results stay valid until the second-next call with the same shapes -- copy them to keep them longer."""
     plans = [a._get_plan() for a in acqfs]
     M = len(plans)
     dev = plans[0].device
@@ -69,6 +93,7 @@ def evaluate_objectives(
     import contextlib
 
     cuda = dev.type == "cuda"  # (CPU "plans" exist only in the gloo tests of this host logic)
+    t0 = _time.perf_counter() if TIMING is not None else 0.0
     with (torch.cuda.device(dev) if cuda else contextlib.nullcontext()):
         Xs = X[lo:hi]
         if Xs.dtype != torch.double:
@@ -90,37 +115,41 @@ def evaluate_objectives(
         for s in streams:
             if s is not cur:
                 cur.wait_stream(s)
+        t0 = _mark("h2d+kernels", t0, dev)
         if shard:
-            backend_cpu = dist.get_backend(group) == "gloo"
-            send = buf.cpu() if backend_cpu else buf
-            recv = torch.empty(world * send.numel(), dtype=buf.dtype, device=send.device)
-            dist.all_gather_into_tensor(recv, send.reshape(-1), group=group)
-            recv = recv.view((world,) + tuple(buf.shape))
-        else:
-            recv = buf.unsqueeze(0)
-        # (world, M, rows * width) -> one flat [kg (M, C) | dX (M, C, d)] block in row order, assembled where
-        # the data is (on the device for NCCL) so that a host caller pays exactly ONE device-to-host copy
-        flat = torch.empty(M * C * width, dtype=torch.double, device=recv.device)
-        kg_v = flat[: M * C].view(M, C)
-        dX_v = flat[M * C:].view(M, C, d) if need_grad else None
-        if C == world * rows:
-            kg_v.view(M, world, rows).copy_(recv[:, :, :rows].permute(1, 0, 2))
+            # per-candidate records [objective][kg | dX]: a rank's shard is then ONE contiguous block of the
+            # gathered buffer, which is already in row order -- no reordering after the collective
+            pack = torch.empty(rows, M, width, dtype=torch.double, device=dev)
+            if n < rows:
+                pack.zero_()
+            pack[:n, :, 0] = buf[:, :n].t()
             if need_grad:
-                dX_v.view(M, world, rows, d).copy_(recv[:, :, rows:].reshape(world, M, rows, d).permute(1, 0, 2, 3))
+                pack[:n, :, 1:] = buf[:, rows: rows + n * d].view(M, n, d).permute(1, 0, 2)
+            backend_cpu = dist.get_backend(group) == "gloo"
+            send = pack.cpu() if backend_cpu else pack
+            recv = torch.empty(world * rows * M * width, dtype=torch.double, device=send.device)
+            dist.all_gather_into_tensor(recv, send.reshape(-1), group=group)
+            recv = recv.view(world * rows, M, width)
+            if C != world * rows:  # ragged shards: drop the padding rows of the shorter ones
+                recv = torch.cat([recv[r * rows: r * rows + (_dist.shard_bounds(C, world, r)[1] - _dist.shard_bounds(C, world, r)[0])]
+                                  for r in range(world)], dim=0)
+            t0 = _mark("pack+all_gather", t0, dev)
+            res, packed = recv, True
         else:
-            for r in range(world):
-                rlo, rhi = _dist.shard_bounds(C, world, r)
-                k = rhi - rlo
-                kg_v[:, rlo:rhi] = recv[r, :, :k]
-                if need_grad:
-                    dX_v[:, rlo:rhi] = recv[r, :, rows: rows + k * d].reshape(M, k, d)
-        if on_host and flat.is_cuda:
-            host = torch.empty(flat.shape, dtype=torch.double, pin_memory=True)  # (cached pinned allocator)
-            host.copy_(flat, non_blocking=True)
+            res, packed = buf, False
+        if on_host and res.is_cuda:
+            host = _scratch.pinned_next(tuple(res.shape))
+            host.copy_(res, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            flat = host
-        elif not on_host and not flat.is_cuda:
-            flat = flat.to(dev)
-    kg = flat[: M * C].view(M, C)
-    dX = flat[M * C:].view(M, C, d) if need_grad else None
+            res = host
+            t0 = _mark("d2h+sync", t0, dev)
+        elif not on_host and not res.is_cuda:
+            res = res.to(dev)
+    # views into the one result block (possibly non-contiguous)
+    if packed:  # (C, M, width)
+        kg = res[:, :, 0].t()
+        dX = res[:, :, 1:].permute(1, 0, 2) if need_grad else None
+    else:       # (M, rows * width) with rows == C
+        kg = res[:, :C]
+        dX = res[:, C:].view(M, C, d) if need_grad else None
     return kg, dX

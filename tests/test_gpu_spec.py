@@ -60,3 +60,38 @@ def test_optimize_for_full_evaluation_coupled():
     assert x.shape == (1, 2) and float(x.min()) >= 0.0 and float(x.max()) <= 1.0
     want = odk.kg_coupled(om, x[0], odk.make_std_grid(4, 2), P.weights, dense=True)
     np.testing.assert_allclose(float(v), float(want), rtol=1e-8, atol=1e-12)
+
+
+def test_concurrent_objectives_give_the_serial_result():
+    """f1: the per-objective optimisations run side by side (threads + streams) but the starting points are
+    drawn in objective order, so the chosen (x, objective, value) equals the serial loop's bit for bit."""
+    from decoupledbo_b200.modules.acquisition_optimisation_strategy import DiscreteKgOptimisationSpec
+
+    P = small_problem(n_train=14, noise=(1e-2, 1e-2))
+    out = {}
+    for concurrent in (True, False):
+        spec = DiscreteKgOptimisationSpec(5, num_restarts=6, raw_samples=24, batch_limit=6, max_iter=25)
+        spec.concurrent_objectives = concurrent
+        torch.manual_seed(7)
+        out[concurrent] = spec.optimize_for_single_objective(P.model, [1.0, 1.5], 2, scalarisation_weights=P.weights)
+    (xa, ia, va), (xb, ib, vb) = out[True], out[False]
+    assert ia == ib and torch.equal(xa, xb) and torch.equal(va, vb)
+
+
+def test_evaluate_objectives_matches_the_individual_acquisition_functions():
+    from decoupledbo_b200.modules.acquisition.discretekg import DiscreteKnowledgeGradient
+    from decoupledbo_b200.multi import evaluate_objectives
+
+    P = small_problem(n_disc=400, n_cand=37)
+    for dev in ("cpu", "cuda"):
+        X = P.candidates.to(dev)
+        acqs = [DiscreteKnowledgeGradient(P.model, P.x_disc.to(dev), P.weights, target_output_ix=i) for i in range(2)]
+        kg, dX = evaluate_objectives(acqs, X, need_grad=True)
+        assert kg.shape == (2, 37) and dX.shape == (2, 37, 2) and kg.device.type == dev
+        for i, a in enumerate(acqs):
+            Xg = X.clone().requires_grad_(True)
+            v = a(Xg.unsqueeze(1))
+            (g,) = torch.autograd.grad(v.sum(), Xg)
+            assert torch.equal(kg[i], v.detach()) and torch.equal(dX[i], g)
+        kg2, none = evaluate_objectives(acqs, X, need_grad=False)
+        assert none is None and torch.equal(kg2, kg)

@@ -35,6 +35,7 @@ for _p in (ROOT, os.path.join(ROOT, "decoupled-kg_b200")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "kg_evals_per_sec_fwd_bwd"
@@ -343,7 +344,8 @@ def main():
 
         def step():
             kg, dX = evaluate_objectives(acqs, X_host, need_grad=True, group=group)
-            return [int(kg[m].argmax()) for m in range(M)]
+            # (numpy: torch's CPU argmax costs ~4 ns per element single-threaded, 0.3 ms per step at 8 GPUs)
+            return [int(np.argmax(kg[m].numpy())) for m in range(M)]
 
         return step
 

@@ -1189,6 +1189,8 @@ static int launch_filter32(const LineBatch& lb, const EmaxScratch& sc, cudaStrea
   if (smem > 47 * 1024) {
     DKG_CUDA_OK(cudaFuncSetAttribute(filter32_kernel<G, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DKG_CUDA_OK(cudaFuncSetAttribute(filter32_kernel<G, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DKG_CUDA_OK(cudaFuncSetAttribute(filter32_kernel<G, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DKG_CUDA_OK(cudaFuncSetAttribute(filter32_kernel<G, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   // two sampled blocks (1024 lines) out of >= 8; smaller rows are filtered in one launch
   const bool two_phase = sc.chain5 != nullptr && sc.chainv != nullptr && nblk >= 8;

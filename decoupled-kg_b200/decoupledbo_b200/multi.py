@@ -73,8 +73,8 @@ def evaluate_objectives(
     ``X``: ``(C, d)`` candidates (host or CUDA tensor; identical on every rank of ``group``).
 
     Returns ``kg (M, C)`` and, if ``need_grad``, ``dX (M, C, d)`` with ``dX[m, c] = d kg[m, c] / d X[c]``,
-    on ``X``'s device, identical on every rank.  Both are VIEWS into one result block (not necessarily
-    contiguous); for host inputs that block is one of two alternating pinned staging buffers, i.e. the
+    on ``X``'s device, identical on every rank.  Both are views into one result block (each ``kg[m]`` and
+    ``dX[m]`` is contiguous); for host inputs that block is one of two alternating pinned staging buffers, i.e. the
     results stay valid until the second-next call with the same shapes -- copy them to keep them longer."""
     plans = [a._get_plan() for a in acqfs]
     M = len(plans)
@@ -117,26 +117,30 @@ def evaluate_objectives(
                 cur.wait_stream(s)
         t0 = _mark("h2d+kernels", t0, dev)
         if shard:
-            # per-candidate records [objective][kg | dX]: a rank's shard is then ONE contiguous block of the
-            # gathered buffer, which is already in row order -- no reordering after the collective
-            pack = torch.empty(rows, M, width, dtype=torch.double, device=dev)
-            if n < rows:
-                pack.zero_()
-            pack[:n, :, 0] = buf[:, :n].t()
-            if need_grad:
-                pack[:n, :, 1:] = buf[:, rows: rows + n * d].view(M, n, d).permute(1, 0, 2)
             backend_cpu = dist.get_backend(group) == "gloo"
-            send = pack.cpu() if backend_cpu else pack
-            recv = torch.empty(world * rows * M * width, dtype=torch.double, device=send.device)
+            send = buf.cpu() if backend_cpu else buf
+            recv = torch.empty(world * send.numel(), dtype=torch.double, device=send.device)
             dist.all_gather_into_tensor(recv, send.reshape(-1), group=group)
-            recv = recv.view(world * rows, M, width)
-            if C != world * rows:  # ragged shards: drop the padding rows of the shorter ones
-                recv = torch.cat([recv[r * rows: r * rows + (_dist.shard_bounds(C, world, r)[1] - _dist.shard_bounds(C, world, r)[0])]
-                                  for r in range(world)], dim=0)
-            t0 = _mark("pack+all_gather", t0, dev)
-            res, packed = recv, True
+            recv = recv.view(world, M, rows * width)
+            # (world, M, [kg | dX]) -> one contiguous [kg (M, C) | dX (M, C, d)] block in row order, assembled
+            # where the data is (on the device under NCCL): two strided copies, then ONE device-to-host copy
+            res = torch.empty(M * C * width, dtype=torch.double, device=recv.device)
+            kg_v = res[: M * C].view(M, C)
+            dX_v = res[M * C:].view(M, C, d) if need_grad else None
+            if C == world * rows:
+                kg_v.view(M, world, rows).copy_(recv[:, :, :rows].permute(1, 0, 2))
+                if need_grad:
+                    dX_v.view(M, world, rows, d).copy_(recv[:, :, rows:].unflatten(2, (rows, d)).permute(1, 0, 2, 3))
+            else:  # ragged shards
+                for r in range(world):
+                    rlo, rhi = _dist.shard_bounds(C, world, r)
+                    k = rhi - rlo
+                    kg_v[:, rlo:rhi] = recv[r, :, :k]
+                    if need_grad:
+                        dX_v[:, rlo:rhi] = recv[r, :, rows: rows + k * d].reshape(M, k, d)
+            t0 = _mark("all_gather+assemble", t0, dev)
         else:
-            res, packed = buf, False
+            res = buf.view(-1)  # rows == C: already [kg (C) | dX (C, d)] per objective
         if on_host and res.is_cuda:
             host = _scratch.pinned_next(tuple(res.shape))
             host.copy_(res, non_blocking=True)
@@ -145,11 +149,11 @@ def evaluate_objectives(
             t0 = _mark("d2h+sync", t0, dev)
         elif not on_host and not res.is_cuda:
             res = res.to(dev)
-    # views into the one result block (possibly non-contiguous)
-    if packed:  # (C, M, width)
-        kg = res[:, :, 0].t()
-        dX = res[:, :, 1:].permute(1, 0, 2) if need_grad else None
-    else:       # (M, rows * width) with rows == C
+    if shard:
+        kg = res[: M * C].view(M, C)
+        dX = res[M * C:].view(M, C, d) if need_grad else None
+    else:
+        res = res.view(M, C * width)
         kg = res[:, :C]
         dX = res[:, C:].view(M, C, d) if need_grad else None
     return kg, dX

@@ -463,17 +463,17 @@ def main():
                 "int8_mma_peak_top_s_measured": mma_peak,
                 "frac_vs_measured_int8_mma_peak": (int8_ops / (ms_g * 1e-3) / 1e12 / mma_peak) if mma_peak else None,
                 "frac_vs_nominal_int8_4500_top_s": int8_ops / (ms_g * 1e-3) / 1e12 / 4500.0,
-                "tensor_pipe_active_ncu": "see profiles/ (ncu sm__pipe_tensor_subpipe... of the same launch)",
                 "dgemm_peak_tflops": dgemm_peak,
                 "frac_vs_dgemm_peak": achieved / dgemm_peak,
                 "flops_per_launch": flops_total / max(n_g, 1),
                 "avg_launch_ms": ms_g / max(n_g, 1),
                 "share_of_step": ms_g / tot_prof if tot_prof > 0 else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this shape from
-                # the ncu --set full capture profiles/r01q_final_kernels_ncu.csv (60.3 MB + 489.5 MB; algorithmic:
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this shape from the
+                # ncu --set full capture profiles/r02e_emax_obj0_tilefilter_v1_ncu.csv (60.4 MB + 488.3 MB; algorithmic:
                 # 537 MB of product rows written once, digit planes served from L2)
-                "traffic": 549.8e6 if (n_cand == 4096 and N == 16384 and args.precision == "float64") else None,
-                "traffic_source": "profiles/r01q_final_kernels_ncu.csv (ncu --set full, one launch, c4 shape)",
+                "traffic": 548.7e6 if (n_cand == 4096 and N == 16384 and args.precision == "float64") else None,
+                "traffic_source": "profiles/r02e_emax_obj0_tilefilter_v1_ncu.csv (ncu --set full, one launch, c4 shape)",
+                "tensor_pipe_active_ncu_pct": 63.6 if (n_cand == 4096 and N == 16384 and args.precision == "float64") else None,
             }
         else:
             roofline = {

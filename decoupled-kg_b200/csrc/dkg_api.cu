@@ -869,7 +869,11 @@ static int forward_once(dkg_plan* p, const double* X, int C, double* kg, double*
         for (int k = 0; k < MAX_D; ++k) bw.ls[m][k] = o.ls[k];
       }
     }
-    { ProfScope ps(7, st); DKG_TRY(emax_hull(lb, sc, out, st)); }
+    // (survivors per set of the previous forward with gradients, read without synchronisation: a stale or
+    // torn value only changes which hull kernels are launched, never a result)
+    const double hint = (w.stats_pinned != nullptr && w.stats_pinned[0] >= 0 && w.spill_checked && w.last_C > 0)
+                            ? (double)w.stats_pinned[1] / ((double)w.last_C * S) : -1.0;
+    { ProfScope ps(7, st); DKG_TRY(emax_hull(lb, sc, out, st, hint)); }
     { ProfScope ps(8, st); DKG_TRY(emax_overflow(lb, sc, out, st)); }
     { ProfScope ps(9, st); DKG_TRY(emax_finalize(lb, out, bw, st)); }
   }

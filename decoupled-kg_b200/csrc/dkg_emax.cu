@@ -1533,8 +1533,11 @@ __device__ __forceinline__ bool higher_intercept(const Line& p, const Line& q) {
 // ------------------------------------------------------------------------------------------
 // hull kernel: one warp per set
 // ------------------------------------------------------------------------------------------
+constexpr int HS_G = 8;       // lanes per set in hull_short_kernel
+constexpr int HS_LINES = 32;  // lines such a group holds in registers (4 per lane)
+
 __global__ void __launch_bounds__(E_THREADS, HULL_CTAS)
-hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
+hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out, int skip_short) {
   __shared__ double s_a[E_THREADS / 32][STAGE_CAP];
   __shared__ double s_b[E_THREADS / 32][STAGE_CAP];
   __shared__ int s_i[E_THREADS / 32][STAGE_CAP];
@@ -1579,6 +1582,7 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
   seeds[nseed++] = lb.Aarg[am_index(lb, c, j)];
   if (lb.a_own != nullptr) seeds[nseed++] = lb.NA;
   const int total = cnt + nseed;
+  if (skip_short && total <= HS_LINES) return;  // hull_short_kernel finishes these, four to a warp
   const double w = s.w;
   auto fetch_global = [&](int k) -> Line {
     if (k < cnt) {
@@ -1699,11 +1703,151 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
   }
 }
 
-int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cudaStream_t st) {
+// Short sets (survivors + seeds <= 32 lines: most sets of a well-filtered batch): a warp per set leaves
+// three quarters of the lanes without a line.  Here 8 lanes share a set (4 lines per lane in registers),
+// four sets per warp advance in lock-step through the same exact march; the Phi / phi evaluations of a
+// set's vertices are batched (8 per group) and deferred to one flush at the end wherever possible.
+__global__ void __launch_bounds__(E_THREADS, 3)
+hull_short_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, gl = lane & (HS_G - 1);
+  const long long nsets = (long long)lb.C * lb.S;
+  const long long set_ll = ((long long)blockIdx.x * (E_THREADS / 32) + (threadIdx.x >> 5)) * (32 / HS_G) + (lane / HS_G);
+  const bool in_range = set_ll < nsets;
+  const size_t set = in_range ? (size_t)set_ll : 0;
+  const int c = (int)(set / lb.S);
+  const int j = (int)(set - (size_t)c * lb.S);
+  const SetInfo s = set_info(lb, sc, c, j);
+  const int cnt = sc.surv_cnt[set];
+  int seeds[4];
+  int nseed = 0;
+  seeds[nseed++] = s.iP;
+  seeds[nseed++] = s.iQ;
+  seeds[nseed++] = lb.Aarg[am_index(lb, c, j)];
+  if (lb.a_own != nullptr) seeds[nseed++] = lb.NA;
+  const int total = cnt + nseed;
+  bool active = in_range && !s.shortcut && cnt <= SURV_CAP && total <= HS_LINES;  // (group-uniform)
+  const double w = s.w;
+  const SurvEntry* list = sc.surv + set * SURV_CAP;
+  Line cache[HS_LINES / HS_G];
+#pragma unroll
+  for (int r = 0; r < HS_LINES / HS_G; ++r) {
+    const int k = gl + HS_G * r;
+    cache[r] = empty_line();
+    if (active && k < total) {
+      if (k < cnt) {
+        const SurvEntry e = list[k];
+        cache[r] = make_line(lb, w, e.a, e.z, e.idx);
+      } else {
+        cache[r] = gather_line(lb, c, j, w, seeds[k - cnt]);
+      }
+    }
+  }
+  // first line of the sorted order (:371-374)
+  Line cur = empty_line();
+#pragma unroll
+  for (int r = 0; r < HS_LINES / HS_G; ++r)
+    if (cache[r].idx >= 0 && (cur.idx < 0 || sorted_before(cache[r], cur))) cur = cache[r];
+#pragma unroll
+  for (int o = HS_G / 2; o > 0; o >>= 1) {
+    const Line oth = shfl_line(cur, o);
+    if (oth.idx >= 0 && (cur.idx < 0 || sorted_before(oth, cur))) cur = oth;
+  }
+  Recorder rec{&out, set, lb.NL};
+  double E = 0.0, carry_cdf = 0.0, carry_pdf = 0.0;
+  int h = 0, hbase = 0;      // vertices found / already flushed
+  Line mine = empty_line();  // vertex hbase + gl of this group's current batch
+  double mine_x = INFINITY;
+  bool finished = false;     // the march of this group has ended; its last batch waits for the final flush
+  int fin_cnt = 0;
+
+  // evaluates Phi / phi for the batches of the groups with `go` (cnt_b vertices each) and folds them in
+  auto flush = [&](bool go, int cnt_b, bool is_last) {
+    const bool act = go && gl < cnt_b;
+    const double cdf = act ? std_normal_cdf(mine_x) : 0.0;
+    const double pdf = act ? std_normal_pdf(mine_x) : 0.0;
+    double lcdf = __shfl_up_sync(full, cdf, 1, HS_G);
+    double lpdf = __shfl_up_sync(full, pdf, 1, HS_G);
+    if (gl == 0) { lcdf = carry_cdf; lpdf = carry_pdf; }
+    const double dP = cdf - lcdf, dp = pdf - lpdf;
+    const double term = act ? __dsub_rn(__dmul_rn(mine.a, dP), __dmul_rn(mine.b, dp)) : 0.0;
+    if (act) {
+      rec.store_inline(hbase + gl, mine, dP, -dp, mine_x, is_last && gl == cnt_b - 1);
+      rec.dense(mine, dP, -dp);
+    }
+#pragma unroll
+    for (int k = 0; k < HS_G; ++k) {
+      const double t = __shfl_sync(full, term, k, HS_G);
+      if (go && k < cnt_b) E += t;  // in hull order, as a sequential sum
+    }
+    const int last_lane = go ? cnt_b - 1 : 0;
+    const double cc = __shfl_sync(full, cdf, last_lane, HS_G), pp = __shfl_sync(full, pdf, last_lane, HS_G);
+    if (go) {
+      carry_cdf = cc;
+      carry_pdf = pp;
+      hbase += cnt_b;
+      mine = empty_line();
+      mine_x = INFINITY;
+    }
+  };
+
+  while (__any_sync(full, active)) {
+    Next best;
+    best.L = empty_line();
+    best.x = INFINITY;
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < HS_LINES / HS_G; ++r) consider_next(best, cur, cache[r]);
+    }
+#pragma unroll
+    for (int o = HS_G / 2; o > 0; o >>= 1) {  // earliest intersection; ties -> earliest line in the sorted order
+      Next oth;
+      oth.L = shfl_line(best.L, o);
+      oth.x = __shfl_xor_sync(full, best.x, o);
+      merge_next(best, oth);
+    }
+    const bool last = best.L.idx < 0;
+    const int slot = h - hbase;
+    if (active && gl == slot) { mine = cur; mine_x = last ? INFINITY : best.x; }
+    if (active) ++h;
+    const bool batch_full = active && !last && slot == HS_G - 1;
+    if (__any_sync(full, batch_full)) flush(batch_full, HS_G, false);
+    if (active && last) {
+      active = false;
+      finished = true;
+      fin_cnt = slot + 1;
+    } else if (active) {
+      cur = best.L;
+    }
+  }
+  if (__any_sync(full, finished)) {
+    flush(finished, fin_cnt, true);
+    if (finished && gl == 0) {
+      finish_set(lb, out, set, s, E, h);
+      if (sc.stats) {
+        atomicAdd((unsigned long long*)&sc.stats[1], (unsigned long long)cnt);
+        atomicAdd((unsigned long long*)&sc.stats[3], (unsigned long long)h);
+      }
+    }
+  }
+}
+
+int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cudaStream_t st, double survivors_hint) {
   const long long sets = (long long)lb.C * lb.S;
   if (sets == 0) return DKG_OK;
   const int wpb = E_THREADS / 32;
-  hull_kernel<<<(unsigned)((sets + wpb - 1) / wpb), E_THREADS, 0, st>>>(lb, sc, out);
+  const char* e = getenv("DKG_HULL_SHORT");
+  // hull records beyond the inline capacity go through the warp-wide recorder of hull_kernel only
+  // measured at c4: with ~9 survivors per set the 8-lane kernel takes the hull stage from 0.227 to 0.182 ms; with
+  // ~32 per set (a third of the sets short) the extra launch costs more than it saves (0.385 -> 0.409 ms)
+  const bool use_short = !(e != nullptr && atoi(e) == 0) && (survivors_hint < 0.0 || survivors_hint <= 16.0) &&
+                         (out.hull_cap >= HS_LINES || (out.hull_idx == nullptr && out.hull_x == nullptr));
+  if (use_short) {
+    const long long per_cta = (long long)wpb * (32 / HS_G);
+    hull_short_kernel<<<(unsigned)((sets + per_cta - 1) / per_cta), E_THREADS, 0, st>>>(lb, sc, out);
+    DKG_LAUNCH_CHECK();
+  }
+  hull_kernel<<<(unsigned)((sets + wpb - 1) / wpb), E_THREADS, 0, st>>>(lb, sc, out, use_short ? 1 : 0);
   DKG_LAUNCH_CHECK();
   return DKG_OK;
 }

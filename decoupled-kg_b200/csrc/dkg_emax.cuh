@@ -167,7 +167,10 @@ int emax_zstat_from_partials(const LineBatch& lb, const EmaxScratch& sc, int nti
 // ztile_valid: sc.ztile holds the per-tile slope ranges of this batch (written by emax_zstat)
 int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st, bool ztile_valid = false);
 // warp-per-set exact hull + closed-form expectation; sets it cannot finish go to the queue
-int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cudaStream_t st);
+// survivors_hint: average survivors per set seen by an earlier forward of the same plan (< 0: unknown); only
+// steers which kernels are launched (8-lane groups for short sets or not) -- the results are identical
+int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cudaStream_t st,
+              double survivors_hint = -1.0);
 // CTA-per-set cooperative path for the queued sets (any input; always terminates)
 int emax_overflow(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cudaStream_t st);
 // kg[c] = mean_j terms[c, j] and, if bw.dX, the fused envelope-theorem backward

@@ -135,7 +135,7 @@ static int ensure_workspace(dkg_plan* p, int C) {
   if (const char* e = getenv("DKG_CHUNK_MB")) chunk_mb = atof(e);
   double per_row = (double)p->ldz * sizeof(double) +
                    (double)p->S * (SURV_CAP * sizeof(SurvEntry) + HULL_CAP * 20.0 + 64.0);
-  if (coupled) per_row += (double)p->ldz * sizeof(double) * (p->M + p->S);
+  if (coupled) per_row += (double)p->ldz * sizeof(double) * p->M;  // M covariance rows; the S slope rows are not materialised
   long long rows = (long long)(chunk_mb * 1048576.0 / per_row);
   int chunk = (int)(rows / GEMM_BM) * GEMM_BM;
   if (chunk < GEMM_BM) chunk = GEMM_BM;
@@ -184,7 +184,7 @@ static int ensure_workspace(dkg_plan* p, int C) {
       DKG_TRY(dev_alloc(&w.COVm[m], (size_t)chunk * p->ldz));
     }
     DKG_TRY(dev_alloc(&w.sdj, (size_t)cap * S));
-    DKG_TRY(dev_alloc(&w.Zc, (size_t)chunk * S * p->ldz));
+    if (getenv("DKG_COUPLED_ROWS") != nullptr) DKG_TRY(dev_alloc(&w.Zc, (size_t)chunk * S * p->ldz));  // (old materialised form, for comparison)
   }
   DKG_TRY(dev_alloc(&w.surv_cnt, (size_t)chunk * S));
   { SurvEntry* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * S * SURV_CAP, false)); w.surv = t; }
@@ -233,7 +233,7 @@ static void destroy_plan(dkg_plan* p) {
     dev_free(o.xs); dev_free(o.alpha); dev_free(o.resid); dev_free(o.chol); dev_free(o.Kinv); dev_free(o.Kmat); dev_free(o.Kxd_dig); dev_free(o.Kxd_scale); dev_free(o.B); dev_free(o.Kxd);
     dev_free(o.BT); dev_free(o.xd_s);
   }
-  dev_free(p->W); dev_free(p->wt); dev_free(p->xd); dev_free(p->alpha_all);
+  dev_free(p->W); dev_free(p->W2); dev_free(p->wt); dev_free(p->xd); dev_free(p->alpha_all);
   dev_free(p->mu_disc); dev_free(p->A0); dev_free(p->A0f); dev_free(p->A0max); dev_free(p->A0arg);
   dev_free(p->A0tmax); dev_free(p->perm);
   free_workspace(p->ws);
@@ -488,6 +488,7 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
   if (rc == DKG_OK) {
     // scalarised intercept table
     rc = dev_alloc(&p->W, (size_t)S * M);
+    if (rc == DKG_OK) rc = dev_alloc(&p->W2, (size_t)S * M);
     if (rc == DKG_OK) rc = dev_alloc(&p->wt, (size_t)S);
     if (rc == DKG_OK) rc = dev_alloc(&p->A0, (size_t)S * p->N_pad);
     if (rc == DKG_OK) rc = dev_alloc(&p->A0f, (size_t)S * p->N_pad);
@@ -496,7 +497,10 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
     if (rc == DKG_OK) {
       double wt_host[MAX_S];
       for (int j = 0; j < S; ++j) wt_host[j] = tgt >= 0 ? p->W_host[j * M + tgt] : 1.0;
+      double w2_host[MAX_S * MAX_M];
+      for (int e = 0; e < S * M; ++e) w2_host[e] = p->W_host[e] * p->W_host[e];
       cudaMemcpyAsync(p->W, p->W_host, sizeof(double) * S * M, cudaMemcpyHostToDevice, st);
+      cudaMemcpyAsync(p->W2, w2_host, sizeof(double) * S * M, cudaMemcpyHostToDevice, st);
       cudaMemcpyAsync(p->wt, wt_host, sizeof(double) * S, cudaMemcpyHostToDevice, st);
       cudaStreamSynchronize(st);  // wt_host is a stack buffer
       rc = build_a0(p->mu_disc, N, M, p->W, S, p->A0, p->A0f, p->N_pad, p->A0max, p->A0arg, st);
@@ -914,7 +918,7 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
     const int cc_pad = round_up(cc, GEMM_BM);
     CoupledArgs ca;
     ca.C = cc; ca.S = S; ca.M = M; ca.d = d; ca.N = N; ca.ldz = p->ldz;
-    ca.W = p->W; ca.sdj = w.sdj + (size_t)c0 * S; ca.Zc = w.Zc;
+    ca.W = p->W; ca.W2 = p->W2; ca.sdj = w.sdj + (size_t)c0 * S; ca.Zc = w.Zc;  // Zc == nullptr: statistics only
     ca.zpv = w.zpv; ca.zpi = w.zpi;
     for (int m = 0; m < M; ++m) {
       const ObjState& o = p->obj[m];
@@ -936,6 +940,10 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
 
     LineBatch lb;
     lb.Z = w.Zc; lb.ldz = p->ldz;
+    if (w.Zc == nullptr) {  // slopes formed on the fly from the covariance rows (line_slope)
+      lb.cov_M = M; lb.cov_w2 = p->W2; lb.cov_sd = ca.sdj;
+      for (int m = 0; m < M; ++m) lb.cov[m] = w.COVm[m];
+    }
     lb.A = p->A0; lb.a_sc = 0; lb.a_sj = p->N_pad;
     lb.A32 = p->A0f;
     lb.A32tmax = p->A0tmax; lb.a32_tiles = p->a0_tiles;
@@ -950,7 +958,7 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
     sc.stats = w.stats;
     sc.spill_used = w.spill_used;
     sc.zpv = w.zpv; sc.zpi = w.zpi;
-    { ProfScope ps(5, st); DKG_TRY(emax_zstat_from_partials(lb, sc, (N + 1 + CS_TILE_LINES - 1) / CS_TILE_LINES, st)); }
+    { ProfScope ps(5, st); DKG_TRY(emax_zstat_from_partials(lb, sc, coupled_stat_segments(N, w.Zc != nullptr), st)); }
     { ProfScope ps(6, st); DKG_TRY(emax_filter(lb, sc, st)); }
     EmaxOut out;
     out.terms = w.kg_terms + (size_t)c0 * S;
@@ -969,10 +977,11 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
     { ProfScope ps(8, st); DKG_TRY(emax_overflow(lb, sc, out, st)); }
     CoupledBackward bw;
     if (dX != nullptr) {
-      bw.dX = dX + (size_t)c0 * d; bw.X = X + (size_t)c0 * d; bw.W = p->W; bw.Zc = w.Zc;
+      bw.dX = dX + (size_t)c0 * d; bw.X = X + (size_t)c0 * d; bw.W = p->W; bw.W2 = p->W2;
       bw.sdj = w.sdj + (size_t)c0 * S; bw.ldz = p->ldz; bw.M = M; bw.d = d; bw.S = S; bw.N = N;
       for (int m = 0; m < M; ++m) {
         const ObjState& o = p->obj[m];
+        bw.COV[m] = w.COVm[m];
         bw.T[m] = w.Tm[m] + (size_t)c0 * o.ldk; bw.ldk[m] = o.ldk; bw.BT[m] = o.BT; bw.n_pad[m] = o.n_pad; bw.ldbt[m] = o.ldbt;
         bw.xd_s[m] = o.xd_s; bw.xs[m] = o.xs; bw.alpha[m] = o.alpha; bw.ntr[m] = o.n; bw.kind[m] = o.kernel;
         bw.outputscale[m] = o.outputscale; bw.y_std[m] = o.y_std;

@@ -44,7 +44,7 @@ coupled_slopes_kernel(CoupledArgs a) {
         const double w = a.W[j * a.M + m];
         s += (w * w) * cov[m];
       }
-    a.Zc[((size_t)c * a.S + j) * a.ldz + n] = s / a.sdj[(size_t)c * a.S + j];
+    if (a.Zc != nullptr) a.Zc[((size_t)c * a.S + j) * a.ldz + n] = s / a.sdj[(size_t)c * a.S + j];
   }
 }
 
@@ -71,31 +71,21 @@ coupled_slopes_stats_kernel(CoupledArgs a, int nseg) {
   for (int j = 0; j < a.S; ++j) {
     double w2[MAX_M];
 #pragma unroll
-    for (int m = 0; m < MAX_M; ++m) {
-      const double w = m < a.M ? a.W[j * a.M + m] : 0.0;
-      w2[m] = w * w;
-    }
+    for (int m = 0; m < MAX_M; ++m) w2[m] = m < a.M ? a.W2[j * a.M + m] : 0.0;
     const size_t row = (size_t)c * a.S + j;
     const double sd = a.sdj[row];
     const double rinv = 1.0 / sd;
-    const bool fast = sd > 1e-290 && sd < 1e290;  // otherwise: plain division (same special values)
-    double* zrow = a.Zc + row * a.ldz + n_lo;
+    double* zrow = a.Zc != nullptr ? a.Zc + row * a.ldz + n_lo : nullptr;  // nullptr: statistics only
     double vmin = INFINITY, vmax = -INFINITY;
     int imin = 0x7fffffff, imax = 0x7fffffff;
 #pragma unroll 4
     for (int i = lane; i < n_cnt; i += 32) {
-      double s = 0.0;
+      double s = 0.0;  // (same fma order and quotient as line_slope(): identical bits in every stage)
 #pragma unroll
       for (int m = 0; m < MAX_M; ++m)
-        if (m < a.M) s += w2[m] * s_cov[m * CS_TILE_LINES + i];
-      double z;
-      if (fast) {
-        const double q = s * rinv;
-        z = fma(fma(-q, sd, s), rinv, q);
-      } else {
-        z = s / sd;
-      }
-      zrow[i] = z;
+        if (m < a.M) s = fma(w2[m], s_cov[m * CS_TILE_LINES + i], s);
+      const double z = coupled_quotient(s, sd, rinv);
+      if (zrow != nullptr) zrow[i] = z;
       if (z < vmin) { vmin = z; imin = n_lo + i; }
       if (z > vmax) { vmax = z; imax = n_lo + i; }
     }
@@ -115,10 +105,113 @@ coupled_slopes_stats_kernel(CoupledArgs a, int nseg) {
   }
 }
 
+// Statistics only (the slope rows are not materialised).  Every warp owns CST_SEG lines of one candidate and
+// keeps the M covariance segments in REGISTERS (CST_SEG / 32 lines per lane); per scalarisation the lane-local
+// min / max of the numerator  s = sum_m w2[j, m] cov_m[n]  costs M fp64 FMAs, two compares and the selects --
+// the quotient is monotone in s (correctly rounded, sd > 0), so it is taken once per (segment, scalarisation) on
+// the reduced value instead of once per line.  The 32 lane-local results of 16 scalarisations x {min, max} are
+// transposed through shared memory: lane k reduces quantity k over the 32 lanes (one pass over 32 padded rows)
+// instead of 16 x 2 five-step shuffle butterflies, which were half of the instructions of the fused
+// assembly + statistics kernel above.
+constexpr int CST_WARPS = 4;
+constexpr int CST_PITCH = 33;  // padded row of the transpose buffer (conflict-free column reads)
+
+template <int MT>
+__global__ void __launch_bounds__(CST_WARPS * 32)
+coupled_stats_kernel(CoupledArgs a, int nseg) {
+  extern __shared__ __align__(16) unsigned char c_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = blockIdx.x * CST_WARPS + warp, c = blockIdx.y;
+  if (seg >= nseg) return;  // (no CTA barrier below: warps are independent)
+  constexpr int E = CST_SEG / 32;
+  double* s_v = reinterpret_cast<double*>(c_smem) + (size_t)warp * (32 * CST_PITCH);
+  int* s_i = reinterpret_cast<int*>(reinterpret_cast<double*>(c_smem) + (size_t)CST_WARPS * 32 * CST_PITCH) +
+             (size_t)warp * (32 * CST_PITCH);
+  const int n_lo = seg * CST_SEG + lane;
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  double cov[MT][E];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int n = n_lo + e * 32;  // column N is the candidate's own line; beyond it: NaN (never selected)
+      cov[m][e] = (m < a.M && n <= a.N) ? a.COV[m][(size_t)c * a.ldz + n] : (m == 0 ? qnan : 0.0);
+    }
+  for (int jb = 0; jb < a.S; jb += 16) {
+#pragma unroll 1
+    for (int jj = 0; jj < 16; ++jj) {
+      const int j = jb + jj;
+      double vmin = INFINITY, vmax = -INFINITY;
+      int emin = 0x7fffffff, emax = 0x7fffffff;
+      if (j < a.S) {
+        double w2[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) w2[m] = m < a.M ? a.W2[j * a.M + m] : 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          double s = 0.0;  // (same fma order as line_slope(): identical bits in every stage)
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+            if (m < a.M) s = fma(w2[m], cov[m][e], s);
+          if (s < vmin) { vmin = s; emin = e; }
+          if (s > vmax) { vmax = s; emax = e; }
+        }
+      }
+      s_v[jj * CST_PITCH + lane] = vmin;
+      s_i[jj * CST_PITCH + lane] = emin == 0x7fffffff ? emin : n_lo + emin * 32;
+      s_v[(16 + jj) * CST_PITCH + lane] = vmax;
+      s_i[(16 + jj) * CST_PITCH + lane] = emax == 0x7fffffff ? emax : n_lo + emax * 32;
+    }
+    __syncwarp();
+    {  // lane k < 16: min of scalarisation jb + k; lane 16 + k: its max (first index wins ties)
+      const bool is_max = lane >= 16;
+      const double* rv = s_v + lane * CST_PITCH;
+      const int* ri = s_i + lane * CST_PITCH;
+      double v = rv[0];
+      int i = ri[0];
+#pragma unroll 8
+      for (int l = 1; l < 32; ++l) {
+        const double ov = rv[l];
+        const int oi = ri[l];
+        const bool better = (is_max ? ov > v : ov < v) || (ov == v && oi < i);
+        if (better) { v = ov; i = oi; }
+      }
+      const int j = jb + (lane & 15);
+      if (j < a.S) {
+        const size_t row = (size_t)c * a.S + j;
+        const double sd = a.sdj[row];
+        const size_t q = (row * nseg + seg) * 2 + (is_max ? 1 : 0);
+        a.zpv[q] = coupled_quotient(v, sd, 1.0 / sd);
+        a.zpi[q] = i;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+int coupled_stat_segments(int N, bool materialised) {
+  return ceil_div(N + 1, materialised ? CS_TILE_LINES : CST_SEG);
+}
+
+template <int MT>
+static int launch_coupled_stats(const CoupledArgs& a, cudaStream_t st) {
+  const int nseg = coupled_stat_segments(a.N, false);
+  const size_t smem = (size_t)CST_WARPS * 32 * CST_PITCH * (sizeof(double) + sizeof(int));
+  DKG_CUDA_OK(cudaFuncSetAttribute(coupled_stats_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  coupled_stats_kernel<MT><<<dim3(ceil_div(nseg, CST_WARPS), a.C), CST_WARPS * 32, smem, st>>>(a, nseg);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
 int coupled_slopes(const CoupledArgs& a, cudaStream_t st) {
   if (a.C == 0) return DKG_OK;
   coupled_sd_kernel<<<ceil_div(a.C * a.S, CP_THREADS), CP_THREADS, 0, st>>>(a);
   DKG_LAUNCH_CHECK();
+  if (a.Zc == nullptr && a.zpv != nullptr && a.zpi != nullptr) {
+    if (a.M <= 2) return launch_coupled_stats<2>(a, st);
+    if (a.M <= 4) return launch_coupled_stats<4>(a, st);
+    return launch_coupled_stats<MAX_M>(a, st);
+  }
   if (a.zpv != nullptr && a.zpi != nullptr) {
     const int nseg = ceil_div(a.N + 1, CS_TILE_LINES);
     const int nwarp = CP_THREADS / 32;
@@ -227,14 +320,22 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
         const double w = bw.W[j * M + m];
         const double sd = bw.sdj[set];
         const double om = (w * w) / sd;
-        const double* zrow = bw.Zc + set * (size_t)bw.ldz;
+        double w2j[MAX_M];
+#pragma unroll
+        for (int mm = 0; mm < MAX_M; ++mm) w2j[mm] = mm < M ? bw.W2[j * M + mm] : 0.0;
+        const double rinv = 1.0 / sd;
+        auto slope = [&](int n) {  // b_jn, formed as everywhere else (line_slope)
+          double sacc = 0.0;
+          for (int mm = 0; mm < M; ++mm) sacc = fma(w2j[mm], bw.COV[mm][(size_t)c * bw.ldz + n], sacc);
+          return coupled_quotient(sacc, sd, rinv);
+        };
         double qb = 0.0;  // sum_n (q / S) b_jn
         HullReader rd(out, set);
         for (int k = 0; k < h; ++k) {
           if (!rd.seek(k)) { s_broken = 1; break; }
           const int idx = rd.idx();
           const double qs = rd.q() * invS;
-          qb += qs * zrow[idx];
+          qb += qs * slope(idx);
           if (idx == NA) {
             gzown += om * qs;
           } else {

@@ -452,7 +452,7 @@ __device__ double4 chain_params(const LineBatch& lb, const EmaxScratch& sc, int 
   const double zP = sgn > 0 ? s.zmin : -s.zmax;
   const double zQ = sgn > 0 ? s.zmax : -s.zmin;
   const double aT = s.amax;
-  const double zT = sgn * lb.Z[(size_t)c * lb.ldz + s.iT];
+  const double zT = sgn * line_slope(lb, c, s.iT);
   const double aP = line_intercept(lb, c, j, iP);
   const double aQ = line_intercept(lb, c, j, iQ);
   if (mag != nullptr) {
@@ -522,7 +522,7 @@ __device__ __forceinline__ unsigned long long append_survivor(const LineBatch& l
                                                               const double4& par, size_t set, int c,
                                                               int j, int n, int pos, int* side_out) {
   const double av = lb.A[a_base(lb, c, j) + n];
-  const double zv = lb.Z[(size_t)c * lb.ldz + n];
+  const double zv = line_slope(lb, c, n);
   if (pos < SURV_CAP) {
     SurvEntry e;
     e.a = av; e.z = zv; e.idx = n; e.pad = 0;
@@ -571,7 +571,7 @@ filter_kernel(LineBatch lb, EmaxScratch sc) {
   for (int g = 0; g < G; ++g) {
     const int c = min(c0 + g, lb.C - 1);
 #pragma unroll
-    for (int r = 0; r < R; ++r) z[g][r] = lb.Z[(size_t)c * lb.ldz + nc[r]];
+    for (int r = 0; r < R; ++r) z[g][r] = line_slope(lb, c, nc[r]);
   }
   double a_nx[R];  // intercepts of the NEXT scalarisation (software prefetch, SHARED_A only)
   if (SHARED_A) {
@@ -730,7 +730,7 @@ __device__ __forceinline__ void flush_warp_pool(const LineBatch& lb, const EmaxS
     const size_t set = (size_t)c * S + j;
     const int n = it.x;
     const double av = lb.A[a_base(lb, c, j) + n];
-    const double zv = lb.Z[(size_t)c * lb.ldz + n];
+    const double zv = line_slope(lb, c, n);
     const double4 par = sc.chain[set];
     const double t1 = fma(par.y, zv, par.x), t2 = fma(par.w, zv, par.z);
     const int side = t1 <= t2 ? 0 : 1;
@@ -775,7 +775,7 @@ chain5_kernel(LineBatch lb, EmaxScratch sc) {
     if (key != 0ull && pc != INFINITY) {
       const int nu = (int)(key & 0xffffffffull);
       const double au = lb.A[a_base(lb, c, j) + nu];
-      const double zu = lb.Z[(size_t)c * lb.ldz + nu];
+      const double zu = line_slope(lb, c, nu);
       const double4 v = sc.chainv[set * 2 + side];  // (z0, a0, z1, a1), raw slope coordinate
       if ((zu - v.x) * (v.z - zu) > 0.0) {          // U strictly between the chord's end points
         const double2 c0u = chord_through(v.x, v.y, zu, au), cu1 = chord_through(zu, au, v.z, v.w);
@@ -1100,9 +1100,26 @@ filter32_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb, int F32_JB)
   for (int g = 0; g < G; ++g) {
     double2 v0 = make_double2(0.0, 0.0), v1 = v0;
     if (live) {
-      const double* zr = lb.Z + (size_t)min(c0 + g, lb.C - 1) * lb.ldz + n0;
-      v0 = *reinterpret_cast<const double2*>(zr);
-      v1 = *reinterpret_cast<const double2*>(zr + 2);
+      const int row = min(c0 + g, lb.C - 1);
+      if (ROWS && lb.cov_M > 0) {
+        // coupled rows are not materialised: 4 slopes from the M covariance rows of this row's candidate
+        const int cc = row / lb.row_mod, jj = row - cc * lb.row_mod;
+        double s4[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int m = 0; m < lb.cov_M; ++m) {
+          const double w2 = lb.cov_w2[jj * lb.cov_M + m];
+          const double* cr = lb.cov[m] + (size_t)cc * lb.ldz + n0;
+          const double2 c0v = *reinterpret_cast<const double2*>(cr), c1v = *reinterpret_cast<const double2*>(cr + 2);
+          s4[0] = fma(w2, c0v.x, s4[0]); s4[1] = fma(w2, c0v.y, s4[1]);
+          s4[2] = fma(w2, c1v.x, s4[2]); s4[3] = fma(w2, c1v.y, s4[3]);
+        }
+        const double sd = lb.cov_sd[row], rinv = 1.0 / sd;
+        v0 = make_double2(coupled_quotient(s4[0], sd, rinv), coupled_quotient(s4[1], sd, rinv));
+        v1 = make_double2(coupled_quotient(s4[2], sd, rinv), coupled_quotient(s4[3], sd, rinv));
+      } else {
+        const double* zr = lb.Z + (size_t)row * lb.ldz + n0;
+        v0 = *reinterpret_cast<const double2*>(zr);
+        v1 = *reinterpret_cast<const double2*>(zr + 2);
+      }
     }
     zp[g][0] = pack_f32x2(__double2float_rn(v0.x), __double2float_rn(v0.y));
     zp[g][1] = pack_f32x2(__double2float_rn(v1.x), __double2float_rn(v1.y));
@@ -1211,6 +1228,156 @@ static int launch_filter32(const LineBatch& lb, const EmaxScratch& sc, cudaStrea
   return DKG_OK;
 }
 
+// ---- coupled path, slope rows not materialised --------------------------------------------------
+// The rows of one candidate (one per scalarisation) are all linear combinations of the same M covariance
+// rows, so a CTA takes FC_CG candidates x 512 lines, every thread keeps the covariance values of its 4
+// consecutive lines in registers (FC_CG x M x 4 doubles) and walks the scalarisations two at a time: the
+// slope is M fp64 FMAs and one multiplication by 1 / sd (the float image of s * RN(1 / sd) differs from the
+// float image of the correctly rounded quotient by at most 2^-52 |z| beyond its own 2^-24 |z| rounding -- far
+// inside the 3.9 * 2^-24 margin chord32() leaves), the float intercepts of a scalarisation are loaded once
+// for both candidates, and the test is the packed float test of filter32_kernel.  Survivors are re-formed
+// exactly (line_slope) when they are written out, so the hull stage sees the same bits as every other stage.
+constexpr int FC_CG = 2;  // candidates per CTA
+constexpr int FC_JG = 2;  // scalarisations per step
+
+template <int MT, bool REFINE>
+__global__ void __launch_bounds__(F32_THREADS, 4)
+filter32_cov_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb) {
+  extern __shared__ __align__(16) unsigned char e_smem[];
+  const int SR = lb.row_mod, M = lb.cov_M;
+  const int ncand = lb.C / SR;
+  const int cbase = blockIdx.y * FC_CG;
+  const int row0 = cbase * SR;
+  const int nset = FC_CG * SR;                                                            // local sets: cl * SR + j
+  ulonglong2* s_p32 = reinterpret_cast<ulonglong2*>(e_smem);                              // [nset][2]
+  unsigned long long* s_far = reinterpret_cast<unsigned long long*>(s_p32 + 2 * nset);    // [nset][2]
+  double* s_ri = reinterpret_cast<double*>(s_far + 2 * nset);                             // [nset] 1 / sd
+  double* s_w2 = s_ri + nset;                                                             // [SR][MT]
+  int2* pool = reinterpret_cast<int2*>(s_w2 + SR * MT) + (threadIdx.x >> 5) * WPOOL;      // this warp's
+  const ulonglong2* g_p32 = reinterpret_cast<const ulonglong2*>(sc.chain32);
+  const ulonglong2 none = make_ulonglong2(0ull, 0x7f8000007f800000ull);  // (0, 0, +inf, +inf): nothing passes
+  for (int e = threadIdx.x; e < nset; e += blockDim.x) {
+    const bool in = cbase + e / SR < ncand;
+    s_p32[2 * e] = in ? g_p32[((size_t)row0 + e) * 2] : none;
+    s_p32[2 * e + 1] = in ? g_p32[((size_t)row0 + e) * 2 + 1] : none;
+    s_far[2 * e] = 0ull;
+    s_far[2 * e + 1] = 0ull;
+    s_ri[e] = in ? 1.0 / lb.cov_sd[row0 + e] : 0.0;
+  }
+  for (int e = threadIdx.x; e < SR * MT; e += blockDim.x) {
+    const int j = e / MT, m = e - j * MT;
+    s_w2[e] = m < M ? lb.cov_w2[j * M + m] : 0.0;
+  }
+  const int n0 = (line_block(blockIdx.x, blk_step, nsb, REFINE) * F32_THREADS + (int)threadIdx.x) * 4;
+  const bool live = n0 < lb.NA;  // lines n0..n0+3; beyond NA the float table holds -inf (never kept)
+  double cv[FC_CG][MT][4];
+#pragma unroll
+  for (int cl = 0; cl < FC_CG; ++cl)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      double2 v0 = make_double2(0.0, 0.0), v1 = v0;
+      if (live && m < M) {
+        const double* cr = lb.cov[m] + (size_t)min(cbase + cl, ncand - 1) * lb.ldz + n0;
+        v0 = *reinterpret_cast<const double2*>(cr);
+        v1 = *reinterpret_cast<const double2*>(cr + 2);
+      }
+      cv[cl][m][0] = v0.x; cv[cl][m][1] = v0.y; cv[cl][m][2] = v1.x; cv[cl][m][3] = v1.y;
+    }
+  const float ninf = -INFINITY;
+  const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+  int wcnt = 0;  // entries in this warp's pool (warp-uniform)
+  __syncthreads();
+
+  for (int j0 = 0; j0 < SR; j0 += FC_JG) {
+    unsigned mask = 0u;
+#pragma unroll
+    for (int jl = 0; jl < FC_JG; ++jl) {
+      const int j = min(j0 + jl, SR - 1);
+      float4 ag = make_float4(ninf, ninf, ninf, ninf);
+      if (live && j0 + jl < SR) ag = *reinterpret_cast<const float4*>(lb.A32 + (size_t)j * lb.a_sj + n0);
+      double w2[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) w2[m] = s_w2[j * MT + m];
+#pragma unroll
+      for (int cl = 0; cl < FC_CG; ++cl) {
+        const int setl = cl * SR + j;
+        const double ri = s_ri[setl];
+        float zf[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+            if (m < M) sacc = fma(w2[m], cv[cl][m][u], sacc);
+          zf[u] = __double2float_rn(sacc * ri);
+        }
+        const ulonglong2 q1 = s_p32[2 * setl], q2 = s_p32[2 * setl + 1];
+        constexpr unsigned B0 = 1u;  // bit layout: (jl * FC_CG + cl) * 4 + line
+        if (jl == 0 && cl == 0) {
+          mask = pair_test32<B0 << 0>(mask, q1.x, q1.y, q2.x, q2.y, pack_f32x2(zf[0], zf[1]), ag.x, ag.y);
+          mask = pair_test32<B0 << 2>(mask, q1.x, q1.y, q2.x, q2.y, pack_f32x2(zf[2], zf[3]), ag.z, ag.w);
+        } else if (jl == 0 && cl == 1) {
+          mask = pair_test32<B0 << 4>(mask, q1.x, q1.y, q2.x, q2.y, pack_f32x2(zf[0], zf[1]), ag.x, ag.y);
+          mask = pair_test32<B0 << 6>(mask, q1.x, q1.y, q2.x, q2.y, pack_f32x2(zf[2], zf[3]), ag.z, ag.w);
+        } else if (jl == 1 && cl == 0) {
+          mask = pair_test32<B0 << 8>(mask, q1.x, q1.y, q2.x, q2.y, pack_f32x2(zf[0], zf[1]), ag.x, ag.y);
+          mask = pair_test32<B0 << 10>(mask, q1.x, q1.y, q2.x, q2.y, pack_f32x2(zf[2], zf[3]), ag.z, ag.w);
+        } else {
+          mask = pair_test32<B0 << 12>(mask, q1.x, q1.y, q2.x, q2.y, pack_f32x2(zf[0], zf[1]), ag.x, ag.y);
+          mask = pair_test32<B0 << 14>(mask, q1.x, q1.y, q2.x, q2.y, pack_f32x2(zf[2], zf[3]), ag.z, ag.w);
+        }
+      }
+    }
+    for (;;) {  // survivors are rare (~1 % of the tests)
+      const unsigned vote = __ballot_sync(0xffffffffu, mask != 0u);
+      if (vote == 0u) break;
+      if (wcnt + 32 > WPOOL) {
+        flush_warp_pool<(1 << 20), REFINE>(lb, sc, pool, wcnt, row0, 0, s_far);
+        wcnt = 0;
+      }
+      if (mask) {
+        const int bit = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        const int slot = bit >> 2;  // jl * FC_CG + cl
+        pool[wcnt + __popc(vote & lt)] = make_int2(n0 + (bit & 3), (slot % FC_CG) * SR + j0 + slot / FC_CG);
+      }
+      wcnt += __popc(vote);
+    }
+  }
+  flush_warp_pool<(1 << 20), REFINE>(lb, sc, pool, wcnt, row0, 0, s_far);
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * nset; e += blockDim.x) {
+    const unsigned long long key = s_far[e];
+    if (key) atomicMax(&sc.far[((size_t)row0 + (e >> 1)) * 2 + (e & 1)], key);
+  }
+}
+
+template <int MT>
+static int launch_filter32_cov(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st) {
+  static_assert(FC_CG == 2 && FC_JG == 2, "bit layout of filter32_cov_kernel");
+  const int SR = lb.row_mod, ncand = lb.C / SR;
+  const int nblk = ceil_div(lb.NA, F32_THREADS * 4);
+  const unsigned gy = ceil_div(ncand, FC_CG);
+  const size_t smem = (size_t)FC_CG * SR * (2 * sizeof(ulonglong2) + 2 * sizeof(unsigned long long) + sizeof(double)) +
+                      (size_t)SR * MT * sizeof(double) + (F32_THREADS / 32) * WPOOL * sizeof(int2);
+  if (smem > 47 * 1024) {
+    DKG_CUDA_OK(cudaFuncSetAttribute(filter32_cov_kernel<MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DKG_CUDA_OK(cudaFuncSetAttribute(filter32_cov_kernel<MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  // (two phases as in launch_filter32: sampled line blocks, second-level chain, the rest)
+  const bool two_phase = sc.chain5 != nullptr && sc.chainv != nullptr && nblk >= 8;
+  const int nsb = two_phase ? 2 : nblk, step = two_phase ? nblk / 2 : 1;
+  filter32_cov_kernel<MT, false><<<dim3(nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
+  DKG_LAUNCH_CHECK();
+  if (two_phase) {
+    chain5_kernel<<<(unsigned)((lb.C + E_THREADS - 1) / E_THREADS), E_THREADS, 0, st>>>(lb, sc);
+    DKG_LAUNCH_CHECK();
+    filter32_cov_kernel<MT, true><<<dim3(nblk - nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
+    DKG_LAUNCH_CHECK();
+  }
+  return DKG_OK;
+}
+
 template <int G, int R>
 static int launch_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st) {
   dim3 grid(ceil_div(lb.NA, E_THREADS * R), ceil_div(lb.C, G));
@@ -1249,8 +1416,11 @@ int emax_filter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st, boo
   const int mode = fe == nullptr ? 0 : strcmp(fe, "f64") == 0 ? 1 : strcmp(fe, "f32") == 0 ? 2 : 0;
   if (mode != 1 && lb.A32 != nullptr && sc.chain32 != nullptr && lb.a_sc == 0 && (lb.row_mod == 0 || lb.S == 1) &&
       (lb.ldz & 1) == 0 && (lb.a_sj & 3) == 0 && lb.ldz >= ((lb.NA + 3) & ~3) && lb.a_sj >= ((lb.NA + 3) & ~3) &&
-      (ctas4 >= 148 || mode == 2))
+      (ctas4 >= 148 || mode == 2)) {
+    if (lb.cov_M > 0 && lb.cov_M <= 4 && lb.row_mod > 0 && lb.C % lb.row_mod == 0 && getenv("DKG_FILTER_COV") == nullptr)
+      return lb.cov_M <= 2 ? launch_filter32_cov<2>(lb, sc, st) : launch_filter32_cov<4>(lb, sc, st);
     return launch_filter32(lb, sc, st);
+  }
   if (getenv("DKG_FILTER_R8") && ctas4 >= 6 * 148) return launch_filter<4, 8>(lb, sc, st);
   if (ctas4 >= 3 * 148) return launch_filter<4, 4>(lb, sc, st);
   return launch_filter<4, 1>(lb, sc, st);
@@ -1293,7 +1463,7 @@ __device__ __forceinline__ Line make_line(const LineBatch& lb, double w, double 
 }
 
 __device__ __forceinline__ Line gather_line(const LineBatch& lb, int c, int j, double w, int idx) {
-  return make_line(lb, w, line_intercept(lb, c, j, idx), lb.Z[(size_t)c * lb.ldz + idx], idx);
+  return make_line(lb, w, line_intercept(lb, c, j, idx), line_slope(lb, c, idx), idx);
 }
 
 __device__ __forceinline__ Line shfl_line(const Line& L, int o) {
@@ -1956,7 +2126,7 @@ overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
         for (int u = 0; u < 4; ++u) {
           const int n = n0 + u * blockDim.x;
           const bool ok = n < lb.NL;
-          zq[u] = ok ? lb.Z[(size_t)c * lb.ldz + n] : 0.0;
+          zq[u] = ok ? line_slope(lb, c, n) : 0.0;
           aq[u] = ok ? line_intercept(lb, c, j, n) : -INFINITY;
         }
 #pragma unroll

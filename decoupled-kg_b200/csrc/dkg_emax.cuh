@@ -31,7 +31,34 @@ struct LineBatch {
   // row_mod > 0 (coupled path): every row is its own set (S == 1) and the shared intercept table /
   // maxima are indexed by (row % row_mod) -- rows are (candidate, scalarisation) pairs
   int row_mod = 0;
+  // cov_M > 0 (coupled path): the slope rows are NOT materialised (they were 8.6 GB per 4096 candidates at c4);
+  // the slope of line n in row (c, j) is formed on the fly from the M covariance rows of candidate c,
+  //   z = (sum_m w2[j, m] cov_m[c, n]) / sd[row]          (line_slope() in dkg_emax.cu; Z is unused)
+  int cov_M = 0;
+  const double* cov[MAX_M] = {};   // [C, ldz] covariance rows Cov_m(x_c, .); column NA = Cov_m(x_c, x_c)
+  const double* cov_w2 = nullptr;  // [row_mod, cov_M] squared scalarisation weights
+  const double* cov_sd = nullptr;  // [rows] sqrt of the scalarised noisy variance
 };
+
+#ifdef __CUDACC__
+// RN(s / sd) through the correctly rounded reciprocal and one residual step (Markstein); the SAME sequence
+// everywhere a coupled slope is formed, so that every stage sees identical bits
+__device__ __forceinline__ double coupled_quotient(double s, double sd, double rinv) {
+  if (sd > 1e-290 && sd < 1e290) {
+    const double q = s * rinv;
+    return fma(fma(-q, sd, s), rinv, q);
+  }
+  return s / sd;
+}
+__device__ __forceinline__ double line_slope(const LineBatch& lb, int row, int n) {
+  if (lb.cov_M == 0) return lb.Z[(size_t)row * lb.ldz + n];
+  const int c = row / lb.row_mod, j = row - c * lb.row_mod;
+  double s = 0.0;
+  for (int m = 0; m < lb.cov_M; ++m) s = fma(lb.cov_w2[j * lb.cov_M + m], lb.cov[m][(size_t)c * lb.ldz + n], s);
+  const double sd = lb.cov_sd[row];
+  return coupled_quotient(s, sd, 1.0 / sd);
+}
+#endif
 
 // one line that survived the streaming chord filter (intercept, raw slope coordinate, index)
 struct SurvEntry {
@@ -226,20 +253,25 @@ struct CoupledArgs {
   const double* COV[MAX_M] = {};    // [C, ldz] covariance rows (un-standardised); column N = Cov_m(x,x)
   const double* varn[MAX_M] = {};   // [C] noisy predictive variance of objective m (un-standardised)
   double* sdj = nullptr;            // [C, S] out: sqrt of the scalarised noisy variance
-  double* Zc = nullptr;             // [C * S, ldz] out: slope rows
+  double* Zc = nullptr;             // [C * S, ldz] out: slope rows (nullptr: statistics only, rows not materialised)
+  const double* W2 = nullptr;       // [S, M] squared weights (the table line_slope() reads)
   // optional: per-(row, tile) min / max of the finished slope rows (first index wins ties), so the row
   // statistics need no second pass over Zc; tile = CS_TILE_LINES consecutive entries of the N + 1
   double* zpv = nullptr;            // [C * S, tiles, 2]
   int* zpi = nullptr;               // [C * S, tiles, 2]
 };
-constexpr int CS_TILE_LINES = 256;  // one warp's segment
+constexpr int CS_TILE_LINES = 256;  // one warp's segment (materialised slope rows)
+constexpr int CST_SEG = 512;        // one warp's segment (statistics only: the covariance values stay in registers)
 int coupled_slopes(const CoupledArgs& a, cudaStream_t st);
+// segments per row of the partial statistics coupled_slopes() writes (input of emax_zstat_from_partials)
+int coupled_stat_segments(int N, bool materialised);
 
 struct CoupledBackward {
   double* dX = nullptr;             // [C, d]
   const double* X = nullptr;        // [C, d]
   const double* W = nullptr;        // [S, M]
-  const double* Zc = nullptr;       // [C * S, ldz]
+  const double* COV[MAX_M] = {};    // [C, ldz] covariance rows (the slopes are formed on the fly, see LineBatch)
+  const double* W2 = nullptr;       // [S, M] squared weights
   const double* sdj = nullptr;      // [C, S]
   int ldz = 0, M = 0, d = 0, S = 0, N = 0;
   const double* T[MAX_M] = {};      // [C, ldk_m]

@@ -126,6 +126,7 @@ struct dkg_plan {
   dkg::ObjState obj[dkg::MAX_M];
   double W_host[dkg::MAX_S * dkg::MAX_M];
   double* W = nullptr;        // [S, M]
+  double* W2 = nullptr;       // [S, M]  squared weights (coupled slopes)
   double* wt = nullptr;       // [S]  W[:, target]
   double* xd = nullptr;       // [N, d]      raw discretisation
   double* xd_s = nullptr;     // [N_pad, d]  discretisation / lengthscale_i (padding rows zero)

@@ -1040,7 +1040,12 @@ int dkg_plan_create(const dkg_objective* objs, int32_t M, int32_t d, const doubl
   dkg_plan* p = new (std::nothrow) dkg_plan();
   if (!p) { set_error("out of host memory"); return DKG_ENOMEM; }
   p->M = M; p->d = d; p->N = N; p->S = S; p->target = target_ix;
+  static_assert(OZ_DEFAULT_DIGITS == 7 && OZ_DEFAULT_DIAGONALS == 7, "dkg_plan's default digit configuration");
   if (flags & DKG_PLAN_FAST32) { p->cov_digits = 4; p->cov_diagonals = 4; }
+  else if (const char* e = getenv("DKG_OZ_DIAGONALS")) {  // measurement switch (8 = the round-1 cut-off)
+    const int v = atoi(e);
+    if (v >= 1 && v <= 2 * p->cov_digits - 1) p->cov_diagonals = v;
+  }
   p->N_pad = round_up(N, GEMM_BN);
   p->ldz = round_up(N + 1, 16);
   cudaGetDevice(&p->device);

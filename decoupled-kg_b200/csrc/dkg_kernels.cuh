@@ -65,7 +65,7 @@ int gemm_cov(const double* KX, int lda, const double* B, int ldb, int M_pad, int
 
 // ---- dkg_ozaki.cu ----------------------------------------------------------------------------
 constexpr int OZ_DEFAULT_DIGITS = 7;
-constexpr int OZ_DEFAULT_DIAGONALS = 8;
+constexpr int OZ_DEFAULT_DIAGONALS = 7;  // balanced digits: the dropped diagonals are zero-mean (see dkg_ozaki.cu)
 constexpr int OZ_MAX_K = 4096;
 int ozaki_kp(int K);
 size_t ozaki_digit_bytes(int rows_pad, int K, int NS);

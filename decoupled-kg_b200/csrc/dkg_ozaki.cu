@@ -7,17 +7,20 @@
 //
 // tcgen05.mma has no f64 kind, and the fp64 DMMA pipe of B200 tops out at 37 TFLOP/s.  The int8
 // kind runs at ~4.5 POP/s, so the product is evaluated with the Ozaki scheme: every row of T and
-// every column of Kxd is scaled by a power of two into (-128, 128) and cut into NS base-256
-// digits,
-//     x = d_0 + d_1 256^-1 + d_2 256^-2 + ...      d_0 = floor(x) in [-128, 127]  (signed),
-//                                                  d_s in [0, 255] for s >= 1     (unsigned),
-// which is EXACT in fp64 (floor / subtract / scale by 256) once x has been rounded to its last
-// digit (round-to-nearest, so the representation error is unbiased, <= 2^-56 of full scale).  Then
+// every column of Kxd is scaled by a power of two into [-127, 127], rounded to its last digit
+// (round-to-nearest: the representation error is unbiased, <= 2^-56 of full scale) and cut into NS
+// BALANCED base-256 digits,
+//     x = d_0 + d_1 256^-1 + d_2 256^-2 + ...      every d_s in [-128, 127]  (signed int8),
+// which is exact (integer arithmetic on the rounded 55-bit fixed-point value).  Then
 //     sum_t x_t y_t = sum_g 256^-g  sum_{i+j=g} sum_t d_i(t) e_j(t),
 // and every inner sum is an integer GEMM whose int32 accumulator cannot overflow
-// (7 pairs * K <= 4096 * 255^2 < 2^31).  Diagonals g < NG are kept; with NS = 7, NG = 8 the
-// dropped terms are below 2^-64 * K of full scale (1e-16 relative to |row|max * |col|max), i.e.
-// under the rounding error of an fp64 dot product of that length.
+// (7 pairs * K <= 4096 * 128^2 < 2^31).  Diagonals g < NG are kept.  Balanced digits have (almost)
+// zero mean, so the dropped diagonals are sums of zero-mean terms: with NS = 7, NG = 7 the largest
+// dropped one (g = 7, six digit pairs) contributes sqrt(6 K) * 74^2 * 2^-56 ~ 4e-12 in units where
+// |row|max, |col|max are in [64, 128), i.e. ~1e-15 * sqrt(K / 400) relative to |row|max * |col|max --
+// the rounding error of an fp64 dot product of that length.  (Round 1 used unsigned digits d_s in
+// [0, 255] for s >= 1: their mean of 127.5 makes every dropped diagonal a BIASED sum ~ K * 127.5^2,
+// which forced NG = 8: 34 digit products instead of 28.)
 //
 // Kernel (ozaki_kernel): persistent, one CTA per SM (grid = #SMs), 128 x 128 output tile, 640 threads.
 //   warp 0      : producer - per k block (K = 32 bytes) two LINEAR cp.async.bulk copies (the digits
@@ -27,7 +30,7 @@
 //   warp 1      : MMA issuer - one lane chosen with elect.sync issues tcgen05.mma.cta_group::1.kind::i8
 //                 (M128 N128 K32, or N256 when two adjacent B digit planes are merged).  The loop is
 //                 k-outer with one TMEM accumulator slot (128 columns) per DIAGONAL: pass 0 folds the
-//                 diagonals 7..4 into the four slots (all 512 TMEM columns), pass 1 the diagonals 3..0,
+//                 diagonals 6..3 into the four slots (all 512 TMEM columns), pass 1 the diagonals 2..0,
 //                 so every digit block is fetched once per pass.  tcgen05.commit frees the stage and
 //                 publishes each slot.  The first and the last k block of a pass are issued slot by
 //                 slot in the order the epilogue drains them, so the drain of one pass overlaps the
@@ -37,8 +40,8 @@
 //                 registers per thread; after the last pass apply the two power-of-two scales and
 //                 write the 32 x 32 block through an 8-column shared-memory transpose.
 //   (warps 2, 3 idle; setmaxnreg 56 for warps 0..3.)
-// Signed / unsigned digits only differ in the instruction descriptor (a_format / b_format), so
-// the first digit of each operand is multiplied as INT8 and the others as UINT8.
+// Every digit plane is signed (a_format = b_format = INT8), so two adjacent B planes can always share
+// one N = 256 instruction.
 // ozaki_pair_kernel is the cta_group::2 variant (cluster of 2, M = 256); measured no faster, not default.
 #include <cstdlib>
 
@@ -85,7 +88,7 @@ struct OzakiArgs {
   int M, N;           // valid rows / cols (store mode)
   int max_kps;        // k blocks per stage (tuning knob)
   int slot_wait;      // wait per accumulator slot (1) or for all slots before the first MMA (0)
-  int b_unsigned;     // every B digit plane is non-negative (kernel values): enables the merged N = 256 MMAs
+  int b_unsigned;     // (name kept from round 1) 1: issue adjacent B digit planes as merged N = 256 MMAs
   int dbg;            // measurement only: 1 = no operand copies (MMAs run on stale smem), 2 = no TMEM drain
 };
 
@@ -210,7 +213,7 @@ __device__ __forceinline__ void issue_pass_k(unsigned tmem_base, unsigned long l
           if (i >= ilo && i <= ihi) {
             const int j = g - i;
             umma_i8(tmem_base + (unsigned)(a * OZ_BN), base + (unsigned long long)((i * OZ_BLK_BYTES) >> 4),
-                    base + (unsigned long long)(((nd + j) * OZ_BLK_BYTES) >> 4), umma_idesc(i == 0, MERGE ? 0 : j == 0),
+                    base + (unsigned long long)(((nd + j) * OZ_BLK_BYTES) >> 4), umma_idesc(1, 1),
                     (i > ilo || !FIRST) ? 1u : 0u);
           }
         }
@@ -220,9 +223,9 @@ __device__ __forceinline__ void issue_pass_k(unsigned tmem_base, unsigned long l
     return;
   }
   if (MERGE) {
-    // B digit planes are all unsigned here, so for a fixed A digit i the products with two
+    // All digit planes have the same format, so for a fixed A digit i the products with two
     // consecutive B digits j, j+1 (diagonals i+j, i+j+1 = adjacent slots; the two digit blocks are
-    // adjacent in the stage) go out as ONE M128 N256 K32 instruction: 19 instead of 34 MMAs per
+    // adjacent in the stage) go out as ONE M128 N256 K32 instruction: 16 instead of 28 MMAs per
     // k block.  The tensor pipe needs ~98 cycles per N = 128 instruction where the arithmetic
     // takes 64 (measured with operand copies and TMEM drains switched off), i.e. there is a
     // fixed cost per instruction that the wider shape amortises.
@@ -235,7 +238,7 @@ __device__ __forceinline__ void issue_pass_k(unsigned tmem_base, unsigned long l
         if (j <= jhi) {
           const bool wide = j + 1 <= jhi;
           umma_i8(tmem_base + (unsigned)((i + j - g_lo) * OZ_BN), base + (unsigned long long)((i * OZ_BLK_BYTES) >> 4),
-                  base + (unsigned long long)(((nd + j) * OZ_BLK_BYTES) >> 4), umma_idesc(i == 0, 0, wide ? 2 * OZ_BN : OZ_BN),
+                  base + (unsigned long long)(((nd + j) * OZ_BLK_BYTES) >> 4), umma_idesc(1, 1, wide ? 2 * OZ_BN : OZ_BN),
                   1u);
         }
       }
@@ -253,7 +256,7 @@ __device__ __forceinline__ void issue_pass_k(unsigned tmem_base, unsigned long l
           if (i <= ihi) {
             const int j = g - i;
             umma_i8(tmem_base + (unsigned)(a * OZ_BN), base + (unsigned long long)((i * OZ_BLK_BYTES) >> 4),
-                    base + (unsigned long long)(((nd + j) * OZ_BLK_BYTES) >> 4), umma_idesc(i == 0, MERGE ? 0 : j == 0),
+                    base + (unsigned long long)(((nd + j) * OZ_BLK_BYTES) >> 4), umma_idesc(1, 1),
                     1u);
           }
         }
@@ -400,7 +403,7 @@ ozaki_kernel(const OzakiArgs args) {
           for (int i = ilo; i <= ihi; ++i, ++ne) {
             const int j = g - i;
             s_prog[p * OZ_MAX_ENT + ne] = make_uint4((unsigned)(i * OZ_BLK_BYTES) >> 4, (unsigned)((nd + j) * OZ_BLK_BYTES) >> 4,
-                                                     umma_idesc(i == 0, j == 0), i > ilo ? 1u : 0u);
+                                                     umma_idesc(1, 1), i > ilo ? 1u : 0u);
           }
         }
         s_slotend[p * OZ_ACC + a] = ne;
@@ -664,7 +667,7 @@ __device__ __forceinline__ void issue_pass_pair_k(unsigned tmem_base, unsigned l
           const int j = g - i;
           umma_i8_pair(tmem_base + (unsigned)(a * OZ_BN), base + (unsigned long long)((i * OZ_BLK_BYTES) >> 4),
                        base + (unsigned long long)((nd * OZ_BLK_BYTES + j * OZP_HALF_BYTES) >> 4),
-                       umma_idesc_pair(i == 0, j == 0), (i > ilo || !FIRST) ? 1u : 0u);
+                       umma_idesc_pair(1, 1), (i > ilo || !FIRST) ? 1u : 0u);
         }
       }
     }
@@ -874,7 +877,7 @@ ozaki_pair_kernel(const OzakiArgs args) {
   }
 }
 
-// One warp per row: power-of-two scale into (-128, 128), then NS exact base-256 digits.
+// One warp per row: power-of-two scale into [-127, 127], then NS exact balanced base-256 digits.
 __global__ void slice_rows_kernel(const double* __restrict__ X, int ld, int rows, int K, int KP, int NS, int block_rows,
                                   unsigned char* __restrict__ out, double* __restrict__ scale) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -887,21 +890,29 @@ __global__ void slice_rows_kernel(const double* __restrict__ X, int ld, int rows
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   int e = 0;
   if (m > 0.0 && m < 1e300) frexp(m, &e);  // m = f 2^e, f in [0.5, 1)
-  const int e7 = e - 7;                     // |x| 2^-e7 < 128
+  int e7 = e - 7;                           // |x| 2^-e7 < 128
+  // balanced digits d_s in [-128, 127] represent exactly the fixed-point values in [-127, 127] (the carries
+  // of the lower digits can raise the leading digit by one): rows whose maximum lies above 127 give up one bit
+  if (scalbn(m, -e7) > 127.0) e7 += 1;
   if (lane == 0) scale[r] = scalbn(1.0, e7);
+  // block image: [row block][k block][digit][row group][k chunk (2)][row in group (8)][16 B]
+  // with block_rows (128, or 64 for the B halves of the CTA-pair kernel) rows x 32 bytes per block
+  const int rb = r / block_rows, ri = r - rb * block_rows;
   for (int k = lane; k < KP; k += 32) {
-    // round to the last digit first (exact: |v| 256^(NS-1) < 2^55 and fp64 has no fraction bits
-    // left above 2^52), so that the digit expansion terminates and the error is unbiased
-    double v = (k < K) ? scalbn(rint(scalbn(x[k], 8 * (NS - 1) - e7)), -8 * (NS - 1)) : 0.0;
-    for (int s = 0; s < NS; ++s) {
-      const double dg = floor(v);
-      // block image: [row block][k block][digit][row group][k chunk (2)][row in group (8)][16 B]
-      // with block_rows (128, or 64 for the B halves of the CTA-pair kernel) rows x 32 bytes per block
-      const int rb = r / block_rows, ri = r - rb * block_rows;
-      const size_t blk = ((size_t)rb * (KP >> 5) + (k >> 5)) * NS + s;
-      const int in_blk = (((ri >> 3) * 2 + ((k & 31) >> 4)) * 8 + (ri & 7)) * 16 + (k & 15);
-      out[blk * (size_t)(block_rows * OZ_KB) + in_blk] = (unsigned char)(int)dg;  // two's complement byte for s = 0
-      v = (v - dg) * 256.0;
+    // round to the last digit first (|V| <= 127 * 256^(NS-1) < 2^55), then peel balanced digits off the low end:
+    // d = ((V + 128) mod 256) - 128, V <- (V - d) / 256; what is left after NS - 1 steps is the leading digit
+    long long V = (k < K && m < 1e300) ? __double2ll_rn(scalbn(x[k], 8 * (NS - 1) - e7)) : 0ll;
+    const size_t blk0 = ((size_t)rb * (KP >> 5) + (k >> 5)) * NS;
+    const int in_blk = (((ri >> 3) * 2 + ((k & 31) >> 4)) * 8 + (ri & 7)) * 16 + (k & 15);
+    for (int s = NS - 1; s >= 0; --s) {
+      int dg;
+      if (s > 0) {
+        dg = (int)((V + 128) & 255) - 128;
+        V = (V - dg) >> 8;
+      } else {
+        dg = (int)V;
+      }
+      out[(blk0 + s) * (size_t)(block_rows * OZ_KB) + in_blk] = (unsigned char)dg;  // two's complement byte
     }
   }
 }
@@ -1041,7 +1052,8 @@ int ozaki_cov(const unsigned char* a_digits, const double* sa, int M_pad, const 
               const double* sb, int N_pad, int K, int NS, int NG, bool b_nonneg, const CovEpilogue& ep,
               cudaStream_t st) {
   OzakiArgs args{};
-  args.b_unsigned = b_nonneg ? 1 : 0;
+  (void)b_nonneg;
+  args.b_unsigned = 1;  // balanced digits: every plane is signed, adjacent B planes can always be merged (DKG_OZ_MERGE=0 disables)
   args.cov = 1;
   args.ep = ep;
   return ozaki_launch(a_digits, sa, M_pad, b_digits, sb, N_pad, K, NS, NG, args, st);
@@ -1052,7 +1064,8 @@ int ozaki_store(const unsigned char* a_digits, const double* sa, int M_pad, cons
                 const double* sb, int N_pad, int K, int NS, int NG, bool b_nonneg, double* D, int ldd, int M,
                 int N, cudaStream_t st) {
   OzakiArgs args{};
-  args.b_unsigned = b_nonneg ? 1 : 0;
+  (void)b_nonneg;
+  args.b_unsigned = 1;  // balanced digits: every plane is signed, adjacent B planes can always be merged (DKG_OZ_MERGE=0 disables)
   args.cov = 0;
   args.D = D;
   args.ldd = ldd;

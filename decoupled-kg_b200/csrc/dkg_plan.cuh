@@ -122,7 +122,7 @@ struct dkg_plan {
   int ldz = 0;    // row stride of the slope buffer (>= N+1, multiple of 16)
   int ldk = 0;    // row stride of Kinv / T (n_i rounded up to GEMM_BN)
   int device = 0;
-  int cov_digits = 7, cov_diagonals = 8;  // base-256 digit configuration of the int8 contraction (DKG_PLAN_FAST32: 4 / 4)
+  int cov_digits = 7, cov_diagonals = 7;  // base-256 digit configuration of the int8 contraction (DKG_PLAN_FAST32: 4 / 4)
   dkg::ObjState obj[dkg::MAX_M];
   double W_host[dkg::MAX_S * dkg::MAX_M];
   double* W = nullptr;        // [S, M]

@@ -197,19 +197,39 @@ chain_kernel(LineBatch lb, EmaxScratch sc) {
 // per row segment: slopes are read and rewritten once, the points are read once per CTA, and the
 // per-(row, tile) minima / maxima are combined by zreduce_kernel.
 constexpr int ZT_BYTES = 64 * 1024;
+// lines per CTA tile: whole filter tiles, 64 KB of scaled points
+__host__ __device__ constexpr int zt_tile_lines(int D) { return (ZT_BYTES / (int)sizeof(double) / D) & ~(FILTER_TILE - 1); }
 
-template <int D>
+__device__ __forceinline__ float warp_min_f32(float v) {
+  float r;
+  asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+// TRACK = false (the KG path, per-tile slope ranges requested): the pass keeps NO running (min, max, index) of
+// the row -- that bookkeeping was ~30 of the ~120 instructions per slope of this issue-bound kernel (fp64
+// DSETP.MIN/MAX with their NaN fix-ups, four 64-bit selects, two index selects; ncu source view, r02f).  The
+// float (min, max) of every 128-line tile is written anyway (one conversion and two FMNMX per slope, one
+// CREDUX pair per tile); rounding to float is monotone, so the row's exact minimum lies in a tile whose float
+// minimum equals the smallest one of the row, and zreduce_tiles_kernel re-reads just those tiles.
+template <int D, bool TRACK>
 __global__ void __launch_bounds__(E_THREADS, 3)
 zfinish_tiled_kernel(LineBatch lb, CovFinish fin, double* __restrict__ zpv, int* __restrict__ zpi,
-                     int tile_lines, int rows_per_cta, float2* __restrict__ ztile, int ztiles) {
+                     int rows_per_cta, float2* __restrict__ ztile, int ztiles) {
   extern __shared__ __align__(16) unsigned char e_smem[];
-  double* s_xd = reinterpret_cast<double*>(e_smem);  // [D][tile_lines]
+  constexpr int TL = zt_tile_lines(D);
+  double* s_xd = reinterpret_cast<double*>(e_smem);  // [D][TL]; lines past the discretisation hold zeros
   const int ntiles = gridDim.x, tile = blockIdx.x;
-  const int n_lo = tile * tile_lines;
-  const int n_cnt = min(tile_lines, fin.N - n_lo);
-  for (int idx = threadIdx.x; idx < n_cnt * D; idx += blockDim.x) {
+  const int n_lo = tile * TL;
+  const int n_cnt = min(TL, fin.N - n_lo);
+  for (int idx = threadIdx.x; idx < TL * D; idx += blockDim.x) {
     const int n = idx / D, k = idx - n * D;
-    s_xd[k * tile_lines + n] = fin.xd_s[(size_t)n_lo * D + idx];
+    s_xd[k * TL + n] = n < n_cnt ? fin.xd_s[(size_t)n_lo * D + idx] : 0.0;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -217,6 +237,7 @@ zfinish_tiled_kernel(LineBatch lb, CovFinish fin, double* __restrict__ zpv, int*
   const int kind = fin.kind;
   const double os = fin.outputscale;
   constexpr int U = 4;
+  static_assert(32 * U == FILTER_TILE, "one trip of a warp = one filter tile");
   for (int r = blockIdx.y * rows_per_cta + warp; r < r_end; r += nwarp) {
     double xr[D];
 #pragma unroll
@@ -228,9 +249,11 @@ zfinish_tiled_kernel(LineBatch lb, CovFinish fin, double* __restrict__ zpv, int*
     double vn[U];  // the next trip's products are requested before this trip's kernel evaluations
 #pragma unroll
     for (int u = 0; u < U; ++u) vn[u] = lane + 32 * u < n_cnt ? zw[lane + 32 * u] : 0.0;
-    // (warp-uniform trip count: the tile statistics below use warp shuffles)
+    // (warp-uniform trip count: the tile statistics below use warp-wide reductions)
+#pragma unroll 2
     for (int b0 = 0; b0 < n_cnt; b0 += 32 * U) {
       const int i0 = b0 + lane;
+      const double* xd0 = s_xd + i0;
       double v[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) v[u] = vn[u];
@@ -242,52 +265,65 @@ zfinish_tiled_kernel(LineBatch lb, CovFinish fin, double* __restrict__ zpv, int*
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int i = i0 + 32 * u;
-        const int il = i < n_cnt ? i : 0;
         double sq = 0.0;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-          const double df = xr[k] - s_xd[k * tile_lines + il];
+          const double df = xr[k] - xd0[k * TL + 32 * u];  // (zero-filled past n_cnt: no bounds check)
           sq = fma(df, df, sq);
         }
         v[u] = (stationary_from_sq(kind, os, sq) - v[u]) * rsd;
       }
-      double tmin = INFINITY, tmax = -INFINITY;  // this trip's 128 consecutive lines = one filter tile
+      float flo = INFINITY, fhi = -INFINITY;  // this trip's 128 consecutive lines = one filter tile
+      if (b0 + 32 * U <= n_cnt) {  // (warp-uniform) whole trip inside the discretisation
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + 32 * u;
-        if (i < n_cnt) {
-          zw[i] = v[u];
-          if (v[u] < vmin) { vmin = v[u]; imin = n_lo + i; }
-          if (v[u] > vmax) { vmax = v[u]; imax = n_lo + i; }
-          tmin = fmin(tmin, v[u]);
-          tmax = fmax(tmax, v[u]);
+        for (int u = 0; u < U; ++u) {
+          zw[i0 + 32 * u] = v[u];
+          if (TRACK) {
+            if (v[u] < vmin) { vmin = v[u]; imin = n_lo + i0 + 32 * u; }
+            if (v[u] > vmax) { vmax = v[u]; imax = n_lo + i0 + 32 * u; }
+          }
+          // the slope as the chord filter will see it (rounded to nearest float; rounding is monotone, so
+          // the extremes of the rounded values bracket every rounded slope of the tile)
+          const float f = __double2float_rn(v[u]);
+          flo = fminf(flo, f);
+          fhi = fmaxf(fhi, f);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + 32 * u;
+          if (i < n_cnt) {
+            zw[i] = v[u];
+            if (TRACK) {
+              if (v[u] < vmin) { vmin = v[u]; imin = n_lo + i; }
+              if (v[u] > vmax) { vmax = v[u]; imax = n_lo + i; }
+            }
+            const float f = __double2float_rn(v[u]);
+            flo = fminf(flo, f);
+            fhi = fmaxf(fhi, f);
+          }
         }
       }
       if (ztile != nullptr) {
-        // (min, max) of the tile's slopes as the chord filter will see them (rounded to nearest float;
-        // rounding is monotone, so these bracket every rounded slope of the tile)
-        float flo = __double2float_rn(tmin), fhi = __double2float_rn(tmax);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          flo = fminf(flo, __shfl_xor_sync(0xffffffffu, flo, o));
-          fhi = fmaxf(fhi, __shfl_xor_sync(0xffffffffu, fhi, o));
-        }
+        flo = warp_min_f32(flo);
+        fhi = warp_max_f32(fhi);
         if (lane == 0) ztile[(size_t)r * ztiles + (n_lo + b0) / FILTER_TILE] = make_float2(flo, fhi);
       }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, vmin, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, imin, o);
-      if (MinOp::better(ov, oi, vmin, imin)) { vmin = ov; imin = oi; }
-      const double pv = __shfl_xor_sync(0xffffffffu, vmax, o);
-      const int pi = __shfl_xor_sync(0xffffffffu, imax, o);
-      if (MaxOp::better(pv, pi, vmax, imax)) { vmax = pv; imax = pi; }
-    }
-    if (lane == 0) {
-      const size_t q = ((size_t)r * ntiles + tile) * 2;
-      zpv[q] = vmin; zpv[q + 1] = vmax;
-      zpi[q] = imin; zpi[q + 1] = imax;
+    if (TRACK) {
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, vmin, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, imin, o);
+        if (MinOp::better(ov, oi, vmin, imin)) { vmin = ov; imin = oi; }
+        const double pv = __shfl_xor_sync(0xffffffffu, vmax, o);
+        const int pi = __shfl_xor_sync(0xffffffffu, imax, o);
+        if (MaxOp::better(pv, pi, vmax, imax)) { vmax = pv; imax = pi; }
+      }
+      if (lane == 0) {
+        const size_t q = ((size_t)r * ntiles + tile) * 2;
+        zpv[q] = vmin; zpv[q + 1] = vmax;
+        zpi[q] = imin; zpi[q + 1] = imax;
+      }
     }
   }
 }
@@ -314,21 +350,87 @@ __global__ void zreduce_kernel(LineBatch lb, int N, int ntiles, const double* __
   zarg[r * 2 + 0] = imin; zarg[r * 2 + 1] = imax;
 }
 
+// one warp per row: exact (min, max, first indices) of the finished slope row from the per-tile float ranges.
+// float(min of the row) is the smallest float tile minimum, and every tile that attains it may hold the exact
+// minimum: those tiles (usually one) are re-read in increasing line order, first index winning ties.
+__global__ void __launch_bounds__(E_THREADS)
+zreduce_tiles_kernel(LineBatch lb, int N, const float2* __restrict__ ztile, int ztiles, double* __restrict__ zst,
+                     int* __restrict__ zarg) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (E_THREADS / 32) + (threadIdx.x >> 5);
+  if (r >= lb.C) return;
+  const float2* zt = ztile + (size_t)r * ztiles;
+  float glo = INFINITY, ghi = -INFINITY;
+  for (int t = lane; t < ztiles; t += 32) {
+    const float2 f = zt[t];
+    glo = fminf(glo, f.x);
+    ghi = fmaxf(ghi, f.y);
+  }
+  glo = warp_min_f32(glo);
+  ghi = warp_max_f32(ghi);
+  const double* z = lb.Z + (size_t)r * lb.ldz;
+  double vmin = INFINITY, vmax = -INFINITY;
+  int imin = 0x7fffffff, imax = 0x7fffffff;
+  for (int t0 = 0; t0 < ztiles; t0 += 32) {
+    const int t = t0 + lane;
+    const float2 f = t < ztiles ? zt[t] : make_float2(INFINITY, -INFINITY);
+    unsigned hit = __ballot_sync(0xffffffffu, f.x == glo || f.y == ghi);
+    while (hit) {
+      const int tt = t0 + __ffs(hit) - 1;
+      hit &= hit - 1u;
+      for (int u = 0; u < FILTER_TILE / 32; ++u) {
+        const int n = tt * FILTER_TILE + lane + 32 * u;
+        if (n < N) {
+          const double v = z[n];
+          if (v < vmin) { vmin = v; imin = n; }
+          if (v > vmax) { vmax = v; imax = n; }
+        }
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, vmin, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, imin, o);
+    if (MinOp::better(ov, oi, vmin, imin)) { vmin = ov; imin = oi; }
+    const double pv = __shfl_xor_sync(0xffffffffu, vmax, o);
+    const int pi = __shfl_xor_sync(0xffffffffu, imax, o);
+    if (MaxOp::better(pv, pi, vmax, imax)) { vmax = pv; imax = pi; }
+  }
+  if (lane == 0) {
+    for (int n = N; n < lb.NL; ++n) {  // the candidate's own line (final already)
+      const double v = z[n];
+      if (v < vmin) { vmin = v; imin = n; }
+      if (v > vmax) { vmax = v; imax = n; }
+    }
+    zst[r * 2 + 0] = vmin; zst[r * 2 + 1] = vmax;
+    zarg[r * 2 + 0] = imin; zarg[r * 2 + 1] = imax;
+  }
+}
+
 template <int D>
 static int launch_zfinish_tiled(const LineBatch& lb, const EmaxScratch& sc, const CovFinish& f, cudaStream_t st) {
-  const int tile_lines = (ZT_BYTES / (int)sizeof(double) / D) & ~(FILTER_TILE - 1);  // whole filter tiles per CTA tile
+  constexpr int tile_lines = zt_tile_lines(D);
   const int ntiles = ceil_div(f.N, tile_lines);
   int gy = ceil_div(3 * 148, ntiles);
   if (gy > ceil_div(lb.C, E_THREADS / 32)) gy = ceil_div(lb.C, E_THREADS / 32);
   const int rows_per_cta = ceil_div(lb.C, gy);
   gy = ceil_div(lb.C, rows_per_cta);
   const size_t smem = (size_t)tile_lines * D * sizeof(double);
-  DKG_CUDA_OK(cudaFuncSetAttribute(zfinish_tiled_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  zfinish_tiled_kernel<D><<<dim3(ntiles, gy), E_THREADS, smem, st>>>(lb, f, sc.zpv, sc.zpi, tile_lines, rows_per_cta, sc.ztile,
-                                                                       sc.ztiles);
-  DKG_LAUNCH_CHECK();
-  zreduce_kernel<<<ceil_div(lb.C, 128), 128, 0, st>>>(lb, f.N, ntiles, sc.zpv, sc.zpi, sc.zst, sc.zarg);
-  DKG_LAUNCH_CHECK();
+  // (DKG_ZSTAT_TRACK=1: the round-2 form with running row statistics in the pass itself, for comparison)
+  const bool track = sc.ztile == nullptr || getenv("DKG_ZSTAT_TRACK") != nullptr;
+  if (track) {
+    DKG_CUDA_OK(cudaFuncSetAttribute(zfinish_tiled_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    zfinish_tiled_kernel<D, true><<<dim3(ntiles, gy), E_THREADS, smem, st>>>(lb, f, sc.zpv, sc.zpi, rows_per_cta, sc.ztile, sc.ztiles);
+    DKG_LAUNCH_CHECK();
+    zreduce_kernel<<<ceil_div(lb.C, 128), 128, 0, st>>>(lb, f.N, ntiles, sc.zpv, sc.zpi, sc.zst, sc.zarg);
+    DKG_LAUNCH_CHECK();
+  } else {
+    DKG_CUDA_OK(cudaFuncSetAttribute(zfinish_tiled_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    zfinish_tiled_kernel<D, false><<<dim3(ntiles, gy), E_THREADS, smem, st>>>(lb, f, sc.zpv, sc.zpi, rows_per_cta, sc.ztile, sc.ztiles);
+    DKG_LAUNCH_CHECK();
+    zreduce_tiles_kernel<<<ceil_div(lb.C, E_THREADS / 32), E_THREADS, 0, st>>>(lb, f.N, sc.ztile, sc.ztiles, sc.zst, sc.zarg);
+    DKG_LAUNCH_CHECK();
+  }
   return DKG_OK;
 }
 

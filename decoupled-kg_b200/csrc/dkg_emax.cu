@@ -43,7 +43,10 @@ constexpr double SHORTCUT_TOL = 1e-9;  // discretekg.py:363
 constexpr int STAGE_CAP = 128;         // lines a warp marches over from registers
 constexpr int CHAIN_MAXV = 32;         // vertices of a warp's refinement chain (one lane each)
 constexpr int HULL_LEVELS = 5;         // refinement passes of the warp kernel before a set is queued
-constexpr int HULL_CTAS = 3;           // resident CTAs per SM the warp hull kernel is compiled for
+#ifndef DKG_HULL_CTAS
+#define DKG_HULL_CTAS 3
+#endif
+constexpr int HULL_CTAS = DKG_HULL_CTAS;  // resident CTAs per SM the warp hull kernel is compiled for
 constexpr double EPS128 = 2.84217094304040074e-14;  // 128 * 2^-52
 
 // ------------------------------------------------------------------------------------------
@@ -1008,7 +1011,10 @@ __device__ __forceinline__ void tf_flush(const LineBatch& lb, const EmaxScratch&
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(TF_THREADS, 3)
+#ifndef DKG_TF_CTAS
+#define DKG_TF_CTAS 4
+#endif
+__global__ void __launch_bounds__(TF_THREADS, DKG_TF_CTAS)
 tilefilter_kernel(LineBatch lb, EmaxScratch sc, int pairs_per_warp, int njb, int use_ztile) {
   __shared__ int2 s_pool[TF_THREADS / 32][TF_POOL];
   __shared__ ulonglong2 s_ch[TF_THREADS / 32][16][4];  // per warp, per scalarisation: (m_k, m_k | c_k, c_k) of chord k
@@ -1018,11 +1024,13 @@ tilefilter_kernel(LineBatch lb, EmaxScratch sc, int pairs_per_warp, int njb, int
   const int chunks = (ntp + pairs_per_warp - 1) / pairs_per_warp;
   // work item = (row, scalarisation batch, chunk of tile pairs); chunk fastest so that neighbouring
   // warps share a row's chain parameters and slope row in L1 / L2
-  const long long item = (long long)blockIdx.x * (TF_THREADS / 32) + warp;
-  if (item >= (long long)lb.C * njb * chunks) return;
-  const int chunk = (int)(item % chunks);
-  const int jb = (int)((item / chunks) % njb);
-  const int c = (int)(item / ((long long)chunks * njb));
+  // (the launcher keeps the item count below 2^31: 32-bit index arithmetic)
+  const unsigned item = blockIdx.x * (unsigned)(TF_THREADS / 32) + (unsigned)warp;
+  if (item >= (unsigned)lb.C * (unsigned)njb * (unsigned)chunks) return;
+  const int chunk = (int)(item % (unsigned)chunks);
+  const unsigned item_cj = item / (unsigned)chunks;
+  const int jb = (int)(item_cj % (unsigned)njb);
+  const int c = (int)(item_cj / (unsigned)njb);
   const int half = lane >> 4, jl = lane & 15;
   const int j_mine = jb * 16 + jl;
   const bool j_ok = j_mine < S;
@@ -1065,13 +1073,17 @@ tilefilter_kernel(LineBatch lb, EmaxScratch sc, int pairs_per_warp, int njb, int
         am_nx = lb.A32tmax[(size_t)tn * S + j_mine];
       }
     }
-    bool culled = true;
+    // side_live bit 0: a line of the tile may pass one of the LEFT chords (P-U, U-T); bit 1: one of the right
+    // chords (T-V, V-Q).  A chord that culls the whole tile cannot pass any single line of it (fma is monotone
+    // in z), so the per-line phase below skips the sides that are dead for the tile: same survivors.
+    unsigned side_live = 0u;
     if (j_ok && tile < ntiles) {
       const float lo = zr.x, hi = zr.y;
-      culled = (am <= fminf(fmaf(mm.x, lo, cc.x), fmaf(mm.x, hi, cc.x))) & (am <= fminf(fmaf(mm.y, lo, cc.y), fmaf(mm.y, hi, cc.y))) &
-               (am <= fminf(fmaf(mm.z, lo, cc.z), fmaf(mm.z, hi, cc.z))) & (am <= fminf(fmaf(mm.w, lo, cc.w), fmaf(mm.w, hi, cc.w)));
+      const bool dead_l = (am <= fminf(fmaf(mm.x, lo, cc.x), fmaf(mm.x, hi, cc.x))) & (am <= fminf(fmaf(mm.y, lo, cc.y), fmaf(mm.y, hi, cc.y)));
+      const bool dead_r = (am <= fminf(fmaf(mm.z, lo, cc.z), fmaf(mm.z, hi, cc.z))) & (am <= fminf(fmaf(mm.w, lo, cc.w), fmaf(mm.w, hi, cc.w)));
+      side_live = (dead_l ? 0u : 1u) | (dead_r ? 0u : 2u);
     }
-    const unsigned live = ~__ballot_sync(0xffffffffu, culled);  // bit (half * 16 + jl): this (tile, set) pair needs the lines
+    const unsigned live = __ballot_sync(0xffffffffu, side_live != 0u);  // bit (half * 16 + jl): this (tile, set) pair needs the lines
     if (live == 0u) continue;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -1099,16 +1111,23 @@ tilefilter_kernel(LineBatch lb, EmaxScratch sc, int pairs_per_warp, int njb, int
         const int j = jb * 16 + jj;
         const float4 a = a_nx;
         if (bits) a_nx = *reinterpret_cast<const float4*>(arow + (size_t)(__ffs(bits) - 1) * a_sj);
-        const ulonglong2 q0 = chw[jj * 4 + 0], q1 = chw[jj * 4 + 1], q2 = chw[jj * 4 + 2], q3 = chw[jj * 4 + 3];
+        const unsigned sides = __shfl_sync(0xffffffffu, side_live, 16 * h + jj);  // (warp-uniform)
         unsigned mask = 0u;
         // a line is kept iff a > fma(m_k, z, c_k) for one of the four chords: two pairs of chords per
         // pair of lines, each as in filter32_kernel (one packed FFMA2 per chord)
-        mask = pair_test32<1u>(mask, q0.x, q0.y, q1.x, q1.y, z01, a.x, a.y);
-        mask = pair_test32<4u>(mask, q0.x, q0.y, q1.x, q1.y, z23, a.z, a.w);
-        unsigned mask2 = 0u;
-        mask2 = pair_test32<1u>(mask2, q2.x, q2.y, q3.x, q3.y, z01, a.x, a.y);
-        mask2 = pair_test32<4u>(mask2, q2.x, q2.y, q3.x, q3.y, z23, a.z, a.w);
-        mask = (mask | mask2) & inmask;
+        if (sides & 1u) {
+          const ulonglong2 q0 = chw[jj * 4 + 0], q1 = chw[jj * 4 + 1];
+          mask = pair_test32<1u>(mask, q0.x, q0.y, q1.x, q1.y, z01, a.x, a.y);
+          mask = pair_test32<4u>(mask, q0.x, q0.y, q1.x, q1.y, z23, a.z, a.w);
+        }
+        if (sides & 2u) {
+          const ulonglong2 q2 = chw[jj * 4 + 2], q3 = chw[jj * 4 + 3];
+          unsigned mask2 = 0u;
+          mask2 = pair_test32<1u>(mask2, q2.x, q2.y, q3.x, q3.y, z01, a.x, a.y);
+          mask2 = pair_test32<4u>(mask2, q2.x, q2.y, q3.x, q3.y, z23, a.z, a.w);
+          mask |= mask2;
+        }
+        mask &= inmask;
         for (;;) {  // survivors are rare
           const unsigned vote = __ballot_sync(0xffffffffu, mask != 0u);
           if (vote == 0u) break;
@@ -1152,6 +1171,7 @@ static int launch_tilefilter(const LineBatch& lb, const EmaxScratch& sc, cudaStr
   if (const char* e = getenv("DKG_TF_PPW")) ppw = atoi(e);
   if (ppw < 1) ppw = 1;
   if (ppw > ntp) ppw = ntp;
+  while ((long long)lb.C * njb * ceil_div(ntp, (int)ppw) >= (1ll << 31) && ppw < ntp) ppw *= 2;  // 32-bit item index in the kernel
   const int chunks = ceil_div(ntp, (int)ppw);
   const long long items = (long long)lb.C * njb * chunks;
   const int wpb = TF_THREADS / 32;
@@ -1718,15 +1738,18 @@ __device__ HullResult warp_march(int total, Fetch fetch, Recorder& rec) {
     Line nxt = empty_line();
     double nx = INFINITY;
     if (!last) {
+      // Smallest intersection of the warp: rounding to float is monotone, so the exact minimum is held by a
+      // lane whose ROUNDED value equals the smallest rounded value -- one CREDUX instead of five rounds of 64-bit
+      // shuffles and NaN-aware fp64 minima.  Usually one lane qualifies; several (equal or float-equal
+      // intersections) are merged exactly: smaller x first, then the earliest line in the sorted order.
       const double myx = best.L.idx >= 0 ? best.x : INFINITY;
-      double xm = myx;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) xm = fmin(xm, __shfl_xor_sync(0xffffffffu, xm, o));
-      const unsigned tied = __ballot_sync(0xffffffffu, best.L.idx >= 0 && myx == xm);
-      int src = __ffs(tied) - 1;
-      if (__popc(tied) > 1) {  // equal intersections: the earliest line in the sorted order wins
+      const float fx = __double2float_rn(myx);
+      const float fm = warp_min_f32(fx);
+      const unsigned tied = __ballot_sync(0xffffffffu, best.L.idx >= 0 && fx == fm);
+      const int src = __ffs(tied) - 1;
+      if (__popc(tied) > 1) {
         Next b2 = best;
-        if (!(best.L.idx >= 0 && myx == xm)) b2.L = empty_line();
+        if (!((tied >> lane) & 1u)) b2.L = empty_line();
         for (int o = 16; o > 0; o >>= 1) {
           Next oth;
           oth.L = shfl_line(b2.L, o);
@@ -1734,13 +1757,14 @@ __device__ HullResult warp_march(int total, Fetch fetch, Recorder& rec) {
           merge_next(b2, oth);
         }
         nxt = b2.L;
+        nx = b2.x;
       } else {
         nxt.a = __shfl_sync(0xffffffffu, best.L.a, src);
         nxt.b = __shfl_sync(0xffffffffu, best.L.b, src);
         nxt.idx = __shfl_sync(0xffffffffu, best.L.idx, src);
         nxt.ref = __shfl_sync(0xffffffffu, best.L.ref, src);
+        nx = __shfl_sync(0xffffffffu, myx, src);
       }
-      nx = xm;
     }
     const int slot = h & 31;
     if (lane == slot) { mine = cur; mine_x = nx; }

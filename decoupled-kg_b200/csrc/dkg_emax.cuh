@@ -50,13 +50,18 @@ __device__ __forceinline__ double coupled_quotient(double s, double sd, double r
   }
   return s / sd;
 }
+// (out of line: line_slope() is inlined at a dozen sites of the hull / overflow / finalize kernels, and two fp64
+// divisions per site added 1.9 k of the 7.5 k instructions of hull_kernel -- instruction-cache misses on the
+// decoupled path, which never executes them)
+static __device__ __noinline__ double coupled_quotient_div(double s, double sd) {
+  return coupled_quotient(s, sd, 1.0 / sd);
+}
 __device__ __forceinline__ double line_slope(const LineBatch& lb, int row, int n) {
   if (lb.cov_M == 0) return lb.Z[(size_t)row * lb.ldz + n];
   const int c = row / lb.row_mod, j = row - c * lb.row_mod;
   double s = 0.0;
   for (int m = 0; m < lb.cov_M; ++m) s = fma(lb.cov_w2[j * lb.cov_M + m], lb.cov[m][(size_t)c * lb.ldz + n], s);
-  const double sd = lb.cov_sd[row];
-  return coupled_quotient(s, sd, 1.0 / sd);
+  return coupled_quotient_div(s, lb.cov_sd[row]);
 }
 #endif
 

@@ -233,6 +233,12 @@ int coupled_slopes(const CoupledArgs& a, cudaStream_t st) {
 // var_j = sum_m W_jm^2 var_m:
 //   dKG = sum_j Ga_j d a_own_j + sum_m [ sum_n Gz_m[n] d cov_m[n] + Cv_m d var_m ]
 //   Gz_m[n] = sum_j om_jm q_jn / S,   Cv_m = -sum_j W_jm^2 / (2 var_j) sum_n (q_jn / S) b_jn
+// The hull records of the candidate (all scalarisations) are staged in shared memory once and their DISTINCT
+// lines found through the same hash table as in finalize_kernel: the same few lines are hull vertices of
+// most scalarisations, so per objective the B_m^T row gathers and the kernel-gradient evaluations run once
+// per distinct line with the merged coefficient Gz_m[n].  (Before: every thread walked every record of every
+// scalarisation through the spill-chain reader for every training point -- 2.05 of the 7.5 ms of a c4 step.)
+// Candidates with more records than the staging capacity take the unmerged loops.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CP_THREADS)
 finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
@@ -250,18 +256,105 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
   if (bw.dX == nullptr) return;
 
   const int d = bw.d, M = bw.M, NA = bw.N;
-  __shared__ int s_broken;
-  if (threadIdx.x == 0) s_broken = 0;
-  __syncthreads();
+  __shared__ int s_broken, s_nrec, s_nuniq, s_hovf;
   const double invS = 1.0 / (double)S;
   int n_pad_max = 0;
   for (int m = 0; m < M; ++m) n_pad_max = max(n_pad_max, bw.n_pad[m]);
   double* s_r = s_term + S;                    // [n_pad_max]
   double* s_sc = s_r + n_pad_max;              // [0] gzown, [1] Cv, [2..2+MAX_D) gkd, [2+MAX_D..) gm[m]
-  double* s_red = s_sc + 2 + MAX_D + MAX_M;    // [nwarps * MAX_D]
+  double* s_red = s_sc + 2 + MAX_D + MAX_M;    // [nwarps * MAX_D]   (sized for CP_THREADS / 32 warps)
+  const int RM = fin_rmax(S);
+  const int HB = fin_hash_bits(S), HN = 1 << HB;
+  double* s_rq = s_red + (CP_THREADS / 32) * MAX_D;  // [RM] q / S of a record
+  double* s_ucz = s_rq + RM;                   // [RM] merged coefficient Gz_m of a distinct line
+  double* s_om = s_ucz + RM;                   // [S]  om_jm of the current objective
+  double* s_qb = s_om + S;                     // [S]  sum_n (q_jn / S) b_jn
+  int* s_ridx = reinterpret_cast<int*>(s_qb + S);  // [RM] record line index
+  int* s_rj = s_ridx + RM;                     // [RM] record scalarisation
+  int* s_flag = s_rj + RM;                     // [RM] hash slot, then first-occurrence flag
+  int* s_uidx = s_flag + RM;                   // [RM] distinct line index
+  int* s_ue = s_uidx + RM;                     // [RM] its first record
+  int* s_roff = s_ue + RM;                     // [S + 1] record offsets per set
+  int* s_hkey = s_roff + ((S + 2) & ~1);       // [HN]
+  int* s_hfirst = s_hkey + HN;                 // [HN]
   double grad[MAX_D];
 #pragma unroll
   for (int k = 0; k < MAX_D; ++k) grad[k] = 0.0;
+
+  for (int j = threadIdx.x; j < S; j += blockDim.x) s_roff[j + 1] = out.hull_cnt[(size_t)c * S + j];
+  for (int h = threadIdx.x; h < HN; h += blockDim.x) { s_hkey[h] = -1; s_hfirst[h] = 0x7fffffff; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int j = 0; j < S; ++j) {
+      const int h = s_roff[j + 1];
+      s_roff[j] = off;
+      off += h;
+    }
+    s_roff[S] = off;
+    s_nrec = off;
+    s_nuniq = 0;
+    s_hovf = 0;
+    s_broken = 0;
+  }
+  __syncthreads();
+  const int nrec = s_nrec;
+  bool merged = nrec <= RM;
+  if (merged) {
+    for (int j = warp; j < S; j += nwarps) {
+      const size_t set = (size_t)c * S + j;
+      const int h = s_roff[j + 1] - s_roff[j];
+      HullReader rd(out, set);
+      for (int k = lane; k < h; k += 32) {
+        const int e = s_roff[j] + k;
+        s_rj[e] = j;
+        if (!rd.seek(k)) { s_broken = 1; s_ridx[e] = NA; s_rq[e] = 0.0; continue; }
+        s_ridx[e] = rd.idx();
+        s_rq[e] = rd.q() * invS;
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nrec; e += blockDim.x) {
+      const int idx = s_ridx[e];
+      unsigned h = ((unsigned)idx * 2654435761u) >> (32 - HB);
+      int probes = 0;
+      for (;; h = (h + 1) & (HN - 1)) {
+        const int prev = atomicCAS(&s_hkey[h], -1, idx);
+        if (prev == -1 || prev == idx) break;
+        if (++probes >= HN) { s_hovf = 1; break; }
+      }
+      atomicMin(&s_hfirst[h], e);
+      s_flag[e] = (int)h;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nrec; e += blockDim.x) s_flag[e] = s_hfirst[s_flag[e]] == e ? 1 : 0;
+    __syncthreads();
+    if (s_hovf) merged = false;
+  }
+  if (merged) {
+    for (int e = threadIdx.x; e < nrec; e += blockDim.x) {
+      if (!s_flag[e]) continue;
+      int rank = 0;  // distinct lines that first occur before e (order = first occurrence: deterministic)
+      for (int f = 0; f < e; ++f) rank += s_flag[f];
+      s_uidx[rank] = s_ridx[e];
+      s_ue[rank] = e;
+      atomicAdd(&s_nuniq, 1);
+    }
+    // qb_j = sum_n (q_jn / S) b_jn: the same for every objective
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+      const size_t set = (size_t)c * S + j;
+      const double sd = bw.sdj[set], rinv = 1.0 / sd;
+      double qb = 0.0;
+      for (int e = s_roff[j]; e < s_roff[j + 1]; ++e) {
+        double sacc = 0.0;  // b_jn, formed as everywhere else (line_slope)
+        for (int mm = 0; mm < M; ++mm) sacc = fma(bw.W2[j * M + mm], bw.COV[mm][(size_t)c * bw.ldz + s_ridx[e]], sacc);
+        qb += s_rq[e] * coupled_quotient(sacc, sd, rinv);
+      }
+      s_qb[j] = qb;
+    }
+  }
+  __syncthreads();
+  const int nuniq = merged ? s_nuniq : 0;
 
   // gm[m] = sum_j Ga_j W[j, m]  (own-line intercept path), computed once by warp 0
   if (warp == 0) {
@@ -290,19 +383,41 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
 
   for (int m = 0; m < M; ++m) {
     const double s2 = bw.y_std[m] * bw.y_std[m];
+    if (merged) {
+      for (int j = threadIdx.x; j < S; j += blockDim.x) {
+        const double w = bw.W[j * M + m];
+        s_om[j] = (w * w) / bw.sdj[(size_t)c * S + j];
+      }
+      __syncthreads();
+      for (int u = threadIdx.x; u < nuniq; u += blockDim.x) {
+        const int idx = s_uidx[u];
+        double acc = 0.0;
+        for (int f = s_ue[u]; f < nrec; ++f)
+          if (s_ridx[f] == idx) acc += s_om[s_rj[f]] * s_rq[f];
+        s_ucz[u] = acc;
+      }
+      __syncthreads();
+    }
     // r_m[t] = sum over hull records (discretisation lines) of om_jm q / S * B_m^T[idx, t]
     for (int t = threadIdx.x; t < bw.n_pad[m]; t += blockDim.x) {
       double acc = 0.0;
-      for (int j = 0; j < S; ++j) {
-        const size_t set = (size_t)c * S + j;
-        const int h = out.hull_cnt[set];
-        const double w = bw.W[j * M + m];
-        const double om = (w * w) / bw.sdj[set];
-        HullReader rd(out, set);
-        for (int k = 0; k < h; ++k) {
-          if (!rd.seek(k)) { s_broken = 1; break; }
-          const int idx = rd.idx();
-          if (idx < NA) acc += om * rd.q() * invS * bw.BT[m][(size_t)idx * bw.ldbt[m] + t];
+      if (merged) {
+        for (int u = 0; u < nuniq; ++u) {
+          const int idx = s_uidx[u];
+          if (idx < NA) acc += s_ucz[u] * bw.BT[m][(size_t)idx * bw.ldbt[m] + t];
+        }
+      } else {
+        for (int j = 0; j < S; ++j) {
+          const size_t set = (size_t)c * S + j;
+          const int h = out.hull_cnt[set];
+          const double w = bw.W[j * M + m];
+          const double om = (w * w) / bw.sdj[set];
+          HullReader rd(out, set);
+          for (int k = 0; k < h; ++k) {
+            if (!rd.seek(k)) { s_broken = 1; break; }
+            const int idx = rd.idx();
+            if (idx < NA) acc += om * rd.q() * invS * bw.BT[m][(size_t)idx * bw.ldbt[m] + t];
+          }
         }
       }
       s_r[t] = acc;
@@ -314,45 +429,58 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
       double xm[MAX_D];
 #pragma unroll
       for (int k = 0; k < MAX_D; ++k) xm[k] = k < d ? bw.X[(size_t)c * d + k] / bw.ls[m][k] : 0.0;
-      for (int j = lane; j < S; j += 32) {
-        const size_t set = (size_t)c * S + j;
-        const int h = out.hull_cnt[set];
-        const double w = bw.W[j * M + m];
-        const double sd = bw.sdj[set];
-        const double om = (w * w) / sd;
-        double w2j[MAX_M];
+      // prior-covariance path of one line with coefficient cz = Gz_m[n] (or one record's share of it)
+      auto line_terms = [&](int idx, double cz) {
+        if (idx == NA) {
+          gzown += cz;
+        } else {
+          double sq = 0.0;
 #pragma unroll
-        for (int mm = 0; mm < MAX_M; ++mm) w2j[mm] = mm < M ? bw.W2[j * M + mm] : 0.0;
-        const double rinv = 1.0 / sd;
-        auto slope = [&](int n) {  // b_jn, formed as everywhere else (line_slope)
-          double sacc = 0.0;
-          for (int mm = 0; mm < M; ++mm) sacc = fma(w2j[mm], bw.COV[mm][(size_t)c * bw.ldz + n], sacc);
-          return coupled_quotient(sacc, sd, rinv);
-        };
-        double qb = 0.0;  // sum_n (q / S) b_jn
-        HullReader rd(out, set);
-        for (int k = 0; k < h; ++k) {
-          if (!rd.seek(k)) { s_broken = 1; break; }
-          const int idx = rd.idx();
-          const double qs = rd.q() * invS;
-          qb += qs * slope(idx);
-          if (idx == NA) {
-            gzown += om * qs;
-          } else {
-            double sq = 0.0;
+          for (int q = 0; q < MAX_D; ++q)
+            if (q < d) {
+              const double df = xm[q] - bw.xd_s[m][(size_t)idx * d + q];
+              sq += df * df;
+            }
+          const double gc = stationary_grad_coeff(bw.kind[m], bw.outputscale[m], sq);
 #pragma unroll
-            for (int q = 0; q < MAX_D; ++q)
-              if (q < d) {
-                const double df = xm[q] - bw.xd_s[m][(size_t)idx * d + q];
-                sq += df * df;
-              }
-            const double gc = stationary_grad_coeff(bw.kind[m], bw.outputscale[m], sq);
-#pragma unroll
-            for (int q = 0; q < MAX_D; ++q)
-              if (q < d) gkd[q] += om * qs * gc * (xm[q] - bw.xd_s[m][(size_t)idx * d + q]) / bw.ls[m][q];
-          }
+          for (int q = 0; q < MAX_D; ++q)
+            if (q < d) gkd[q] += cz * gc * (xm[q] - bw.xd_s[m][(size_t)idx * d + q]) / bw.ls[m][q];
         }
-        cv -= (w * w) / (2.0 * sd * sd) * qb;
+      };
+      if (merged) {
+        for (int u = lane; u < nuniq; u += 32) line_terms(s_uidx[u], s_ucz[u]);
+        for (int j = lane; j < S; j += 32) {
+          const double w = bw.W[j * M + m];
+          const double sd = bw.sdj[(size_t)c * S + j];
+          cv -= (w * w) / (2.0 * sd * sd) * s_qb[j];
+        }
+      } else {
+        for (int j = lane; j < S; j += 32) {
+          const size_t set = (size_t)c * S + j;
+          const int h = out.hull_cnt[set];
+          const double w = bw.W[j * M + m];
+          const double sd = bw.sdj[set];
+          const double om = (w * w) / sd;
+          double w2j[MAX_M];
+#pragma unroll
+          for (int mm = 0; mm < MAX_M; ++mm) w2j[mm] = mm < M ? bw.W2[j * M + mm] : 0.0;
+          const double rinv = 1.0 / sd;
+          auto slope = [&](int n) {  // b_jn, formed as everywhere else (line_slope)
+            double sacc = 0.0;
+            for (int mm = 0; mm < M; ++mm) sacc = fma(w2j[mm], bw.COV[mm][(size_t)c * bw.ldz + n], sacc);
+            return coupled_quotient(sacc, sd, rinv);
+          };
+          double qb = 0.0;  // sum_n (q / S) b_jn
+          HullReader rd(out, set);
+          for (int k = 0; k < h; ++k) {
+            if (!rd.seek(k)) { s_broken = 1; break; }
+            const int idx = rd.idx();
+            const double qs = rd.q() * invS;
+            qb += qs * slope(idx);
+            line_terms(idx, om * qs);
+          }
+          cv -= (w * w) / (2.0 * sd * sd) * qb;
+        }
       }
       gzown = warp_sum(gzown);
       cv = warp_sum(cv);
@@ -386,7 +514,7 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
     }
     if (threadIdx.x == 0)
       for (int k = 0; k < MAX_D; ++k) grad[k] += s2 * s_sc[2 + k];  // prior-covariance term, once
-    __syncthreads();  // s_r / s_sc are reused by the next objective
+    __syncthreads();  // s_r / s_sc / s_om / s_ucz are reused by the next objective
   }
 #pragma unroll
   for (int k = 0; k < MAX_D; ++k) grad[k] = warp_sum(grad[k]);
@@ -407,7 +535,8 @@ int emax_finalize_coupled(int C, int S, const EmaxOut& out, const CoupledBackwar
   for (int m = 0; m < bw.M; ++m) n_pad_max = n_pad_max > bw.n_pad[m] ? n_pad_max : bw.n_pad[m];
   size_t smem = sizeof(double) * S;
   if (bw.dX != nullptr)
-    smem = sizeof(double) * ((size_t)S + n_pad_max + 2 + MAX_D + MAX_M + (CP_THREADS / 32) * MAX_D);
+    smem = sizeof(double) * ((size_t)S + n_pad_max + 2 + MAX_D + MAX_M + (CP_THREADS / 32) * MAX_D + 2 * fin_rmax(S) + 2 * S) +
+           sizeof(int) * ((size_t)5 * fin_rmax(S) + ((S + 2) & ~1) + (2 << fin_hash_bits(S)));
   if (smem > 47 * 1024)
     DKG_CUDA_OK(cudaFuncSetAttribute(finalize_coupled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   finalize_coupled_kernel<<<C, CP_THREADS / 2, smem, st>>>(S, out, bw);  // short barrier-separated phases: more CTAs per SM

@@ -2152,11 +2152,6 @@ int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cu
 // overflow kernel: one CTA per queued set, all lines, always terminates
 // ------------------------------------------------------------------------------------------
 constexpr int OVF_MAXV = 130;  // chain vertices
-constexpr int FIN_RMAX = 2560; // most hull records per candidate merged in shared memory (10 per scalarisation)
-// slots of the distinct-line hash table (a power of two; distinct hull lines per candidate: tens at S = 16,
-// many hundreds at S = 256)
-__host__ __device__ inline int fin_hash_bits(int S) { return S <= 64 ? 10 : 12; }
-__host__ __device__ inline int fin_rmax(int S) { const int r = 10 * S; return r < 256 ? 256 : r > FIN_RMAX ? FIN_RMAX : r; }
 constexpr int OVF_ROUNDS = 6;
 constexpr int OVF_CTAS_PER_SM = 4;
 

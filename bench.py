@@ -427,8 +427,8 @@ def main():
                 "share_of_step": ms_g / tot_prof if tot_prof > 0 else None, "traffic": None,
             }
         elif int8_engine:
-            # The contraction runs on the int8 tensor cores as 34 exact digit-plane products
-            # (7 base-256 digits, 8 diagonals; csrc/dkg_ozaki.cu) of K padded to 32.  Its roofline is
+            # The contraction runs on the int8 tensor cores as 28 exact digit-plane products
+            # (7 balanced base-256 digits, 7 diagonals; csrc/dkg_ozaki.cu) of K padded to 32.  Its roofline is
             # the int8 tensor peak; B200's dense i8 rate is twice its bf16 rate, and the bf16 rate
             # is the measured cuBLAS figure of MEASURED_PEAKS.json (burst: this kernel is timed alone).
             bf16 = None
@@ -438,7 +438,10 @@ def main():
                 src = "2 x MEASURED_PEAKS.json bf16_tflops (burst)"
             except Exception:
                 bf16, src = 2250.0, "2 x 2250 TFLOP/s nominal dense bf16 (B200_PROFILING.md fallback)"
-            products = 34.0 if args.precision == "float64" else 10.0  # digit-pair products (7/8 or 4/4 digits/diagonals)
+            # digit-pair products = pairs (i, j) of digits with i + j < diagonals: 7 balanced signed digits and 7
+            # diagonals -> 28 (round 1: unsigned digits needed 8 diagonals -> 34); reduced precision 4 / 4 -> 10
+            ns, ng = (7, int(os.environ.get("DKG_OZ_DIAGONALS", "7"))) if args.precision == "float64" else (4, 4)
+            products = float(sum(1 for i in range(ns) for j in range(ns) if i + j < ng))
             kp = sum(-(-m.n // 32) * 32 for m in P.model.models) / sum(m.n for m in P.model.models)
             int8_ops = flops_total * products * kp
             int8_peak = 2.0 * bf16
@@ -469,11 +472,11 @@ def main():
                 "avg_launch_ms": ms_g / max(n_g, 1),
                 "share_of_step": ms_g / tot_prof if tot_prof > 0 else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this shape from the
-                # ncu --set full capture profiles/r02e_emax_obj0_tilefilter_v1_ncu.csv (60.4 MB + 488.3 MB; algorithmic:
+                # ncu --set full capture profiles/r04c_obj0_kernels_ncu.csv (61.4 MB + 489.8 MB; algorithmic:
                 # 537 MB of product rows written once, digit planes served from L2)
-                "traffic": 548.7e6 if (n_cand == 4096 and N == 16384 and args.precision == "float64") else None,
-                "traffic_source": "profiles/r02e_emax_obj0_tilefilter_v1_ncu.csv (ncu --set full, one launch, c4 shape)",
-                "tensor_pipe_active_ncu_pct": 63.6 if (n_cand == 4096 and N == 16384 and args.precision == "float64") else None,
+                "traffic": 551.3e6 if (n_cand == 4096 and N == 16384 and args.precision == "float64") else None,
+                "traffic_source": "profiles/r04c_obj0_kernels_ncu.csv (ncu --set full, one launch, c4 shape)",
+                "tensor_pipe_active_ncu_pct": 58.6 if (n_cand == 4096 and N == 16384 and args.precision == "float64") else None,
             }
         else:
             roofline = {

@@ -919,7 +919,7 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
     CoupledArgs ca;
     ca.C = cc; ca.S = S; ca.M = M; ca.d = d; ca.N = N; ca.ldz = p->ldz;
     ca.W = p->W; ca.W2 = p->W2; ca.sdj = w.sdj + (size_t)c0 * S; ca.Zc = w.Zc;  // Zc == nullptr: statistics only
-    ca.zpv = w.zpv; ca.zpi = w.zpi;
+    ca.zpv = w.zpv; ca.zpi = w.zpi; ca.zst = w.zst; ca.zarg = w.zarg;
     for (int m = 0; m < M; ++m) {
       const ObjState& o = p->obj[m];
       // covariance rows of objective m: same GEMM as the decoupled path with sd = 1

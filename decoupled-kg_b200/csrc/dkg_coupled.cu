@@ -11,6 +11,8 @@
 //   finalize_coupled: kg[c] = mean_j and the envelope-theorem backward through all M objectives.
 #include "dkg_emax.cuh"
 
+#include <cstdlib>
+
 namespace dkg {
 
 constexpr int CP_THREADS = 256;
@@ -189,13 +191,153 @@ coupled_stats_kernel(CoupledArgs a, int nseg) {
   }
 }
 
+// ---- statistics only, coarse ranges first (default) ---------------------------------------------
+// The exact (min, max, index) bookkeeping above costs ~8 of the ~12 instructions per (line, scalarisation) of
+// an issue-bound kernel.  The HIGH WORD of a double (sign, exponent, 20 mantissa bits), mapped from
+// sign-magnitude to two's complement, is a monotone (non-strict) integer image of the value, so the exact minimum
+// of a row lies in a segment whose smallest key equals the smallest key of the row: pass 1 only keeps the key
+// range of the numerators per (row, segment) -- M fp64 FMAs and four integer ALU instructions per (line,
+// scalarisation), one REDUX pair per (segment, scalarisation); a float conversion instead of the key runs on the
+// quarter-rate conversion pipe and was the limiter -- and pass 2 (one warp per row) re-forms the numerators of
+// just the segments that attain the row's extreme keys, exactly, with the first index winning ties.
+__device__ __forceinline__ int order_key(double s) {
+  const int hi = __double2hiint(s);
+  return hi ^ ((hi >> 31) & 0x7fffffff);
+}
+
+template <int MT>
+__global__ void __launch_bounds__(CST_WARPS * 32)
+coupled_range_kernel(CoupledArgs a, int nseg, int2* __restrict__ zrange) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = blockIdx.x * CST_WARPS + warp, c = blockIdx.y;
+  if (seg >= nseg) return;
+  constexpr int E = CST_SEG / 32;
+  const int n_lo = seg * CST_SEG + lane;
+  const bool whole = (seg + 1) * CST_SEG <= a.N + 1;  // (warp-uniform) every line of the segment exists
+  double cov[MT][E];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int n = n_lo + e * 32;  // column N is the candidate's own line
+      cov[m][e] = (m < a.M && n <= a.N) ? a.COV[m][(size_t)c * a.ldz + n] : 0.0;
+    }
+#pragma unroll 2
+  for (int j = 0; j < a.S; ++j) {
+    double w2[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) w2[m] = m < a.M ? a.W2[j * a.M + m] : 0.0;
+    int klo = 0x7fffffff, khi = (int)0x80000000;
+    if (whole) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        double s = 0.0;  // (same fma order as line_slope(): identical bits in every stage)
+#pragma unroll
+        for (int m = 0; m < MT; ++m) s = fma(w2[m], cov[m][e], s);  // (w2 = cov = 0 beyond M)
+        const int k = order_key(s);
+        klo = min(klo, k);
+        khi = max(khi, k);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) s = fma(w2[m], cov[m][e], s);  // (w2 = cov = 0 beyond M)
+        const int k = order_key(s);
+        if (n_lo + e * 32 <= a.N) {
+          klo = min(klo, k);
+          khi = max(khi, k);
+        }
+      }
+    }
+    klo = __reduce_min_sync(0xffffffffu, klo);
+    khi = __reduce_max_sync(0xffffffffu, khi);
+    if (lane == 0) zrange[((size_t)c * a.S + j) * nseg + seg] = make_int2(klo, khi);
+  }
+}
+
+// one warp per row (candidate, scalarisation): exact extremes of the numerator from the segments that attain
+// the extreme keys, then the quotient (monotone in the numerator) once per extreme
+__global__ void __launch_bounds__(CP_THREADS)
+coupled_zreduce_kernel(CoupledArgs a, int nseg, const int2* __restrict__ zrange) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (CP_THREADS / 32) + (threadIdx.x >> 5);
+  if (row >= a.C * a.S) return;
+  const int c = row / a.S, j = row - c * a.S;
+  const int2* zr = zrange + (size_t)row * nseg;
+  int glo = 0x7fffffff, ghi = (int)0x80000000;
+  for (int t = lane; t < nseg; t += 32) {
+    const int2 f = zr[t];
+    glo = min(glo, f.x);
+    ghi = max(ghi, f.y);
+  }
+  glo = __reduce_min_sync(0xffffffffu, glo);
+  ghi = __reduce_max_sync(0xffffffffu, ghi);
+  double w2[MAX_M];
+#pragma unroll
+  for (int m = 0; m < MAX_M; ++m) w2[m] = m < a.M ? a.W2[j * a.M + m] : 0.0;
+  double vmin = INFINITY, vmax = -INFINITY;
+  int imin = 0x7fffffff, imax = 0x7fffffff;
+  for (int t0 = 0; t0 < nseg; t0 += 32) {
+    const int t = t0 + lane;
+    const int2 f = t < nseg ? zr[t] : make_int2(0x7fffffff, (int)0x80000000);
+    unsigned hit = __ballot_sync(0xffffffffu, t < nseg && (f.x == glo || f.y == ghi));
+    while (hit) {
+      const int seg = t0 + __ffs(hit) - 1;
+      hit &= hit - 1u;
+      for (int e = 0; e < CST_SEG / 32; ++e) {
+        const int n = seg * CST_SEG + lane + 32 * e;
+        if (n <= a.N) {
+          double s = 0.0;
+#pragma unroll
+          for (int m = 0; m < MAX_M; ++m)
+            if (m < a.M) s = fma(w2[m], a.COV[m][(size_t)c * a.ldz + n], s);
+          if (s < vmin) { vmin = s; imin = n; }
+          if (s > vmax) { vmax = s; imax = n; }
+        }
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, vmin, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, imin, o);
+    if (ov < vmin || (ov == vmin && oi < imin)) { vmin = ov; imin = oi; }
+    const double pv = __shfl_xor_sync(0xffffffffu, vmax, o);
+    const int pi = __shfl_xor_sync(0xffffffffu, imax, o);
+    if (pv > vmax || (pv == vmax && pi < imax)) { vmax = pv; imax = pi; }
+  }
+  if (lane == 0) {
+    const double sd = a.sdj[row], rinv = 1.0 / sd;
+    a.zst[row * 2 + 0] = coupled_quotient(vmin, sd, rinv);
+    a.zst[row * 2 + 1] = coupled_quotient(vmax, sd, rinv);
+    a.zarg[row * 2 + 0] = imin;
+    a.zarg[row * 2 + 1] = imax;
+  }
+}
+
+template <int MT>
+static int launch_coupled_ranges(const CoupledArgs& a, cudaStream_t st) {
+  const int nseg = ceil_div(a.N + 1, CST_SEG);
+  int2* zrange = reinterpret_cast<int2*>(a.zpv);  // [C * S, nseg] int2 <= the [C * S, tiles, 2] doubles reserved
+  coupled_range_kernel<MT><<<dim3(ceil_div(nseg, CST_WARPS), a.C), CST_WARPS * 32, 0, st>>>(a, nseg, zrange);
+  DKG_LAUNCH_CHECK();
+  coupled_zreduce_kernel<<<ceil_div(a.C * a.S, CP_THREADS / 32), CP_THREADS, 0, st>>>(a, nseg, zrange);
+  DKG_LAUNCH_CHECK();
+  return DKG_OK;
+}
+
+// segments of per-(row, segment) partials the caller has to reduce (emax_zstat_from_partials); 0: the row
+// statistics were written directly
 int coupled_stat_segments(int N, bool materialised) {
+  if (!materialised && getenv("DKG_COUPLED_STATS_EXACT") == nullptr) return 0;
   return ceil_div(N + 1, materialised ? CS_TILE_LINES : CST_SEG);
 }
 
 template <int MT>
 static int launch_coupled_stats(const CoupledArgs& a, cudaStream_t st) {
-  const int nseg = coupled_stat_segments(a.N, false);
+  if (a.zst != nullptr && a.zarg != nullptr && getenv("DKG_COUPLED_STATS_EXACT") == nullptr) return launch_coupled_ranges<MT>(a, st);
+  const int nseg = ceil_div(a.N + 1, CST_SEG);
   const size_t smem = (size_t)CST_WARPS * 32 * CST_PITCH * (sizeof(double) + sizeof(int));
   DKG_CUDA_OK(cudaFuncSetAttribute(coupled_stats_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   coupled_stats_kernel<MT><<<dim3(ceil_div(nseg, CST_WARPS), a.C), CST_WARPS * 32, smem, st>>>(a, nseg);

@@ -485,8 +485,10 @@ int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int
 
 int emax_zstat_from_partials(const LineBatch& lb, const EmaxScratch& sc, int ntiles, cudaStream_t st) {
   if (lb.C == 0) return DKG_OK;
-  zreduce_kernel<<<ceil_div(lb.C, 128), 128, 0, st>>>(lb, lb.NL, ntiles, sc.zpv, sc.zpi, sc.zst, sc.zarg);
-  DKG_LAUNCH_CHECK();
+  if (ntiles > 0) {
+    zreduce_kernel<<<ceil_div(lb.C, 128), 128, 0, st>>>(lb, lb.NL, ntiles, sc.zpv, sc.zpi, sc.zst, sc.zarg);
+    DKG_LAUNCH_CHECK();
+  }
   const long long sets = (long long)lb.C * lb.S;
   chain_kernel<<<(unsigned)((sets + E_THREADS - 1) / E_THREADS), E_THREADS, 0, st>>>(lb, sc);
   DKG_LAUNCH_CHECK();
@@ -1361,10 +1363,11 @@ static int launch_filter32(const LineBatch& lb, const EmaxScratch& sc, cudaStrea
 // exactly (line_slope) when they are written out, so the hull stage sees the same bits as every other stage.
 constexpr int FC_CG = 2;  // candidates per CTA
 constexpr int FC_JG = 2;  // scalarisations per step
+constexpr int FC_NB = 4;  // line blocks (512 lines each) per CTA
 
 template <int MT, bool REFINE>
 __global__ void __launch_bounds__(F32_THREADS, 4)
-filter32_cov_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb) {
+filter32_cov_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb, int nblk_phase) {
   extern __shared__ __align__(16) unsigned char e_smem[];
   const int SR = lb.row_mod, M = lb.cov_M;
   const int ncand = lb.C / SR;
@@ -1390,7 +1393,14 @@ filter32_cov_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb) {
     const int j = e / MT, m = e - j * MT;
     s_w2[e] = m < M ? lb.cov_w2[j * M + m] : 0.0;
   }
-  const int n0 = (line_block(blockIdx.x, blk_step, nsb, REFINE) * F32_THREADS + (int)threadIdx.x) * 4;
+  const float ninf = -INFINITY;
+  const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+  int wcnt = 0;  // entries in this warp's pool (warp-uniform)
+  __syncthreads();
+  // FC_NB line blocks per CTA: the chain parameters / reciprocals / weights above are loaded once for all of
+  // them (with one block per CTA that set-up and its barrier were a fifth of the kernel's instructions)
+  for (int bi = blockIdx.x * FC_NB; bi < min(nblk_phase, (int)(blockIdx.x + 1) * FC_NB); ++bi) {
+  const int n0 = (line_block(bi, blk_step, nsb, REFINE) * F32_THREADS + (int)threadIdx.x) * 4;
   const bool live = n0 < lb.NA;  // lines n0..n0+3; beyond NA the float table holds -inf (never kept)
   double cv[FC_CG][MT][4];
 #pragma unroll
@@ -1405,11 +1415,6 @@ filter32_cov_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb) {
       }
       cv[cl][m][0] = v0.x; cv[cl][m][1] = v0.y; cv[cl][m][2] = v1.x; cv[cl][m][3] = v1.y;
     }
-  const float ninf = -INFINITY;
-  const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
-  int wcnt = 0;  // entries in this warp's pool (warp-uniform)
-  __syncthreads();
-
   for (int j0 = 0; j0 < SR; j0 += FC_JG) {
     unsigned mask = 0u;
 #pragma unroll
@@ -1429,8 +1434,7 @@ filter32_cov_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb) {
         for (int u = 0; u < 4; ++u) {
           double sacc = 0.0;
 #pragma unroll
-          for (int m = 0; m < MT; ++m)
-            if (m < M) sacc = fma(w2[m], cv[cl][m][u], sacc);
+          for (int m = 0; m < MT; ++m) sacc = fma(w2[m], cv[cl][m][u], sacc);  // (w2 = cv = 0 beyond M)
           zf[u] = __double2float_rn(sacc * ri);
         }
         const ulonglong2 q1 = s_p32[2 * setl], q2 = s_p32[2 * setl + 1];
@@ -1466,6 +1470,7 @@ filter32_cov_kernel(LineBatch lb, EmaxScratch sc, int blk_step, int nsb) {
       wcnt += __popc(vote);
     }
   }
+  }  // line blocks
   flush_warp_pool<(1 << 20), REFINE>(lb, sc, pool, wcnt, row0, 0, s_far);
   __syncthreads();
   for (int e = threadIdx.x; e < 2 * nset; e += blockDim.x) {
@@ -1489,12 +1494,12 @@ static int launch_filter32_cov(const LineBatch& lb, const EmaxScratch& sc, cudaS
   // (two phases as in launch_filter32: sampled line blocks, second-level chain, the rest)
   const bool two_phase = sc.chain5 != nullptr && sc.chainv != nullptr && nblk >= 8;
   const int nsb = two_phase ? 2 : nblk, step = two_phase ? nblk / 2 : 1;
-  filter32_cov_kernel<MT, false><<<dim3(nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
+  filter32_cov_kernel<MT, false><<<dim3(ceil_div(nsb, FC_NB), gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb, nsb);
   DKG_LAUNCH_CHECK();
   if (two_phase) {
     chain5_kernel<<<(unsigned)((lb.C + E_THREADS - 1) / E_THREADS), E_THREADS, 0, st>>>(lb, sc);
     DKG_LAUNCH_CHECK();
-    filter32_cov_kernel<MT, true><<<dim3(nblk - nsb, gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb);
+    filter32_cov_kernel<MT, true><<<dim3(ceil_div(nblk - nsb, FC_NB), gy), F32_THREADS, smem, st>>>(lb, sc, step, nsb, nblk - nsb);
     DKG_LAUNCH_CHECK();
   }
   return DKG_OK;

@@ -199,7 +199,8 @@ struct CovFinish {
 };
 int emax_zstat(const LineBatch& lb, const EmaxScratch& sc, double* amax_out, int* aarg_out,
                cudaStream_t st, const CovFinish* fin = nullptr, bool* ztile_written = nullptr);
-// row statistics from per-tile partials (sc.zpv / sc.zpi filled by the producer of the slope rows),
+// row statistics from per-tile partials (sc.zpv / sc.zpi filled by the producer of the slope rows;
+// ntiles == 0: sc.zst / sc.zarg are final already, only the chord chains are written),
 // then the chord chains: replaces emax_zstat when the producer already saw every slope
 int emax_zstat_from_partials(const LineBatch& lb, const EmaxScratch& sc, int ntiles, cudaStream_t st);
 // ztile_valid: sc.ztile holds the per-tile slope ranges of this batch (written by emax_zstat)
@@ -270,6 +271,10 @@ struct CoupledArgs {
   // statistics need no second pass over Zc; tile = CS_TILE_LINES consecutive entries of the N + 1
   double* zpv = nullptr;            // [C * S, tiles, 2]
   int* zpi = nullptr;               // [C * S, tiles, 2]
+  // statistics-only form: the final row statistics are written here directly (zpv then only holds the
+  // per-segment float ranges of the slope numerators)
+  double* zst = nullptr;            // [C * S, 2]
+  int* zarg = nullptr;              // [C * S, 2]
 };
 constexpr int CS_TILE_LINES = 256;  // one warp's segment (materialised slope rows)
 constexpr int CST_SEG = 512;        // one warp's segment (statistics only: the covariance values stay in registers)

@@ -235,7 +235,7 @@ static void destroy_plan(dkg_plan* p) {
   }
   dev_free(p->W); dev_free(p->W2); dev_free(p->wt); dev_free(p->xd); dev_free(p->alpha_all);
   dev_free(p->mu_disc); dev_free(p->A0); dev_free(p->A0f); dev_free(p->A0max); dev_free(p->A0arg);
-  dev_free(p->A0tmax); dev_free(p->perm);
+  dev_free(p->A0tmax); dev_free(p->A0targ); dev_free(p->perm);
   free_workspace(p->ws);
   delete p;
 }
@@ -506,7 +506,8 @@ static int build_plan(dkg_plan* p, const dkg_objective* objs, const double* x_di
       rc = build_a0(p->mu_disc, N, M, p->W, S, p->A0, p->A0f, p->N_pad, p->A0max, p->A0arg, st);
       p->a0_tiles = ceil_div(p->N_pad, FILTER_TILE);
       if (rc == DKG_OK) rc = dev_alloc(&p->A0tmax, (size_t)S * p->a0_tiles);
-      if (rc == DKG_OK) rc = build_a0_tilemax(p->A0f, p->N_pad, S, FILTER_TILE, p->a0_tiles, p->A0tmax, st);
+      if (rc == DKG_OK) rc = dev_alloc(&p->A0targ, (size_t)S * p->a0_tiles);
+      if (rc == DKG_OK) rc = build_a0_tilemax(p->A0f, p->N_pad, S, FILTER_TILE, p->a0_tiles, p->A0tmax, p->A0targ, st);
     }
   }
   cudaStreamSynchronize(st);
@@ -810,7 +811,7 @@ static int forward_once(dkg_plan* p, const double* X, int C, double* kg, double*
     lb.Z = w.Z; lb.ldz = p->ldz;
     lb.A = p->A0; lb.a_sc = 0; lb.a_sj = p->N_pad;
     lb.A32 = p->A0f;
-    lb.A32tmax = p->A0tmax; lb.a32_tiles = p->a0_tiles;
+    lb.A32tmax = p->A0tmax; lb.A32targ = p->A0targ; lb.a32_tiles = p->a0_tiles;
     lb.a_own = w.a_new + (size_t)c0 * S;
     lb.wt = p->wt;
     lb.Amax = p->A0max; lb.Aarg = p->A0arg; lb.am_sc = 0;
@@ -946,7 +947,7 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
     }
     lb.A = p->A0; lb.a_sc = 0; lb.a_sj = p->N_pad;
     lb.A32 = p->A0f;
-    lb.A32tmax = p->A0tmax; lb.a32_tiles = p->a0_tiles;
+    lb.A32tmax = p->A0tmax; lb.A32targ = p->A0targ; lb.a32_tiles = p->a0_tiles;
     lb.a_own = w.a_new + (size_t)c0 * S;
     lb.wt = nullptr;
     lb.Amax = p->A0max; lb.Aarg = p->A0arg; lb.am_sc = 0;
@@ -1126,7 +1127,7 @@ int dkg_plan_append_point(dkg_plan* plan, int32_t m, const double* x_host, doubl
   if (state) A(make_kxd_digits(o, p, st));
   A(mu_disc(p->xd, N, d, o, p->mu_disc, p->M, m, st));
   A(build_a0(p->mu_disc, N, p->M, p->W, p->S, p->A0, p->A0f, p->N_pad, p->A0max, p->A0arg, st));
-  A(build_a0_tilemax(p->A0f, p->N_pad, p->S, FILTER_TILE, p->a0_tiles, p->A0tmax, st));
+  A(build_a0_tilemax(p->A0f, p->N_pad, p->S, FILTER_TILE, p->a0_tiles, p->A0tmax, p->A0targ, st));
   if (m == p->target) { p->chol = o.chol; }
   drop_graphs(p->ws);  // captured launches carry n
   cudaError_t e = cudaStreamSynchronize(st);

@@ -985,6 +985,60 @@ probe32_kernel(LineBatch lb, EmaxScratch sc, int JB) {
   }
 }
 
+// Champion probe (default when the plan carries the tile champions).  The sample above covers 1/16 of the lines
+// wherever they happen to lie; the vertices U / V that make the second-level chain tight are HIGH lines.  The
+// plan knows, per (128-line tile, scalarisation), the line with the largest intercept of the tile (the intercept
+// table is candidate-independent), and within a Morton tile the slopes vary little, so that line is (nearly) the
+// tile's farthest line above any chord.  Probing just those N / 128 champions per set -- one gathered slope each,
+// the 16 champions of a tile lie within 1 KB of the slope row -- finds better vertices with an eighth of the
+// tests: survivors per set 40 -> 20 / 8.5 -> 5.6 on the two c4 objectives (CPU simulation before the kernel was
+// written; measured: see DESIGN.md), which is what the hull stage pays for.
+constexpr int PC_THREADS = 256;
+
+__global__ void __launch_bounds__(PC_THREADS)
+probe_champ_kernel(LineBatch lb, EmaxScratch sc) {
+  extern __shared__ __align__(16) unsigned char e_smem[];
+  unsigned long long* s_far = reinterpret_cast<unsigned long long*>(e_smem);  // [S][2]
+  const int S = lb.S, c = blockIdx.x;
+  for (int e = threadIdx.x; e < 2 * S; e += blockDim.x) s_far[e] = 0ull;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int half = lane >> 4, jl = lane & 15;
+  const int ntiles = lb.a32_tiles;
+  const double* zrow = lb.Z + (size_t)c * lb.ldz;
+  for (int jb = 0; jb < S; jb += 16) {
+    const int j = jb + jl;
+    const bool j_ok = j < S;
+    float4 q1 = make_float4(0.f, 0.f, INFINITY, INFINITY), q2 = q1;  // (m, m, c, c) of the chords P-T, T-Q
+    if (j_ok) {
+      q1 = sc.chain32[((size_t)c * S + j) * 2];
+      q2 = sc.chain32[((size_t)c * S + j) * 2 + 1];
+    }
+    for (int t0 = 2 * warp; t0 < ntiles; t0 += 2 * nwarp) {
+      const int tile = t0 + half;
+      if (!j_ok || tile >= ntiles) continue;
+      const int n = lb.A32targ[(size_t)tile * S + j];
+      if (n < 0 || n >= lb.NA) continue;
+      const float a = lb.A32tmax[(size_t)tile * S + j];
+      const double zv = zrow[n];
+      const float z = __double2float_rn(zv);
+      if ((a > fmaf(q1.x, z, q1.z)) | (a > fmaf(q2.x, z, q2.z))) {
+        const double av = lb.A[a_base(lb, c, j) + n];
+        const double4 par = sc.chain[(size_t)c * S + j];
+        const double t1 = fma(par.y, zv, par.x), t2 = fma(par.w, zv, par.z);
+        const int side = t1 <= t2 ? 0 : 1;
+        const double ex = av - (side == 0 ? t1 : t2);
+        if (ex > 0.0) atomicMax(&s_far[2 * j + side], pack_excess(ex, n));
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * S; e += blockDim.x) {
+    const unsigned long long key = s_far[e];
+    if (key) atomicMax(&sc.far[(size_t)c * S * 2 + e], key);
+  }
+}
+
 constexpr int TF_THREADS = 256;
 constexpr int TF_POOL = 128;  // parked (line, scalarisation) entries per warp
 
@@ -1152,7 +1206,11 @@ tilefilter_kernel(LineBatch lb, EmaxScratch sc, int pairs_per_warp, int njb, int
 
 static int launch_tilefilter(const LineBatch& lb, const EmaxScratch& sc, cudaStream_t st, bool ztile_valid) {
   const long long sets = (long long)lb.C * lb.S;
-  {  // probe: every PROBE_STRIDE-th line against the 3-point chain -> farthest line above each chord
+  if (lb.A32targ != nullptr && getenv("DKG_PROBE_SAMPLE") == nullptr) {
+    // probe: the tile champions against the 3-point chain -> farthest champion above each chord
+    probe_champ_kernel<<<lb.C, PC_THREADS, (size_t)2 * lb.S * sizeof(unsigned long long), st>>>(lb, sc);
+    DKG_LAUNCH_CHECK();
+  } else {  // probe: 16 lines out of every 256 against the 3-point chain -> farthest line above each chord
     const int nsamp = ceil_div(lb.NA, PROBE_PERIOD) * PROBE_CHUNK;
     const int JB = lb.S <= 64 ? lb.S : 32;
     const size_t smem = (size_t)PROBE_G * JB * (2 * sizeof(float4) + 2 * sizeof(unsigned long long));
@@ -2141,7 +2199,8 @@ int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cu
   // hull records beyond the inline capacity go through the warp-wide recorder of hull_kernel only
   // measured at c4: with ~9 survivors per set the 8-lane kernel takes the hull stage from 0.227 to 0.182 ms; with
   // ~32 per set (a third of the sets short) the extra launch costs more than it saves (0.385 -> 0.409 ms)
-  const bool use_short = !(e != nullptr && atoi(e) == 0) && (survivors_hint < 0.0 || survivors_hint <= 16.0) &&
+  static const double short_max = getenv("DKG_HULL_SHORT_MAX") != nullptr ? atof(getenv("DKG_HULL_SHORT_MAX")) : 16.0;
+  const bool use_short = !(e != nullptr && atoi(e) == 0) && (survivors_hint < 0.0 || survivors_hint <= short_max) &&
                          (out.hull_cap >= HS_LINES || (out.hull_idx == nullptr && out.hull_x == nullptr));
   if (use_short) {
     const long long per_cta = (long long)wpb * (32 / HS_G);

@@ -19,6 +19,7 @@ struct LineBatch {
   const double* A = nullptr;
   const float* A32 = nullptr;      // optional float copy of A (same strides; shared table only): fp32 chord filter
   const float* A32tmax = nullptr;  // optional [a32_tiles, S] max of A32 over tiles of FILTER_TILE lines (tile culling)
+  const int* A32targ = nullptr;    // optional [a32_tiles, S] the line attaining it (-1: the tile is padding only)
   int a32_tiles = 0;
   long long a_sc = 0;
   int a_sj = 0;

@@ -19,7 +19,7 @@ int mu_disc(const double* xd, int N, int d, const ObjState& o, double* mu, int M
 int build_a0(const double* mu, int N, int M, const double* W, int S, double* A0, float* A0f, int ld,
              double* A0max, int* A0arg, cudaStream_t st);
 
-int build_a0_tilemax(const float* A0f, int ld, int S, int tile, int ntiles, float* out, cudaStream_t st);
+int build_a0_tilemax(const float* A0f, int ld, int S, int tile, int ntiles, float* out, int* out_arg, cudaStream_t st);
 int gather_rows(const double* in, const int* perm, int rows, int d, double* out, cudaStream_t st);
 int unpermute(const double* src, long long ld, long long rows, long long cols, const int* perm, int n_perm, bool by_rows,
               double* out, cudaStream_t st);

@@ -140,6 +140,7 @@ struct dkg_plan {
   double* A0 = nullptr;       // [S, N_pad]   scalarised intercepts of the discretisation lines
   float* A0f = nullptr;       // [S, N_pad]   float copy of A0 (fp32 chord filter; padding = -inf)
   float* A0tmax = nullptr;    // [a0_tiles, S] max of A0f over tiles of FILTER_TILE consecutive lines (tile culling)
+  int* A0targ = nullptr;      // [a0_tiles, S] the line attaining it (the tile's champion: sample of the second-level chain)
   int a0_tiles = 0;
   // Internal line order: the discretisation is re-ordered along a Morton curve at plan time, so that
   // FILTER_TILE consecutive lines are neighbours in input space -- similar posterior means and similar

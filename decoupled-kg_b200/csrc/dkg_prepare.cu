@@ -341,18 +341,30 @@ __global__ void a0max_kernel(const double* __restrict__ A0, int N, int ld, doubl
 
 // A0tmax[t, j] = max of the float intercepts of scalarisation j over the lines [t * tile, (t + 1) * tile):
 // the fp32 chord filter culls a whole warp tile of lines with one test against it
-__global__ void a0_tilemax_kernel(const float* __restrict__ A0f, int ld, int tile, int ntiles, float* __restrict__ out) {
+__global__ void a0_tilemax_kernel(const float* __restrict__ A0f, int ld, int tile, int ntiles, float* __restrict__ out,
+                                  int* __restrict__ out_arg) {
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), j = blockIdx.y, lane = threadIdx.x & 31;
   if (t >= ntiles) return;
   float m = -INFINITY;
-  for (int n = t * tile + lane; n < min((t + 1) * tile, ld); n += 32) m = fmaxf(m, A0f[(size_t)j * ld + n]);
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if (lane == 0) out[(size_t)t * gridDim.y + j] = m;  // [tile][S]: a half-warp of the tile filter reads 16 neighbours
+  int a = 0x7fffffff;  // first line of the tile that attains the maximum (the tile's "champion"); -1: padding only
+  for (int n = t * tile + lane; n < min((t + 1) * tile, ld); n += 32) {
+    const float v = A0f[(size_t)j * ld + n];
+    if (v > m) { m = v; a = n; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, a, o);
+    if (om > m || (om == m && oa < a)) { m = om; a = oa; }
+  }
+  if (lane == 0) {
+    out[(size_t)t * gridDim.y + j] = m;  // [tile][S]: a half-warp of the tile filter reads 16 neighbours
+    if (out_arg != nullptr) out_arg[(size_t)t * gridDim.y + j] = a == 0x7fffffff ? -1 : a;
+  }
 }
 
-int build_a0_tilemax(const float* A0f, int ld, int S, int tile, int ntiles, float* out, cudaStream_t st) {
+int build_a0_tilemax(const float* A0f, int ld, int S, int tile, int ntiles, float* out, int* out_arg, cudaStream_t st) {
   dim3 grid(ceil_div(ntiles, 4), S);
-  a0_tilemax_kernel<<<grid, 128, 0, st>>>(A0f, ld, tile, ntiles, out);
+  a0_tilemax_kernel<<<grid, 128, 0, st>>>(A0f, ld, tile, ntiles, out, out_arg);
   DKG_LAUNCH_CHECK();
   return DKG_OK;
 }

@@ -2199,7 +2199,7 @@ int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cu
   // hull records beyond the inline capacity go through the warp-wide recorder of hull_kernel only
   // measured at c4: with ~9 survivors per set the 8-lane kernel takes the hull stage from 0.227 to 0.182 ms; with
   // ~32 per set (a third of the sets short) the extra launch costs more than it saves (0.385 -> 0.409 ms)
-  static const double short_max = getenv("DKG_HULL_SHORT_MAX") != nullptr ? atof(getenv("DKG_HULL_SHORT_MAX")) : 16.0;
+  static const double short_max = getenv("DKG_HULL_SHORT_MAX") != nullptr ? atof(getenv("DKG_HULL_SHORT_MAX")) : 32.0;
   const bool use_short = !(e != nullptr && atoi(e) == 0) && (survivors_hint < 0.0 || survivors_hint <= short_max) &&
                          (out.hull_cap >= HS_LINES || (out.hull_idx == nullptr && out.hull_x == nullptr));
   if (use_short) {

@@ -230,7 +230,7 @@ static void destroy_plan(dkg_plan* p) {
   cudaDeviceSynchronize();
   for (int m = 0; m < p->M; ++m) {
     ObjState& o = p->obj[m];
-    dev_free(o.xs); dev_free(o.alpha); dev_free(o.resid); dev_free(o.chol); dev_free(o.Kinv); dev_free(o.Kmat); dev_free(o.Kxd_dig); dev_free(o.Kxd_scale); dev_free(o.B); dev_free(o.Kxd);
+    dev_free(o.xs); dev_free(o.alpha); dev_free(o.resid); dev_free(o.chol); dev_free(o.Kinv); dev_free(o.Kmat); dev_free(o.Kxd_dig); dev_free(o.Kxd_scale); dev_free(o.Kinv_dig); dev_free(o.Kmat_dig); dev_free(o.Kinv_scale); dev_free(o.Kmat_scale); dev_free(o.B); dev_free(o.Kxd);
     dev_free(o.BT); dev_free(o.xd_s);
   }
   dev_free(p->W); dev_free(p->W2); dev_free(p->wt); dev_free(p->xd); dev_free(p->alpha_all);
@@ -251,8 +251,27 @@ static bool use_int8_cov() {
   return v != 0;
 }
 
+// digit planes of the rows of K^-1 and K (both symmetric): B operands of T0 = KX K^-1, R = KX - T0 K, T = T0 + R K^-1
+// on the int8 engine (solve_T).  Rows n .. ldk keep zero digits and a zero scale.
+static int make_solve_digits(ObjState& o, const dkg_plan* p, cudaStream_t st) {
+  if (!use_int8_cov() || o.n > OZ_MAX_K || o.Kinv == nullptr || o.Kmat == nullptr || (o.ldk % 128) != 0) return DKG_OK;
+  const int k_cap = o.cap > o.n ? (o.cap < OZ_MAX_K ? o.cap : OZ_MAX_K) : o.n;
+  const size_t bytes = ozaki_digit_bytes(o.ldk, k_cap, p->cov_digits);
+  if (o.Kinv_dig == nullptr) DKG_TRY(dev_alloc(&o.Kinv_dig, bytes));
+  if (o.Kmat_dig == nullptr) DKG_TRY(dev_alloc(&o.Kmat_dig, bytes));
+  if (o.Kinv_scale == nullptr) DKG_TRY(dev_alloc(&o.Kinv_scale, (size_t)o.ldk + 128));
+  if (o.Kmat_scale == nullptr) DKG_TRY(dev_alloc(&o.Kmat_scale, (size_t)o.ldk + 128));
+  // (the k block count follows n: planes written for a smaller n are stale, so clear before re-slicing)
+  DKG_CUDA_OK(cudaMemsetAsync(o.Kinv_dig, 0, bytes, st));
+  DKG_CUDA_OK(cudaMemsetAsync(o.Kmat_dig, 0, bytes, st));
+  DKG_TRY(ozaki_slice_rows(o.Kinv, o.ldk, o.n, o.n, 128, p->cov_digits, o.Kinv_dig, o.Kinv_scale, st));
+  DKG_TRY(ozaki_slice_rows(o.Kmat, o.ldk, o.n, o.n, 128, p->cov_digits, o.Kmat_dig, o.Kmat_scale, st));
+  return DKG_OK;
+}
+
 // digit planes of Kxd^T (one row per discretisation point) for the int8 path
 static int make_kxd_digits(ObjState& o, const dkg_plan* p, cudaStream_t st) {
+  DKG_TRY(make_solve_digits(o, p, st));
   if (!use_int8_cov() || o.n > OZ_MAX_K) return DKG_OK;
   double* KT = nullptr;
   DKG_TRY(dev_alloc(&KT, (size_t)p->N * o.n_pad, false));
@@ -547,13 +566,49 @@ static int t_solve_mode() {
   return mode;
 }
 
-static int solve_T(const ObjState& o, const double* KX, double* T, double* R, int C, int C_pad,
-                   cudaStream_t st) {
+static bool t_solve_int8() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DKG_T_GEMM");  // =dmma: the fp64 DMMA GEMMs for every batch size
+    v = (e != nullptr && strcmp(e, "dmma") == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+
+static int solve_T(const dkg_plan* p, Workspace& w, const ObjState& o, const double* KX, double* T, double* R, int C,
+                   int C_pad, cudaStream_t st) {
   const int mode = t_solve_mode();
   if (mode == 1 && o.chol != nullptr && o.n <= batched_solve_max_n())
     return launch_batched_cholesky_solve(o.chol, o.n, KX, o.ldk, C, T, o.ldk, st);
+  const bool refine = !(mode == 2 || (!o.refine && mode != 3));
+  if (t_solve_int8() && o.Kinv_dig != nullptr && w.T_dig != nullptr && o.n >= 256) {
+    // (a rule of the PLAN -- its number of training points --, never of the batch size: sub-batches and full
+    // batches must give identical bits.  At n = 100 the DMMA GEMMs take ~17 us each and win: 52 vs 83 us per solve.)
+    // The same exact int8 digit-plane products as the covariance contraction.  The fp64 DMMA
+    // GEMM needs 75 us for a [4096, 416] x [416, 416] product (one under-filled wave of 128 x 64 tiles at 72 %
+    // of the DMMA rate); here it is one wave of 128 x 128 tiles of ~25 us plus 20 us of digit slicing.
+    const int NS = p->cov_digits, NG = p->cov_diagonals;
+    for (int c0 = 0; c0 < C; c0 += w.chunk_C) {
+      const int cc = (C - c0) < w.chunk_C ? (C - c0) : w.chunk_C;
+      const int cc_pad = round_up(cc, GEMM_BM);
+      const double* kx = KX + (size_t)c0 * o.ldk;
+      double* t = T + (size_t)c0 * o.ldk;
+      double* r = R + (size_t)c0 * o.ldk;
+      DKG_TRY(ozaki_slice_rows(kx, o.ldk, cc, o.n, 128, NS, w.T_dig, w.T_scale, st));
+      DKG_TRY(ozaki_store_axpy(w.T_dig, w.T_scale, cc_pad, o.Kinv_dig, o.Kinv_scale, o.ldk, o.n, NS, NG, nullptr, 0, 1.0,
+                               t, o.ldk, cc, o.ldk, st));
+      if (!refine) continue;
+      DKG_TRY(ozaki_slice_rows(t, o.ldk, cc, o.n, 128, NS, w.T_dig, w.T_scale, st));
+      DKG_TRY(ozaki_store_axpy(w.T_dig, w.T_scale, cc_pad, o.Kmat_dig, o.Kmat_scale, o.ldk, o.n, NS, NG, kx, o.ldk, -1.0,
+                               r, o.ldk, cc, o.ldk, st));
+      DKG_TRY(ozaki_slice_rows(r, o.ldk, cc, o.n, 128, NS, w.T_dig, w.T_scale, st));
+      DKG_TRY(ozaki_store_axpy(w.T_dig, w.T_scale, cc_pad, o.Kinv_dig, o.Kinv_scale, o.ldk, o.n, NS, NG, t, o.ldk, 1.0,
+                               t, o.ldk, cc, o.ldk, st));
+    }
+    return DKG_OK;
+  }
   DKG_TRY(gemm_store(KX, o.ldk, o.Kinv, o.ldk, C_pad, o.ldk, o.n_pad, T, o.ldk, st));
-  if (mode == 2 || (!o.refine && mode != 3)) return DKG_OK;
+  if (!refine) return DKG_OK;
   DKG_TRY(gemm_axpy(T, o.ldk, o.Kmat, o.ldk, C_pad, o.ldk, o.n_pad, KX, o.ldk, -1.0, R, o.ldk, st));
   DKG_TRY(gemm_axpy(R, o.ldk, o.Kinv, o.ldk, C_pad, o.ldk, o.n_pad, T, o.ldk, 1.0, T, o.ldk, st));
   return DKG_OK;
@@ -576,7 +631,12 @@ static bool graphs_enabled() {
 
 static bool graph_eligible(const dkg_plan* p, int C) {
   // launch-bound sizes only: a few hundred microseconds of kernels at most
-  return graphs_enabled() && !g_prof_on && C <= p->ws.chunk_C && (long long)C * p->N <= (1ll << 21);
+  static long long max_cn = -1;
+  if (max_cn < 0) {
+    const char* e = getenv("DKG_GRAPH_MAX_CN");  // (measurement switch: replay larger batches from a graph too)
+    max_cn = e != nullptr ? atoll(e) : (1ll << 21);
+  }
+  return graphs_enabled() && !g_prof_on && C <= p->ws.chunk_C && (long long)C * p->N <= max_cn;
 }
 
 // Replays (capturing at first use) the launch sequence of one forward over the staging buffers
@@ -774,7 +834,7 @@ static int forward_once(dkg_plan* p, const double* X, int C, double* kg, double*
   { ProfScope ps(0, st); DKG_TRY(launch_xprep(xa, st)); }
 
   // T = KX K^-1 (backward stable), then the predictive variance
-  { ProfScope ps(1, st); DKG_TRY(solve_T(ot, w.KX, w.T, w.R, C, C_pad, st)); }
+  { ProfScope ps(1, st); DKG_TRY(solve_T(p, w, ot, w.KX, w.T, w.R, C, C_pad, st)); }
   const double ystd2 = ot.y_std * ot.y_std;
   { ProfScope ps(2, st);
     DKG_TRY(launch_var(w.KX, p->ldk, w.T, p->ldk, ot.n, C, ot.kernel, ot.outputscale, ot.noise,
@@ -906,7 +966,7 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
     }
     xa.W = p->W; xa.Xs = w.Xs; xa.KX = w.KXm[m]; xa.n_pad = o.ldk; xa.a_new = w.a_new;
     { ProfScope ps(0, st); DKG_TRY(launch_xprep(xa, st)); }  // (a_new / means are recomputed identically each time)
-    { ProfScope ps(1, st); DKG_TRY(solve_T(o, w.KXm[m], w.Tm[m], w.R, C, C_pad, st)); }
+    { ProfScope ps(1, st); DKG_TRY(solve_T(p, w, o, w.KXm[m], w.Tm[m], w.R, C, C_pad, st)); }
     // var = noisy variance (un-standardised) -> w.var reused per objective below via varlat
     DKG_TRY(launch_var(w.KXm[m], o.ldk, w.Tm[m], o.ldk, o.n, C, o.kernel, o.outputscale, o.noise,
                        o.y_std * o.y_std, w.varlat[m], w.sd, w.zown, st));

@@ -79,6 +79,9 @@ int ozaki_cov(const unsigned char* a_digits, const double* sa, int M_pad, const 
 int ozaki_store(const unsigned char* a_digits, const double* sa, int M_pad, const unsigned char* b_digits,
                 const double* sb, int N_pad, int K, int NS, int NG, bool b_nonneg, double* D, int ldd, int M,
                 int N, cudaStream_t st);
+int ozaki_store_axpy(const unsigned char* a_digits, const double* sa, int M_pad, const unsigned char* b_digits,
+                     const double* sb, int N_pad, int K, int NS, int NG, const double* Cin, int ldc, double alpha,
+                     double* D, int ldd, int M, int N, cudaStream_t st);
 // b_nonneg: every entry of the B operand is >= 0 (true for kernel values), which lets all its digit planes be
 // multiplied as UINT8 and pairs of them be merged into N = 256 instructions
 int ozaki_mma_peak(int M_pad, int N_pad, int K, int NS, int NG, int reps, int mode, double* tops_out, double* ms_out,

@@ -83,8 +83,11 @@ struct OzakiArgs {
   const double* sb;   // [cols] power-of-two row scale of B
   int cov;            // 1: covariance epilogue, 0: plain store
   CovEpilogue ep;
-  double* D;          // store mode
+  double* D;          // store mode: D = Cin + alpha * A B^T (Cin == nullptr: D = alpha * A B^T)
   int ldd;
+  const double* Cin;
+  int ldc;
+  double alpha;
   int M, N;           // valid rows / cols (store mode)
   int max_kps;        // k blocks per stage (tuning knob)
   int slot_wait;      // wait per accumulator slot (1) or for all slots before the first MMA (0)
@@ -346,8 +349,11 @@ __device__ __forceinline__ void store_tail(const double (&acc)[32], double sa_r,
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int r = 4 * it + hr;
-      if (row0 + r < args.M && col < args.N)
-        args.D[(size_t)(row0 + r) * args.ldd + col] = my_stage[r * OZ_EPI_LD + hc] * sb_c;
+      if (row0 + r < args.M && col < args.N) {
+        double v = my_stage[r * OZ_EPI_LD + hc] * sb_c;
+        if (args.Cin != nullptr) v = fma(args.alpha, v, args.Cin[(size_t)(row0 + r) * args.ldc + col]);
+        args.D[(size_t)(row0 + r) * args.ldd + col] = v;
+      }
     }
   }
   __syncwarp();
@@ -1069,6 +1075,23 @@ int ozaki_store(const unsigned char* a_digits, const double* sa, int M_pad, cons
   args.cov = 0;
   args.D = D;
   args.ldd = ldd;
+  args.M = M;
+  args.N = N;
+  return ozaki_launch(a_digits, sa, M_pad, b_digits, sb, N_pad, K, NS, NG, args, st);
+}
+
+// D[M, N] = Cin + alpha * A B^T from digit planes (the T = KX K^-1 products and their refinement step)
+int ozaki_store_axpy(const unsigned char* a_digits, const double* sa, int M_pad, const unsigned char* b_digits,
+                     const double* sb, int N_pad, int K, int NS, int NG, const double* Cin, int ldc, double alpha,
+                     double* D, int ldd, int M, int N, cudaStream_t st) {
+  OzakiArgs args{};
+  args.b_unsigned = 1;
+  args.cov = 0;
+  args.D = D;
+  args.ldd = ldd;
+  args.Cin = Cin;
+  args.ldc = ldc;
+  args.alpha = alpha;
   args.M = M;
   args.N = N;
   return ozaki_launch(a_digits, sa, M_pad, b_digits, sb, N_pad, K, NS, NG, args, st);

@@ -31,6 +31,11 @@ struct ObjState {
   double* Kxd = nullptr;     // [n_pad, N_pad]  k(X_train, X_disc) (raw cross-kernel, GEMM B operand)
   unsigned char* Kxd_dig = nullptr;  // [digits][N_pad][KP] base-256 digit planes of Kxd^T (int8 tensor-core path)
   double* Kxd_scale = nullptr;       // [N_pad] power-of-two scale of each discretisation point's column
+  // digit planes of the rows of K^-1 and K (B operands of the int8 T = KX K^-1 products and their refinement step)
+  unsigned char* Kinv_dig = nullptr;
+  unsigned char* Kmat_dig = nullptr;
+  double* Kinv_scale = nullptr;      // [ldk]
+  double* Kmat_scale = nullptr;      // [ldk]
   double* B = nullptr;       // [n_pad, N_pad]  K^-1 k(X_train, X_disc), zero padded (backward only)
   double* BT = nullptr;      // [N, ldbt]
   int ldbt = 0;              // row stride of BT (>= n_pad; the capacity, so that appends stay in place)

@@ -2217,7 +2217,10 @@ int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cu
 // ------------------------------------------------------------------------------------------
 constexpr int OVF_MAXV = 130;  // chain vertices
 constexpr int OVF_ROUNDS = 6;
-constexpr int OVF_CTAS_PER_SM = 4;
+// one set per CTA and usually only a handful of queued sets: the time of this stage is the latency of the slowest
+// set, so the CTAs are wide (the block-wide scans and marches scale with the thread count)
+constexpr int OVF_THREADS = 512;
+constexpr int OVF_CTAS_PER_SM = 2;
 
 // index k of the chain vertex with the largest v_b[k] <= b  (requires b >= v_b[0])
 __device__ __forceinline__ int chain_locate(const double* v_b, int nv, double b) {
@@ -2229,16 +2232,16 @@ __device__ __forceinline__ int chain_locate(const double* v_b, int nv, double b)
   return lo;
 }
 
-__global__ void __launch_bounds__(E_THREADS, OVF_CTAS_PER_SM)
+__global__ void __launch_bounds__(OVF_THREADS, OVF_CTAS_PER_SM)
 overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
   __shared__ double v_b[OVF_MAXV], v_a[OVF_MAXV], v_m[OVF_MAXV], v_slack[OVF_MAXV];
   __shared__ int v_idx[OVF_MAXV];
   __shared__ unsigned long long v_best[OVF_MAXV];
-  __shared__ double n_b[OVF_MAXV], n_a[OVF_MAXV];
-  __shared__ int n_i[OVF_MAXV];
+  __shared__ double n_b[OVF_MAXV], n_a[OVF_MAXV], g_b[OVF_MAXV], g_a[OVF_MAXV];
+  __shared__ int n_i[OVF_MAXV], g_i[OVF_MAXV];
   __shared__ int s_nv, s_grew, s_list;
-  __shared__ double r_a[E_THREADS / 32], r_b[E_THREADS / 32], r_x[E_THREADS / 32];
-  __shared__ int r_idx[E_THREADS / 32], r_ref[E_THREADS / 32];
+  __shared__ double r_a[OVF_THREADS / 32], r_b[OVF_THREADS / 32], r_x[OVF_THREADS / 32];
+  __shared__ int r_idx[OVF_THREADS / 32], r_ref[OVF_THREADS / 32];
   __shared__ double c_a, c_b;
   __shared__ int c_idx, c_ref;
 
@@ -2345,19 +2348,24 @@ overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
       __syncthreads();
       if (s_list <= SURV_CAP) { small_enough = true; break; }
       if (round == OVF_ROUNDS) break;
-      // insert the farthest line of every chord (thread 0; chains are tiny)
+      // insert the farthest line of every chord: the candidates are gathered in parallel (two dependent global
+      // loads each -- one thread doing that for up to 64 chords was most of a late round), thread 0 merges
+      for (int k = tid; k + 1 < nv; k += blockDim.x) {
+        g_i[k] = -1;
+        if (v_best[k] != 0ull) {
+          const Line L = gather_line(lb, c, j, w, (int)(v_best[k] & 0xffffffffull));
+          if (L.b > v_b[k] && L.b < v_b[k + 1]) { g_b[k] = L.b; g_a[k] = L.a; g_i[k] = L.idx; }
+        }
+      }
+      __syncthreads();
       if (tid == 0) {
         int m = 0;
         bool grew = false;
         for (int k = 0; k < nv; ++k) {
           n_b[m] = v_b[k]; n_a[m] = v_a[k]; n_i[m] = v_idx[k]; ++m;
-          if (k + 1 < nv && v_best[k] != 0ull && m + (nv - k) < OVF_MAXV) {
-            const int n = (int)(v_best[k] & 0xffffffffull);
-            const Line L = gather_line(lb, c, j, w, n);
-            if (L.b > v_b[k] && L.b < v_b[k + 1]) {
-              n_b[m] = L.b; n_a[m] = L.a; n_i[m] = L.idx; ++m;
-              grew = true;
-            }
+          if (k + 1 < nv && g_i[k] >= 0 && m + (nv - k) < OVF_MAXV) {
+            n_b[m] = g_b[k]; n_a[m] = g_a[k]; n_i[m] = g_i[k]; ++m;
+            grew = true;
           }
         }
         for (int k = 0; k < m; ++k) { v_b[k] = n_b[k]; v_a[k] = n_a[k]; v_idx[k] = n_i[k]; }
@@ -2368,37 +2376,12 @@ overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
       if (!s_grew) break;  // no chord has anything above it, yet too many lines: all near-hull
     }
 
-    if (small_enough) {
-      // ---- the list is complete: warp 0 marches over it plus the chain vertices ----
-      const int nv = s_nv;
-      __syncthreads();
-      if (warp == 0) {
-        const int cnt = min(s_list, SURV_CAP);
-        const int total = cnt + nv;
-        auto fetch = [&](int k) -> Line {
-          if (k < cnt) {
-            const SurvEntry e = list[k];
-            return make_line(lb, w, e.a, e.z, e.idx);
-          }
-          Line L;
-          L.a = v_a[k - cnt]; L.b = v_b[k - cnt]; L.idx = v_idx[k - cnt];
-          L.ref = ref_index(lb, L.idx);
-          return L;
-        };
-        const HullResult r = warp_march(total, fetch, rec);
-        if (lane == 0) {
-          finish_set(lb, out, set, s, r.E, r.h);
-          if (sc.stats) {
-            atomicAdd((unsigned long long*)&sc.stats[2], 1ull);
-            atomicAdd((unsigned long long*)&sc.stats[3], (unsigned long long)r.h);
-          }
-        }
-      }
-    } else {
-      // ---- exact block-wide march over ALL lines (e.g. every line is a hull vertex) ----
+    // ---- exact block-wide march over `total` lines exposed by fetch(k): every thread scans its share for the next
+    // vertex, warps and then the CTA reduce (earliest intersection, ties by the reference's sorted order) ----
+    auto block_march = [&](int total, auto fetch, bool all_lines) {
       Line cur = empty_line();
-      for (int n = tid; n < lb.NL; n += blockDim.x) {
-        const Line L = gather_line(lb, c, j, w, n);
+      for (int k = tid; k < total; k += blockDim.x) {
+        const Line L = fetch(k);
         if (cur.idx < 0 || sorted_before(L, cur)) cur = L;
       }
       for (int o = 16; o > 0; o >>= 1) {
@@ -2409,7 +2392,7 @@ overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
       __syncthreads();
       if (tid == 0) {
         Line best = empty_line();
-        for (int k = 0; k < E_THREADS / 32; ++k) {
+        for (int k = 0; k < OVF_THREADS / 32; ++k) {
           Line L;
           L.a = r_a[k]; L.b = r_b[k]; L.idx = r_idx[k]; L.ref = r_ref[k];
           if (L.idx >= 0 && (best.idx < 0 || sorted_before(L, best))) best = L;
@@ -2424,7 +2407,7 @@ overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
         Next best;
         best.L = empty_line();
         best.x = INFINITY;
-        for (int n = tid; n < lb.NL; n += blockDim.x) consider_next(best, cur, gather_line(lb, c, j, w, n));
+        for (int k = tid; k < total; k += blockDim.x) consider_next(best, cur, fetch(k));
         for (int o = 16; o > 0; o >>= 1) {
           Next oth;
           oth.L = shfl_line(best.L, o);
@@ -2439,7 +2422,7 @@ overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
         Next nx;
         nx.L = empty_line();
         nx.x = INFINITY;
-        for (int k = 0; k < E_THREADS / 32; ++k) {
+        for (int k = 0; k < OVF_THREADS / 32; ++k) {
           Next o;
           o.L.a = r_a[k]; o.L.b = r_b[k]; o.L.idx = r_idx[k]; o.L.ref = r_ref[k]; o.x = r_x[k];
           merge_next(nx, o);
@@ -2464,10 +2447,30 @@ overflow_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
         finish_set(lb, out, set, s, E, h);
         if (sc.stats) {
           atomicAdd((unsigned long long*)&sc.stats[2], 1ull);
-          atomicAdd((unsigned long long*)&sc.stats[5], 1ull);
+          if (all_lines) atomicAdd((unsigned long long*)&sc.stats[5], 1ull);
           atomicAdd((unsigned long long*)&sc.stats[3], (unsigned long long)h);
         }
       }
+    };
+    if (small_enough) {
+      // ---- the list is complete: march over it plus the chain vertices.  (A single warp marching over a list of
+      // up to SURV_CAP lines in global memory took ~100 us per set: 60 dependent trips per vertex.) ----
+      const int nv = s_nv;
+      __syncthreads();
+      const int cnt = min(s_list, SURV_CAP);
+      block_march(cnt + nv, [&](int k) -> Line {
+        if (k < cnt) {
+          const SurvEntry e = list[k];
+          return make_line(lb, w, e.a, e.z, e.idx);
+        }
+        Line L;
+        L.a = v_a[k - cnt]; L.b = v_b[k - cnt]; L.idx = v_idx[k - cnt];
+        L.ref = ref_index(lb, L.idx);
+        return L;
+      }, false);
+    } else {
+      // ---- every line (e.g. all of them are hull vertices) ----
+      block_march(lb.NL, [&](int n) -> Line { return gather_line(lb, c, j, w, n); }, true);
     }
   }
 }
@@ -2476,7 +2479,7 @@ int emax_overflow(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out
   if (lb.C == 0) return DKG_OK;
   long long sets = (long long)lb.C * lb.S;
   int grid = (int)(sets < OVF_CTAS_PER_SM * 148 ? sets : OVF_CTAS_PER_SM * 148);
-  overflow_kernel<<<grid, E_THREADS, 0, st>>>(lb, sc, out);
+  overflow_kernel<<<grid, OVF_THREADS, 0, st>>>(lb, sc, out);
   DKG_LAUNCH_CHECK();
   return DKG_OK;
 }

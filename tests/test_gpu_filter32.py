@@ -152,3 +152,27 @@ def test_tiled_statistics_pass_matches_row_pass_on_ragged_sizes(d):
     for (kg_t, g_t), (kg_r, g_r) in zip(out["tiled"], out["rows"]):
         assert torch.equal(kg_t, kg_r)
         assert torch.equal(g_t, g_r)
+
+
+def test_champion_probe_and_sample_probe_give_identical_bits_at_c4():
+    """The second-level chain only decides how MANY lines survive, never which hull comes out: the champion probe
+    (tile maxima of the intercept table, default) and the 1/16 line sample (DKG_PROBE_SAMPLE=1) must give the same
+    bits.  At the full c4 batch the champion chain leaves a few sets with truncated survivor lists, which the
+    overflow kernel redoes from all lines (block-wide march): those sets are covered here too."""
+    from decoupledbo_b200 import synthetic
+
+    P = synthetic.problem_c4(n_cand=4096)
+    dev = torch.device("cuda")
+    X = P.candidates.to(dev)
+    xd = P.x_disc.to(dev)
+    for target in (0, 1):
+        kgc, gc, stc = _eval(P, target, X, "tile", xd)
+        os.environ["DKG_PROBE_SAMPLE"] = "1"
+        try:
+            kgs, gs, sts = _eval(P, target, X, "tile", xd)
+        finally:
+            os.environ.pop("DKG_PROBE_SAMPLE", None)
+        assert torch.equal(kgc, kgs)
+        assert torch.equal(gc, gs)
+        assert stc[3] == sts[3]  # identical hulls
+        assert stc[1] < sts[1]  # the champions make the tighter chain

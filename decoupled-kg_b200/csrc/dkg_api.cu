@@ -79,7 +79,7 @@ static void free_workspace(Workspace& w) {
   if (w.cap_stream) { cudaStreamDestroy(w.cap_stream); w.cap_stream = nullptr; }
   dev_free(w.X); dev_free(w.kg); dev_free(w.dX); dev_free(w.KX); dev_free(w.T); dev_free(w.R); dev_free(w.T_dig); dev_free(w.T_scale); dev_free(w.var);
   dev_free(w.sd); dev_free(w.zown); dev_free(w.Xs); dev_free(w.a_new); dev_free(w.kg_terms);
-  dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.zpv); dev_free(w.zpi); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } { double4* t = (double4*)w.chain; dev_free(t); w.chain = nullptr; } { float4* t = (float4*)w.chain32; dev_free(t); w.chain32 = nullptr; } { double4* t = (double4*)w.chainv; dev_free(t); w.chainv = nullptr; } { double4* t = (double4*)w.chain5; dev_free(t); w.chain5 = nullptr; } { float4* t = (float4*)w.chain5f; dev_free(t); w.chain5f = nullptr; } { float2* t = (float2*)w.ztile; dev_free(t); w.ztile = nullptr; } dev_free(w.far); dev_free(w.ovf_sets); dev_free(w.ovf_count);
+  dev_free(w.Z); dev_free(w.zst); dev_free(w.zarg); dev_free(w.zpv); dev_free(w.zpi); dev_free(w.surv_cnt); { SurvEntry* t = (SurvEntry*)w.surv; dev_free(t); w.surv = nullptr; } { double4* t = (double4*)w.chain; dev_free(t); w.chain = nullptr; } { float4* t = (float4*)w.chain32; dev_free(t); w.chain32 = nullptr; } { double4* t = (double4*)w.chainv; dev_free(t); w.chainv = nullptr; } { double4* t = (double4*)w.chain5; dev_free(t); w.chain5 = nullptr; } { float4* t = (float4*)w.chain5f; dev_free(t); w.chain5f = nullptr; } { float2* t = (float2*)w.ztile; dev_free(t); w.ztile = nullptr; } dev_free(w.far); dev_free(w.ovf_sets); dev_free(w.long_sets); dev_free(w.ovf_count);
   dev_free(w.hull_cnt); dev_free(w.hull_idx); dev_free(w.hull_p); dev_free(w.hull_q);
   dev_free(w.spill_head); dev_free(w.spill_next); dev_free(w.spill_idx); dev_free(w.spill_p); dev_free(w.spill_q);
   w.spill_used = nullptr;  // (part of the stats allocation)
@@ -199,6 +199,7 @@ static int ensure_workspace(dkg_plan* p, int C) {
     { float2* t = nullptr; DKG_TRY(dev_alloc(&t, (size_t)chunk * w.ztiles, false)); w.ztile = t; }
   }
   DKG_TRY(dev_alloc(&w.ovf_sets, (size_t)chunk * S, false));
+  DKG_TRY(dev_alloc(&w.long_sets, (size_t)chunk * S + 1));
   DKG_TRY(dev_alloc(&w.ovf_count, (size_t)1));
   DKG_TRY(dev_alloc(&w.hull_cnt, (size_t)chunk * S));
   DKG_TRY(dev_alloc(&w.hull_idx, (size_t)chunk * S * HULL_CAP, false));
@@ -879,6 +880,7 @@ static int forward_once(dkg_plan* p, const double* X, int C, double* kg, double*
     EmaxScratch sc;
     sc.zst = w.zst; sc.zarg = w.zarg; sc.surv_cnt = w.surv_cnt; sc.surv = (SurvEntry*)w.surv;
     sc.ovf_sets = w.ovf_sets; sc.ovf_count = w.ovf_count; sc.far = w.far; sc.chain = (double4*)w.chain;
+    sc.long_sets = w.long_sets; sc.long_count = w.long_sets + (size_t)w.chunk_C * S;
     sc.chain32 = (float4*)w.chain32;
     sc.chainv = (double4*)w.chainv;
     sc.zpv = w.zpv; sc.zpi = w.zpi;
@@ -1015,6 +1017,7 @@ static int forward_coupled(dkg_plan* p, const double* X, int C, double* kg, doub
     EmaxScratch sc;
     sc.zst = w.zst; sc.zarg = w.zarg; sc.surv_cnt = w.surv_cnt; sc.surv = (SurvEntry*)w.surv;
     sc.ovf_sets = w.ovf_sets; sc.ovf_count = w.ovf_count; sc.far = w.far; sc.chain = (double4*)w.chain;
+    sc.long_sets = w.long_sets; sc.long_count = w.long_sets + (size_t)w.chunk_C * S;
     sc.chain32 = (float4*)w.chain32; sc.chainv = (double4*)w.chainv; sc.chain5 = (double4*)w.chain5;
     sc.stats = w.stats;
     sc.spill_used = w.spill_used;

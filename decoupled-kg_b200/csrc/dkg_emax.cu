@@ -176,6 +176,7 @@ chain_kernel(LineBatch lb, EmaxScratch sc) {
   if (sc.far != nullptr) { sc.far[set * 2] = 0ull; sc.far[set * 2 + 1] = 0ull; }
   if (set == 0) {
     *sc.ovf_count = 0;
+    if (sc.long_count != nullptr) *sc.long_count = 0;
     if (sc.spill_used != nullptr) *sc.spill_used = 0;
   }
   ChainMag mag;
@@ -1895,19 +1896,11 @@ __device__ __forceinline__ bool higher_intercept(const Line& p, const Line& q) {
 constexpr int HS_G = 8;       // lanes per set in hull_short_kernel
 constexpr int HS_LINES = 32;  // lines such a group holds in registers (4 per lane)
 
-__global__ void __launch_bounds__(E_THREADS, HULL_CTAS)
-hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out, int skip_short) {
-  __shared__ double s_a[E_THREADS / 32][STAGE_CAP];
-  __shared__ double s_b[E_THREADS / 32][STAGE_CAP];
-  __shared__ int s_i[E_THREADS / 32][STAGE_CAP];
-  __shared__ double s_cm[E_THREADS / 32][CHAIN_MAXV];  // chord slopes / slacks of the refinement chain
-  __shared__ double s_cs[E_THREADS / 32][CHAIN_MAXV];
-  __shared__ unsigned long long s_fk[E_THREADS / 32][CHAIN_MAXV];  // farthest line above every chord
+// one warp, one set (the warp's slices of the staging arrays are passed in)
+__device__ __forceinline__ void hull_one_set(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, size_t set, int skip_short,
+                                             double* sa_w, double* sb_w, int* si_w, double* scm_w, double* scs_w,
+                                             unsigned long long* sfk_w) {
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const long long set_ll = (long long)blockIdx.x * (E_THREADS / 32) + warp;
-  if (set_ll >= (long long)lb.C * lb.S) return;
-  const size_t set = (size_t)set_ll;
   const int c = (int)(set / lb.S);
   const int j = (int)(set - (size_t)c * lb.S);
   const SetInfo s = set_info(lb, sc, c, j);
@@ -1958,7 +1951,7 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out, int skip_short) {
     // code, and its instruction-cache footprint, a third smaller)
     for (int k = lane; k < total; k += 32) {
       const Line L = fetch_global(k);
-      s_a[warp][k] = L.a; s_b[warp][k] = L.b; s_i[warp][k] = L.idx;
+      sa_w[k] = L.a; sb_w[k] = L.b; si_w[k] = L.idx;
     }
     staged = total;
   } else {
@@ -1981,9 +1974,9 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out, int skip_short) {
     if (!(hasR && F2.idx >= 0 && F2.b > T.b && F2.b < Q.b)) F2 = empty_line();
     if (F1.idx >= 0) { Chord ch; ch.set(P, T); if (!(ch.excess(F1) > 0.0)) F1 = empty_line(); }  // concave
     if (F2.idx >= 0) { Chord ch; ch.set(T, Q); if (!(ch.excess(F2) > 0.0)) F2 = empty_line(); }
-    double* vb = s_b[warp];
-    double* va = s_a[warp];
-    int* vi = s_i[warp];
+    double* vb = sb_w;
+    double* va = sa_w;
+    int* vi = si_w;
     int nv = 0;
     if (lane == 0) {
       const Line vs[5] = {hasL ? P : empty_line(), F1, T, F2, hasR ? Q : empty_line()};
@@ -1996,10 +1989,10 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out, int skip_short) {
       __syncwarp();
       if (lane < nv - 1) {  // chord lane: vertex lane -> vertex lane + 1
         const double m = (va[lane + 1] - va[lane]) / (vb[lane + 1] - vb[lane]);
-        s_cm[warp][lane] = m;
-        s_cs[warp][lane] = EPS128 * (fabs(va[lane]) + fabs(va[lane + 1]) + fabs(m) * fmax(fabs(vb[lane]), fabs(vb[lane + 1])));
+        scm_w[lane] = m;
+        scs_w[lane] = EPS128 * (fabs(va[lane]) + fabs(va[lane + 1]) + fabs(m) * fmax(fabs(vb[lane]), fabs(vb[lane + 1])));
       }
-      if (lane < CHAIN_MAXV) s_fk[warp][lane] = 0ull;
+      if (lane < CHAIN_MAXV) sfk_w[lane] = 0ull;
       __syncwarp();
       staged = nv;
       for (int k0 = 0; k0 < total; k0 += 32) {
@@ -2015,20 +2008,20 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out, int skip_short) {
           for (int step = CHAIN_MAXV / 2; step > 0; step >>= 1)
             if (q + step < nv && vb[q + step] <= L.b) q += step;
           if (q < nv - 1 && L.b > vb[q]) {
-            const double ex = L.a - fma(s_cm[warp][q], L.b - vb[q], va[q]);
-            keep = ex > -s_cs[warp][q];
-            if (ex > 0.0) atomicMax(&s_fk[warp][q], pack_excess(ex, k));
+            const double ex = L.a - fma(scm_w[q], L.b - vb[q], va[q]);
+            keep = ex > -scs_w[q];
+            if (ex > 0.0) atomicMax(&sfk_w[q], pack_excess(ex, k));
           }
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         const int pos = staged + __popc(m & ((1u << lane) - 1u));
-        if (keep && pos < STAGE_CAP) { s_a[warp][pos] = L.a; s_b[warp][pos] = L.b; s_i[warp][pos] = L.idx; }
+        if (keep && pos < STAGE_CAP) { sa_w[pos] = L.a; sb_w[pos] = L.b; si_w[pos] = L.idx; }
         staged += __popc(m);
       }
       if (staged <= STAGE_CAP) { fits = true; break; }
       // the farthest line above every chord becomes a vertex
       __syncwarp();
-      const unsigned long long key = lane < nv - 1 ? s_fk[warp][lane] : 0ull;
+      const unsigned long long key = lane < nv - 1 ? sfk_w[lane] : 0ull;
       const unsigned ins = __ballot_sync(0xffffffffu, key != 0ull);
       if (ins == 0u || nv + __popc(ins) > CHAIN_MAXV || level + 1 == HULL_LEVELS) break;
       const Line F = key ? fetch_global((int)(key & 0xffffffffull)) : empty_line();
@@ -2048,7 +2041,7 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out, int skip_short) {
   __syncwarp();
   auto fetch_smem = [&](int k) -> Line {
     Line L;
-    L.a = s_a[warp][k]; L.b = s_b[warp][k]; L.idx = s_i[warp][k];
+    L.a = sa_w[k]; L.b = sb_w[k]; L.idx = si_w[k];
     L.ref = ref_index(lb, L.idx);
     return L;
   };
@@ -2060,6 +2053,30 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out, int skip_short) {
       atomicAdd((unsigned long long*)&sc.stats[3], (unsigned long long)r.h);
     }
   }
+}
+
+// One warp per set, or -- when hull_short_kernel ran first and queued the sets it left (sc.long_sets) -- a fixed
+// grid of warps walking that queue: a warp per set just to find out that the set was short cost 60 us per launch.
+__global__ void __launch_bounds__(E_THREADS, HULL_CTAS)
+hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out, int skip_short, int from_queue) {
+  __shared__ double s_a[E_THREADS / 32][STAGE_CAP];
+  __shared__ double s_b[E_THREADS / 32][STAGE_CAP];
+  __shared__ int s_i[E_THREADS / 32][STAGE_CAP];
+  __shared__ double s_cm[E_THREADS / 32][CHAIN_MAXV];  // chord slopes / slacks of the refinement chain
+  __shared__ double s_cs[E_THREADS / 32][CHAIN_MAXV];
+  __shared__ unsigned long long s_fk[E_THREADS / 32][CHAIN_MAXV];  // farthest line above every chord
+  const int warp = threadIdx.x >> 5;
+  if (from_queue) {
+    const int n = *sc.long_count;
+    for (int qi = blockIdx.x * (E_THREADS / 32) + warp; qi < n; qi += gridDim.x * (E_THREADS / 32)) {
+      hull_one_set(lb, sc, out, (size_t)sc.long_sets[qi], 0, s_a[warp], s_b[warp], s_i[warp], s_cm[warp], s_cs[warp], s_fk[warp]);
+      __syncwarp();
+    }
+    return;
+  }
+  const long long set_ll = (long long)blockIdx.x * (E_THREADS / 32) + warp;
+  if (set_ll >= (long long)lb.C * lb.S) return;
+  hull_one_set(lb, sc, out, (size_t)set_ll, skip_short, s_a[warp], s_b[warp], s_i[warp], s_cm[warp], s_cs[warp], s_fk[warp]);
 }
 
 // Short sets (survivors + seeds <= 32 lines: most sets of a well-filtered batch): a warp per set leaves
@@ -2086,6 +2103,13 @@ hull_short_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
   if (lb.a_own != nullptr) seeds[nseed++] = lb.NA;
   const int total = cnt + nseed;
   bool active = in_range && !s.shortcut && cnt <= SURV_CAP && total <= HS_LINES;  // (group-uniform)
+  if (in_range && gl == 0) {
+    if (active) {
+      if (out.amax_is_own != nullptr) out.amax_is_own[set] = s.own_is_max;
+    } else if (sc.long_sets != nullptr) {
+      sc.long_sets[atomicAdd(sc.long_count, 1)] = (int)set;  // left to hull_kernel (long list, shortcut set, truncated list)
+    }
+  }
   const double w = s.w;
   const SurvEntry* list = sc.surv + set * SURV_CAP;
   Line cache[HS_LINES / HS_G];
@@ -2207,7 +2231,13 @@ int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cu
     hull_short_kernel<<<(unsigned)((sets + per_cta - 1) / per_cta), E_THREADS, 0, st>>>(lb, sc, out);
     DKG_LAUNCH_CHECK();
   }
-  hull_kernel<<<(unsigned)((sets + wpb - 1) / wpb), E_THREADS, 0, st>>>(lb, sc, out, use_short ? 1 : 0);
+  if (use_short && sc.long_sets != nullptr && sc.long_count != nullptr) {
+    long long ctas = (sets + wpb - 1) / wpb;
+    if (ctas > 148 * HULL_CTAS * 4) ctas = 148 * HULL_CTAS * 4;
+    hull_kernel<<<(unsigned)ctas, E_THREADS, 0, st>>>(lb, sc, out, 0, 1);
+  } else {
+    hull_kernel<<<(unsigned)((sets + wpb - 1) / wpb), E_THREADS, 0, st>>>(lb, sc, out, use_short ? 1 : 0, 0);
+  }
   DKG_LAUNCH_CHECK();
   return DKG_OK;
 }

@@ -95,6 +95,8 @@ struct EmaxScratch {
   unsigned long long* far = nullptr;  // [C, S, 2] farthest late survivor above the left / right
                                       // chord, packed (float excess << 32 | line); 0 = none
   int* ovf_sets = nullptr;      // [C * S] queue of sets for the cooperative kernel
+  int* long_sets = nullptr;     // optional [C * S] queue of the sets hull_short_kernel leaves to hull_kernel ...
+  int* long_count = nullptr;    // ... and its length (reset by chain_kernel)
   int* ovf_count = nullptr;     // [1]
   int* spill_used = nullptr;    // [1] blocks claimed from the hull-record spill pool (optional)
   long long* stats = nullptr;   // [8] (optional)

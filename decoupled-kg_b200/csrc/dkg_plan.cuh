@@ -82,6 +82,7 @@ struct Workspace {
   void* surv = nullptr;     // [chunk_C, S, SURV_CAP] SurvEntry (intercept, slope, index)
   unsigned long long* far = nullptr;  // [chunk_C, S, 2] farthest late survivors (chain seeds)
   int* ovf_sets = nullptr;  // [chunk_C * S] queue of sets for the cooperative kernel
+  int* long_sets = nullptr; // [chunk_C * S + 1] queue of the sets hull_short_kernel left to hull_kernel; last entry = count
   int* ovf_count = nullptr; // [1]
   int* hull_cnt = nullptr;  // [chunk_C, S]
   int* hull_idx = nullptr;  // [chunk_C, S, HULL_CAP]

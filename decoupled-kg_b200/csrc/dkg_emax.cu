@@ -1893,8 +1893,7 @@ __device__ __forceinline__ bool higher_intercept(const Line& p, const Line& q) {
 // ------------------------------------------------------------------------------------------
 // hull kernel: one warp per set
 // ------------------------------------------------------------------------------------------
-constexpr int HS_G = 8;       // lanes per set in hull_short_kernel
-constexpr int HS_LINES = 32;  // lines such a group holds in registers (4 per lane)
+// hull_short_kernel<G>: G lanes per set (8 or 16), 4 lines per lane in registers -> sets of up to 32 / 64 lines
 
 // one warp, one set (the warp's slices of the staging arrays are passed in)
 __device__ __forceinline__ void hull_one_set(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, size_t set, int skip_short,
@@ -1934,7 +1933,7 @@ __device__ __forceinline__ void hull_one_set(const LineBatch& lb, const EmaxScra
   seeds[nseed++] = lb.Aarg[am_index(lb, c, j)];
   if (lb.a_own != nullptr) seeds[nseed++] = lb.NA;
   const int total = cnt + nseed;
-  if (skip_short && total <= HS_LINES) return;  // hull_short_kernel finishes these, four to a warp
+  if (skip_short && total <= skip_short) return;  // hull_short_kernel finishes these, several to a warp
   const double w = s.w;
   auto fetch_global = [&](int k) -> Line {
     if (k < cnt) {
@@ -2083,8 +2082,10 @@ hull_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out, int skip_short, int from_
 // three quarters of the lanes without a line.  Here 8 lanes share a set (4 lines per lane in registers),
 // four sets per warp advance in lock-step through the same exact march; the Phi / phi evaluations of a
 // set's vertices are batched (8 per group) and deferred to one flush at the end wherever possible.
+template <int HS_G>
 __global__ void __launch_bounds__(E_THREADS, 3)
 hull_short_kernel(LineBatch lb, EmaxScratch sc, EmaxOut out) {
+  constexpr int HS_LINES = 4 * HS_G;  // lines a group holds in registers (4 per lane)
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, gl = lane & (HS_G - 1);
   const long long nsets = (long long)lb.C * lb.S;
@@ -2220,15 +2221,18 @@ int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cu
   if (sets == 0) return DKG_OK;
   const int wpb = E_THREADS / 32;
   const char* e = getenv("DKG_HULL_SHORT");
-  // hull records beyond the inline capacity go through the warp-wide recorder of hull_kernel only
-  // measured at c4: with ~9 survivors per set the 8-lane kernel takes the hull stage from 0.227 to 0.182 ms; with
-  // ~32 per set (a third of the sets short) the extra launch costs more than it saves (0.385 -> 0.409 ms)
-  static const double short_max = getenv("DKG_HULL_SHORT_MAX") != nullptr ? atof(getenv("DKG_HULL_SHORT_MAX")) : 32.0;
+  // hull records beyond the inline capacity go through the warp-wide recorder of hull_kernel only.
+  // Measured at c4: ~9 survivors per set: 8 lanes per set take the hull stage from 0.227 to 0.13 ms; ~29 per set (most
+  // sets hold 33 .. 64 lines with their seeds): 16 lanes per set.  The sets a short kernel leaves are queued for hull_kernel.
+  static const double short_max = getenv("DKG_HULL_SHORT_MAX") != nullptr ? atof(getenv("DKG_HULL_SHORT_MAX")) : 48.0;
+  static const double short8_max = getenv("DKG_HULL_SHORT8_MAX") != nullptr ? atof(getenv("DKG_HULL_SHORT8_MAX")) : 16.0;
+  const int G = (survivors_hint < 0.0 || survivors_hint <= short8_max) ? 8 : 16;
   const bool use_short = !(e != nullptr && atoi(e) == 0) && (survivors_hint < 0.0 || survivors_hint <= short_max) &&
-                         (out.hull_cap >= HS_LINES || (out.hull_idx == nullptr && out.hull_x == nullptr));
+                         (out.hull_cap >= 4 * G || (out.hull_idx == nullptr && out.hull_x == nullptr));
   if (use_short) {
-    const long long per_cta = (long long)wpb * (32 / HS_G);
-    hull_short_kernel<<<(unsigned)((sets + per_cta - 1) / per_cta), E_THREADS, 0, st>>>(lb, sc, out);
+    const long long per_cta = (long long)wpb * (32 / G);
+    if (G == 8) hull_short_kernel<8><<<(unsigned)((sets + per_cta - 1) / per_cta), E_THREADS, 0, st>>>(lb, sc, out);
+    else hull_short_kernel<16><<<(unsigned)((sets + per_cta - 1) / per_cta), E_THREADS, 0, st>>>(lb, sc, out);
     DKG_LAUNCH_CHECK();
   }
   if (use_short && sc.long_sets != nullptr && sc.long_count != nullptr) {
@@ -2236,7 +2240,7 @@ int emax_hull(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out, cu
     if (ctas > 148 * HULL_CTAS * 4) ctas = 148 * HULL_CTAS * 4;
     hull_kernel<<<(unsigned)ctas, E_THREADS, 0, st>>>(lb, sc, out, 0, 1);
   } else {
-    hull_kernel<<<(unsigned)((sets + wpb - 1) / wpb), E_THREADS, 0, st>>>(lb, sc, out, use_short ? 1 : 0, 0);
+    hull_kernel<<<(unsigned)((sets + wpb - 1) / wpb), E_THREADS, 0, st>>>(lb, sc, out, use_short ? 4 * G : 0, 0);
   }
   DKG_LAUNCH_CHECK();
   return DKG_OK;

@@ -156,8 +156,10 @@ static int ensure_workspace(dkg_plan* p, int C) {
         const int nc = p->obj[m].cap > p->obj[m].n ? p->obj[m].cap : p->obj[m].n;  // (room for appended points)
         n_max = n_max > nc ? n_max : nc;
       }
-    DKG_TRY(dev_alloc(&w.T_dig, ozaki_digit_bytes(chunk, n_max, p->cov_digits)));
-    DKG_TRY(dev_alloc(&w.T_scale, (size_t)chunk + 128));  // + one row block: the CTA-pair kernel reads 256-row pairs
+    // (sized for the whole batch, not for a chunk: the T solve slices all rows at once -- with many scalarisations
+    // a chunk is a few hundred candidates and chunk-sized products were launches of a dozen tiles each)
+    DKG_TRY(dev_alloc(&w.T_dig, ozaki_digit_bytes(cap, n_max, p->cov_digits)));
+    DKG_TRY(dev_alloc(&w.T_scale, (size_t)cap + 128));  // + one row block: the CTA-pair kernel reads 256-row pairs
   }
   DKG_TRY(dev_alloc(&w.var, (size_t)cap));
   DKG_TRY(dev_alloc(&w.sd, (size_t)cap));
@@ -589,8 +591,8 @@ static int solve_T(const dkg_plan* p, Workspace& w, const ObjState& o, const dou
     // GEMM needs 75 us for a [4096, 416] x [416, 416] product (one under-filled wave of 128 x 64 tiles at 72 %
     // of the DMMA rate); here it is one wave of 128 x 128 tiles of ~25 us plus 20 us of digit slicing.
     const int NS = p->cov_digits, NG = p->cov_diagonals;
-    for (int c0 = 0; c0 < C; c0 += w.chunk_C) {
-      const int cc = (C - c0) < w.chunk_C ? (C - c0) : w.chunk_C;
+    for (int c0 = 0; c0 < C; c0 += w.cap_C) {  // (one pass: the digit buffer holds cap_C >= C rows)
+      const int cc = (C - c0) < w.cap_C ? (C - c0) : w.cap_C;
       const int cc_pad = round_up(cc, GEMM_BM);
       const double* kx = KX + (size_t)c0 * o.ldk;
       double* t = T + (size_t)c0 * o.ldk;

@@ -2589,24 +2589,68 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
   for (int h = threadIdx.x; h < HN; h += blockDim.x) { s_hkey[h] = -1; s_hfirst[h] = 0x7fffffff; }
   __syncthreads();
   const int nrec = s_nrec;
-  bool merged = nrec <= RM;
-  if (merged) {
+  // The records are merged in BATCHES of up to RM (what the shared-memory tables hold): a candidate with more
+  // records than that (S = 256 on a noisy objective: thousands) used to fall back to loops in which every thread
+  // walked every record of every scalarisation through the spill-chain reader for every training point -- ~3 ms
+  // per candidate, 13 of the 21 ms of a c5 S = 256 launch.  r_t and the scalar terms simply accumulate over the
+  // batches (one batch -- every S <= 64 case -- adds to zero: the same bits as before).
+  bool merged = true;
+  for (int t = threadIdx.x; t < bw.n_pad; t += blockDim.x) s_r[t] = 0.0;
+  double gsum = 0.0, gzown = 0.0, gkd[MAX_D], gm[MAX_M];  // (warp 0)
+#pragma unroll
+  for (int k = 0; k < MAX_D; ++k) gkd[k] = 0.0;
+#pragma unroll
+  for (int m = 0; m < MAX_M; ++m) gm[m] = 0.0;
+  double xs_t[MAX_D];
+#pragma unroll
+  for (int k = 0; k < MAX_D; ++k)
+    xs_t[k] = k < d ? bw.X[(size_t)c * d + k] / bw.ls[tgt][k] : 0.0;
+  auto slope_terms = [&](int idx, double cz) {
+    gsum += cz * zrow[idx];
+    if (idx == lb.NA) {
+      gzown += cz;
+    } else {
+      double sq = 0.0;
+#pragma unroll
+      for (int q = 0; q < MAX_D; ++q)
+        if (q < d) {
+          double df = xs_t[q] - bw.xd_s[(size_t)idx * d + q];
+          sq += df * df;
+        }
+      const double gc = stationary_grad_coeff(bw.kind[tgt], bw.outputscale[tgt], sq);
+#pragma unroll
+      for (int q = 0; q < MAX_D; ++q)
+        if (q < d)
+          gkd[q] += cz * gc * (xs_t[q] - bw.xd_s[(size_t)idx * d + q]) / bw.ls[tgt][q];
+    }
+  };
+  for (int b0 = 0; b0 < nrec && merged; b0 += RM) {
+    const int nb = min(RM, nrec - b0);  // records b0 .. b0 + nb of the candidate (set-major order)
+    if (b0 > 0) {
+      __syncthreads();  // the previous batch's tables are done with
+      for (int h = threadIdx.x; h < HN; h += blockDim.x) { s_hkey[h] = -1; s_hfirst[h] = 0x7fffffff; }
+      if (threadIdx.x == 0) s_nuniq = 0;
+      __syncthreads();
+    }
     for (int j = warp; j < S; j += nwarps) {
+      if (s_roff[j + 1] <= b0 || s_roff[j] >= b0 + nb) continue;  // no record of this set in the batch
       const size_t set = (size_t)c * S + j;
       const double wj = bw.W[j * bw.M + tgt];
       const int h = s_roff[j + 1] - s_roff[j];
       HullReader rd(out, set);
       for (int k = lane; k < h; k += 32) {
-        if (!rd.seek(k)) { s_broken = 1; s_ridx[s_roff[j] + k] = lb.NA; s_rcz[s_roff[j] + k] = 0.0; continue; }
-        s_ridx[s_roff[j] + k] = rd.idx();
-        s_rcz[s_roff[j] + k] = wj * rd.q() * invS;
+        const int e = s_roff[j] + k - b0;
+        if (e < 0 || e >= nb) continue;
+        if (!rd.seek(k)) { s_broken = 1; s_ridx[e] = lb.NA; s_rcz[e] = 0.0; continue; }
+        s_ridx[e] = rd.idx();
+        s_rcz[e] = wj * rd.q() * invS;
       }
     }
     __syncthreads();
     // first occurrence of every line through a small hash table: slot claim by compare-and-swap,
     // first record by atomicMin (order independent, hence deterministic); a quadratic scan here cost
     // 17 % of the kernel at S = 16 and made S = 256 unusable
-    for (int e = threadIdx.x; e < nrec; e += blockDim.x) {
+    for (int e = threadIdx.x; e < nb; e += blockDim.x) {
       const int idx = s_ridx[e];
       unsigned h = ((unsigned)idx * 2654435761u) >> (32 - HB);
       int probes = 0;
@@ -2619,36 +2663,39 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
       s_flag[e] = (int)h;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < nrec; e += blockDim.x) s_flag[e] = s_hfirst[s_flag[e]] == e ? 1 : 0;
+    for (int e = threadIdx.x; e < nb; e += blockDim.x) s_flag[e] = s_hfirst[s_flag[e]] == e ? 1 : 0;
     __syncthreads();
-    if (s_hovf) merged = false;  // more distinct lines than slots: the unmerged loops below
-  }
-  if (merged) {
-    for (int e = threadIdx.x; e < nrec; e += blockDim.x) {
+    if (s_hovf) { merged = false; break; }  // more distinct lines than slots (cannot happen while HN > RM): unmerged loops
+    for (int e = threadIdx.x; e < nb; e += blockDim.x) {
       if (!s_flag[e]) continue;
       const int idx = s_ridx[e];
       int rank = 0;  // distinct lines that first occur before e
       for (int f = 0; f < e; ++f) rank += s_flag[f];
       double acc = 0.0;
-      for (int f = e; f < nrec; ++f)
+      for (int f = e; f < nb; ++f)
         if (s_ridx[f] == idx) acc += s_rcz[f];
       s_uidx[rank] = idx;
       s_ucz[rank] = acc;
       atomicAdd(&s_nuniq, 1);
     }
     __syncthreads();
-  }
-  const int nuniq = merged ? s_nuniq : 0;
-
-  // r_t over this thread's training points; every thread walks the same list in order
-  for (int t = threadIdx.x; t < bw.n_pad; t += blockDim.x) {
-    double acc = 0.0;
-    if (merged) {
+    const int nuniq = s_nuniq;
+    // r_t over this thread's training points; every thread walks the same list in order
+    for (int t = threadIdx.x; t < bw.n_pad; t += blockDim.x) {
+      double acc = 0.0;
       for (int u = 0; u < nuniq; ++u) {
         const int idx = s_uidx[u];
         if (idx < lb.NA) acc += s_ucz[u] * bw.BT[(size_t)idx * bw.ldbt + t];
       }
-    } else {
+      s_r[t] += acc;
+    }
+    if (warp == 0)
+      for (int u = lane; u < nuniq; u += 32) slope_terms(s_uidx[u], s_ucz[u]);
+  }
+  if (!merged) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < bw.n_pad; t += blockDim.x) {
+      double acc = 0.0;
       for (int j = 0; j < S; ++j) {
         const size_t set = (size_t)c * S + j;
         const int h = out.hull_cnt[set];
@@ -2663,41 +2710,14 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
           }
         }
       }
+      s_r[t] = acc;
     }
-    s_r[t] = acc;
+    gsum = gzown = 0.0;
+#pragma unroll
+    for (int k = 0; k < MAX_D; ++k) gkd[k] = 0.0;
   }
   // scalars: warp 0
   if (warp == 0) {
-    double gsum = 0.0, gzown = 0.0, gkd[MAX_D], gm[MAX_M];
-#pragma unroll
-    for (int k = 0; k < MAX_D; ++k) gkd[k] = 0.0;
-#pragma unroll
-    for (int m = 0; m < MAX_M; ++m) gm[m] = 0.0;
-    double xs_t[MAX_D];
-#pragma unroll
-    for (int k = 0; k < MAX_D; ++k)
-      xs_t[k] = k < d ? bw.X[(size_t)c * d + k] / bw.ls[tgt][k] : 0.0;
-    auto slope_terms = [&](int idx, double cz) {
-      gsum += cz * zrow[idx];
-      if (idx == lb.NA) {
-        gzown += cz;
-      } else {
-        double sq = 0.0;
-#pragma unroll
-        for (int q = 0; q < MAX_D; ++q)
-          if (q < d) {
-            double df = xs_t[q] - bw.xd_s[(size_t)idx * d + q];
-            sq += df * df;
-          }
-        const double gc = stationary_grad_coeff(bw.kind[tgt], bw.outputscale[tgt], sq);
-#pragma unroll
-        for (int q = 0; q < MAX_D; ++q)
-          if (q < d)
-            gkd[q] += cz * gc * (xs_t[q] - bw.xd_s[(size_t)idx * d + q]) / bw.ls[tgt][q];
-      }
-    };
-    if (merged)
-      for (int u = lane; u < nuniq; u += 32) slope_terms(s_uidx[u], s_ucz[u]);
     for (int j = lane; j < S; j += 32) {  // lane l owns scalarisations l, l+32, ...
       const size_t set = (size_t)c * S + j;
       const int h = out.hull_cnt[set];

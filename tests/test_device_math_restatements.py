@@ -75,3 +75,31 @@ def test_reciprocal_residual_quotient_matches_division():
         assert abs(got - want) <= math.ulp(want)
         exact += got == want
     assert exact >= n - 2  # correctly rounded (Markstein), up to the rare all-ones-significand divisors
+
+
+def order_key(s):
+    """dkg_coupled.cu::order_key: high word of the double, sign-magnitude -> two's complement."""
+    hi = (np.asarray(s, dtype=np.float64).view(np.int64) >> 32).astype(np.int32)
+    return hi ^ ((hi >> 31) & np.int32(0x7FFFFFFF))
+
+
+def test_coarse_keys_are_monotone_so_the_exact_extreme_lies_in_a_segment_with_the_extreme_key():
+    """The row statistics keep only a coarse, MONOTONE image of every value per segment / tile -- the float rounding in
+    zfinish_tiled_kernel, the integer order key in coupled_range_kernel -- and re-read exactly just the segments that
+    attain the extreme image.  Monotone (non-strict) is all that needs: x <= y  =>  image(x) <= image(y)."""
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.standard_normal(20000) * np.exp(rng.standard_normal(20000) * 8),
+                        [0.0, 1e-310, -1e-310, 1e308, -1e308, np.inf, -np.inf, 1.0, np.nextafter(1.0, 2.0), -1.0, np.nextafter(-1.0, -2.0)]])
+    x = np.sort(x)
+    k = order_key(x).astype(np.int64)
+    assert np.all(k[1:] >= k[:-1])
+    with np.errstate(over="ignore"):
+        f = x.astype(np.float32)
+    assert np.all(f[1:] >= f[:-1])
+    # segments of 512 values in arbitrary order: the exact minimum / maximum sit in a segment that attains the extreme key
+    y = rng.permutation(x[np.isfinite(x)])[: 512 * 39].reshape(39, 512)
+    for image in (lambda v: order_key(v).astype(np.int64), lambda v: v.astype(np.float32)):
+        im = image(y)
+        lo_seg = np.nonzero(im.min(axis=1) == im.min())[0]
+        hi_seg = np.nonzero(im.max(axis=1) == im.max())[0]
+        assert y.min() == y[lo_seg].min() and y.max() == y[hi_seg].max()

@@ -1228,7 +1228,7 @@ static int launch_tilefilter(const LineBatch& lb, const EmaxScratch& sc, cudaStr
   // (4 pairs per warp measured best at c4: 0.62 ms vs 0.72 at 16 and 1.08 at 64 -- short items balance the
   // very uneven work per row and keep more loads in flight)
   long long ppw = (long long)lb.C * njb * ntp / (148ll * 64);
-  if (ppw > 4) ppw = 4;
+  if (ppw > 3) ppw = 3;  // (re-measured with 4 CTAs per SM and the champion probe: 0.452 / 0.288 ms at 3, 0.458 / 0.301 at 2, 0.478 / 0.305 at 4)
   if (const char* e = getenv("DKG_TF_PPW")) ppw = atoi(e);
   if (ppw < 1) ppw = 1;
   if (ppw > ntp) ppw = ntp;

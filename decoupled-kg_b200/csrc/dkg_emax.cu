@@ -1097,13 +1097,6 @@ tilefilter_kernel(LineBatch lb, EmaxScratch sc, int pairs_per_warp, int njb, int
     mm = sc.chain5f[((size_t)c * S + j_mine) * 2 + 0];
     cc = sc.chain5f[((size_t)c * S + j_mine) * 2 + 1];
   }
-  if (half == 0) {  // packed copies for the per-line tests (one broadcast LDS.128 per chord)
-    s_ch[warp][jl][0] = make_ulonglong2(pack_f32x2(mm.x, mm.x), pack_f32x2(cc.x, cc.x));
-    s_ch[warp][jl][1] = make_ulonglong2(pack_f32x2(mm.y, mm.y), pack_f32x2(cc.y, cc.y));
-    s_ch[warp][jl][2] = make_ulonglong2(pack_f32x2(mm.z, mm.z), pack_f32x2(cc.z, cc.z));
-    s_ch[warp][jl][3] = make_ulonglong2(pack_f32x2(mm.w, mm.w), pack_f32x2(cc.w, cc.w));
-  }
-  __syncwarp();
   const double* zrow = lb.Z + (size_t)c * lb.ldz;
   int2* pool = s_pool[warp];
   int wcnt = 0;
@@ -1119,6 +1112,13 @@ tilefilter_kernel(LineBatch lb, EmaxScratch sc, int pairs_per_warp, int njb, int
       am_nx = lb.A32tmax[(size_t)tile * S + j_mine];
     }
   }
+  if (half == 0) {  // packed copies for the per-line tests (one broadcast LDS.128 per chord)
+    s_ch[warp][jl][0] = make_ulonglong2(pack_f32x2(mm.x, mm.x), pack_f32x2(cc.x, cc.x));
+    s_ch[warp][jl][1] = make_ulonglong2(pack_f32x2(mm.y, mm.y), pack_f32x2(cc.y, cc.y));
+    s_ch[warp][jl][2] = make_ulonglong2(pack_f32x2(mm.z, mm.z), pack_f32x2(cc.z, cc.z));
+    s_ch[warp][jl][3] = make_ulonglong2(pack_f32x2(mm.w, mm.w), pack_f32x2(cc.w, cc.w));
+  }
+  __syncwarp();
   for (int tp = tp_lo; tp < tp_hi; ++tp) {
     const int tile = 2 * tp + half;
     const float2 zr = zr_nx;

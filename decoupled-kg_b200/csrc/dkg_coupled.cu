@@ -380,10 +380,10 @@ int coupled_slopes(const CoupledArgs& a, cudaStream_t st) {
 // most scalarisations, so per objective the B_m^T row gathers and the kernel-gradient evaluations run once
 // per distinct line with the merged coefficient Gz_m[n].  (Before: every thread walked every record of every
 // scalarisation through the spill-chain reader for every training point -- 2.05 of the 7.5 ms of a c4 step.)
-// Candidates with more records than the staging capacity take the unmerged loops.
+// Candidates with more records than the staging capacity are handled in batches of that capacity.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CP_THREADS)
-finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
+finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw, int rec_batch) {
   extern __shared__ __align__(16) unsigned char c_smem[];
   const int c = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -402,29 +402,33 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
   const double invS = 1.0 / (double)S;
   int n_pad_max = 0;
   for (int m = 0; m < M; ++m) n_pad_max = max(n_pad_max, bw.n_pad[m]);
-  double* s_r = s_term + S;                    // [n_pad_max]
-  double* s_sc = s_r + n_pad_max;              // [0] gzown, [1] Cv, [2..2+MAX_D) gkd, [2+MAX_D..) gm[m]
-  double* s_red = s_sc + 2 + MAX_D + MAX_M;    // [nwarps * MAX_D]   (sized for CP_THREADS / 32 warps)
+  constexpr int SCW = 2 + MAX_D;                 // per objective: [0] gzown, [1] Cv, [2..) gkd
+  double* s_r = s_term + S;                      // [M][n_pad_max]  r_m, accumulated over the record batches
+  double* s_sc = s_r + (size_t)M * n_pad_max;    // [M][SCW], then gm[MAX_M]
+  double* s_gm = s_sc + MAX_M * SCW;             // [MAX_M]
+  double* s_red = s_gm + MAX_M;                  // [nwarps * MAX_D]   (sized for CP_THREADS / 32 warps)
   const int RM = fin_rmax(S);
   const int HB = fin_hash_bits(S), HN = 1 << HB;
   double* s_rq = s_red + (CP_THREADS / 32) * MAX_D;  // [RM] q / S of a record
-  double* s_ucz = s_rq + RM;                   // [RM] merged coefficient Gz_m of a distinct line
-  double* s_om = s_ucz + RM;                   // [S]  om_jm of the current objective
-  double* s_qb = s_om + S;                     // [S]  sum_n (q_jn / S) b_jn
+  double* s_ucz = s_rq + RM;                     // [RM] merged coefficient Gz_m of a distinct line
+  double* s_om = s_ucz + RM;                     // [S]  om_jm of the current objective
+  double* s_qb = s_om + S;                       // [S]  sum_n (q_jn / S) b_jn
   int* s_ridx = reinterpret_cast<int*>(s_qb + S);  // [RM] record line index
-  int* s_rj = s_ridx + RM;                     // [RM] record scalarisation
-  int* s_flag = s_rj + RM;                     // [RM] hash slot, then first-occurrence flag
-  int* s_uidx = s_flag + RM;                   // [RM] distinct line index
-  int* s_ue = s_uidx + RM;                     // [RM] its first record
-  int* s_roff = s_ue + RM;                     // [S + 1] record offsets per set
-  int* s_hkey = s_roff + ((S + 2) & ~1);       // [HN]
-  int* s_hfirst = s_hkey + HN;                 // [HN]
+  int* s_rj = s_ridx + RM;                       // [RM] record scalarisation
+  int* s_flag = s_rj + RM;                       // [RM] hash slot, then first-occurrence flag
+  int* s_uidx = s_flag + RM;                     // [RM] distinct line index
+  int* s_ue = s_uidx + RM;                       // [RM] its first record
+  int* s_roff = s_ue + RM;                       // [S + 1] record offsets per set
+  int* s_hkey = s_roff + ((S + 2) & ~1);         // [HN]
+  int* s_hfirst = s_hkey + HN;                   // [HN]
   double grad[MAX_D];
 #pragma unroll
   for (int k = 0; k < MAX_D; ++k) grad[k] = 0.0;
 
-  for (int j = threadIdx.x; j < S; j += blockDim.x) s_roff[j + 1] = out.hull_cnt[(size_t)c * S + j];
+  for (int j = threadIdx.x; j < S; j += blockDim.x) { s_roff[j + 1] = out.hull_cnt[(size_t)c * S + j]; s_qb[j] = 0.0; }
   for (int h = threadIdx.x; h < HN; h += blockDim.x) { s_hkey[h] = -1; s_hfirst[h] = 0x7fffffff; }
+  for (int e = threadIdx.x; e < M * n_pad_max; e += blockDim.x) s_r[e] = 0.0;
+  for (int e = threadIdx.x; e < MAX_M * SCW; e += blockDim.x) s_sc[e] = 0.0;
   __syncthreads();
   if (threadIdx.x == 0) {
     int off = 0;
@@ -441,62 +445,6 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
   }
   __syncthreads();
   const int nrec = s_nrec;
-  bool merged = nrec <= RM;
-  if (merged) {
-    for (int j = warp; j < S; j += nwarps) {
-      const size_t set = (size_t)c * S + j;
-      const int h = s_roff[j + 1] - s_roff[j];
-      HullReader rd(out, set);
-      for (int k = lane; k < h; k += 32) {
-        const int e = s_roff[j] + k;
-        s_rj[e] = j;
-        if (!rd.seek(k)) { s_broken = 1; s_ridx[e] = NA; s_rq[e] = 0.0; continue; }
-        s_ridx[e] = rd.idx();
-        s_rq[e] = rd.q() * invS;
-      }
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < nrec; e += blockDim.x) {
-      const int idx = s_ridx[e];
-      unsigned h = ((unsigned)idx * 2654435761u) >> (32 - HB);
-      int probes = 0;
-      for (;; h = (h + 1) & (HN - 1)) {
-        const int prev = atomicCAS(&s_hkey[h], -1, idx);
-        if (prev == -1 || prev == idx) break;
-        if (++probes >= HN) { s_hovf = 1; break; }
-      }
-      atomicMin(&s_hfirst[h], e);
-      s_flag[e] = (int)h;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < nrec; e += blockDim.x) s_flag[e] = s_hfirst[s_flag[e]] == e ? 1 : 0;
-    __syncthreads();
-    if (s_hovf) merged = false;
-  }
-  if (merged) {
-    for (int e = threadIdx.x; e < nrec; e += blockDim.x) {
-      if (!s_flag[e]) continue;
-      int rank = 0;  // distinct lines that first occur before e (order = first occurrence: deterministic)
-      for (int f = 0; f < e; ++f) rank += s_flag[f];
-      s_uidx[rank] = s_ridx[e];
-      s_ue[rank] = e;
-      atomicAdd(&s_nuniq, 1);
-    }
-    // qb_j = sum_n (q_jn / S) b_jn: the same for every objective
-    for (int j = threadIdx.x; j < S; j += blockDim.x) {
-      const size_t set = (size_t)c * S + j;
-      const double sd = bw.sdj[set], rinv = 1.0 / sd;
-      double qb = 0.0;
-      for (int e = s_roff[j]; e < s_roff[j + 1]; ++e) {
-        double sacc = 0.0;  // b_jn, formed as everywhere else (line_slope)
-        for (int mm = 0; mm < M; ++mm) sacc = fma(bw.W2[j * M + mm], bw.COV[mm][(size_t)c * bw.ldz + s_ridx[e]], sacc);
-        qb += s_rq[e] * coupled_quotient(sacc, sd, rinv);
-      }
-      s_qb[j] = qb;
-    }
-  }
-  __syncthreads();
-  const int nuniq = merged ? s_nuniq : 0;
 
   // gm[m] = sum_j Ga_j W[j, m]  (own-line intercept path), computed once by warp 0
   if (warp == 0) {
@@ -519,13 +467,77 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
 #pragma unroll
     for (int m = 0; m < MAX_M; ++m) gm[m] = warp_sum(gm[m]);
     if (lane == 0)
-      for (int m = 0; m < MAX_M; ++m) s_sc[2 + MAX_D + m] = gm[m];
+      for (int m = 0; m < MAX_M; ++m) s_gm[m] = gm[m];
   }
-  __syncthreads();
 
-  for (int m = 0; m < M; ++m) {
-    const double s2 = bw.y_std[m] * bw.y_std[m];
-    if (merged) {
+  // ---- the hull records in batches of what the shared-memory tables hold (one batch unless S is large): distinct
+  // lines of the batch through the hash table, then per objective the merged coefficients, the B_m^T row gathers
+  // into r_m and the prior-covariance terms; everything accumulates over the batches ----
+  const int RB = rec_batch > 0 && rec_batch < RM ? rec_batch : RM;  // (a smaller batch only as a test hook: DKG_FIN_BATCH)
+  for (int b0 = 0; b0 < nrec; b0 += RB) {
+    const int nb = min(RB, nrec - b0);
+    __syncthreads();  // the previous batch's tables are done with (first batch: s_gm / the clears above are visible)
+    if (b0 > 0) {
+      for (int h = threadIdx.x; h < HN; h += blockDim.x) { s_hkey[h] = -1; s_hfirst[h] = 0x7fffffff; }
+      if (threadIdx.x == 0) s_nuniq = 0;
+      __syncthreads();
+    }
+    for (int j = warp; j < S; j += nwarps) {
+      if (s_roff[j + 1] <= b0 || s_roff[j] >= b0 + nb) continue;
+      const size_t set = (size_t)c * S + j;
+      const int h = s_roff[j + 1] - s_roff[j];
+      HullReader rd(out, set);
+      for (int k = lane; k < h; k += 32) {
+        const int e = s_roff[j] + k - b0;
+        if (e < 0 || e >= nb) continue;
+        s_rj[e] = j;
+        if (!rd.seek(k)) { s_broken = 1; s_ridx[e] = NA; s_rq[e] = 0.0; continue; }
+        s_ridx[e] = rd.idx();
+        s_rq[e] = rd.q() * invS;
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nb; e += blockDim.x) {
+      const int idx = s_ridx[e];
+      unsigned h = ((unsigned)idx * 2654435761u) >> (32 - HB);
+      int probes = 0;
+      for (;; h = (h + 1) & (HN - 1)) {
+        const int prev = atomicCAS(&s_hkey[h], -1, idx);
+        if (prev == -1 || prev == idx) break;
+        if (++probes >= HN) { s_hovf = 1; break; }  // (cannot happen: HN > RM)
+      }
+      atomicMin(&s_hfirst[h], e);
+      s_flag[e] = (int)h;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nb; e += blockDim.x) s_flag[e] = s_hfirst[s_flag[e]] == e ? 1 : 0;
+    __syncthreads();
+    if (s_hovf) s_broken = 1;  // fail loudly rather than silently drop lines
+    for (int e = threadIdx.x; e < nb; e += blockDim.x) {
+      if (!s_flag[e]) continue;
+      int rank = 0;  // distinct lines that first occur before e (order = first occurrence: deterministic)
+      for (int f = 0; f < e; ++f) rank += s_flag[f];
+      s_uidx[rank] = s_ridx[e];
+      s_ue[rank] = e;
+      atomicAdd(&s_nuniq, 1);
+    }
+    // qb_j = sum_n (q_jn / S) b_jn: the same for every objective; this batch's records of set j
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+      const int e_lo = max(s_roff[j], b0) - b0, e_hi = min(s_roff[j + 1], b0 + nb) - b0;
+      if (e_lo >= e_hi) continue;
+      const size_t set = (size_t)c * S + j;
+      const double sd = bw.sdj[set], rinv = 1.0 / sd;
+      double qb = 0.0;
+      for (int e = e_lo; e < e_hi; ++e) {
+        double sacc = 0.0;  // b_jn, formed as everywhere else (line_slope)
+        for (int mm = 0; mm < M; ++mm) sacc = fma(bw.W2[j * M + mm], bw.COV[mm][(size_t)c * bw.ldz + s_ridx[e]], sacc);
+        qb += s_rq[e] * coupled_quotient(sacc, sd, rinv);
+      }
+      s_qb[j] += qb;
+    }
+    __syncthreads();
+    const int nuniq = s_nuniq;
+    for (int m = 0; m < M; ++m) {
       for (int j = threadIdx.x; j < S; j += blockDim.x) {
         const double w = bw.W[j * M + m];
         s_om[j] = (w * w) / bw.sdj[(size_t)c * S + j];
@@ -534,114 +546,81 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
       for (int u = threadIdx.x; u < nuniq; u += blockDim.x) {
         const int idx = s_uidx[u];
         double acc = 0.0;
-        for (int f = s_ue[u]; f < nrec; ++f)
+        for (int f = s_ue[u]; f < nb; ++f)
           if (s_ridx[f] == idx) acc += s_om[s_rj[f]] * s_rq[f];
         s_ucz[u] = acc;
       }
       __syncthreads();
-    }
-    // r_m[t] = sum over hull records (discretisation lines) of om_jm q / S * B_m^T[idx, t]
-    for (int t = threadIdx.x; t < bw.n_pad[m]; t += blockDim.x) {
-      double acc = 0.0;
-      if (merged) {
+      // r_m[t] += sum over the distinct discretisation lines of Gz_m[n] * B_m^T[n, t]
+      double* rm = s_r + (size_t)m * n_pad_max;
+      for (int t = threadIdx.x; t < bw.n_pad[m]; t += blockDim.x) {
+        double acc = 0.0;
         for (int u = 0; u < nuniq; ++u) {
           const int idx = s_uidx[u];
           if (idx < NA) acc += s_ucz[u] * bw.BT[m][(size_t)idx * bw.ldbt[m] + t];
         }
-      } else {
-        for (int j = 0; j < S; ++j) {
-          const size_t set = (size_t)c * S + j;
-          const int h = out.hull_cnt[set];
-          const double w = bw.W[j * M + m];
-          const double om = (w * w) / bw.sdj[set];
-          HullReader rd(out, set);
-          for (int k = 0; k < h; ++k) {
-            if (!rd.seek(k)) { s_broken = 1; break; }
-            const int idx = rd.idx();
-            if (idx < NA) acc += om * rd.q() * invS * bw.BT[m][(size_t)idx * bw.ldbt[m] + t];
+        rm[t] += acc;
+      }
+      if (warp == 0) {  // prior-covariance path of the distinct lines with their coefficient Gz_m[n]
+        double gzown = 0.0, gkd[MAX_D];
+#pragma unroll
+        for (int k = 0; k < MAX_D; ++k) gkd[k] = 0.0;
+        double xm[MAX_D];
+#pragma unroll
+        for (int k = 0; k < MAX_D; ++k) xm[k] = k < d ? bw.X[(size_t)c * d + k] / bw.ls[m][k] : 0.0;
+        for (int u = lane; u < nuniq; u += 32) {
+          const int idx = s_uidx[u];
+          const double cz = s_ucz[u];
+          if (idx == NA) {
+            gzown += cz;
+          } else {
+            double sq = 0.0;
+#pragma unroll
+            for (int q = 0; q < MAX_D; ++q)
+              if (q < d) {
+                const double df = xm[q] - bw.xd_s[m][(size_t)idx * d + q];
+                sq += df * df;
+              }
+            const double gc = stationary_grad_coeff(bw.kind[m], bw.outputscale[m], sq);
+#pragma unroll
+            for (int q = 0; q < MAX_D; ++q)
+              if (q < d) gkd[q] += cz * gc * (xm[q] - bw.xd_s[m][(size_t)idx * d + q]) / bw.ls[m][q];
           }
         }
+        gzown = warp_sum(gzown);
+#pragma unroll
+        for (int k = 0; k < MAX_D; ++k) gkd[k] = warp_sum(gkd[k]);
+        if (lane == 0) {
+          s_sc[m * SCW + 0] += gzown;
+          for (int k = 0; k < MAX_D; ++k) s_sc[m * SCW + 2 + k] += gkd[k];
+        }
       }
-      s_r[t] = acc;
+      __syncthreads();  // s_om / s_ucz are reused by the next objective
     }
-    if (warp == 0) {
-      double gzown = 0.0, cv = 0.0, gkd[MAX_D];
-#pragma unroll
-      for (int k = 0; k < MAX_D; ++k) gkd[k] = 0.0;
-      double xm[MAX_D];
-#pragma unroll
-      for (int k = 0; k < MAX_D; ++k) xm[k] = k < d ? bw.X[(size_t)c * d + k] / bw.ls[m][k] : 0.0;
-      // prior-covariance path of one line with coefficient cz = Gz_m[n] (or one record's share of it)
-      auto line_terms = [&](int idx, double cz) {
-        if (idx == NA) {
-          gzown += cz;
-        } else {
-          double sq = 0.0;
-#pragma unroll
-          for (int q = 0; q < MAX_D; ++q)
-            if (q < d) {
-              const double df = xm[q] - bw.xd_s[m][(size_t)idx * d + q];
-              sq += df * df;
-            }
-          const double gc = stationary_grad_coeff(bw.kind[m], bw.outputscale[m], sq);
-#pragma unroll
-          for (int q = 0; q < MAX_D; ++q)
-            if (q < d) gkd[q] += cz * gc * (xm[q] - bw.xd_s[m][(size_t)idx * d + q]) / bw.ls[m][q];
-        }
-      };
-      if (merged) {
-        for (int u = lane; u < nuniq; u += 32) line_terms(s_uidx[u], s_ucz[u]);
-        for (int j = lane; j < S; j += 32) {
-          const double w = bw.W[j * M + m];
-          const double sd = bw.sdj[(size_t)c * S + j];
-          cv -= (w * w) / (2.0 * sd * sd) * s_qb[j];
-        }
-      } else {
-        for (int j = lane; j < S; j += 32) {
-          const size_t set = (size_t)c * S + j;
-          const int h = out.hull_cnt[set];
-          const double w = bw.W[j * M + m];
-          const double sd = bw.sdj[set];
-          const double om = (w * w) / sd;
-          double w2j[MAX_M];
-#pragma unroll
-          for (int mm = 0; mm < MAX_M; ++mm) w2j[mm] = mm < M ? bw.W2[j * M + mm] : 0.0;
-          const double rinv = 1.0 / sd;
-          auto slope = [&](int n) {  // b_jn, formed as everywhere else (line_slope)
-            double sacc = 0.0;
-            for (int mm = 0; mm < M; ++mm) sacc = fma(w2j[mm], bw.COV[mm][(size_t)c * bw.ldz + n], sacc);
-            return coupled_quotient(sacc, sd, rinv);
-          };
-          double qb = 0.0;  // sum_n (q / S) b_jn
-          HullReader rd(out, set);
-          for (int k = 0; k < h; ++k) {
-            if (!rd.seek(k)) { s_broken = 1; break; }
-            const int idx = rd.idx();
-            const double qs = rd.q() * invS;
-            qb += qs * slope(idx);
-            line_terms(idx, om * qs);
-          }
-          cv -= (w * w) / (2.0 * sd * sd) * qb;
-        }
+  }
+  __syncthreads();
+
+  for (int m = 0; m < M; ++m) {
+    const double s2 = bw.y_std[m] * bw.y_std[m];
+    if (warp == 0) {  // Cv_m from the complete qb_j
+      double cv = 0.0;
+      for (int j = lane; j < S; j += 32) {
+        const double w = bw.W[j * M + m];
+        const double sd = bw.sdj[(size_t)c * S + j];
+        cv -= (w * w) / (2.0 * sd * sd) * s_qb[j];
       }
-      gzown = warp_sum(gzown);
       cv = warp_sum(cv);
-#pragma unroll
-      for (int k = 0; k < MAX_D; ++k) gkd[k] = warp_sum(gkd[k]);
-      if (lane == 0) {
-        s_sc[0] = gzown;
-        s_sc[1] = cv;
-        for (int k = 0; k < MAX_D; ++k) s_sc[2 + k] = gkd[k];
-      }
+      if (lane == 0) s_sc[m * SCW + 1] = cv;
     }
     __syncthreads();
-    const double cT = -2.0 * s2 * (s_sc[0] + s_sc[1]);
-    const double cm = s_sc[2 + MAX_D + m] * bw.y_std[m];
+    const double* rm = s_r + (size_t)m * n_pad_max;
+    const double cT = -2.0 * s2 * (s_sc[m * SCW + 0] + s_sc[m * SCW + 1]);
+    const double cm = s_gm[m] * bw.y_std[m];
     double xm[MAX_D];
 #pragma unroll
     for (int k = 0; k < MAX_D; ++k) xm[k] = k < d ? bw.X[(size_t)c * d + k] / bw.ls[m][k] : 0.0;
     for (int t = threadIdx.x; t < bw.ntr[m]; t += blockDim.x) {
-      const double u = cm * bw.alpha[m][t] - s2 * s_r[t] + cT * bw.T[m][(size_t)c * bw.ldk[m] + t];
+      const double u = cm * bw.alpha[m][t] - s2 * rm[t] + cT * bw.T[m][(size_t)c * bw.ldk[m] + t];
       double sq = 0.0;
 #pragma unroll
       for (int k = 0; k < MAX_D; ++k)
@@ -655,8 +634,7 @@ finalize_coupled_kernel(int S, EmaxOut out, CoupledBackward bw) {
         if (k < d) grad[k] += gc * (xm[k] - bw.xs[m][(size_t)t * d + k]) / bw.ls[m][k];
     }
     if (threadIdx.x == 0)
-      for (int k = 0; k < MAX_D; ++k) grad[k] += s2 * s_sc[2 + k];  // prior-covariance term, once
-    __syncthreads();  // s_r / s_sc / s_om / s_ucz are reused by the next objective
+      for (int k = 0; k < MAX_D; ++k) grad[k] += s2 * s_sc[m * SCW + 2 + k];  // prior-covariance term, once
   }
 #pragma unroll
   for (int k = 0; k < MAX_D; ++k) grad[k] = warp_sum(grad[k]);
@@ -677,11 +655,13 @@ int emax_finalize_coupled(int C, int S, const EmaxOut& out, const CoupledBackwar
   for (int m = 0; m < bw.M; ++m) n_pad_max = n_pad_max > bw.n_pad[m] ? n_pad_max : bw.n_pad[m];
   size_t smem = sizeof(double) * S;
   if (bw.dX != nullptr)
-    smem = sizeof(double) * ((size_t)S + n_pad_max + 2 + MAX_D + MAX_M + (CP_THREADS / 32) * MAX_D + 2 * fin_rmax(S) + 2 * S) +
+    smem = sizeof(double) * ((size_t)S + (size_t)bw.M * n_pad_max + (size_t)MAX_M * (2 + MAX_D) + MAX_M +
+                             (CP_THREADS / 32) * MAX_D + 2 * fin_rmax(S) + 2 * S) +
            sizeof(int) * ((size_t)5 * fin_rmax(S) + ((S + 2) & ~1) + (2 << fin_hash_bits(S)));
   if (smem > 47 * 1024)
     DKG_CUDA_OK(cudaFuncSetAttribute(finalize_coupled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  finalize_coupled_kernel<<<C, CP_THREADS / 2, smem, st>>>(S, out, bw);  // short barrier-separated phases: more CTAs per SM
+  const char* fbe = getenv("DKG_FIN_BATCH");  // test hook: hull records merged per batch (default: the table capacity)
+  finalize_coupled_kernel<<<C, CP_THREADS / 2, smem, st>>>(S, out, bw, fbe != nullptr ? atoi(fbe) : 0);  // short barrier-separated phases: more CTAs per SM
   DKG_LAUNCH_CHECK();
   return DKG_OK;
 }

@@ -2527,7 +2527,7 @@ int emax_overflow(const LineBatch& lb, const EmaxScratch& sc, const EmaxOut& out
 // code - and the instruction-cache misses - at d = 4)
 template <int D>
 __global__ void __launch_bounds__(E_THREADS, 3)
-finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
+finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw, int rec_batch) {
   extern __shared__ __align__(16) unsigned char e_smem[];
   const int c = blockIdx.x;
   const int lane = threadIdx.x & 31;
@@ -2624,8 +2624,9 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw) {
           gkd[q] += cz * gc * (xs_t[q] - bw.xd_s[(size_t)idx * d + q]) / bw.ls[tgt][q];
     }
   };
-  for (int b0 = 0; b0 < nrec && merged; b0 += RM) {
-    const int nb = min(RM, nrec - b0);  // records b0 .. b0 + nb of the candidate (set-major order)
+  const int RB = rec_batch > 0 && rec_batch < RM ? rec_batch : RM;  // (a smaller batch only as a test hook: DKG_FIN_BATCH)
+  for (int b0 = 0; b0 < nrec && merged; b0 += RB) {
+    const int nb = min(RB, nrec - b0);  // records b0 .. b0 + nb of the candidate (set-major order)
     if (b0 > 0) {
       __syncthreads();  // the previous batch's tables are done with
       for (int h = threadIdx.x; h < HN; h += blockDim.x) { s_hkey[h] = -1; s_hfirst[h] = 0x7fffffff; }
@@ -2803,12 +2804,14 @@ int emax_finalize(const LineBatch& lb, const EmaxOut& out, const BackwardArgs& b
   // 128-thread CTAs (6 per SM) hide the short barrier-separated phases best; with many scalarisations
   // the hull records exceed the merge capacity and the per-record loops want the wider CTA
   const int fin_default = lb.S > 32 ? 256 : 128;
+  const char* fbe = getenv("DKG_FIN_BATCH");  // test hook: hull records merged per batch (default: the table capacity)
+  const int rec_batch = fbe != nullptr ? atoi(fbe) : 0;
   const int fin_threads = fte != nullptr && (atoi(fte) == 256 || atoi(fte) == 128 || atoi(fte) == 64) ? atoi(fte) : fin_default;
 #define DKG_FINALIZE(DD)                                                                                       \
   do {                                                                                                         \
     if (smem > 47 * 1024)                                                                                      \
       DKG_CUDA_OK(cudaFuncSetAttribute(finalize_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    finalize_kernel<DD><<<lb.C, fin_threads, smem, st>>>(lb, out, bw);                                         \
+    finalize_kernel<DD><<<lb.C, fin_threads, smem, st>>>(lb, out, bw, rec_batch);                              \
   } while (0)
   switch (bw.dX != nullptr ? bw.d : 1) {
     case 1: DKG_FINALIZE(1); break;

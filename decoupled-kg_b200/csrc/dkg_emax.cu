@@ -2596,6 +2596,7 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw, int rec_batch) {
   // batches (one batch -- every S <= 64 case -- adds to zero: the same bits as before).
   bool merged = true;
   for (int t = threadIdx.x; t < bw.n_pad; t += blockDim.x) s_r[t] = 0.0;
+  for (int j = threadIdx.x; j < S; j += blockDim.x) s_ga[j] = 0.0;  // p / S of the set's own-line record, filled while staging
   double gsum = 0.0, gzown = 0.0, gkd[MAX_D], gm[MAX_M];  // (warp 0)
 #pragma unroll
   for (int k = 0; k < MAX_D; ++k) gkd[k] = 0.0;
@@ -2643,8 +2644,10 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw, int rec_batch) {
         const int e = s_roff[j] + k - b0;
         if (e < 0 || e >= nb) continue;
         if (!rd.seek(k)) { s_broken = 1; s_ridx[e] = lb.NA; s_rcz[e] = 0.0; continue; }
-        s_ridx[e] = rd.idx();
+        const int idx = rd.idx();
+        s_ridx[e] = idx;
         s_rcz[e] = wj * rd.q() * invS;
+        if (idx == lb.NA) s_ga[j] = rd.p() * invS;  // (a line is a hull vertex of its set at most once)
       }
     }
     __syncthreads();
@@ -2721,15 +2724,19 @@ finalize_kernel(LineBatch lb, EmaxOut out, BackwardArgs bw, int rec_batch) {
   if (warp == 0) {
     for (int j = lane; j < S; j += 32) {  // lane l owns scalarisations l, l+32, ...
       const size_t set = (size_t)c * S + j;
-      const int h = out.hull_cnt[set];
-      const double wj = bw.W[j * bw.M + tgt];
       double ga = out.amax_is_own[set] ? -invS : 0.0;
-      HullReader rd(out, set);
-      for (int k = 0; k < h; ++k) {
-        if (!rd.seek(k)) { s_broken = 1; break; }
-        const int idx = rd.idx();
-        if (idx == lb.NA) ga += rd.p() * invS;
-        if (!merged) slope_terms(idx, wj * rd.q() * invS);
+      if (merged) {
+        ga += s_ga[j];  // (staged with the records: no dependent walk over the set's records on the critical path)
+      } else {
+        const int h = out.hull_cnt[set];
+        const double wj = bw.W[j * bw.M + tgt];
+        HullReader rd(out, set);
+        for (int k = 0; k < h; ++k) {
+          if (!rd.seek(k)) { s_broken = 1; break; }
+          const int idx = rd.idx();
+          if (idx == lb.NA) ga += rd.p() * invS;
+          slope_terms(idx, wj * rd.q() * invS);
+        }
       }
       s_ga[j] = ga;
 #pragma unroll

@@ -91,7 +91,7 @@ DKG_API const char* dkg_last_error(void);
  */
 #define DKG_PLAN_DEFAULT 0u
 /* Reduced-precision mode: the covariance contraction (the O(C n N) term) keeps 4 base-256 digits per
- * operand (10 int8 digit products instead of 34), i.e. ~2^-31 of every row's scale -- float32-class
+ * operand (10 int8 digit products instead of 28), i.e. ~2^-31 of every row's scale -- float32-class
  * accuracy for that term, everything else stays float64.  Stated tolerance of the KG values in
  * this mode: |dKG| <= 1e-4 |KG| + 1e-7 max|intercept| (tests/test_gpu_fast_mode.py). */
 #define DKG_PLAN_FAST32 1u

@@ -129,9 +129,21 @@ static int ensure_workspace(dkg_plan* p, int C) {
   const int cap = round_up(C, GEMM_BM);
   const bool coupled = p->target < 0;
   // Candidates are processed in chunks that bound the scratch memory (slope rows + survivor
-  // lists).  DKG_CHUNK_MB (default 6144) is the budget for both; at c4 shapes it covers all 4096
-  // candidates in one chunk (0.5 GB of slope rows + 1.6 GB of survivor lists).
+  // lists).  The budget for both is a quarter of the memory that is free now, at least 6 GB and at most 32 GB
+  // (DKG_CHUNK_MB overrides): at c4 shapes 3.8 GB cover all 4096 candidates in one chunk either way; with many
+  // scalarisations (c5: S = 256, 12.7 MB per candidate) a 6 GB budget meant chunks of 384 candidates -- launches of
+  // 2.6 waves of tiles, the last chunk below the size the tile-first filter needs -- and 8.5 instead of 5.9 ms for
+  // 2048 candidates.  B200 has 180 GB; the chunks are for whatever does not fit, not a habit.
   double chunk_mb = 6144.0;
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      const double quarter = (double)free_b / 1048576.0 / 4.0;
+      if (quarter > chunk_mb) chunk_mb = quarter < 32768.0 ? quarter : 32768.0;
+    } else {
+      cudaGetLastError();
+    }
+  }
   if (const char* e = getenv("DKG_CHUNK_MB")) chunk_mb = atof(e);
   double per_row = (double)p->ldz * sizeof(double) +
                    (double)p->S * (SURV_CAP * sizeof(SurvEntry) + HULL_CAP * 20.0 + 64.0);
@@ -140,6 +152,10 @@ static int ensure_workspace(dkg_plan* p, int C) {
   int chunk = (int)(rows / GEMM_BM) * GEMM_BM;
   if (chunk < GEMM_BM) chunk = GEMM_BM;
   if (chunk > cap) chunk = cap;
+  if (chunk < cap) {  // equal chunks: the same number of launches, no small remainder chunk
+    const int nch = ceil_div(cap, chunk);
+    chunk = round_up(ceil_div(cap, nch), GEMM_BM);
+  }
   const size_t S = p->S;
   DKG_TRY(dev_alloc(&w.X, (size_t)cap * p->d));
   DKG_TRY(dev_alloc(&w.kg, (size_t)cap));
